@@ -1,0 +1,25 @@
+"""
+gc_slam_b200 -- B200 (sm_100a) implementation of GC-SLAM v2's per-scan LiDAR evidence path.
+
+Layout
+  csrc/          CUDA kernels + the C-ABI (include/gcs_b200.h) -> lib/libgcs_b200.so
+  _lib.py        ctypes binding of the C-ABI (raises if the library is missing: no CPU fallback)
+  certs.py       CertBundle / ExpectedEffect contract types (same field names as the reference)
+  constants.py   budgets and epsilons of the path
+  operators.py   bin family: point_budget_resample, deskew_constant_twist, bin_soft_assign, ...
+  primitives.py  primitive family: extract_lidar_surfels, associate_primitives_ot, map update, ...
+  synth.py       seeded synthetic scans / maps
+Sub-modules are imported on demand so that ``import gc_slam_b200`` itself never touches CUDA.
+"""
+
+__version__ = "0.1.0"
+
+_LAZY = ("constants", "certs", "synth", "_lib", "operators", "primitives", "manifest", "sharding", "build")
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        import importlib
+
+        return importlib.import_module(f"{__name__}.{name}")
+    raise AttributeError(name)

@@ -1,0 +1,130 @@
+"""
+Seeded synthetic inputs for the LiDAR evidence path.  Host-side NumPy only;
+used by tests/, bench.py and __graft_entry__.smoke().  No reference code is involved: the scene is a
+20 x 8 x 3 m room with two pillars, sampled in VLP-16 firing order.
+
+Sensor conventions mirrored from the reference:
+  * range weights: fl/backend/backend_node.py:449-459 (sigmoid window 0.5 m .. 50 m, sigma 0.25, floor 1e-12)
+  * extrinsic T_base_lidar: config/gc_unified.yaml:18-24 ([t, rotvec])
+  * per-point stamps over a 0.1 s sweep: docs/KIMERA_DATASET_AND_PIPELINE.md:49,212
+  * epoch time base 1.6657729e9: config/time_alignment/kimera_10_14_acl_jackal_005.yaml:4
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import constants as C
+
+T_BASE_LIDAR = np.array([-0.065447, -0.100474, 0.108987, -0.002723, -0.069383, 0.028979])
+EPOCH_T0 = 1.6657729e9
+SCAN_PERIOD = 0.1
+
+
+def rotvec_to_matrix(r):
+    r = np.asarray(r, dtype=np.float64)
+    th = np.linalg.norm(r)
+    K = np.array([[0, -r[2], r[1]], [r[2], 0, -r[0]], [-r[1], r[0], 0]])
+    if th < 1e-12:
+        return np.eye(3) + K
+    return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th**2 * (K @ K)
+
+
+def _ray_room(u, o):
+    """Distance along unit rays u (N,3) from o (3,) to the room box + two pillars."""
+    lo = np.array([-10.0, -4.0, -0.6])
+    hi = np.array([10.0, 4.0, 2.4])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t_lo = (lo[None, :] - o[None, :]) / u
+        t_hi = (hi[None, :] - o[None, :]) / u
+    t_exit = np.where(u > 0, t_hi, t_lo)
+    t_exit = np.where(np.abs(u) < 1e-12, np.inf, t_exit)
+    r = np.min(t_exit, axis=1)
+    for cx, cy, rad in ((3.0, 1.5, 0.3), (-4.0, -2.0, 0.4)):
+        ox, oy = o[0] - cx, o[1] - cy
+        a = u[:, 0] ** 2 + u[:, 1] ** 2
+        b = 2 * (ox * u[:, 0] + oy * u[:, 1])
+        c = ox * ox + oy * oy - rad * rad
+        disc = b * b - 4 * a * c
+        ok = (disc > 0) & (a > 1e-12)
+        sq = np.sqrt(np.where(ok, disc, 0.0))
+        t_c = np.where(ok, (-b - sq) / (2 * np.where(ok, a, 1.0)), np.inf)
+        t_c = np.where(t_c > 0, t_c, np.inf)
+        r = np.minimum(r, t_c)
+    return r
+
+
+def vlp16_scan(n_points: int, seed: int, t0: float = EPOCH_T0, sensor_xy=(0.0, 0.0)):
+    """
+    One synthetic VLP-16-shaped scan, already in the base frame.
+    Returns (points (N,3) f64, stamps (N,) f64, weights (N,) f64, ring (N,) u8, tag (N,) u8).
+    """
+    rng = np.random.default_rng(seed)
+    i = np.arange(n_points)
+    ring = (i % 16).astype(np.uint8)
+    n_cols = max(1, (n_points + 15) // 16)
+    az = 2.0 * np.pi * (i // 16) / n_cols
+    el = np.deg2rad(-15.0 + 2.0 * ring.astype(np.float64))
+    u = np.stack([np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el)], axis=1)
+    o = np.array([sensor_xy[0], sensor_xy[1], 0.0])
+    rng_m = _ray_room(u, o) + rng.normal(0.0, 0.02, size=n_points)
+    rng_m = np.clip(rng_m, 0.5, 50.0)
+    p_lidar = u * rng_m[:, None]
+    dist = np.linalg.norm(p_lidar, axis=1)
+    a = (dist - C.GC_RANGE_WEIGHT_MIN_R) / C.GC_RANGE_WEIGHT_SIGMA
+    b = (C.GC_RANGE_WEIGHT_MAX_R - dist) / C.GC_RANGE_WEIGHT_SIGMA
+    w = (1.0 / (1.0 + np.exp(-a))) * (1.0 / (1.0 + np.exp(-b)))
+    w = w * (1.0 - C.GC_WEIGHT_FLOOR) + C.GC_WEIGHT_FLOOR
+    R = rotvec_to_matrix(T_BASE_LIDAR[3:])
+    p_base = p_lidar @ R.T + T_BASE_LIDAR[None, :3]
+    t = t0 + SCAN_PERIOD * i / float(n_points)
+    return (np.ascontiguousarray(p_base), t.astype(np.float64), w.astype(np.float64), ring,
+            np.zeros(n_points, np.uint8))
+
+
+def scan_twist(seed: int):
+    """xi_body = [rho ~ U(-0.1,0.1)^3 m, phi ~ U(-0.05,0.05)^3 rad] (IMU-twist stand-in)."""
+    rng = np.random.default_rng(seed)
+    return np.concatenate([rng.uniform(-0.1, 0.1, 3), rng.uniform(-0.05, 0.05, 3)])
+
+
+def hypothesis_poses(n_hyp: int, seed: int = 42):
+    """H poses [t(3), rotvec(3)] = N(0, diag(0.05 m, 0.02 rad)) about the origin."""
+    rng = np.random.default_rng(seed)
+    return np.concatenate([rng.normal(0, 0.05, (n_hyp, 3)), rng.normal(0, 0.02, (n_hyp, 3))], axis=1)
+
+
+def lidar_origin_base():
+    return T_BASE_LIDAR[:3].copy()
+
+
+def fibonacci_atlas(n_bins: int = C.GC_B_BINS):
+    """48 quasi-uniform unit directions; same closed form as archive/bin_atlas.py:40-75."""
+    i = np.arange(n_bins, dtype=np.float64) + 0.5
+    phi = np.arccos(1 - 2 * i / n_bins)
+    theta = np.pi * (1 + np.sqrt(5)) * i
+    d = np.stack([np.sin(phi) * np.cos(theta), np.sin(phi) * np.sin(theta), np.cos(phi)], axis=1)
+    return d / (np.linalg.norm(d, axis=1, keepdims=True) + C.GC_EPS_MASS)
+
+
+def random_map_bin_stats(n_bins: int, seed: int, bin_dirs=None):
+    """
+    Plausible additive map-side bin statistics (archive/bin_atlas.py:83-105 layout) without running any
+    operator: per bin a vMF-ish cloud of directions about the bin axis and a Gaussian cloud of positions.
+    """
+    rng = np.random.default_rng(seed)
+    dirs = fibonacci_atlas(n_bins) if bin_dirs is None else np.asarray(bin_dirs)
+    S_dir = np.zeros((n_bins, 3)); S_sc = np.zeros((n_bins, 3, 3)); N = np.zeros(n_bins)
+    sum_p = np.zeros((n_bins, 3)); sum_pp = np.zeros((n_bins, 3, 3))
+    for b in range(n_bins):
+        m = 64
+        w = rng.gamma(2.0, 1.0, m)
+        u = dirs[b][None, :] + 0.25 * rng.normal(size=(m, 3))
+        u /= np.linalg.norm(u, axis=1, keepdims=True)
+        p = u * rng.uniform(2.0, 12.0, (m, 1))
+        N[b] = w.sum()
+        S_dir[b] = (w[:, None] * u).sum(0)
+        S_sc[b] = np.einsum("n,ni,nj->ij", w, u, u)
+        sum_p[b] = (w[:, None] * p).sum(0)
+        sum_pp[b] = np.einsum("n,ni,nj->ij", w, p, p)
+    return dict(S_dir=S_dir, S_dir_scatter=S_sc, N_dir=N, N_pos=N.copy(), sum_p=sum_p, sum_ppT=sum_pp)
