@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""
+bench.py -- LiDAR evidence path throughput on B200 (contract in the task statement, tier section 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scans S] [--points P]
+                    [--precision f64|mixed]
+
+Workload (N=1, BASELINE.json metric "LiDAR evidence path scans/s ... @65k pts"): the full bin-family path
+(PointBudgetResample -> DeskewConstantTwist -> ray directions -> BinSoftAssign -> ScanBinMomentMatch+kappa ->
+MatrixFisherRotation -> PlanarTranslationEvidence -> 22-D LiDAR evidence) over a batch of S synthetic
+VLP-16-shaped scans of 65,536 points each (n_points_cap = 65,536, stride 1), one hypothesis per scan,
+48-bin Fibonacci atlas, tau = 0.1, deskewed points + weights materialised (contract output).  A "step" is one
+pass of that path over the batch.  The batch (S x 2.75 MB in, S x 2.1 MB out) is larger than the 126 MB L2.
+
+  value   whole-job scans/s with the batch resident in HBM (CUDA events, max over ranks)
+  e2e     the same through the public Python plugin API with HOST buffers: pinned host -> device copy of every raw
+          scan and device -> host read of the 22-D evidence + certificates inside the timed region
+  roofline  bin_scan_kernel: algorithmic bytes (42*n_raw + 32*cap per scan) / its CUDA-event duration,
+          against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the NumPy oracle (restatement of the reference's CPU path) on a bounded sample, rank 0 only
+
+--impl reference times that CPU path on all host cores (one process per core) with the same metric/config.
+For N > 1 (torchrun) scans are sharded across ranks with no data-path collective ("scaling": "weak").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_BINS = 48
+TAU = 0.1
+BYTES_IN_PER_PT = 42   # 3+1+1 float64 + ring + tag   
+BYTES_OUT_PER_PT = 32  # deskewed point (3 f64) + weight
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(n_scans, n_points, seed0):
+    """Synthetic batch on the host (seeded; scans differ by sensor position, noise seed and twist)."""
+    from gc_slam_b200 import synth
+    pts = np.empty((n_scans, n_points, 3)); t = np.empty((n_scans, n_points)); w = np.empty((n_scans, n_points))
+    ring = np.empty((n_scans, n_points), np.uint8); tag = np.zeros((n_scans, n_points), np.uint8)
+    t0 = np.empty(n_scans); xi = np.empty((n_scans, 6))
+    n_unique = min(n_scans, 8)  # generating 65k-point scans costs ~20 ms each; tile 8 distinct scans
+    for s in range(n_unique):
+        rng = np.random.default_rng(seed0 + s)
+        p, tt, ww, rg, _ = synth.vlp16_scan(n_points, seed0 + s, t0=synth.EPOCH_T0 + 0.1 * s,
+                                            sensor_xy=tuple(rng.uniform(-2, 2, 2)))
+        pts[s], t[s], w[s], ring[s] = p, tt, ww, rg
+        t0[s] = synth.EPOCH_T0 + 0.1 * s
+        xi[s] = synth.scan_twist(seed0 + s)
+    for s in range(n_unique, n_scans):
+        k = s % n_unique
+        pts[s], t[s], w[s], ring[s], t0[s] = pts[k], t[k], w[k], ring[k], t0[k]
+        xi[s] = synth.scan_twist(seed0 + s)
+    poses = synth.hypothesis_poses(n_scans, 42)
+    return dict(pts=pts, t=t, w=w, ring=ring, tag=tag, t0=t0, t1=t0 + 0.1, xi=xi, poses=poses)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (NumPy restatement of the reference's CPU path)
+# ----------------------------------------------------------------------------------------------------------
+def _cpu_one_scan(args):
+    seed, n_points = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from gc_slam_b200 import synth
+    from oracle import bin_path as ob
+    from oracle import lie
+    p, tt, ww, rg, tg = synth.vlp16_scan(n_points, seed, t0=synth.EPOCH_T0)
+    bins = synth.fibonacci_atlas(N_BINS)
+    ms = synth.random_map_bin_stats(N_BINS, 7, bins)
+    pose = synth.hypothesis_poses(1, seed)[0]
+    t_start = time.perf_counter()
+    ob.lidar_evidence_bins(p, tt, ww, rg, tg, n_points, synth.scan_twist(seed), synth.EPOCH_T0, synth.EPOCH_T0 + 0.1,
+                           synth.lidar_origin_base(), bins, TAU, ms, lie.so3_exp(pose[3:]), pose[:3])
+    return time.perf_counter() - t_start
+
+
+def cpu_baseline_single(n_points, n_sample=3):
+    """Oracle on this process only (threads = whatever BLAS uses; reported)."""
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([int(i.get("num_threads", 1)) for i in threadpool_info()] or [1])
+    except Exception:
+        threads = 1
+    _cpu_one_scan((999, min(n_points, 4096)))  # warm imports
+    dts = [_cpu_one_scan((1000 + i, n_points)) for i in range(n_sample)]
+    return {"value": 1.0 / float(np.median(dts)), "unit": "scans/s", "cores": threads, "kind": "port",
+            "sample": f"{n_sample} scans x {n_points} points, full bin path, NumPy oracle in-process (median)"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the CPU path on all host cores, one single-threaded process per core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
+    n_points = args.points
+    per_step = cores  # bounded sample: one scan per core per step
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        for _ in range(max(1, min(args.warmup, 1))):
+            pool.map(_cpu_one_scan, [(900 + i, n_points) for i in range(per_step)])
+        t_start = time.perf_counter()
+        for k in range(args.steps):
+            pool.map(_cpu_one_scan, [(2000 + k * per_step + i, n_points) for i in range(per_step)])
+        dt = time.perf_counter() - t_start
+    value = args.steps * per_step / dt
+    line = {
+        "impl": "reference", "metric": "lidar_evidence_path_scans_per_s", "value": value, "unit": "scans/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, per_step),
+        "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_step} scans x {n_points} points per step, one process per host core"},
+        "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, scans_per_step):
+    return {"workload": f"bin-family LiDAR evidence path (resample+deskew+soft-assign+moments+kappa+MatrixFisher+"
+                        f"planar-translation+22D), batch of {scans_per_step} synthetic VLP-16-shaped scans x "
+                        f"{args.points} points, cap {args.points} (stride 1), 1 hypothesis/scan, {N_BINS} bins, tau {TAU}",
+            "points_per_scan": args.points, "scans_per_step_per_gpu": scans_per_step, "n_bins": N_BINS, "tau": TAU,
+            "precision": args.precision, "l2_policy": "inputs larger than L2 (batch in+out > 126 MB)",
+            "partition": "scans sharded across ranks, no collective"}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gc_slam_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from gc_slam_b200 import _lib as L
+    from gc_slam_b200 import operators as ops
+    from gc_slam_b200 import synth
+
+    S, P = args.scans, args.points
+    prec = L.PREC_F64 if args.precision == "f64" else L.PREC_MIXED
+    batch = make_batch(S, P, 1000 + 100 * rank)
+    plan = ops.BinPathPlan(S, P, P, n_hyp=1, n_bins=N_BINS, tau=TAU, origin=synth.lidar_origin_base(), precision=prec,
+                           want_evidence=True, materialize_deskewed=True)
+    bins = synth.fibonacci_atlas(N_BINS)
+    plan.set_bins(bins, TAU)
+    plan.set_map(synth.random_map_bin_stats(N_BINS, 7, bins))
+    # pinned host staging (the e2e leg copies from these every step)
+    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in batch.items()}
+    h2d_bytes = plan.upload(host["pts"], host["t"], host["w"], host["ring"], host["tag"], host["t0"], host["t1"],
+                            host["xi"], host["poses"])
+    torch.cuda.synchronize()
+    ctx = plan.io.ctx
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        plan.run()
+    barrier()
+    ctx.timing_enable(True)
+    launches0 = ctx.launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        plan.run()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launches - launches0
+    k_ms, k_n = ctx.timing_collect()
+    ctx.timing_enable(False)
+    t_max = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    ms_total = float(t_max.item())
+    value = world * S * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the plugin API with host buffers ------------------------------------------
+    out_host = torch.empty(S * (L.BC_NCERT + 22 * 22 + 22), dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        plan.upload(host["pts"], host["t"], host["w"], host["ring"], host["tag"], host["t0"], host["t1"], host["xi"],
+                    host["poses"])
+        plan.run()
+        o = plan.outputs()
+        out_host.copy_(torch.cat([o.cert.reshape(-1), o.L22.reshape(-1), o.h22.reshape(-1)]), non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e_steps = max(2, min(args.steps, 10))
+    ev0.record()
+    for _ in range(e_steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    e_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * S * e_steps / (float(e_ms.item()) * 1e-3)
+    d2h_bytes = out_host.numel() * 8
+
+    # ---- single-scan latency (p50) through the same API, host buffers in, evidence out ----------------
+    lat = None
+    if rank == 0:
+        p1 = ops.BinPathPlan(1, P, P, n_hyp=1, n_bins=N_BINS, tau=TAU, origin=synth.lidar_origin_base(), precision=prec)
+        p1.set_bins(bins, TAU)
+        p1.set_map(synth.random_map_bin_stats(N_BINS, 7, bins))
+        h1 = {k: v[:1].clone().pin_memory() for k, v in host.items()}
+        o1 = torch.empty(L.BC_NCERT + 22 * 22 + 22, dtype=torch.float64).pin_memory()
+        ts_e2e, ts_dev = [], []
+        for i in range(60):
+            torch.cuda.synchronize()
+            a = time.perf_counter()
+            p1.upload(h1["pts"], h1["t"], h1["w"], h1["ring"], h1["tag"], h1["t0"], h1["t1"], h1["xi"], h1["poses"])
+            b = time.perf_counter()
+            p1.run()
+            oo = p1.outputs()
+            o1.copy_(torch.cat([oo.cert.reshape(-1), oo.L22.reshape(-1), oo.h22.reshape(-1)]), non_blocking=True)
+            torch.cuda.synchronize()
+            c = time.perf_counter()
+            if i >= 10:
+                ts_e2e.append(c - a)
+        for i in range(60):
+            torch.cuda.synchronize()
+            a = time.perf_counter()
+            p1.run()
+            torch.cuda.synchronize()
+            if i >= 10:
+                ts_dev.append(time.perf_counter() - a)
+        lat = {"p50_ms_host_in_evidence_out": 1e3 * float(np.median(ts_e2e)),
+               "p50_ms_device_resident": 1e3 * float(np.median(ts_dev)), "points": P, "reps": 50}
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        bytes_per_launch = S * (BYTES_IN_PER_PT * P + BYTES_OUT_PER_PT * P)
+        k_avg_ms = k_ms / max(k_n, 1)
+        achieved = bytes_per_launch / (k_avg_ms * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "bin_scan_traffic.json")
+        if os.path.exists(prof):
+            try:
+                with open(prof) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        cpu = cpu_baseline_single(P) if world == 1 and not args.no_cpu else None
+        line = {
+            "metric": "lidar_evidence_path_scans_per_s", "value": value, "unit": "scans/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, S),
+            "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(d2h_bytes), "steps": e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "bin_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(bytes_per_launch), "kernel_ms_avg": k_avg_ms,
+                         "kernel_launches_timed": k_n, "kernel_share_of_step": k_ms / ms_total},
+            "latency": lat,
+            "points_per_s": value * P,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scans", type=int, default=128, help="scans per step per GPU")
+    ap.add_argument("--points", type=int, default=65536)
+    ap.add_argument("--precision", default="f64", choices=["f64", "mixed"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the in-run CPU baseline")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

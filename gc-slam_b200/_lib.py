@@ -1,0 +1,220 @@
+"""
+ctypes binding of the C-ABI in include/gcs_b200.h.
+
+No fallback: if libgcs_b200.so is missing or no B200 is visible, this module (or ``context()``) raises.
+torch is used only for device memory (tensors' ``data_ptr()``) and stream handles.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgcs_b200.so")
+
+GCS_OK, GCS_EINVAL, GCS_ECUDA, GCS_ENOMEM, GCS_ECOMM = 0, -1, -2, -3, -4
+PREC_F64, PREC_MIXED, PREC_TC = 0, 1, 2
+
+# certificate / record layouts (enums of the header)
+RS_MASS_IN, RS_MASS_SEL, RS_SUMSQ_SEL, RS_ESS, RS_MASS_SCALE, RS_NCERT = 0, 1, 2, 3, 4, 8
+DK_SUM_W_OUT, DK_SUM_W_IN, DK_NCERT = 0, 1, 4
+SA_ENTROPY_SUM, SA_MAX_RESP, SA_NCERT = 0, 1, 4
+ST_ESS, ST_SUPPORT_FRAC, ST_PSD_DELTA, ST_MASS_EPS_RATIO, ST_NCERT = 0, 1, 2, 3, 8
+(BC_RS_MASS_IN, BC_RS_ESS, BC_RS_MASS_SCALE, BC_DK_SUM_W_OUT, BC_DK_SUM_W_IN, BC_SA_ENTROPY_SUM, BC_SA_MAX_RESP,
+ BC_ST_ESS, BC_ST_SUPPORT_FRAC, BC_ST_PSD_DELTA, BC_ST_MASS_EPS_RATIO) = range(11)
+BC_NCERT = 16
+EV = dict(R_MF=0, L_ROT=9, H_ROT=18, DELTA_ROT=21, SVD_S=24, SCAN_METRICS=27, MAP_METRICS=44, T_WLS=61, L_TRANS=64,
+          H_TRANS=73, DELTA_TRANS=76, XY_INFO=79, Z_INFO=80, Z_SCALE=81,
+          MF_EIG_MIN=82, MF_EIG_MAX=83, MF_COND=84, MF_NEAR_NULL=85, MF_NLL_PER_ESS=86, MF_DIR_SCORE=87,
+          MF_PSD_DELTA=88, MF_MASS_EPS=89, MF_ROT_NLL=90, MF_N_EFF=91,
+          PT_EIG_MIN=92, PT_EIG_MAX=93, PT_COND=94, PT_NEAR_NULL=95, PT_NLL_PER_ESS=96, PT_PSD_DELTA=97,
+          PT_MASS_EPS=98, PT_TRANS_NLL=99, PT_N_EFF=100)
+EV_NREC = 104
+
+_vp = C.c_void_p
+_i64 = C.c_int64
+_dbl = C.c_double
+_int = C.c_int
+
+
+class BinStats(C.Structure):
+    _fields_ = [(n, _vp) for n in ("N", "s_dir", "S_scatter", "p_bar", "Sigma_p", "kappa", "sum_p", "sum_ppT")]
+
+
+class MapBinStats(C.Structure):
+    _fields_ = [(n, _vp) for n in ("S_dir", "S_scatter", "N_dir", "N_pos", "sum_p", "sum_ppT")]
+
+
+class BinsArgs(C.Structure):
+    _fields_ = [
+        ("pts", _vp), ("t", _vp), ("w", _vp), ("ring", _vp), ("tag", _vp),
+        ("n_raw", _i64), ("cap", _i64), ("n_scans", C.c_int32), ("n_hyp", C.c_int32),
+        ("scan_t0", _vp), ("scan_t1", _vp), ("xi", _vp), ("poses", _vp),
+        ("bin_dirs", _vp), ("n_bins", C.c_int32), ("precision", C.c_int32),
+        ("origin", _dbl * 3), ("tau", _dbl), ("eps_mass", _dbl), ("eps_psd", _dbl),
+        ("map", C.POINTER(MapBinStats)),
+        ("shard_row0", _i64), ("n_raw_total", _i64), ("cap_total", _i64), ("bin_norm_max", _dbl),
+        ("rs_pts", _vp), ("rs_t", _vp), ("rs_w", _vp), ("rs_ring", _vp), ("rs_tag", _vp),
+        ("dk_pts", _vp), ("dk_w", _vp), ("resp", _vp),
+        ("stats", BinStats),
+        ("evidence", _vp), ("L22", _vp), ("h22", _vp), ("cert", _vp),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/gcs_b200.h appears here
+PROTOTYPES = {
+    "gcs_version": (_int, []),
+    "gcs_version_string": (C.c_char_p, []),
+    "gcs_create": (_int, [C.POINTER(_vp), _int]),
+    "gcs_destroy": (_int, [_vp]),
+    "gcs_last_error": (C.c_char_p, [_vp]),
+    "gcs_reserve_workspace": (_int, [_vp, C.c_uint64]),
+    "gcs_device_sm_count": (_int, [_vp]),
+    "gcs_kernel_launches": (C.c_uint64, [_vp]),
+    "gcs_timing_enable": (_int, [_vp, _int]),
+    "gcs_timing_collect": (_int, [_vp, C.POINTER(_dbl), C.POINTER(_int)]),
+    "gcs_point_budget_resample": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gcs_deskew_constant_twist": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_dbl), _dbl, _dbl, _vp, _vp, _vp]),
+    "gcs_ray_directions": (_int, [_vp, _vp, _vp, _i64, C.POINTER(_dbl), _dbl, _vp]),
+    "gcs_bin_soft_assign": (_int, [_vp, _vp, _vp, _i64, _vp, _int, _dbl, _dbl, _int, _vp, _vp]),
+    "gcs_scan_bin_moment_match": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_dbl), _i64, _int, _dbl, _dbl,
+                                         C.POINTER(BinStats), _vp]),
+    "gcs_kappa_from_resultant_batch": (_int, [_vp, _vp, _vp, _i64, _dbl, _dbl, _dbl, _dbl, _vp]),
+    "gcs_map_bin_update": (_int, [_vp, _vp, C.POINTER(MapBinStats), _vp, _vp, _vp, _vp, _vp, _int, C.POINTER(_dbl), _int, _dbl]),
+    "gcs_map_bin_derived": (_int, [_vp, _vp, C.POINTER(MapBinStats), _int, _dbl, _dbl, _vp, _vp, _vp, _vp]),
+    "gcs_bin_evidence": (_int, [_vp, _vp, C.POINTER(BinStats), _int, _int, C.POINTER(MapBinStats), _vp, _dbl, _dbl, _vp, _vp, _vp]),
+    "gcs_matrix_fisher_rotation": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, C.POINTER(_dbl), _dbl, _dbl, _vp]),
+    "gcs_planar_translation": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, C.POINTER(_dbl),
+                                      C.POINTER(_dbl), _dbl, _dbl, _vp]),
+    "gcs_bins_raw_sums_len": (_int, [_int]),
+    "gcs_lidar_evidence_bins": (_int, [_vp, _vp, C.POINTER(BinsArgs)]),
+    "gcs_bins_mass": (_int, [_vp, _vp, C.POINTER(BinsArgs), _vp]),
+    "gcs_bins_accumulate": (_int, [_vp, _vp, C.POINTER(BinsArgs), _vp, _vp, _vp]),
+    "gcs_bins_finalize": (_int, [_vp, _vp, C.POINTER(BinsArgs), _vp, _vp, _vp]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def register_prototypes(extra):
+    """Other modules (primitive family) add their entry points here before the library is first loaded."""
+    PROTOTYPES.update(extra)
+    global _lib
+    if _lib is not None:
+        for name, (res, args) in extra.items():
+            fn = getattr(_lib, name)
+            fn.restype, fn.argtypes = res, args
+
+
+def load():
+    """dlopen the library (works without a GPU; nothing CUDA runs until gcs_create)."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: build it with `python -m gc_slam_b200.build` "
+                    "(nvcc, sm_100a).  gc_slam_b200 has no CPU fallback.")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in PROTOTYPES.items():
+                fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+    return _lib
+
+
+class GcsError(RuntimeError):
+    pass
+
+
+class Context:
+    """One gcs_ctx: bound to a device, not re-entrant (one per calling thread / stream)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = _vp()
+        rc = self.lib.gcs_create(C.byref(h), int(device))
+        if rc != GCS_OK:
+            msg = self.lib.gcs_last_error(None).decode()
+            raise RuntimeError(f"gcs_create(device={device}) failed [{rc}]: {msg}")
+        self.handle = h
+        self.device = int(device)
+
+    def check(self, rc: int):
+        if rc == GCS_OK:
+            return
+        msg = self.lib.gcs_last_error(self.handle).decode()
+        if rc == GCS_EINVAL:
+            raise ValueError(msg)
+        raise GcsError(f"[gcs {rc}] {msg}")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.gcs_kernel_launches(self.handle))
+
+    @property
+    def sm_count(self) -> int:
+        return int(self.lib.gcs_device_sm_count(self.handle))
+
+    def timing_enable(self, on: bool = True):
+        self.check(self.lib.gcs_timing_enable(self.handle, 1 if on else 0))
+
+    def timing_collect(self):
+        """-> (summed device ms of the dominant kernel, number of launches) since the last collect."""
+        ms, n = _dbl(0.0), _int(0)
+        self.check(self.lib.gcs_timing_collect(self.handle, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.gcs_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_tls = threading.local()
+
+
+def context(device: int | None = None) -> Context:
+    """Per-thread, per-device context (the reference calls operators from a worker thread and a 2-thread pool)."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("gc_slam_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        device = torch.cuda.current_device()
+    cache = getattr(_tls, "ctx", None)
+    if cache is None:
+        cache = _tls.ctx = {}
+    if device not in cache:
+        cache[device] = Context(device)
+    return cache[device]
+
+
+def stream_ptr(device=None):
+    import torch
+
+    return _vp(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return _vp(0)
+    if not t.is_cuda:
+        raise ValueError("expected a CUDA tensor")
+    if not t.is_contiguous():
+        raise ValueError("expected a contiguous tensor")
+    return _vp(t.data_ptr())
+
+
+def version_string() -> str:
+    return load().gcs_version_string().decode()
