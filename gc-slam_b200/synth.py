@@ -128,3 +128,117 @@ def random_map_bin_stats(n_bins: int, seed: int, bin_dirs=None):
         sum_p[b] = (w[:, None] * p).sum(0)
         sum_pp[b] = np.einsum("n,ni,nj->ij", w, p, p)
     return dict(S_dir=S_dir, S_dir_scatter=S_sc, N_dir=N, N_pos=N.copy(), sum_p=sum_p, sum_ppT=sum_pp)
+
+
+# --------------------------------------------------------------------------------------------------
+# primitive family: synthetic surfel map, camera splats
+# --------------------------------------------------------------------------------------------------
+def _tile_ids_from_xyz(XYZ, h):
+    """Packed MA-hex tile ids (closed form of fl/common/tiling.py:126-145; 21 bits per axis, bias 2^20)."""
+    XYZ = np.asarray(XYZ, np.float64).reshape(-1, 3)
+    s2 = XYZ[:, 0] * 0.5 + XYZ[:, 1] * (np.sqrt(np.float64(3.0)) * 0.5)
+    c1 = np.floor(XYZ[:, 0] / h).astype(np.int64)
+    c2 = np.floor(s2 / h).astype(np.int64)
+    cz = np.floor(XYZ[:, 2] / h).astype(np.int64)
+    m = (1 << 21) - 1
+    return (((c1 + (1 << 20)) & m) << 42) | (((c2 + (1 << 20)) & m) << 21) | ((cz + (1 << 20)) & m)
+
+
+def room_surface_points(n, seed):
+    """n points + outward-ish normals on the surfaces of the synthetic room (base frame)."""
+    rng = np.random.default_rng(seed)
+    i = np.arange(n)
+    az = rng.uniform(0, 2 * np.pi, n)
+    el = rng.uniform(-0.6, 0.6, n)
+    u = np.stack([np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el)], axis=1)
+    r = np.clip(_ray_room(u, np.zeros(3)), 0.5, 50.0)
+    p = u * r[:, None]
+    # surface normal = axis of the wall that was hit (largest |coordinate| relative to the box), else radial
+    lo = np.array([-10.0, -4.0, -0.6]); hi = np.array([10.0, 4.0, 2.4])
+    d_lo = np.abs(p - lo[None]); d_hi = np.abs(p - hi[None])
+    d = np.minimum(d_lo, d_hi)
+    ax = np.argmin(d, axis=1)
+    nrm = np.zeros((n, 3))
+    nrm[i, ax] = np.where(d_lo[i, ax] < d_hi[i, ax], 1.0, -1.0)
+    far = d[i, ax] > 0.05  # pillars
+    nrm[far] = -u[far] * np.array([1.0, 1.0, 0.0])
+    nrm[far] /= np.linalg.norm(nrm[far], axis=1, keepdims=True) + 1e-12
+    R = rotvec_to_matrix(T_BASE_LIDAR[3:])
+    return p @ R.T + T_BASE_LIDAR[None, :3], nrm @ R.T
+
+
+def synthetic_atlas(n_surfels, m_tile, seed, scan_seq=10, h_tile=C.GC_H_TILE, n_lobes=C.GC_VMF_N_LOBES,
+                    camera_fraction=0.2):
+    """
+    Synthetic surfel atlas as plain NumPy tile dicts (field names of fl/backend/structures/primitive_map.py:98-145).
+    Surfels lie on the room surfaces, tiles are MA-hex cells (h = 2 m) keyed by position, at most m_tile per tile,
+    slots are scattered (holes stay invalid), Lambda from plane-like covariances, eta = kappa * n, kappa ~ U(1,100),
+    weights ~ Gamma(2,1), last_supported_scan_seq ~ U{0..scan_seq}, ids sequential.
+    Returns dict(tiles={tile_id: tile}, next_global_id, total_count, m_tile).
+    """
+    rng = np.random.default_rng(seed)
+    pos, nrm = room_surface_points(n_surfels, seed + 1)
+    tids = _tile_ids_from_xyz(pos, h_tile)
+    order = np.argsort(tids, kind="stable")
+    pos, nrm, tids = pos[order], nrm[order], tids[order]
+    uniq, start, counts = np.unique(tids, return_index=True, return_counts=True)
+    tiles = {}
+    next_id = 0
+    for tid, s0, cnt in zip(uniq, start, counts):
+        k = int(min(cnt, m_tile))
+        slots = np.sort(rng.choice(m_tile, size=k, replace=False))
+        mu, n = pos[s0:s0 + k], nrm[s0:s0 + k]
+        # clutter: perturb the wall normals so that direction statistics are not rank deficient near the sensor
+        n = n + 0.35 * rng.normal(size=n.shape)
+        n = n / (np.linalg.norm(n, axis=1, keepdims=True) + 1e-12)
+        # orthonormal basis with n as third axis
+        a = np.where(np.abs(n[:, 2:3]) < 0.9, np.array([[0.0, 0.0, 1.0]]), np.array([[1.0, 0.0, 0.0]]))
+        e1 = np.cross(n, a); e1 /= np.linalg.norm(e1, axis=1, keepdims=True) + 1e-12
+        e2 = np.cross(n, e1)
+        V = np.stack([e1, e2, n], axis=2)
+        var = np.stack([rng.uniform(0.004, 0.02, k), rng.uniform(0.004, 0.02, k), rng.uniform(5e-5, 4e-4, k)], axis=1)
+        Lam = np.einsum("kij,kj,klj->kil", V, 1.0 / var, V)
+        t = dict(tile_id=int(tid), Lambdas=np.zeros((m_tile, 3, 3)), thetas=np.zeros((m_tile, 3)),
+                 etas=np.zeros((m_tile, n_lobes, 3)), weights=np.zeros(m_tile), timestamps=np.zeros(m_tile),
+                 created_timestamps=np.zeros(m_tile), last_supported_scan_seq=np.zeros(m_tile, np.int64),
+                 last_update_scan_seq=np.zeros(m_tile, np.int64), primitive_ids=np.zeros(m_tile, np.int64),
+                 valid_mask=np.zeros(m_tile, bool), colors=np.zeros((m_tile, 3)), cam_mass=np.zeros(m_tile),
+                 lidar_mass=np.zeros(m_tile), rgb_cam_accum=np.zeros((m_tile, 3)), rgb_cam_denom=np.zeros(m_tile),
+                 rgb=np.full((m_tile, 3), 0.5), next_local_id=int(slots.max()) + 1 if k else 0, count=k)
+        t["Lambdas"][slots] = Lam
+        t["thetas"][slots] = np.einsum("kij,kj->ki", Lam, mu)
+        t["etas"][slots, 0, :] = rng.uniform(1.0, 100.0, (k, 1)) * n
+        w = rng.gamma(2.0, 1.0, k)
+        w[rng.uniform(size=k) < 0.01] = 5e-5          # a few below the cull threshold
+        t["weights"][slots] = w
+        t["timestamps"][slots] = EPOCH_T0 - rng.uniform(0, 5, k)
+        t["created_timestamps"][slots] = EPOCH_T0 - 10.0
+        ls = rng.integers(0, scan_seq + 1, k)
+        t["last_supported_scan_seq"][slots] = ls
+        t["last_update_scan_seq"][slots] = ls
+        t["primitive_ids"][slots] = next_id + np.arange(k)
+        t["valid_mask"][slots] = True
+        is_cam = rng.uniform(size=k) < camera_fraction
+        col = rng.uniform(0, 1, (k, 3))
+        cm = np.where(is_cam, w, 0.0)
+        t["cam_mass"][slots] = cm
+        t["lidar_mass"][slots] = np.where(is_cam, 0.0, w)
+        t["rgb_cam_accum"][slots] = col * cm[:, None]
+        t["rgb_cam_denom"][slots] = cm
+        t["rgb"][slots] = np.where(is_cam[:, None], col, 0.5)
+        t["colors"][slots] = t["rgb"][slots]
+        tiles[int(tid)] = t
+        next_id += k
+    return dict(tiles=tiles, next_global_id=next_id, total_count=next_id, m_tile=int(m_tile))
+
+
+def camera_splats(n, seed):
+    """Random camera splats in the body frame (positions 1-6 m ahead): positions, covariances, directions, kappas,
+    weights, timestamps, colors -- the inputs of measurement_batch_from_camera_splats."""
+    rng = np.random.default_rng(seed)
+    pos = np.stack([rng.uniform(1.0, 6.0, n), rng.uniform(-2.5, 2.5, n), rng.uniform(-0.4, 1.5, n)], axis=1)
+    A = rng.normal(size=(n, 3, 3)) * 0.03
+    cov = A @ np.transpose(A, (0, 2, 1)) + 1e-4 * np.eye(3)[None]
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return dict(positions=pos, covariances=cov, directions=d, kappas=rng.uniform(1, 50, n), weights=rng.uniform(0.2, 1.0, n),
+                timestamps=np.full(n, EPOCH_T0 + 0.05), colors=rng.uniform(0, 1, (n, 3)))
