@@ -189,8 +189,11 @@ def context(device: int | None = None) -> Context:
 
     if not torch.cuda.is_available():
         raise RuntimeError("gc_slam_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if isinstance(device, torch.device):
+        device = device.index
     if device is None:
         device = torch.cuda.current_device()
+    device = int(device)
     cache = getattr(_tls, "ctx", None)
     if cache is None:
         cache = _tls.ctx = {}

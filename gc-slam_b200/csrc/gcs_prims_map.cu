@@ -1,0 +1,1114 @@
+// gcs_prims_map.cu -- primitive-map side of the LiDAR evidence path:
+//   a11  recency inflation, per-tile top-k view extraction
+//   a12  OT association (pool cost -> stable top-K -> unbalanced Sinkhorn, 50 fixed iterations)
+//   a13  pose evidence from soft correspondences (WLS translation + scatter-SVD rotation)
+//   a14  map update: PoE fuse (sorted segmented scatter, no float atomics), insert/evict, cull, forget
+// All selections reproduce jnp.argsort / lax.sort semantics (stable, first operand is the only key) through
+// cta_select_k (gcs_select.cuh).  All floating reductions are fixed-order.
+#include "gcs_select.cuh"
+
+namespace gcs {
+
+constexpr int kBig = 1024;  // CTA size of the single-CTA kernels
+
+__device__ __forceinline__ double block_sum_1024(double v, double* sred) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sred[i];
+  __syncthreads();
+  return s;  // valid in every thread
+}
+
+__device__ __forceinline__ void load_mat3(const double* p, Mat3& M) {
+#pragma unroll
+  for (int k = 0; k < 9; ++k) M.m[k] = p[k];
+}
+
+// mean position / direction / kappa of one measurement row (measurement_batch.py:390-411)
+__device__ inline void meas_row_moments(const gcs_meas_batch& B, int i, double eps_lift, double eps_mass, double* mu,
+                                        double* dir, double* kappa) {
+  Mat3 L;
+  load_mat3(B.Lambdas + 9 * i, L);
+  L(0, 0) += eps_lift; L(1, 1) += eps_lift; L(2, 2) += eps_lift;
+  const double th[3] = {B.thetas[3 * i], B.thetas[3 * i + 1], B.thetas[3 * i + 2]};
+  mat3_solve(L, th, mu);
+  double es[3];
+  for (int k = 0; k < 3; ++k) es[k] = B.etas[9 * i + k] + B.etas[9 * i + 3 + k] + B.etas[9 * i + 6 + k];
+  const double n = sqrt(es[0] * es[0] + es[1] * es[1] + es[2] * es[2]);
+  *kappa = n;
+  for (int k = 0; k < 3; ++k) dir[k] = es[k] / (n + eps_mass);
+}
+
+__device__ __forceinline__ long long pack_tile_id(long long c1, long long c2, long long cz) {
+  const long long m = (1ll << 21) - 1, b = 1ll << 20;  // fl/common/tiling.py:74-100
+  return (((c1 + b) & m) << 42) | (((c2 + b) & m) << 21) | ((cz + b) & m);
+}
+__device__ __forceinline__ void tile_cell(const double* p, double h, long long* c) {
+  const double s2 = p[0] * 0.5 + p[1] * (sqrt(3.0) * 0.5);
+  c[0] = (long long)floor(p[0] / h); c[1] = (long long)floor(s2 / h); c[2] = (long long)floor(p[2] / h);
+}
+
+// =================================================================================================
+// a11: recency inflation
+// =================================================================================================
+struct TileList {
+  int32_t index[16];
+  int64_t id[16];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) recency_inflate_kernel(gcs_atlas A, TileList T, long long scan_seq, double lam,
+                                                              double min_scale, double* __restrict__ part) {
+  __shared__ double sred[3][8];
+  const int a = blockIdx.y;
+  const int ti = T.index[a];
+  double s_down = 0.0, s_tr = 0.0, s_n = 0.0;
+  if (ti >= 0) {
+    const int64_t base = (int64_t)ti * A.m_tile;
+    for (int s = blockIdx.x * 256 + threadIdx.x; s < A.m_tile; s += gridDim.x * 256) {
+      const int64_t o = base + s;
+      const bool v = A.valid[o] != 0;
+      long long dt = scan_seq - A.last_supported_scan_seq[o];
+      if (dt < 0) dt = 0;
+      double decay = exp(-lam * (double)dt);
+      decay = fmin(fmax(decay, min_scale), 1.0);
+      if (!v) decay = 1.0;
+      if (v) {
+        for (int k = 0; k < 9; ++k) A.Lambdas[9 * o + k] *= decay;
+        for (int k = 0; k < 3; ++k) A.thetas[3 * o + k] *= decay;
+        s_down += 1.0 - decay; s_tr += 1.0 / decay - 1.0; s_n += 1.0;
+      }
+    }
+  }
+  double v3[3] = {s_down, s_tr, s_n};
+  for (int k = 0; k < 3; ++k) {
+    double r = warp_sum(v3[k]);
+    if ((threadIdx.x & 31) == 0) sred[k][threadIdx.x >> 5] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int g = 0; g < 8; ++g) s += sred[threadIdx.x][g];
+    part[((int64_t)a * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = s;
+  }
+}
+__global__ void sum_parts_kernel(const double* __restrict__ part, int n_parts, int width, double* __restrict__ out, int out_len) {
+  const int k = threadIdx.x;
+  if (k >= out_len) return;
+  double a = 0.0;
+  if (k < width)
+    for (int c = 0; c < n_parts; ++c) a += part[(int64_t)c * width + k];
+  out[k] = a;
+}
+
+// =================================================================================================
+// a11: view extraction
+// =================================================================================================
+struct SelectSmem {
+  KeyIdx out[1024];
+  int hist[256];
+  int scan[2 * kBig];
+};
+
+__global__ void __launch_bounds__(kBig) map_view_kernel(gcs_atlas A, TileList T, int m_view, double eps_lift, double eps_mass,
+                                                        gcs_map_view V, int32_t* __restrict__ n_valid_out) {
+  __shared__ SelectSmem sm;
+  const int a = blockIdx.x;
+  const int ti = T.index[a];
+  const int M = A.m_tile;
+  const int64_t base = (int64_t)(ti < 0 ? 0 : ti) * M;
+  auto key = [&](int s) -> unsigned long long {
+    double score = -1e30;
+    if (ti >= 0 && A.valid[base + s]) score = A.weights[base + s];
+    return f64_orderable(-score);  // ascending sort of -score (primitive_map.py:316-320)
+  };
+  cta_select_k(M, m_view, key, sm.out, sm.hist, sm.scan);
+  int local_valid = 0;
+  for (int j = threadIdx.x; j < m_view; j += kBig) {
+    const int slot = sm.out[j].idx;
+    const int64_t o = base + slot;
+    const int r = a * m_view + j;
+    Mat3 L;
+    double th[3] = {0, 0, 0}, et[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, w = 0.0, col[3] = {0.5, 0.5, 0.5};
+    long long pid = 0, last = 0;
+    bool v = false;
+    for (int k = 0; k < 9; ++k) L.m[k] = 0.0;
+    if (ti >= 0) {
+      load_mat3(A.Lambdas + 9 * o, L);
+      for (int k = 0; k < 3; ++k) { th[k] = A.thetas[3 * o + k]; col[k] = A.rgb[3 * o + k]; }
+      for (int k = 0; k < 9; ++k) et[k] = A.etas[9 * o + k];
+      w = A.weights[o]; pid = A.primitive_ids[o]; last = A.last_supported_scan_seq[o]; v = A.valid[o] != 0;
+    }
+    L(0, 0) += eps_lift; L(1, 1) += eps_lift; L(2, 2) += eps_lift;
+    double mu[3];
+    mat3_solve(L, th, mu);
+    Mat3 S = mat3_inv(L);
+    const double es[3] = {et[0] + et[3] + et[6], et[1] + et[4] + et[7], et[2] + et[5] + et[8]};
+    const double kap = sqrt(es[0] * es[0] + es[1] * es[1] + es[2] * es[2]);
+    V.candidate_tile_ids[r] = T.id[a];
+    V.candidate_slots[r] = slot;
+    V.valid[r] = v ? 1 : 0;
+    for (int k = 0; k < 3; ++k) {
+      V.positions[3 * r + k] = mu[k];
+      V.directions[3 * r + k] = es[k] / (kap + eps_mass);
+      V.colors[3 * r + k] = col[k];
+    }
+    for (int k = 0; k < 9; ++k) { V.covariances[9 * r + k] = S.m[k]; V.etas[9 * r + k] = et[k]; }
+    V.kappas[r] = kap; V.weights[r] = w; V.primitive_ids[r] = pid; V.last_supported_scan_seq[r] = last;
+    local_valid += v ? 1 : 0;
+  }
+  if (local_valid) atomicAdd(n_valid_out, local_valid);
+}
+
+// =================================================================================================
+// a12: association
+// =================================================================================================
+// A_vmf(k) = log(4 pi) + log sinh k - log k with the reference's three branches (primitive_association.py:141-149)
+__device__ __forceinline__ double A_vmf(double k, double eps) {
+  k = fmax(k, eps);
+  double ls;
+  if (k > 20.0) ls = k - log(2.0);
+  else if (k >= 1e-2) ls = log(sinh(k));
+  else ls = log(k + (k * k * k) / 6.0);
+  return log(4.0 * 3.141592653589793) + ls - log(k);
+}
+
+// cost of (measurement, map entry)   (primitive_association.py:152-197)
+__device__ __forceinline__ double pair_cost(const double* mp, const double* md, double mk, double A_k1, const double* vp,
+                                            const double* vd, double vk, double beta) {
+  const double eig_min = 1e-12;
+  const double d0 = mp[0] - vp[0], d1 = mp[1] - vp[1], d2 = mp[2] - vp[2];
+  const double d_pos = d0 * d0 + d1 * d1 + d2 * d2;
+  const double e0 = mk * md[0] + vk * vd[0], e1 = mk * md[1] + vk * vd[1], e2 = mk * md[2] + vk * vd[2];
+  const double km = 0.5 * sqrt(e0 * e0 + e1 * e1 + e2 * e2);
+  const double A_km = A_vmf(fmax(km, eig_min), eig_min);
+  const double A_k2 = A_vmf(fmax(vk, eig_min), eig_min);
+  const double bc = exp(A_km - 0.5 * (A_k1 + A_k2));
+  double d_dir = fmax(0.0, 1.0 - bc);
+  if (!(mk > 0.0 && vk > 0.0)) d_dir = 0.0;
+  return d_pos + beta * d_dir;
+}
+
+struct AssocWs {
+  double* mpos;     // (N,3)
+  double* mdir;     // (N,3)
+  double* mkap;     // (N)
+  int8_t* stencil;  // (N, n_st)  view tile index or -1
+};
+
+__global__ void __launch_bounds__(128) assoc_prepare_kernel(gcs_meas_batch B, int N, TileList T, gcs_assoc_cfg cfg,
+                                                            int n_st, const int* __restrict__ dq,
+                                                            const int* __restrict__ dr, const int* __restrict__ dz,
+                                                            AssocWs W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double mu[3], dir[3], kap;
+  meas_row_moments(B, i, cfg.eps_lift, cfg.eps_mass, mu, dir, &kap);
+  for (int k = 0; k < 3; ++k) { W.mpos[3 * i + k] = mu[k]; W.mdir[3 * i + k] = dir[k]; }
+  W.mkap[i] = kap;
+  long long c[3];
+  tile_cell(mu, fmax(cfg.h_tile, 1e-12), c);
+  for (int s = 0; s < n_st; ++s) {
+    const long long tid = pack_tile_id(c[0] + dq[s], c[1] + dr[s], c[2] + dz[s]);
+    int idx = -1;
+    for (int a = 0; a < T.n; ++a)
+      if (T.id[a] == tid) { idx = a; break; }  // argmax of the equality mask = first match
+    W.stencil[i * n_st + s] = (int8_t)idx;
+  }
+}
+
+// one warp per measurement row: stream the candidate pool, keep the K best (cost, pool position) per lane, merge.
+template <int K>
+__global__ void __launch_bounds__(256) assoc_topk_kernel(gcs_meas_batch B, int N, gcs_map_view V, int m_view, int n_st,
+                                                         AssocWs W, gcs_assoc_cfg cfg, gcs_assoc_result R) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const int i = warp;
+  const double mp[3] = {W.mpos[3 * i], W.mpos[3 * i + 1], W.mpos[3 * i + 2]};
+  const double md[3] = {W.mdir[3 * i], W.mdir[3 * i + 1], W.mdir[3 * i + 2]};
+  const double mk = W.mkap[i];
+  const double A_k1 = A_vmf(fmax(mk, 1e-12), 1e-12);
+  double bc[K];
+  int bj[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { bc[k] = 1.0e300; bj[k] = 0x7fffffff; }
+  const int P = n_st * m_view;
+  for (int j = lane; j < P; j += 32) {
+    const int s = j / m_view, off = j - s * m_view;
+    const int tix = W.stencil[i * n_st + s];
+    const int v = (tix < 0 ? 0 : tix) * m_view + off;
+    double c = 1e12;
+    if (tix >= 0 && V.valid[v])
+      c = pair_cost(mp, md, mk, A_k1, V.positions + 3 * v, V.directions + 3 * v, V.kappas[v], cfg.beta);
+    // insertion into the lane-local sorted list (j increases, so equal costs keep the earlier j first)
+    if (c < bc[K - 1]) {
+      bc[K - 1] = c; bj[K - 1] = j;
+#pragma unroll
+      for (int k = K - 1; k > 0; --k) {
+        if (bc[k] < bc[k - 1]) {
+          const double tc = bc[k]; bc[k] = bc[k - 1]; bc[k - 1] = tc;
+          const int tj = bj[k]; bj[k] = bj[k - 1]; bj[k - 1] = tj;
+        }
+      }
+    }
+  }
+  // K-round tournament over the lanes' heads by (cost, j)
+  const bool mvalid = B.valid[i] != 0;
+  for (int r = 0; r < K; ++r) {
+    double hc = bc[0];
+    int hj = bj[0], hl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double oc = __shfl_xor_sync(0xffffffffu, hc, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, hj, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, hl, o);
+      if (oc < hc || (oc == hc && oj < hj)) { hc = oc; hj = oj; hl = ol; }
+    }
+    if (lane == hl) {
+#pragma unroll
+      for (int k = 0; k < K - 1; ++k) { bc[k] = bc[k + 1]; bj[k] = bj[k + 1]; }
+      bc[K - 1] = 1.0e300; bj[K - 1] = 0x7fffffff;
+    }
+    if (lane == 0) {
+      const int s = hj / m_view, off = hj - s * m_view;
+      const int tix = W.stencil[i * n_st + s];
+      int v = (tix < 0 ? 0 : tix) * m_view + off;
+      if (!mvalid) v = 0;  // invalid measurement rows point at pool entry 0 (:379)
+      R.candidate_pool_indices[i * K + r] = v;
+      R.candidate_tile_ids[i * K + r] = V.candidate_tile_ids[v];
+      R.candidate_slots[i * K + r] = (long long)V.candidate_slots[v];
+    }
+  }
+}
+
+// single CTA: cost of the selected candidates, recency term, row-min shift, unbalanced Sinkhorn, certificates
+template <int K>
+__global__ void __launch_bounds__(kBig) assoc_sinkhorn_kernel(gcs_meas_batch B, int N, gcs_map_view V, AssocWs W,
+                                                              gcs_assoc_cfg cfg, gcs_assoc_result R,
+                                                              double* __restrict__ cert, double* __restrict__ brow_ws) {
+  __shared__ double sred[32];
+  __shared__ double sv[K];
+  __shared__ SelectSmem sel;
+  const int tid = threadIdx.x;
+  constexpr int RPT = 2;  // rows per thread: N <= 2048
+  double Km[RPT][K], Cm[RPT][K], u[RPT], a[RPT];
+  const double eps = fmax(cfg.epsilon, 1e-12);
+  double nvalid = 0.0;
+  for (int q = 0; q < RPT; ++q) {
+    const int i = tid + q * kBig;
+    nvalid += (i < N && B.valid[i]) ? 1.0 : 0.0;
+  }
+  const double sum_valid = block_sum_1024(nvalid, sred);
+  const double sum_a = fmax(sum_valid, cfg.eps_mass);
+  for (int q = 0; q < RPT; ++q) {
+    const int i = tid + q * kBig;
+    u[q] = 1.0; a[q] = 0.0;
+    for (int k = 0; k < K; ++k) { Km[q][k] = 0.0; Cm[q][k] = 0.0; }
+    if (i >= N) continue;
+    a[q] = (B.valid[i] ? 1.0 : 0.0) / sum_a;
+    const double mp[3] = {W.mpos[3 * i], W.mpos[3 * i + 1], W.mpos[3 * i + 2]};
+    const double md[3] = {W.mdir[3 * i], W.mdir[3 * i + 1], W.mdir[3 * i + 2]};
+    const double mk = W.mkap[i];
+    const double A_k1 = A_vmf(fmax(mk, 1e-12), 1e-12);
+    double rmin = 1.0e300, bsum = 0.0, bdec[K];
+    for (int k = 0; k < K; ++k) {
+      const int v = R.candidate_pool_indices[i * K + k];
+      double c = pair_cost(mp, md, mk, A_k1, V.positions + 3 * v, V.directions + 3 * v, V.kappas[v], cfg.beta);
+      long long dt = cfg.scan_seq - V.last_supported_scan_seq[v];
+      if (dt < 0) dt = 0;
+      c += cfg.epsilon * cfg.recency_decay_lambda * (double)dt;
+      Cm[q][k] = c;
+      rmin = fmin(rmin, c);
+      double d = exp(-cfg.recency_decay_lambda * (double)dt);
+      if (!(d > 0.0)) d = 0.0;
+      bdec[k] = d; bsum += d;
+    }
+    for (int k = 0; k < K; ++k) {
+      Cm[q][k] -= rmin;
+      Km[q][k] = exp(-Cm[q][k] / eps);
+      brow_ws[i * K + k] = bdec[k] / fmax(bsum, cfg.eps_mass);  // diagnostics only (:420-425)
+    }
+  }
+  if (tid < K) sv[tid] = 1.0;
+  __syncthreads();
+  const double ua = 1.0 / (1.0 + cfg.tau_a / eps), vb = 1.0 / (1.0 + cfg.tau_b / eps);
+  const double bk = 1.0 / (double)K;
+  for (int it = 0; it < cfg.k_sinkhorn; ++it) {
+    double ktu[K];
+    for (int k = 0; k < K; ++k) ktu[k] = 0.0;
+    for (int q = 0; q < RPT; ++q) {
+      const int i = tid + q * kBig;
+      if (i >= N) continue;
+      double kv = 0.0;
+      for (int k = 0; k < K; ++k) kv += Km[q][k] * sv[k];
+      u[q] = pow(a[q] / (kv + 1e-12), ua);
+      for (int k = 0; k < K; ++k) ktu[k] += Km[q][k] * u[q];
+    }
+    double tot[K];
+    for (int k = 0; k < K; ++k) tot[k] = block_sum_1024(ktu[k], sred);
+    if (tid < K) sv[tid] = pow(bk / (tot[tid] + 1e-12), vb);
+    __syncthreads();
+  }
+  // outputs + certificate sums
+  double s_row = 0, s_row2 = 0, s_da = 0, s_nov = 0, s_cost = 0, col[K];
+  for (int k = 0; k < K; ++k) col[k] = 0.0;
+  for (int q = 0; q < RPT; ++q) {
+    const int i = tid + q * kBig;
+    if (i >= N) continue;
+    const bool mv = B.valid[i] != 0;
+    double row = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const double pi = u[q] * Km[q][k] * sv[k];
+      row += pi; col[k] += pi; s_cost += pi * Cm[q][k];
+      R.responsibilities[i * K + k] = mv ? pi : 0.0;
+      R.cost_matrix[i * K + k] = Cm[q][k];
+    }
+    R.row_masses[i] = row;
+    s_row += row; s_row2 += row * row;
+    const double d = row - a[q];
+    s_da += d * d;
+    s_nov += fmax(a[q] - row, 0.0);
+  }
+  const double S_row = block_sum_1024(s_row, sred), S_row2 = block_sum_1024(s_row2, sred);
+  const double S_da = block_sum_1024(s_da, sred), S_nov = block_sum_1024(s_nov, sred), S_cost = block_sum_1024(s_cost, sred);
+  double db = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const double ck = block_sum_1024(col[k], sred);
+    db += (ck - bk) * (ck - bk);
+  }
+  // p95 of the diagnostic per-row recency marginal: the (total - idx)-th largest of N*K values
+  const int total = N * K;
+  int idx95 = (int)(0.95 * (double)total);
+  if (idx95 > total - 1) idx95 = total - 1;
+  const int kk = total - idx95;
+  double b95 = -1.0;
+  if (kk >= 1 && kk <= 1024 && total >= kk) {
+    auto key = [&](int j) -> unsigned long long { return ~f64_orderable(brow_ws[j]); };  // descending
+    cta_select_k(total, kk, key, sel.out, sel.hist, sel.scan);
+    b95 = brow_ws[sel.out[kk - 1].idx];
+  }
+  if (tid == 0) {
+    const int n0 = N - (int)sum_valid;  // zeros of a sort first
+    int ia = (int)(0.95 * (double)N);
+    if (ia > N - 1) ia = N - 1;
+    cert[GCS_OT_MARGINAL_A] = sqrt(S_da);
+    cert[GCS_OT_MARGINAL_B] = sqrt(db);
+    cert[GCS_OT_MASS_TOTAL] = S_row;
+    cert[GCS_OT_SUM_A] = sum_a;
+    cert[GCS_OT_SUM_M] = S_row;
+    cert[GCS_OT_SUM_NOVEL] = S_nov;
+    cert[GCS_OT_P95_A] = (ia < n0) ? 0.0 : 1.0 / sum_a;
+    cert[GCS_OT_NONZERO_A] = ((1.0 / sum_a) > cfg.eps_mass) ? sum_valid : 0.0;
+    cert[GCS_OT_B_RECENCY_P95] = b95;
+    cert[GCS_OT_ESS] = S_row * S_row / (S_row2 + cfg.eps_mass);
+    cert[GCS_OT_TOTAL_COST] = S_cost;
+    cert[GCS_OT_SUM_M2] = S_row2;
+    for (int k = GCS_OT_SUM_M2 + 1; k < GCS_OT_NCERT; ++k) cert[k] = 0.0;
+  }
+}
+
+// =================================================================================================
+// a13: pose evidence
+// =================================================================================================
+template <int K>
+__global__ void __launch_bounds__(kBig) pose_evidence_kernel(gcs_meas_batch B, int N, gcs_map_view V, gcs_assoc_result R,
+                                                             double p0, double p1, double p2, double r0, double r1,
+                                                             double r2, double eps_lift, double eps_mass,
+                                                             double* __restrict__ L22, double* __restrict__ h22,
+                                                             double* __restrict__ rec) {
+  __shared__ double sred[32];
+  __shared__ double tot[28];
+  const int tid = threadIdx.x;
+  const double rv[3] = {r0, r1, r2}, tp[3] = {p0, p1, p2};
+  const Mat3 Rp = so3_exp(rv);
+  double acc[28];
+  for (int k = 0; k < 28; ++k) acc[k] = 0.0;
+  // 0..8 L_t, 9..11 h_t, 12 trans cost, 13..21 S, 22 rot cost, 23 sum row mass, 24 n valid rows
+  for (int i = tid; i < N; i += kBig) {
+    if (!B.valid[i]) continue;
+    double mu[3], dir[3], kap;
+    meas_row_moments(B, i, eps_lift, eps_mass, mu, dir, &kap);
+    Mat3 L;
+    load_mat3(B.Lambdas + 9 * i, L);
+    L(0, 0) += eps_lift; L(1, 1) += eps_lift; L(2, 2) += eps_lift;
+    double mw[3], dw[3];
+    mat3_vec(Rp, mu, mw);
+    mat3_vec(Rp, dir, dw);
+    double pis = 0.0, wt[3] = {0, 0, 0};
+    for (int k = 0; k < K; ++k) {
+      const double pi = R.responsibilities[i * K + k];
+      const int v = R.candidate_pool_indices[i * K + k];
+      const double* vp = V.positions + 3 * v;
+      const double* vd = V.directions + 3 * v;
+      pis += pi;
+      const double tg[3] = {vp[0] - mw[0], vp[1] - mw[1], vp[2] - mw[2]};
+      const double rs[3] = {tg[0] - tp[0], tg[1] - tp[1], tg[2] - tp[2]};
+      for (int c = 0; c < 3; ++c) wt[c] += pi * tg[c];
+      double Lr[3];
+      mat3_vec(L, rs, Lr);
+      acc[12] += pi * (rs[0] * Lr[0] + rs[1] * Lr[1] + rs[2] * Lr[2]);
+      const double w = pi * sqrt(kap * V.kappas[v] + 1e-12);
+      for (int a = 0; a < 3; ++a)
+        for (int c = 0; c < 3; ++c) acc[13 + 3 * a + c] += w * vd[a] * dir[c];
+      acc[22] += w * (1.0 - (dw[0] * vd[0] + dw[1] * vd[1] + dw[2] * vd[2]));
+    }
+    for (int k = 0; k < 9; ++k) acc[k] += pis * L.m[k];
+    double Lw[3];
+    mat3_vec(L, wt, Lw);
+    for (int c = 0; c < 3; ++c) acc[9 + c] += Lw[c];
+    acc[23] += R.row_masses[i];
+    acc[24] += 1.0;
+  }
+  for (int k = 0; k < 25; ++k) {
+    const double s = block_sum_1024(acc[k], sred);
+    if (tid == 0) tot[k] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    Mat3 Lt, S, U, Vm;
+    for (int k = 0; k < 9; ++k) { Lt.m[k] = tot[k]; S.m[k] = tot[13 + k]; }
+    Lt(0, 0) += eps_lift; Lt(1, 1) += eps_lift; Lt(2, 2) += eps_lift;
+    double sv[3];
+    svd3(S, U, sv, Vm);
+    Mat3 Vt = mat3_T(Vm);
+    Mat3 Rs = mat3_mul(U, Vt);
+    if (mat3_det(Rs) < 0.0) {
+      for (int r = 0; r < 3; ++r) U(r, 2) = -U(r, 2);  // U diag(1,1,-1) V^T
+      Rs = mat3_mul(U, Vt);
+    }
+    Mat3 Rd = mat3_mul(Rs, mat3_T(Rp));
+    double dr[3];
+    so3_log(Rd, dr);
+    const double lr[3] = {sv[0] + eps_lift, sv[1] + eps_lift, sv[2] + eps_lift};  // L_rot = diag(s + eps) (quirk Q5)
+    for (int k = 0; k < 9; ++k) { rec[GCS_VP_L_TRANS + k] = Lt.m[k]; rec[GCS_VP_L_ROT + k] = 0.0; rec[GCS_VP_R_SCATTER + k] = Rs.m[k]; }
+    for (int k = 0; k < 3; ++k) {
+      rec[GCS_VP_H_TRANS + k] = tot[9 + k];
+      rec[GCS_VP_L_ROT + 4 * k] = lr[k];
+      rec[GCS_VP_H_ROT + k] = lr[k] * dr[k];
+      rec[GCS_VP_SVD_S + k] = sv[k];
+      rec[GCS_VP_DELTA_ROT + k] = dr[k];
+    }
+    rec[GCS_VP_TRANS_COST] = tot[12]; rec[GCS_VP_ROT_COST] = tot[22];
+    rec[GCS_VP_SUM_ROW_MASS] = tot[23]; rec[GCS_VP_N_VALID_ROWS] = tot[24];
+    for (int k = GCS_VP_R_SCATTER + 9; k < GCS_VP_NREC; ++k) rec[k] = 0.0;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 22 * 22; idx += kBig) {
+    const int r = idx / 22, c = idx - r * 22;
+    double v = (r == c) ? eps_lift : 0.0;
+    if (r < 3 && c < 3) v = rec[GCS_VP_L_TRANS + 3 * r + c];
+    else if (r >= 3 && r < 6 && c >= 3 && c < 6) v = rec[GCS_VP_L_ROT + 3 * (r - 3) + (c - 3)];
+    L22[idx] = v;
+  }
+  if (tid < 22) h22[tid] = tid < 3 ? rec[GCS_VP_H_TRANS + tid] : (tid < 6 ? rec[GCS_VP_H_ROT + tid - 3] : 0.0);
+}
+
+// =================================================================================================
+// a14: map update
+// =================================================================================================
+struct UpdWs {
+  double* Lw;       // (N,9) world-frame precision of each measurement
+  double* thw;      // (N,3)
+  double* etw;      // (N,9)
+  long long* mtile; // (N) packed tile id of the world-frame mean
+  double* novelty;  // (N)
+  double* score;    // (N)
+  unsigned long long* pairs;  // (n_pairs_pow2) key<<32 | pair index, sorted
+  int* ins_idx;     // (T,k)
+  uint8_t* ins_new; // (T,k)
+  double* ins_w;    // (T,k)
+  int* ins_slot;    // (T,k)
+  int* n_ins;       // (T)
+  double* part;     // partial stats
+};
+
+// per-measurement world transform, tile id, novelty, insertion score (pipeline.py:1248-1256, :1331-1346)
+__global__ void __launch_bounds__(kBig) upd_prepare_kernel(gcs_meas_batch B, int N, gcs_assoc_result R, double p0, double p1,
+                                                           double p2, double r0, double r1, double r2,
+                                                           gcs_map_update_cfg cfg, UpdWs W) {
+  __shared__ double sred[32];
+  const int tid = threadIdx.x;
+  const double rv[3] = {r0, r1, r2}, tt[3] = {p0, p1, p2};
+  const Mat3 Rm = so3_exp(rv);
+  const Mat3 Rt = mat3_T(Rm);
+  double nv = 0.0;
+  for (int i = tid; i < N; i += kBig) nv += B.valid[i] ? 1.0 : 0.0;
+  const double denom = fmax(block_sum_1024(nv, sred), cfg.eps_mass);
+  for (int i = tid; i < N; i += kBig) {
+    Mat3 L;
+    load_mat3(B.Lambdas + 9 * i, L);
+    Mat3 Lw = mat3_mul(mat3_mul(Rm, L), Rt);
+    Mat3 Lr = L;
+    Lr(0, 0) += cfg.eps_lift; Lr(1, 1) += cfg.eps_lift; Lr(2, 2) += cfg.eps_lift;
+    const double th[3] = {B.thetas[3 * i], B.thetas[3 * i + 1], B.thetas[3 * i + 2]};
+    double mub[3], muw[3], thw[3];
+    mat3_solve(Lr, th, mub);
+    mat3_vec(Rm, mub, muw);
+    for (int k = 0; k < 3; ++k) muw[k] += tt[k];
+    mat3_vec(Lw, muw, thw);
+    for (int k = 0; k < 9; ++k) W.Lw[9 * i + k] = Lw.m[k];
+    for (int k = 0; k < 3; ++k) W.thw[3 * i + k] = thw[k];
+    for (int b = 0; b < 3; ++b) {
+      const double e[3] = {B.etas[9 * i + 3 * b], B.etas[9 * i + 3 * b + 1], B.etas[9 * i + 3 * b + 2]};
+      double ew[3];
+      mat3_vec(Rm, e, ew);
+      for (int k = 0; k < 3; ++k) W.etw[9 * i + 3 * b + k] = ew[k];
+    }
+    long long c[3];
+    tile_cell(muw, fmax(cfg.h_tile, 1e-12), c);
+    W.mtile[i] = pack_tile_id(c[0], c[1], c[2]);
+    const double v = B.valid[i] ? 1.0 : 0.0;
+    const double nov = fmax(v / denom - R.row_masses[i], 0.0);
+    W.novelty[i] = nov;
+    W.score[i] = nov * B.weights[i] - (1.0 - v) * 1e6;
+  }
+}
+
+// Sort all (measurement, candidate) pairs by target (active tile, slot); pair index is the tie-break, so every
+// target's contributions are added in pair order: deterministic, no floating atomics.
+__global__ void __launch_bounds__(kBig) upd_sort_pairs_kernel(gcs_meas_batch B, int N, int K, gcs_assoc_result R, TileList T,
+                                                              int m_tile, int n_pow2, unsigned long long* __restrict__ out) {
+  extern __shared__ unsigned long long sp[];
+  const int n_pairs = N * K;
+  for (int p = threadIdx.x; p < n_pow2; p += kBig) {
+    unsigned long long key = 0xffffffffull;
+    if (p < n_pairs) {
+      const int i = p / K;
+      if (B.valid[i]) {
+        const long long tid = R.candidate_tile_ids[p];
+        int a = -1;
+        for (int q = 0; q < T.n; ++q)
+          if (T.id[q] == tid) { a = q; break; }
+        const long long slot = R.candidate_slots[p];
+        if (a >= 0 && slot >= 0 && slot < m_tile) key = (unsigned long long)a * (unsigned long long)m_tile + (unsigned long long)slot;
+      }
+    }
+    sp[p] = (key << 32) | (unsigned long long)(unsigned)p;
+  }
+  for (int size = 2; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n_pow2 >> 1); t += kBig) {
+        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const unsigned long long x = sp[lo], y = sp[hi];
+        if ((y < x) == up) { sp[lo] = y; sp[hi] = x; }
+      }
+    }
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < n_pow2; p += kBig) out[p] = sp[p];
+}
+
+// one thread per sorted position; segment heads fold their segment into the tile slot (primitive_map.py:1037-1123)
+__global__ void __launch_bounds__(256) upd_fuse_kernel(gcs_atlas A, TileList T, gcs_meas_batch B, int K, gcs_assoc_result R,
+                                                       UpdWs W, int n_pow2, gcs_map_update_cfg cfg,
+                                                       double* __restrict__ part) {
+  __shared__ double sred[8];
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  double fused_mass = 0.0;
+  if (q < n_pow2) {
+    const unsigned long long e = W.pairs[q];
+    const unsigned key = (unsigned)(e >> 32);
+    const bool head = key != 0xffffffffu && (q == 0 || (unsigned)(W.pairs[q - 1] >> 32) != key);
+    if (head) {
+      const int a = (int)(key / (unsigned)A.m_tile), slot = (int)(key % (unsigned)A.m_tile);
+      const int64_t o = (int64_t)T.index[a] * A.m_tile + slot;
+      double dL[9], dth[3], det[9], dw = 0, drs = 0, dcam = 0, dlid = 0, dacc[3] = {0, 0, 0}, dden = 0;
+      for (int k = 0; k < 9; ++k) { dL[k] = 0; det[k] = 0; }
+      for (int k = 0; k < 3; ++k) dth[k] = 0;
+      for (int j = q; j < n_pow2; ++j) {
+        const unsigned long long ej = W.pairs[j];
+        if ((unsigned)(ej >> 32) != key) break;
+        const int p = (int)(unsigned)(ej & 0xffffffffull);
+        const int i = p / K;
+        const double r = R.responsibilities[p];
+        const double wm = B.weights[i];
+        for (int k = 0; k < 9; ++k) { dL[k] += r * W.Lw[9 * i + k]; det[k] += r * W.etw[9 * i + k]; }
+        for (int k = 0; k < 3; ++k) dth[k] += r * W.thw[3 * i + k];
+        dw += r * wm; drs += r;
+        const double wc = r * wm * (B.sources[i] == 0 ? 1.0 : 0.0), wl = r * wm * (B.sources[i] == 1 ? 1.0 : 0.0);
+        dcam += wc; dlid += wl; dden += wc;
+        for (int k = 0; k < 3; ++k) dacc[k] += fmin(fmax(B.colors[3 * i + k], 0.0), 1.0) * wc;
+        fused_mass += wm * r;
+      }
+      for (int k = 0; k < 9; ++k) { A.Lambdas[9 * o + k] += dL[k]; A.etas[9 * o + k] += det[k]; }
+      for (int k = 0; k < 3; ++k) { A.thetas[3 * o + k] += dth[k]; A.rgb_cam_accum[3 * o + k] += dacc[k]; }
+      A.weights[o] += dw; A.cam_mass[o] += dcam; A.lidar_mass[o] += dlid; A.rgb_cam_denom[o] += dden;
+      if (drs > 0.0) { A.last_supported_scan_seq[o] = cfg.scan_seq; A.last_update_scan_seq[o] = cfg.scan_seq; }
+      if (!cfg.strict_tile_state) A.timestamps[o] = cfg.timestamp;
+    }
+  }
+  double s = warp_sum(fused_mass);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int g = 0; g < 8; ++g) t += sred[g];
+    part[blockIdx.x] = t;
+  }
+}
+
+// quirk Q7: every fuse call stamps `timestamps` at ALL slot numbers of its block in the tile it was called for
+__global__ void upd_stamp_strict_kernel(gcs_atlas A, TileList T, gcs_assoc_result R, int n_pairs, double ts) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  const long long slot = R.candidate_slots[p];
+  if (slot < 0 || slot >= A.m_tile) return;
+  for (int a = 0; a < T.n; ++a) A.timestamps[(int64_t)T.index[a] * A.m_tile + slot] = ts;
+}
+// n_fused of one fuse call = number of distinct slot numbers in its block (:1155), summed over blocks x tiles
+__global__ void __launch_bounds__(kBig) upd_block_unique_kernel(gcs_assoc_result R, int N, int K, int block_rows,
+                                                                int* __restrict__ out_unique) {
+  __shared__ unsigned long long s[4096];
+  __shared__ int cnt;
+  const int b = blockIdx.x;
+  const int n = block_rows * K;
+  int np = 1;
+  while (np < n) np <<= 1;
+  for (int e = threadIdx.x; e < np; e += kBig) {
+    unsigned long long x = ~0ull;
+    if (e < n) {
+      int row = b * block_rows + e / K;
+      if (row > N - 1) row = N - 1;  // rows past N are clipped to the last row (:578-579)
+      x = (unsigned long long)R.candidate_slots[row * K + (e % K)];
+    }
+    s[e] = x;
+  }
+  if (threadIdx.x == 0) cnt = 0;
+  cta_bitonic_sort_u64(s, np);
+  int local = 0;
+  for (int e = threadIdx.x; e < n; e += kBig)
+    if (e == 0 || s[e] != s[e - 1]) ++local;
+  if (local) atomicAdd(&cnt, local);
+  __syncthreads();
+  if (threadIdx.x == 0) out_unique[b] = cnt;
+}
+
+// rgb of every slot of the active tiles after fusion (:1100-1107)
+__global__ void __launch_bounds__(256) upd_rgb_sweep_kernel(gcs_atlas A, TileList T, double eps_mass) {
+  const int a = blockIdx.y;
+  const int64_t base = (int64_t)T.index[a] * A.m_tile;
+  for (int s = blockIdx.x * 256 + threadIdx.x; s < A.m_tile; s += gridDim.x * 256) {
+    const int64_t o = base + s;
+    const bool has = A.cam_mass[o] > 0.0;
+    const double den = fmax(A.rgb_cam_denom[o], eps_mass);
+    for (int k = 0; k < 3; ++k) {
+      const double est = fmin(fmax(A.rgb_cam_accum[3 * o + k] / den, 0.0), 1.0);
+      const double v = has ? est : 0.5;
+      A.rgb[3 * o + k] = v;
+      A.colors[3 * o + k] = v;
+    }
+  }
+}
+
+// per active tile: which measurements to insert and which slots to evict (pipeline.py:1348-1366, primitive_map.py:837-855)
+__global__ void __launch_bounds__(kBig) upd_insert_select_kernel(gcs_atlas A, TileList T, gcs_meas_batch B, int N, UpdWs W,
+                                                                 gcs_map_update_cfg cfg) {
+  __shared__ SelectSmem sm;
+  __shared__ int s_any;
+  const int a = blockIdx.x, tid = threadIdx.x, k = cfg.k_insert_tile;
+  const long long my_id = T.id[a];
+  auto score_t = [&](int i) -> double { return (W.mtile[i] == my_id) ? W.score[i] : -1e30; };
+  auto key1 = [&](int i) -> unsigned long long { return f64_orderable(-score_t(i)); };
+  cta_select_k(N, k, key1, sm.out, sm.hist, sm.scan);
+  if (tid == 0) s_any = 0;
+  __syncthreads();
+  int idx = 0;
+  bool in_t = false, vnew = false;
+  double w_ins = 0.0;
+  if (tid < k) {
+    idx = sm.out[tid].idx;
+    in_t = W.mtile[idx] == my_id;
+    vnew = in_t && (score_t(idx) > -1e20);
+    w_ins = in_t ? W.novelty[idx] * B.weights[idx] : 0.0;
+    if (vnew) atomicOr(&s_any, 1);
+  }
+  __syncthreads();
+  if (tid < k) {
+    if (!s_any) vnew = true;  // zero-mass placeholders keep the insert count fixed (:1355, quirk Q6)
+    W.ins_idx[a * k + tid] = idx;
+    W.ins_new[a * k + tid] = vnew ? 1 : 0;
+    W.ins_w[a * k + tid] = w_ins;
+  }
+  __syncthreads();
+  // eviction targets: k lowest retention, empty slots first
+  const int64_t base = (int64_t)T.index[a] * A.m_tile;
+  auto key2 = [&](int s) -> unsigned long long {
+    const int64_t o = base + s;
+    double keyv = -INFINITY;
+    if (A.valid[o]) {
+      long long dt = cfg.scan_seq - A.last_supported_scan_seq[o];
+      if (dt < 0) dt = 0;
+      keyv = A.weights[o] * exp(-cfg.recency_decay_lambda * (double)dt);
+    }
+    return f64_orderable(keyv);
+  };
+  cta_select_k(A.m_tile, k, key2, sm.out, sm.hist, sm.scan);
+  if (tid < k) W.ins_slot[a * k + tid] = sm.out[tid].idx;
+  if (tid == 0) {
+    int n = 0;
+    double mass = 0.0;
+    for (int j = 0; j < k; ++j) { n += W.ins_new[a * k + j]; mass += W.ins_w[a * k + j]; }
+    W.n_ins[a] = n;
+    // p95 of the insert masses of this tile: ascending rank int(0.95 k)
+    int r95 = (int)(0.95 * (double)k);
+    if (r95 > k - 1) r95 = k - 1;
+    double p95 = 0.0;
+    for (int j = 0; j < k; ++j) {
+      const double x = W.ins_w[a * k + j];
+      int less = 0, eq = 0;
+      for (int m = 0; m < k; ++m) { const double y = W.ins_w[a * k + m]; less += (y < x); eq += (y == x); }
+      if (less <= r95 && r95 < less + eq) { p95 = x; break; }
+    }
+    W.part[64 + 2 * a] = mass;
+    W.part[64 + 2 * a + 1] = p95;
+  }
+}
+
+__global__ void upd_insert_apply_kernel(gcs_atlas A, TileList T, gcs_meas_batch B, UpdWs W, gcs_map_update_cfg cfg,
+                                        long long* __restrict__ out_ids, int* __restrict__ out_slots) {
+  const int a = blockIdx.x, j = threadIdx.x, k = cfg.k_insert_tile;
+  if (j >= k) return;
+  long long base_id = cfg.next_global_id;
+  for (int q = 0; q < a; ++q) base_id += W.n_ins[q];
+  int prefix = 0;
+  for (int m = 0; m <= j; ++m) prefix += W.ins_new[a * k + m];
+  const bool doit = W.ins_new[a * k + j] != 0;
+  const int slot = W.ins_slot[a * k + j];
+  const long long nid = doit ? base_id + (prefix - 1) : -1;
+  out_ids[a * k + j] = nid;
+  out_slots[a * k + j] = slot;
+  if (!doit) return;
+  const int i = W.ins_idx[a * k + j];
+  const int64_t o = (int64_t)T.index[a] * A.m_tile + slot;
+  const double w = W.ins_w[a * k + j];
+  for (int c = 0; c < 9; ++c) { A.Lambdas[9 * o + c] = W.Lw[9 * i + c]; A.etas[9 * o + c] = W.etw[9 * i + c]; }
+  const bool is_cam = B.sources[i] == 0, is_lid = B.sources[i] == 1;
+  const double cam = is_cam ? w : 0.0;
+  for (int c = 0; c < 3; ++c) {
+    A.thetas[3 * o + c] = W.thw[3 * i + c];
+    const double col = B.colors[3 * i + c];
+    const double rgbn = (cam > 0.0) ? fmin(fmax(col, 0.0), 1.0) : 0.5;
+    A.colors[3 * o + c] = rgbn; A.rgb[3 * o + c] = rgbn;
+    A.rgb_cam_accum[3 * o + c] = col * cam;
+  }
+  A.weights[o] = w; A.timestamps[o] = cfg.timestamp; A.created_timestamps[o] = cfg.timestamp;
+  A.last_supported_scan_seq[o] = cfg.scan_seq; A.last_update_scan_seq[o] = cfg.scan_seq;
+  A.primitive_ids[o] = nid; A.valid[o] = 1;
+  A.cam_mass[o] = cam; A.lidar_mass[o] = is_lid ? w : 0.0; A.rgb_cam_denom[o] = cam;
+}
+
+// cull (w < threshold) then forget (w *= gamma) over the active tiles  (primitive_map.py:1175-1384)
+__global__ void __launch_bounds__(256) upd_maintain_kernel(gcs_atlas A, TileList T, double thr, double gamma,
+                                                           double* __restrict__ part) {
+  __shared__ double sred[3][8];
+  const int a = blockIdx.y;
+  const int64_t base = (int64_t)T.index[a] * A.m_tile;
+  double n_cull = 0, m_cull = 0, n_valid = 0;
+  for (int s = blockIdx.x * 256 + threadIdx.x; s < A.m_tile; s += gridDim.x * 256) {
+    const int64_t o = base + s;
+    const double w = A.weights[o];
+    if (A.valid[o]) {
+      if (w < thr) { A.valid[o] = 0; n_cull += 1.0; m_cull += w; }
+      else n_valid += 1.0;
+    }
+    A.weights[o] = gamma * w;
+  }
+  double v3[3] = {n_cull, m_cull, n_valid};
+  for (int k = 0; k < 3; ++k) {
+    double r = warp_sum(v3[k]);
+    if ((threadIdx.x & 31) == 0) sred[k][threadIdx.x >> 5] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int g = 0; g < 8; ++g) s += sred[threadIdx.x][g];
+    part[((int64_t)a * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = s;
+  }
+}
+
+__global__ void upd_stats_kernel(UpdWs W, const double* __restrict__ fuse_part, int n_fuse_parts,
+                                 const int* __restrict__ blk_unique, int n_blocks, const double* __restrict__ maint_part,
+                                 int maint_blocks, int n_tiles, int k_ins, gcs_map_update_cfg cfg, double* __restrict__ stats) {
+  if (threadIdx.x != 0) return;
+  double fm = 0.0;
+  for (int c = 0; c < n_fuse_parts; ++c) fm += fuse_part[c];
+  long long uq = 0;
+  for (int b = 0; b < n_blocks; ++b) uq += blk_unique[b];
+  double im = 0.0, p95 = 0.0, nc = 0.0, mc = 0.0;
+  long long ni = 0;
+  for (int a = 0; a < n_tiles; ++a) {
+    im += W.part[64 + 2 * a];
+    p95 = fmax(p95, W.part[64 + 2 * a + 1]);
+    ni += W.n_ins[a];
+    double tv = 0.0;
+    for (int b = 0; b < maint_blocks; ++b) {
+      nc += maint_part[((int64_t)a * maint_blocks + b) * 3];
+      mc += maint_part[((int64_t)a * maint_blocks + b) * 3 + 1];
+      tv += maint_part[((int64_t)a * maint_blocks + b) * 3 + 2];
+    }
+    if (a < 16) stats[GCS_MU_TILE_COUNT0 + a] = tv;
+  }
+  stats[GCS_MU_FUSED_COUNT] = (double)(uq * n_tiles);
+  stats[GCS_MU_FUSED_MASS] = fm;
+  stats[GCS_MU_INSERT_COUNT] = (double)ni;
+  stats[GCS_MU_INSERT_MASS] = im;
+  stats[GCS_MU_INSERT_MASS_P95] = p95;
+  stats[GCS_MU_EVICTED_COUNT] = nc;
+  stats[GCS_MU_EVICTED_MASS] = mc;
+  stats[GCS_MU_NEXT_GLOBAL_ID] = (double)(cfg.next_global_id + ni);
+}
+
+}  // namespace gcs
+
+using namespace gcs;
+
+static int64_t cdivm(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+static int check_atlas(gcs_ctx* ctx, const gcs_atlas* a, const char* who) {
+  GCS_REQUIRE(ctx, a && a->Lambdas && a->thetas && a->etas && a->weights && a->timestamps && a->created_timestamps &&
+                       a->last_supported_scan_seq && a->last_update_scan_seq && a->primitive_ids && a->valid && a->colors &&
+                       a->cam_mass && a->lidar_mass && a->rgb_cam_accum && a->rgb_cam_denom && a->rgb,
+              "%s: atlas pointer is NULL", who);
+  GCS_REQUIRE(ctx, a->m_tile >= 1 && a->n_tiles_cap >= 1, "%s: bad atlas shape", who);
+  return GCS_OK;
+}
+static int make_tile_list(gcs_ctx* ctx, const gcs_atlas* a, const int32_t* idx, const int64_t* ids, int n, bool allow_missing,
+                          TileList* T, const char* who) {
+  GCS_REQUIRE(ctx, idx && n >= 1 && n <= 16, "%s: n_tiles=%d not in [1,16]", who, n);
+  T->n = n;
+  for (int i = 0; i < 16; ++i) { T->index[i] = -1; T->id[i] = 0; }
+  for (int i = 0; i < n; ++i) {
+    GCS_REQUIRE(ctx, idx[i] < a->n_tiles_cap, "%s: tile index %d out of range", who, idx[i]);
+    GCS_REQUIRE(ctx, allow_missing || idx[i] >= 0, "%s: tile %d missing from the pool", who, i);
+    T->index[i] = idx[i];
+    if (ids) T->id[i] = ids[i];
+  }
+  return GCS_OK;
+}
+static int check_view(gcs_ctx* ctx, const gcs_map_view* v, const char* who) {
+  GCS_REQUIRE(ctx, v && v->candidate_tile_ids && v->candidate_slots && v->valid && v->positions && v->covariances &&
+                       v->directions && v->kappas && v->weights && v->primitive_ids && v->last_supported_scan_seq && v->etas &&
+                       v->colors, "%s: view pointer is NULL", who);
+  return GCS_OK;
+}
+static int check_assoc(gcs_ctx* ctx, const gcs_assoc_result* r, const char* who) {
+  GCS_REQUIRE(ctx, r && r->responsibilities && r->candidate_pool_indices && r->candidate_tile_ids && r->candidate_slots &&
+                       r->row_masses && r->cost_matrix, "%s: association pointer is NULL", who);
+  return GCS_OK;
+}
+static int check_mbatch(gcs_ctx* ctx, const gcs_meas_batch* b, const char* who) {
+  GCS_REQUIRE(ctx, b && b->Lambdas && b->thetas && b->etas && b->weights && b->sources && b->source_indices && b->valid &&
+                       b->timestamps && b->colors, "%s: measurement batch pointer is NULL", who);
+  return GCS_OK;
+}
+
+extern "C" {
+
+int gcs_map_recency_inflate(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int32_t* tile_index, int32_t n_tiles,
+                            int64_t scan_seq, double lam, double min_scale, double* stats) {
+  if (!ctx) return GCS_EINVAL;
+  GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = check_atlas(ctx, atlas, "map_recency_inflate");
+  if (rc) return rc;
+  TileList T;
+  rc = make_tile_list(ctx, atlas, tile_index, nullptr, n_tiles, true, &T, "map_recency_inflate");
+  if (rc) return rc;
+  GCS_REQUIRE(ctx, stats != nullptr, "map_recency_inflate: stats is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = (int)(cdivm(atlas->m_tile, 256) < 64 ? cdivm(atlas->m_tile, 256) : 64);
+  rc = gcs_ws_reserve(ctx, (uint64_t)n_tiles * blocks * 3 * 8);
+  if (rc) return rc;
+  double* part = (double*)ctx->ws;
+  gcs_timing_begin(ctx, st);
+  recency_inflate_kernel<<<dim3(blocks, n_tiles), 256, 0, st>>>(*atlas, T, scan_seq, lam, min_scale, part);
+  gcs_timing_end(ctx, st);
+  GCS_LAUNCH_CHECK(ctx);
+  sum_parts_kernel<<<1, 32, 0, st>>>(part, n_tiles * blocks, 3, stats, 4);
+  GCS_LAUNCH_CHECK(ctx);
+  return GCS_OK;
+}
+
+int gcs_extract_atlas_map_view(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int32_t* tile_index,
+                               const int64_t* tile_ids, int32_t n_tiles, int32_t m_tile_view, double eps_lift,
+                               double eps_mass, const gcs_map_view* view, int32_t* out_n_valid) {
+  if (!ctx) return GCS_EINVAL;
+  GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = check_atlas(ctx, atlas, "extract_atlas_map_view");
+  if (rc) return rc;
+  GCS_REQUIRE(ctx, m_tile_view > 0, "extract_atlas_map_view: m_tile_view must be > 0, got %d", m_tile_view);
+  GCS_REQUIRE(ctx, m_tile_view <= 1024 && m_tile_view <= atlas->m_tile, "extract_atlas_map_view: m_tile_view=%d exceeds 1024 or m_tile", m_tile_view);
+  rc = check_view(ctx, view, "extract_atlas_map_view");
+  if (rc) return rc;
+  GCS_REQUIRE(ctx, tile_ids && out_n_valid, "extract_atlas_map_view: NULL pointer");
+  TileList T;
+  rc = make_tile_list(ctx, atlas, tile_index, tile_ids, n_tiles, true, &T, "extract_atlas_map_view");
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  GCS_CHECK_CUDA(ctx, cudaMemsetAsync(out_n_valid, 0, sizeof(int32_t), st));
+  gcs_timing_begin(ctx, st);
+  map_view_kernel<<<n_tiles, kBig, 0, st>>>(*atlas, T, m_tile_view, eps_lift, eps_mass, *view, out_n_valid);
+  gcs_timing_end(ctx, st);
+  GCS_LAUNCH_CHECK(ctx);
+  return GCS_OK;
+}
+
+int gcs_associate_primitives_ot(gcs_ctx* ctx, void* stream, const gcs_meas_batch* batch, const gcs_map_view* view,
+                                const int64_t* view_tile_ids, int32_t n_tiles, int32_t m_tile_view,
+                                const gcs_assoc_cfg* cfg, const gcs_assoc_result* out, double* cert) {
+  if (!ctx) return GCS_EINVAL;
+  GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = check_mbatch(ctx, batch, "associate_primitives_ot");
+  if (rc) return rc;
+  rc = check_view(ctx, view, "associate_primitives_ot");
+  if (rc) return rc;
+  rc = check_assoc(ctx, out, "associate_primitives_ot");
+  if (rc) return rc;
+  GCS_REQUIRE(ctx, cfg && cert && view_tile_ids, "associate_primitives_ot: NULL pointer");
+  GCS_REQUIRE(ctx, cfg->k_assoc == 8, "associate_primitives_ot: k_assoc=%d (this build instantiates K_ASSOC=8)", cfg->k_assoc);
+  GCS_REQUIRE(ctx, n_tiles >= 1 && n_tiles <= 16 && m_tile_view >= cfg->k_assoc, "associate_primitives_ot: bad view shape");
+  const int N = batch->n_feat + batch->n_surfel;
+  GCS_REQUIRE(ctx, N >= 1 && N <= 2048, "associate_primitives_ot: N_total=%d exceeds the single-CTA Sinkhorn budget 2048", N);
+  GCS_REQUIRE(ctx, cfg->r_stencil_xy >= 0 && cfg->r_stencil_xy <= 2 && cfg->r_stencil_z >= 0 && cfg->r_stencil_z <= 1,
+              "associate_primitives_ot: stencil radius out of range");
+  // stencil offsets in the reference's order: z slab outer, sorted axial disk inner (tiling.py:171-186)
+  int dq[64], dr[64], dz[64], n_st = 0;
+  const int rr = cfg->r_stencil_xy;
+  for (int z = -cfg->r_stencil_z; z <= cfg->r_stencil_z; ++z)
+    for (int q = -rr; q <= rr; ++q) {
+      const int r_min = (-rr > -q - rr) ? -rr : -q - rr, r_max = (rr < -q + rr) ? rr : -q + rr;
+      for (int r = r_min; r <= r_max; ++r) { dq[n_st] = q; dr[n_st] = r; dz[n_st] = z; ++n_st; }
+    }
+  TileList T;
+  T.n = n_tiles;
+  for (int i = 0; i < 16; ++i) { T.index[i] = i; T.id[i] = i < n_tiles ? view_tile_ids[i] : 0; }
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_pos = take((size_t)N * 3 * 8), o_dir = take((size_t)N * 3 * 8), o_kap = take((size_t)N * 8),
+               o_st = take((size_t)N * n_st), o_off = take(3 * 64 * 4), o_brow = take((size_t)N * 8 * 8);
+  rc = gcs_ws_reserve(ctx, off);
+  if (rc) return rc;
+  char* ws = (char*)ctx->ws;
+  AssocWs W;
+  W.mpos = (double*)(ws + o_pos); W.mdir = (double*)(ws + o_dir); W.mkap = (double*)(ws + o_kap); W.stencil = (int8_t*)(ws + o_st);
+  int* d_off = (int*)(ws + o_off);
+  int h_off[3 * 64];
+  for (int i = 0; i < 64; ++i) { h_off[i] = dq[i < n_st ? i : 0]; h_off[64 + i] = dr[i < n_st ? i : 0]; h_off[128 + i] = dz[i < n_st ? i : 0]; }
+  GCS_CHECK_CUDA(ctx, cudaMemcpyAsync(d_off, h_off, sizeof(h_off), cudaMemcpyHostToDevice, st));
+  assoc_prepare_kernel<<<(N + 127) / 128, 128, 0, st>>>(*batch, N, T, *cfg, n_st, d_off, d_off + 64, d_off + 128, W);
+  GCS_LAUNCH_CHECK(ctx);
+  gcs_timing_begin(ctx, st);
+  assoc_topk_kernel<8><<<(unsigned)cdivm((int64_t)N * 32, 256), 256, 0, st>>>(*batch, N, *view, m_tile_view, n_st, W, *cfg, *out);
+  gcs_timing_end(ctx, st);
+  GCS_LAUNCH_CHECK(ctx);
+  assoc_sinkhorn_kernel<8><<<1, kBig, 0, st>>>(*batch, N, *view, W, *cfg, *out, cert, (double*)(ws + o_brow));
+  GCS_LAUNCH_CHECK(ctx);
+  return GCS_OK;
+}
+
+int gcs_visual_pose_evidence(gcs_ctx* ctx, void* stream, const gcs_meas_batch* batch, const gcs_map_view* view,
+                             const gcs_assoc_result* assoc, int32_t k_assoc, const double* pose6, double eps_lift,
+                             double eps_mass, double* out_L22, double* out_h22, double* out_rec) {
+  if (!ctx) return GCS_EINVAL;
+  GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = check_mbatch(ctx, batch, "visual_pose_evidence");
+  if (rc) return rc;
+  rc = check_view(ctx, view, "visual_pose_evidence");
+  if (rc) return rc;
+  rc = check_assoc(ctx, assoc, "visual_pose_evidence");
+  if (rc) return rc;
+  GCS_REQUIRE(ctx, pose6 && out_L22 && out_h22 && out_rec, "visual_pose_evidence: NULL pointer");
+  GCS_REQUIRE(ctx, k_assoc == 8, "visual_pose_evidence: k_assoc=%d (this build instantiates K_ASSOC=8)", k_assoc);
+  const int N = batch->n_feat + batch->n_surfel;
+  pose_evidence_kernel<8><<<1, kBig, 0, (cudaStream_t)stream>>>(*batch, N, *view, *assoc, pose6[0], pose6[1], pose6[2], pose6[3],
+                                                                pose6[4], pose6[5], eps_lift, eps_mass, out_L22, out_h22, out_rec);
+  GCS_LAUNCH_CHECK(ctx);
+  return GCS_OK;
+}
+
+int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int32_t* tile_index, const int64_t* tile_ids,
+                   int32_t n_tiles, const gcs_meas_batch* batch, const gcs_assoc_result* assoc, const double* pose6,
+                   const gcs_map_update_cfg* cfg, int64_t* out_new_ids, int32_t* out_insert_slots, double* stats) {
+  if (!ctx) return GCS_EINVAL;
+  GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = check_atlas(ctx, atlas, "map_update");
+  if (rc) return rc;
+  rc = check_mbatch(ctx, batch, "map_update");
+  if (rc) return rc;
+  rc = check_assoc(ctx, assoc, "map_update");
+  if (rc) return rc;
+  GCS_REQUIRE(ctx, tile_ids && pose6 && cfg && out_new_ids && out_insert_slots && stats, "map_update: NULL pointer");
+  TileList T;
+  rc = make_tile_list(ctx, atlas, tile_index, tile_ids, n_tiles, false, &T, "map_update");
+  if (rc) return rc;
+  const int N = batch->n_feat + batch->n_surfel, K = cfg->k_assoc, k_ins = cfg->k_insert_tile;
+  GCS_REQUIRE(ctx, K >= 1 && k_ins >= 1 && k_ins <= 1024 && k_ins <= N && k_ins <= atlas->m_tile, "map_update: bad k_assoc/k_insert_tile");
+  GCS_REQUIRE(ctx, (int64_t)n_tiles * atlas->m_tile < 0xffffffffll, "map_update: active tiles x m_tile overflow the 32-bit target key");
+  const int n_pairs = N * K;
+  int n_pow2 = 1;
+  while (n_pow2 < n_pairs) n_pow2 <<= 1;
+  GCS_REQUIRE(ctx, n_pow2 <= 16384, "map_update: N_total*K_ASSOC=%d exceeds the in-CTA sort budget 16384", n_pairs);
+  const int block_rows = cfg->assoc_block_size > 0 ? cfg->assoc_block_size : 256;
+  GCS_REQUIRE(ctx, block_rows * K <= 4096, "map_update: assoc_block_size*K_ASSOC exceeds 4096");
+  const int n_blocks = (N + block_rows - 1) / block_rows;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int sweep_blocks = (int)(cdivm(atlas->m_tile, 256) < 64 ? cdivm(atlas->m_tile, 256) : 64);
+  const int fuse_blocks = n_pow2 / 256 > 0 ? n_pow2 / 256 : 1;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_Lw = take((size_t)N * 72), o_thw = take((size_t)N * 24), o_etw = take((size_t)N * 72), o_mt = take((size_t)N * 8),
+               o_nov = take((size_t)N * 8), o_sc = take((size_t)N * 8), o_pairs = take((size_t)n_pow2 * 8),
+               o_ii = take((size_t)n_tiles * k_ins * 4), o_in = take((size_t)n_tiles * k_ins), o_iw = take((size_t)n_tiles * k_ins * 8),
+               o_is = take((size_t)n_tiles * k_ins * 4), o_ni = take(16 * 4), o_part = take(128 * 8),
+               o_fpart = take((size_t)fuse_blocks * 8), o_uq = take((size_t)n_blocks * 4),
+               o_mpart = take((size_t)n_tiles * sweep_blocks * 3 * 8);
+  rc = gcs_ws_reserve(ctx, off);
+  if (rc) return rc;
+  char* ws = (char*)ctx->ws;
+  UpdWs W;
+  W.Lw = (double*)(ws + o_Lw); W.thw = (double*)(ws + o_thw); W.etw = (double*)(ws + o_etw); W.mtile = (long long*)(ws + o_mt);
+  W.novelty = (double*)(ws + o_nov); W.score = (double*)(ws + o_sc); W.pairs = (unsigned long long*)(ws + o_pairs);
+  W.ins_idx = (int*)(ws + o_ii); W.ins_new = (uint8_t*)(ws + o_in); W.ins_w = (double*)(ws + o_iw); W.ins_slot = (int*)(ws + o_is);
+  W.n_ins = (int*)(ws + o_ni); W.part = (double*)(ws + o_part);
+  double* fpart = (double*)(ws + o_fpart);
+  int* uq = (int*)(ws + o_uq);
+  double* mpart = (double*)(ws + o_mpart);
+
+  upd_prepare_kernel<<<1, kBig, 0, st>>>(*batch, N, *assoc, pose6[0], pose6[1], pose6[2], pose6[3], pose6[4], pose6[5], *cfg, W);
+  GCS_LAUNCH_CHECK(ctx);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCS_CHECK_CUDA(ctx, cudaFuncSetAttribute(upd_sort_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    attr_set = true;
+  }
+  upd_sort_pairs_kernel<<<1, kBig, (size_t)n_pow2 * 8, st>>>(*batch, N, K, *assoc, T, atlas->m_tile, n_pow2, W.pairs);
+  GCS_LAUNCH_CHECK(ctx);
+  gcs_timing_begin(ctx, st);
+  upd_fuse_kernel<<<fuse_blocks, 256, 0, st>>>(*atlas, T, *batch, K, *assoc, W, n_pow2, *cfg, fpart);
+  gcs_timing_end(ctx, st);
+  GCS_LAUNCH_CHECK(ctx);
+  if (cfg->strict_tile_state) {
+    upd_stamp_strict_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(*atlas, T, *assoc, n_pairs, cfg->timestamp);
+    GCS_LAUNCH_CHECK(ctx);
+  }
+  upd_block_unique_kernel<<<n_blocks, kBig, 0, st>>>(*assoc, N, K, block_rows, uq);
+  GCS_LAUNCH_CHECK(ctx);
+  upd_rgb_sweep_kernel<<<dim3(sweep_blocks, n_tiles), 256, 0, st>>>(*atlas, T, cfg->eps_mass);
+  GCS_LAUNCH_CHECK(ctx);
+  upd_insert_select_kernel<<<n_tiles, kBig, 0, st>>>(*atlas, T, *batch, N, W, *cfg);
+  GCS_LAUNCH_CHECK(ctx);
+  upd_insert_apply_kernel<<<n_tiles, ((k_ins + 31) / 32) * 32, 0, st>>>(*atlas, T, *batch, W, *cfg, (long long*)out_new_ids, out_insert_slots);
+  GCS_LAUNCH_CHECK(ctx);
+  upd_maintain_kernel<<<dim3(sweep_blocks, n_tiles), 256, 0, st>>>(*atlas, T, cfg->cull_weight_threshold, cfg->forgetting_factor, mpart);
+  GCS_LAUNCH_CHECK(ctx);
+  upd_stats_kernel<<<1, 32, 0, st>>>(W, fpart, fuse_blocks, uq, n_blocks, mpart, sweep_blocks, n_tiles, k_ins, *cfg, stats);
+  GCS_LAUNCH_CHECK(ctx);
+  return GCS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,454 @@
+// gcs_prims_surfel.cu -- LiDAR surfel extraction (a10) and MeasurementBatch builders.
+//
+//   S1 surfel_center      weighted centre of the unmasked points (two-level fixed-order reduction)
+//   S2 surfel_cell_key    MA-hex 3-D cell of every point: floor in float64 exactly as hex_cell_3d_batch, Python-style mod
+//   S3 surfel_rank_*      stable rank of every point inside its cell ("the 32 lowest original indices per cell"):
+//                         per-chunk ordered counting with warp match + a per-cell exclusive scan over chunks.
+//                         Equivalent to the reference's stable argsort by (masked, cell) without sorting anything.
+//   S4 surfel_fit         one thread per cell: weighted centroid / covariance, Jacobi eigh, tangent basis, Wishart-
+//                         regularised precision, vMF kappa
+//   S5 surfel_select      valid cells in ascending cell order -> first n_surfel slots of the LiDAR slice (info form)
+#include "gcs_common.cuh"
+
+namespace gcs {
+
+constexpr int kSurfThreads = 256;
+
+struct SurfelGeom {
+  int nc1, nc2, ncz, n_cells, max_occ, min_points;
+  double h;
+};
+
+__device__ __forceinline__ bool surfel_point_ok(const double* p) {
+  // jnp.all(jnp.abs(points) < 0.1 * GC_NONFINITE_SENTINEL)   (lidar_surfel_extraction.py:259-262); NaN -> false
+  return (fabs(p[0]) < 1e5) && (fabs(p[1]) < 1e5) && (fabs(p[2]) < 1e5);
+}
+
+// ---- S1 ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSurfThreads) surfel_center_partial_kernel(const double* __restrict__ pts,
+                                                                             const double* __restrict__ w, int64_t n,
+                                                                             int64_t per_block, double* __restrict__ part) {
+  __shared__ double sred[4][kSurfThreads / 32];
+  const int64_t i0 = (int64_t)blockIdx.x * per_block;
+  const int64_t i1 = (i0 + per_block < n) ? i0 + per_block : n;
+  double a[4] = {0, 0, 0, 0};
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += kSurfThreads) {
+    const double p[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    const double we = surfel_point_ok(p) ? w[i] : 0.0;
+    a[0] += p[0] * we; a[1] += p[1] * we; a[2] += p[2] * we; a[3] += we;
+  }
+  for (int k = 0; k < 4; ++k) {
+    double v = warp_sum(a[k]);
+    if ((threadIdx.x & 31) == 0) sred[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0.0;
+    for (int g = 0; g < kSurfThreads / 32; ++g) s += sred[threadIdx.x][g];
+    part[blockIdx.x * 4 + threadIdx.x] = s;
+  }
+}
+__global__ void surfel_center_final_kernel(const double* __restrict__ part, int n_parts, double eig_min,
+                                           double* __restrict__ center) {
+  if (threadIdx.x != 0) return;
+  double a[4] = {0, 0, 0, 0};
+  for (int c = 0; c < n_parts; ++c)
+    for (int k = 0; k < 4; ++k) a[k] += part[4 * c + k];
+  const double ws = a[3] + eig_min;
+  center[0] = a[0] / ws; center[1] = a[1] / ws; center[2] = a[2] / ws; center[3] = a[3];
+}
+
+// ---- S2 ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pymod(int a, int n) { int r = a % n; return r < 0 ? r + n : r; }
+
+__global__ void __launch_bounds__(kSurfThreads) surfel_cell_key_kernel(const double* __restrict__ pts,
+                                                                       const double* __restrict__ center, int64_t n,
+                                                                       SurfelGeom G, int32_t* __restrict__ key) {
+  const int64_t i = (int64_t)blockIdx.x * kSurfThreads + threadIdx.x;
+  if (i >= n) return;
+  const double p[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+  int k = G.n_cells;  // masked points sort last and never enter a bucket
+  if (surfel_point_ok(p)) {
+    const double x = p[0] - center[0], y = p[1] - center[1], z = p[2] - center[2];
+    const double s2 = x * 0.5 + y * (sqrt(3.0) * 0.5);  // ma_hex_web.py:233-235
+    const int c1 = (int)floor(x / G.h), c2 = (int)floor(s2 / G.h), cz = (int)floor(z / G.h);
+    k = pymod(c1, G.nc1) * (G.nc2 * G.ncz) + pymod(c2, G.nc2) * G.ncz + pymod(cz, G.ncz);
+  }
+  key[i] = k;
+}
+
+// ---- S3 ------------------------------------------------------------------------------------------------
+// One CTA walks a contiguous chunk of points in index order, 1024 at a time, warps strictly in order, keeping a
+// running per-cell count in shared memory.  local_rank[i] = number of earlier points of the same chunk in the
+// same cell.  hist[chunk][cell] = points of this chunk per cell.
+__global__ void __launch_bounds__(1024) surfel_rank_chunk_kernel(const int32_t* __restrict__ key, int64_t n,
+                                                                 int64_t per_chunk, int n_keys,
+                                                                 int32_t* __restrict__ local_rank,
+                                                                 int32_t* __restrict__ hist) {
+  extern __shared__ int s_cnt[];  // n_keys ints
+  for (int k = threadIdx.x; k < n_keys; k += 1024) s_cnt[k] = 0;
+  __syncthreads();
+  const int64_t i0 = (int64_t)blockIdx.x * per_chunk;
+  const int64_t i1 = (i0 + per_chunk < n) ? i0 + per_chunk : n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t base = i0; base < i1; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const bool on = i < i1;
+    const int k = on ? key[i] : -1 - (int)threadIdx.x;  // inactive lanes get unique negative keys
+    const unsigned peers = __match_any_sync(0xffffffffu, k);
+    const int before = __popc(peers & ((1u << lane) - 1u));
+    const bool leader = (lane == 31 - __clz(peers));  // highest lane of the group updates the counter
+    for (int wv = 0; wv < 32; ++wv) {
+      if (warp == wv && on) {
+        const int basecnt = s_cnt[k];
+        local_rank[i] = basecnt + before;
+        __syncwarp(peers);
+        if (leader) s_cnt[k] = basecnt + __popc(peers);
+      }
+      __syncthreads();
+    }
+  }
+  for (int k = threadIdx.x; k < n_keys; k += 1024) hist[(int64_t)blockIdx.x * n_keys + k] = s_cnt[k];
+}
+// per key: exclusive scan over chunks (in place) + total
+__global__ void surfel_rank_scan_kernel(int32_t* __restrict__ hist, int n_chunks, int n_keys, int32_t* __restrict__ total) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_keys) return;
+  int acc = 0;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int v = hist[(int64_t)c * n_keys + k];
+    hist[(int64_t)c * n_keys + k] = acc;
+    acc += v;
+  }
+  total[k] = acc;
+}
+__global__ void surfel_bucket_init_kernel(int32_t* __restrict__ bucket, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) bucket[i] = -1;
+}
+__global__ void __launch_bounds__(kSurfThreads) surfel_bucket_fill_kernel(const int32_t* __restrict__ key,
+                                                                          const int32_t* __restrict__ local_rank,
+                                                                          const int32_t* __restrict__ hist, int64_t n,
+                                                                          int64_t per_chunk, int n_keys, SurfelGeom G,
+                                                                          int32_t* __restrict__ bucket) {
+  const int64_t i = (int64_t)blockIdx.x * kSurfThreads + threadIdx.x;
+  if (i >= n) return;
+  const int k = key[i];
+  if (k >= G.n_cells) return;
+  const int chunk = (int)(i / per_chunk);
+  const int rank = hist[(int64_t)chunk * n_keys + k] + local_rank[i];
+  if (rank < G.max_occ) bucket[(int64_t)k * G.max_occ + rank] = (int32_t)i;
+}
+
+// ---- S4 ------------------------------------------------------------------------------------------------
+struct CellFit {  // per cell, SoA in workspace
+  double* centroid;  // (C,3) in original (un-centred) coordinates
+  double* Sigma;     // (C,9)
+  double* normal;    // (C,3)
+  double* kappa;     // (C)
+  double* w;         // (C)
+  double* t;         // (C)
+  uint8_t* valid;    // (C)
+};
+
+__device__ __forceinline__ void normalize3(double* v, double eps) {
+  const double inv = 1.0 / (sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) + eps);
+  v[0] *= inv; v[1] *= inv; v[2] *= inv;
+}
+
+__global__ void __launch_bounds__(128) surfel_fit_kernel(const double* __restrict__ pts, const double* __restrict__ ts,
+                                                         const double* __restrict__ w, const double* __restrict__ center,
+                                                         const int32_t* __restrict__ bucket,
+                                                         const int32_t* __restrict__ total, SurfelGeom G,
+                                                         gcs_surfel_cfg cfg, CellFit F) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= G.n_cells) return;
+  const double eps = 1e-12, eig_min = cfg.eig_min;
+  const int cnt = total[c] < G.max_occ ? total[c] : G.max_occ;
+  const double cx = center[0], cy = center[1], cz = center[2];
+  // pass 1: weighted centroid
+  double wsum = 0.0, m0 = 0.0, m1 = 0.0, m2 = 0.0, tsum = 0.0;
+  for (int o = 0; o < cnt; ++o) {
+    const int i = bucket[(int64_t)c * G.max_occ + o];
+    const double wi = w[i];
+    m0 += (pts[3 * i] - cx) * wi; m1 += (pts[3 * i + 1] - cy) * wi; m2 += (pts[3 * i + 2] - cz) * wi;
+    wsum += wi; tsum += ts[i];
+  }
+  const double w_sum = wsum + eps;
+  const double mu[3] = {m0 / w_sum, m1 / w_sum, m2 / w_sum};
+  // pass 2: weighted covariance.  Absent slots gather point 0 with weight 0 in the reference (lidar_surfel_extraction.py
+  // :115-121): they add exactly 0 to every weighted sum, so they are skipped here.
+  double s00 = 0, s01 = 0, s02 = 0, s11 = 0, s12 = 0, s22 = 0;
+  for (int o = 0; o < cnt; ++o) {
+    const int i = bucket[(int64_t)c * G.max_occ + o];
+    const double wi = w[i];
+    const double d0 = (pts[3 * i] - cx) - mu[0], d1 = (pts[3 * i + 1] - cy) - mu[1], d2 = (pts[3 * i + 2] - cz) - mu[2];
+    s00 += wi * d0 * d0; s01 += wi * d0 * d1; s02 += wi * d0 * d2;
+    s11 += wi * d1 * d1; s12 += wi * d1 * d2; s22 += wi * d2 * d2;
+  }
+  Mat3 cov;
+  cov(0, 0) = s00 / w_sum + eig_min; cov(1, 1) = s11 / w_sum + eig_min; cov(2, 2) = s22 / w_sum + eig_min;
+  cov(0, 1) = cov(1, 0) = s01 / w_sum; cov(0, 2) = cov(2, 0) = s02 / w_sum; cov(1, 2) = cov(2, 1) = s12 / w_sum;
+  double ev[3];
+  Mat3 V;
+  eigh3(cov, ev, V);
+  double nrm[3] = {V(0, 0), V(1, 0), V(2, 0)};
+  const double sgn = nrm[2] < 0.0 ? -1.0 : 1.0;  // deterministic sign (:130)
+  nrm[0] *= sgn; nrm[1] *= sgn; nrm[2] *= sgn;
+  normalize3(nrm, eps);
+  double nn[3] = {nrm[0], nrm[1], nrm[2]};
+  normalize3(nn, eps);  // _orthonormal_basis_from_normal normalises again (:72)
+  double e1[3];
+  if (fabs(nn[2]) < 0.9) { e1[0] = -nn[1]; e1[1] = nn[0]; e1[2] = 0.0; }
+  else { e1[0] = -nn[2]; e1[1] = 0.0; e1[2] = nn[0]; }
+  normalize3(e1, eps);
+  double e2[3] = {nn[1] * e1[2] - nn[2] * e1[1], nn[2] * e1[0] - nn[0] * e1[2], nn[0] * e1[1] - nn[1] * e1[0]};
+  normalize3(e2, eps);
+  // pass 3: in-plane spreads
+  double v1 = 0.0, v2 = 0.0;
+  for (int o = 0; o < cnt; ++o) {
+    const int i = bucket[(int64_t)c * G.max_occ + o];
+    const double wi = w[i];
+    const double d0 = (pts[3 * i] - cx) - mu[0], d1 = (pts[3 * i + 1] - cy) - mu[1], d2 = (pts[3 * i + 2] - cz) - mu[2];
+    const double p1 = d0 * e1[0] + d1 * e1[1] + d2 * e1[2];
+    const double p2 = d0 * e2[0] + d1 * e2[1] + d2 * e2[2];
+    v1 += wi * (p1 * p1); v2 += wi * (p2 * p2);
+  }
+  // An empty cell in the reference still gathers max_occ copies of point 0 with zero weight; all sums are 0 there too.
+  const double var_e1 = v1 / w_sum + cfg.sensor_noise_var_per_axis;
+  const double var_e2 = v2 / w_sum + cfg.sensor_noise_var_per_axis;
+  const double sig_perp = fmax(ev[0], eig_min);
+  const double var_perp = sig_perp + cfg.sensor_noise_var_per_axis;
+  const double D[3] = {fmax(var_e1, eig_min), fmax(var_e2, eig_min), fmax(var_perp, eig_min)};
+  const double* B[3] = {e1, e2, nrm};  // V = [e1 e2 normal]
+  Mat3 Sigma;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double a = 0.0;
+      for (int k = 0; k < 3; ++k) a += B[k][i] * D[k] * B[k][j];
+      Sigma(i, j) = a;
+    }
+  Mat3 S2;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) S2(i, j) = 0.5 * (Sigma(i, j) + Sigma(j, i)) + ((i == j) ? eig_min : 0.0);
+  Mat3 S3 = S2;
+  S3(0, 0) += eig_min; S3(1, 1) += eig_min; S3(2, 2) += eig_min;
+  Mat3 Lam = mat3_inv(S3);
+  const double psi = fmax(cfg.wishart_psi_scale, eps);
+  const double reg = cfg.wishart_nu / psi;
+  Mat3 Lreg;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      const double sym = 0.5 * (Lam(i, j) + Lam(j, i));
+      const double l1 = sym + ((i == j) ? reg : 0.0);
+      Lreg(i, j) = l1;
+    }
+  Mat3 Lreg2;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Lreg2(i, j) = 0.5 * (Lreg(i, j) + Lreg(j, i)) + ((i == j) ? eig_min : 0.0);
+  Mat3 Sr = mat3_inv(Lreg2);
+  double kap = cfg.kappa_main_scale / sqrt(fmax(sig_perp, eig_min));
+  kap = fmin(fmax(kap, cfg.kappa_min), cfg.kappa_max);
+  const bool valid = (cnt >= G.min_points) && (wsum > 0.0);
+  F.centroid[3 * c] = mu[0] + cx; F.centroid[3 * c + 1] = mu[1] + cy; F.centroid[3 * c + 2] = mu[2] + cz;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) F.Sigma[9 * c + 3 * i + j] = 0.5 * (Sr(i, j) + Sr(j, i)) + ((i == j) ? eig_min : 0.0);
+  F.normal[3 * c] = nrm[0]; F.normal[3 * c + 1] = nrm[1]; F.normal[3 * c + 2] = nrm[2];
+  F.kappa[c] = kap; F.w[c] = wsum; F.t[c] = tsum / w_sum;  // unweighted stamp sum / weight sum, as written (:160)
+  F.valid[c] = valid ? 1 : 0;
+}
+
+// ---- S5 ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) surfel_select_kernel(CellFit F, SurfelGeom G, gcs_meas_batch B, double eps_lift,
+                                                             int32_t* __restrict__ out_n_valid,
+                                                             const int32_t* __restrict__ total,
+                                                             int32_t* __restrict__ out_count) {
+  __shared__ int s_scan[1024];
+  __shared__ int s_total;
+  const int tid = threadIdx.x;
+  const int per = (G.n_cells + 1023) / 1024;
+  const int c0 = tid * per, c1 = (c0 + per < G.n_cells) ? c0 + per : G.n_cells;
+  int cnt = 0;
+  for (int c = c0; c < c1; ++c) cnt += F.valid[c];
+  s_scan[tid] = cnt;
+  __syncthreads();
+  if (tid == 0) {
+    int a = 0;
+    for (int t = 0; t < 1024; ++t) { const int v = s_scan[t]; s_scan[t] = a; a += v; }
+    s_total = a;
+  }
+  __syncthreads();
+  int slot = s_scan[tid];
+  for (int c = c0; c < c1; ++c) {
+    if (out_count) out_count[c] = total[c] < G.max_occ ? total[c] : G.max_occ;
+    if (!F.valid[c]) continue;
+    if (slot < B.n_surfel) {
+      const int r = B.n_feat + slot;
+      Mat3 S;
+      for (int k = 0; k < 9; ++k) S.m[k] = F.Sigma[9 * c + k];
+      S(0, 0) += eps_lift; S(1, 1) += eps_lift; S(2, 2) += eps_lift;
+      Mat3 L = mat3_inv(S);  // measurement_batch_add_lidar_surfels (measurement_batch.py:299-301)
+      const double mu[3] = {F.centroid[3 * c], F.centroid[3 * c + 1], F.centroid[3 * c + 2]};
+      double th[3];
+      mat3_vec(L, mu, th);
+      for (int k = 0; k < 9; ++k) B.Lambdas[9 * r + k] = L.m[k];
+      const double kap = F.kappa[c];
+      const double nz = fmin(fmax(F.normal[3 * c + 2], -1.0), 1.0);
+      const double g = 0.25 + 0.5 * (nz + 1.0) / 2.0;
+      for (int k = 0; k < 3; ++k) {
+        B.thetas[3 * r + k] = th[k];
+        B.etas[9 * r + k] = kap * F.normal[3 * c + k];
+        B.etas[9 * r + 3 + k] = 0.0;
+        B.etas[9 * r + 6 + k] = 0.0;
+        B.colors[3 * r + k] = g;
+      }
+      B.weights[r] = F.w[c];
+      B.sources[r] = 1;
+      B.source_indices[r] = slot;
+      B.valid[r] = 1;
+      B.timestamps[r] = F.t[c];
+    }
+    ++slot;
+  }
+  if (tid == 0) out_n_valid[0] = s_total < B.n_surfel ? s_total : B.n_surfel;
+}
+
+__global__ void camera_batch_kernel(const double* __restrict__ pos, const double* __restrict__ cov,
+                                    const double* __restrict__ dir, const double* __restrict__ kap,
+                                    const double* __restrict__ w, const double* __restrict__ ts,
+                                    const double* __restrict__ col, int n, double eps_lift, gcs_meas_batch B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Mat3 S;
+  for (int k = 0; k < 9; ++k) S.m[k] = cov[9 * i + k];
+  S(0, 0) += eps_lift; S(1, 1) += eps_lift; S(2, 2) += eps_lift;
+  Mat3 L = mat3_inv(S);
+  const double mu[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+  double th[3];
+  mat3_vec(L, mu, th);
+  for (int k = 0; k < 9; ++k) B.Lambdas[9 * i + k] = L.m[k];
+  for (int k = 0; k < 3; ++k) {
+    B.thetas[3 * i + k] = th[k];
+    B.etas[9 * i + k] = kap[i] * dir[3 * i + k];
+    B.etas[9 * i + 3 + k] = 0.0;
+    B.etas[9 * i + 6 + k] = 0.0;
+    B.colors[3 * i + k] = col ? fmin(fmax(col[3 * i + k], 0.0), 1.0) : 0.5;
+  }
+  B.weights[i] = w[i];
+  B.sources[i] = 0;
+  B.source_indices[i] = i;
+  B.valid[i] = 1;
+  B.timestamps[i] = ts[i];
+}
+
+}  // namespace gcs
+
+using namespace gcs;
+
+static int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+static int check_batch(gcs_ctx* ctx, const gcs_meas_batch* b, const char* who) {
+  GCS_REQUIRE(ctx, b && b->Lambdas && b->thetas && b->etas && b->weights && b->sources && b->source_indices && b->valid &&
+                       b->timestamps && b->colors, "%s: measurement batch pointer is NULL", who);
+  GCS_REQUIRE(ctx, b->n_feat >= 0 && b->n_surfel >= 0 && b->n_feat + b->n_surfel >= 1, "%s: bad batch budget", who);
+  return GCS_OK;
+}
+
+extern "C" {
+
+int gcs_batch_from_camera_splats(gcs_ctx* ctx, void* stream, const double* positions, const double* covariances,
+                                 const double* directions, const double* kappas, const double* weights,
+                                 const double* timestamps, const double* colors, int32_t n, double eps_lift,
+                                 const gcs_meas_batch* batch) {
+  if (!ctx) return GCS_EINVAL;
+  GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = check_batch(ctx, batch, "batch_from_camera_splats");
+  if (rc) return rc;
+  GCS_REQUIRE(ctx, n >= 0, "batch_from_camera_splats: n=%d", n);
+  const int nv = n < batch->n_feat ? n : batch->n_feat;  // truncate to the N_FEAT budget
+  if (nv == 0) return GCS_OK;
+  GCS_REQUIRE(ctx, positions && covariances && directions && kappas && weights && timestamps, "batch_from_camera_splats: NULL input");
+  camera_batch_kernel<<<(nv + 127) / 128, 128, 0, (cudaStream_t)stream>>>(positions, covariances, directions, kappas, weights,
+                                                                          timestamps, colors, nv, eps_lift, *batch);
+  GCS_LAUNCH_CHECK(ctx);
+  return GCS_OK;
+}
+
+int gcs_extract_lidar_surfels(gcs_ctx* ctx, void* stream, const double* pts, const double* timestamps,
+                              const double* weights, int64_t n, const gcs_surfel_cfg* cfg, const gcs_meas_batch* batch,
+                              int32_t* out_n_valid, int32_t* out_bucket, int32_t* out_count) {
+  if (!ctx) return GCS_EINVAL;
+  GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = check_batch(ctx, batch, "extract_lidar_surfels");
+  if (rc) return rc;
+  GCS_REQUIRE(ctx, cfg && pts && timestamps && weights && out_n_valid && n >= 1, "extract_lidar_surfels: bad args");
+  GCS_REQUIRE(ctx, cfg->n_cells_1 > 0 && cfg->n_cells_2 > 0 && cfg->n_cells_z > 0 && cfg->max_occupants > 0 &&
+                       cfg->max_occupants <= 1024, "extract_lidar_surfels: bad grid config");
+  GCS_REQUIRE(ctx, n < (1ll << 31), "extract_lidar_surfels: n too large for int32 point indices");
+  cudaStream_t st = (cudaStream_t)stream;
+  SurfelGeom G;
+  G.nc1 = cfg->n_cells_1; G.nc2 = cfg->n_cells_2; G.ncz = cfg->n_cells_z;
+  G.n_cells = G.nc1 * G.nc2 * G.ncz;
+  G.max_occ = cfg->max_occupants; G.min_points = cfg->min_points_per_voxel;
+  G.h = cfg->voxel_size_m > 1e-12 ? cfg->voxel_size_m : 1e-12;
+  const int n_keys = G.n_cells + 1;
+  GCS_REQUIRE(ctx, (size_t)n_keys * sizeof(int) <= 160 * 1024, "extract_lidar_surfels: %d cells exceed the shared-memory counter", G.n_cells);
+  int n_chunks = (int)cdiv(n, 1024);
+  const int max_chunks = ctx->sm_count * 2;
+  if (n_chunks > max_chunks) n_chunks = max_chunks;
+  const int64_t per_chunk = cdiv(cdiv(n, n_chunks), 1024) * 1024;
+  n_chunks = (int)cdiv(n, per_chunk);
+  const int n_cblocks = (int)(cdiv(n, 8192) < 256 ? cdiv(n, 8192) : 256);
+  const int64_t per_cblock = cdiv(n, n_cblocks);
+  // workspace carve-up
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_part = take((size_t)n_cblocks * 4 * 8), o_center = take(4 * 8), o_key = take((size_t)n * 4),
+               o_lrank = take((size_t)n * 4), o_hist = take((size_t)n_chunks * n_keys * 4), o_total = take((size_t)n_keys * 4),
+               o_bucket = take((size_t)G.n_cells * G.max_occ * 4), o_cen = take((size_t)G.n_cells * 3 * 8),
+               o_sig = take((size_t)G.n_cells * 9 * 8), o_nrm = take((size_t)G.n_cells * 3 * 8), o_kap = take((size_t)G.n_cells * 8),
+               o_w = take((size_t)G.n_cells * 8), o_t = take((size_t)G.n_cells * 8), o_val = take((size_t)G.n_cells);
+  rc = gcs_ws_reserve(ctx, off);
+  if (rc) return rc;
+  char* ws = (char*)ctx->ws;
+  double* part = (double*)(ws + o_part);
+  double* center = (double*)(ws + o_center);
+  int32_t* key = (int32_t*)(ws + o_key);
+  int32_t* lrank = (int32_t*)(ws + o_lrank);
+  int32_t* hist = (int32_t*)(ws + o_hist);
+  int32_t* total = (int32_t*)(ws + o_total);
+  int32_t* bucket = out_bucket ? out_bucket : (int32_t*)(ws + o_bucket);
+  CellFit F;
+  F.centroid = (double*)(ws + o_cen); F.Sigma = (double*)(ws + o_sig); F.normal = (double*)(ws + o_nrm);
+  F.kappa = (double*)(ws + o_kap); F.w = (double*)(ws + o_w); F.t = (double*)(ws + o_t); F.valid = (uint8_t*)(ws + o_val);
+
+  surfel_center_partial_kernel<<<n_cblocks, kSurfThreads, 0, st>>>(pts, weights, n, per_cblock, part);
+  GCS_LAUNCH_CHECK(ctx);
+  surfel_center_final_kernel<<<1, 32, 0, st>>>(part, n_cblocks, cfg->eig_min, center);
+  GCS_LAUNCH_CHECK(ctx);
+  surfel_cell_key_kernel<<<(unsigned)cdiv(n, kSurfThreads), kSurfThreads, 0, st>>>(pts, center, n, G, key);
+  GCS_LAUNCH_CHECK(ctx);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCS_CHECK_CUDA(ctx, cudaFuncSetAttribute(surfel_rank_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  surfel_rank_chunk_kernel<<<n_chunks, 1024, (size_t)n_keys * sizeof(int), st>>>(key, n, per_chunk, n_keys, lrank, hist);
+  GCS_LAUNCH_CHECK(ctx);
+  surfel_rank_scan_kernel<<<(n_keys + 255) / 256, 256, 0, st>>>(hist, n_chunks, n_keys, total);
+  GCS_LAUNCH_CHECK(ctx);
+  const int64_t nb = (int64_t)G.n_cells * G.max_occ;
+  surfel_bucket_init_kernel<<<(unsigned)cdiv(nb, 256), 256, 0, st>>>(bucket, nb);
+  GCS_LAUNCH_CHECK(ctx);
+  surfel_bucket_fill_kernel<<<(unsigned)cdiv(n, kSurfThreads), kSurfThreads, 0, st>>>(key, lrank, hist, n, per_chunk, n_keys, G, bucket);
+  GCS_LAUNCH_CHECK(ctx);
+  gcs_timing_begin(ctx, st);
+  surfel_fit_kernel<<<(G.n_cells + 127) / 128, 128, 0, st>>>(pts, timestamps, weights, center, bucket, total, G, *cfg, F);
+  gcs_timing_end(ctx, st);
+  GCS_LAUNCH_CHECK(ctx);
+  surfel_select_kernel<<<1, 1024, 0, st>>>(F, G, *batch, cfg->eps_lift, out_n_valid, total, out_count);
+  GCS_LAUNCH_CHECK(ctx);
+  return GCS_OK;
+}
+
+}  // extern "C"

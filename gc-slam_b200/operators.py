@@ -462,10 +462,13 @@ def map_update_from_scan(map_stats: MapBinStats, scan: ScanBinStats, pose_start_
     B = map_stats.N_dir.shape[0]
     m = map_stats._c()
     pose = _host_vec(pose_start_of_scan, 6)
+    # hold the (possibly re-laid-out) tensors until the call returns: ctypes only sees raw addresses
+    sN, ssd, sS, ssp, sspp = (scan.N.contiguous(), scan.s_dir.contiguous(), scan.S_dir_scatter.contiguous(),
+                              scan.sum_p.contiguous(), scan.sum_ppT.contiguous())
     io.ctx.check(io.ctx.lib.gcs_map_bin_update(
-        io.ctx.handle, io.stream(), C.byref(m), L.ptr(scan.N.contiguous()), L.ptr(scan.s_dir.contiguous()),
-        L.ptr(scan.S_dir_scatter.contiguous()), L.ptr(scan.sum_p.contiguous()), L.ptr(scan.sum_ppT.contiguous()), B,
+        io.ctx.handle, io.stream(), C.byref(m), L.ptr(sN), L.ptr(ssd), L.ptr(sS), L.ptr(ssp), L.ptr(sspp), B,
         _dptr(pose), 1 if planar_z else 0, float(forgetting_factor)))
+    del sN, ssd, sS, ssp, sspp
     return map_stats
 
 

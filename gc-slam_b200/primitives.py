@@ -1,0 +1,701 @@
+"""
+Primitive-family LiDAR evidence operators -- host-side mirror of the reference's Python interface
+(``fl/`` = fl_ws/src/fl_slam_poc/fl_slam_poc/ in whabacivch/GC-SLAM):
+
+  MeasurementBatch, measurement_batch_from_camera_splats, create_empty_measurement_batch
+                                     fl/backend/structures/measurement_batch.py:68-259
+  SurfelExtractionConfig, extract_lidar_surfels
+                                     fl/backend/operators/lidar_surfel_extraction.py:45-431
+  AtlasMap (device tile pool), AtlasMapView, extract_atlas_map_view, primitive_map_recency_inflate,
+  primitive_map_cull, primitive_map_forget
+                                     fl/backend/structures/primitive_map.py:98-1484
+  AssociationConfig, PrimitiveAssociationResult, associate_primitives_ot
+                                     fl/backend/operators/primitive_association.py:71-553
+  VisualPoseEvidenceResult, visual_pose_evidence
+                                     fl/backend/operators/visual_pose_evidence.py:50-436
+  map_update_step12b                 fl/backend/pipeline.py:1233-1447 (fuse x blocks x tiles, insert, cull, forget)
+  ma_hex_stencil_tile_ids, tile_ids_from_xyz_batch   fl/common/tiling.py:126-209 (host integer helpers)
+
+Every operator returns ``(result, CertBundle, ExpectedEffect)``; arrays are torch CUDA tensors.  All arithmetic on
+arrays happens in libgcs_b200.so; the host code here only marshals pointers and assembles certificates.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from enum import Enum
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import constants
+from .certs import (CertBundle, ComputeCert, ExpectedEffect, InfluenceCert, MapUpdateCert, OTCert, SupportCert)
+from .operators import _IO, _dptr, _host_vec
+
+F64 = torch.float64
+_vp, _i32, _i64, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+
+
+# --------------------------------------------------------------------------------------------------
+# C structs
+# --------------------------------------------------------------------------------------------------
+class CMeasBatch(C.Structure):
+    _fields_ = [(n, _vp) for n in ("Lambdas", "thetas", "etas", "weights", "sources", "source_indices", "valid",
+                                   "timestamps", "colors")] + [("n_feat", _i32), ("n_surfel", _i32)]
+
+
+class CSurfelCfg(C.Structure):
+    _fields_ = [(n, _i32) for n in ("n_cells_1", "n_cells_2", "n_cells_z", "max_occupants", "min_points_per_voxel")] + \
+               [(n, _dbl) for n in ("voxel_size_m", "sensor_noise_var_per_axis", "wishart_nu", "wishart_psi_scale",
+                                    "kappa_main_scale", "kappa_min", "kappa_max", "eig_min", "eps_lift")]
+
+
+_ATLAS_FIELDS = ("Lambdas", "thetas", "etas", "weights", "timestamps", "created_timestamps", "last_supported_scan_seq",
+                 "last_update_scan_seq", "primitive_ids", "valid", "colors", "cam_mass", "lidar_mass", "rgb_cam_accum",
+                 "rgb_cam_denom", "rgb")
+
+
+class CAtlas(C.Structure):
+    _fields_ = [(n, _vp) for n in _ATLAS_FIELDS] + [("m_tile", _i32), ("n_tiles_cap", _i32)]
+
+
+_VIEW_FIELDS = ("candidate_tile_ids", "candidate_slots", "valid", "positions", "covariances", "directions", "kappas",
+                "weights", "primitive_ids", "last_supported_scan_seq", "etas", "colors")
+
+
+class CMapView(C.Structure):
+    _fields_ = [(n, _vp) for n in _VIEW_FIELDS]
+
+
+class CAssocCfg(C.Structure):
+    _fields_ = [(n, _i32) for n in ("k_assoc", "k_sinkhorn", "r_stencil_xy", "r_stencil_z")] + \
+               [(n, _dbl) for n in ("beta", "epsilon", "tau_a", "tau_b", "eps_mass", "eps_lift", "h_tile",
+                                    "recency_decay_lambda")] + [("scan_seq", _i64)]
+
+
+class CAssocResult(C.Structure):
+    _fields_ = [(n, _vp) for n in ("responsibilities", "candidate_pool_indices", "candidate_tile_ids", "candidate_slots",
+                                   "row_masses", "cost_matrix")]
+
+
+class CMapUpdateCfg(C.Structure):
+    _fields_ = [(n, _i32) for n in ("k_insert_tile", "k_assoc", "assoc_block_size", "strict_tile_state")] + \
+               [(n, _dbl) for n in ("recency_decay_lambda", "eps_lift", "eps_mass", "h_tile", "cull_weight_threshold",
+                                    "forgetting_factor")] + [("scan_seq", _i64), ("next_global_id", _i64), ("timestamp", _dbl)]
+
+
+OT = dict(MARGINAL_A=0, MARGINAL_B=1, MASS_TOTAL=2, SUM_A=3, SUM_M=4, SUM_NOVEL=5, P95_A=6, NONZERO_A=7, B_RECENCY_P95=8,
+          ESS=9, TOTAL_COST=10, SUM_M2=11, NCERT=16)
+VP = dict(L_TRANS=0, H_TRANS=9, L_ROT=12, H_ROT=21, TRANS_COST=24, ROT_COST=25, SUM_ROW_MASS=26, N_VALID_ROWS=27, SVD_S=28,
+          DELTA_ROT=31, R_SCATTER=34, NREC=48)
+MU = dict(FUSED_COUNT=0, FUSED_MASS=1, INSERT_COUNT=2, INSERT_MASS=3, INSERT_MASS_P95=4, EVICTED_COUNT=5, EVICTED_MASS=6,
+          NEXT_GLOBAL_ID=7, TILE_COUNT0=8, NSTATS=24)
+
+_int = C.c_int
+L.register_prototypes({
+    "gcs_batch_from_camera_splats": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dbl, C.POINTER(CMeasBatch)]),
+    "gcs_extract_lidar_surfels": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(CSurfelCfg), C.POINTER(CMeasBatch), _vp, _vp, _vp]),
+    "gcs_map_recency_inflate": (_int, [_vp, _vp, C.POINTER(CAtlas), C.POINTER(_i32), _i32, _i64, _dbl, _dbl, _vp]),
+    "gcs_extract_atlas_map_view": (_int, [_vp, _vp, C.POINTER(CAtlas), C.POINTER(_i32), C.POINTER(_i64), _i32, _i32, _dbl, _dbl,
+                                          C.POINTER(CMapView), _vp]),
+    "gcs_associate_primitives_ot": (_int, [_vp, _vp, C.POINTER(CMeasBatch), C.POINTER(CMapView), C.POINTER(_i64), _i32, _i32,
+                                           C.POINTER(CAssocCfg), C.POINTER(CAssocResult), _vp]),
+    "gcs_visual_pose_evidence": (_int, [_vp, _vp, C.POINTER(CMeasBatch), C.POINTER(CMapView), C.POINTER(CAssocResult), _i32,
+                                        C.POINTER(_dbl), _dbl, _dbl, _vp, _vp, _vp]),
+    "gcs_map_update": (_int, [_vp, _vp, C.POINTER(CAtlas), C.POINTER(_i32), C.POINTER(_i64), _i32, C.POINTER(CMeasBatch),
+                              C.POINTER(CAssocResult), C.POINTER(_dbl), C.POINTER(CMapUpdateCfg), _vp, _vp, _vp]),
+})
+
+
+# --------------------------------------------------------------------------------------------------
+# tiling helpers (host integers; the reference also evaluates these on the host: fl/common/tiling.py)
+# --------------------------------------------------------------------------------------------------
+_BITS, _BIAS = 21, 1 << 20
+
+
+def tile_id_from_cell_3d(c1: int, c2: int, cz: int) -> int:
+    m = (1 << _BITS) - 1
+    return int((((int(c1) + _BIAS) & m) << (2 * _BITS)) | (((int(c2) + _BIAS) & m) << _BITS) | ((int(cz) + _BIAS) & m))
+
+
+def ma_hex_cell_3d_from_xyz(xyz, h_tile: float):
+    xyz = np.asarray(xyz, dtype=np.float64).ravel()
+    if xyz.shape[0] < 3:
+        raise ValueError(f"ma_hex_cell_3d_from_xyz: expected xyz (3,), got shape {xyz.shape}")
+    h = max(float(h_tile), 1e-12)
+    s1 = float(np.array([1.0, 0.0]) @ xyz[:2])
+    s2 = float(np.array([0.5, 0.5 * np.sqrt(3.0)]) @ xyz[:2])
+    return int(np.floor(s1 / h)), int(np.floor(s2 / h)), int(np.floor(float(xyz[2]) / h))
+
+
+def hex_disk_axial(radius: int):
+    r = int(radius)
+    out = [(q, rr) for q in range(-r, r + 1) for rr in range(max(-r, -q - r), min(r, -q + r) + 1)]
+    out.sort()
+    return out
+
+
+def ma_hex_stencil_tile_ids(center_xyz, h_tile: float = constants.GC_H_TILE, radius_xy: int = constants.GC_R_STENCIL_TILES_XY,
+                            radius_z: int = constants.GC_R_STENCIL_TILES_Z) -> List[int]:
+    c1, c2, cz = ma_hex_cell_3d_from_xyz(center_xyz, h_tile)
+    return [tile_id_from_cell_3d(c1 + dq, c2 + dr, cz + dz) for dz in range(-int(radius_z), int(radius_z) + 1)
+            for dq, dr in hex_disk_axial(radius_xy)]
+
+
+# --------------------------------------------------------------------------------------------------
+# MeasurementBatch
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class MeasurementBatch:
+    Lambdas: torch.Tensor
+    thetas: torch.Tensor
+    etas: torch.Tensor
+    weights: torch.Tensor
+    sources: torch.Tensor
+    source_indices: torch.Tensor
+    valid_mask: torch.Tensor  # uint8 on device (0/1)
+    timestamps: torch.Tensor
+    colors: torch.Tensor
+    n_feat: int
+    n_surfel: int
+    n_camera_valid: int
+    n_lidar_valid: int
+
+    @property
+    def n_total(self) -> int:
+        return self.n_feat + self.n_surfel
+
+    @property
+    def n_valid(self) -> int:
+        return self.n_camera_valid + self.n_lidar_valid
+
+    @property
+    def camera_slice(self) -> slice:
+        return slice(0, self.n_feat)
+
+    @property
+    def lidar_slice(self) -> slice:
+        return slice(self.n_feat, self.n_total)
+
+    def _c(self) -> CMeasBatch:
+        b = CMeasBatch()
+        b.Lambdas, b.thetas, b.etas, b.weights = L.ptr(self.Lambdas), L.ptr(self.thetas), L.ptr(self.etas), L.ptr(self.weights)
+        b.sources, b.source_indices, b.valid = L.ptr(self.sources), L.ptr(self.source_indices), L.ptr(self.valid_mask)
+        b.timestamps, b.colors, b.n_feat, b.n_surfel = L.ptr(self.timestamps), L.ptr(self.colors), self.n_feat, self.n_surfel
+        return b
+
+    def clone(self) -> "MeasurementBatch":
+        return MeasurementBatch(**{k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in self.__dict__.items()})
+
+
+def create_empty_measurement_batch(n_feat: int = constants.GC_N_FEAT, n_surfel: int = constants.GC_N_SURFEL, device=None
+                                   ) -> MeasurementBatch:
+    io = _IO(device)
+    n = n_feat + n_surfel
+    return MeasurementBatch(Lambdas=io.zeros(n, 3, 3), thetas=io.zeros(n, 3), etas=io.zeros(n, constants.GC_VMF_N_LOBES, 3),
+                            weights=io.zeros(n), sources=io.zeros(n, dtype=torch.int32),
+                            source_indices=io.zeros(n, dtype=torch.int32), valid_mask=io.zeros(n, dtype=torch.uint8),
+                            timestamps=io.zeros(n), colors=io.zeros(n, 3), n_feat=int(n_feat), n_surfel=int(n_surfel),
+                            n_camera_valid=0, n_lidar_valid=0)
+
+
+def measurement_batch_from_camera_splats(positions, covariances, directions, kappas, weights, timestamps, colors=None,
+                                         n_feat: int = constants.GC_N_FEAT, n_surfel: int = constants.GC_N_SURFEL,
+                                         eps_lift: float = constants.GC_EPS_LIFT) -> MeasurementBatch:
+    io = _IO()
+    b = create_empty_measurement_batch(n_feat, n_surfel)
+    pos = io.dev_in(positions, shape=(-1, 3))
+    n = pos.shape[0]
+    nv = min(n, n_feat)
+    if nv > 0:
+        cb = b._c()
+        # keep every staged tensor referenced until the call returns (ctypes only sees raw addresses)
+        cov, dirs = io.dev_in(covariances, shape=(-1, 3, 3)), io.dev_in(directions, shape=(-1, 3))
+        kap, wts, ts = io.dev_in(kappas, shape=(-1,)), io.dev_in(weights, shape=(-1,)), io.dev_in(timestamps, shape=(-1,))
+        col = io.dev_in(colors, shape=(-1, 3)) if colors is not None else None
+        io.ctx.check(io.ctx.lib.gcs_batch_from_camera_splats(
+            io.ctx.handle, io.stream(), L.ptr(pos), L.ptr(cov), L.ptr(dirs), L.ptr(kap), L.ptr(wts), L.ptr(ts), L.ptr(col), n,
+            float(eps_lift), C.byref(cb)))
+        del cov, dirs, kap, wts, ts, col
+    b.n_camera_valid = nv
+    return b
+
+
+# --------------------------------------------------------------------------------------------------
+# a10 surfel extraction
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class SurfelExtractionConfig:
+    n_surfel: int = constants.GC_N_SURFEL
+    n_feat: int = constants.GC_N_FEAT
+    voxel_size_m: float = 0.1
+    hex3d_num_cells_1: int = 32
+    hex3d_num_cells_2: int = 32
+    hex3d_num_cells_z: int = 8
+    hex3d_max_occupants: int = 32
+    min_points_per_voxel: int = 3
+    sensor_noise_var_per_axis: float = 1e-6
+    wishart_nu: float = 5.0
+    wishart_psi_scale: float = 0.1
+    kappa_main_scale: float = 10.0
+    kappa_min: float = 0.1
+    kappa_max: float = 100.0
+    eig_min: float = 1e-12
+    eps_lift: float = constants.GC_EPS_LIFT
+
+    def _c(self) -> CSurfelCfg:
+        return CSurfelCfg(self.hex3d_num_cells_1, self.hex3d_num_cells_2, self.hex3d_num_cells_z, self.hex3d_max_occupants,
+                          self.min_points_per_voxel, self.voxel_size_m, self.sensor_noise_var_per_axis, self.wishart_nu,
+                          self.wishart_psi_scale, self.kappa_main_scale, self.kappa_min, self.kappa_max, self.eig_min,
+                          self.eps_lift)
+
+
+def extract_lidar_surfels(points, timestamps, weights, config: Optional[SurfelExtractionConfig] = None,
+                          base_batch: Optional[MeasurementBatch] = None, chart_id: str = constants.GC_CHART_ID,
+                          anchor_id: str = "surfel_extraction", return_bucket: bool = False
+                          ) -> Tuple[MeasurementBatch, CertBundle, ExpectedEffect]:
+    if config is None:
+        config = SurfelExtractionConfig()
+    io = _IO()
+    pts = io.dev_in(points, shape=(-1, 3))
+    n = pts.shape[0]
+    t = io.dev_in(timestamps, shape=(-1,))
+    w = io.dev_in(weights, shape=(-1,))
+    if t.shape[0] != n or w.shape[0] != n:
+        raise ValueError("extract_lidar_surfels: points/timestamps/weights length mismatch")
+    batch = base_batch.clone() if base_batch is not None else create_empty_measurement_batch(config.n_feat, config.n_surfel)
+    if batch.n_surfel != config.n_surfel or batch.n_feat != config.n_feat:
+        raise ValueError("extract_lidar_surfels: base_batch budget differs from config")
+    n_cells = config.hex3d_num_cells_1 * config.hex3d_num_cells_2 * config.hex3d_num_cells_z
+    nv_d = io.zeros(1, dtype=torch.int32)
+    bucket = io.empty(n_cells, config.hex3d_max_occupants, dtype=torch.int32) if return_bucket else None
+    count = io.empty(n_cells, dtype=torch.int32) if return_bucket else None
+    cb, cc = batch._c(), config._c()
+    io.ctx.check(io.ctx.lib.gcs_extract_lidar_surfels(io.ctx.handle, io.stream(), L.ptr(pts), L.ptr(t), L.ptr(w), n, C.byref(cc),
+                                                      C.byref(cb), L.ptr(nv_d), L.ptr(bucket), L.ptr(count)))
+    n_use = int(io.host(nv_d)[0])
+    batch.n_lidar_valid = n_use
+    support_frac = float(n_use) / float(max(config.n_surfel, 1))
+    cert = CertBundle.create_approx(chart_id=chart_id, anchor_id=anchor_id,
+                                    triggers=["ma_hex3d_binning", "plane_fit_batched", "wishart_regularization"],
+                                    support=SupportCert(ess_total=float(n_use), support_frac=support_frac),
+                                    influence=InfluenceCert.identity(), compute=io.compute())
+    effect = ExpectedEffect("surfel_extraction", float(n_use), float(n_use))
+    if return_bucket:
+        batch._bucket, batch._bucket_count = bucket, count
+    return batch, cert, effect
+
+
+# --------------------------------------------------------------------------------------------------
+# a11 atlas: device tile pool
+# --------------------------------------------------------------------------------------------------
+_ATLAS_SHAPES = dict(Lambdas=(3, 3), thetas=(3,), etas=(constants.GC_VMF_N_LOBES, 3), weights=(), timestamps=(),
+                     created_timestamps=(), last_supported_scan_seq=(), last_update_scan_seq=(), primitive_ids=(), valid=(),
+                     colors=(3,), cam_mass=(), lidar_mass=(), rgb_cam_accum=(3,), rgb_cam_denom=(), rgb=(3,))
+_ATLAS_DTYPES = dict(last_supported_scan_seq=torch.int64, last_update_scan_seq=torch.int64, primitive_ids=torch.int64,
+                     valid=torch.uint8)
+_NP_NAME = dict(valid="valid_mask")
+
+
+class AtlasMap:
+    """
+    Atlas of primitive map tiles, resident in HBM: one (T_cap, M_TILE, ...) array per PrimitiveMapTile field
+    (15.6 MB per 50,000-slot tile) and a host dict tile_id -> pool row.  Mirrors AtlasMap / PrimitiveMapTile
+    (primitive_map.py:98-211); tiles are created on demand as the reference's fuse / insert do.
+    """
+
+    def __init__(self, m_tile: int = constants.GC_PRIMITIVE_MAP_MAX_SIZE, n_tiles_cap: int = 32, device=None):
+        io = _IO(device)
+        self.device = io.dev
+        self.m_tile, self.n_tiles_cap = int(m_tile), int(n_tiles_cap)
+        self.fields: Dict[str, torch.Tensor] = {}
+        for name in _ATLAS_FIELDS:
+            self.fields[name] = torch.zeros((self.n_tiles_cap, self.m_tile) + _ATLAS_SHAPES[name],
+                                            dtype=_ATLAS_DTYPES.get(name, F64), device=self.device)
+        self.fields["rgb"].fill_(0.5)
+        self.tiles: Dict[int, int] = {}       # tile_id -> pool row
+        self.next_global_id = 0
+        self.total_count = 0
+
+    @property
+    def n_tiles(self) -> int:
+        return len(self.tiles)
+
+    @property
+    def tile_ids(self) -> List[int]:
+        return list(self.tiles.keys())
+
+    def _c(self) -> CAtlas:
+        a = CAtlas()
+        for name in _ATLAS_FIELDS:
+            setattr(a, name, L.ptr(self.fields[name]))
+        a.m_tile, a.n_tiles_cap = self.m_tile, self.n_tiles_cap
+        return a
+
+    def ensure_tile(self, tile_id: int) -> int:
+        tile_id = int(tile_id)
+        if tile_id not in self.tiles:
+            if len(self.tiles) >= self.n_tiles_cap:
+                raise RuntimeError(f"AtlasMap pool is full ({self.n_tiles_cap} tiles); create it with a larger n_tiles_cap")
+            self.tiles[tile_id] = len(self.tiles)  # pool rows are zero-initialised = create_empty_tile
+        return self.tiles[tile_id]
+
+    def index_list(self, tile_ids, create: bool = False):
+        return [(self.ensure_tile(t) if create else self.tiles.get(int(t), -1)) for t in tile_ids]
+
+    def tile_count(self, tile_id: int) -> int:
+        row = self.tiles.get(int(tile_id))
+        return 0 if row is None else int(self.fields["valid"][row].sum().item())
+
+    def upload_tile(self, tile_id: int, tile: dict):
+        """Host NumPy tile (field names of PrimitiveMapTile) -> pool row."""
+        row = self.ensure_tile(tile_id)
+        for name in _ATLAS_FIELDS:
+            src = np.asarray(tile[_NP_NAME.get(name, name)])
+            t = torch.from_numpy(np.ascontiguousarray(src.astype(np.uint8) if name == "valid" else src))
+            self.fields[name][row].copy_(t.to(self.fields[name].dtype))
+
+    def download_tile(self, tile_id: int) -> dict:
+        row = self.tiles[int(tile_id)]
+        out = {"tile_id": int(tile_id)}
+        for name in _ATLAS_FIELDS:
+            a = self.fields[name][row].cpu().numpy()
+            out[_NP_NAME.get(name, name)] = a.astype(bool) if name == "valid" else a
+        out["count"] = int(out["valid_mask"].sum())
+        return out
+
+    @classmethod
+    def from_numpy(cls, atlas: dict, n_tiles_cap: Optional[int] = None, device=None) -> "AtlasMap":
+        cap = n_tiles_cap or max(8, len(atlas["tiles"]) + 8)
+        a = cls(m_tile=atlas["m_tile"], n_tiles_cap=cap, device=device)
+        for tid, t in atlas["tiles"].items():
+            a.upload_tile(tid, t)
+        a.next_global_id, a.total_count = int(atlas["next_global_id"]), int(atlas["total_count"])
+        return a
+
+
+def create_empty_atlas_map(m_tile: int = constants.GC_PRIMITIVE_MAP_MAX_SIZE, n_tiles_cap: int = 32) -> AtlasMap:
+    return AtlasMap(m_tile=m_tile, n_tiles_cap=n_tiles_cap)
+
+
+@dataclass
+class PrimitiveMapRecencyInflateStats:
+    staleness_inflation_strength: float
+    staleness_cov_inflation_trace: float
+    stale_precision_downscale_total: float
+
+
+def _i32arr(v):
+    return (_i32 * len(v))(*[int(x) for x in v])
+
+
+def _i64arr(v):
+    return (_i64 * len(v))(*[int(x) for x in v])
+
+
+def primitive_map_recency_inflate(atlas_map: AtlasMap, tile_ids: List[int], scan_seq: int,
+                                  recency_decay_lambda: float = constants.GC_RECENCY_DECAY_LAMBDA,
+                                  min_scale: float = constants.GC_RECENCY_MIN_SCALE, chart_id: str = constants.GC_CHART_ID,
+                                  anchor_id: str = "primitive_map_recency_inflate"):
+    """In place on the device pool (the reference rebuilds the tiles functionally); returns (atlas, cert, effect, stats)."""
+    io = _IO(atlas_map.device)
+    idx = atlas_map.index_list(tile_ids, create=False)
+    stats_d = io.zeros(4)
+    ca = atlas_map._c()
+    io.ctx.check(io.ctx.lib.gcs_map_recency_inflate(io.ctx.handle, io.stream(), C.byref(ca), _i32arr(idx), len(idx),
+                                                    int(scan_seq), float(recency_decay_lambda), float(min_scale), L.ptr(stats_d)))
+    s = io.host(stats_d)
+    stats = PrimitiveMapRecencyInflateStats(staleness_inflation_strength=float(s[0] / max(s[2], 1.0)),
+                                            staleness_cov_inflation_trace=float(s[1]),
+                                            stale_precision_downscale_total=float(s[0]))
+    cert = CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id, compute=io.compute())
+    return atlas_map, cert, ExpectedEffect("primitive_map_recency_inflate", float(s[2]), float(s[2])), stats
+
+
+@dataclass
+class AtlasMapView:
+    candidate_tile_ids: torch.Tensor
+    candidate_slots: torch.Tensor
+    valid_mask: torch.Tensor
+    tile_ids: List[int]
+    m_tile_view: int
+    positions: torch.Tensor
+    covariances: torch.Tensor
+    directions: torch.Tensor
+    kappas: torch.Tensor
+    weights: torch.Tensor
+    primitive_ids: torch.Tensor
+    last_supported_scan_seq: torch.Tensor
+    etas: torch.Tensor
+    colors: torch.Tensor
+    n_valid: int = 0
+
+    @property
+    def count(self) -> int:
+        return int(self.positions.shape[0])
+
+    def _c(self) -> CMapView:
+        v = CMapView()
+        v.candidate_tile_ids, v.candidate_slots, v.valid = L.ptr(self.candidate_tile_ids), L.ptr(self.candidate_slots), L.ptr(self.valid_mask)
+        v.positions, v.covariances, v.directions, v.kappas = L.ptr(self.positions), L.ptr(self.covariances), L.ptr(self.directions), L.ptr(self.kappas)
+        v.weights, v.primitive_ids, v.last_supported_scan_seq = L.ptr(self.weights), L.ptr(self.primitive_ids), L.ptr(self.last_supported_scan_seq)
+        v.etas, v.colors = L.ptr(self.etas), L.ptr(self.colors)
+        return v
+
+
+def extract_atlas_map_view(atlas_map: AtlasMap, tile_ids: List[int], m_tile_view: int, eps_lift: float = constants.GC_EPS_LIFT,
+                           eps_mass: float = constants.GC_EPS_MASS) -> AtlasMapView:
+    if m_tile_view <= 0:
+        raise ValueError(f"extract_atlas_map_view: m_tile_view must be > 0, got {m_tile_view}")
+    io = _IO(atlas_map.device)
+    P = len(tile_ids) * int(m_tile_view)
+    view = AtlasMapView(candidate_tile_ids=io.empty(P, dtype=torch.int64), candidate_slots=io.empty(P, dtype=torch.int32),
+                        valid_mask=io.empty(P, dtype=torch.uint8), tile_ids=[int(t) for t in tile_ids], m_tile_view=int(m_tile_view),
+                        positions=io.empty(P, 3), covariances=io.empty(P, 3, 3), directions=io.empty(P, 3), kappas=io.empty(P),
+                        weights=io.empty(P), primitive_ids=io.empty(P, dtype=torch.int64),
+                        last_supported_scan_seq=io.empty(P, dtype=torch.int64), etas=io.empty(P, constants.GC_VMF_N_LOBES, 3),
+                        colors=io.empty(P, 3))
+    nv = io.zeros(1, dtype=torch.int32)
+    ca, cv = atlas_map._c(), view._c()
+    idx = atlas_map.index_list(tile_ids, create=False)
+    io.ctx.check(io.ctx.lib.gcs_extract_atlas_map_view(io.ctx.handle, io.stream(), C.byref(ca), _i32arr(idx), _i64arr(tile_ids),
+                                                       len(tile_ids), int(m_tile_view), float(eps_lift), float(eps_mass),
+                                                       C.byref(cv), L.ptr(nv)))
+    view.n_valid = int(io.host(nv)[0])
+    return view
+
+
+# --------------------------------------------------------------------------------------------------
+# a12 association
+# --------------------------------------------------------------------------------------------------
+class MeasurementMassPolicy(Enum):
+    UNIFORM = "uniform"
+    WEIGHT_PROPORTIONAL = "weight_proportional"
+    FEATURE_CONFIDENCE = "feature_confidence"
+
+
+class MapMassPolicy(Enum):
+    UNIFORM = "uniform"
+    PRIMITIVE_MASS = "primitive_mass"
+    MASS_TEMPERED = "mass_tempered"
+
+
+@dataclass
+class AssociationConfig:
+    k_assoc: int = constants.GC_K_ASSOC
+    k_sinkhorn: int = constants.GC_K_SINKHORN
+    beta: float = 0.5
+    epsilon: float = 0.1
+    tau_a: float = 0.5
+    tau_b: float = 0.5
+    cost_subtract_row_min: bool = True
+    cost_scale_by_median: bool = False
+    a_policy: MeasurementMassPolicy = MeasurementMassPolicy.UNIFORM
+    b_policy: MapMassPolicy = MapMassPolicy.UNIFORM
+    eps_mass: float = constants.GC_EPS_MASS
+    h_tile: float = constants.GC_H_TILE
+    r_stencil_tiles_xy: int = constants.GC_R_STENCIL_TILES_XY
+    r_stencil_tiles_z: int = constants.GC_R_STENCIL_TILES_Z
+    scan_seq: int = 0
+    recency_decay_lambda: float = constants.GC_RECENCY_DECAY_LAMBDA
+
+
+@dataclass
+class PrimitiveAssociationResult:
+    responsibilities: torch.Tensor
+    candidate_pool_indices: torch.Tensor
+    candidate_tile_ids: torch.Tensor
+    candidate_slots: torch.Tensor
+    row_masses: torch.Tensor
+    cost_matrix: torch.Tensor
+
+    def _c(self) -> CAssocResult:
+        r = CAssocResult()
+        r.responsibilities, r.candidate_pool_indices = L.ptr(self.responsibilities), L.ptr(self.candidate_pool_indices)
+        r.candidate_tile_ids, r.candidate_slots = L.ptr(self.candidate_tile_ids), L.ptr(self.candidate_slots)
+        r.row_masses, r.cost_matrix = L.ptr(self.row_masses), L.ptr(self.cost_matrix)
+        return r
+
+
+def _empty_assoc(io, N, K):
+    return PrimitiveAssociationResult(responsibilities=io.zeros(N, K), candidate_pool_indices=io.zeros(N, K, dtype=torch.int32),
+                                      candidate_tile_ids=io.zeros(N, K, dtype=torch.int64),
+                                      candidate_slots=io.zeros(N, K, dtype=torch.int64), row_masses=io.zeros(N),
+                                      cost_matrix=io.zeros(N, K))
+
+
+def associate_primitives_ot(measurement_batch: MeasurementBatch, map_view: AtlasMapView, config: AssociationConfig = None,
+                            eps_lift: float = constants.GC_EPS_LIFT, eps_mass: float = constants.GC_EPS_MASS,
+                            chart_id: str = constants.GC_CHART_ID, anchor_id: str = "primitive_ot"
+                            ) -> Tuple[PrimitiveAssociationResult, CertBundle, ExpectedEffect]:
+    if config is None:
+        config = AssociationConfig()
+    if config.a_policy != MeasurementMassPolicy.UNIFORM:
+        if config.a_policy == MeasurementMassPolicy.WEIGHT_PROPORTIONAL:
+            raise ValueError("MeasurementMassPolicy.WEIGHT_PROPORTIONAL is not built in this release (pipeline uses UNIFORM)")
+        raise ValueError(f"Unsupported measurement mass policy: {config.a_policy}. Only UNIFORM and WEIGHT_PROPORTIONAL are implemented.")
+    if config.b_policy != MapMassPolicy.UNIFORM:
+        raise ValueError(f"Unsupported map mass policy: {config.b_policy}. Only UNIFORM is implemented.")
+    if not config.cost_subtract_row_min or config.cost_scale_by_median:
+        raise ValueError("associate_primitives_ot: only cost_subtract_row_min=True, cost_scale_by_median=False is built")
+    io = _IO(measurement_batch.Lambdas.device)
+    N, K = measurement_batch.n_total, int(config.k_assoc)
+    if measurement_batch.n_valid == 0 or map_view.n_valid == 0:
+        cert = CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id)
+        return _empty_assoc(io, N, K), cert, ExpectedEffect("primitive_association_ot", 0.0, 0.0)
+    res = _empty_assoc(io, N, K)
+    cfg = CAssocCfg(K, int(config.k_sinkhorn), int(config.r_stencil_tiles_xy), int(config.r_stencil_tiles_z), float(config.beta),
+                    float(config.epsilon), float(config.tau_a), float(config.tau_b), float(config.eps_mass), float(eps_lift),
+                    float(config.h_tile), float(config.recency_decay_lambda), int(config.scan_seq))
+    cert_d = io.zeros(OT["NCERT"])
+    cb, cv, cr = measurement_batch._c(), map_view._c(), res._c()
+    io.ctx.check(io.ctx.lib.gcs_associate_primitives_ot(io.ctx.handle, io.stream(), C.byref(cb), C.byref(cv),
+                                                        _i64arr(map_view.tile_ids), len(map_view.tile_ids),
+                                                        int(map_view.m_tile_view), C.byref(cfg), C.byref(cr), L.ptr(cert_d)))
+    c = io.host(cert_d)
+    tm = float(c[OT["MASS_TOTAL"]])
+    n_nonzero_a = int(c[OT["NONZERO_A"]])
+    compute = io.compute(alloc_bytes_est=int(N * K * 8 * 4), largest_tensor_shape=(int(N), int(K)), segment_sum_k=int(K),
+                         psd_projection_count=0, chol_solve_count=0)
+    cert = CertBundle.create_approx(
+        chart_id=chart_id, anchor_id=anchor_id, triggers=["sinkhorn_fixed_iter", "sinkhorn_unbalanced_kl_relax"],
+        frobenius_applied=False,
+        support=SupportCert(ess_total=float(c[OT["ESS"]]), support_frac=float(n_nonzero_a) / float(max(N, 1))),
+        influence=InfluenceCert.identity().with_overrides(mass_epsilon_ratio=float(config.eps_mass) / (tm + config.eps_mass)),
+        compute=compute)
+    b_val = 1.0 / float(K)
+    cert.ot = OTCert(marginal_defect_a=float(c[OT["MARGINAL_A"]]), marginal_defect_b=float(c[OT["MARGINAL_B"]]),
+                     transport_mass_total=tm, dual_gap_proxy=0.0, sum_a=float(c[OT["SUM_A"]]), sum_b=float(b_val * K),
+                     sum_m=float(c[OT["SUM_M"]]), sum_novel=float(c[OT["SUM_NOVEL"]]), p95_a=float(c[OT["P95_A"]]), p95_b=b_val,
+                     nonzero_a=n_nonzero_a, nonzero_b=int(K if b_val > config.eps_mass else 0), epsilon=float(config.epsilon),
+                     tau_a=float(config.tau_a), tau_b=float(config.tau_b), n_iters=int(config.k_sinkhorn),
+                     b_policy=str(config.b_policy.value), b_recency_decay_lambda=float(config.recency_decay_lambda),
+                     b_recency_p95=float(c[OT["B_RECENCY_P95"]]))
+    total_cost = float(c[OT["TOTAL_COST"]])
+    return res, cert, ExpectedEffect("primitive_association_ot", total_cost, total_cost)
+
+
+# --------------------------------------------------------------------------------------------------
+# a13 pose evidence
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class VisualPoseEvidenceResult:
+    L_pose: torch.Tensor
+    h_pose: torch.Tensor
+    L_trans: torch.Tensor
+    h_trans: torch.Tensor
+    L_rot: torch.Tensor
+    h_rot: torch.Tensor
+    total_weighted_cost: float
+    n_associations: int
+    mean_transported_mass: float
+
+
+def visual_pose_evidence(association_result: PrimitiveAssociationResult, measurement_batch: MeasurementBatch,
+                         map_view: AtlasMapView, belief_pred, eps_lift: float = constants.GC_EPS_LIFT,
+                         eps_mass: float = constants.GC_EPS_MASS, chart_id: str = constants.GC_CHART_ID,
+                         anchor_id: str = "visual_pose_evidence", z_lin_pose=None
+                         ) -> Tuple[VisualPoseEvidenceResult, CertBundle, ExpectedEffect]:
+    io = _IO(measurement_batch.Lambdas.device)
+    N_meas = measurement_batch.n_valid
+    N_assoc, K = association_result.responsibilities.shape
+    if N_meas == 0 or N_assoc == 0 or map_view.n_valid == 0:
+        res = VisualPoseEvidenceResult(L_pose=eps_lift * torch.eye(22, dtype=F64, device=io.dev), h_pose=io.zeros(22),
+                                       L_trans=io.zeros(3, 3), h_trans=io.zeros(3), L_rot=io.zeros(3, 3), h_rot=io.zeros(3),
+                                       total_weighted_cost=0.0, n_associations=0, mean_transported_mass=0.0)
+        return res, CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id), ExpectedEffect("visual_pose_evidence", 0.0, 0.0)
+    if z_lin_pose is not None:
+        pose = _host_vec(z_lin_pose.detach().cpu().numpy().ravel()[:6] if isinstance(z_lin_pose, torch.Tensor)
+                         else np.asarray(z_lin_pose, np.float64).ravel()[:6], 6)
+    elif hasattr(belief_pred, "mean_world_pose"):
+        pose = _host_vec(belief_pred.mean_world_pose(eps_lift=eps_lift), 6)
+    else:
+        pose = _host_vec(belief_pred, 6)
+    L22, h22, rec_d = io.empty(22, 22), io.empty(22), io.zeros(VP["NREC"])
+    cb, cv, cr = measurement_batch._c(), map_view._c(), association_result._c()
+    io.ctx.check(io.ctx.lib.gcs_visual_pose_evidence(io.ctx.handle, io.stream(), C.byref(cb), C.byref(cv), C.byref(cr), int(K),
+                                                     _dptr(pose), float(eps_lift), float(eps_mass), L.ptr(L22), L.ptr(h22), L.ptr(rec_d)))
+    r = io.host(rec_d)
+    n_rows = int(r[VP["N_VALID_ROWS"]])
+    total_cost = float(r[VP["TRANS_COST"]] + r[VP["ROT_COST"]])
+    res = VisualPoseEvidenceResult(L_pose=L22, h_pose=h22, L_trans=rec_d[0:9].reshape(3, 3), h_trans=rec_d[9:12],
+                                   L_rot=rec_d[12:21].reshape(3, 3), h_rot=rec_d[21:24], total_weighted_cost=total_cost,
+                                   n_associations=int(n_rows * K),
+                                   mean_transported_mass=float(r[VP["SUM_ROW_MASS"]] / max(n_rows, 1)))
+    cert = CertBundle.create_approx(
+        chart_id=chart_id, anchor_id=anchor_id, triggers=["linearization", "ot_soft_correspondence"], frobenius_applied=True,
+        support=SupportCert(ess_total=float(r[VP["SUM_ROW_MASS"]]), support_frac=float(n_rows) / float(max(N_meas, 1))),
+        influence=InfluenceCert.identity().with_overrides(lift_strength=eps_lift), compute=io.compute())
+    return res, cert, ExpectedEffect("visual_pose_evidence", total_cost, total_cost)
+
+
+# --------------------------------------------------------------------------------------------------
+# a14 map update (pipeline step 12b)
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class MapUpdateResult:
+    atlas_map: AtlasMap
+    n_fused: int
+    n_inserted: int
+    n_culled: int
+    new_ids: torch.Tensor       # (n_tiles, k_insert) int64, -1 where nothing was inserted
+    insert_slots: torch.Tensor  # (n_tiles, k_insert) int32
+    tile_counts: List[int]
+
+
+def map_update_step12b(atlas_map: AtlasMap, measurement_batch: MeasurementBatch, association_result: PrimitiveAssociationResult,
+                       active_tile_ids: List[int], z_t, scan_seq: int, timestamp: float,
+                       k_insert_tile: int = constants.GC_K_INSERT_TILE,
+                       recency_decay_lambda: float = constants.GC_RECENCY_DECAY_LAMBDA, eps_lift: float = constants.GC_EPS_LIFT,
+                       eps_mass: float = constants.GC_EPS_MASS, h_tile: float = constants.GC_H_TILE,
+                       cull_weight_threshold: float = constants.GC_PRIMITIVE_CULL_WEIGHT_THRESHOLD,
+                       forgetting_factor: float = constants.GC_PRIMITIVE_FORGETTING_FACTOR,
+                       assoc_block_size: int = constants.GC_ASSOC_BLOCK_SIZE, strict_tile_state: bool = True,
+                       inflate_stats: Optional[PrimitiveMapRecencyInflateStats] = None,
+                       chart_id: str = constants.GC_CHART_ID) -> Tuple[MapUpdateResult, CertBundle, ExpectedEffect]:
+    """
+    Whole primitive-map update of one scan in one call (in place on the device pool): rigid pushforward of the
+    measurement batch with z_t, PoE fuse into the associated slots, novelty-driven insertion into the lowest-retention
+    slots, cull, forget.  Replaces the Python loops of pipeline.py:1258-1447 (6 blocks x 7 tiles of primitive_map_fuse,
+    7 x insert_masked, 7 x cull / forget).
+    """
+    io = _IO(atlas_map.device)
+    n_exist_before = len([t for t in active_tile_ids if int(t) in atlas_map.tiles])
+    idx = atlas_map.index_list(active_tile_ids, create=True)
+    nt = len(active_tile_ids)
+    K = association_result.responsibilities.shape[1]
+    cfg = CMapUpdateCfg(int(k_insert_tile), int(K), int(assoc_block_size), 1 if strict_tile_state else 0,
+                        float(recency_decay_lambda), float(eps_lift), float(eps_mass), float(h_tile),
+                        float(cull_weight_threshold), float(forgetting_factor), int(scan_seq), int(atlas_map.next_global_id),
+                        float(timestamp))
+    new_ids = io.empty(nt, int(k_insert_tile), dtype=torch.int64)
+    slots = io.empty(nt, int(k_insert_tile), dtype=torch.int32)
+    stats_d = io.zeros(MU["NSTATS"])
+    ca, cb, cr = atlas_map._c(), measurement_batch._c(), association_result._c()
+    pose = _host_vec(z_t, 6)
+    io.ctx.check(io.ctx.lib.gcs_map_update(io.ctx.handle, io.stream(), C.byref(ca), _i32arr(idx), _i64arr(active_tile_ids), nt,
+                                           C.byref(cb), C.byref(cr), _dptr(pose), C.byref(cfg), L.ptr(new_ids), L.ptr(slots),
+                                           L.ptr(stats_d)))
+    s = io.host(stats_d)
+    n_ins, n_cull = int(s[MU["INSERT_COUNT"]]), int(s[MU["EVICTED_COUNT"]])
+    atlas_map.next_global_id = int(s[MU["NEXT_GLOBAL_ID"]])
+    atlas_map.total_count = atlas_map.total_count + n_ins - n_cull
+    result = MapUpdateResult(atlas_map=atlas_map, n_fused=int(s[MU["FUSED_COUNT"]]), n_inserted=n_ins, n_culled=n_cull,
+                             new_ids=new_ids, insert_slots=slots,
+                             tile_counts=[int(s[MU["TILE_COUNT0"] + a]) for a in range(min(nt, 16))])
+    inactive = [int(t) for t in atlas_map.tile_ids if int(t) not in set(int(x) for x in active_tile_ids)]
+    mu = MapUpdateCert(
+        n_active_tiles=nt, tile_ids_active=[int(t) for t in active_tile_ids], n_inactive_tiles=len(inactive),
+        tile_ids_inactive=inactive, tile_cache_hits=nt, tile_cache_misses=0,
+        insert_count_total=n_ins, insert_mass_total=float(s[MU["INSERT_MASS"]]), insert_mass_p95=float(s[MU["INSERT_MASS_P95"]]),
+        evicted_count=n_cull, evicted_mass_total=float(s[MU["EVICTED_MASS"]]), fused_count=int(s[MU["FUSED_COUNT"]]),
+        fused_mass_total=float(s[MU["FUSED_MASS"]]), merged_count=0,
+        staleness_inflation_strength=float(inflate_stats.staleness_inflation_strength) if inflate_stats else 0.0,
+        staleness_cov_inflation_trace=float(inflate_stats.staleness_cov_inflation_trace) if inflate_stats else 0.0,
+        stale_precision_downscale_total=float(inflate_stats.stale_precision_downscale_total) if inflate_stats else 0.0)
+    _ = n_exist_before
+    cert = CertBundle.create_exact(chart_id=chart_id, anchor_id="map_update", map_update=mu, compute=io.compute())
+    return result, cert, ExpectedEffect("map_update", float(n_ins), float(n_ins))

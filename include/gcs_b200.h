@@ -248,6 +248,155 @@ int gcs_bins_accumulate(gcs_ctx* ctx, void* stream, const gcs_bins_args* args, c
 int gcs_bins_finalize(gcs_ctx* ctx, void* stream, const gcs_bins_args* args, const double* mass,
                       const double* raw_sums, const double* raw_max);
 
+
+/* ================================================================================================
+ * Primitive family (BASELINE config 3): LiDAR surfels -> map view -> OT association -> pose evidence -> map update
+ * ================================================================================================ */
+
+/* MeasurementBatch (fl/backend/structures/measurement_batch.py:68-134): fixed (n_feat + n_surfel) rows, camera
+ * splats first.  All pointers (dev).  etas are (N_total, 3 lobes, 3).                                        */
+typedef struct {
+  double* Lambdas;         /* (Nt,3,3) */
+  double* thetas;          /* (Nt,3)   */
+  double* etas;            /* (Nt,3,3) */
+  double* weights;         /* (Nt)     */
+  int32_t* sources;        /* (Nt) 0 = camera, 1 = lidar */
+  int32_t* source_indices; /* (Nt)     */
+  uint8_t* valid;          /* (Nt)     */
+  double* timestamps;      /* (Nt)     */
+  double* colors;          /* (Nt,3)   */
+  int32_t n_feat;
+  int32_t n_surfel;
+} gcs_meas_batch;
+
+/* measurement_batch_from_camera_splats (measurement_batch.py:174-259): fills rows [0, n) of an all-zero batch. */
+int gcs_batch_from_camera_splats(gcs_ctx* ctx, void* stream, const double* positions, const double* covariances,
+                                 const double* directions, const double* kappas, const double* weights,
+                                 const double* timestamps, const double* colors /*dev (n,3) or NULL = gray*/,
+                                 int32_t n, double eps_lift, const gcs_meas_batch* batch);
+
+/* ---- a10 extract_lidar_surfels : fl/backend/operators/lidar_surfel_extraction.py:84-431,
+ *      bin_points_3d fl/common/ma_hex_web.py:243-303 --------------------------------------------------------- */
+typedef struct {
+  int32_t n_cells_1, n_cells_2, n_cells_z, max_occupants, min_points_per_voxel;
+  double voxel_size_m, sensor_noise_var_per_axis, wishart_nu, wishart_psi_scale, kappa_main_scale, kappa_min,
+      kappa_max, eig_min, eps_lift;
+} gcs_surfel_cfg;
+/* Writes the first n_valid rows of the LiDAR slice of `batch` (rows beyond stay as the caller left them, exactly
+ * as the reference's .at[start:end].set).  out_n_valid: dev int32[1].  Optional debug outputs (dev or NULL):
+ * out_bucket (n_cells, max_occ) int32 with -1 = empty, out_count (n_cells) int32 clipped to max_occ.           */
+int gcs_extract_lidar_surfels(gcs_ctx* ctx, void* stream, const double* pts /*dev (n,3)*/,
+                              const double* timestamps /*dev (n)*/, const double* weights /*dev (n)*/, int64_t n,
+                              const gcs_surfel_cfg* cfg /*host*/, const gcs_meas_batch* batch /*host struct*/,
+                              int32_t* out_n_valid, int32_t* out_bucket, int32_t* out_count);
+
+/* ---- a11 tiles: PrimitiveMapTile / AtlasMap (fl/backend/structures/primitive_map.py:98-211) ----------------
+ * The atlas is a pool of n_tiles_cap tiles of m_tile slots each, one SoA array per field, all (dev).           */
+typedef struct {
+  double* Lambdas;            /* (T,M,3,3) */
+  double* thetas;             /* (T,M,3)   */
+  double* etas;               /* (T,M,3,3) */
+  double* weights;            /* (T,M)     */
+  double* timestamps;         /* (T,M)     */
+  double* created_timestamps; /* (T,M)     */
+  int64_t* last_supported_scan_seq; /* (T,M) */
+  int64_t* last_update_scan_seq;    /* (T,M) */
+  int64_t* primitive_ids;     /* (T,M)     */
+  uint8_t* valid;             /* (T,M)     */
+  double* colors;             /* (T,M,3)   */
+  double* cam_mass;           /* (T,M)     */
+  double* lidar_mass;         /* (T,M)     */
+  double* rgb_cam_accum;      /* (T,M,3)   */
+  double* rgb_cam_denom;      /* (T,M)     */
+  double* rgb;                /* (T,M,3)   */
+  int32_t m_tile;
+  int32_t n_tiles_cap;
+} gcs_atlas;
+
+/* primitive_map_recency_inflate (primitive_map.py:1400-1484).  tile_index: host int32[n_tiles], pool index of each
+ * active tile or -1 if the tile does not exist (skipped).  stats: dev double[4] =
+ * [downscale_total, cov_inflation_trace, n_valid_total, -].                                                    */
+int gcs_map_recency_inflate(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int32_t* tile_index,
+                            int32_t n_tiles, int64_t scan_seq, double recency_decay_lambda, double min_scale,
+                            double* stats);
+
+/* AtlasMapView (primitive_map.py:269-300), pool of n_tiles * m_tile_view rows, all (dev). */
+typedef struct {
+  int64_t* candidate_tile_ids; /* (P) */
+  int32_t* candidate_slots;    /* (P) */
+  uint8_t* valid;              /* (P) */
+  double* positions;           /* (P,3)   */
+  double* covariances;         /* (P,3,3) */
+  double* directions;          /* (P,3)   */
+  double* kappas;              /* (P)     */
+  double* weights;             /* (P)     */
+  int64_t* primitive_ids;      /* (P)     */
+  int64_t* last_supported_scan_seq; /* (P) */
+  double* etas;                /* (P,3,3) */
+  double* colors;              /* (P,3)   */
+} gcs_map_view;
+/* extract_atlas_map_view (primitive_map.py:356-450, :303-322, :474-498): per stencil tile the first m_tile_view
+ * slots of a stable descending sort by weight (invalid -> -1e30), then mu = solve(Lambda+eps I, theta),
+ * Sigma = inv(.), kappa = |sum eta|, dir = sum eta / (kappa + eps).  tile_index[i] = -1: tile missing = empty tile.
+ * out_n_valid: dev int32[1] = number of valid pool rows.                                                       */
+int gcs_extract_atlas_map_view(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int32_t* tile_index /*host*/,
+                               const int64_t* tile_ids /*host*/, int32_t n_tiles, int32_t m_tile_view,
+                               double eps_lift, double eps_mass, const gcs_map_view* view, int32_t* out_n_valid);
+
+/* ---- a12 associate_primitives_ot : fl/backend/operators/primitive_association.py:105-553 -------------------- */
+typedef struct {
+  int32_t k_assoc, k_sinkhorn, r_stencil_xy, r_stencil_z;
+  double beta, epsilon, tau_a, tau_b, eps_mass, eps_lift, h_tile, recency_decay_lambda;
+  int64_t scan_seq;
+} gcs_assoc_cfg;
+typedef struct {
+  double* responsibilities;        /* (Nt,K) */
+  int32_t* candidate_pool_indices; /* (Nt,K) */
+  int64_t* candidate_tile_ids;     /* (Nt,K) */
+  int64_t* candidate_slots;        /* (Nt,K) */
+  double* row_masses;              /* (Nt)   */
+  double* cost_matrix;             /* (Nt,K) */
+} gcs_assoc_result;
+enum { GCS_OT_MARGINAL_A = 0, GCS_OT_MARGINAL_B, GCS_OT_MASS_TOTAL, GCS_OT_SUM_A, GCS_OT_SUM_M, GCS_OT_SUM_NOVEL,
+       GCS_OT_P95_A, GCS_OT_NONZERO_A, GCS_OT_B_RECENCY_P95, GCS_OT_ESS, GCS_OT_TOTAL_COST, GCS_OT_SUM_M2,
+       GCS_OT_NCERT = 16 };
+/* view_tile_ids: host int64[n_tiles] (tile list of the view, in view order).  Measurement rows use UNIFORM
+ * a-marginal, b = 1/K (the only policies the reference implements).  cert: dev double[GCS_OT_NCERT].          */
+int gcs_associate_primitives_ot(gcs_ctx* ctx, void* stream, const gcs_meas_batch* batch, const gcs_map_view* view,
+                                const int64_t* view_tile_ids /*host*/, int32_t n_tiles, int32_t m_tile_view,
+                                const gcs_assoc_cfg* cfg, const gcs_assoc_result* out, double* cert);
+
+/* ---- a13 visual_pose_evidence : fl/backend/operators/visual_pose_evidence.py:74-436 ------------------------ */
+enum { GCS_VP_L_TRANS = 0 /*9*/, GCS_VP_H_TRANS = 9 /*3*/, GCS_VP_L_ROT = 12 /*9*/, GCS_VP_H_ROT = 21 /*3*/,
+       GCS_VP_TRANS_COST = 24, GCS_VP_ROT_COST, GCS_VP_SUM_ROW_MASS, GCS_VP_N_VALID_ROWS, GCS_VP_SVD_S /*3*/ = 28,
+       GCS_VP_DELTA_ROT /*3*/ = 31, GCS_VP_R_SCATTER /*9*/ = 34, GCS_VP_NREC = 48 };
+int gcs_visual_pose_evidence(gcs_ctx* ctx, void* stream, const gcs_meas_batch* batch, const gcs_map_view* view,
+                             const gcs_assoc_result* assoc, int32_t k_assoc, const double* pose6 /*host [t,rotvec]*/,
+                             double eps_lift, double eps_mass, double* out_L22 /*dev (22,22)*/,
+                             double* out_h22 /*dev (22)*/, double* out_rec /*dev [GCS_VP_NREC]*/);
+
+/* ---- a14 map update = pipeline step 12b : fl/backend/pipeline.py:1233-1447 with primitive_map_fuse /
+ *      insert_masked / cull / forget (fl/backend/structures/primitive_map.py:807-1384).  This is what survives of
+ *      "PoseCovInflationPushforward" (README.md:119).  merge_reduce is not run: it is a no-op for tiles larger than
+ *      GC_PRIMITIVE_MERGE_MAX_TILE_SIZE = 2048 (primitive_map.py:1881-1890) and M_TILE is 50,000.               */
+typedef struct {
+  int32_t k_insert_tile, k_assoc, assoc_block_size, strict_tile_state; /* strict: reproduce the unmasked timestamp
+                                                                           stamping of quirk Q7                    */
+  double recency_decay_lambda, eps_lift, eps_mass, h_tile, cull_weight_threshold, forgetting_factor;
+  int64_t scan_seq, next_global_id;
+  double timestamp;
+} gcs_map_update_cfg;
+enum { GCS_MU_FUSED_COUNT = 0, GCS_MU_FUSED_MASS, GCS_MU_INSERT_COUNT, GCS_MU_INSERT_MASS, GCS_MU_INSERT_MASS_P95,
+       GCS_MU_EVICTED_COUNT, GCS_MU_EVICTED_MASS, GCS_MU_NEXT_GLOBAL_ID, GCS_MU_TILE_COUNT0 /* 16 tile counts */ = 8,
+       GCS_MU_NSTATS = 24 };
+/* tile_index / tile_ids: host arrays of the n_tiles active tiles (all must exist in the pool: the host layer creates
+ * empty tiles first, as the reference's fuse/insert do).  out_new_ids: dev int64 (n_tiles, k_insert) (-1 = not
+ * inserted); out_insert_slots: dev int32 (n_tiles, k_insert); stats: dev double[GCS_MU_NSTATS].                 */
+int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int32_t* tile_index,
+                   const int64_t* tile_ids, int32_t n_tiles, const gcs_meas_batch* batch,
+                   const gcs_assoc_result* assoc, const double* pose6 /*host z_t*/, const gcs_map_update_cfg* cfg,
+                   int64_t* out_new_ids, int32_t* out_insert_slots, double* stats);
+
 #ifdef __cplusplus
 }
 #endif
