@@ -1,0 +1,111 @@
+"""
+CPU: the C-ABI library loads without a GPU and exports every symbol include/gcs_b200.h declares; the ctypes
+prototypes cover all of them; contract types behave like the reference's (schema pins from the reference's
+test/test_cert_schema.py and test/test_budget_assertions.py); no product module imports the oracle.
+"""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "gcs_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(gcs_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from gc_slam_b200 import _lib, primitives  # noqa: F401  (primitives registers its prototypes)
+    lib = _lib.load()
+    syms = _declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/gcs_b200.h but not exported"
+        assert s in _lib.PROTOTYPES, f"{s} has no ctypes prototype"
+    assert lib.gcs_version() >= 100 and b"gcs_sm100a" in lib.gcs_version_string()
+    assert lib.gcs_bins_raw_sums_len(48) == 48 * 25 + 8
+
+
+def test_struct_layouts_match_header_sizes():
+    from gc_slam_b200 import _lib, primitives as P
+    assert ctypes.sizeof(_lib.BinStats) == 8 * 8 and ctypes.sizeof(_lib.MapBinStats) == 6 * 8
+    # gcs_bins_args: 5 ptr + 2 i64 + 2 i32 + 4 ptr + ptr + 2 i32 + 6 dbl + ptr + 3 i64 + dbl + 8 ptr + 8 ptr + 4 ptr
+    assert ctypes.sizeof(_lib.BinsArgs) == 8 * (5 + 2 + 1 + 4 + 1 + 1 + 6 + 1 + 3 + 1 + 8 + 8 + 4)
+    assert ctypes.sizeof(P.CMeasBatch) == 9 * 8 + 8 and ctypes.sizeof(P.CAtlas) == 16 * 8 + 8
+    assert ctypes.sizeof(P.CMapView) == 12 * 8 and ctypes.sizeof(P.CAssocResult) == 6 * 8
+    assert ctypes.sizeof(P.CSurfelCfg) == 5 * 4 + 4 + 9 * 8 and ctypes.sizeof(P.CAssocCfg) == 4 * 4 + 8 * 8 + 8
+    assert ctypes.sizeof(P.CMapUpdateCfg) == 4 * 4 + 6 * 8 + 2 * 8 + 8
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gc_slam_b200 import operators
+    import numpy as np
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        operators.point_budget_resample(np.zeros((4, 3)), np.zeros(4), np.ones(4))
+    from gc_slam_b200 import _lib
+    h = ctypes.c_void_p()
+    assert _lib.load().gcs_create(ctypes.byref(h), 0) != 0
+    assert b"no CPU fallback" in _lib.load().gcs_last_error(None) or b"CUDA" in _lib.load().gcs_last_error(None)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gc-slam_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports oracle/"
+
+
+def test_cert_schema_and_aggregation():
+    from gc_slam_b200.certs import (CertBundle, ComputeCert, DeviceRuntimeCert, ExpectedEffect, InfluenceCert, MapUpdateCert,
+                                    OTCert, ScanIOCert, SupportCert, aggregate_certificates)
+    c = CertBundle.create_approx("GC-RIGHT-01", "a", ["X"], support=SupportCert(3.0, 0.5),
+                                 influence=InfluenceCert.identity().with_overrides(psd_projection_delta=0.25))
+    d = c.to_dict()
+    for k in ("chart_id", "anchor_id", "exact", "approximation_triggers", "frobenius_applied", "conditioning", "support",
+              "mismatch", "excitation", "influence", "overconfidence", "compute", "total_trigger_magnitude"):
+        assert k in d
+    assert d["exact"] is False and d["total_trigger_magnitude"] == 0.25 and "ot" not in d
+    cc = ComputeCert()
+    assert isinstance(cc.alloc_bytes_est, int) and isinstance(cc.largest_tensor_shape, tuple) and len(cc.largest_tensor_shape) == 2
+    assert isinstance(cc.scan_io, ScanIOCert) and isinstance(cc.device_runtime, DeviceRuntimeCert)
+    assert set(cc.to_dict()["device_runtime"]) == {"host_sync_count_est", "device_to_host_bytes_est", "host_to_device_bytes_est",
+                                                   "jit_recompile_count"}
+    e = CertBundle.create_exact("GC-RIGHT-01", "b", ot=OTCert(transport_mass_total=2.0), map_update=MapUpdateCert(fused_count=3))
+    agg = aggregate_certificates([c, e])
+    assert agg.exact is False and agg.approximation_triggers == ["X"] and agg.ot.transport_mass_total == 2.0
+    assert agg.map_update.fused_count == 3 and agg.support.ess_total == 1.5
+    assert ExpectedEffect("x", 1.0).to_dict() == {"objective_name": "x", "predicted": 1.0, "realized": None}
+    assert aggregate_certificates([]).chart_id == "unknown"
+
+
+def test_constants_and_manifest():
+    from gc_slam_b200 import constants as K, manifest
+    assert (K.GC_D_Z, K.GC_K_HYP, K.GC_N_POINTS_CAP, K.GC_K_ASSOC, K.GC_K_SINKHORN) == (22, 4, 8192, 8, 50)
+    assert K.GC_N_ACTIVE_TILES == 7 == K.GC_N_STENCIL_TILES and K.GC_M_TILE == 50000 and K.GC_M_TILE_VIEW == 1024
+    b = manifest.patch_backends({"core_array": "jax", "imu": "jax"})
+    for k in ("core_array", "se3", "domain_projection_psd", "deskew", "lidar_evidence", "map_update", "sinkhorn_backend",
+              "point_budget", "bin_soft_assign", "scan_bin_moment_match", "matrix_fisher", "surfel_extraction", "association"):
+        assert b[k].startswith("gcs_sm100a:")
+    assert b["imu"] == "jax"
+
+
+def test_tiling_helpers_match_oracle():
+    import numpy as np
+    from gc_slam_b200 import primitives as P
+    from oracle import prim_path as op
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        c = rng.uniform(-30, 30, 3)
+        assert P.ma_hex_stencil_tile_ids(c, 2.0, 1, 0) == op.stencil_tile_ids(c, 2.0, 1, 0)
+    assert len(P.hex_disk_axial(1)) == 7 and len(P.hex_disk_axial(2)) == 19
