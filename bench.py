@@ -56,7 +56,7 @@ def measured_peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -90,21 +90,26 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, reasons, sm_all, pw = [], [], set(), [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); smax.append(float(f[2]))
+                clk, mx, power, util = float(f[1]), float(f[2]), float(f[3]), float(f[4])
             except ValueError:
                 continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            sm_all.append(clk); smax.append(mx)
+            if util >= 50.0:  # samples taken while the GPU was busy
+                sm.append(clk); pw.append(power)
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        use = sm if sm else sm_all
+        return {"sm_mhz": float(np.median(use)) if use else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm_all), "samples_under_load": len(sm),
+                "power_w_median": float(np.median(pw)) if pw else None}
 
 
 def make_batch(n_scans, n_points, seed0):
@@ -205,6 +210,63 @@ def workload_config(args, scans_per_step):
 
 
 # ----------------------------------------------------------------------------------------------------------
+# BASELINE config 3 (reported under "extra"): 65,536-point scan, surfel association against a 1 M-surfel synthetic map,
+# pose evidence and the primitive-map update.  Single scan ("replicas only": this part of the path does not shard).
+# ----------------------------------------------------------------------------------------------------------
+def primitive_path_extra(n_points, n_map=1_000_000, reps=10):
+    import torch
+    from gc_slam_b200 import primitives as PR
+    from gc_slam_b200 import operators as ops
+    from gc_slam_b200 import synth
+
+    t_build = time.perf_counter()
+    atlas_np = synth.synthetic_atlas(n_map, 50000, 7, scan_seq=20)
+    amap = PR.AtlasMap.from_numpy(atlas_np, n_tiles_cap=len(atlas_np["tiles"]) + 16)
+    del atlas_np
+    pts, t, w, ring, tag = synth.vlp16_scan(n_points, 4242, t0=synth.EPOCH_T0)
+    xi = synth.scan_twist(4242)
+    cam = synth.camera_splats(512, 99)
+    pose = np.array([0.1, -0.2, 0.0, 0.0, 0.0, 0.05])
+    t_build = time.perf_counter() - t_build
+    stages = {k: [] for k in ("deskew", "surfel_extraction", "recency_inflate", "map_view", "association", "pose_evidence",
+                              "map_update", "total")}
+    pts_d = torch.from_numpy(pts).cuda(); t_d = torch.from_numpy(t).cuda(); w_d = torch.from_numpy(w).cuda()
+    base = PR.measurement_batch_from_camera_splats(cam["positions"], cam["covariances"], cam["directions"], cam["kappas"],
+                                                   cam["weights"], cam["timestamps"], cam["colors"])
+    cfg = PR.SurfelExtractionConfig()
+    for rep in range(reps + 2):
+        scan_seq = 21 + rep
+        torch.cuda.synchronize()
+        tk = [time.perf_counter()]
+
+        def tick():
+            torch.cuda.synchronize()
+            tk.append(time.perf_counter())
+        dk, _, _ = ops.deskew_constant_twist(pts_d, t_d, w_d, synth.EPOCH_T0, synth.EPOCH_T0 + 0.1, xi, 1.0, "c", "a"); tick()
+        batch, _, _ = PR.extract_lidar_surfels(dk.points, t_d, dk.weights, cfg, base); tick()
+        active = PR.ma_hex_stencil_tile_ids(pose[:3])
+        amap, _, _, inf = PR.primitive_map_recency_inflate(amap, active, scan_seq); tick()
+        view = PR.extract_atlas_map_view(amap, active, 1024); tick()
+        assoc, c_as, _ = PR.associate_primitives_ot(batch, view, PR.AssociationConfig(scan_seq=scan_seq)); tick()
+        vpe, _, _ = PR.visual_pose_evidence(assoc, batch, view, pose, z_lin_pose=pose); tick()
+        res, c_mu, _ = PR.map_update_step12b(amap, batch, assoc, active, pose, scan_seq, synth.EPOCH_T0 + 0.1 * rep,
+                                             inflate_stats=inf); tick()
+        if rep >= 2:
+            d = np.diff(tk)
+            for k, v in zip(list(stages)[:-1], d):
+                stages[k].append(v)
+            stages["total"].append(tk[-1] - tk[0])
+    p50 = {k: 1e3 * float(np.median(v)) for k, v in stages.items()}
+    alg_bytes = 104e6  # ~104 MB per scan at 65,536 points / 1 M-surfel map, 7 active tiles
+    return {"workload": f"{n_points}-point scan, {n_map} surfel synthetic map ({len(amap.tiles)} tiles of 50,000 slots), 512 camera "
+                        "splats + 1024 surfels, K_ASSOC 8, 7-tile stencil, map update with K_INSERT 64",
+            "p50_ms_per_stage": p50, "scans_per_s": 1e3 / p50["total"], "algorithmic_bytes_per_scan": alg_bytes,
+            "achieved_GBps_model": alg_bytes / (p50["total"] * 1e-3) / 1e9, "n_lidar_surfels": int(batch.n_lidar_valid),
+            "n_inserted_last": int(res.n_inserted), "map_build_s": t_build, "reps": reps,
+            "note": "wall clock per operator call incl. its one certificate read-back (host sync)"}
+
+
+# ----------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -244,14 +306,21 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput -------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        plan.run()
-    barrier()
-    ctx.timing_enable(True)
-    launches0 = ctx.launches
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        plan.run()
+    # keep the device under the same load for ~1 s before timing: clocks settle to their power-capped value and the
+    # 100 ms nvidia-smi sampler gets samples that describe the timed region
+    torch.cuda.synchronize()
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 1.0:
+        plan.run()
+        torch.cuda.synchronize()
+    barrier()
+    ctx.timing_enable(True)
+    launches0 = ctx.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -260,10 +329,15 @@ def run_ours(args):
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launches - launches0
-    k_ms, k_n = ctx.timing_collect()
+    k_ms, k_n = ctx.timing_collect()   # CUDA-event brackets of bin_scan_kernel inside the timed region only
     ctx.timing_enable(False)
+    # a few more untimed passes so the sampler certainly covers the timed kernels' regime
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 0.5:
+        plan.run()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
     t_max = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
@@ -271,29 +345,44 @@ def run_ours(args):
     value = world * S * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the plugin API with host buffers ------------------------------------------
-    out_host = torch.empty(S * (L.BC_NCERT + 22 * 22 + 22), dtype=torch.float64).pin_memory()
+    # Two BinPathPlans on two streams: the pinned-host -> device copy of batch k+1 overlaps the kernels of batch k
+    # (what a replay tool built on the public API does).  Every step still copies all of its inputs from host memory
+    # and reads its 22-D evidence + certificates back to pinned host memory.
+    plan_b = ops.BinPathPlan(S, P, P, n_hyp=1, n_bins=N_BINS, tau=TAU, origin=synth.lidar_origin_base(), precision=prec,
+                             want_evidence=True, materialize_deskewed=True, own_context=True)
+    plan_b.set_bins(bins, TAU)
+    plan_b.set_map(synth.random_map_bin_stats(N_BINS, 7, bins))
+    plans = (plan, plan_b)
+    streams = (torch.cuda.Stream(), torch.cuda.Stream())
+    outs_host = [torch.empty(S * (L.BC_NCERT + 22 * 22 + 22), dtype=torch.float64).pin_memory() for _ in range(2)]
 
-    def e2e_step():
-        plan.upload(host["pts"], host["t"], host["w"], host["ring"], host["tag"], host["t0"], host["t1"], host["xi"],
-                    host["poses"])
-        plan.run()
-        o = plan.outputs()
-        out_host.copy_(torch.cat([o.cert.reshape(-1), o.L22.reshape(-1), o.h22.reshape(-1)]), non_blocking=True)
+    def e2e_step(k):
+        pl, stq, oh = plans[k % 2], streams[k % 2], outs_host[k % 2]
+        with torch.cuda.stream(stq):
+            pl.upload(host["pts"], host["t"], host["w"], host["ring"], host["tag"], host["t0"], host["t1"], host["xi"],
+                      host["poses"])
+            pl.run()
+            o = pl.outputs()
+            oh.copy_(torch.cat([o.cert.reshape(-1), o.L22.reshape(-1), o.h22.reshape(-1)]), non_blocking=True)
 
-    for _ in range(2):
-        e2e_step()
+    torch.cuda.synchronize()
+    for k in range(2):
+        e2e_step(k)
     barrier()
     e_steps = max(2, min(args.steps, 10))
-    ev0.record()
-    for _ in range(e_steps):
-        e2e_step()
-    ev1.record()
+    t_e0 = time.perf_counter()
+    for k in range(e_steps):
+        e2e_step(k)
+    for stq in streams:
+        stq.synchronize()
+    e_wall_ms = (time.perf_counter() - t_e0) * 1e3   # two streams: device time == wall time between the syncs
     barrier()
-    e_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    e_ms = torch.tensor([e_wall_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * S * e_steps / (float(e_ms.item()) * 1e-3)
-    d2h_bytes = out_host.numel() * 8
+    d2h_bytes = outs_host[0].numel() * 8
+    del plan_b
 
     # ---- single-scan latency (p50) through the same API, host buffers in, evidence out ----------------
     lat = None
@@ -326,6 +415,9 @@ def run_ours(args):
         lat = {"p50_ms_host_in_evidence_out": 1e3 * float(np.median(ts_e2e)),
                "p50_ms_device_resident": 1e3 * float(np.median(ts_dev)), "points": P, "reps": 50}
 
+    prim = None
+    if rank == 0 and world == 1 and not args.no_prim:
+        prim = primitive_path_extra(P)
     if rank == 0:
         peak, peak_src = measured_peaks()
         bytes_per_launch = S * (BYTES_IN_PER_PT * P + BYTES_OUT_PER_PT * P)
@@ -346,7 +438,8 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, S),
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(d2h_bytes), "steps": e_steps},
+                    "d2h_bytes_per_step": int(d2h_bytes), "steps": e_steps,
+                    "how": "2 plans on 2 streams (copy of batch k+1 overlaps kernels of batch k); wall clock between syncs"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "bin_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -355,6 +448,7 @@ def run_ours(args):
                          "kernel_launches_timed": k_n, "kernel_share_of_step": k_ms / ms_total},
             "latency": lat,
             "points_per_s": value * P,
+            "extra": {"primitive_path": prim},
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -373,6 +467,7 @@ def main():
     ap.add_argument("--points", type=int, default=65536)
     ap.add_argument("--precision", default="f64", choices=["f64", "mixed"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the in-run CPU baseline")
+    ap.add_argument("--no-prim", action="store_true", help="skip the primitive-path (config 3) stage timings")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -45,8 +45,8 @@ F64 = torch.float64
 class _IO:
     """Counts the bytes this call really moved between host and device (DeviceRuntimeCert)."""
 
-    def __init__(self, device=None):
-        self.ctx = L.context(device)
+    def __init__(self, device=None, ctx=None):
+        self.ctx = ctx if ctx is not None else L.context(device)
         self.dev = torch.device("cuda", self.ctx.device)
         self.h2d = 0
         self.d2h = 0
@@ -606,8 +606,15 @@ class BinPathPlan:
     def __init__(self, n_scans, n_raw, cap, n_hyp=1, n_bins=constants.GC_B_BINS, tau=constants.GC_TAU_SOFT_ASSIGN,
                  origin=(0.0, 0.0, 0.0), precision=L.PREC_F64, want_evidence=True, materialize_resampled=False,
                  materialize_deskewed=True, materialize_responsibilities=False, device=None,
-                 shard_row0=0, n_raw_total=0, cap_total=0):
-        io = self.io = _IO(device)
+                 shard_row0=0, n_raw_total=0, cap_total=0, own_context=False):
+        # own_context: a private gcs_ctx (workspace) so that this plan may run on its own stream concurrently with
+        # other plans -- a gcs_ctx is not re-entrant (include/gcs_b200.h).
+        if own_context:
+            if device is None:
+                device = torch.cuda.current_device()
+            io = self.io = _IO(ctx=L.Context(device.index if isinstance(device, torch.device) else int(device)))
+        else:
+            io = self.io = _IO(device)
         self.S, self.H, self.U, self.B = int(n_scans), int(n_hyp), int(n_scans) * int(n_hyp), int(n_bins)
         self.n_raw, self.cap = int(n_raw), int(cap)
         S, U, B = self.S, self.U, self.B
