@@ -15,23 +15,6 @@
 
 namespace gcs {
 
-struct BinScanParams {
-  const double* pts; const double* t; const double* w; const uint8_t* ring; const uint8_t* tag;
-  int64_t n_raw;     // local raw rows per scan
-  int64_t cap;       // local output rows per scan
-  int64_t n_sel;     // local selected rows = ceil(n_raw / stride)
-  int64_t stride;
-  int n_scans, n_hyp, n_bins;
-  const double* t0s; const double* t1s; const double* xi; const double* bin_dirs;
-  double origin[3];
-  double inv_tau, shift, eps_mass;
-  int use_true_max;
-  const double* mass;  // (S, kNMass), already global
-  double* rs_pts; double* rs_t; double* rs_w; uint8_t* rs_ring; uint8_t* rs_tag;
-  double* dk_pts; double* dk_w; double* resp;
-  double* partial;  // (U, ctas_per_unit, part_len)
-  int part_len;
-};
 
 __device__ __forceinline__ double hw_sum(double v) {
   v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -677,6 +660,7 @@ static int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 struct BinsGeom {
   int64_t stride, n_sel, cap_total, n_raw_total;
   int U, ctas_per_unit, part_len, raw_len, mass_chunks;
+  int tc_parts;   // partial slots per unit of the tensor-core kernel (0 when another precision was asked for)
   int64_t mass_rows_per_chunk;
 };
 
@@ -719,6 +703,7 @@ static int bins_geometry(gcs_ctx* ctx, const gcs_bins_args* a, BinsGeom* g) {
     }
     g->ctas_per_unit = (int)best;
   }
+  g->tc_parts = a->precision == GCS_PREC_TC ? bin_scan_tc_parts(ctx->sm_count, g->U, a->cap) : 0;
   g->raw_len = raw_sums_len(a->n_bins);
   g->part_len = g->raw_len + kNMax;
   int64_t chunks = ceil_div64(a->n_raw > 0 ? a->n_raw : 1, 2048);
@@ -745,7 +730,8 @@ struct BinsWs { double* mass_partial; double* mass; double* partial; double* raw
 static int bins_ws(gcs_ctx* ctx, const gcs_bins_args* a, const BinsGeom& g, BinsWs* w) {
   uint64_t n_mp = (uint64_t)a->n_scans * g.mass_chunks * kNMass;
   uint64_t n_m = (uint64_t)a->n_scans * kNMass;
-  uint64_t n_p = (uint64_t)g.U * g.ctas_per_unit * g.part_len;
+  const int parts = g.ctas_per_unit > g.tc_parts ? g.ctas_per_unit : g.tc_parts;
+  uint64_t n_p = (uint64_t)g.U * parts * g.part_len;
   uint64_t n_r = (uint64_t)g.U * g.raw_len;
   uint64_t n_x = (uint64_t)g.U * kNMax;
   uint64_t total = (n_mp + n_m + n_p + n_r + n_x + 16) * sizeof(double);
@@ -782,12 +768,20 @@ static int accumulate_impl(gcs_ctx* ctx, cudaStream_t st, const gcs_bins_args* a
   P.partial = w.partial; P.part_len = g.part_len;
   dim3 grid(g.ctas_per_unit, g.U);
   const int Q = pick_q(a->n_bins);
+  // GCS_PREC_TC needs the constant softmax shift and no materialised responsibilities; otherwise it degrades to MIXED
+  const bool use_tc = a->precision == GCS_PREC_TC && bin_scan_tc_supported(P);
+  int n_parts = g.ctas_per_unit;
+  if (use_tc) {
+    n_parts = g.tc_parts;
+    GCS_CHECK_CUDA(ctx, cudaMemsetAsync(P.partial, 0, (size_t)g.U * n_parts * g.part_len * sizeof(double), st));
+  }
   gcs_timing_begin(ctx, st);
-  if (a->precision == GCS_PREC_F64) GCS_CHECK_CUDA(ctx, launch_scan<0>(Q, grid, st, P));
+  if (use_tc) GCS_CHECK_CUDA(ctx, launch_bin_scan_tc(ctx->sm_count, st, P, n_parts));
+  else if (a->precision == GCS_PREC_F64) GCS_CHECK_CUDA(ctx, launch_scan<0>(Q, grid, st, P));
   else GCS_CHECK_CUDA(ctx, launch_scan<1>(Q, grid, st, P));
   gcs_timing_end(ctx, st);
   GCS_LAUNCH_CHECK(ctx);
-  reduce_partials_kernel<<<dim3((g.raw_len + kNMax + 63) / 64, g.U), 256, 0, st>>>(w.partial, g.ctas_per_unit, g.part_len,
+  reduce_partials_kernel<<<dim3((g.raw_len + kNMax + 63) / 64, g.U), 256, 0, st>>>(w.partial, n_parts, g.part_len,
                                                                                     a->n_bins, kNF, raw_sums, raw_max);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
