@@ -40,7 +40,8 @@ template <int Q>
 struct TcCfg {
   static constexpr int kBinsPad = 16 * Q;   // rows of the e_hi block == first row of the e_lo block
   static constexpr int kRows = 32 * Q;      // rows of A that carry data
-  static constexpr int kEpi = Q;            // epilogue warps (32 TMEM lanes each)
+  static constexpr int kEpi = 4;            // epilogue warps: a full warpgroup, one warp per 32 TMEM lanes (for Q = 3 the
+                                            // fourth drains padding lanes; it keeps the register re-allocation aligned)
   static constexpr int kThreads = 32 * (kProd + kEpi);
   static constexpr int kABytes = kRows * tc::kRowBytes;
   static constexpr int kBBytes = kBRows * tc::kRowBytes;
@@ -49,7 +50,7 @@ struct TcCfg {
 };
 
 struct TcMisc {
-  float4 bins[kMaxBins];
+  float4 bins2[kMaxBins * 2];  // per bin: (bx, bx, by, by), (bz, bz, -c2, -c2), pre-scaled by log2(e)/tau
   uint64_t bar_stage[kProd];   // MMAs that read the warp's operand tile have completed
   uint64_t bar_full[kProd];    // the warp's accumulator holds a finished round
   uint64_t bar_empty[kProd];   // the epilogue has drained it
@@ -69,6 +70,341 @@ __device__ __forceinline__ int cta_of_tile(const TcGeom& G, int64_t g) {
   return (int)(((g + 1) * G.n_cta - 1) / G.total_tiles);
 }
 
+// segment of one unit handled by this CTA
+struct TcSeg { int u, s, h; int64_t unit_t0, lt0, lt1; };
+
+__device__ __forceinline__ void bar_all(int n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
+
+template <int Q>
+__device__ __forceinline__ bool next_segment(const TcGeom& G, int n_hyp, int64_t& g0, int64_t g_end, TcSeg& sg) {
+  if (g0 >= g_end) return false;
+  sg.u = (int)(g0 / G.tiles_per_unit);
+  sg.unit_t0 = (int64_t)sg.u * G.tiles_per_unit;
+  const int64_t g1 = (sg.unit_t0 + G.tiles_per_unit < g_end) ? sg.unit_t0 + G.tiles_per_unit : g_end;
+  sg.lt0 = g0 - sg.unit_t0; sg.lt1 = g1 - sg.unit_t0;
+  sg.s = sg.u / n_hyp; sg.h = sg.u - sg.s * n_hyp;
+  g0 = g1;
+  return true;
+}
+
+// Segment combine, executed by all threads of the CTA after the epilogue has written its row sums to `red`.
+template <int Q>
+__device__ __forceinline__ void write_partial(const BinScanParams& P, const TcGeom& G, const TcSeg& sg, const TcMisc& mi,
+                                              const double* red, int cta, int tid) {
+  using C = TcCfg<Q>;
+  const int nb = P.n_bins;
+  const int slot = cta - cta_of_tile(G, sg.unit_t0);
+  double* part = P.partial + ((int64_t)sg.u * G.n_parts + slot) * P.part_len;
+  for (int idx = tid; idx < nb * kNF; idx += C::kThreads) {
+    const int b = idx / kNF, f = idx - b * kNF;
+    part[b * kRowLen + f] = red[b * kNF + f] + red[(C::kBinsPad + b) * kNF + f];
+  }
+  if (tid < kNExtras + kNMax) {
+    double* ex = part + nb * kRowLen;
+    double r = 0.0;
+    if (tid <= kExCount) {
+      for (int w = 0; w < kProd; ++w) r += mi.ex[w][tid];
+      ex[tid] = r;
+    } else if (tid < kNExtras) {
+      ex[tid] = 0.0;
+    } else if (tid == kNExtras + kMxResp) {
+      for (int w = 0; w < kProd; ++w) r = fmax(r, mi.ex[w][5]);
+      ex[tid] = r;
+    } else {
+      ex[tid] = 0.0;
+    }
+  }
+}
+
+// Barrier schedule of a segment (all kThreads threads, named barrier 1):
+//   [producers: tiles + MMAs | epilogue: drains]  B1  [epilogue: row sums -> red]  B2  [all: partial]  B3  [all: re-zero red]  B4
+template <int Q>
+__device__ __forceinline__ void segment_tail(const BinScanParams& P, const TcGeom& G, const TcSeg& sg, TcMisc& mi,
+                                             unsigned char* stages, int cta, int tid, const double* acc_or_null) {
+  using C = TcCfg<Q>;
+  double* red = reinterpret_cast<double*>(stages);   // operand tiles are idle: every MMA of the segment has completed
+  bar_all(C::kThreads);
+  if (acc_or_null) {
+    const int R = tid - 32 * kProd;
+#pragma unroll
+    for (int f = 0; f < kNF; ++f) red[R * kNF + f] = acc_or_null[f];
+  }
+  bar_all(C::kThreads);
+  write_partial<Q>(P, G, sg, mi, red, cta, tid);
+  bar_all(C::kThreads);
+  // padding rows of the operand tiles alias this scratch: keep it free of NaN bit patterns
+  for (int k = tid; k < (128 * kNF * 8 + 15) / 16; k += C::kThreads) reinterpret_cast<uint4*>(stages)[k] = make_uint4(0, 0, 0, 0);
+  tc::fence_smem_to_async();
+  bar_all(C::kThreads);
+}
+
+template <int Q>
+__device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGeom& G, TcMisc& mi, unsigned char* stages,
+                                              uint32_t tmem, int cta, int tid) {
+  using C = TcCfg<Q>;
+  const int wid = tid >> 5, lane = tid & 31;
+  uint32_t n_stage_uses = 0, n_rounds = 0;   // uses of the operand tile / finished accumulator rounds
+  // lane-dependent byte offsets of this lane's element inside a row, for the 8 row phases of the swizzle
+  uint32_t off[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) off[j] = (uint32_t)((((lane >> 2) ^ j) << 4) | ((lane & 3) << 2));
+  // same for the pair layout (points 2j, 2j+1 of the tile, j = lane & 15): one 8-byte store per row
+  uint32_t off2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) off2[j] = (uint32_t)(((((lane & 15) >> 1) ^ j) << 4) | ((lane & 1) << 3));
+  int64_t g0 = cta_tile0(G, cta);
+  const int64_t g_end = cta_tile0(G, cta + 1);
+  TcSeg sg;
+  while (next_segment<Q>(G, P.n_hyp, g0, g_end, sg)) {
+    const int u = sg.u, s = sg.s, h = sg.h;
+    const int64_t lt0 = sg.lt0, lt1 = sg.lt1;
+    unsigned char* sA = stages + wid * C::kStageBytes;
+    unsigned char* sB = sA + C::kABytes;
+    const uint32_t aA = tc::smem_u32(sA), aB = tc::smem_u32(sB);
+    const double t0 = P.t0s[s], t1 = P.t1s[s];
+    const double inv_denom = 1.0 / fmax(t1 - t0, 1e-12);
+    const WindowCtx wctx = make_window_ctx(t0, t1);
+    const TwistCtx tw = make_twist_ctx(P.xi + (int64_t)u * 6);
+    const double mass_scale = P.mass[s * kNMass + kMassAll] / (P.mass[s * kNMass + kMassSel] + P.eps_mass);
+    const double* pts = P.pts + (int64_t)s * P.n_raw * 3;
+    const double* tp = P.t + (int64_t)s * P.n_raw;
+    const double* wp = P.w + (int64_t)s * P.n_raw;
+    const uint8_t* rp = P.ring ? P.ring + (int64_t)s * P.n_raw : nullptr;
+    const uint8_t* gp = P.tag ? P.tag + (int64_t)s * P.n_raw : nullptr;
+    double ent_dot = 0.0, ent_log = 0.0, mx_resp = 0.0, sum_wdk = 0.0, sum_wrs = 0.0, n_rows = 0.0;
+    uint32_t in_round = 0;
+    // pair layout of the soft-assign stage: lane = (half, j); the lane evaluates bins [half*NB2, half*NB2 + NB2) for
+    // the two points 2j, 2j+1 of the tile (packed f32x2 math, 8-byte operand stores)
+    constexpr int NB2 = C::kBinsPad / 2;
+    const int half = lane >> 4, pj = lane & 15;
+    unsigned char* sA_lane = sA + half * NB2 * tc::kRowBytes;
+    const float4* bins_lane = mi.bins2 + half * NB2 * 2;
+
+    // software pipeline: the raw rows of the warp's next tile are requested before this tile is processed
+    double nx[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    uint8_t nrg = 0, ntg = 0;
+    auto fetch = [&](int64_t tile) {
+      const int64_t ii = tile * tc::kTileK + lane;
+      nx[0] = nx[1] = nx[2] = nx[3] = nx[4] = 0.0; nrg = 0; ntg = 0;
+      if (tile < lt1 && ii < P.n_sel) {
+        const int64_t j = ii * P.stride;
+        nx[0] = pts[3 * j]; nx[1] = pts[3 * j + 1]; nx[2] = pts[3 * j + 2];
+        nx[3] = tp[j]; nx[4] = wp[j];
+        if (rp) nrg = rp[j];
+        if (gp) ntg = gp[j];
+      }
+    };
+    fetch(lt0 + wid);
+    for (int64_t lt = lt0 + wid; lt < lt1; lt += kProd) {
+      // ---------------- stage 1 (lane = point): resample gather, deskew, window weight, ray direction (float64)
+      const int64_t i = lt * tc::kTileK + lane;
+      const bool row = i < P.cap;
+      const double p[3] = {nx[0], nx[1], nx[2]}, tt = nx[3], ww = nx[4];
+      const uint8_t rg = nrg, tg = ntg;
+      fetch(lt + kProd);
+      const double w_rs = ww * mass_scale;
+      if (row && h == 0 && P.rs_pts) {
+        const int64_t o = (int64_t)s * P.cap + i;
+        P.rs_pts[3 * o] = p[0]; P.rs_pts[3 * o + 1] = p[1]; P.rs_pts[3 * o + 2] = p[2];
+        P.rs_t[o] = tt; P.rs_w[o] = w_rs; P.rs_ring[o] = rg; P.rs_tag[o] = tg;
+      }
+      const double alpha = (tt - t0) * inv_denom;
+      double p0[3];
+      deskew_point_ctx(p, alpha, tw, p0);
+      const double w_dk = w_rs * window_weight_ctx(tt, wctx);
+      if (row) {
+        const int64_t o = (int64_t)u * P.cap + i;
+        if (P.dk_pts) { P.dk_pts[3 * o] = p0[0]; P.dk_pts[3 * o + 1] = p0[1]; P.dk_pts[3 * o + 2] = p0[2]; }
+        if (P.dk_w) P.dk_w[o] = w_dk;
+        sum_wdk += w_dk; sum_wrs += w_rs; n_rows += 1.0;
+      }
+      const double r0 = p0[0] - P.origin[0], r1 = p0[1] - P.origin[1], r2 = p0[2] - P.origin[2];
+      const double rr = fma(r0, r0, fma(r1, r1, r2 * r2));
+      const double y = fast_rsqrt(fmax(rr, 1e-300));
+      const double invn = fma(-P.eps_mass * y, y, y);          // 1 / (|r| + eps) to first order in eps / |r|
+      const float f0 = (float)(r0 * invn), f1 = (float)(r1 * invn), f2 = (float)(r2 * invn);
+
+      // ---------------- stage 2 (pair layout): A = [e_hi ; e_lo], softmax numerators in log2 units, unnormalised
+      const float2 g0 = make_float2(__shfl_sync(0xffffffffu, f0, 2 * pj), __shfl_sync(0xffffffffu, f0, 2 * pj + 1));
+      const float2 g1 = make_float2(__shfl_sync(0xffffffffu, f1, 2 * pj), __shfl_sync(0xffffffffu, f1, 2 * pj + 1));
+      const float2 g2 = make_float2(__shfl_sync(0xffffffffu, f2, 2 * pj), __shfl_sync(0xffffffffu, f2, 2 * pj + 1));
+      // the tensor core may still be reading this warp's previous tile
+      if (n_stage_uses > 0) tc::mbar_wait(&mi.bar_stage[wid], (n_stage_uses - 1) & 1);
+      float2 sum = make_float2(0.f, 0.f), dot = sum;
+      float mx0 = 0.f, mx1 = 0.f;
+      // groups of kGrp bins: table loads of the next group are issued before the operand stores of this one (the
+      // compiler cannot move shared-memory loads across those stores by itself), math of a group is independent
+      constexpr int kGrp = 4;
+      static_assert(NB2 % kGrp == 0, "bin half must be a multiple of the group size");
+      float4 tab[2][kGrp][2];
+#pragma unroll
+      for (int k = 0; k < kGrp; ++k) { tab[0][k][0] = bins_lane[2 * k]; tab[0][k][1] = bins_lane[2 * k + 1]; }
+#pragma unroll
+      for (int g = 0; g < NB2 / kGrp; ++g) {
+        const int cur = g & 1;
+        if (g + 1 < NB2 / kGrp) {
+#pragma unroll
+          for (int k = 0; k < kGrp; ++k) {
+            tab[cur ^ 1][k][0] = bins_lane[2 * ((g + 1) * kGrp + k)];
+            tab[cur ^ 1][k][1] = bins_lane[2 * ((g + 1) * kGrp + k) + 1];
+          }
+        }
+        float2 l[kGrp], e[kGrp], hi[kGrp], lo[kGrp];
+#pragma unroll
+        for (int k = 0; k < kGrp; ++k) {
+          const float4 ta = tab[cur][k][0], tb = tab[cur][k][1];
+          l[k] = tc::fma2(g0, make_float2(ta.x, ta.y),
+                          tc::fma2(g1, make_float2(ta.z, ta.w), tc::fma2(g2, make_float2(tb.x, tb.y), make_float2(tb.z, tb.w))));
+        }
+#pragma unroll
+        for (int k = 0; k < kGrp; ++k) e[k] = make_float2(tc::ex2f(l[k].x), tc::ex2f(l[k].y));
+#pragma unroll
+        for (int k = 0; k < kGrp; ++k) {
+          sum = tc::add2(sum, e[k]);
+          dot = tc::fma2(e[k], l[k], dot);
+          mx0 = fmaxf(mx0, e[k].x); mx1 = fmaxf(mx1, e[k].y);
+          hi[k] = make_float2(tc::tf32_hi(e[k].x), tc::tf32_hi(e[k].y));
+          lo[k] = tc::sub2(e[k], hi[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kGrp; ++k) {
+          const int b = g * kGrp + k;
+          *reinterpret_cast<float2*>(sA_lane + b * tc::kRowBytes + off2[b & 7]) = hi[k];
+          *reinterpret_cast<float2*>(sA_lane + (C::kBinsPad + b) * tc::kRowBytes + off2[b & 7]) = lo[k];
+        }
+      }
+      // both bin halves -> every lane holds the full row sums of its two points; then back to lane = point
+      sum.x += __shfl_xor_sync(0xffffffffu, sum.x, 16); sum.y += __shfl_xor_sync(0xffffffffu, sum.y, 16);
+      dot.x += __shfl_xor_sync(0xffffffffu, dot.x, 16); dot.y += __shfl_xor_sync(0xffffffffu, dot.y, 16);
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 16)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 16));
+      const int src = lane >> 1;
+      const bool odd = lane & 1;
+      const float sa = __shfl_sync(0xffffffffu, sum.x, src), sb = __shfl_sync(0xffffffffu, sum.y, src);
+      const float da_ = __shfl_sync(0xffffffffu, dot.x, src), db_ = __shfl_sync(0xffffffffu, dot.y, src);
+      const float ma = __shfl_sync(0xffffffffu, mx0, src), mb = __shfl_sync(0xffffffffu, mx1, src);
+      const float sumf = odd ? sb : sa, dotf = odd ? db_ : da_, emax = odd ? mb : ma;
+
+      // ---------------- stage 3 (lane = point): B = [phi_hi ; phi_lo], phi = (w / Z) (1, d, d d^T, p, p p^T)
+      const double ssum = (double)sumf;
+      double inv;
+      {
+        float rf;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(sumf));
+        inv = (double)rf;
+        inv = fma(inv, fma(-ssum, inv, 1.0), inv);
+        inv = fma(inv, fma(-ssum, inv, 1.0), inv);
+      }
+      if (row) {
+        ent_dot = fma(inv * kLn2, (double)dotf, ent_dot);
+        ent_log = fma((double)__log2f(sumf), kLn2, ent_log);
+        mx_resp = fmax(mx_resp, (double)emax * inv);
+      }
+      {
+        const float sc = row ? (float)(w_dk * inv) : 0.f;
+        const float q0 = (float)p0[0], q1 = (float)p0[1], q2 = (float)p0[2];
+        const float sd0 = sc * f0, sd1 = sc * f1, sd2 = sc * f2;
+        const float sp0 = sc * q0, sp1 = sc * q1, sp2 = sc * q2;
+        const float v[kNF] = {sc, sd0, sd1, sd2, sd0 * f0, sd0 * f1, sd0 * f2, sd1 * f1, sd1 * f2, sd2 * f2,
+                              sp0, sp1, sp2, sp0 * q0, sp0 * q1, sp0 * q2, sp1 * q1, sp1 * q2, sp2 * q2};
+#pragma unroll
+        for (int f = 0; f < kNF; ++f) {
+          float hi, lo;
+          tc::split_tf32(v[f], hi, lo);
+          *reinterpret_cast<float*>(sB + f * tc::kRowBytes + off[f & 7]) = hi;
+          *reinterpret_cast<float*>(sB + (kNF + f) * tc::kRowBytes + off[(kNF + f) & 7]) = lo;
+        }
+      }
+      tc::fence_smem_to_async();
+      __syncwarp();
+      const bool last = (in_round + 1 == (uint32_t)G.flush) || (lt + kProd >= lt1);
+      if (lane == 0) {
+        if (in_round == 0 && n_rounds > 0) tc::mbar_wait(&mi.bar_empty[wid], (n_rounds - 1) & 1);
+        tc::fence_after_sync();
+        const uint64_t da = tc::smem_desc_sw128(aA), db = tc::smem_desc_sw128(aB);
+        const uint32_t idesc = tc::idesc_tf32(128, kMmaN);
+        const uint32_t d_tmem = tmem + wid * kAccStride;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_ss(d_tmem, da + 2 * ks, db + 2 * ks, idesc, (in_round | ks) > 0);
+        tc::mma_commit(&mi.bar_stage[wid]);
+        if (last) tc::mma_commit(&mi.bar_full[wid]);
+      }
+      ++n_stage_uses;
+      if (last) { in_round = 0; ++n_rounds; } else { ++in_round; }
+      __syncwarp();
+    }
+    // per-warp sums of the scalar certificates (fixed shuffle tree)
+    double v;
+    v = warp_sum(ent_dot); if (lane == 0) mi.ex[wid][kExEntDot] = v;
+    v = warp_sum(ent_log); if (lane == 0) mi.ex[wid][kExEntLog] = v;
+    v = warp_sum(sum_wdk); if (lane == 0) mi.ex[wid][kExSumWdk] = v;
+    v = warp_sum(sum_wrs); if (lane == 0) mi.ex[wid][kExSumWrs] = v;
+    v = warp_sum(n_rows);  if (lane == 0) mi.ex[wid][kExCount] = v;
+    v = warp_max(mx_resp); if (lane == 0) mi.ex[wid][5] = v;
+    segment_tail<Q>(P, G, sg, mi, stages, cta, tid, nullptr);
+  }
+}
+
+template <int Q>
+__device__ __forceinline__ void epilogue_role(const BinScanParams& P, const TcGeom& G, TcMisc& mi, unsigned char* stages,
+                                              uint32_t tmem, int cta, int tid) {
+  const int wid = tid >> 5, lane = tid & 31;
+  uint32_t n_drained[kProd];   // rounds drained per producer warp
+#pragma unroll
+  for (int w = 0; w < kProd; ++w) n_drained[w] = 0;
+  int64_t g0 = cta_tile0(G, cta);
+  const int64_t g_end = cta_tile0(G, cta + 1);
+  TcSeg sg;
+  while (next_segment<Q>(G, P.n_hyp, g0, g_end, sg)) {
+    const int64_t lt0 = sg.lt0, lt1 = sg.lt1;
+    double acc[kNF];   // per TMEM lane (= operand row): hi-feature column + lo-feature column
+#pragma unroll
+    for (int c = 0; c < kNF; ++c) acc[c] = 0.0;
+    const int q = wid - kProd;
+    const int n_seg = (int)(lt1 - lt0);
+    const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+    int rounds[kProd];
+#pragma unroll
+    for (int w = 0; w < kProd; ++w) {
+      const int tiles_w = n_seg > w ? (n_seg - w + kProd - 1) / kProd : 0;
+      rounds[w] = (tiles_w + G.flush - 1) / G.flush;
+    }
+    for (int r = 0;; ++r) {
+      bool any = false;
+#pragma unroll
+      for (int w = 0; w < kProd; ++w) {
+        if (r < rounds[w]) {
+          any = true;
+          tc::mbar_wait(&mi.bar_full[w], n_drained[w] & 1);
+          ++n_drained[w];
+          tc::fence_after_sync();
+          uint32_t a0[16], a1[16], a2[4], a3[2];
+          const uint32_t addr = tmem + lane_base + w * kAccStride;
+          tc::tmem_ld_x16(addr, a0);
+          tc::tmem_ld_x16(addr + 16, a1);
+          tc::tmem_ld_x4(addr + 32, a2);
+          tc::tmem_ld_x2(addr + 36, a3);
+          tc::tmem_ld_wait();
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&mi.bar_empty[w]);
+          // column f holds row x phi_hi[f], column 19 + f row x phi_lo[f] (2^-11 of the former): one float32 add, then
+          // the float64 accumulation
+          float v[2 * kNF];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { v[c] = __uint_as_float(a0[c]); v[16 + c] = __uint_as_float(a1[c]); }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[32 + c] = __uint_as_float(a2[c]);
+          v[36] = __uint_as_float(a3[0]); v[37] = __uint_as_float(a3[1]);
+#pragma unroll
+          for (int f = 0; f < kNF; ++f) acc[f] += (double)(v[f] + v[kNF + f]);
+        }
+      }
+      if (!any) break;
+    }
+    segment_tail<Q>(P, G, sg, mi, stages, cta, tid, acc);
+  }
+}
+
 template <int Q>
 __global__ void __launch_bounds__(TcCfg<Q>::kThreads, 1) bin_scan_tc_kernel(const BinScanParams P, const TcGeom G) {
   using C = TcCfg<Q>;
@@ -76,7 +412,7 @@ __global__ void __launch_bounds__(TcCfg<Q>::kThreads, 1) bin_scan_tc_kernel(cons
   // 1 KB alignment by pointer arithmetic on the __shared__ symbol (keeps the shared address space: STS/LDS, not generic)
   unsigned char* stages = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   TcMisc& mi = *reinterpret_cast<TcMisc*>(stages + C::kStagesBytes);
-  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, wid = tid >> 5;
   const int nb = P.n_bins;
 
   // ---- one-time setup
@@ -85,10 +421,13 @@ __global__ void __launch_bounds__(TcCfg<Q>::kThreads, 1) bin_scan_tc_kernel(cons
     const double sc = P.inv_tau * kLog2e;
     const float c2 = (float)(P.shift * kLog2e);
     for (int b = tid; b < kMaxBins; b += C::kThreads) {
-      float4 v = make_float4(0.f, 0.f, 0.f, -1.0e30f);   // bins past n_bins: e = 2^(-1e30) = 0
-      if (b < nb) v = make_float4((float)(P.bin_dirs[3 * b] * sc), (float)(P.bin_dirs[3 * b + 1] * sc),
-                                  (float)(P.bin_dirs[3 * b + 2] * sc), -c2);
-      mi.bins[b] = v;
+      float x = 0.f, y = 0.f, z = 0.f, w = -1.0e30f;   // bins past n_bins: e = 2^(-1e30) = 0
+      if (b < nb) {
+        x = (float)(P.bin_dirs[3 * b] * sc); y = (float)(P.bin_dirs[3 * b + 1] * sc); z = (float)(P.bin_dirs[3 * b + 2] * sc);
+        w = -c2;
+      }
+      mi.bins2[2 * b] = make_float4(x, x, y, y);
+      mi.bins2[2 * b + 1] = make_float4(z, z, w, w);
     }
   }
   if (tid == 0) {
@@ -106,245 +445,13 @@ __global__ void __launch_bounds__(TcCfg<Q>::kThreads, 1) bin_scan_tc_kernel(cons
   tc::fence_after_sync();
   const uint32_t tmem = mi.tmem;
 
-  // ---- persistent range of this CTA
-  const int cta = blockIdx.x;
-  const int64_t g_begin = cta_tile0(G, cta), g_end = cta_tile0(G, cta + 1);
-
-  // per-thread state that survives across unit segments
-  uint32_t n_stage_uses = 0, n_rounds = 0;        // producer: uses of the operand tile / finished accumulator rounds
-  uint32_t n_drained[kProd];                      // epilogue: rounds drained per producer warp
-#pragma unroll
-  for (int w = 0; w < kProd; ++w) n_drained[w] = 0;
-  // lane-dependent byte offsets of this lane's element inside a row, for the 8 row phases of the swizzle
-  uint32_t off[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) off[j] = (uint32_t)((((lane >> 2) ^ j) << 4) | ((lane & 3) << 2));
-
-  for (int64_t g0 = g_begin; g0 < g_end;) {
-    const int u = (int)(g0 / G.tiles_per_unit);
-    const int64_t unit_t0 = (int64_t)u * G.tiles_per_unit;
-    const int64_t g1 = (unit_t0 + G.tiles_per_unit < g_end) ? unit_t0 + G.tiles_per_unit : g_end;
-    const int64_t lt0 = g0 - unit_t0, lt1 = g1 - unit_t0;   // local tile range inside unit u
-    const int s = u / P.n_hyp, h = u - s * P.n_hyp;
-
-    if (wid < kProd) {
-      // =============================== producer warp ===============================
-      unsigned char* sA = stages + wid * C::kStageBytes;
-      unsigned char* sB = sA + C::kABytes;
-      const uint32_t aA = tc::smem_u32(sA), aB = tc::smem_u32(sB);
-      const double t0 = P.t0s[s], t1 = P.t1s[s];
-      const double inv_denom = 1.0 / fmax(t1 - t0, 1e-12);
-      const double inv_sig = window_inv_sigma(t0, t1);
-      double xi[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) xi[k] = P.xi[(int64_t)u * 6 + k];
-      const double mass_scale = P.mass[s * kNMass + kMassAll] / (P.mass[s * kNMass + kMassSel] + P.eps_mass);
-      const double* pts = P.pts + (int64_t)s * P.n_raw * 3;
-      const double* tp = P.t + (int64_t)s * P.n_raw;
-      const double* wp = P.w + (int64_t)s * P.n_raw;
-      const uint8_t* rp = P.ring ? P.ring + (int64_t)s * P.n_raw : nullptr;
-      const uint8_t* gp = P.tag ? P.tag + (int64_t)s * P.n_raw : nullptr;
-      double ent_dot = 0.0, ent_log = 0.0, mx_resp = 0.0, sum_wdk = 0.0, sum_wrs = 0.0, n_rows = 0.0;
-      uint32_t in_round = 0;
-
-      // software pipeline: the raw rows of the warp's next tile are requested before this tile is processed
-      double nx[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-      uint8_t nrg = 0, ntg = 0;
-      auto fetch = [&](int64_t tile) {
-        const int64_t ii = tile * tc::kTileK + lane;
-        nx[0] = nx[1] = nx[2] = nx[3] = nx[4] = 0.0; nrg = 0; ntg = 0;
-        if (tile < lt1 && ii < P.n_sel) {
-          const int64_t j = ii * P.stride;
-          nx[0] = pts[3 * j]; nx[1] = pts[3 * j + 1]; nx[2] = pts[3 * j + 2];
-          nx[3] = tp[j]; nx[4] = wp[j];
-          if (rp) nrg = rp[j];
-          if (gp) ntg = gp[j];
-        }
-      };
-      fetch(lt0 + wid);
-      for (int64_t lt = lt0 + wid; lt < lt1; lt += kProd) {
-        const int64_t i = lt * tc::kTileK + lane;
-        const bool row = i < P.cap;
-        const double p[3] = {nx[0], nx[1], nx[2]}, tt = nx[3], ww = nx[4];
-        const uint8_t rg = nrg, tg = ntg;
-        fetch(lt + kProd);
-        const double w_rs = ww * mass_scale;
-        if (row && h == 0 && P.rs_pts) {
-          const int64_t o = (int64_t)s * P.cap + i;
-          P.rs_pts[3 * o] = p[0]; P.rs_pts[3 * o + 1] = p[1]; P.rs_pts[3 * o + 2] = p[2];
-          P.rs_t[o] = tt; P.rs_w[o] = w_rs; P.rs_ring[o] = rg; P.rs_tag[o] = tg;
-        }
-        const double alpha = (tt - t0) * inv_denom;
-        double p0[3];
-        deskew_point(p, alpha, xi, p0);
-        const double w_dk = w_rs * window_weight(tt, t0, t1, inv_sig);
-        if (row) {
-          const int64_t o = (int64_t)u * P.cap + i;
-          if (P.dk_pts) { P.dk_pts[3 * o] = p0[0]; P.dk_pts[3 * o + 1] = p0[1]; P.dk_pts[3 * o + 2] = p0[2]; }
-          if (P.dk_w) P.dk_w[o] = w_dk;
-          sum_wdk += w_dk; sum_wrs += w_rs; n_rows += 1.0;
-        }
-        const double r0 = p0[0] - P.origin[0], r1 = p0[1] - P.origin[1], r2 = p0[2] - P.origin[2];
-        const double nrm = sqrt(r0 * r0 + r1 * r1 + r2 * r2);
-        const double invn = 1.0 / (nrm + P.eps_mass);
-        const double d0 = r0 * invn, d1 = r1 * invn, d2 = r2 * invn;
-        const float f0 = (float)d0, f1 = (float)d1, f2 = (float)d2;
-
-        // the tensor core may still be reading this warp's previous tile
-        if (n_stage_uses > 0) tc::mbar_wait(&mi.bar_stage[wid], (n_stage_uses - 1) & 1);
-
-        // ---- A = [e_hi ; e_lo]: softmax numerators in log2 units, unnormalised (1/Z goes into B)
-        float sum = 0.f, dot = 0.f, emax = 0.f;
-#pragma unroll
-        for (int b = 0; b < C::kBinsPad; ++b) {
-          const float4 bb = mi.bins[b];
-          const float l = fmaf(f0, bb.x, fmaf(f1, bb.y, fmaf(f2, bb.z, bb.w)));
-          float e;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(l));
-          sum += e;
-          dot = fmaf(e, l, dot);
-          emax = fmaxf(emax, e);
-          float hi, lo;
-          tc::split_tf32(e, hi, lo);
-          *reinterpret_cast<float*>(sA + b * tc::kRowBytes + off[b & 7]) = hi;
-          *reinterpret_cast<float*>(sA + (C::kBinsPad + b) * tc::kRowBytes + off[b & 7]) = lo;
-        }
-        const double ssum = (double)sum;
-        const double inv = 1.0 / ssum;
-        if (row) {
-          ent_dot = fma(inv * kLn2, (double)dot, ent_dot);
-          ent_log += log(ssum);
-          mx_resp = fmax(mx_resp, (double)emax * inv);
-        }
-        // ---- B = [phi_hi ; phi_lo], phi = (w / Z) * (1, d, d d^T, p, p p^T)
-        {
-          const double sc = row ? w_dk * inv : 0.0;
-          const double sd0 = sc * d0, sd1 = sc * d1, sd2 = sc * d2;
-          const double sp0 = sc * p0[0], sp1 = sc * p0[1], sp2 = sc * p0[2];
-          const double v[kNF] = {sc, sd0, sd1, sd2, sd0 * d0, sd0 * d1, sd0 * d2, sd1 * d1, sd1 * d2, sd2 * d2,
-                                 sp0, sp1, sp2, sp0 * p0[0], sp0 * p0[1], sp0 * p0[2], sp1 * p0[1], sp1 * p0[2], sp2 * p0[2]};
-#pragma unroll
-          for (int f = 0; f < kNF; ++f) {
-            float hi, lo;
-            tc::split_tf32((float)v[f], hi, lo);
-            *reinterpret_cast<float*>(sB + f * tc::kRowBytes + off[f & 7]) = hi;
-            *reinterpret_cast<float*>(sB + (kNF + f) * tc::kRowBytes + off[(kNF + f) & 7]) = lo;
-          }
-        }
-        tc::fence_smem_to_async();
-        __syncwarp();
-        const bool last = (in_round + 1 == (uint32_t)G.flush) || (lt + kProd >= lt1);
-        if (lane == 0) {
-          if (in_round == 0 && n_rounds > 0) tc::mbar_wait(&mi.bar_empty[wid], (n_rounds - 1) & 1);
-          tc::fence_after_sync();
-          const uint64_t da = tc::smem_desc_sw128(aA), db = tc::smem_desc_sw128(aB);
-          const uint32_t idesc = tc::idesc_tf32(128, kMmaN);
-          const uint32_t d_tmem = tmem + wid * kAccStride;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_ss(d_tmem, da + 2 * ks, db + 2 * ks, idesc, (in_round | ks) > 0);
-          tc::mma_commit(&mi.bar_stage[wid]);
-          if (last) tc::mma_commit(&mi.bar_full[wid]);
-        }
-        ++n_stage_uses;
-        if (last) { in_round = 0; ++n_rounds; } else { ++in_round; }
-        __syncwarp();
-      }
-      // per-warp sums of the scalar certificates (fixed shuffle tree)
-      double v;
-      v = warp_sum(ent_dot); if (lane == 0) mi.ex[wid][kExEntDot] = v;
-      v = warp_sum(ent_log); if (lane == 0) mi.ex[wid][kExEntLog] = v;
-      v = warp_sum(sum_wdk); if (lane == 0) mi.ex[wid][kExSumWdk] = v;
-      v = warp_sum(sum_wrs); if (lane == 0) mi.ex[wid][kExSumWrs] = v;
-      v = warp_sum(n_rows);  if (lane == 0) mi.ex[wid][kExCount] = v;
-      v = warp_max(mx_resp); if (lane == 0) mi.ex[wid][5] = v;
-    }
-
-    // =============================== epilogue warps ===============================
-    double acc[2 * kNF];
-    if (wid >= kProd) {
-#pragma unroll
-      for (int c = 0; c < 2 * kNF; ++c) acc[c] = 0.0;
-      const int q = wid - kProd;
-      const int n_seg = (int)(lt1 - lt0);
-      const uint32_t lane_base = (uint32_t)(32 * q) << 16;
-      int rounds[kProd];
-#pragma unroll
-      for (int w = 0; w < kProd; ++w) {
-        const int tiles_w = n_seg > w ? (n_seg - w + kProd - 1) / kProd : 0;
-        rounds[w] = (tiles_w + G.flush - 1) / G.flush;
-      }
-      for (int r = 0;; ++r) {
-        bool any = false;
-#pragma unroll
-        for (int w = 0; w < kProd; ++w) {
-          if (r < rounds[w]) {
-            any = true;
-            tc::mbar_wait(&mi.bar_full[w], n_drained[w] & 1);
-            ++n_drained[w];
-            tc::fence_after_sync();
-            uint32_t a0[16], a1[16], a2[4], a3[2];
-            const uint32_t addr = tmem + lane_base + w * kAccStride;
-            tc::tmem_ld_x16(addr, a0);
-            tc::tmem_ld_x16(addr + 16, a1);
-            tc::tmem_ld_x4(addr + 32, a2);
-            tc::tmem_ld_x2(addr + 36, a3);
-            tc::tmem_ld_wait();
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&mi.bar_empty[w]);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) acc[c] += (double)__uint_as_float(a0[c]);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) acc[16 + c] += (double)__uint_as_float(a1[c]);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[32 + c] += (double)__uint_as_float(a2[c]);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) acc[36 + c] += (double)__uint_as_float(a3[c]);
-          }
-        }
-        if (!any) break;
-      }
-    }
-
-    // =============================== combine the segment ===============================
-    __syncthreads();   // every MMA of the segment has completed (the epilogue waited for all of them)
-    double* red = reinterpret_cast<double*>(stages);   // operand tiles are idle now
-    if (wid >= kProd) {
-      const int R = 32 * (wid - kProd) + lane;
-#pragma unroll
-      for (int f = 0; f < kNF; ++f) red[R * kNF + f] = acc[f] + acc[kNF + f];
-    }
-    __syncthreads();
-    {
-      const int slot = cta - cta_of_tile(G, unit_t0);
-      double* part = P.partial + ((int64_t)u * G.n_parts + slot) * P.part_len;
-      for (int idx = tid; idx < nb * kNF; idx += C::kThreads) {
-        const int b = idx / kNF, f = idx - b * kNF;
-        part[b * kRowLen + f] = red[b * kNF + f] + red[(C::kBinsPad + b) * kNF + f];
-      }
-      if (tid < kNExtras + kNMax) {
-        double* ex = part + nb * kRowLen;
-        double r = 0.0;
-        if (tid <= kExCount) {
-          for (int w = 0; w < kProd; ++w) r += mi.ex[w][tid];
-          ex[tid] = r;
-        } else if (tid < kNExtras) {
-          ex[tid] = 0.0;
-        } else if (tid == kNExtras + kMxResp) {
-          for (int w = 0; w < kProd; ++w) r = fmax(r, mi.ex[w][5]);
-          ex[tid] = r;
-        } else {
-          ex[tid] = 0.0;
-        }
-      }
-    }
-    __syncthreads();
-    // the scratch area must read as finite floats again where padding rows alias it (any bit pattern is harmless for
-    // the rows that matter, but keep NaN payloads out of the accumulator columns nobody reads)
-    for (int k = tid; k < (C::kRows * kNF * 8 + 15) / 16; k += C::kThreads) reinterpret_cast<uint4*>(stages)[k] = make_uint4(0, 0, 0, 0);
-    tc::fence_smem_to_async();
-    __syncthreads();
-    g0 = g1;
+  // ---- roles.  Register re-allocation: the two producer warpgroups take what the epilogue warpgroup gives up.
+  if (wid < kProd) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    producer_role<Q>(P, G, mi, stages, tmem, blockIdx.x, tid);
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    epilogue_role<Q>(P, G, mi, stages, tmem, blockIdx.x, tid);
   }
 
   tc::fence_before_sync();

@@ -510,6 +510,132 @@ __device__ inline double window_inv_sigma(double t0, double t1) {
   return 1.0 / fmax(kTimeWarpSigmaFrac * fmax(t1 - t0, 1e-12), 1e-6);
 }
 
+// ---- division-free float64 helpers (MUFU seed + Newton; ~1 ulp, no denormal/branchy slow path) -------------------
+// x must be finite and > 0 (or +inf: returns 0).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+// 1/sqrt(x) for finite x > 0
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  return fma(y, e, y);
+}
+// 2^t for |t| <= 1000 (clamped): same polynomial as exp2_nonpos
+__device__ __forceinline__ double exp2_bounded(double t) {
+  t = fmin(fmax(t, -1000.0), 1000.0);
+  const double magic = 6755399441055744.0;
+  const double tm = t + magic;
+  const int k = __double2loint(tm);
+  const double r = t - (tm - magic);
+  double q = 1.3691488853904128e-12;
+  q = fma(q, r, 2.5678435993488206e-11);
+  q = fma(q, r, 4.4455382718708116e-10);
+  q = fma(q, r, 7.054911620801123e-09);
+  q = fma(q, r, 1.01780860092397e-07);
+  q = fma(q, r, 1.321548679014431e-06);
+  q = fma(q, r, 1.5252733804059841e-05);
+  q = fma(q, r, 0.0001540353039338161);
+  q = fma(q, r, 0.0013333558146428443);
+  q = fma(q, r, 0.009618129107628477);
+  q = fma(q, r, 0.05550410866482158);
+  q = fma(q, r, 0.24022650695910072);
+  q = fma(q, r, 0.6931471805599453);
+  q = fma(q, r, 1.0);
+  return __hiloint2double(__double2hiint(q) + (k << 20), __double2loint(q));
+}
+
+// ---- constant-twist deskew with the per-scan invariants hoisted ---------------------------------------------------
+// xi = (rho, phi).  For a point at sweep fraction a:  R = Exp(a phi), t = V(a phi) a rho,  p0 = R^T (p - t), with
+//   K = [phi]x:   t  = a (rho + a (C c1 + a G c2)),  c1 = phi x rho,  c2 = K^2 rho = phi (phi.rho) - |phi|^2 rho
+//                 p0 = q - S a (phi x q) + C a^2 (phi (phi.q) - |phi|^2 q),   q = p - t
+// S, C, G = sin(th)/th, (1-cos th)/th^2, (th - sin th)/th^3 at th = a |phi| (Maclaurin series in th^2).
+// Same algebra as deskew_point (se3_jax.py:473-504, deskew_constant_twist.py:48-56); ~60 flops per point instead of ~105.
+struct TwistCtx {
+  double rho[3], phi[3], c1[3], c2[3], th1sq;
+  const double* xi;
+};
+__device__ inline TwistCtx make_twist_ctx(const double* xi) {
+  TwistCtx c;
+  c.xi = xi;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { c.rho[k] = xi[k]; c.phi[k] = xi[3 + k]; }
+  c.th1sq = c.phi[0] * c.phi[0] + c.phi[1] * c.phi[1] + c.phi[2] * c.phi[2];
+  c.c1[0] = c.phi[1] * c.rho[2] - c.phi[2] * c.rho[1];
+  c.c1[1] = c.phi[2] * c.rho[0] - c.phi[0] * c.rho[2];
+  c.c1[2] = c.phi[0] * c.rho[1] - c.phi[1] * c.rho[0];
+  const double pr = c.phi[0] * c.rho[0] + c.phi[1] * c.rho[1] + c.phi[2] * c.rho[2];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) c.c2[k] = c.phi[k] * pr - c.th1sq * c.rho[k];
+  return c;
+}
+__device__ __forceinline__ void deskew_point_ctx(const double* p, double a, const TwistCtx& c, double* p0) {
+  const double a2 = a * a;
+  const double th2 = a2 * c.th1sq;
+  if (!(th2 < 0.25)) {   // large angles (garbage sweep fractions of zero-stamped padded rows): reference closed forms
+    deskew_point(p, a, c.xi, p0);
+    return;
+  }
+  double S, C, G;
+  if (th2 < 0.01) {      // truncation < th2^5 / 11! < 3e-18
+    S = -2.505210838544172e-08;              C = -2.08767569878681e-09;              G = -1.6059043836821613e-10;
+    S = fma(S, th2, 2.7557319223985893e-06); C = fma(C, th2, 2.755731922398589e-07); G = fma(G, th2, 2.505210838544172e-08);
+  } else {
+    S = 2.8114572543455206e-15;              C = 1.5619206968586225e-16;              G = 8.22063524662433e-18;
+    S = fma(S, th2, -7.647163731819816e-13); C = fma(C, th2, -4.779477332387385e-14); G = fma(G, th2, -2.8114572543455206e-15);
+    S = fma(S, th2, 1.6059043836821613e-10); C = fma(C, th2, 1.1470745597729725e-11); G = fma(G, th2, 7.647163731819816e-13);
+    S = fma(S, th2, -2.505210838544172e-08); C = fma(C, th2, -2.08767569878681e-09);  G = fma(G, th2, -1.6059043836821613e-10);
+    S = fma(S, th2, 2.7557319223985893e-06); C = fma(C, th2, 2.755731922398589e-07);  G = fma(G, th2, 2.505210838544172e-08);
+  }
+  S = fma(S, th2, -0.0001984126984126984); C = fma(C, th2, -2.48015873015873e-05);  G = fma(G, th2, -2.7557319223985893e-06);
+  S = fma(S, th2, 0.008333333333333333);   C = fma(C, th2, 0.001388888888888889);   G = fma(G, th2, 0.0001984126984126984);
+  S = fma(S, th2, -0.16666666666666666);   C = fma(C, th2, -0.041666666666666664);  G = fma(G, th2, -0.008333333333333333);
+  S = fma(S, th2, 1.0);                    C = fma(C, th2, 0.5);                    G = fma(G, th2, 0.16666666666666666);
+  const double aG = a * G;
+  double q[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double u = fma(aG, c.c2[k], C * c.c1[k]);
+    q[k] = fma(-a, fma(a, u, c.rho[k]), p[k]);
+  }
+  const double x0 = c.phi[1] * q[2] - c.phi[2] * q[1];
+  const double x1 = c.phi[2] * q[0] - c.phi[0] * q[2];
+  const double x2 = c.phi[0] * q[1] - c.phi[1] * q[0];
+  const double pq = fma(c.phi[0], q[0], fma(c.phi[1], q[1], c.phi[2] * q[2]));
+  const double sa = S * a, ca = C * a2;
+  p0[0] = fma(ca, fma(c.phi[0], pq, -c.th1sq * q[0]), fma(-sa, x0, q[0]));
+  p0[1] = fma(ca, fma(c.phi[1], pq, -c.th1sq * q[1]), fma(-sa, x1, q[1]));
+  p0[2] = fma(ca, fma(c.phi[2], pq, -c.th1sq * q[2]), fma(-sa, x2, q[2]));
+}
+
+// ---- window weight with one exponential and no division -----------------------------------------------------------
+// sigmoid(a) sigmoid(b) with a + b = S = (t1 - t0)/sigma constant over the scan:  x = e^-a, c = e^-S
+//   1 / ((1 + x)(1 + c/x)) = x / (c + x (1 + c + x)).
+struct WindowCtx { double t0, inv_sig, c, one_plus_c; };
+__device__ inline WindowCtx make_window_ctx(double t0, double t1) {
+  WindowCtx w;
+  w.t0 = t0;
+  w.inv_sig = window_inv_sigma(t0, t1);
+  w.c = exp(-(t1 - t0) * w.inv_sig);
+  w.one_plus_c = 1.0 + w.c;
+  return w;
+}
+__device__ __forceinline__ double window_weight_ctx(double t, const WindowCtx& w) {
+  const double a = (t - w.t0) * w.inv_sig;
+  const double x = exp2_bounded(fmin(a * -1.4426950408889634, 500.0));   // x^2 must stay finite
+  const double den = fma(x, w.one_plus_c + x, w.c);
+  return fma(x * fast_rcp(den), 1.0 - kWeightFloor, kWeightFloor);
+}
+
 __device__ inline double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
