@@ -3,7 +3,7 @@
 bench.py -- LiDAR evidence path throughput on B200 (contract in the task statement, tier section 4).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scans S] [--points P]
-                    [--precision f64|mixed]
+                    [--precision tc|mixed|f64]
 
 Workload (N=1, BASELINE.json metric "LiDAR evidence path scans/s ... @65k pts"): the full bin-family path
 (PointBudgetResample -> DeskewConstantTwist -> ray directions -> BinSoftAssign -> ScanBinMomentMatch+kappa ->
@@ -286,7 +286,7 @@ def run_ours(args):
     from gc_slam_b200 import synth
 
     S, P = args.scans, args.points
-    prec = L.PREC_F64 if args.precision == "f64" else L.PREC_MIXED
+    prec = {"f64": L.PREC_F64, "mixed": L.PREC_MIXED, "tc": L.PREC_TC}[args.precision]
     batch = make_batch(S, P, 1000 + 100 * rank)
     plan = ops.BinPathPlan(S, P, P, n_hyp=1, n_bins=N_BINS, tau=TAU, origin=synth.lidar_origin_base(), precision=prec,
                            want_evidence=True, materialize_deskewed=True)
@@ -415,6 +415,35 @@ def run_ours(args):
         lat = {"p50_ms_host_in_evidence_out": 1e3 * float(np.median(ts_e2e)),
                "p50_ms_device_resident": 1e3 * float(np.median(ts_dev)), "points": P, "reps": 50}
 
+    # the same batch through the all-float64 kernels (reference dtype), for the record next to the headline precision
+    f64_leg = None
+    if rank == 0 and world == 1 and args.precision != "f64":
+        plan64 = ops.BinPathPlan(S, P, P, n_hyp=1, n_bins=N_BINS, tau=TAU, origin=synth.lidar_origin_base(),
+                                 precision=L.PREC_F64, want_evidence=True, materialize_deskewed=True)
+        plan64.set_bins(bins, TAU)
+        plan64.set_map(synth.random_map_bin_stats(N_BINS, 7, bins))
+        plan64.upload(host["pts"], host["t"], host["w"], host["ring"], host["tag"], host["t0"], host["t1"], host["xi"],
+                      host["poses"])
+        for _ in range(3):
+            plan64.run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            plan64.run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms64 = e0.elapsed_time(e1) / 5
+        o64, otc = plan64.outputs(), plan.outputs()
+
+        def _rel(a, b):
+            return float((a - b).abs().max() / b.abs().max())
+        f64_leg = {"ms_per_step": ms64, "scans_per_s": S / (ms64 * 1e-3),
+                   "max_rel_diff_vs_headline_precision": {k: _rel(otc.stats[k], o64.stats[k]) for k in ("N", "S_scatter", "Sigma_p", "kappa")
+                                                          if k in o64.stats},
+                   "L22_rel_diff": _rel(otc.L22, o64.L22)}
+        del plan64
+
     prim = None
     if rank == 0 and world == 1 and not args.no_prim:
         prim = primitive_path_extra(P)
@@ -423,38 +452,49 @@ def run_ours(args):
         bytes_per_launch = S * (BYTES_IN_PER_PT * P + BYTES_OUT_PER_PT * P)
         k_avg_ms = k_ms / max(k_n, 1)
         achieved = bytes_per_launch / (k_avg_ms * 1e-3) / 1e9
+        kernel_name = KERNEL_OF[args.precision]
         traffic = None
         prof = os.path.join(ROOT, "profiles", "bin_scan_traffic.json")
         if os.path.exists(prof):
             try:
                 with open(prof) as f:
-                    traffic = json.load(f).get("dram_bytes_per_launch")
+                    tj = json.load(f)
+                ent = tj.get(kernel_name, tj if "dram_bytes_per_launch" in tj else None)
+                # the capture is of a 128-scan x 65536-point launch; traffic scales with the points of a launch
+                if ent:
+                    traffic = ent["dram_bytes_per_launch"] * (S * P) / float(ent.get("points_in_profiled_launch", 128 * 65536))
             except Exception:
                 traffic = None
         cpu = cpu_baseline_single(P) if world == 1 and not args.no_cpu else None
         line = {
             "metric": "lidar_evidence_path_scans_per_s", "value": value, "unit": "scans/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_OF[args.precision], "data": "synthetic",
             "config": workload_config(args, S),
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "steps": e_steps,
                     "how": "2 plans on 2 streams (copy of batch k+1 overlaps kernels of batch k); wall clock between syncs"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "bin_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(bytes_per_launch), "kernel_ms_avg": k_avg_ms,
                          "kernel_launches_timed": k_n, "kernel_share_of_step": k_ms / ms_total},
             "latency": lat,
             "points_per_s": value * P,
-            "extra": {"primitive_path": prim},
+            "extra": {"primitive_path": prim, "float64_path": f64_leg},
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+KERNEL_OF = {"f64": "bin_scan_kernel", "mixed": "bin_scan_kernel", "tc": "bin_scan_tc_kernel"}
+DTYPE_OF = {"f64": "f64",
+            "mixed": "f64 (f32 MUFU soft-assign exponentials)",
+            "tc": "f64 geometry/epilogue + f32 soft-assign + tf32x2 tensor-core moments flushed to f64"}
 
 
 def main():
@@ -465,7 +505,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scans", type=int, default=128, help="scans per step per GPU")
     ap.add_argument("--points", type=int, default=65536)
-    ap.add_argument("--precision", default="f64", choices=["f64", "mixed"])
+    ap.add_argument("--precision", default="tc", choices=["tc", "mixed", "f64"],
+                    help="tc: tcgen05 moment contraction (tf32 hi/lo operands, float64 flushes), float32 soft-assign, float64 "
+                         "geometry -- inside the 1e-5 parity tolerance (tests/test_gpu_bins.py); f64: everything float64")
     ap.add_argument("--no-cpu", action="store_true", help="skip the in-run CPU baseline")
     ap.add_argument("--no-prim", action="store_true", help="skip the primitive-path (config 3) stage timings")
     args = ap.parse_args()

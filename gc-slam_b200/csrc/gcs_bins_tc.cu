@@ -29,20 +29,26 @@ namespace gcs {
 
 namespace {
 
-constexpr int kProd = 8;            // producer warps per CTA
-constexpr int kAccStride = 64;      // TMEM columns between per-warp accumulators (8 x 64 = 512 = all of TMEM)
-constexpr int kMmaN = 48;           // >= 2 * kNF, multiple of 16
+constexpr int kMaxProd = 12;        // producer warps per CTA (upper bound; see TcCfg)
+constexpr int kMmaN = 40;           // >= 2 * kNF, multiple of 8 (N = 40 at M = 128 is a legal tcgen05 shape: tools/tc_probe.cu)
+constexpr int kAccStride = kMmaN;   // TMEM columns between per-warp accumulators (12 x 40 = 480 <= 512)
 constexpr int kBRows = 40;          // B tile rows kept in shared memory (38 used)
 constexpr double kLog2e = 1.4426950408889634;
 constexpr double kLn2 = 0.6931471805599453;
 
 template <int Q>
 struct TcCfg {
+  // producer warps: as many 17 KB / 21 KB operand tiles as fit in shared memory, in whole warpgroups
+  static constexpr int kProd = Q <= 3 ? 12 : 8;
+  static constexpr int kRegProd = Q <= 3 ? 136 : 184;   // setmaxnreg targets (launch allocation 128 per thread)
+  static constexpr int kRegEpi = 104;
   static constexpr int kBinsPad = 16 * Q;   // rows of the e_hi block == first row of the e_lo block
   static constexpr int kRows = 32 * Q;      // rows of A that carry data
-  static constexpr int kEpi = 4;            // epilogue warps: a full warpgroup, one warp per 32 TMEM lanes (for Q = 3 the
-                                            // fourth drains padding lanes; it keeps the register re-allocation aligned)
-  static constexpr int kThreads = 32 * (kProd + kEpi);
+  // Warpgroup after the producers: epilogue warps, one per 32 TMEM lanes that carry data (Q of them).  For Q = 3 its
+  // fourth warp is the MMA issuer; for Q = 4 the issuer is the first warp of one more (otherwise idle) warpgroup.
+  static constexpr int kEpi = Q;
+  static constexpr int kIssuerWarp = Q <= 3 ? kProd + 3 : kProd + 4;
+  static constexpr int kThreads = Q <= 3 ? 32 * (kProd + 4) : 32 * (kProd + 8);
   static constexpr int kABytes = kRows * tc::kRowBytes;
   static constexpr int kBBytes = kBRows * tc::kRowBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;            // 17 KB (Q=3) / 21 KB (Q=4): multiples of 1 KB
@@ -51,11 +57,14 @@ struct TcCfg {
 
 struct TcMisc {
   float4 bins2[kMaxBins * 2];  // per bin: (bx, bx, by, by), (bz, bz, -c2, -c2), pre-scaled by log2(e)/tau
-  uint64_t bar_stage[kProd];   // MMAs that read the warp's operand tile have completed
-  uint64_t bar_full[kProd];    // the warp's accumulator holds a finished round
-  uint64_t bar_empty[kProd];   // the epilogue has drained it
+  uint64_t bar_tile[kMaxProd];    // the producer warp has written (and fenced) its operand tile
+  uint64_t bar_stage[kMaxProd];   // MMAs that read the warp's operand tile have completed
+  uint64_t bar_full[kMaxProd];    // the warp's accumulator holds a finished round
+  uint64_t bar_empty[kMaxProd];   // the epilogue has drained it
   uint32_t tmem;
-  double ex[kProd][8];
+  double ex[kMaxProd][8];
+  TwistCtx tw[kMaxProd];        // per producer warp: hoisted invariants of the current unit (reloaded every tile)
+  WindowCtx win[kMaxProd];
 };
 
 struct TcGeom {
@@ -92,6 +101,7 @@ template <int Q>
 __device__ __forceinline__ void write_partial(const BinScanParams& P, const TcGeom& G, const TcSeg& sg, const TcMisc& mi,
                                               const double* red, int cta, int tid) {
   using C = TcCfg<Q>;
+  constexpr int kProd = C::kProd;
   const int nb = P.n_bins;
   const int slot = cta - cta_of_tile(G, sg.unit_t0);
   double* part = P.partial + ((int64_t)sg.u * G.n_parts + slot) * P.part_len;
@@ -122,6 +132,7 @@ template <int Q>
 __device__ __forceinline__ void segment_tail(const BinScanParams& P, const TcGeom& G, const TcSeg& sg, TcMisc& mi,
                                              unsigned char* stages, int cta, int tid, const double* acc_or_null) {
   using C = TcCfg<Q>;
+  constexpr int kProd = C::kProd;
   double* red = reinterpret_cast<double*>(stages);   // operand tiles are idle: every MMA of the segment has completed
   bar_all(C::kThreads);
   if (acc_or_null) {
@@ -142,8 +153,9 @@ template <int Q>
 __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGeom& G, TcMisc& mi, unsigned char* stages,
                                               uint32_t tmem, int cta, int tid) {
   using C = TcCfg<Q>;
+  constexpr int kProd = C::kProd;
   const int wid = tid >> 5, lane = tid & 31;
-  uint32_t n_stage_uses = 0, n_rounds = 0;   // uses of the operand tile / finished accumulator rounds
+  uint32_t n_stage_uses = 0;   // uses of the operand tile
   // lane-dependent byte offsets of this lane's element inside a row, for the 8 row phases of the swizzle
   uint32_t off[8];
 #pragma unroll
@@ -163,8 +175,9 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
     const uint32_t aA = tc::smem_u32(sA), aB = tc::smem_u32(sB);
     const double t0 = P.t0s[s], t1 = P.t1s[s];
     const double inv_denom = 1.0 / fmax(t1 - t0, 1e-12);
-    const WindowCtx wctx = make_window_ctx(t0, t1);
-    const TwistCtx tw = make_twist_ctx(P.xi + (int64_t)u * 6);
+    __syncwarp();
+    if (lane == 0) { mi.win[wid] = make_window_ctx(t0, t1); mi.tw[wid] = make_twist_ctx(P.xi + (int64_t)u * 6); }
+    __syncwarp();
     const double mass_scale = P.mass[s * kNMass + kMassAll] / (P.mass[s * kNMass + kMassSel] + P.eps_mass);
     const double* pts = P.pts + (int64_t)s * P.n_raw * 3;
     const double* tp = P.t + (int64_t)s * P.n_raw;
@@ -172,13 +185,12 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
     const uint8_t* rp = P.ring ? P.ring + (int64_t)s * P.n_raw : nullptr;
     const uint8_t* gp = P.tag ? P.tag + (int64_t)s * P.n_raw : nullptr;
     double ent_dot = 0.0, ent_log = 0.0, mx_resp = 0.0, sum_wdk = 0.0, sum_wrs = 0.0, n_rows = 0.0;
-    uint32_t in_round = 0;
     // pair layout of the soft-assign stage: lane = (half, j); the lane evaluates bins [half*NB2, half*NB2 + NB2) for
     // the two points 2j, 2j+1 of the tile (packed f32x2 math, 8-byte operand stores)
     constexpr int NB2 = C::kBinsPad / 2;
     const int half = lane >> 4, pj = lane & 15;
     unsigned char* sA_lane = sA + half * NB2 * tc::kRowBytes;
-    const float4* bins_lane = mi.bins2 + half * NB2 * 2;
+    const float4* bins_lane = mi.bins2 + half * 2;   // entry i of this half at bins_lane[4 * i], [4 * i + 1]
 
     // software pipeline: the raw rows of the warp's next tile are requested before this tile is processed
     double nx[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -210,8 +222,8 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
       }
       const double alpha = (tt - t0) * inv_denom;
       double p0[3];
-      deskew_point_ctx(p, alpha, tw, p0);
-      const double w_dk = w_rs * window_weight_ctx(tt, wctx);
+      deskew_point_ctx(p, alpha, mi.tw[wid], p0);
+      const double w_dk = w_rs * window_weight_ctx(tt, mi.win[wid]);
       if (row) {
         const int64_t o = (int64_t)u * P.cap + i;
         if (P.dk_pts) { P.dk_pts[3 * o] = p0[0]; P.dk_pts[3 * o + 1] = p0[1]; P.dk_pts[3 * o + 2] = p0[2]; }
@@ -238,15 +250,15 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
       static_assert(NB2 % kGrp == 0, "bin half must be a multiple of the group size");
       float4 tab[2][kGrp][2];
 #pragma unroll
-      for (int k = 0; k < kGrp; ++k) { tab[0][k][0] = bins_lane[2 * k]; tab[0][k][1] = bins_lane[2 * k + 1]; }
+      for (int k = 0; k < kGrp; ++k) { tab[0][k][0] = bins_lane[4 * k]; tab[0][k][1] = bins_lane[4 * k + 1]; }
 #pragma unroll
       for (int g = 0; g < NB2 / kGrp; ++g) {
         const int cur = g & 1;
         if (g + 1 < NB2 / kGrp) {
 #pragma unroll
           for (int k = 0; k < kGrp; ++k) {
-            tab[cur ^ 1][k][0] = bins_lane[2 * ((g + 1) * kGrp + k)];
-            tab[cur ^ 1][k][1] = bins_lane[2 * ((g + 1) * kGrp + k) + 1];
+            tab[cur ^ 1][k][0] = bins_lane[4 * ((g + 1) * kGrp + k)];
+            tab[cur ^ 1][k][1] = bins_lane[4 * ((g + 1) * kGrp + k) + 1];
           }
         }
         float2 l[kGrp], e[kGrp], hi[kGrp], lo[kGrp];
@@ -316,21 +328,8 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
       }
       tc::fence_smem_to_async();
       __syncwarp();
-      const bool last = (in_round + 1 == (uint32_t)G.flush) || (lt + kProd >= lt1);
-      if (lane == 0) {
-        if (in_round == 0 && n_rounds > 0) tc::mbar_wait(&mi.bar_empty[wid], (n_rounds - 1) & 1);
-        tc::fence_after_sync();
-        const uint64_t da = tc::smem_desc_sw128(aA), db = tc::smem_desc_sw128(aB);
-        const uint32_t idesc = tc::idesc_tf32(128, kMmaN);
-        const uint32_t d_tmem = tmem + wid * kAccStride;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_ss(d_tmem, da + 2 * ks, db + 2 * ks, idesc, (in_round | ks) > 0);
-        tc::mma_commit(&mi.bar_stage[wid]);
-        if (last) tc::mma_commit(&mi.bar_full[wid]);
-      }
+      if (lane == 0) tc::mbar_arrive(&mi.bar_tile[wid]);   // the issuer warp takes it from here
       ++n_stage_uses;
-      if (last) { in_round = 0; ++n_rounds; } else { ++in_round; }
-      __syncwarp();
     }
     // per-warp sums of the scalar certificates (fixed shuffle tree)
     double v;
@@ -347,6 +346,7 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
 template <int Q>
 __device__ __forceinline__ void epilogue_role(const BinScanParams& P, const TcGeom& G, TcMisc& mi, unsigned char* stages,
                                               uint32_t tmem, int cta, int tid) {
+  constexpr int kProd = TcCfg<Q>::kProd;
   const int wid = tid >> 5, lane = tid & 31;
   uint32_t n_drained[kProd];   // rounds drained per producer warp
 #pragma unroll
@@ -405,6 +405,61 @@ __device__ __forceinline__ void epilogue_role(const BinScanParams& P, const TcGe
   }
 }
 
+// MMA issuer: one thread feeds the tensor core for the whole CTA, tiles taken in a fixed order (tile index, then warp) so
+// that every accumulator sees its warp's tiles in sequence.  Producers never block on the tensor-core queue.
+template <int Q>
+__device__ __forceinline__ void issuer_role(const BinScanParams& P, const TcGeom& G, TcMisc& mi, unsigned char* stages,
+                                            uint32_t tmem, int cta, int tid) {
+  using C = TcCfg<Q>;
+  constexpr int kProd = C::kProd;
+  const int lane = tid & 31;
+  uint32_t n_tiles[kProd], n_rounds[kProd];
+#pragma unroll
+  for (int w = 0; w < kProd; ++w) { n_tiles[w] = 0; n_rounds[w] = 0; }
+  int64_t g0 = cta_tile0(G, cta);
+  const int64_t g_end = cta_tile0(G, cta + 1);
+  const uint32_t idesc = tc::idesc_tf32(128, kMmaN);
+  const uint32_t a0 = tc::smem_u32(stages);
+  TcSeg sg;
+  while (next_segment<Q>(G, P.n_hyp, g0, g_end, sg)) {
+    if (lane == 0) {
+      const int n_seg = (int)(sg.lt1 - sg.lt0);
+      for (int t = 0; t * kProd < n_seg; ++t) {
+        const uint32_t in_round = (uint32_t)(t % G.flush);
+#pragma unroll
+        for (int w = 0; w < kProd; ++w) {
+          if (t * kProd + w < n_seg) {
+            tc::mbar_wait(&mi.bar_tile[w], n_tiles[w] & 1);
+            ++n_tiles[w];
+            if (in_round == 0 && n_rounds[w] > 0) tc::mbar_wait(&mi.bar_empty[w], (n_rounds[w] - 1) & 1);
+            tc::fence_after_sync();
+            const uint64_t da = tc::smem_desc_sw128(a0 + w * C::kStageBytes);
+            const uint64_t db = tc::smem_desc_sw128(a0 + w * C::kStageBytes + C::kABytes);
+            const uint32_t d_tmem = tmem + w * kAccStride;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_ss(d_tmem, da + 2 * ks, db + 2 * ks, idesc, (in_round | ks) > 0);
+            tc::mma_commit(&mi.bar_stage[w]);
+            const bool last = (in_round + 1 == (uint32_t)G.flush) || ((t + 1) * kProd + w >= n_seg);
+            if (last) { tc::mma_commit(&mi.bar_full[w]); ++n_rounds[w]; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    segment_tail<Q>(P, G, sg, mi, stages, cta, tid, nullptr);
+  }
+}
+
+// warps of the CTA that have no role in a configuration still take part in the segment barriers
+template <int Q>
+__device__ __forceinline__ void idle_role(const BinScanParams& P, const TcGeom& G, TcMisc& mi, unsigned char* stages, int cta,
+                                          int tid) {
+  int64_t g0 = cta_tile0(G, cta);
+  const int64_t g_end = cta_tile0(G, cta + 1);
+  TcSeg sg;
+  while (next_segment<Q>(G, P.n_hyp, g0, g_end, sg)) segment_tail<Q>(P, G, sg, mi, stages, cta, tid, nullptr);
+}
+
 template <int Q>
 __global__ void __launch_bounds__(TcCfg<Q>::kThreads, 1) bin_scan_tc_kernel(const BinScanParams P, const TcGeom G) {
   using C = TcCfg<Q>;
@@ -412,6 +467,7 @@ __global__ void __launch_bounds__(TcCfg<Q>::kThreads, 1) bin_scan_tc_kernel(cons
   // 1 KB alignment by pointer arithmetic on the __shared__ symbol (keeps the shared address space: STS/LDS, not generic)
   unsigned char* stages = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   TcMisc& mi = *reinterpret_cast<TcMisc*>(stages + C::kStagesBytes);
+  constexpr int kProd = C::kProd;
   const int tid = threadIdx.x, wid = tid >> 5;
   const int nb = P.n_bins;
 
@@ -420,18 +476,22 @@ __global__ void __launch_bounds__(TcCfg<Q>::kThreads, 1) bin_scan_tc_kernel(cons
   {
     const double sc = P.inv_tau * kLog2e;
     const float c2 = (float)(P.shift * kLog2e);
-    for (int b = tid; b < kMaxBins; b += C::kThreads) {
+    for (int b = tid; b < C::kBinsPad; b += C::kThreads) {
       float x = 0.f, y = 0.f, z = 0.f, w = -1.0e30f;   // bins past n_bins: e = 2^(-1e30) = 0
       if (b < nb) {
         x = (float)(P.bin_dirs[3 * b] * sc); y = (float)(P.bin_dirs[3 * b + 1] * sc); z = (float)(P.bin_dirs[3 * b + 2] * sc);
         w = -c2;
       }
-      mi.bins2[2 * b] = make_float4(x, x, y, y);
-      mi.bins2[2 * b + 1] = make_float4(z, z, w, w);
+      // interleave the two bin halves (lanes 0-15 / 16-31 read entry i of their half in the same instruction): the two
+      // 16-byte reads of a warp then fall into different banks
+      const int e = (b % (C::kBinsPad / 2)) * 2 + b / (C::kBinsPad / 2);
+      mi.bins2[2 * e] = make_float4(x, x, y, y);
+      mi.bins2[2 * e + 1] = make_float4(z, z, w, w);
     }
   }
   if (tid == 0) {
     for (int w = 0; w < kProd; ++w) {
+      tc::mbar_init(&mi.bar_tile[w], 1);
       tc::mbar_init(&mi.bar_stage[w], 1);
       tc::mbar_init(&mi.bar_full[w], 1);
       tc::mbar_init(&mi.bar_empty[w], C::kEpi);
@@ -445,13 +505,18 @@ __global__ void __launch_bounds__(TcCfg<Q>::kThreads, 1) bin_scan_tc_kernel(cons
   tc::fence_after_sync();
   const uint32_t tmem = mi.tmem;
 
-  // ---- roles.  Register re-allocation: the two producer warpgroups take what the epilogue warpgroup gives up.
+  // ---- roles.  Register re-allocation: the producer warpgroups take what the other warpgroups give up.
   if (wid < kProd) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::kRegProd));
     producer_role<Q>(P, G, mi, stages, tmem, blockIdx.x, tid);
+  } else if (wid < kProd + 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::kRegEpi));
+    if (wid < kProd + C::kEpi) epilogue_role<Q>(P, G, mi, stages, tmem, blockIdx.x, tid);
+    else issuer_role<Q>(P, G, mi, stages, tmem, blockIdx.x, tid);
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-    epilogue_role<Q>(P, G, mi, stages, tmem, blockIdx.x, tid);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (wid == C::kIssuerWarp) issuer_role<Q>(P, G, mi, stages, tmem, blockIdx.x, tid);
+    else idle_role<Q>(P, G, mi, stages, blockIdx.x, tid);
   }
 
   tc::fence_before_sync();
@@ -470,7 +535,8 @@ int tc_flush_tiles() {
   return v;
 }
 
-TcGeom make_geom(int sm_count, int n_units, int64_t cap, int n_parts) {
+TcGeom make_geom(int sm_count, int n_units, int64_t cap, int n_parts, int n_prod) {
+  const int kProd = n_prod;
   TcGeom G;
   G.tiles_per_unit = (cap + tc::kTileK - 1) / tc::kTileK;
   G.total_tiles = G.tiles_per_unit * n_units;
@@ -501,7 +567,7 @@ cudaError_t launch_q(cudaStream_t st, const BinScanParams& P, const TcGeom& G) {
 
 // a unit is touched by at most ceil(n_cta / U) + 1 CTAs
 int bin_scan_tc_parts(int sm_count, int n_units, int64_t cap) {
-  TcGeom G = make_geom(sm_count, n_units, cap, 0);
+  TcGeom G = make_geom(sm_count, n_units, cap, 0, 8);   // fewest producer warps of any instantiation: most CTAs
   return (G.n_cta + n_units - 1) / n_units + 1;
 }
 
@@ -511,8 +577,8 @@ bool bin_scan_tc_supported(const BinScanParams& P) {
 
 cudaError_t launch_bin_scan_tc(int sm_count, cudaStream_t st, const BinScanParams& P, int n_parts) {
   const int U = P.n_scans * P.n_hyp;
-  TcGeom G = make_geom(sm_count, U, P.cap, n_parts);
-  return P.n_bins <= 48 ? launch_q<3>(st, P, G) : launch_q<4>(st, P, G);
+  if (P.n_bins <= 48) return launch_q<3>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<3>::kProd));
+  return launch_q<4>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<4>::kProd));
 }
 
 }  // namespace gcs

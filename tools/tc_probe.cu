@@ -122,6 +122,26 @@ int main() {
     }
   printf("probe1 layout: max |D - A.B^T| = %.3e  (expect ~1e-6)  %s\n", worst, worst < 1e-4 ? "OK" : "MISMATCH");
 
+  // ---- 1b. is N = 40 (multiple of 8, not of 16) a legal shape at M = 128?
+  {
+    for (int i = 0; i < N * 32; ++i) B[i] = tf32_trunc(rnd() * 2.f - 1.f);   // fresh operands: stale TMEM cannot pass
+    cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
+    probe_kernel<<<1, 128, smem>>>(dA, dB, dD, 1, 0, 40, dclk);
+    cudaError_t e2 = cudaDeviceSynchronize();
+    printf("probe1b N=40 launch: %s\n", cudaGetErrorString(e2));
+    if (e2 == cudaSuccess) {
+      cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+      double w2 = 0;
+      for (int m = 0; m < M; ++m)
+        for (int n = 0; n < 40; ++n) {
+          double s = 0;
+          for (int k = 0; k < 32; ++k) s += (double)A[m * 32 + k] * (double)B[n * 32 + k];
+          w2 = fmax(w2, fabs(s - D[m * N + n]));
+        }
+      printf("probe1b N=40: max |D - A.B^T| over 128x40 = %.3e %s\n", w2, w2 < 1e-4 ? "OK" : "MISMATCH");
+    } else return 1;
+  }
+
   // ---- 2a. input rounding: A[0,0] = 1 + 2^-11 + 2^-13, B[0,0] = 1, everything else 0
   std::fill(A.begin(), A.end(), 0.f); std::fill(B.begin(), B.end(), 0.f);
   A[0] = 1.f + ldexpf(1.f, -11) + ldexpf(1.f, -13); B[0] = 1.f;
