@@ -63,6 +63,13 @@ class BinsArgs(C.Structure):
     ]
 
 
+class Pc2Layout(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("point_step", "off_x", "type_x", "off_y", "type_y", "off_z", "type_z", "off_ring",
+                                         "type_ring", "off_time", "type_time")]
+
+
+PC_N_NONFINITE, PC_TIME_RESCALED, PC_NCERT = 0, 1, 4
+
 # name -> (restype, argtypes); every symbol declared in include/gcs_b200.h appears here
 PROTOTYPES = {
     "gcs_version": (_int, []),
@@ -75,6 +82,8 @@ PROTOTYPES = {
     "gcs_kernel_launches": (C.c_uint64, [_vp]),
     "gcs_timing_enable": (_int, [_vp, _int]),
     "gcs_timing_collect": (_int, [_vp, C.POINTER(_dbl), C.POINTER(_int)]),
+    "gcs_parse_pointcloud2_vlp16": (_int, [_vp, _vp, _vp, _int, _i64, C.POINTER(Pc2Layout), _vp, C.POINTER(_dbl), C.POINTER(_dbl),
+                                           _vp, _vp, _vp, _vp, _vp, _vp]),
     "gcs_point_budget_resample": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gcs_deskew_constant_twist": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_dbl), _dbl, _dbl, _vp, _vp, _vp]),
     "gcs_ray_directions": (_int, [_vp, _vp, _vp, _i64, C.POINTER(_dbl), _dbl, _vp]),

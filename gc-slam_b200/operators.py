@@ -211,6 +211,68 @@ class PlanarTranslationResult:
 # --------------------------------------------------------------------------------------------------
 # a1 PointBudgetResample
 # --------------------------------------------------------------------------------------------------
+def pc2_layout(fields, point_step: int) -> "L.Pc2Layout":
+    """
+    {name: (offset, PointField datatype)} -> gcs_pc2_layout.  Field selection as parse_pointcloud2_vlp16
+    (backend_node.py:396-417): x, y, z, ring required (RuntimeError otherwise), per-point time from "t" else "time".
+    """
+    missing = [k for k in ("x", "y", "z", "ring") if k not in fields]
+    if missing:
+        raise RuntimeError(f"PointCloud2 (VLP-16 layout) missing required fields: {missing}. "
+                           f"Present fields: {sorted(list(fields.keys()))}")
+    lay = L.Pc2Layout()
+    lay.point_step = int(point_step)
+    for k in ("x", "y", "z", "ring"):
+        setattr(lay, "off_" + k, int(fields[k][0]))
+        setattr(lay, "type_" + k, int(fields[k][1]))
+    tf = "t" if "t" in fields else ("time" if "time" in fields else None)
+    lay.off_time, lay.type_time = (int(fields[tf][0]), int(fields[tf][1])) if tf else (-1, 0)
+    return lay
+
+
+def _pad16(data) -> torch.Tensor:
+    """uint8 host payload -> uint8 host tensor whose length is a multiple of 16 (the device decoder reads 16-byte words)."""
+    t = data if isinstance(data, torch.Tensor) else torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy() if isinstance(data, (bytes, bytearray, memoryview)) else np.ascontiguousarray(data, dtype=np.uint8))
+    t = t.reshape(-1)
+    pad = (-t.numel()) % 16
+    return torch.cat([t, torch.zeros(pad, dtype=torch.uint8)]) if pad else t
+
+
+def parse_pointcloud2_vlp16(data, n_points: int, point_step: int, fields, header_stamp_sec: float = 0.0,
+                            R_base_lidar=None, t_base_lidar=None, device=None):
+    """
+    Device-side parse_pointcloud2_vlp16 (backend_node.py:377-468) fused with the LiDAR -> base transform of the scan
+    callback (backend_node.py:1682-1684; skipped when R_base_lidar is None).  `data` is the message payload (bytes /
+    uint8 array / uint8 tensor, host or device).  Returns (points (N,3), timestamps (N,), weights (N,), ring (N,) u8,
+    tag (N,) u8) as CUDA tensors plus dict(n_nonfinite, time_rescaled).
+    """
+    io = _IO(device)
+    lay = pc2_layout(fields, point_step)
+    n = int(n_points)
+    pts, t, w = io.empty(max(n, 0), 3), io.empty(max(n, 0)), io.empty(max(n, 0))
+    ring, tag = io.empty(max(n, 0), dtype=torch.uint8), io.empty(max(n, 0), dtype=torch.uint8)
+    if n <= 0:                                                                 # backend_node.py:386-394
+        return pts, t, w, ring, tag, dict(n_nonfinite=0, time_rescaled=False)
+    if isinstance(data, torch.Tensor) and data.is_cuda:
+        d_dev = data.reshape(-1)
+        if d_dev.numel() % 16:
+            d_dev = torch.cat([d_dev, torch.zeros((-d_dev.numel()) % 16, dtype=torch.uint8, device=d_dev.device)])
+    else:
+        host = _pad16(data)
+        d_dev = host.to(io.dev)
+        io.h2d += host.numel()
+    if d_dev.numel() < n * int(point_step):
+        raise ValueError(f"payload has {d_dev.numel()} bytes, {n} points of {point_step} bytes need {n * int(point_step)}")
+    stamp = io.dev_in(np.array([header_stamp_sec], np.float64))
+    cert = io.zeros(1, L.PC_NCERT)
+    R = None if R_base_lidar is None else (C.c_double * 9)(*np.asarray(R_base_lidar, np.float64).reshape(9))
+    tb = None if t_base_lidar is None else (C.c_double * 3)(*np.asarray(t_base_lidar, np.float64).reshape(3))
+    io.ctx.check(io.ctx.lib.gcs_parse_pointcloud2_vlp16(io.ctx.handle, io.stream(), L.ptr(d_dev), 1, n, C.byref(lay), L.ptr(stamp),
+                                                        R, tb, L.ptr(pts), L.ptr(t), L.ptr(w), L.ptr(ring), L.ptr(tag), L.ptr(cert)))
+    c = io.host(cert).reshape(-1)
+    return pts, t, w, ring, tag, dict(n_nonfinite=int(c[L.PC_N_NONFINITE]), time_rescaled=bool(c[L.PC_TIME_RESCALED]))
+
+
 def point_budget_resample(points, timestamps, weights, ring=None, tag=None,
                           n_points_cap: int = constants.GC_N_POINTS_CAP, chart_id: str = constants.GC_CHART_ID,
                           anchor_id: str = "initial") -> Tuple[PointBudgetResult, CertBundle, ExpectedEffect]:
@@ -683,6 +745,44 @@ class BinPathPlan:
             dst.copy_(src_t.reshape(dst.shape), non_blocking=non_blocking)
             n += dst.numel() * dst.element_size()
         return n
+
+    def enable_pointcloud2(self, fields, point_step: int, R_base_lidar=None, t_base_lidar=None):
+        """
+        Let the plan ingest PointCloud2 payloads directly: allocates the device staging buffer for
+        n_scans x n_raw points of `point_step` bytes; upload_pointcloud2() then moves the wire bytes (22 B/point for the
+        VLP-16 driver layout instead of 42 B/point of decoded arrays) and decodes them on the device.
+        """
+        io = self.io
+        self._pc2_lay = pc2_layout(fields, point_step)
+        nbytes = self.S * self.n_raw * int(point_step)
+        self._pc2_dev = io.empty(nbytes + ((-nbytes) % 16), dtype=torch.uint8)
+        self._pc2_stamp = io.zeros(self.S)
+        self._pc2_cert = io.zeros(self.S, L.PC_NCERT)
+        self._pc2_R = None if R_base_lidar is None else (C.c_double * 9)(*np.asarray(R_base_lidar, np.float64).reshape(9))
+        self._pc2_t = None if t_base_lidar is None else (C.c_double * 3)(*np.asarray(t_base_lidar, np.float64).reshape(3))
+        return nbytes
+
+    def upload_pointcloud2(self, payload, header_stamps=None, t0=None, t1=None, xi=None, poses=None, non_blocking=True):
+        """payload: uint8 host tensor (ideally pinned) holding the n_scans messages back to back.  Returns bytes copied."""
+        io = self.io
+        src = payload if isinstance(payload, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(payload, dtype=np.uint8))
+        src = src.reshape(-1)
+        n = self.S * self.n_raw * self._pc2_lay.point_step
+        if src.numel() < n:
+            raise ValueError(f"payload has {src.numel()} bytes, the plan needs {n}")
+        self._pc2_dev[:n].copy_(src[:n], non_blocking=non_blocking)
+        moved = n
+        for dst, s_ in ((self._pc2_stamp, header_stamps), (self.t0, t0), (self.t1, t1), (self.xi, xi), (self.poses, poses)):
+            if s_ is None:
+                continue
+            st = s_ if isinstance(s_, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(s_, dtype=np.float64))
+            dst.copy_(st.reshape(dst.shape), non_blocking=non_blocking)
+            moved += dst.numel() * dst.element_size()
+        io.ctx.check(io.ctx.lib.gcs_parse_pointcloud2_vlp16(
+            io.ctx.handle, io.stream(), L.ptr(self._pc2_dev), self.S, self.n_raw, C.byref(self._pc2_lay), L.ptr(self._pc2_stamp),
+            self._pc2_R, self._pc2_t, L.ptr(self.pts), L.ptr(self.t), L.ptr(self.w), L.ptr(self.ring), L.ptr(self.tag),
+            L.ptr(self._pc2_cert)))
+        return moved
 
     # -- launches ----------------------------------------------------------------------------------
     def run(self):

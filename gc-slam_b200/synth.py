@@ -82,6 +82,46 @@ def vlp16_scan(n_points: int, seed: int, t0: float = EPOCH_T0, sensor_xy=(0.0, 0
             np.zeros(n_points, np.uint8))
 
 
+# VLP-16 driver layout used on the wire (docs/KIMERA_DATASET_AND_PIPELINE.md section 6): x, y, z, intensity float32,
+# ring uint16, time float32 -> 22 bytes per point.  (offset, sensor_msgs/PointField datatype)
+PC2_VLP16_FIELDS = {"x": (0, 7), "y": (4, 7), "z": (8, 7), "intensity": (12, 7), "ring": (16, 4), "time": (18, 7)}
+PC2_VLP16_POINT_STEP = 22
+
+
+def vlp16_pointcloud2(n_points: int, seed: int, t0: float = 0.0, sensor_xy=(0.0, 0.0), time_unit: str = "s"):
+    """
+    The same synthetic sweep as vlp16_scan, as PointCloud2 wire bytes in the LIDAR frame (float32 coordinates, what the
+    driver publishes).  Per-point time is the offset into the sweep in seconds ("s") or nanoseconds ("ns").
+    Returns (data uint8 (N * 22,), fields, point_step).
+    """
+    rng = np.random.default_rng(seed)
+    i = np.arange(n_points)
+    ring = (i % 16).astype(np.uint16)
+    n_cols = max(1, (n_points + 15) // 16)
+    az = 2.0 * np.pi * (i // 16) / n_cols
+    el = np.deg2rad(-15.0 + 2.0 * ring.astype(np.float64))
+    u = np.stack([np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el)], axis=1)
+    o = np.array([sensor_xy[0], sensor_xy[1], 0.0])
+    rng_m = np.clip(_ray_room(u, o) + rng.normal(0.0, 0.02, size=n_points), 0.5, 50.0)
+    p = (u * rng_m[:, None]).astype(np.float32)
+    toff = t0 + SCAN_PERIOD * i / float(n_points)
+    if time_unit == "ns":
+        toff = toff * 1e9
+    rec = np.zeros(n_points, dtype=np.dtype({"names": ["x", "y", "z", "intensity", "ring", "time"],
+                                             "formats": ["<f4", "<f4", "<f4", "<f4", "<u2", "<f4"],
+                                             "offsets": [0, 4, 8, 12, 16, 18], "itemsize": PC2_VLP16_POINT_STEP}))
+    rec["x"], rec["y"], rec["z"] = p[:, 0], p[:, 1], p[:, 2]
+    rec["intensity"] = rng.uniform(0, 255, n_points).astype(np.float32)
+    rec["ring"] = ring
+    rec["time"] = toff.astype(np.float32)
+    return np.frombuffer(rec.tobytes(), dtype=np.uint8).copy(), dict(PC2_VLP16_FIELDS), PC2_VLP16_POINT_STEP
+
+
+def base_lidar_extrinsics():
+    """(R_base_lidar (3,3), t_base_lidar (3,)) of config/gc_unified.yaml:18-24."""
+    return rotvec_to_matrix(T_BASE_LIDAR[3:]), T_BASE_LIDAR[:3].copy()
+
+
 def scan_twist(seed: int):
     """xi_body = [rho ~ U(-0.1,0.1)^3 m, phi ~ U(-0.05,0.05)^3 rad] (IMU-twist stand-in)."""
     rng = np.random.default_rng(seed)

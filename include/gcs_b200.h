@@ -61,6 +61,27 @@ typedef enum {
   GCS_PREC_TC = 2     /* MIXED + the 48x19 moment contraction on tcgen05 (3xTF32 split, f64 chunk flushes)   */
 } gcs_precision;
 
+/* ---- (8f-1) PointCloud2 ingest : fl/backend/backend_node.py:377-468 (parse_pointcloud2_vlp16) and :1682-1684 --
+ * Wire payload of n_msgs messages of n_points points each (same layout, back to back) -> SoA arrays in the base
+ * frame.  Field datatypes are the sensor_msgs/PointField codes (1 INT8 .. 6 UINT32, 7 FLOAT32, 8 FLOAT64).
+ * Non-finite coordinates become +-1e6 (GC_NONFINITE_SENTINEL); ring is taken modulo 256; the per-point time is
+ * multiplied by 1e-9 for a message in which any value exceeds 1e6 (the reference's unit switch); without a time field
+ * every point gets header_stamp[m]; weights are the range sigmoid window; tag = 0.  `data` must be readable up to
+ * the next multiple of 16 bytes past its end.  x, y, z or ring missing (offset < 0) -> GCS_EINVAL.              */
+typedef struct {
+  int32_t point_step;
+  int32_t off_x, type_x, off_y, type_y, off_z, type_z;
+  int32_t off_ring, type_ring;
+  int32_t off_time, type_time; /* off_time < 0: no per-point time field ("t" or "time") */
+} gcs_pc2_layout;
+enum { GCS_PC_N_NONFINITE = 0, GCS_PC_TIME_RESCALED, GCS_PC_NCERT = 4 };
+int gcs_parse_pointcloud2_vlp16(gcs_ctx* ctx, void* stream, const uint8_t* data /*dev*/, int n_msgs, int64_t n_points,
+                                const gcs_pc2_layout* layout /*host*/, const double* header_stamp /*dev (n_msgs) or NULL*/,
+                                const double* R_base_lidar /*host [9] row-major or NULL*/,
+                                const double* t_base_lidar /*host [3] or NULL*/, double* pts /*dev (n_msgs,n,3)*/,
+                                double* t /*dev (n_msgs,n)*/, double* w /*dev (n_msgs,n)*/, uint8_t* ring /*dev*/,
+                                uint8_t* tag /*dev*/, double* cert /*dev (n_msgs, GCS_PC_NCERT)*/);
+
 /* ---- a1 PointBudgetResample : fl/backend/operators/point_budget.py:50-109,117-221 --------------------- */
 enum { GCS_RS_MASS_IN = 0, GCS_RS_MASS_SEL, GCS_RS_SUMSQ_SEL, GCS_RS_ESS, GCS_RS_MASS_SCALE, GCS_RS_NCERT = 8 };
 int gcs_point_budget_resample(gcs_ctx* ctx, void* stream,
