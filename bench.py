@@ -138,17 +138,23 @@ def make_batch(n_scans, n_points, seed0):
 # CPU arm: the oracle (NumPy restatement of the reference's CPU path)
 # ----------------------------------------------------------------------------------------------------------
 def _cpu_one_scan(args):
+    """One scan through the CPU path, from the PointCloud2 payload (as the e2e leg): decode + base transform + bin path.
+    Input generation is outside the timed span; returns the seconds of the path itself."""
     seed, n_points = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     from gc_slam_b200 import synth
     from oracle import bin_path as ob
-    from oracle import lie
-    p, tt, ww, rg, tg = synth.vlp16_scan(n_points, seed, t0=synth.EPOCH_T0)
+    from oracle import lie, pc2
+    data, fields, step = synth.vlp16_pointcloud2(n_points, seed, time_unit="s")
+    payload = data.tobytes()
+    R_bl, t_bl = synth.base_lidar_extrinsics()
     bins = synth.fibonacci_atlas(N_BINS)
     ms = synth.random_map_bin_stats(N_BINS, 7, bins)
     pose = synth.hypothesis_poses(1, seed)[0]
     t_start = time.perf_counter()
-    ob.lidar_evidence_bins(p, tt, ww, rg, tg, n_points, synth.scan_twist(seed), synth.EPOCH_T0, synth.EPOCH_T0 + 0.1,
+    p, tt, ww, rg, tg = pc2.parse_pointcloud2_vlp16(payload, n_points, step, fields, 0.0)
+    p = pc2.lidar_to_base(p, R_bl, t_bl)
+    ob.lidar_evidence_bins(p, tt, ww, rg, tg, n_points, synth.scan_twist(seed), 0.0, 0.1,
                            synth.lidar_origin_base(), bins, TAU, ms, lie.so3_exp(pose[3:]), pose[:3])
     return time.perf_counter() - t_start
 
@@ -163,7 +169,7 @@ def cpu_baseline_single(n_points, n_sample=3):
     _cpu_one_scan((999, min(n_points, 4096)))  # warm imports
     dts = [_cpu_one_scan((1000 + i, n_points)) for i in range(n_sample)]
     return {"value": 1.0 / float(np.median(dts)), "unit": "scans/s", "cores": threads, "kind": "port",
-            "sample": f"{n_sample} scans x {n_points} points, full bin path, NumPy oracle in-process (median)"}
+            "sample": f"{n_sample} scans x {n_points} points, PointCloud2 decode + full bin path, NumPy oracle in-process (median)"}
 
 
 def run_reference_arm(args):
@@ -182,18 +188,20 @@ def run_reference_arm(args):
     with ctx.Pool(cores) as pool:
         for _ in range(max(1, min(args.warmup, 1))):
             pool.map(_cpu_one_scan, [(900 + i, n_points) for i in range(per_step)])
-        t_start = time.perf_counter()
+        # a step = one scan per core, all cores concurrently; its duration = the slowest core's path time (the workers
+        # time the path only: generating the synthetic message is not part of it)
+        dt = 0.0
         for k in range(args.steps):
-            pool.map(_cpu_one_scan, [(2000 + k * per_step + i, n_points) for i in range(per_step)])
-        dt = time.perf_counter() - t_start
+            dt += max(pool.map(_cpu_one_scan, [(2000 + k * per_step + i, n_points) for i in range(per_step)], chunksize=1))
     value = args.steps * per_step / dt
     line = {
         "impl": "reference", "metric": "lidar_evidence_path_scans_per_s", "value": value, "unit": "scans/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, per_step),
+        "config": workload_config(args, args.scans),     # the GPU arm's config; each step here is a bounded sample of it
         "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": "port",
-                         "sample": f"{per_step} scans x {n_points} points per step, one process per host core"},
+                         "sample": f"{per_step} scans x {n_points} points per step (one single-threaded process per host core), "
+                                   f"PointCloud2 decode + base transform + full bin path, NumPy oracle"},
         "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -356,31 +364,56 @@ def run_ours(args):
     streams = (torch.cuda.Stream(), torch.cuda.Stream())
     outs_host = [torch.empty(S * (L.BC_NCERT + 22 * 22 + 22), dtype=torch.float64).pin_memory() for _ in range(2)]
 
-    def e2e_step(k):
+    # The host-side input of the path is what the node receives: PointCloud2 payloads (VLP-16 driver layout, 22 bytes
+    # per point, LIDAR frame).  parse_pointcloud2_vlp16 + the base transform (backend_node.py:377-468, :1682-1684)
+    # run on the device, then the same bin path.  The decoded-arrays variant (five float64 / uint8 arrays, 42 bytes
+    # per point, what the reference uploads after its NumPy decode) is timed too and reported under extra.
+    R_bl, t_bl = synth.base_lidar_extrinsics()
+    msgs = [synth.vlp16_pointcloud2(P, 1000 + 100 * rank + k, time_unit="s") for k in range(min(S, 8))]
+    pc_fields, pc_step = msgs[0][1], msgs[0][2]
+    payload = torch.from_numpy(np.concatenate([msgs[k % len(msgs)][0] for k in range(S)])).pin_memory()
+    for pl in plans:
+        pl.enable_pointcloud2(pc_fields, pc_step, R_bl, t_bl)
+    t0_rel = torch.zeros(S, dtype=torch.float64).pin_memory()
+    t1_rel = torch.full((S,), 0.1, dtype=torch.float64).pin_memory()
+    moved = {}
+
+    def e2e_step(k, wire=True):
         pl, stq, oh = plans[k % 2], streams[k % 2], outs_host[k % 2]
         with torch.cuda.stream(stq):
-            pl.upload(host["pts"], host["t"], host["w"], host["ring"], host["tag"], host["t0"], host["t1"], host["xi"],
-                      host["poses"])
+            if wire:
+                moved["wire"] = pl.upload_pointcloud2(payload, None, t0_rel, t1_rel, host["xi"], host["poses"])
+            else:
+                moved["arrays"] = pl.upload(host["pts"], host["t"], host["w"], host["ring"], host["tag"], host["t0"], host["t1"],
+                                            host["xi"], host["poses"])
             pl.run()
             o = pl.outputs()
             oh.copy_(torch.cat([o.cert.reshape(-1), o.L22.reshape(-1), o.h22.reshape(-1)]), non_blocking=True)
 
-    torch.cuda.synchronize()
-    for k in range(2):
-        e2e_step(k)
-    barrier()
     e_steps = max(2, min(args.steps, 10))
-    t_e0 = time.perf_counter()
-    for k in range(e_steps):
-        e2e_step(k)
-    for stq in streams:
-        stq.synchronize()
-    e_wall_ms = (time.perf_counter() - t_e0) * 1e3   # two streams: device time == wall time between the syncs
-    barrier()
-    e_ms = torch.tensor([e_wall_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * S * e_steps / (float(e_ms.item()) * 1e-3)
+
+    def e2e_run(wire):
+        torch.cuda.synchronize()
+        for k in range(2):
+            e2e_step(k, wire)
+        for stq in streams:
+            stq.synchronize()
+        barrier()
+        t_e0 = time.perf_counter()
+        for k in range(e_steps):
+            e2e_step(k, wire)
+        for stq in streams:
+            stq.synchronize()
+        wall_ms = (time.perf_counter() - t_e0) * 1e3   # two streams: device time == wall time between the syncs
+        barrier()
+        e_ms = torch.tensor([wall_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+        return world * S * e_steps / (float(e_ms.item()) * 1e-3)
+
+    e2e_arrays = e2e_run(False)
+    e2e_value = e2e_run(True)
+    h2d_bytes = moved["wire"]
     d2h_bytes = outs_host[0].numel() * 8
     del plan_b
 
@@ -391,13 +424,14 @@ def run_ours(args):
         p1.set_bins(bins, TAU)
         p1.set_map(synth.random_map_bin_stats(N_BINS, 7, bins))
         h1 = {k: v[:1].clone().pin_memory() for k, v in host.items()}
+        p1.enable_pointcloud2(pc_fields, pc_step, R_bl, t_bl)
+        pay1 = payload[: P * pc_step].clone().pin_memory()
         o1 = torch.empty(L.BC_NCERT + 22 * 22 + 22, dtype=torch.float64).pin_memory()
         ts_e2e, ts_dev = [], []
         for i in range(60):
             torch.cuda.synchronize()
             a = time.perf_counter()
-            p1.upload(h1["pts"], h1["t"], h1["w"], h1["ring"], h1["tag"], h1["t0"], h1["t1"], h1["xi"], h1["poses"])
-            b = time.perf_counter()
+            p1.upload_pointcloud2(pay1, None, t0_rel[:1], t1_rel[:1], h1["xi"], h1["poses"])
             p1.run()
             oo = p1.outputs()
             o1.copy_(torch.cat([oo.cert.reshape(-1), oo.L22.reshape(-1), oo.h22.reshape(-1)]), non_blocking=True)
@@ -412,7 +446,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             if i >= 10:
                 ts_dev.append(time.perf_counter() - a)
-        lat = {"p50_ms_host_in_evidence_out": 1e3 * float(np.median(ts_e2e)),
+        lat = {"p50_ms_host_in_evidence_out": 1e3 * float(np.median(ts_e2e)),   # PointCloud2 payload in pinned memory -> 22-D evidence on the host
                "p50_ms_device_resident": 1e3 * float(np.median(ts_dev)), "points": P, "reps": 50}
 
     # the same batch through the all-float64 kernels (reference dtype), for the record next to the headline precision
@@ -434,6 +468,10 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         ms64 = e0.elapsed_time(e1) / 5
+        plan.upload(host["pts"], host["t"], host["w"], host["ring"], host["tag"], host["t0"], host["t1"], host["xi"],
+                    host["poses"])          # the e2e leg left the wire-decoded batch in the plan's buffers
+        plan.run()
+        torch.cuda.synchronize()
         o64, otc = plan64.outputs(), plan.outputs()
 
         def _rel(a, b):
@@ -473,6 +511,7 @@ def run_ours(args):
             "config": workload_config(args, S),
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "steps": e_steps,
+                    "input": "PointCloud2 payloads (VLP-16 layout, 22 B/point) in pinned host memory; decode + base transform on the device",
                     "how": "2 plans on 2 streams (copy of batch k+1 overlaps kernels of batch k); wall clock between syncs"},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -482,7 +521,9 @@ def run_ours(args):
                          "kernel_launches_timed": k_n, "kernel_share_of_step": k_ms / ms_total},
             "latency": lat,
             "points_per_s": value * P,
-            "extra": {"primitive_path": prim, "float64_path": f64_leg},
+            "extra": {"primitive_path": prim, "float64_path": f64_leg,
+                      "e2e_decoded_arrays": {"value": e2e_arrays, "unit": "scans/s", "h2d_bytes_per_step": int(moved["arrays"]),
+                                             "input": "five decoded arrays (float64 points/stamps/weights, uint8 ring/tag), 42 B/point"}},
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
