@@ -8,7 +8,7 @@
 
 namespace gcs {
 
-constexpr int kFinalThreads = 64;
+constexpr int kFinalThreads = 128;   // 64 bin threads + 64 helpers (gcs_bins_final.cu: thread roles)
 
 struct FinalParams {
   int n_bins, n_hyp;
@@ -69,17 +69,61 @@ __device__ inline void scatter_metrics17(const Mat3& S, double N_total, double e
 
 constexpr int kRedW = 32;  // doubles per bin in the reduction scratch
 
+// Thread roles (kFinalThreads = 128): threads 0..63 own one bin each; threads 64..127 are helpers that take the work
+// that does not depend on the bin threads' critical path -- the map-side derived statistics of bin (tid - 64), the
+// Matrix-Fisher tail (so3_log, PSD projection, certificates), the two scatter-metric records and the map-scatter
+// eigenvalues of the planarisation -- so that the serial chain of a unit is
+//   per-bin PSD projection -> 3x3 SVD -> per-bin 3x3 inverse -> WLS solve + PSD projection
+// instead of the sum of every eigen-decomposition in the epilogue.
 __global__ void __launch_bounds__(kFinalThreads) bins_finalize_kernel(const FinalParams P) {
   __shared__ double red[kMaxBins * kRedW];
   __shared__ double tot[kRedW];
   __shared__ double sR[9];
-  const int u = blockIdx.x, b = threadIdx.x, B = P.n_bins;
-  const bool on = b < B;
+  __shared__ double sMap[kMaxBins * 12];   // per bin: map centroid (3) + Sigma_c (9), written by the helper threads
+  __shared__ double sZs;
+  __shared__ double sMF[21];               // SVD factors handed from thread 0 to the Matrix-Fisher helper
+  __shared__ double sL[9];                 // projected translation information matrix
+  const int u = blockIdx.x, tid = threadIdx.x, B = P.n_bins;
+  const bool helper = tid >= kMaxBins;
+  const int b = helper ? tid - kMaxBins : tid;
+  const bool on = !helper && b < B;
   const double eps = P.eps_mass;
 
   double N = 0.0, sdir[3] = {0, 0, 0}, pbar[3] = {0, 0, 0};
   Mat3 S, Sig;
   for (int i = 0; i < 9; ++i) { S.m[i] = 0.0; Sig.m[i] = 0.0; }
+
+  // ---------------- helpers: map derived stats of bin b (archive/bin_atlas.py:159-198), independent of the scan
+  double mN_dir = 0, mN_pos = 0, mSd[3] = {0, 0, 0};
+  Mat3 mS;
+  for (int i = 0; i < 9; ++i) mS.m[i] = 0.0;
+  if (P.evidence && b < B) {
+    if (!helper) {
+      if (P.map.N_dir) mN_dir = P.map.N_dir[b];
+      if (P.map.N_pos) mN_pos = P.map.N_pos[b];
+      for (int k = 0; k < 3; ++k)
+        if (P.map.S_dir) mSd[k] = P.map.S_dir[3 * b + k];
+      for (int k = 0; k < 9; ++k)
+        if (P.map.S_scatter) mS.m[k] = P.map.S_scatter[9 * b + k];
+    } else if (P.do_pt) {
+      double* o = sMap + b * 12;
+      if (P.map_centroid && P.map_Sigma_c) {
+        for (int k = 0; k < 3; ++k) o[k] = P.map_centroid[3 * b + k];
+        for (int k = 0; k < 9; ++k) o[3 + k] = P.map_Sigma_c[9 * b + k];
+      } else {
+        const double np_ = P.map.N_pos ? P.map.N_pos[b] : 0.0;
+        const double invp = 1.0 / (np_ + eps + kF64Eps);
+        double cen[3];
+        for (int k = 0; k < 3; ++k) cen[k] = (P.map.sum_p ? P.map.sum_p[3 * b + k] : 0.0) * invp;
+        Mat3 craw;
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) craw(i, j) = (P.map.sum_ppT ? P.map.sum_ppT[9 * b + 3 * i + j] : 0.0) * invp - cen[i] * cen[j];
+        const Mat3 Sc = psd_project3(craw, P.eps_psd, nullptr);
+        for (int k = 0; k < 3; ++k) o[k] = cen[k];
+        for (int k = 0; k < 9; ++k) o[3 + k] = Sc.m[k];
+      }
+    }
+  }
 
   if (P.raw_sums) {
     // ---------------- ScanBinMomentMatch epilogue (binning.py:178-209)
@@ -119,13 +163,15 @@ __global__ void __launch_bounds__(kFinalThreads) bins_finalize_kernel(const Fina
         if (P.out.sum_ppT) P.out.sum_ppT[ub * 9 + k] = Spp.m[k];
       }
     }
-    red[b * kRedW + 0] = on ? N : 0.0;
-    red[b * kRedW + 1] = on ? N * N : 0.0;
-    red[b * kRedW + 2] = on ? N / (N + eps) : 0.0;
-    red[b * kRedW + 3] = on ? delta : 0.0;
-    red[b * kRedW + 4] = on ? eps_ratio : 0.0;
+    if (!helper) {
+      red[b * kRedW + 0] = on ? N : 0.0;
+      red[b * kRedW + 1] = on ? N * N : 0.0;
+      red[b * kRedW + 2] = on ? N / (N + eps) : 0.0;
+      red[b * kRedW + 3] = on ? delta : 0.0;
+      red[b * kRedW + 4] = on ? eps_ratio : 0.0;
+    }
     __syncthreads();
-    if (b == 0) {
+    if (tid == kMaxBins) {   // first helper: certificate scalars of the statistics
       double sN = 0, sN2 = 0, sFr = 0, sD = 0, mR = 0;
       for (int k = 0; k < B; ++k) {
         sN += red[k * kRedW]; sN2 += red[k * kRedW + 1]; sFr += red[k * kRedW + 2]; sD += red[k * kRedW + 3];
@@ -158,7 +204,7 @@ __global__ void __launch_bounds__(kFinalThreads) bins_finalize_kernel(const Fina
         for (int k = GCS_BC_ST_MASS_EPS_RATIO + 1; k < GCS_BC_NCERT; ++k) c[k] = 0.0;
       }
     }
-    __syncthreads();
+    __syncthreads();   // red[] is rewritten below
   } else if (on) {
     const int64_t ub = (int64_t)u * B + b;
     N = P.in.N[ub];
@@ -173,23 +219,8 @@ __global__ void __launch_bounds__(kFinalThreads) bins_finalize_kernel(const Fina
   }
   if (!P.evidence) return;
 
-  // ---------------- MatrixFisherRotation (matrix_fisher_evidence.py:155-256)
-  double mN_dir = 0, mN_pos = 0, mSd[3] = {0, 0, 0}, msp[3] = {0, 0, 0};
-  Mat3 mS, mSpp;
-  for (int i = 0; i < 9; ++i) { mS.m[i] = 0.0; mSpp.m[i] = 0.0; }
-  if (on) {
-    if (P.map.N_dir) mN_dir = P.map.N_dir[b];
-    if (P.map.N_pos) mN_pos = P.map.N_pos[b];
-    for (int k = 0; k < 3; ++k) {
-      if (P.map.S_dir) mSd[k] = P.map.S_dir[3 * b + k];
-      if (P.map.sum_p) msp[k] = P.map.sum_p[3 * b + k];
-    }
-    for (int k = 0; k < 9; ++k) {
-      if (P.map.S_scatter) mS.m[k] = P.map.S_scatter[9 * b + k];
-      if (P.map.sum_ppT) mSpp.m[k] = P.map.sum_ppT[9 * b + k];
-    }
-  }
-  {
+  // ---------------- MatrixFisherRotation (matrix_fisher_evidence.py:155-256): per-bin terms, then column sums
+  if (!helper) {
     const double w_b = sqrt(N * mN_dir + eps);
     const double sn = sqrt(sdir[0] * sdir[0] + sdir[1] * sdir[1] + sdir[2] * sdir[2]);
     const double mn = sqrt(mSd[0] * mSd[0] + mSd[1] * mSd[1] + mSd[2] * mSd[2]);
@@ -204,115 +235,47 @@ __global__ void __launch_bounds__(kFinalThreads) bins_finalize_kernel(const Fina
     r[27] = on ? N : 0.0; r[28] = on ? mN_dir : 0.0; r[29] = on ? wf : 0.0;
   }
   __syncthreads();
-  if (b < 30) {
+  if (tid < 30) {
     double a = 0.0;
-    for (int k = 0; k < B; ++k) a += red[k * kRedW + b];
-    tot[b] = a;
+    for (int k = 0; k < B; ++k) a += red[k * kRedW + tid];
+    tot[tid] = a;
   }
   __syncthreads();
   double* ev = P.evidence + (int64_t)u * GCS_EV_NREC;
   double pose[6];
   for (int k = 0; k < 6; ++k) pose[k] = P.use_pose_val ? P.pose_val[k] : P.poses[(int64_t)u * 6 + k];
+
+  // critical path: the SVD alone (thread 0); its consumers wait at the next barrier, the rest of the Matrix-Fisher
+  // record is finished by helper threads while the bin threads go on with the translation evidence
+  Mat3 mfU, mfV;
+  double mfs[3] = {0, 0, 0};
   if (!P.do_mf) {
-    if (b < 9) sR[b] = P.R_hat[b];
-    if (b == 0) for (int k = 0; k < GCS_EV_T_WLS; ++k) ev[k] = 0.0;
-  } else if (b == 0) {
-    Mat3 H, U, V;
+    if (tid < 9) sR[tid] = P.R_hat[tid];
+    if (tid == 0) for (int k = 0; k < GCS_EV_T_WLS; ++k) ev[k] = 0.0;
+  } else if (tid == 0) {
+    Mat3 H;
     for (int k = 0; k < 9; ++k) H.m[k] = tot[k];
-    double sv[3];
-    svd3(H, U, sv, V);
-    Mat3 Vt = mat3_T(V);
-    const double det = mat3_det(mat3_mul(U, Vt));
+    svd3(H, mfU, mfs, mfV);
+    Mat3 Vt = mat3_T(mfV);
+    const double det = mat3_det(mat3_mul(mfU, Vt));
     const double sg = det > 0.0 ? 1.0 : (det < 0.0 ? -1.0 : 0.0);  // jnp.sign
-    for (int r = 0; r < 3; ++r) U(r, 2) *= sg;
-    Mat3 Rmf = mat3_mul(U, Vt);
-    const double ld[3] = {sv[1] + sv[2], sv[0] + sv[2], sv[0] + sv[1]};
-    Mat3 Lraw;
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) {
-        double a = 0.0;
-        for (int k = 0; k < 3; ++k) a += V(i, k) * ld[k] * V(j, k);
-        Lraw(i, j) = a;
-      }
-    Mat3 Rp = so3_exp(pose + 3);
-    Mat3 Rerr = mat3_mul(mat3_T(Rp), Rmf);
-    double dr[3];
-    so3_log(Rerr, dr);
-    double c6[6];
-    Mat3 L = psd_project3(Lraw, P.eps_psd, c6);
-    double hr[3];
-    mat3_vec(L, dr, hr);
-    const double nll = 0.5 * (dr[0] * hr[0] + dr[1] * hr[1] + dr[2] * hr[2]);
-    const double Neff = tot[29];
-    for (int k = 0; k < 9; ++k) { ev[GCS_EV_R_MF + k] = Rmf.m[k]; ev[GCS_EV_L_ROT + k] = L.m[k]; sR[k] = P.use_R_hat ? P.R_hat[k] : Rmf.m[k]; }
-    for (int k = 0; k < 3; ++k) { ev[GCS_EV_H_ROT + k] = hr[k]; ev[GCS_EV_DELTA_ROT + k] = dr[k]; ev[GCS_EV_SVD_S + k] = sv[k]; }
-    const double smin = fmin(sv[0], fmin(sv[1], sv[2])), smax = fmax(sv[0], fmax(sv[1], sv[2]));
-    ev[GCS_EV_MF_EIG_MIN] = smin; ev[GCS_EV_MF_EIG_MAX] = smax; ev[GCS_EV_MF_COND] = smax / (smin + eps);
-    ev[GCS_EV_MF_NEAR_NULL] = (double)((sv[0] < eps) + (sv[1] < eps) + (sv[2] < eps));
-    ev[GCS_EV_MF_NLL_PER_ESS] = nll / (Neff + eps);
-    ev[GCS_EV_MF_DIR_SCORE] = sv[0] + sv[1] + sv[2];
-    ev[GCS_EV_MF_PSD_DELTA] = c6[0];
-    ev[GCS_EV_MF_MASS_EPS] = eps / (Neff + eps);
-    ev[GCS_EV_MF_ROT_NLL] = nll;
-    ev[GCS_EV_MF_N_EFF] = Neff;
-  } else if (b == 1 && P.do_mf) {
+    for (int r = 0; r < 3; ++r) mfU(r, 2) *= sg;
+    const Mat3 Rmf = mat3_mul(mfU, Vt);
+    for (int k = 0; k < 9; ++k) { ev[GCS_EV_R_MF + k] = Rmf.m[k]; sR[k] = P.use_R_hat ? P.R_hat[k] : Rmf.m[k]; }
+    // hand the factors to the helper that finishes the record
+    for (int k = 0; k < 9; ++k) { sMF[k] = Rmf.m[k]; sMF[9 + k] = mfV.m[k]; }
+    for (int k = 0; k < 3; ++k) sMF[18 + k] = mfs[k];
+  } else if (tid == kMaxBins + 1 && P.do_mf) {
     Mat3 St;
     for (int k = 0; k < 9; ++k) St.m[k] = tot[9 + k];
     scatter_metrics17(St, tot[27], eps, ev + GCS_EV_SCAN_METRICS);
-  } else if (b == 2 && P.do_mf) {
+  } else if (tid == kMaxBins + 2 && P.do_mf) {
     Mat3 Mt;
     for (int k = 0; k < 9; ++k) Mt.m[k] = tot[18 + k];
     scatter_metrics17(Mt, tot[28], eps, ev + GCS_EV_MAP_METRICS);
   }
-  __syncthreads();
-  if (!P.do_pt) {
-    if (b == 0) for (int k = GCS_EV_T_WLS; k < GCS_EV_MF_EIG_MIN; ++k) ev[k] = 0.0;
-    if (b == 0) for (int k = GCS_EV_PT_EIG_MIN; k < GCS_EV_NREC; ++k) ev[k] = 0.0;
-    return;
-  }
-
-  // ---------------- PlanarTranslationEvidence (matrix_fisher_evidence.py:413-499, :502-671)
-  {
-    Mat3 R;
-    for (int k = 0; k < 9; ++k) R.m[k] = sR[k];
-    // map derived stats for this bin (archive/bin_atlas.py:159-198)
-    const double invp = 1.0 / (mN_pos + eps + kF64Eps);
-    double cen[3] = {msp[0] * invp, msp[1] * invp, msp[2] * invp};
-    Mat3 Sc;
-    if (P.map_centroid && P.map_Sigma_c) {
-      for (int k = 0; k < 3; ++k) cen[k] = on ? P.map_centroid[3 * b + k] : 0.0;
-      for (int k = 0; k < 9; ++k) Sc.m[k] = on ? P.map_Sigma_c[9 * b + k] : 0.0;
-    } else {
-      Mat3 craw;
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) craw(i, j) = mSpp(i, j) * invp - cen[i] * cen[j];
-      Sc = psd_project3(craw, P.eps_psd, nullptr);
-    }
-    double pr[3];
-    mat3_vec(R, pbar, pr);
-    const double tb[3] = {cen[0] - pr[0], cen[1] - pr[1], cen[2] - pr[2]};
-    Mat3 RS = mat3_mul(mat3_mul(R, Sig), mat3_T(R));
-    Mat3 Sg;
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) Sg(i, j) = (Sc(i, j) + RS(i, j)) + ((i == j) ? eps : 0.0);
-    const double wb = sqrt(N * mN_pos + eps);
-    Mat3 Wi = mat3_inv(Sg);
-    double* r = red + b * kRedW;
-    for (int k = 0; k < 9; ++k) { Wi.m[k] *= wb; r[k] = on ? Wi.m[k] : 0.0; }
-    double hb[3];
-    mat3_vec(Wi, tb, hb);
-    for (int k = 0; k < 3; ++k) r[9 + k] = on ? hb[k] : 0.0;
-    r[12] = on ? wb : 0.0;
-  }
-  __syncthreads();
-  if (b < 13) {
-    double a = 0.0;
-    for (int k = 0; k < B; ++k) a += red[k * kRedW + b];
-    tot[b] = a;  // tot[18..28] (map scatter, N totals) are still intact
-  }
-  __syncthreads();
-  if (b == 0) {
-    // self-adaptive z precision from the total map scatter (:579-592)
+  if (tid == kMaxBins + 3 && P.do_pt) {
+    // self-adaptive z precision from the total map scatter (:579-592): needs only the column sums
     Mat3 Tm;
     const double Nd = tot[28] + eps;
     for (int k = 0; k < 9; ++k) Tm.m[k] = tot[18 + k] / Nd;
@@ -320,59 +283,150 @@ __global__ void __launch_bounds__(kFinalThreads) bins_finalize_kernel(const Fina
     Mat3 Vd;
     eigh3(Tm, w, Vd);
     const double l1 = fmax(w[2], eps), l3 = fmax(w[0], 0.0);
-    const double zs = l3 / l1;
-    Mat3 Lf;
-    for (int k = 0; k < 9; ++k) Lf.m[k] = tot[k];
-    const double hf[3] = {tot[9], tot[10], tot[11]};
-    Mat3 Lreg = Lf;
-    Lreg(0, 0) += eps; Lreg(1, 1) += eps; Lreg(2, 2) += eps;
-    double tw[3];
-    mat3_solve(Lreg, hf, tw);
-    const double mk[3] = {1.0, 1.0, zs};
-    Mat3 Lraw;
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) Lraw(i, j) = Lf(i, j) * mk[i] * mk[j];
-    const double Neff = tot[12];
-    const double dt[3] = {tw[0] - pose[0], tw[1] - pose[1], tw[2] - pose[2]};
-    double c6[6];
-    Mat3 L = psd_project3(Lraw, P.eps_psd, c6);
-    double ht[3];
-    mat3_vec(L, dt, ht);
-    const double nll = 0.5 * (dt[0] * ht[0] + dt[1] * ht[1] + dt[2] * ht[2]);
+    sZs = l3 / l1;
+  }
+  const double Neff_mf = tot[29];
+  __syncthreads();   // sR, the SVD factors and sZs are published; tot[0..29] may be overwritten from here on
+
+  // From here the two halves of the CTA run independently until the final barrier: warps 0-1 (bin threads) carry the
+  // translation evidence and synchronise among themselves on named barrier 1; warp 2's first thread finishes the
+  // Matrix-Fisher record.
+  if (helper) {
+    if (tid == kMaxBins && P.do_mf) {
+      Mat3 Rmf, V;
+      double sv[3];
+      for (int k = 0; k < 9; ++k) { Rmf.m[k] = sMF[k]; V.m[k] = sMF[9 + k]; }
+      for (int k = 0; k < 3; ++k) sv[k] = sMF[18 + k];
+      const double ld[3] = {sv[1] + sv[2], sv[0] + sv[2], sv[0] + sv[1]};
+      Mat3 Lraw;
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          double a = 0.0;
+          for (int k = 0; k < 3; ++k) a += V(i, k) * ld[k] * V(j, k);
+          Lraw(i, j) = a;
+        }
+      Mat3 Rp = so3_exp(pose + 3);
+      Mat3 Rerr = mat3_mul(mat3_T(Rp), Rmf);
+      double dr[3];
+      so3_log(Rerr, dr);
+      double c6[6];
+      Mat3 L = psd_project3(Lraw, P.eps_psd, c6);
+      double hr[3];
+      mat3_vec(L, dr, hr);
+      const double nll = 0.5 * (dr[0] * hr[0] + dr[1] * hr[1] + dr[2] * hr[2]);
+      const double Neff = Neff_mf;
+      for (int k = 0; k < 9; ++k) ev[GCS_EV_L_ROT + k] = L.m[k];
+      for (int k = 0; k < 3; ++k) { ev[GCS_EV_H_ROT + k] = hr[k]; ev[GCS_EV_DELTA_ROT + k] = dr[k]; ev[GCS_EV_SVD_S + k] = sv[k]; }
+      const double smin = fmin(sv[0], fmin(sv[1], sv[2])), smax = fmax(sv[0], fmax(sv[1], sv[2]));
+      ev[GCS_EV_MF_EIG_MIN] = smin; ev[GCS_EV_MF_EIG_MAX] = smax; ev[GCS_EV_MF_COND] = smax / (smin + eps);
+      ev[GCS_EV_MF_NEAR_NULL] = (double)((sv[0] < eps) + (sv[1] < eps) + (sv[2] < eps));
+      ev[GCS_EV_MF_NLL_PER_ESS] = nll / (Neff + eps);
+      ev[GCS_EV_MF_DIR_SCORE] = sv[0] + sv[1] + sv[2];
+      ev[GCS_EV_MF_PSD_DELTA] = c6[0];
+      ev[GCS_EV_MF_MASS_EPS] = eps / (Neff + eps);
+      ev[GCS_EV_MF_ROT_NLL] = nll;
+      ev[GCS_EV_MF_N_EFF] = Neff;
+    }
+  } else if (!P.do_pt) {
+    if (tid == 0) for (int k = GCS_EV_T_WLS; k < GCS_EV_MF_EIG_MIN; ++k) ev[k] = 0.0;
+    if (tid == 0) for (int k = GCS_EV_PT_EIG_MIN; k < GCS_EV_NREC; ++k) ev[k] = 0.0;
+  } else {
+    // ---------------- PlanarTranslationEvidence (matrix_fisher_evidence.py:413-499, :502-671)
+    {
+      Mat3 R;
+      for (int k = 0; k < 9; ++k) R.m[k] = sR[k];
+      const double* mo = sMap + b * 12;
+      double cen[3] = {0, 0, 0};
+      Mat3 Sc;
+      for (int k = 0; k < 9; ++k) Sc.m[k] = 0.0;
+      if (on) {
+        for (int k = 0; k < 3; ++k) cen[k] = mo[k];
+        for (int k = 0; k < 9; ++k) Sc.m[k] = mo[3 + k];
+      }
+      double pr[3];
+      mat3_vec(R, pbar, pr);
+      const double tb[3] = {cen[0] - pr[0], cen[1] - pr[1], cen[2] - pr[2]};
+      Mat3 RS = mat3_mul(mat3_mul(R, Sig), mat3_T(R));
+      Mat3 Sg;
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Sg(i, j) = (Sc(i, j) + RS(i, j)) + ((i == j) ? eps : 0.0);
+      const double wb = sqrt(N * mN_pos + eps);
+      Mat3 Wi = mat3_inv(Sg);
+      double* r = red + b * kRedW;
+      for (int k = 0; k < 9; ++k) { Wi.m[k] *= wb; r[k] = on ? Wi.m[k] : 0.0; }
+      double hb[3];
+      mat3_vec(Wi, tb, hb);
+      for (int k = 0; k < 3; ++k) r[9 + k] = on ? hb[k] : 0.0;
+      r[12] = on ? wb : 0.0;
+    }
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+    if (tid < 13) {
+      double a = 0.0;
+      for (int k = 0; k < B; ++k) a += red[k * kRedW + tid];
+      tot[tid] = a;
+    }
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+    if (tid == 0) {
+      const double zs = sZs;
+      Mat3 Lf;
+      for (int k = 0; k < 9; ++k) Lf.m[k] = tot[k];
+      const double hf[3] = {tot[9], tot[10], tot[11]};
+      Mat3 Lreg = Lf;
+      Lreg(0, 0) += eps; Lreg(1, 1) += eps; Lreg(2, 2) += eps;
+      double tw[3];
+      mat3_solve(Lreg, hf, tw);
+      const double mk[3] = {1.0, 1.0, zs};
+      Mat3 Lraw;
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Lraw(i, j) = Lf(i, j) * mk[i] * mk[j];
+      const double Neff = tot[12];
+      const double dt[3] = {tw[0] - pose[0], tw[1] - pose[1], tw[2] - pose[2]};
+      double c6[6];
+      Mat3 L = psd_project3(Lraw, P.eps_psd, c6);
+      double ht[3];
+      mat3_vec(L, dt, ht);
+      const double nll = 0.5 * (dt[0] * ht[0] + dt[1] * ht[1] + dt[2] * ht[2]);
+      for (int k = 0; k < 3; ++k) { ev[GCS_EV_T_WLS + k] = tw[k]; ev[GCS_EV_H_TRANS + k] = ht[k]; ev[GCS_EV_DELTA_TRANS + k] = dt[k]; }
+      for (int k = 0; k < 9; ++k) { ev[GCS_EV_L_TRANS + k] = L.m[k]; sL[k] = L.m[k]; }
+      ev[GCS_EV_XY_INFO] = 0.5 * (L(0, 0) + L(1, 1));
+      ev[GCS_EV_Z_INFO] = L(2, 2);
+      ev[GCS_EV_Z_SCALE] = zs;
+      ev[GCS_EV_PT_NLL_PER_ESS] = nll / (Neff + eps);
+      ev[GCS_EV_PT_PSD_DELTA] = c6[0];
+      ev[GCS_EV_PT_MASS_EPS] = eps / (Neff + eps);
+      ev[GCS_EV_PT_TRANS_NLL] = nll;
+      ev[GCS_EV_PT_N_EFF] = Neff;
+      for (int k = GCS_EV_PT_N_EFF + 1; k < GCS_EV_NREC; ++k) ev[k] = 0.0;
+    }
+  }
+  __syncthreads();   // both halves done: every field of the evidence record except the conditioning scalars is written
+  if (!P.do_pt) return;
+  if (tid == kMaxBins) {
+    // conditioning of the projected information matrix (eigvalsh of L, :640-655): nothing below depends on it
+    Mat3 L;
+    for (int k = 0; k < 9; ++k) L.m[k] = sL[k];
     double le[3];
     Mat3 Vl;
     eigh3(L, le, Vl);
-    for (int k = 0; k < 3; ++k) { ev[GCS_EV_T_WLS + k] = tw[k]; ev[GCS_EV_H_TRANS + k] = ht[k]; ev[GCS_EV_DELTA_TRANS + k] = dt[k]; }
-    for (int k = 0; k < 9; ++k) ev[GCS_EV_L_TRANS + k] = L.m[k];
-    ev[GCS_EV_XY_INFO] = 0.5 * (L(0, 0) + L(1, 1));
-    ev[GCS_EV_Z_INFO] = L(2, 2);
-    ev[GCS_EV_Z_SCALE] = zs;
     ev[GCS_EV_PT_EIG_MIN] = le[0]; ev[GCS_EV_PT_EIG_MAX] = le[2]; ev[GCS_EV_PT_COND] = le[2] / (le[0] + eps);
     ev[GCS_EV_PT_NEAR_NULL] = (double)((le[0] < eps) + (le[1] < eps) + (le[2] < eps));
-    ev[GCS_EV_PT_NLL_PER_ESS] = nll / (Neff + eps);
-    ev[GCS_EV_PT_PSD_DELTA] = c6[0];
-    ev[GCS_EV_PT_MASS_EPS] = eps / (Neff + eps);
-    ev[GCS_EV_PT_TRANS_NLL] = nll;
-    ev[GCS_EV_PT_N_EFF] = Neff;
-    for (int k = GCS_EV_PT_N_EFF + 1; k < GCS_EV_NREC; ++k) ev[k] = 0.0;
   }
-  __syncthreads();
   // ---------------- build_combined_lidar_evidence_22d (:729-756)
   if (P.L22) {
     double* L22 = P.L22 + (int64_t)u * 22 * 22;
-    for (int idx = b; idx < 22 * 22; idx += kFinalThreads) {
+    for (int idx = tid; idx < 22 * 22; idx += kFinalThreads) {
       const int r = idx / 22, c = idx - r * 22;
       double v = 0.0;
-      if (r < 3 && c < 3) v = ev[GCS_EV_L_TRANS + 3 * r + c];
+      if (r < 3 && c < 3) v = sL[3 * r + c];
       else if (r >= 3 && r < 6 && c >= 3 && c < 6) v = ev[GCS_EV_L_ROT + 3 * (r - 3) + (c - 3)];
       L22[idx] = v;
     }
   }
-  if (P.h22 && b < 22) {
+  if (P.h22 && tid < 22) {
     double v = 0.0;
-    if (b < 3) v = ev[GCS_EV_H_TRANS + b];
-    else if (b < 6) v = ev[GCS_EV_H_ROT + (b - 3)];
-    P.h22[(int64_t)u * 22 + b] = v;
+    if (tid < 3) v = ev[GCS_EV_H_TRANS + tid];
+    else if (tid < 6) v = ev[GCS_EV_H_ROT + (tid - 3)];
+    P.h22[(int64_t)u * 22 + tid] = v;
   }
 }
 

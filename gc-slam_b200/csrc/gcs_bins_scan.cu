@@ -110,23 +110,59 @@ __global__ void __launch_bounds__(256) mass_partial_kernel(const double* __restr
   __shared__ double sred[8];
   const int s = blockIdx.y, c = blockIdx.x;
   const double* ws = w + (int64_t)s * n_raw;
-  int64_t r0 = (int64_t)c * rows_per_chunk;
+  const int64_t r0 = (int64_t)c * rows_per_chunk;
   int64_t r1 = r0 + rows_per_chunk;
   if (r1 > n_raw) r1 = n_raw;
+  const int n = (int)(r1 > r0 ? r1 - r0 : 0);          // rows of this chunk (chunks are < 2^31 rows)
+  const double* wc = ws + r0;
   double a = 0.0, b = 0.0, q = 0.0, cnt = 0.0;
-  for (int64_t j = r0 + threadIdx.x; j < r1; j += blockDim.x) {
-    double v = ws[j];
-    a += v;
-    if (j % stride == 0) { b += v; q += v * v; cnt += 1.0; }
+  if (stride == 1) {
+    // every row is selected: one pass, 16-byte loads when the chunk is aligned.  Each thread keeps two partial sums
+    // (even / odd element of its pairs) combined in a fixed order below.
+    double a1 = 0.0, q1 = 0.0;
+    if ((reinterpret_cast<uintptr_t>(wc) & 15) == 0) {
+      const double2* w2 = reinterpret_cast<const double2*>(wc);
+      const int n2 = n >> 1;
+#pragma unroll 8
+      for (int j = threadIdx.x; j < n2; j += 256) {
+        const double2 v = __ldg(w2 + j);
+        a += v.x; q = fma(v.x, v.x, q);
+        a1 += v.y; q1 = fma(v.y, v.y, q1);
+      }
+      if ((n & 1) && threadIdx.x == 0) { const double v = wc[n - 1]; a += v; q = fma(v, v, q); }
+    } else {
+#pragma unroll 4
+      for (int j = threadIdx.x; j < n; j += 256) { const double v = wc[j]; a += v; q = fma(v, v, q); }
+    }
+    a += a1; q += q1;
+    b = a;
+    cnt = 0.0;   // filled in by thread 0 below (exact integer)
+  } else {
+    // rows r0 + j with (r0 + j) % stride == 0 are selected: 32-bit phase arithmetic inside the chunk
+    const uint32_t st = (uint32_t)(stride > 0x7fffffff ? 0x7fffffff : stride);
+    const uint32_t ph0 = (uint32_t)(r0 % stride);        // phase of the first row of the chunk
+    for (int j = threadIdx.x; j < n; j += 256) {
+      const double v = wc[j];
+      a += v;
+      const bool sel = stride > 0x7fffffff ? (r0 + j) % stride == 0 : ((ph0 + (uint32_t)j) % st) == 0;
+      if (sel) { b += v; q = fma(v, v, q); cnt += 1.0; }
+    }
   }
-  double A = block_sum_fixed(a, sred);
-  double Bs = block_sum_fixed(b, sred);
-  double Qs = block_sum_fixed(q, sred);
-  double Cn = block_sum_fixed(cnt, sred);
-  if (threadIdx.x == 0) {
-    double* o = partial + ((int64_t)s * gridDim.x + c) * kNMass;
-    o[kMassAll] = A; o[kMassSel] = Bs; o[kMassSelSq] = Qs; o[kMassNSel] = Cn;
+  // one fixed-order block reduction for the four sums
+  __shared__ double s4[4][8];
+  a = warp_sum(a); b = warp_sum(b); q = warp_sum(q); cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) {
+    const int wi = threadIdx.x >> 5;
+    s4[0][wi] = a; s4[1][wi] = b; s4[2][wi] = q; s4[3][wi] = cnt;
   }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double r = 0.0;
+    for (int i = 0; i < 8; ++i) r += s4[threadIdx.x][i];
+    if (threadIdx.x == kMassNSel && stride == 1) r = (double)n;
+    partial[((int64_t)s * gridDim.x + c) * kNMass + threadIdx.x] = r;
+  }
+  (void)sred;
 }
 __global__ void mass_final_kernel(const double* __restrict__ partial, int chunks, int n_scans, double* __restrict__ mass) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -706,8 +742,12 @@ static int bins_geometry(gcs_ctx* ctx, const gcs_bins_args* a, BinsGeom* g) {
   g->tc_parts = a->precision == GCS_PREC_TC ? bin_scan_tc_parts(ctx->sm_count, g->U, a->cap) : 0;
   g->raw_len = raw_sums_len(a->n_bins);
   g->part_len = g->raw_len + kNMax;
-  int64_t chunks = ceil_div64(a->n_raw > 0 ? a->n_raw : 1, 2048);
+  // ~4 CTAs per SM over the whole batch, >= 1024 rows each, at most 64 per scan: fat chunks keep the loads in flight
+  int64_t chunks = ceil_div64(4 * (int64_t)ctx->sm_count, a->n_scans);
+  const int64_t max_by_rows = ceil_div64(a->n_raw > 0 ? a->n_raw : 1, 1024);
+  if (chunks > max_by_rows) chunks = max_by_rows;
   if (chunks > 64) chunks = 64;
+  if (chunks < 1) chunks = 1;
   g->mass_chunks = (int)chunks;
   g->mass_rows_per_chunk = ceil_div64(a->n_raw > 0 ? a->n_raw : 1, chunks);
   // keep stride alignment of chunk boundaries irrelevant: selection uses the absolute local row index

@@ -150,14 +150,50 @@ __host__ __device__ inline void mat3_solve(const Mat3& A, const double* b, doubl
   }
 }
 
+// ---- division-free float64 helpers (MUFU seed + Newton; ~1 ulp, no denormal/branchy slow path) -------------------
+// x must be finite and > 0 (or +inf: returns 0).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+// 1/sqrt(x) for finite x > 0
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  return fma(y, e, y);
+}
 // One Jacobi rotation annihilating a_pq of a symmetric 3x3; (arp, arq) are the two entries coupling the third
 // index r to p and q; vp / vq are the eigenvector columns p and q.  Everything stays in registers.
 __host__ __device__ inline void jacobi_rot(double& app, double& aqq, double& apq, double& arp, double& arq, double* vp,
                                            double* vq) {
   if (apq == 0.0) return;
+#ifdef __CUDA_ARCH__
+  // device: reciprocal / reciprocal-sqrt by MUFU seed + Newton (the IEEE division and sqrt sequences are ~3x longer
+  // dependent chains, and this rotation sits on the serial path of every 3x3 eigen-decomposition of the epilogue)
+  if (fabs(apq) < 1e-290) return;
+  const double theta = (aqq - app) * (0.5 * fast_rcp(fabs(apq))) * (apq < 0.0 ? -1.0 : 1.0);
+  const double th1 = fma(theta, theta, 1.0);
+  double t, c;
+  if (th1 < 1e300) {
+    t = (theta >= 0.0 ? 1.0 : -1.0) * fast_rcp(fabs(theta) + th1 * fast_rsqrt(th1));
+    c = fast_rsqrt(fma(t, t, 1.0));
+  } else {   // |theta| > 1e150: the rotation angle is below double precision
+    t = 0.5 / theta;
+    c = 1.0;
+  }
+#else
   const double theta = (aqq - app) / (2.0 * apq);
   const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
   const double c = 1.0 / sqrt(t * t + 1.0);
+#endif
   const double sn = t * c;
   app -= t * apq;
   aqq += t * apq;
@@ -248,9 +284,26 @@ __host__ __device__ inline double hestenes_rot(double* gp, double* gq, double* v
   const double denom = sqrt(alpha * beta);
   const double rel = denom > 0.0 ? fabs(gamma) / denom : 0.0;
   if (rel < 1e-17) return rel;
+#ifdef __CUDA_ARCH__
+  if (fabs(gamma) < 1e-290) return 0.0;
+  double t, c;
+  {
+    const double zeta = (beta - alpha) * (0.5 * fast_rcp(fabs(gamma))) * (gamma < 0.0 ? -1.0 : 1.0);
+    const double z1 = fma(zeta, zeta, 1.0);
+    if (z1 < 1e300) {
+      t = (zeta >= 0.0 ? 1.0 : -1.0) * fast_rcp(fabs(zeta) + z1 * fast_rsqrt(z1));
+      c = fast_rsqrt(fma(t, t, 1.0));
+    } else {
+      t = 0.5 / zeta;
+      c = 1.0;
+    }
+  }
+  const double sn = c * t;
+#else
   const double zeta = (beta - alpha) / (2.0 * gamma);
   const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
   const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+#endif
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const double a = gp[k], b = gq[k];
@@ -510,26 +563,6 @@ __device__ inline double window_inv_sigma(double t0, double t1) {
   return 1.0 / fmax(kTimeWarpSigmaFrac * fmax(t1 - t0, 1e-12), 1e-6);
 }
 
-// ---- division-free float64 helpers (MUFU seed + Newton; ~1 ulp, no denormal/branchy slow path) -------------------
-// x must be finite and > 0 (or +inf: returns 0).
-__device__ __forceinline__ double fast_rcp(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  return fma(r, e, r);
-}
-// 1/sqrt(x) for finite x > 0
-__device__ __forceinline__ double fast_rsqrt(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double hx = 0.5 * x;
-  double e = fma(-hx * y, y, 0.5);
-  y = fma(y, e, y);
-  e = fma(-hx * y, y, 0.5);
-  return fma(y, e, y);
-}
 // 2^t for |t| <= 1000 (clamped): same polynomial as exp2_nonpos
 __device__ __forceinline__ double exp2_bounded(double t) {
   t = fmin(fmax(t, -1000.0), 1000.0);

@@ -785,6 +785,23 @@ class BinPathPlan:
         return moved
 
     # -- launches ----------------------------------------------------------------------------------
+    def capture(self):
+        """
+        Capture run() (mass, memset, scan, reduce, finalize: seven small launches) into a CUDA graph; replay() then
+        costs one graph launch.  The buffers of the plan are fixed, so upload() / upload_pointcloud2() between replays
+        feed new scans.  Call after set_bins / set_map / the first upload.
+        """
+        self.run()                       # reserves the workspace and sets kernel attributes outside the capture
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run()
+        self._graph = g
+        return self
+
+    def replay(self):
+        self._graph.replay()
+
     def run(self):
         io = self.io
         io.ctx.check(io.ctx.lib.gcs_lidar_evidence_bins(io.ctx.handle, io.stream(), C.byref(self.args)))
