@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(kBig) assoc_sinkhorn_kernel(gcs_meas_batch B, 
                                                               gcs_assoc_cfg cfg, gcs_assoc_result R,
                                                               double* __restrict__ cert, double* __restrict__ brow_ws) {
   __shared__ double sred[32];
+  __shared__ double sredK[(kBig / 32) * K];
   __shared__ double sv[K];
   __shared__ SelectSmem sel;
   const int tid = threadIdx.x;
@@ -347,9 +348,19 @@ __global__ void __launch_bounds__(kBig) assoc_sinkhorn_kernel(gcs_meas_batch B, 
       u[q] = pow(a[q] / (kv + 1e-12), ua);
       for (int k = 0; k < K; ++k) ktu[k] += Km[q][k] * u[q];
     }
-    double tot[K];
-    for (int k = 0; k < K; ++k) tot[k] = block_sum_1024(ktu[k], sred);
-    if (tid < K) sv[tid] = pow(bk / (tot[tid] + 1e-12), vb);
+    // all K column sums in one fixed-order block reduction (2 barriers per Sinkhorn iteration instead of 25)
+#pragma unroll
+    for (int k = 0; k < K; ++k) ktu[k] = warp_sum(ktu[k]);
+    if ((tid & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) sredK[(tid >> 5) * K + k] = ktu[k];
+    }
+    __syncthreads();
+    if (tid < K) {
+      double t = 0.0;
+      for (int w = 0; w < kBig / 32; ++w) t += sredK[w * K + tid];
+      sv[tid] = pow(bk / (t + 1e-12), vb);
+    }
     __syncthreads();
   }
   // outputs + certificate sums
@@ -603,47 +614,63 @@ __global__ void __launch_bounds__(kBig) upd_sort_pairs_kernel(gcs_meas_batch B, 
   for (int p = threadIdx.x; p < n_pow2; p += kBig) out[p] = sp[p];
 }
 
-// one thread per sorted position; segment heads fold their segment into the tile slot (primitive_map.py:1037-1123)
+// One WARP per sorted position; the warp of a segment head folds its segment into the tile slot
+// (primitive_map.py:1037-1123): lanes stride over the segment's pairs (ascending pair index), then a fixed shuffle tree
+// combines the 32 lane sums -- deterministic, and popular slots (hundreds of pairs) cost L/32 iterations instead of L.
+constexpr int kFuseVals = 29;   // dLambda 9, deta 9, dtheta 3, dw, dr, dcam, dlid, dacc 3, dden
 __global__ void __launch_bounds__(256) upd_fuse_kernel(gcs_atlas A, TileList T, gcs_meas_batch B, int K, gcs_assoc_result R,
                                                        UpdWs W, int n_pow2, gcs_map_update_cfg cfg,
                                                        double* __restrict__ part) {
   __shared__ double sred[8];
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   double fused_mass = 0.0;
   if (q < n_pow2) {
     const unsigned long long e = W.pairs[q];
     const unsigned key = (unsigned)(e >> 32);
-    const bool head = key != 0xffffffffu && (q == 0 || (unsigned)(W.pairs[q - 1] >> 32) != key);
+    const bool head = key != 0xffffffffu && (q == 0 || (unsigned)(W.pairs[q - 1] >> 32) != key);   // warp-uniform
     if (head) {
-      const int a = (int)(key / (unsigned)A.m_tile), slot = (int)(key % (unsigned)A.m_tile);
-      const int64_t o = (int64_t)T.index[a] * A.m_tile + slot;
-      double dL[9], dth[3], det[9], dw = 0, drs = 0, dcam = 0, dlid = 0, dacc[3] = {0, 0, 0}, dden = 0;
-      for (int k = 0; k < 9; ++k) { dL[k] = 0; det[k] = 0; }
-      for (int k = 0; k < 3; ++k) dth[k] = 0;
-      for (int j = q; j < n_pow2; ++j) {
-        const unsigned long long ej = W.pairs[j];
-        if ((unsigned)(ej >> 32) != key) break;
-        const int p = (int)(unsigned)(ej & 0xffffffffull);
-        const int i = p / K;
-        const double r = R.responsibilities[p];
-        const double wm = B.weights[i];
-        for (int k = 0; k < 9; ++k) { dL[k] += r * W.Lw[9 * i + k]; det[k] += r * W.etw[9 * i + k]; }
-        for (int k = 0; k < 3; ++k) dth[k] += r * W.thw[3 * i + k];
-        dw += r * wm; drs += r;
-        const double wc = r * wm * (B.sources[i] == 0 ? 1.0 : 0.0), wl = r * wm * (B.sources[i] == 1 ? 1.0 : 0.0);
-        dcam += wc; dlid += wl; dden += wc;
-        for (int k = 0; k < 3; ++k) dacc[k] += fmin(fmax(B.colors[3 * i + k], 0.0), 1.0) * wc;
-        fused_mass += wm * r;
+      double v[kFuseVals];
+#pragma unroll
+      for (int k = 0; k < kFuseVals; ++k) v[k] = 0.0;
+      for (int base = q;; base += 32) {
+        const int j = base + lane;
+        bool valid = j < n_pow2;
+        unsigned long long ej = 0;
+        if (valid) { ej = W.pairs[j]; valid = (unsigned)(ej >> 32) == key; }
+        if (valid) {
+          const int p = (int)(unsigned)(ej & 0xffffffffull);
+          const int i = p / K;
+          const double r = R.responsibilities[p];
+          const double wm = B.weights[i];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) { v[k] += r * W.Lw[9 * i + k]; v[9 + k] += r * W.etw[9 * i + k]; }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) v[18 + k] += r * W.thw[3 * i + k];
+          v[21] += r * wm; v[22] += r;
+          const double wc = r * wm * (B.sources[i] == 0 ? 1.0 : 0.0), wl = r * wm * (B.sources[i] == 1 ? 1.0 : 0.0);
+          v[23] += wc; v[24] += wl; v[28] += wc;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) v[25 + k] += fmin(fmax(B.colors[3 * i + k], 0.0), 1.0) * wc;
+          fused_mass += wm * r;
+        }
+        if (!__all_sync(0xffffffffu, valid)) break;
       }
-      for (int k = 0; k < 9; ++k) { A.Lambdas[9 * o + k] += dL[k]; A.etas[9 * o + k] += det[k]; }
-      for (int k = 0; k < 3; ++k) { A.thetas[3 * o + k] += dth[k]; A.rgb_cam_accum[3 * o + k] += dacc[k]; }
-      A.weights[o] += dw; A.cam_mass[o] += dcam; A.lidar_mass[o] += dlid; A.rgb_cam_denom[o] += dden;
-      if (drs > 0.0) { A.last_supported_scan_seq[o] = cfg.scan_seq; A.last_update_scan_seq[o] = cfg.scan_seq; }
-      if (!cfg.strict_tile_state) A.timestamps[o] = cfg.timestamp;
+#pragma unroll
+      for (int k = 0; k < kFuseVals; ++k) v[k] = warp_sum(v[k]);
+      if (lane == 0) {
+        const int a = (int)(key / (unsigned)A.m_tile), slot = (int)(key % (unsigned)A.m_tile);
+        const int64_t o = (int64_t)T.index[a] * A.m_tile + slot;
+        for (int k = 0; k < 9; ++k) { A.Lambdas[9 * o + k] += v[k]; A.etas[9 * o + k] += v[9 + k]; }
+        for (int k = 0; k < 3; ++k) { A.thetas[3 * o + k] += v[18 + k]; A.rgb_cam_accum[3 * o + k] += v[25 + k]; }
+        A.weights[o] += v[21]; A.cam_mass[o] += v[23]; A.lidar_mass[o] += v[24]; A.rgb_cam_denom[o] += v[28];
+        if (v[22] > 0.0) { A.last_supported_scan_seq[o] = cfg.scan_seq; A.last_update_scan_seq[o] = cfg.scan_seq; }
+        if (!cfg.strict_tile_state) A.timestamps[o] = cfg.timestamp;
+      }
     }
   }
-  double s = warp_sum(fused_mass);
-  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  const double s = warp_sum(fused_mass);
+  if (lane == 0) sred[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
@@ -1058,7 +1085,7 @@ int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int
   const int n_blocks = (N + block_rows - 1) / block_rows;
   cudaStream_t st = (cudaStream_t)stream;
   const int sweep_blocks = (int)(cdivm(atlas->m_tile, 256) < 64 ? cdivm(atlas->m_tile, 256) : 64);
-  const int fuse_blocks = n_pow2 / 256 > 0 ? n_pow2 / 256 : 1;
+  const int fuse_blocks = (n_pow2 + 7) / 8;   // upd_fuse_kernel: one warp per sorted position, 8 warps per block
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_Lw = take((size_t)N * 72), o_thw = take((size_t)N * 24), o_etw = take((size_t)N * 72), o_mt = take((size_t)N * 8),

@@ -61,77 +61,124 @@ __device__ inline void cta_bitonic_sort_u64(unsigned long long* s, int n_pow2) {
 }
 
 // Select the k smallest (key, index) pairs among n items; result sorted ascending in out[0..k).
-//   KeyFn: unsigned long long operator()(int i) const   (must be cheap: it is evaluated ~10 times per item)
-//   out:   shared memory, capacity >= next_pow2(k)
-//   hist:  shared memory, 256 ints;  scan: shared memory, 2*blockDim.x ints
-// Requires k <= n.  All threads of the CTA must call.
+//   KeyFn: unsigned long long operator()(int i) const   (evaluated ~4-5 times per item)
+//   out:   shared memory, capacity >= max(1024, next_pow2(k)) entries (also used as the candidate buffer)
+//   hist:  unused (kept for the call sites);  scan: shared memory, >= 1024 + 64 ints
+// Requires k <= n and k <= 1024.  All threads of the CTA must call; blockDim.x >= 32.
+//
+// MSD radix select with 10-bit digits.  As soon as the items that still match the prefix fit the candidate buffer
+// (usually after two passes) they are gathered and sorted by (key, index), which yields the k-th key T and the index
+// T_idx of the last tie that is taken; a single sweep then collects {key < T} and {key == T, index <= T_idx} in any
+// order and a bitonic sort by (key, index) puts them in the order of a stable sort.  When more than 1024 items tie on
+// the k-th key (e.g. a tile with fewer than k valid slots) T_idx comes from an index-ordered count of the ties.
 template <typename KeyFn>
 __device__ inline void cta_select_k(int n, int k, KeyFn key, KeyIdx* out, int* hist, int* scan) {
+  (void)hist;
   __shared__ unsigned long long s_prefix;
-  __shared__ int s_need;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ int s_need, s_count, s_slot, s_tidx;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  int* h = scan;            // 1024 bins
+  int* wsum = scan + 1024;  // per-warp partials of the tie count (<= 32)
   unsigned long long prefix = 0ull, mask = 0ull;
-  int need = k;  // rank (1-based) of the threshold among items matching the prefix
-  for (int pass = 7; pass >= 0; --pass) {
-    for (int b = tid; b < 256; b += nt) hist[b] = 0;
+  int need = k;             // rank (1-based) of the threshold among the items matching the prefix
+  bool have_cands = false;
+  for (int shift = 54; shift >= -6; shift -= 10) {
+    const int sh = shift < 0 ? 0 : shift;
+    const int bits = shift < 0 ? 4 : 10;
+    const unsigned long long dm = (1ull << bits) - 1ull;
+    for (int b = tid; b < 1024; b += nt) h[b] = 0;
     __syncthreads();
-    const int shift = pass * 8;
     for (int i = tid; i < n; i += nt) {
       const unsigned long long kk = key(i);
-      if ((kk & mask) == prefix) atomicAdd(&hist[(int)((kk >> shift) & 0xffull)], 1);
+      if ((kk & mask) == prefix) atomicAdd(&h[(int)((kk >> sh) & dm)], 1);
     }
     __syncthreads();
-    if (tid == 0) {
-      int acc = 0, b = 0;
-      for (; b < 256; ++b) {
-        if (acc + hist[b] >= need) break;
-        acc += hist[b];
+    if (tid < 32) {
+      // lane l owns bins [32 l, 32 l + 32): local sum, exclusive scan over lanes, then the owning lane walks its bins
+      int loc = 0;
+      for (int b = 0; b < 32; ++b) loc += h[32 * lane + b];
+      int inc = loc;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
       }
-      s_prefix = prefix | ((unsigned long long)b << shift);
-      s_need = need - acc;
+      const int exc = inc - loc;
+      if (exc < need && need <= inc) {
+        int acc = exc, b = 32 * lane;
+        for (;; ++b) {
+          if (acc + h[b] >= need) break;
+          acc += h[b];
+        }
+        s_prefix = prefix | ((unsigned long long)b << sh);
+        s_need = need - acc;
+        s_count = h[b];
+      }
     }
     __syncthreads();
     prefix = s_prefix;
     need = s_need;
-    mask |= (0xffull << shift);
+    mask |= (dm << sh);
+    const int m = s_count;
     __syncthreads();
+    if (m <= 1024) { have_cands = true; break; }
   }
-  const unsigned long long T = prefix;  // k-th smallest key; `need` = how many items equal to T are taken
-  // index-ordered compaction: thread t owns the contiguous chunk [c0, c1)
-  const int chunk = (n + nt - 1) / nt;
-  const int c0 = tid * chunk, c1 = (c0 + chunk < n) ? c0 + chunk : n;
-  int n_less = 0, n_eq = 0;
-  for (int i = c0; i < c1; ++i) {
-    const unsigned long long kk = key(i);
-    n_less += (kk < T);
-    n_eq += (kk == T);
-  }
-  scan[tid] = n_less;
-  scan[nt + tid] = n_eq;
-  __syncthreads();
-  if (tid == 0) {
-    int a = 0, b = 0;
-    for (int t = 0; t < nt; ++t) {
-      const int x = scan[t], y = scan[nt + t];
-      scan[t] = a; scan[nt + t] = b;
-      a += x; b += y;
+  unsigned long long T = prefix;
+  int T_idx = 0x7fffffff;
+  if (have_cands) {
+    if (tid == 0) s_slot = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+      const unsigned long long kk = key(i);
+      if ((kk & mask) == prefix) {
+        const int sl = atomicAdd(&s_slot, 1);
+        out[sl].key = kk; out[sl].idx = i;
+      }
     }
-    s_need = a;  // total number of keys strictly below T  (== k - need)
+    __syncthreads();
+    const int m = s_slot;
+    int mp = 1;
+    while (mp < m) mp <<= 1;
+    for (int i = m + tid; i < mp; i += nt) { out[i].key = ~0ull; out[i].idx = 0x7fffffff; }
+    __syncthreads();
+    cta_bitonic_sort(out, mp);
+    T = out[need - 1].key;
+    T_idx = out[need - 1].idx;
+    __syncthreads();
+  } else {
+    // more than 1024 items equal the k-th key: take the first `need` of them in index order
+    const int chunk = (n + nt - 1) / nt;
+    const int c0 = tid * chunk, c1 = (c0 + chunk < n) ? c0 + chunk : n;
+    int n_eq = 0;
+    for (int i = c0; i < c1; ++i) n_eq += (key(i) == T);
+    int inc = n_eq;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) wsum[tid >> 5] = inc;
+    __syncthreads();
+    int before = inc - n_eq;
+    for (int w = 0; w < (tid >> 5); ++w) before += wsum[w];
+    if (before < need && need <= before + n_eq) {
+      int r = before;
+      for (int i = c0; i < c1; ++i)
+        if (key(i) == T && ++r == need) { s_tidx = i; break; }
+    }
+    __syncthreads();
+    T_idx = s_tidx;
   }
+  if (tid == 0) s_slot = 0;
   __syncthreads();
-  const int total_less = s_need;
-  int o_less = scan[tid], o_eq = scan[nt + tid];
-  for (int i = c0; i < c1; ++i) {
+  for (int i = tid; i < n; i += nt) {
     const unsigned long long kk = key(i);
-    if (kk < T) {
-      out[o_less].key = kk; out[o_less].idx = i; ++o_less;
-    } else if (kk == T) {
-      if (o_eq < need) { out[total_less + o_eq].key = kk; out[total_less + o_eq].idx = i; }
-      ++o_eq;
+    if (kk < T || (kk == T && i <= T_idx)) {
+      const int sl = atomicAdd(&s_slot, 1);
+      out[sl].key = kk; out[sl].idx = i;
     }
   }
   int kp = 1;
   while (kp < k) kp <<= 1;
+  __syncthreads();
   for (int i = k + tid; i < kp; i += nt) { out[i].key = ~0ull; out[i].idx = 0x7fffffff; }
   __syncthreads();
   cta_bitonic_sort(out, kp);
