@@ -284,6 +284,10 @@ __global__ void __launch_bounds__(256) assoc_topk_kernel(gcs_meas_batch B, int N
   }
 }
 
+// x^y for x >= 0 (0^y = 0 for y > 0) as exp(y log x): the Sinkhorn scalings are smooth in x, the ~|y log x| ulp of this
+// form are far inside the tolerance, and it is ~3x shorter than the correctly-rounded pow() on the serial path
+__device__ __forceinline__ double pow_pos(double x, double y) { return x > 0.0 ? exp(y * log(x)) : 0.0; }
+
 // single CTA: cost of the selected candidates, recency term, row-min shift, unbalanced Sinkhorn, certificates
 template <int K>
 __global__ void __launch_bounds__(kBig) assoc_sinkhorn_kernel(gcs_meas_batch B, int N, gcs_map_view V, AssocWs W,
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(kBig) assoc_sinkhorn_kernel(gcs_meas_batch B, 
       if (i >= N) continue;
       double kv = 0.0;
       for (int k = 0; k < K; ++k) kv += Km[q][k] * sv[k];
-      u[q] = pow(a[q] / (kv + 1e-12), ua);
+      u[q] = pow_pos(a[q] / (kv + 1e-12), ua);
       for (int k = 0; k < K; ++k) ktu[k] += Km[q][k] * u[q];
     }
     // all K column sums in one fixed-order block reduction (2 barriers per Sinkhorn iteration instead of 25)
@@ -356,10 +360,15 @@ __global__ void __launch_bounds__(kBig) assoc_sinkhorn_kernel(gcs_meas_batch B, 
       for (int k = 0; k < K; ++k) sredK[(tid >> 5) * K + k] = ktu[k];
     }
     __syncthreads();
-    if (tid < K) {
+    if (tid < 32) {
+      // warp 0: lane l holds warp l's partials; one shuffle tree per column
       double t = 0.0;
-      for (int w = 0; w < kBig / 32; ++w) t += sredK[w * K + tid];
-      sv[tid] = pow(bk / (t + 1e-12), vb);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const double c = warp_sum(sredK[tid * K + k]);
+        if (tid == k) t = c;
+      }
+      if (tid < K) sv[tid] = pow_pos(bk / (t + 1e-12), vb);
     }
     __syncthreads();
   }
@@ -858,27 +867,44 @@ __global__ void __launch_bounds__(256) upd_maintain_kernel(gcs_atlas A, TileList
   }
 }
 
-__global__ void upd_stats_kernel(UpdWs W, const double* __restrict__ fuse_part, int n_fuse_parts,
-                                 const int* __restrict__ blk_unique, int n_blocks, const double* __restrict__ maint_part,
-                                 int maint_blocks, int n_tiles, int k_ins, gcs_map_update_cfg cfg, double* __restrict__ stats) {
+// fixed-order block sum of a strided array by 256 threads (thread t adds elements t, t+256, ..., then a shuffle /
+// shared-memory tree): deterministic, and ~n/256 dependent loads instead of n
+__device__ __forceinline__ double sum256(const double* __restrict__ p, int n, int stride, double* sbuf) {
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) a += p[(int64_t)i * stride];
+  a = warp_sum(a);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sbuf[threadIdx.x >> 5] = a;
+  __syncthreads();
+  double r = 0.0;
+  for (int w = 0; w < 8; ++w) r += sbuf[w];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(256) upd_stats_kernel(UpdWs W, const double* __restrict__ fuse_part, int n_fuse_parts,
+                                                        const int* __restrict__ blk_unique, int n_blocks,
+                                                        const double* __restrict__ maint_part, int maint_blocks, int n_tiles,
+                                                        int k_ins, gcs_map_update_cfg cfg, double* __restrict__ stats) {
+  __shared__ double sbuf[8];
+  const double fm = sum256(fuse_part, n_fuse_parts, 1, sbuf);
+  double nc = 0.0, mc = 0.0;
+  for (int a = 0; a < n_tiles; ++a) {
+    const double* mp = maint_part + (int64_t)a * maint_blocks * 3;
+    nc += sum256(mp, maint_blocks, 3, sbuf);
+    mc += sum256(mp + 1, maint_blocks, 3, sbuf);
+    const double tv = sum256(mp + 2, maint_blocks, 3, sbuf);
+    if (threadIdx.x == 0 && a < 16) stats[GCS_MU_TILE_COUNT0 + a] = tv;
+  }
   if (threadIdx.x != 0) return;
-  double fm = 0.0;
-  for (int c = 0; c < n_fuse_parts; ++c) fm += fuse_part[c];
   long long uq = 0;
   for (int b = 0; b < n_blocks; ++b) uq += blk_unique[b];
-  double im = 0.0, p95 = 0.0, nc = 0.0, mc = 0.0;
+  double im = 0.0, p95 = 0.0;
   long long ni = 0;
   for (int a = 0; a < n_tiles; ++a) {
     im += W.part[64 + 2 * a];
     p95 = fmax(p95, W.part[64 + 2 * a + 1]);
     ni += W.n_ins[a];
-    double tv = 0.0;
-    for (int b = 0; b < maint_blocks; ++b) {
-      nc += maint_part[((int64_t)a * maint_blocks + b) * 3];
-      mc += maint_part[((int64_t)a * maint_blocks + b) * 3 + 1];
-      tv += maint_part[((int64_t)a * maint_blocks + b) * 3 + 2];
-    }
-    if (a < 16) stats[GCS_MU_TILE_COUNT0 + a] = tv;
   }
   stats[GCS_MU_FUSED_COUNT] = (double)(uq * n_tiles);
   stats[GCS_MU_FUSED_MASS] = fm;
@@ -888,6 +914,7 @@ __global__ void upd_stats_kernel(UpdWs W, const double* __restrict__ fuse_part, 
   stats[GCS_MU_EVICTED_COUNT] = nc;
   stats[GCS_MU_EVICTED_MASS] = mc;
   stats[GCS_MU_NEXT_GLOBAL_ID] = (double)(cfg.next_global_id + ni);
+  (void)k_ins;
 }
 
 }  // namespace gcs
@@ -1133,7 +1160,7 @@ int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int
   GCS_LAUNCH_CHECK(ctx);
   upd_maintain_kernel<<<dim3(sweep_blocks, n_tiles), 256, 0, st>>>(*atlas, T, cfg->cull_weight_threshold, cfg->forgetting_factor, mpart);
   GCS_LAUNCH_CHECK(ctx);
-  upd_stats_kernel<<<1, 32, 0, st>>>(W, fpart, fuse_blocks, uq, n_blocks, mpart, sweep_blocks, n_tiles, k_ins, *cfg, stats);
+  upd_stats_kernel<<<1, 256, 0, st>>>(W, fpart, fuse_blocks, uq, n_blocks, mpart, sweep_blocks, n_tiles, k_ins, *cfg, stats);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
 }
