@@ -405,44 +405,68 @@ __device__ __forceinline__ void epilogue_role(const BinScanParams& P, const TcGe
   }
 }
 
-// MMA issuer: one thread feeds the tensor core for the whole CTA, tiles taken in a fixed order (tile index, then warp) so
-// that every accumulator sees its warp's tiles in sequence.  Producers never block on the tensor-core queue.
+// MMA issuer: one thread feeds the tensor core for the whole CTA; producers never block on the tensor-core queue.  Lane w
+// of the issuer warp watches the barriers of producer warp w (one mbarrier.test_wait polls all of them at once) and
+// lane 0 issues whichever tiles are ready -- no fixed order across warps, so a late warp does not hold up the MMAs (and
+// hence the operand-tile release) of the others.  Each accumulator still sees only its own warp's tiles, in sequence,
+// and the epilogue drains in a fixed order: results do not depend on the issue order.
 template <int Q>
 __device__ __forceinline__ void issuer_role(const BinScanParams& P, const TcGeom& G, TcMisc& mi, unsigned char* stages,
                                             uint32_t tmem, int cta, int tid) {
   using C = TcCfg<Q>;
   constexpr int kProd = C::kProd;
   const int lane = tid & 31;
-  uint32_t n_tiles[kProd], n_rounds[kProd];
-#pragma unroll
-  for (int w = 0; w < kProd; ++w) { n_tiles[w] = 0; n_rounds[w] = 0; }
   int64_t g0 = cta_tile0(G, cta);
   const int64_t g_end = cta_tile0(G, cta + 1);
   const uint32_t idesc = tc::idesc_tf32(128, kMmaN);
   const uint32_t a0 = tc::smem_u32(stages);
   TcSeg sg;
+  // lane w (< kProd) keeps the tile / round counters of producer warp w and polls its barriers; lane 0 issues
+  uint32_t par_tile = 0, par_empty = 0;   // phases to test next: lane's bar_tile; bar_empty of its previous round
+  bool have_round = false;                // a round of this lane's warp has been handed to the epilogue
   while (next_segment<Q>(G, P.n_hyp, g0, g_end, sg)) {
-    if (lane == 0) {
+    {
       const int n_seg = (int)(sg.lt1 - sg.lt0);
-      for (int t = 0; t * kProd < n_seg; ++t) {
-        const uint32_t in_round = (uint32_t)(t % G.flush);
-#pragma unroll
-        for (int w = 0; w < kProd; ++w) {
-          if (t * kProd + w < n_seg) {
-            tc::mbar_wait(&mi.bar_tile[w], n_tiles[w] & 1);
-            ++n_tiles[w];
-            if (in_round == 0 && n_rounds[w] > 0) tc::mbar_wait(&mi.bar_empty[w], (n_rounds[w] - 1) & 1);
-            tc::fence_after_sync();
+      const int my_tiles = (lane < kProd && n_seg > lane) ? (n_seg - lane + kProd - 1) / kProd : 0;
+      int t = 0, in_round = 0;
+      for (;;) {
+        const bool pending = t < my_tiles;
+        bool ready = false;
+        if (pending) {
+          ready = tc::mbar_test_wait(&mi.bar_tile[lane], par_tile);
+          if (ready && in_round == 0 && have_round) ready = tc::mbar_test_wait(&mi.bar_empty[lane], par_empty);
+        }
+        const unsigned rdy = __ballot_sync(0xffffffffu, ready);
+        if (rdy == 0u) {
+          if (__ballot_sync(0xffffffffu, pending) == 0u) break;
+          continue;
+        }
+        const bool last = (in_round + 1 == G.flush) || (t + 1 >= my_tiles);
+        const unsigned first_m = __ballot_sync(0xffffffffu, ready && in_round == 0);
+        const unsigned last_m = __ballot_sync(0xffffffffu, ready && last);
+        tc::fence_after_sync();
+        if (lane == 0) {
+          unsigned m = rdy;
+          while (m) {
+            const int w = __ffs(m) - 1;
+            m &= m - 1;
             const uint64_t da = tc::smem_desc_sw128(a0 + w * C::kStageBytes);
             const uint64_t db = tc::smem_desc_sw128(a0 + w * C::kStageBytes + C::kABytes);
             const uint32_t d_tmem = tmem + w * kAccStride;
+            const uint32_t acc0 = ((first_m >> w) & 1u) ^ 1u;
+            tc::mma_tf32_ss(d_tmem, da, db, idesc, acc0);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_ss(d_tmem, da + 2 * ks, db + 2 * ks, idesc, (in_round | ks) > 0);
+            for (int ks = 1; ks < 4; ++ks) tc::mma_tf32_ss(d_tmem, da + 2 * ks, db + 2 * ks, idesc, 1u);
             tc::mma_commit(&mi.bar_stage[w]);
-            const bool last = (in_round + 1 == (uint32_t)G.flush) || ((t + 1) * kProd + w >= n_seg);
-            if (last) { tc::mma_commit(&mi.bar_full[w]); ++n_rounds[w]; }
+            if ((last_m >> w) & 1u) tc::mma_commit(&mi.bar_full[w]);
           }
         }
+        if (ready) {
+          ++t;
+          par_tile ^= 1u;
+          if (last) { in_round = 0; if (have_round) par_empty ^= 1u; have_round = true; } else ++in_round;
+        }
+        __syncwarp();
       }
     }
     __syncwarp();
