@@ -36,7 +36,13 @@ constexpr int kBRows = 40;          // B tile rows kept in shared memory (38 use
 constexpr double kLog2e = 1.4426950408889634;
 constexpr double kLn2 = 0.6931471805599453;
 
-template <int Q>
+// operand scaling of the 16-bit variant (all powers of two, undone exactly on the float64 partials):
+//   e' = e * 2^kShiftE (folded into the logit offset), every "lo" term is the residual * 2^kShiftLo, and the three feature
+//   classes (1, d, d d^T), p, p p^T carry 2^kShiftD, 2^kShiftP, 2^kShiftPP.  With these, fp16 operands stay finite for
+//   w / Z < 2000 and |p| < 500 m; outside that range the moments come out as inf / NaN (never silently wrong).
+constexpr int kShiftE = 14, kShiftLo = 11, kShiftD = 5, kShiftP = -2, kShiftPP = -12;
+
+template <int Q, bool H>
 struct TcCfg {
   // producer warps: as many 17 KB / 21 KB operand tiles as fit in shared memory, in whole warpgroups
   static constexpr int kProd = Q <= 3 ? 12 : 8;
@@ -49,16 +55,19 @@ struct TcCfg {
   static constexpr int kEpi = Q;
   static constexpr int kIssuerWarp = Q <= 3 ? kProd + 3 : kProd + 4;
   static constexpr int kThreads = Q <= 3 ? 32 * (kProd + 4) : 32 * (kProd + 8);
-  static constexpr int kABytes = kRows * tc::kRowBytes;
-  static constexpr int kBBytes = kBRows * tc::kRowBytes;
-  static constexpr int kStageBytes = kABytes + kBBytes;            // 17 KB (Q=3) / 21 KB (Q=4): multiples of 1 KB
-  static constexpr int kStagesBytes = kProd * kStageBytes + 1024;  // + tail read by the last B tile's padding rows
+  static constexpr int kRowB = H ? tc::kRowBytes16 : tc::kRowBytes;   // bytes of one operand row (32 points)
+  static constexpr int kNBuf = H ? 2 : 1;                             // operand tiles per producer warp
+  static constexpr int kMmaPerTile = H ? 2 : 4;                       // K = 16 (f16) / 8 (tf32) points per MMA
+  static constexpr int kABytes = kRows * kRowB;
+  static constexpr int kBBytes = kBRows * kRowB;
+  static constexpr int kStageBytes = kABytes + kBBytes;   // tf32: 17 / 21 KB (multiples of 1 KB); f16: 8.5 / 10.5 KB (of 512 B)
+  static constexpr int kStagesBytes = kProd * kNBuf * kStageBytes + 1024;   // + tail read by the last B tile's padding rows
 };
 
 struct TcMisc {
   float4 bins2[kMaxBins * 2];  // per bin: (bx, bx, by, by), (bz, bz, -c2, -c2), pre-scaled by log2(e)/tau
-  uint64_t bar_tile[kMaxProd];    // the producer warp has written (and fenced) its operand tile
-  uint64_t bar_stage[kMaxProd];   // MMAs that read the warp's operand tile have completed
+  uint64_t bar_tile[kMaxProd][2];    // the producer warp has written (and fenced) its operand tile (buffer 0 / 1)
+  uint64_t bar_stage[kMaxProd][2];   // MMAs that read the warp's operand tile (buffer 0 / 1) have completed
   uint64_t bar_full[kMaxProd];    // the warp's accumulator holds a finished round
   uint64_t bar_empty[kMaxProd];   // the epilogue has drained it
   uint32_t tmem;
@@ -84,7 +93,6 @@ struct TcSeg { int u, s, h; int64_t unit_t0, lt0, lt1; };
 
 __device__ __forceinline__ void bar_all(int n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
 
-template <int Q>
 __device__ __forceinline__ bool next_segment(const TcGeom& G, int n_hyp, int64_t& g0, int64_t g_end, TcSeg& sg) {
   if (g0 >= g_end) return false;
   sg.u = (int)(g0 / G.tiles_per_unit);
@@ -97,17 +105,22 @@ __device__ __forceinline__ bool next_segment(const TcGeom& G, int n_hyp, int64_t
 }
 
 // Segment combine, executed by all threads of the CTA after the epilogue has written its row sums to `red`.
-template <int Q>
+template <int Q, bool H>
 __device__ __forceinline__ void write_partial(const BinScanParams& P, const TcGeom& G, const TcSeg& sg, const TcMisc& mi,
                                               const double* red, int cta, int tid) {
-  using C = TcCfg<Q>;
+  using C = TcCfg<Q, H>;
   constexpr int kProd = C::kProd;
   const int nb = P.n_bins;
   const int slot = cta - cta_of_tile(G, sg.unit_t0);
   double* part = P.partial + ((int64_t)sg.u * G.n_parts + slot) * P.part_len;
   for (int idx = tid; idx < nb * kNF; idx += C::kThreads) {
     const int b = idx / kNF, f = idx - b * kNF;
-    part[b * kRowLen + f] = red[b * kNF + f] + red[(C::kBinsPad + b) * kNF + f];
+    if (H) {
+      const double sc_f = ldexp(1.0, -kShiftE - (f < 10 ? kShiftD : (f < 13 ? kShiftP : kShiftPP)));
+      part[b * kRowLen + f] = fma(red[(C::kBinsPad + b) * kNF + f], ldexp(1.0, -kShiftLo), red[b * kNF + f]) * sc_f;
+    } else {
+      part[b * kRowLen + f] = red[b * kNF + f] + red[(C::kBinsPad + b) * kNF + f];
+    }
   }
   if (tid < kNExtras + kNMax) {
     double* ex = part + nb * kRowLen;
@@ -128,10 +141,10 @@ __device__ __forceinline__ void write_partial(const BinScanParams& P, const TcGe
 
 // Barrier schedule of a segment (all kThreads threads, named barrier 1):
 //   [producers: tiles + MMAs | epilogue: drains]  B1  [epilogue: row sums -> red]  B2  [all: partial]  B3  [all: re-zero red]  B4
-template <int Q>
+template <int Q, bool H>
 __device__ __forceinline__ void segment_tail(const BinScanParams& P, const TcGeom& G, const TcSeg& sg, TcMisc& mi,
                                              unsigned char* stages, int cta, int tid, const double* acc_or_null) {
-  using C = TcCfg<Q>;
+  using C = TcCfg<Q, H>;
   constexpr int kProd = C::kProd;
   double* red = reinterpret_cast<double*>(stages);   // operand tiles are idle: every MMA of the segment has completed
   bar_all(C::kThreads);
@@ -141,7 +154,7 @@ __device__ __forceinline__ void segment_tail(const BinScanParams& P, const TcGeo
     for (int f = 0; f < kNF; ++f) red[R * kNF + f] = acc_or_null[f];
   }
   bar_all(C::kThreads);
-  write_partial<Q>(P, G, sg, mi, red, cta, tid);
+  write_partial<Q, H>(P, G, sg, mi, red, cta, tid);
   bar_all(C::kThreads);
   // padding rows of the operand tiles alias this scratch: keep it free of NaN bit patterns
   for (int k = tid; k < (128 * kNF * 8 + 15) / 16; k += C::kThreads) reinterpret_cast<uint4*>(stages)[k] = make_uint4(0, 0, 0, 0);
@@ -149,10 +162,10 @@ __device__ __forceinline__ void segment_tail(const BinScanParams& P, const TcGeo
   bar_all(C::kThreads);
 }
 
-template <int Q>
+template <int Q, bool H>
 __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGeom& G, TcMisc& mi, unsigned char* stages,
                                               uint32_t tmem, int cta, int tid) {
-  using C = TcCfg<Q>;
+  using C = TcCfg<Q, H>;
   constexpr int kProd = C::kProd;
   const int wid = tid >> 5, lane = tid & 31;
   uint32_t n_stage_uses = 0;   // uses of the operand tile
@@ -164,15 +177,20 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
   uint32_t off2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) off2[j] = (uint32_t)(((((lane & 15) >> 1) ^ j) << 4) | ((lane & 1) << 3));
+  // 16-bit rows (64 B, SWIZZLE_64B: chunk ^= (row >> 1) & 3): element = point (2 B) / point pair (4 B)
+  uint32_t offh[4], off2h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    offh[j] = (uint32_t)((((lane >> 3) ^ j) << 4) | ((lane & 7) << 1));
+    off2h[j] = (uint32_t)(((((lane & 15) >> 2) ^ j) << 4) | ((lane & 3) << 2));
+  }
   int64_t g0 = cta_tile0(G, cta);
   const int64_t g_end = cta_tile0(G, cta + 1);
   TcSeg sg;
-  while (next_segment<Q>(G, P.n_hyp, g0, g_end, sg)) {
+  while (next_segment(G, P.n_hyp, g0, g_end, sg)) {
     const int u = sg.u, s = sg.s, h = sg.h;
     const int64_t lt0 = sg.lt0, lt1 = sg.lt1;
-    unsigned char* sA = stages + wid * C::kStageBytes;
-    unsigned char* sB = sA + C::kABytes;
-    const uint32_t aA = tc::smem_u32(sA), aB = tc::smem_u32(sB);
+    unsigned char* const sA0 = stages + wid * C::kNBuf * C::kStageBytes;
     const double t0 = P.t0s[s], t1 = P.t1s[s];
     const double inv_denom = 1.0 / fmax(t1 - t0, 1e-12);
     __syncwarp();
@@ -189,7 +207,6 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
     // the two points 2j, 2j+1 of the tile (packed f32x2 math, 8-byte operand stores)
     constexpr int NB2 = C::kBinsPad / 2;
     const int half = lane >> 4, pj = lane & 15;
-    unsigned char* sA_lane = sA + half * NB2 * tc::kRowBytes;
     const float4* bins_lane = mi.bins2 + half * 2;   // entry i of this half at bins_lane[4 * i], [4 * i + 1]
 
     // software pipeline: the raw rows of the warp's next tile are requested before this tile is processed
@@ -240,8 +257,15 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
       const float2 g0 = make_float2(__shfl_sync(0xffffffffu, f0, 2 * pj), __shfl_sync(0xffffffffu, f0, 2 * pj + 1));
       const float2 g1 = make_float2(__shfl_sync(0xffffffffu, f1, 2 * pj), __shfl_sync(0xffffffffu, f1, 2 * pj + 1));
       const float2 g2 = make_float2(__shfl_sync(0xffffffffu, f2, 2 * pj), __shfl_sync(0xffffffffu, f2, 2 * pj + 1));
-      // the tensor core may still be reading this warp's previous tile
-      if (n_stage_uses > 0) tc::mbar_wait(&mi.bar_stage[wid], (n_stage_uses - 1) & 1);
+      // the tensor core may still be reading the operand tile this one goes into
+      const uint32_t buf = H ? (n_stage_uses & 1u) : 0u;
+      unsigned char* const sA = sA0 + buf * C::kStageBytes;
+      unsigned char* const sB = sA + C::kABytes;
+      // tf32: the lane's bins are [half * NB2, half * NB2 + NB2); f16: bins 2 i + half (rows of the two halves then fall
+      // into different banks: a 64-byte row covers half of them)
+      unsigned char* const sA_lane = sA + (H ? half * tc::kRowBytes16 : half * NB2 * tc::kRowBytes);
+      if (n_stage_uses >= (uint32_t)C::kNBuf)
+        tc::mbar_wait(&mi.bar_stage[wid][buf], ((n_stage_uses / C::kNBuf) - 1) & 1);
       float2 sum = make_float2(0.f, 0.f), dot = sum;
       float mx0 = 0.f, mx1 = 0.f;
       // groups of kGrp bins: table loads of the next group are issued before the operand stores of this one (the
@@ -275,14 +299,35 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
           sum = tc::add2(sum, e[k]);
           dot = tc::fma2(e[k], l[k], dot);
           mx0 = fmaxf(mx0, e[k].x); mx1 = fmaxf(mx1, e[k].y);
-          hi[k] = make_float2(tc::tf32_hi(e[k].x), tc::tf32_hi(e[k].y));
-          lo[k] = tc::sub2(e[k], hi[k]);
+          if (!H) {
+            hi[k] = make_float2(tc::tf32_hi(e[k].x), tc::tf32_hi(e[k].y));
+            lo[k] = tc::sub2(e[k], hi[k]);
+          }
         }
+        if (!H) {
 #pragma unroll
-        for (int k = 0; k < kGrp; ++k) {
-          const int b = g * kGrp + k;
-          *reinterpret_cast<float2*>(sA_lane + b * tc::kRowBytes + off2[b & 7]) = hi[k];
-          *reinterpret_cast<float2*>(sA_lane + (C::kBinsPad + b) * tc::kRowBytes + off2[b & 7]) = lo[k];
+          for (int k = 0; k < kGrp; ++k) {
+            const int b = g * kGrp + k;
+            *reinterpret_cast<float2*>(sA_lane + b * tc::kRowBytes + off2[b & 7]) = hi[k];
+            *reinterpret_cast<float2*>(sA_lane + (C::kBinsPad + b) * tc::kRowBytes + off2[b & 7]) = lo[k];
+          }
+        } else {
+          // e' = hi + lo / 2^kShiftLo, both fp16: one packed conversion per point pair, residual exact in float32
+          uint32_t h2[kGrp], l2[kGrp];
+#pragma unroll
+          for (int k = 0; k < kGrp; ++k) {
+            h2[k] = tc::pack_f16x2(e[k].x, e[k].y);
+            const float2 r = tc::sub2(e[k], tc::unpack_f16x2(h2[k]));
+            const float2 rs = tc::mul2(r, make_float2((float)(1 << kShiftLo), (float)(1 << kShiftLo)));
+            l2[k] = tc::pack_f16x2(rs.x, rs.y);
+          }
+#pragma unroll
+          for (int k = 0; k < kGrp; ++k) {
+            const int i = g * kGrp + k;   // row 2 i + half; lo rows kBinsPad further down (same swizzle phase)
+            const int ro = (i >> 2) * tc::kGroupBytes16 + ((2 * i) & 7) * tc::kRowBytes16;
+            *reinterpret_cast<uint32_t*>(sA_lane + ro + off2h[i & 3]) = h2[k];
+            *reinterpret_cast<uint32_t*>(sA_lane + C::kBinsPad * tc::kRowBytes16 + ro + off2h[i & 3]) = l2[k];
+          }
         }
       }
       // both bin halves -> every lane holds the full row sums of its two points; then back to lane = point
@@ -312,23 +357,39 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
         mx_resp = fmax(mx_resp, (double)emax * inv);
       }
       {
-        const float sc = row ? (float)(w_dk * inv) : 0.f;
+        const float sc0 = row ? (float)(w_dk * inv) : 0.f;
+        // 16-bit operands: inv is 1 / (2^kShiftE Z); the feature classes carry their own power-of-two scales
+        const float sc = H ? sc0 * (float)(1 << (kShiftE + kShiftD)) : sc0;
+        const float scp = H ? sc0 * (float)(1 << (kShiftE + kShiftP)) : sc0;
+        const float scpp = H ? sc0 * (float)(1 << (kShiftE + kShiftPP)) : sc0;
         const float q0 = (float)p0[0], q1 = (float)p0[1], q2 = (float)p0[2];
         const float sd0 = sc * f0, sd1 = sc * f1, sd2 = sc * f2;
-        const float sp0 = sc * q0, sp1 = sc * q1, sp2 = sc * q2;
+        const float sp0 = scp * q0, sp1 = scp * q1, sp2 = scp * q2;
+        const float sq0 = scpp * q0, sq1 = scpp * q1, sq2 = scpp * q2;
         const float v[kNF] = {sc, sd0, sd1, sd2, sd0 * f0, sd0 * f1, sd0 * f2, sd1 * f1, sd1 * f2, sd2 * f2,
-                              sp0, sp1, sp2, sp0 * q0, sp0 * q1, sp0 * q2, sp1 * q1, sp1 * q2, sp2 * q2};
+                              sp0, sp1, sp2, sq0 * q0, sq0 * q1, sq0 * q2, sq1 * q1, sq1 * q2, sq2 * q2};
+        if (!H) {
 #pragma unroll
-        for (int f = 0; f < kNF; ++f) {
-          float hi, lo;
-          tc::split_tf32(v[f], hi, lo);
-          *reinterpret_cast<float*>(sB + f * tc::kRowBytes + off[f & 7]) = hi;
-          *reinterpret_cast<float*>(sB + (kNF + f) * tc::kRowBytes + off[(kNF + f) & 7]) = lo;
+          for (int f = 0; f < kNF; ++f) {
+            float hi, lo;
+            tc::split_tf32(v[f], hi, lo);
+            *reinterpret_cast<float*>(sB + f * tc::kRowBytes + off[f & 7]) = hi;
+            *reinterpret_cast<float*>(sB + (kNF + f) * tc::kRowBytes + off[(kNF + f) & 7]) = lo;
+          }
+        } else {
+#pragma unroll
+          for (int f = 0; f < kNF; ++f) {
+            const __half hi = __float2half_rn(v[f]);
+            const __half lo = __float2half_rn((v[f] - __half2float(hi)) * (float)(1 << kShiftLo));
+            constexpr int r1 = kNF;
+            *reinterpret_cast<__half*>(sB + tc::row_base16(f) + offh[(f >> 1) & 3]) = hi;
+            *reinterpret_cast<__half*>(sB + tc::row_base16(r1 + f) + offh[((r1 + f) >> 1) & 3]) = lo;
+          }
         }
       }
       tc::fence_smem_to_async();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&mi.bar_tile[wid]);   // the issuer warp takes it from here
+      if (lane == 0) tc::mbar_arrive(&mi.bar_tile[wid][buf]);   // the issuer warp takes it from here
       ++n_stage_uses;
     }
     // per-warp sums of the scalar certificates (fixed shuffle tree)
@@ -339,14 +400,14 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
     v = warp_sum(sum_wrs); if (lane == 0) mi.ex[wid][kExSumWrs] = v;
     v = warp_sum(n_rows);  if (lane == 0) mi.ex[wid][kExCount] = v;
     v = warp_max(mx_resp); if (lane == 0) mi.ex[wid][5] = v;
-    segment_tail<Q>(P, G, sg, mi, stages, cta, tid, nullptr);
+    segment_tail<Q, H>(P, G, sg, mi, stages, cta, tid, nullptr);
   }
 }
 
-template <int Q>
+template <int Q, bool H>
 __device__ __forceinline__ void epilogue_role(const BinScanParams& P, const TcGeom& G, TcMisc& mi, unsigned char* stages,
                                               uint32_t tmem, int cta, int tid) {
-  constexpr int kProd = TcCfg<Q>::kProd;
+  constexpr int kProd = TcCfg<Q, H>::kProd;
   const int wid = tid >> 5, lane = tid & 31;
   uint32_t n_drained[kProd];   // rounds drained per producer warp
 #pragma unroll
@@ -354,7 +415,7 @@ __device__ __forceinline__ void epilogue_role(const BinScanParams& P, const TcGe
   int64_t g0 = cta_tile0(G, cta);
   const int64_t g_end = cta_tile0(G, cta + 1);
   TcSeg sg;
-  while (next_segment<Q>(G, P.n_hyp, g0, g_end, sg)) {
+  while (next_segment(G, P.n_hyp, g0, g_end, sg)) {
     const int64_t lt0 = sg.lt0, lt1 = sg.lt1;
     double acc[kNF];   // per TMEM lane (= operand row): hi-feature column + lo-feature column
 #pragma unroll
@@ -396,12 +457,13 @@ __device__ __forceinline__ void epilogue_role(const BinScanParams& P, const TcGe
           for (int c = 0; c < 4; ++c) v[32 + c] = __uint_as_float(a2[c]);
           v[36] = __uint_as_float(a3[0]); v[37] = __uint_as_float(a3[1]);
 #pragma unroll
-          for (int f = 0; f < kNF; ++f) acc[f] += (double)(v[f] + v[kNF + f]);
+          for (int f = 0; f < kNF; ++f)
+            acc[f] += (double)(H ? fmaf(v[kNF + f], 1.0f / (float)(1 << kShiftLo), v[f]) : v[f] + v[kNF + f]);
         }
       }
       if (!any) break;
     }
-    segment_tail<Q>(P, G, sg, mi, stages, cta, tid, acc);
+    segment_tail<Q, H>(P, G, sg, mi, stages, cta, tid, acc);
   }
 }
 
@@ -410,21 +472,22 @@ __device__ __forceinline__ void epilogue_role(const BinScanParams& P, const TcGe
 // lane 0 issues whichever tiles are ready -- no fixed order across warps, so a late warp does not hold up the MMAs (and
 // hence the operand-tile release) of the others.  Each accumulator still sees only its own warp's tiles, in sequence,
 // and the epilogue drains in a fixed order: results do not depend on the issue order.
-template <int Q>
+template <int Q, bool H>
 __device__ __forceinline__ void issuer_role(const BinScanParams& P, const TcGeom& G, TcMisc& mi, unsigned char* stages,
                                             uint32_t tmem, int cta, int tid) {
-  using C = TcCfg<Q>;
+  using C = TcCfg<Q, H>;
   constexpr int kProd = C::kProd;
   const int lane = tid & 31;
   int64_t g0 = cta_tile0(G, cta);
   const int64_t g_end = cta_tile0(G, cta + 1);
-  const uint32_t idesc = tc::idesc_tf32(128, kMmaN);
+  const uint32_t idesc = H ? tc::idesc_f16(128, kMmaN) : tc::idesc_tf32(128, kMmaN);
   const uint32_t a0 = tc::smem_u32(stages);
   TcSeg sg;
   // lane w (< kProd) keeps the tile / round counters of producer warp w and polls its barriers; lane 0 issues
-  uint32_t par_tile = 0, par_empty = 0;   // phases to test next: lane's bar_tile; bar_empty of its previous round
+  uint32_t n_done = 0;      // tiles of this lane's warp issued so far: operand buffer n_done % kNBuf, phase n_done / kNBuf
+  uint32_t par_empty = 0;   // phase of bar_empty to test next (the warp's previous round)
   bool have_round = false;                // a round of this lane's warp has been handed to the epilogue
-  while (next_segment<Q>(G, P.n_hyp, g0, g_end, sg)) {
+  while (next_segment(G, P.n_hyp, g0, g_end, sg)) {
     {
       const int n_seg = (int)(sg.lt1 - sg.lt0);
       const int my_tiles = (lane < kProd && n_seg > lane) ? (n_seg - lane + kProd - 1) / kProd : 0;
@@ -433,7 +496,7 @@ __device__ __forceinline__ void issuer_role(const BinScanParams& P, const TcGeom
         const bool pending = t < my_tiles;
         bool ready = false;
         if (pending) {
-          ready = tc::mbar_test_wait(&mi.bar_tile[lane], par_tile);
+          ready = tc::mbar_test_wait(&mi.bar_tile[lane][n_done % C::kNBuf], (n_done / C::kNBuf) & 1u);
           if (ready && in_round == 0 && have_round) ready = tc::mbar_test_wait(&mi.bar_empty[lane], par_empty);
         }
         const unsigned rdy = __ballot_sync(0xffffffffu, ready);
@@ -444,49 +507,55 @@ __device__ __forceinline__ void issuer_role(const BinScanParams& P, const TcGeom
         const bool last = (in_round + 1 == G.flush) || (t + 1 >= my_tiles);
         const unsigned first_m = __ballot_sync(0xffffffffu, ready && in_round == 0);
         const unsigned last_m = __ballot_sync(0xffffffffu, ready && last);
+        const unsigned buf_m = H ? __ballot_sync(0xffffffffu, ready && (n_done & 1u)) : 0u;   // operand buffer of the tile
         tc::fence_after_sync();
         if (lane == 0) {
           unsigned m = rdy;
           while (m) {
             const int w = __ffs(m) - 1;
             m &= m - 1;
-            const uint64_t da = tc::smem_desc_sw128(a0 + w * C::kStageBytes);
-            const uint64_t db = tc::smem_desc_sw128(a0 + w * C::kStageBytes + C::kABytes);
+            const uint32_t buf = (buf_m >> w) & 1u;
+            const uint32_t sa = a0 + (w * C::kNBuf + buf) * C::kStageBytes;
+            const uint64_t da = H ? tc::smem_desc_sw64(sa) : tc::smem_desc_sw128(sa);
+            const uint64_t db = H ? tc::smem_desc_sw64(sa + C::kABytes) : tc::smem_desc_sw128(sa + C::kABytes);
             const uint32_t d_tmem = tmem + w * kAccStride;
             const uint32_t acc0 = ((first_m >> w) & 1u) ^ 1u;
-            tc::mma_tf32_ss(d_tmem, da, db, idesc, acc0);
+            // one MMA consumes 32 bytes of every operand row (8 tf32 / 16 fp16 points): descriptor start + 2 (x 16 B)
 #pragma unroll
-            for (int ks = 1; ks < 4; ++ks) tc::mma_tf32_ss(d_tmem, da + 2 * ks, db + 2 * ks, idesc, 1u);
-            tc::mma_commit(&mi.bar_stage[w]);
+            for (int ks = 0; ks < C::kMmaPerTile; ++ks) {
+              if (H) tc::mma_f16_ss(d_tmem, da + 2 * ks, db + 2 * ks, idesc, ks ? 1u : acc0);
+              else tc::mma_tf32_ss(d_tmem, da + 2 * ks, db + 2 * ks, idesc, ks ? 1u : acc0);
+            }
+            tc::mma_commit(&mi.bar_stage[w][buf]);
             if ((last_m >> w) & 1u) tc::mma_commit(&mi.bar_full[w]);
           }
         }
         if (ready) {
           ++t;
-          par_tile ^= 1u;
+          ++n_done;
           if (last) { in_round = 0; if (have_round) par_empty ^= 1u; have_round = true; } else ++in_round;
         }
         __syncwarp();
       }
     }
     __syncwarp();
-    segment_tail<Q>(P, G, sg, mi, stages, cta, tid, nullptr);
+    segment_tail<Q, H>(P, G, sg, mi, stages, cta, tid, nullptr);
   }
 }
 
 // warps of the CTA that have no role in a configuration still take part in the segment barriers
-template <int Q>
+template <int Q, bool H>
 __device__ __forceinline__ void idle_role(const BinScanParams& P, const TcGeom& G, TcMisc& mi, unsigned char* stages, int cta,
                                           int tid) {
   int64_t g0 = cta_tile0(G, cta);
   const int64_t g_end = cta_tile0(G, cta + 1);
   TcSeg sg;
-  while (next_segment<Q>(G, P.n_hyp, g0, g_end, sg)) segment_tail<Q>(P, G, sg, mi, stages, cta, tid, nullptr);
+  while (next_segment(G, P.n_hyp, g0, g_end, sg)) segment_tail<Q, H>(P, G, sg, mi, stages, cta, tid, nullptr);
 }
 
-template <int Q>
-__global__ void __launch_bounds__(TcCfg<Q>::kThreads, 1) bin_scan_tc_kernel(const BinScanParams P, const TcGeom G) {
-  using C = TcCfg<Q>;
+template <int Q, bool H>
+__global__ void __launch_bounds__(TcCfg<Q, H>::kThreads, 1) bin_scan_tc_kernel(const BinScanParams P, const TcGeom G) {
+  using C = TcCfg<Q, H>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1 KB alignment by pointer arithmetic on the __shared__ symbol (keeps the shared address space: STS/LDS, not generic)
   unsigned char* stages = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -504,19 +573,21 @@ __global__ void __launch_bounds__(TcCfg<Q>::kThreads, 1) bin_scan_tc_kernel(cons
       float x = 0.f, y = 0.f, z = 0.f, w = -1.0e30f;   // bins past n_bins: e = 2^(-1e30) = 0
       if (b < nb) {
         x = (float)(P.bin_dirs[3 * b] * sc); y = (float)(P.bin_dirs[3 * b + 1] * sc); z = (float)(P.bin_dirs[3 * b + 2] * sc);
-        w = -c2;
+        w = H ? (float)kShiftE - c2 : -c2;   // 16-bit operands: e' = 2^kShiftE e
       }
       // interleave the two bin halves (lanes 0-15 / 16-31 read entry i of their half in the same instruction): the two
       // 16-byte reads of a warp then fall into different banks
-      const int e = (b % (C::kBinsPad / 2)) * 2 + b / (C::kBinsPad / 2);
+      const int e = H ? b : (b % (C::kBinsPad / 2)) * 2 + b / (C::kBinsPad / 2);
       mi.bins2[2 * e] = make_float4(x, x, y, y);
       mi.bins2[2 * e + 1] = make_float4(z, z, w, w);
     }
   }
   if (tid == 0) {
     for (int w = 0; w < kProd; ++w) {
-      tc::mbar_init(&mi.bar_tile[w], 1);
-      tc::mbar_init(&mi.bar_stage[w], 1);
+      tc::mbar_init(&mi.bar_tile[w][0], 1);
+      tc::mbar_init(&mi.bar_tile[w][1], 1);
+      tc::mbar_init(&mi.bar_stage[w][0], 1);
+      tc::mbar_init(&mi.bar_stage[w][1], 1);
       tc::mbar_init(&mi.bar_full[w], 1);
       tc::mbar_init(&mi.bar_empty[w], C::kEpi);
     }
@@ -532,15 +603,15 @@ __global__ void __launch_bounds__(TcCfg<Q>::kThreads, 1) bin_scan_tc_kernel(cons
   // ---- roles.  Register re-allocation: the producer warpgroups take what the other warpgroups give up.
   if (wid < kProd) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::kRegProd));
-    producer_role<Q>(P, G, mi, stages, tmem, blockIdx.x, tid);
+    producer_role<Q, H>(P, G, mi, stages, tmem, blockIdx.x, tid);
   } else if (wid < kProd + 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::kRegEpi));
-    if (wid < kProd + C::kEpi) epilogue_role<Q>(P, G, mi, stages, tmem, blockIdx.x, tid);
-    else issuer_role<Q>(P, G, mi, stages, tmem, blockIdx.x, tid);
+    if (wid < kProd + C::kEpi) epilogue_role<Q, H>(P, G, mi, stages, tmem, blockIdx.x, tid);
+    else issuer_role<Q, H>(P, G, mi, stages, tmem, blockIdx.x, tid);
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (wid == C::kIssuerWarp) issuer_role<Q>(P, G, mi, stages, tmem, blockIdx.x, tid);
-    else idle_role<Q>(P, G, mi, stages, blockIdx.x, tid);
+    if (wid == C::kIssuerWarp) issuer_role<Q, H>(P, G, mi, stages, tmem, blockIdx.x, tid);
+    else idle_role<Q, H>(P, G, mi, stages, blockIdx.x, tid);
   }
 
   tc::fence_before_sync();
@@ -573,17 +644,27 @@ TcGeom make_geom(int sm_count, int n_units, int64_t cap, int n_parts, int n_prod
   return G;
 }
 
-template <int Q>
+// GCS_TC_OPERANDS=tf32 selects the 32-bit operand variant (same results to ~1e-6; kept for comparison)
+bool tc_use_f16() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GCS_TC_OPERANDS");
+    v = (e && e[0] == 't') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int Q, bool H>
 cudaError_t launch_q(cudaStream_t st, const BinScanParams& P, const TcGeom& G) {
-  using C = TcCfg<Q>;
+  using C = TcCfg<Q, H>;
   static bool attr_set = false;
   const int smem = C::kStagesBytes + (int)sizeof(TcMisc) + 1024;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(bin_scan_tc_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(bin_scan_tc_kernel<Q, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  bin_scan_tc_kernel<Q><<<G.n_cta, C::kThreads, smem, st>>>(P, G);
+  bin_scan_tc_kernel<Q, H><<<G.n_cta, C::kThreads, smem, st>>>(P, G);
   return cudaSuccess;
 }
 
@@ -601,8 +682,12 @@ bool bin_scan_tc_supported(const BinScanParams& P) {
 
 cudaError_t launch_bin_scan_tc(int sm_count, cudaStream_t st, const BinScanParams& P, int n_parts) {
   const int U = P.n_scans * P.n_hyp;
-  if (P.n_bins <= 48) return launch_q<3>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<3>::kProd));
-  return launch_q<4>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<4>::kProd));
+  if (tc_use_f16()) {
+    if (P.n_bins <= 48) return launch_q<3, true>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<3, true>::kProd));
+    return launch_q<4, true>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<4, true>::kProd));
+  }
+  if (P.n_bins <= 48) return launch_q<3, false>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<3, false>::kProd));
+  return launch_q<4, false>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<4, false>::kProd));
 }
 
 }  // namespace gcs

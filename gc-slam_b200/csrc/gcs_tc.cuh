@@ -8,6 +8,7 @@
 // into a fixed row touches every bank exactly once.  One tcgen05.mma consumes K = 8 points (32 B of every row); a
 // 32-point tile is four MMAs whose descriptors advance the start address by 32 B.
 #pragma once
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace gcs {
@@ -33,6 +34,38 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t
   d |= (uint64_t)1 << 46;                                  // descriptor version (sm_100)
   d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
   return d;
+}
+
+// ---- 16-bit operands (kind::f16): K-major rows of 32 points = 64 bytes, SWIZZLE_64B: groups of 8 rows 512 B apart, the
+// four 16-byte chunks of a row XOR-permuted by bits 1-2 of the row index.  One tcgen05.mma consumes K = 16 points (32 B).
+constexpr int kRowBytes16 = 64;
+constexpr int kGroupBytes16 = 512;
+__device__ __forceinline__ uint32_t swz64_offset(int r, int byte_in_row) {
+  return (uint32_t)((r >> 3) * kGroupBytes16 + (r & 7) * kRowBytes16 + ((((byte_in_row >> 4) ^ (r >> 1)) & 3) << 4) +
+                    (byte_in_row & 15));
+}
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t smem_addr, uint32_t sbo_bytes = kGroupBytes16) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                                  // SWIZZLE_64B
+  return d;
+}
+// instruction descriptor, kind::f16: D f32, A/B f16 (format 0), both K-major, dense
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 // instruction descriptor, kind::tf32: D f32, A/B tf32, both K-major, dense
@@ -164,6 +197,25 @@ __device__ __forceinline__ float2 sub2(float2 a, float2 b) {
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
 }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+// two float32 -> packed fp16 pair (lo in bits 0-15, hi in bits 16-31), round to nearest; and back (exact)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+// byte offset of row r of a 16-bit operand tile (before the in-row swizzled offset)
+__host__ __device__ constexpr int row_base16(int r) { return (r >> 3) * kGroupBytes16 + (r & 7) * kRowBytes16; }
 __device__ __forceinline__ float ex2f(float x) {
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
