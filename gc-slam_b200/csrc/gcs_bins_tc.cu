@@ -16,6 +16,12 @@
 //   epilogue warps (Q per CTA, one per 32 TMEM lanes) drain every accumulator after `flush` tiles (tcgen05.ld) into
 //            float64 registers: the float32 accumulator (which truncates) never sums more than flush x 4 MMA steps.
 //
+// Operand formats.  The default keeps every operand as two fp16 terms (kind::f16, K = 16 per MMA, 64-byte rows,
+// SWIZZLE_64B): x = hi + lo / 2^11 with power-of-two pre-scales per operand class (kShift*), undone exactly on the
+// float64 partials.  Half the operand bytes of the tf32 form, so every producer warp owns TWO operand tiles and starts
+// its next tile while the tensor core still reads the previous one.  The tf32 form (kind::tf32, K = 8, 128-byte rows,
+// SWIZZLE_128B, one tile per warp) is kept for sharp kernels (tau < 0.05) where fp16's exponent range is too small.
+//
 // A CTA is persistent over a contiguous range of 32-point tiles of the flattened (unit, tile) space -- every SM gets
 // the same amount of work whatever the batch shape -- and writes one partial per unit segment it touched, in the
 // layout of bin_scan_kernel, so reduce_partials_kernel and the finalize kernel are shared with the other precisions.
@@ -644,14 +650,17 @@ TcGeom make_geom(int sm_count, int n_units, int64_t cap, int n_parts, int n_prod
   return G;
 }
 
-// GCS_TC_OPERANDS=tf32 selects the 32-bit operand variant (same results to ~1e-6; kept for comparison)
-bool tc_use_f16() {
-  static int v = -1;
-  if (v < 0) {
+// Operand format.  fp16 hi/lo operands need bounded magnitudes (see kShift*): w / Z stays small as long as every ray is
+// within a few tau (in cosine) of some bin, which holds for any atlas that covers the sphere when tau >= 0.05 (the
+// 48-bin Fibonacci atlas: Z >= exp(-0.045 / tau)).  Sharper kernels use the tf32 operands, whose exponent range is that
+// of float32.  GCS_TC_OPERANDS=tf32 / f16 forces one variant (A/B runs).
+bool tc_use_f16(double inv_tau) {
+  static int forced = -2;
+  if (forced == -2) {
     const char* e = getenv("GCS_TC_OPERANDS");
-    v = (e && e[0] == 't') ? 0 : 1;
+    forced = !e ? -1 : (e[0] == 't' ? 0 : 1);
   }
-  return v == 1;
+  return forced >= 0 ? forced == 1 : inv_tau <= 20.0;
 }
 
 template <int Q, bool H>
@@ -682,7 +691,7 @@ bool bin_scan_tc_supported(const BinScanParams& P) {
 
 cudaError_t launch_bin_scan_tc(int sm_count, cudaStream_t st, const BinScanParams& P, int n_parts) {
   const int U = P.n_scans * P.n_hyp;
-  if (tc_use_f16()) {
+  if (tc_use_f16(P.inv_tau)) {
     if (P.n_bins <= 48) return launch_q<3, true>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<3, true>::kProd));
     return launch_q<4, true>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<4, true>::kProd));
   }
