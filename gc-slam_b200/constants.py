@@ -16,6 +16,8 @@ GC_KAPPA_BLEND_R0 = 0.8  # :95
 GC_KAPPA_BLEND_TAU = 0.03  # :96
 GC_TIME_WARP_SIGMA_FRAC = 0.1  # :141
 GC_WEIGHT_FLOOR = 1e-12  # :237
+GC_MAX_IMU_PREINT_LEN = 512  # :67  IMU buffer length handed to the preintegration (zero-padded)
+GC_GRAVITY_W = (0.0, 0.0, -9.81)  # :80  Z-up world, gravity along -Z
 GC_NONFINITE_SENTINEL = 1e6  # :238
 GC_RANGE_WEIGHT_SIGMA = 0.25  # :241
 GC_RANGE_WEIGHT_MIN_R = 0.5  # :242

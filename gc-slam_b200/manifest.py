@@ -15,6 +15,8 @@ ENTRY_POINTS = {
     "core_array": "torch.cuda+libgcs_b200",
     "se3": "gcs_common.cuh:so3_exp/so3_log/deskew_point",
     "domain_projection_psd": "gcs_common.cuh:psd_project3",
+    "pointcloud2_ingest": "gcs_parse_pointcloud2_vlp16",
+    "imu_preintegration": "gcs_imu_scan_twist",
     "point_budget": "gcs_point_budget_resample",
     "deskew": "gcs_deskew_constant_twist",
     "bin_soft_assign": "gcs_bin_soft_assign",

@@ -746,6 +746,21 @@ class BinPathPlan:
             n += dst.numel() * dst.element_size()
         return n
 
+    def set_twist_from_imu(self, scan_index, imu_stamps, imu_gyro, imu_accel, scan_start_time, scan_end_time, sigma_warp,
+                           rotvec_start_WB, gyro_bias, accel_bias, gravity_W=None, deskew_rotation_only=False):
+        """
+        SURVEY.md 8f-2: derive the n_hyp constant twists of scan `scan_index` from its IMU buffer on the device
+        (window weights -> preintegration -> se3_log, fl/backend/pipeline.py:436-483) and write them straight into this
+        plan's xi rows -- no host round trip between the IMU prologue and the deskew.  Returns the ImuTwistResult.
+        """
+        from . import imu
+        s = int(scan_index)
+        if not 0 <= s < self.S:
+            raise ValueError(f"scan_index {s} outside [0, {self.S})")
+        return imu.imu_scan_twist(imu_stamps, imu_gyro, imu_accel, scan_start_time, scan_end_time, sigma_warp,
+                                  rotvec_start_WB, gyro_bias, accel_bias, gravity_W, deskew_rotation_only,
+                                  xi_out=self.xi[s * self.H:(s + 1) * self.H])
+
     def enable_pointcloud2(self, fields, point_step: int, R_base_lidar=None, t_base_lidar=None):
         """
         Let the plan ingest PointCloud2 payloads directly: allocates the device staging buffer for

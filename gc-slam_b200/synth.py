@@ -282,3 +282,34 @@ def camera_splats(n, seed):
     d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
     return dict(positions=pos, covariances=cov, directions=d, kappas=rng.uniform(1, 50, n), weights=rng.uniform(0.2, 1.0, n),
                 timestamps=np.full(n, EPOCH_T0 + 0.05), colors=rng.uniform(0, 1, (n, 3)))
+
+
+def imu_window(n_total: int, n_valid: int, seed: int, t_start: float = EPOCH_T0, rate_hz: float = 200.0,
+               lead_s: float = 0.02, gyro_scale: float = 0.4, accel_noise: float = 0.3):
+    """
+    IMU buffer as the pipeline hands it to the preintegration (fixed length GC_MAX_IMU_PREINT_LEN = 512,
+    fl/common/constants.py:65-67): `n_valid` samples at `rate_hz` starting `lead_s` before the scan, zero-padded
+    stamps / rates after them.  Gyro: slowly varying body rates; accel: specific force of a body near rest
+    (+9.81 on z) plus a smooth manoeuvre and white noise.  Returns (stamps (M,), gyro (M,3), accel (M,3)).
+    """
+    rng = np.random.default_rng(seed)
+    stamps = np.zeros(n_total)
+    gyro = np.zeros((n_total, 3))
+    accel = np.zeros((n_total, 3))
+    k = np.arange(n_valid)
+    tt = k / rate_hz
+    stamps[:n_valid] = t_start - lead_s + tt
+    w0 = rng.uniform(-gyro_scale, gyro_scale, 3)
+    w1 = rng.uniform(-gyro_scale, gyro_scale, 3)
+    gyro[:n_valid] = w0[None, :] + np.sin(2.0 * np.pi * 1.3 * tt)[:, None] * w1[None, :] + rng.normal(0.0, 0.01, (n_valid, 3))
+    a0 = rng.uniform(-1.0, 1.0, 3)
+    accel[:n_valid] = np.array([0.0, 0.0, 9.81])[None, :] + np.cos(2.0 * np.pi * 0.7 * tt)[:, None] * a0[None, :] \
+        + rng.normal(0.0, accel_noise, (n_valid, 3))
+    return stamps, gyro, accel
+
+
+def imu_hypothesis_params(n_hyp: int, seed: int):
+    """Per-hypothesis inputs of the twist prologue: start orientation (rotvec), gyro / accel bias, time-warp sigma."""
+    rng = np.random.default_rng(seed)
+    return dict(rotvec0=rng.uniform(-0.6, 0.6, (n_hyp, 3)), gyro_bias=rng.normal(0.0, 0.01, (n_hyp, 3)),
+                accel_bias=rng.normal(0.0, 0.05, (n_hyp, 3)), sigma=rng.uniform(0.01, 0.03, n_hyp))

@@ -82,6 +82,24 @@ int gcs_parse_pointcloud2_vlp16(gcs_ctx* ctx, void* stream, const uint8_t* data 
                                 double* t /*dev (n_msgs,n)*/, double* w /*dev (n_msgs,n)*/, uint8_t* ring /*dev*/,
                                 uint8_t* tag /*dev*/, double* cert /*dev (n_msgs, GCS_PC_NCERT)*/);
 
+/* ---- (8f-2) IMU scan twist : fl/backend/operators/imu_preintegration.py:19-146 (smooth_window_weights,
+ * preintegrate_imu_relative_pose_jax), fl/common/geometry/se3_jax.py:178-256 (se3_log), glue fl/backend/pipeline.py:436-483.
+ * One launch serves n_hyp hypotheses that share the IMU buffer (stamps may be zero-padded, as the pipeline pads to
+ * GC_MAX_IMU_PREINT_LEN = 512) and differ in the belief-derived parameters.  params row (GCS_IMU_NPARAM doubles):
+ * rotvec_start_WB[3], gyro_bias[3], accel_bias[3], gravity_W[3], sigma, scan_start_time, scan_end_time, trans_scale
+ * (0 for rotation-only deskew, else 1).  out row: the reference's return tuple at the GCS_IMU_* offsets plus
+ * xi_body = se3_log(delta_pose) with its translation scaled.  xi_out (n_hyp, 6), if given, receives xi_body
+ * contiguously -- the layout gcs_bins_args.xi and gcs_deskew_constant_twist read.  gyro == accel == NULL: weights only. */
+enum { GCS_IMU_NPARAM = 16 };
+enum { GCS_IMU_DELTA_POSE = 0, GCS_IMU_DELTA_R = 6, GCS_IMU_DELTA_P = 15, GCS_IMU_DELTA_V = 18, GCS_IMU_ESS = 21,
+       GCS_IMU_A_BODY_MEAN = 22, GCS_IMU_A_WORLD_NOG_MEAN = 25, GCS_IMU_A_WORLD_MEAN = 28, GCS_IMU_DT_EFF_SUM = 31,
+       GCS_IMU_XI_BODY = 32, GCS_IMU_NOUT = 40 };
+int gcs_imu_scan_twist(gcs_ctx* ctx, void* stream, const double* stamps /*dev (M)*/, const double* gyro /*dev (M,3) or NULL*/,
+                       const double* accel /*dev (M,3) or NULL*/, int64_t n_samples, const double* params /*dev (n_hyp,16)*/,
+                       const double* weights_in /*dev (n_hyp, M) or NULL: use these instead of the smooth window*/,
+                       int n_hyp, double* out /*dev (n_hyp, GCS_IMU_NOUT)*/, double* xi_out /*dev (n_hyp,6) or NULL*/,
+                       double* weights_out /*dev (n_hyp, M) or NULL*/);
+
 /* ---- a1 PointBudgetResample : fl/backend/operators/point_budget.py:50-109,117-221 --------------------- */
 enum { GCS_RS_MASS_IN = 0, GCS_RS_MASS_SEL, GCS_RS_SUMSQ_SEL, GCS_RS_ESS, GCS_RS_MASS_SCALE, GCS_RS_NCERT = 8 };
 int gcs_point_budget_resample(gcs_ctx* ctx, void* stream,
