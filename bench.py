@@ -557,7 +557,7 @@ def run_ours(args):
 KERNEL_OF = {"f64": "bin_scan_kernel", "mixed": "bin_scan_kernel", "tc": "bin_scan_tc_kernel"}
 DTYPE_OF = {"f64": "f64",
             "mixed": "f64 (f32 MUFU soft-assign exponentials)",
-            "tc": "f64 geometry/epilogue + f32 soft-assign + tf32x2 tensor-core moments flushed to f64"}
+            "tc": "f64 geometry/epilogue + f32 soft-assign + fp16 hi/lo tensor-core moments (f32 accumulate) flushed to f64"}
 
 
 def main():
@@ -569,7 +569,7 @@ def main():
     ap.add_argument("--scans", type=int, default=128, help="scans per step per GPU")
     ap.add_argument("--points", type=int, default=65536)
     ap.add_argument("--precision", default="tc", choices=["tc", "mixed", "f64"],
-                    help="tc: tcgen05 moment contraction (tf32 hi/lo operands, float64 flushes), float32 soft-assign, float64 "
+                    help="tc: tcgen05 moment contraction (fp16 hi/lo operands, float64 flushes), float32 soft-assign, float64 "
                          "geometry -- inside the 1e-5 parity tolerance (tests/test_gpu_bins.py); f64: everything float64")
     ap.add_argument("--no-cpu", action="store_true", help="skip the in-run CPU baseline")
     ap.add_argument("--no-prim", action="store_true", help="skip the primitive-path (config 3) stage timings")
