@@ -265,13 +265,29 @@ def primitive_path_extra(n_points, n_map=1_000_000, reps=10):
                 stages[k].append(v)
             stages["total"].append(tk[-1] - tk[0])
     p50 = {k: 1e3 * float(np.median(v)) for k, v in stages.items()}
+    # the same path through the fused entry (lidar_evidence_primitives: two host synchronisations instead of seven)
+    fused = []
+    for rep in range(reps + 2):
+        scan_seq = 21 + reps + 2 + rep
+        torch.cuda.synchronize()
+        a0 = time.perf_counter()
+        out = PR.lidar_evidence_primitives(pts_d, t_d, w_d, synth.EPOCH_T0, synth.EPOCH_T0 + 0.1, xi, amap, active, pose,
+                                           scan_seq, base_batch=base)
+        torch.cuda.synchronize()
+        if rep >= 2:
+            fused.append(time.perf_counter() - a0)
+    p50["fused_entry_total"] = 1e3 * float(np.median(fused))
+    res = out["map_update"][0]
+    batch = out["surfels"][0]
     alg_bytes = 104e6  # ~104 MB per scan at 65,536 points / 1 M-surfel map, 7 active tiles
     return {"workload": f"{n_points}-point scan, {n_map} surfel synthetic map ({len(amap.tiles)} tiles of 50,000 slots), 512 camera "
                         "splats + 1024 surfels, K_ASSOC 8, 7-tile stencil, map update with K_INSERT 64",
-            "p50_ms_per_stage": p50, "scans_per_s": 1e3 / p50["total"], "algorithmic_bytes_per_scan": alg_bytes,
-            "achieved_GBps_model": alg_bytes / (p50["total"] * 1e-3) / 1e9, "n_lidar_surfels": int(batch.n_lidar_valid),
+            "p50_ms_per_stage": p50, "scans_per_s": 1e3 / p50["fused_entry_total"],
+            "scans_per_s_operator_by_operator": 1e3 / p50["total"], "algorithmic_bytes_per_scan": alg_bytes,
+            "achieved_GBps_model": alg_bytes / (p50["fused_entry_total"] * 1e-3) / 1e9, "n_lidar_surfels": int(batch.n_lidar_valid),
             "n_inserted_last": int(res.n_inserted), "map_build_s": t_build, "reps": reps,
-            "note": "wall clock per operator call incl. its one certificate read-back (host sync)"}
+            "note": "per-stage: wall clock per operator call incl. its one certificate read-back (host sync); fused_entry_total: "
+                    "the whole path through lidar_evidence_primitives (two host syncs), which scans_per_s is quoted on"}
 
 
 # ----------------------------------------------------------------------------------------------------------

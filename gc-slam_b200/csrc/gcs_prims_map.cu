@@ -112,10 +112,23 @@ struct SelectSmem {
   int hist[256];
   int scan[2 * kBig];
 };
+// dynamic shared memory of the tile-wide selects: the 32-bit key cache of cta_select_k (one word per tile slot), when a
+// tile fits next to the static buffers (50,000 slots: 200,000 of the 232,448 bytes an sm_100 CTA may use)
+constexpr size_t kSelectStaticBytes = sizeof(SelectSmem) + 256;
+inline size_t select_cache_bytes(int m_tile) {
+  const size_t want = (size_t)m_tile * sizeof(uint32_t);
+  return want + kSelectStaticBytes <= 232448 ? want : 0;
+}
+template <typename Kern>
+cudaError_t select_cache_attr(Kern kern, size_t bytes) {
+  return bytes > 48 * 1024 - kSelectStaticBytes
+             ? cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) : cudaSuccess;
+}
 
 __global__ void __launch_bounds__(kBig) map_view_kernel(gcs_atlas A, TileList T, int m_view, double eps_lift, double eps_mass,
-                                                        gcs_map_view V, int32_t* __restrict__ n_valid_out) {
+                                                        gcs_map_view V, int32_t* __restrict__ n_valid_out, int use_cache) {
   __shared__ SelectSmem sm;
+  extern __shared__ uint32_t key_cache[];
   const int a = blockIdx.x;
   const int ti = T.index[a];
   const int M = A.m_tile;
@@ -125,7 +138,7 @@ __global__ void __launch_bounds__(kBig) map_view_kernel(gcs_atlas A, TileList T,
     if (ti >= 0 && A.valid[base + s]) score = A.weights[base + s];
     return f64_orderable(-score);  // ascending sort of -score (primitive_map.py:316-320)
   };
-  cta_select_k(M, m_view, key, sm.out, sm.hist, sm.scan);
+  cta_select_k(M, m_view, key, sm.out, sm.hist, sm.scan, use_cache ? key_cache : nullptr);
   int local_valid = 0;
   for (int j = threadIdx.x; j < m_view; j += kBig) {
     const int slot = sm.out[j].idx;
@@ -743,8 +756,9 @@ __global__ void __launch_bounds__(256) upd_rgb_sweep_kernel(gcs_atlas A, TileLis
 
 // per active tile: which measurements to insert and which slots to evict (pipeline.py:1348-1366, primitive_map.py:837-855)
 __global__ void __launch_bounds__(kBig) upd_insert_select_kernel(gcs_atlas A, TileList T, gcs_meas_batch B, int N, UpdWs W,
-                                                                 gcs_map_update_cfg cfg) {
+                                                                 gcs_map_update_cfg cfg, int use_cache) {
   __shared__ SelectSmem sm;
+  extern __shared__ uint32_t key_cache[];
   __shared__ int s_any;
   const int a = blockIdx.x, tid = threadIdx.x, k = cfg.k_insert_tile;
   const long long my_id = T.id[a];
@@ -783,7 +797,7 @@ __global__ void __launch_bounds__(kBig) upd_insert_select_kernel(gcs_atlas A, Ti
     }
     return f64_orderable(keyv);
   };
-  cta_select_k(A.m_tile, k, key2, sm.out, sm.hist, sm.scan);
+  cta_select_k(A.m_tile, k, key2, sm.out, sm.hist, sm.scan, use_cache ? key_cache : nullptr);
   if (tid < k) W.ins_slot[a * k + tid] = sm.out[tid].idx;
   if (tid == 0) {
     int n = 0;
@@ -1005,7 +1019,9 @@ int gcs_extract_atlas_map_view(gcs_ctx* ctx, void* stream, const gcs_atlas* atla
   cudaStream_t st = (cudaStream_t)stream;
   GCS_CHECK_CUDA(ctx, cudaMemsetAsync(out_n_valid, 0, sizeof(int32_t), st));
   gcs_timing_begin(ctx, st);
-  map_view_kernel<<<n_tiles, kBig, 0, st>>>(*atlas, T, m_tile_view, eps_lift, eps_mass, *view, out_n_valid);
+  // no key cache here: the view's key is two cached loads, and the 200 KB carve-out it would take from L1 costs more
+  // than the re-evaluations (measured 208 us with, 158 us without; the eviction select of the map update gains 35 %)
+  map_view_kernel<<<n_tiles, kBig, 0, st>>>(*atlas, T, m_tile_view, eps_lift, eps_mass, *view, out_n_valid, 0);
   gcs_timing_end(ctx, st);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
@@ -1154,7 +1170,9 @@ int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int
   GCS_LAUNCH_CHECK(ctx);
   upd_rgb_sweep_kernel<<<dim3(sweep_blocks, n_tiles), 256, 0, st>>>(*atlas, T, cfg->eps_mass);
   GCS_LAUNCH_CHECK(ctx);
-  upd_insert_select_kernel<<<n_tiles, kBig, 0, st>>>(*atlas, T, *batch, N, W, *cfg);
+  const size_t kc_ins = select_cache_bytes(atlas->m_tile);
+  GCS_CHECK_CUDA(ctx, select_cache_attr(upd_insert_select_kernel, kc_ins));
+  upd_insert_select_kernel<<<n_tiles, kBig, kc_ins, st>>>(*atlas, T, *batch, N, W, *cfg, kc_ins ? 1 : 0);
   GCS_LAUNCH_CHECK(ctx);
   upd_insert_apply_kernel<<<n_tiles, ((k_ins + 31) / 32) * 32, 0, st>>>(*atlas, T, *batch, W, *cfg, (long long*)out_new_ids, out_insert_slots);
   GCS_LAUNCH_CHECK(ctx);

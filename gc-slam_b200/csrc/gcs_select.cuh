@@ -64,6 +64,10 @@ __device__ inline void cta_bitonic_sort_u64(unsigned long long* s, int n_pow2) {
 //   KeyFn: unsigned long long operator()(int i) const   (evaluated ~4-5 times per item)
 //   out:   shared memory, capacity >= max(1024, next_pow2(k)) entries (also used as the candidate buffer)
 //   hist:  unused (kept for the call sites);  scan: shared memory, >= 1024 + 64 ints
+//   kc:    optional shared-memory cache of n 32-bit words (NULL: none).  The first histogram pass stores the high word
+//          of every key there; the later passes and sweeps then decide from the cache and evaluate key(i) only for
+//          items whose high word equals the prefix / threshold -- one evaluation per item instead of four or five
+//          (the eviction key costs an exp() and three global loads per evaluation).
 // Requires k <= n and k <= 1024.  All threads of the CTA must call; blockDim.x >= 32.
 //
 // MSD radix select with 10-bit digits.  As soon as the items that still match the prefix fit the candidate buffer
@@ -72,7 +76,7 @@ __device__ inline void cta_bitonic_sort_u64(unsigned long long* s, int n_pow2) {
 // order and a bitonic sort by (key, index) puts them in the order of a stable sort.  When more than 1024 items tie on
 // the k-th key (e.g. a tile with fewer than k valid slots) T_idx comes from an index-ordered count of the ties.
 template <typename KeyFn>
-__device__ inline void cta_select_k(int n, int k, KeyFn key, KeyIdx* out, int* hist, int* scan) {
+__device__ inline void cta_select_k(int n, int k, KeyFn key, KeyIdx* out, int* hist, int* scan, uint32_t* kc = nullptr) {
   (void)hist;
   __shared__ unsigned long long s_prefix;
   __shared__ int s_need, s_count, s_slot, s_tidx;
@@ -88,9 +92,26 @@ __device__ inline void cta_select_k(int n, int k, KeyFn key, KeyIdx* out, int* h
     const unsigned long long dm = (1ull << bits) - 1ull;
     for (int b = tid; b < 1024; b += nt) h[b] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += nt) {
-      const unsigned long long kk = key(i);
-      if ((kk & mask) == prefix) atomicAdd(&h[(int)((kk >> sh) & dm)], 1);
+    if (kc && shift == 54) {
+      for (int i = tid; i < n; i += nt) {
+        const unsigned long long kk = key(i);
+        kc[i] = (uint32_t)(kk >> 32);
+        atomicAdd(&h[(int)((kk >> sh) & dm)], 1);
+      }
+    } else if (kc && sh >= 32) {
+      // digit and prefix live in the cached high word
+      const uint32_t m32 = (uint32_t)(mask >> 32), p32 = (uint32_t)(prefix >> 32);
+      for (int i = tid; i < n; i += nt) {
+        const uint32_t hw = kc[i];
+        if ((hw & m32) == p32) atomicAdd(&h[(int)((hw >> (sh - 32)) & (uint32_t)dm)], 1);
+      }
+    } else {
+      const uint32_t m32 = (uint32_t)(mask >> 32), p32 = (uint32_t)(prefix >> 32);
+      for (int i = tid; i < n; i += nt) {
+        if (kc && (kc[i] & m32) != p32) continue;
+        const unsigned long long kk = key(i);
+        if ((kk & mask) == prefix) atomicAdd(&h[(int)((kk >> sh) & dm)], 1);
+      }
     }
     __syncthreads();
     if (tid < 32) {
@@ -127,11 +148,15 @@ __device__ inline void cta_select_k(int n, int k, KeyFn key, KeyIdx* out, int* h
   if (have_cands) {
     if (tid == 0) s_slot = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += nt) {
-      const unsigned long long kk = key(i);
-      if ((kk & mask) == prefix) {
-        const int sl = atomicAdd(&s_slot, 1);
-        out[sl].key = kk; out[sl].idx = i;
+    {
+      const uint32_t m32 = (uint32_t)(mask >> 32), p32 = (uint32_t)(prefix >> 32);
+      for (int i = tid; i < n; i += nt) {
+        if (kc && (kc[i] & m32) != p32) continue;
+        const unsigned long long kk = key(i);
+        if ((kk & mask) == prefix) {
+          const int sl = atomicAdd(&s_slot, 1);
+          out[sl].key = kk; out[sl].idx = i;
+        }
       }
     }
     __syncthreads();
@@ -149,7 +174,8 @@ __device__ inline void cta_select_k(int n, int k, KeyFn key, KeyIdx* out, int* h
     const int chunk = (n + nt - 1) / nt;
     const int c0 = tid * chunk, c1 = (c0 + chunk < n) ? c0 + chunk : n;
     int n_eq = 0;
-    for (int i = c0; i < c1; ++i) n_eq += (key(i) == T);
+    const uint32_t t32 = (uint32_t)(T >> 32);
+    for (int i = c0; i < c1; ++i) n_eq += ((!kc || kc[i] == t32) && key(i) == T);
     int inc = n_eq;
     for (int o = 1; o < 32; o <<= 1) {
       const int v = __shfl_up_sync(0xffffffffu, inc, o);
@@ -162,18 +188,22 @@ __device__ inline void cta_select_k(int n, int k, KeyFn key, KeyIdx* out, int* h
     if (before < need && need <= before + n_eq) {
       int r = before;
       for (int i = c0; i < c1; ++i)
-        if (key(i) == T && ++r == need) { s_tidx = i; break; }
+        if ((!kc || kc[i] == t32) && key(i) == T && ++r == need) { s_tidx = i; break; }
     }
     __syncthreads();
     T_idx = s_tidx;
   }
   if (tid == 0) s_slot = 0;
   __syncthreads();
-  for (int i = tid; i < n; i += nt) {
-    const unsigned long long kk = key(i);
-    if (kk < T || (kk == T && i <= T_idx)) {
-      const int sl = atomicAdd(&s_slot, 1);
-      out[sl].key = kk; out[sl].idx = i;
+  {
+    const uint32_t t32f = (uint32_t)(T >> 32);
+    for (int i = tid; i < n; i += nt) {
+      if (kc && kc[i] > t32f) continue;             // high word above the threshold's: key > T
+      const unsigned long long kk = key(i);
+      if (kk < T || (kk == T && i <= T_idx)) {
+        const int sl = atomicAdd(&s_slot, 1);
+        out[sl].key = kk; out[sl].idx = i;
+      }
     }
   }
   int kp = 1;

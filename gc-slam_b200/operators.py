@@ -93,6 +93,64 @@ class _IO:
         return ComputeCert(device_runtime=self.runtime_cert(), **kw)
 
 
+# ---- deferred certificate reads ------------------------------------------------------------------------------------
+# An operator body is a generator: it enqueues its kernels, then yields (io, device tensor of certificate scalars,
+# provisional result) and is resumed with the host copy of that tensor to assemble (result, CertBundle, ExpectedEffect).
+# `_drive` runs one operator the way the reference's call sites expect (one batched read-back, i.e. one host sync per
+# operator).  `drive_group` advances several operators to their yield first -- later ones may consume the provisional
+# (device-side) results of earlier ones -- and serves all their read-backs with ONE stream synchronisation.
+_PINNED = {}
+
+
+def _pinned_like(t, slot):
+    key = (slot, t.dtype, t.numel())
+    buf = _PINNED.get(key)
+    if buf is None:
+        buf = _PINNED[key] = torch.empty(t.numel(), dtype=t.dtype).pin_memory()
+    return buf
+
+
+def _drive(gen):
+    try:
+        io, t, _prov = next(gen)
+        while True:
+            io, t, _prov = gen.send(io.host(t))
+    except StopIteration as e:
+        return e.value
+
+
+class _Pending:
+    """An operator advanced to its certificate read-back; `provisional` holds its device-side outputs."""
+
+    def __init__(self, gen):
+        self.gen, self.done, self.value = gen, False, None
+        try:
+            self.io, self.tensor, self.provisional = next(gen)
+        except StopIteration as e:           # early exit without any device work
+            self.done, self.value, self.provisional = True, e.value, (e.value[0] if isinstance(e.value, tuple) else e.value)
+
+
+def drive_group(pending):
+    """Finish a list of _Pending operators with one stream synchronisation; returns their final values in order."""
+    live = [p for p in pending if not p.done]
+    bufs = []
+    for k, p in enumerate(live):
+        b = _pinned_like(p.tensor, k)
+        b.copy_(p.tensor.detach().reshape(-1), non_blocking=True)
+        bufs.append(b)
+    if live:
+        torch.cuda.current_stream(live[0].io.dev).synchronize()
+    for k, (p, b) in enumerate(zip(live, bufs)):
+        p.io.d2h += b.numel() * b.element_size()
+        p.io.syncs += 1 if k == 0 else 0
+        try:
+            p.gen.send(b.numpy().reshape(tuple(p.tensor.shape)).copy())
+            raise RuntimeError("operator body yielded twice: not usable in a fused group")
+        except StopIteration as e:
+            p.done, p.value = True, e.value
+    return [p.value for p in pending]
+
+
 def _dptr(a):
     return (C.c_double * len(a))(*[float(v) for v in a])
 
@@ -315,6 +373,12 @@ def point_budget_resample(points, timestamps, weights, ring=None, tag=None,
 def deskew_constant_twist(points, timestamps, weights, scan_start_time: float, scan_end_time: float, xi_body,
                           ess_imu: float, chart_id: str, anchor_id: str
                           ) -> Tuple[DeskewConstantTwistResult, CertBundle, ExpectedEffect]:
+    return _drive(_deskew_constant_twist_gen(points, timestamps, weights, scan_start_time, scan_end_time, xi_body, ess_imu,
+                                             chart_id, anchor_id))
+
+
+def _deskew_constant_twist_gen(points, timestamps, weights, scan_start_time, scan_end_time, xi_body, ess_imu, chart_id,
+                               anchor_id):
     io = _IO()
     pts = io.dev_in(points, shape=(-1, 3))
     t = io.dev_in(timestamps, shape=(-1,))
@@ -328,9 +392,9 @@ def deskew_constant_twist(points, timestamps, weights, scan_start_time: float, s
     io.ctx.check(io.ctx.lib.gcs_deskew_constant_twist(
         io.ctx.handle, io.stream(), L.ptr(pts), L.ptr(t), L.ptr(w), n, _dptr(xi), float(scan_start_time),
         float(scan_end_time), L.ptr(o_pts), L.ptr(o_w), L.ptr(cert_d)))
-    c = io.host(cert_d)
-    retained = float(c[L.DK_SUM_W_OUT] / (c[L.DK_SUM_W_IN] + constants.GC_EPS_MASS))
     result = DeskewConstantTwistResult(points=o_pts, timestamps=t, weights=o_w, ess_imu=float(ess_imu))
+    c = yield io, cert_d, result
+    retained = float(c[L.DK_SUM_W_OUT] / (c[L.DK_SUM_W_IN] + constants.GC_EPS_MASS))
     cert = CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id,
                                    support=SupportCert(ess_total=float(ess_imu), support_frac=retained),
                                    influence=InfluenceCert.identity(), compute=io.compute())

@@ -33,7 +33,7 @@ import torch
 from . import _lib as L
 from . import constants
 from .certs import (CertBundle, ComputeCert, ExpectedEffect, InfluenceCert, MapUpdateCert, OTCert, SupportCert)
-from .operators import _IO, _dptr, _host_vec
+from .operators import _IO, _Pending, _deskew_constant_twist_gen, _dptr, _drive, _host_vec, drive_group
 
 F64 = torch.float64
 _vp, _i32, _i64, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
@@ -257,6 +257,10 @@ def extract_lidar_surfels(points, timestamps, weights, config: Optional[SurfelEx
                           base_batch: Optional[MeasurementBatch] = None, chart_id: str = constants.GC_CHART_ID,
                           anchor_id: str = "surfel_extraction", return_bucket: bool = False
                           ) -> Tuple[MeasurementBatch, CertBundle, ExpectedEffect]:
+    return _drive(_extract_lidar_surfels_gen(points, timestamps, weights, config, base_batch, chart_id, anchor_id, return_bucket))
+
+
+def _extract_lidar_surfels_gen(points, timestamps, weights, config, base_batch, chart_id, anchor_id, return_bucket=False):
     if config is None:
         config = SurfelExtractionConfig()
     io = _IO()
@@ -276,7 +280,8 @@ def extract_lidar_surfels(points, timestamps, weights, config: Optional[SurfelEx
     cb, cc = batch._c(), config._c()
     io.ctx.check(io.ctx.lib.gcs_extract_lidar_surfels(io.ctx.handle, io.stream(), L.ptr(pts), L.ptr(t), L.ptr(w), n, C.byref(cc),
                                                       C.byref(cb), L.ptr(nv_d), L.ptr(bucket), L.ptr(count)))
-    n_use = int(io.host(nv_d)[0])
+    batch.n_lidar_valid = -1                      # not known on the host yet
+    n_use = int((yield io, nv_d, batch)[0])
     batch.n_lidar_valid = n_use
     support_frac = float(n_use) / float(max(config.n_surfel, 1))
     cert = CertBundle.create_approx(chart_id=chart_id, anchor_id=anchor_id,
@@ -401,13 +406,19 @@ def primitive_map_recency_inflate(atlas_map: AtlasMap, tile_ids: List[int], scan
                                   min_scale: float = constants.GC_RECENCY_MIN_SCALE, chart_id: str = constants.GC_CHART_ID,
                                   anchor_id: str = "primitive_map_recency_inflate"):
     """In place on the device pool (the reference rebuilds the tiles functionally); returns (atlas, cert, effect, stats)."""
+    return _drive(_recency_inflate_gen(atlas_map, tile_ids, scan_seq, recency_decay_lambda, min_scale, chart_id, anchor_id))
+
+
+def _recency_inflate_gen(atlas_map, tile_ids, scan_seq, recency_decay_lambda=constants.GC_RECENCY_DECAY_LAMBDA,
+                         min_scale=constants.GC_RECENCY_MIN_SCALE, chart_id=constants.GC_CHART_ID,
+                         anchor_id="primitive_map_recency_inflate"):
     io = _IO(atlas_map.device)
     idx = atlas_map.index_list(tile_ids, create=False)
     stats_d = io.zeros(4)
     ca = atlas_map._c()
     io.ctx.check(io.ctx.lib.gcs_map_recency_inflate(io.ctx.handle, io.stream(), C.byref(ca), _i32arr(idx), len(idx),
                                                     int(scan_seq), float(recency_decay_lambda), float(min_scale), L.ptr(stats_d)))
-    s = io.host(stats_d)
+    s = yield io, stats_d, atlas_map
     stats = PrimitiveMapRecencyInflateStats(staleness_inflation_strength=float(s[0] / max(s[2], 1.0)),
                                             staleness_cov_inflation_trace=float(s[1]),
                                             stale_precision_downscale_total=float(s[0]))
@@ -448,6 +459,10 @@ class AtlasMapView:
 
 def extract_atlas_map_view(atlas_map: AtlasMap, tile_ids: List[int], m_tile_view: int, eps_lift: float = constants.GC_EPS_LIFT,
                            eps_mass: float = constants.GC_EPS_MASS) -> AtlasMapView:
+    return _drive(_extract_atlas_map_view_gen(atlas_map, tile_ids, m_tile_view, eps_lift, eps_mass))
+
+
+def _extract_atlas_map_view_gen(atlas_map, tile_ids, m_tile_view, eps_lift=constants.GC_EPS_LIFT, eps_mass=constants.GC_EPS_MASS):
     if m_tile_view <= 0:
         raise ValueError(f"extract_atlas_map_view: m_tile_view must be > 0, got {m_tile_view}")
     io = _IO(atlas_map.device)
@@ -464,7 +479,8 @@ def extract_atlas_map_view(atlas_map: AtlasMap, tile_ids: List[int], m_tile_view
     io.ctx.check(io.ctx.lib.gcs_extract_atlas_map_view(io.ctx.handle, io.stream(), C.byref(ca), _i32arr(idx), _i64arr(tile_ids),
                                                        len(tile_ids), int(m_tile_view), float(eps_lift), float(eps_mass),
                                                        C.byref(cv), L.ptr(nv)))
-    view.n_valid = int(io.host(nv)[0])
+    view.n_valid = -1                             # not known on the host yet
+    view.n_valid = int((yield io, nv, view)[0])
     return view
 
 
@@ -531,6 +547,11 @@ def associate_primitives_ot(measurement_batch: MeasurementBatch, map_view: Atlas
                             eps_lift: float = constants.GC_EPS_LIFT, eps_mass: float = constants.GC_EPS_MASS,
                             chart_id: str = constants.GC_CHART_ID, anchor_id: str = "primitive_ot"
                             ) -> Tuple[PrimitiveAssociationResult, CertBundle, ExpectedEffect]:
+    return _drive(_associate_primitives_ot_gen(measurement_batch, map_view, config, eps_lift, eps_mass, chart_id, anchor_id))
+
+
+def _associate_primitives_ot_gen(measurement_batch, map_view, config=None, eps_lift=constants.GC_EPS_LIFT,
+                                 eps_mass=constants.GC_EPS_MASS, chart_id=constants.GC_CHART_ID, anchor_id="primitive_ot"):
     if config is None:
         config = AssociationConfig()
     if config.a_policy != MeasurementMassPolicy.UNIFORM:
@@ -555,7 +576,7 @@ def associate_primitives_ot(measurement_batch: MeasurementBatch, map_view: Atlas
     io.ctx.check(io.ctx.lib.gcs_associate_primitives_ot(io.ctx.handle, io.stream(), C.byref(cb), C.byref(cv),
                                                         _i64arr(map_view.tile_ids), len(map_view.tile_ids),
                                                         int(map_view.m_tile_view), C.byref(cfg), C.byref(cr), L.ptr(cert_d)))
-    c = io.host(cert_d)
+    c = yield io, cert_d, res
     tm = float(c[OT["MASS_TOTAL"]])
     n_nonzero_a = int(c[OT["NONZERO_A"]])
     compute = io.compute(alloc_bytes_est=int(N * K * 8 * 4), largest_tensor_shape=(int(N), int(K)), segment_sum_k=int(K),
@@ -599,6 +620,13 @@ def visual_pose_evidence(association_result: PrimitiveAssociationResult, measure
                          eps_mass: float = constants.GC_EPS_MASS, chart_id: str = constants.GC_CHART_ID,
                          anchor_id: str = "visual_pose_evidence", z_lin_pose=None
                          ) -> Tuple[VisualPoseEvidenceResult, CertBundle, ExpectedEffect]:
+    return _drive(_visual_pose_evidence_gen(association_result, measurement_batch, map_view, belief_pred, eps_lift, eps_mass,
+                                            chart_id, anchor_id, z_lin_pose))
+
+
+def _visual_pose_evidence_gen(association_result, measurement_batch, map_view, belief_pred, eps_lift=constants.GC_EPS_LIFT,
+                              eps_mass=constants.GC_EPS_MASS, chart_id=constants.GC_CHART_ID, anchor_id="visual_pose_evidence",
+                              z_lin_pose=None):
     io = _IO(measurement_batch.Lambdas.device)
     N_meas = measurement_batch.n_valid
     N_assoc, K = association_result.responsibilities.shape
@@ -618,7 +646,7 @@ def visual_pose_evidence(association_result: PrimitiveAssociationResult, measure
     cb, cv, cr = measurement_batch._c(), map_view._c(), association_result._c()
     io.ctx.check(io.ctx.lib.gcs_visual_pose_evidence(io.ctx.handle, io.stream(), C.byref(cb), C.byref(cv), C.byref(cr), int(K),
                                                      _dptr(pose), float(eps_lift), float(eps_mass), L.ptr(L22), L.ptr(h22), L.ptr(rec_d)))
-    r = io.host(rec_d)
+    r = yield io, rec_d, None
     n_rows = int(r[VP["N_VALID_ROWS"]])
     total_cost = float(r[VP["TRANS_COST"]] + r[VP["ROT_COST"]])
     res = VisualPoseEvidenceResult(L_pose=L22, h_pose=h22, L_trans=rec_d[0:9].reshape(3, 3), h_trans=rec_d[9:12],
@@ -656,6 +684,19 @@ def map_update_step12b(atlas_map: AtlasMap, measurement_batch: MeasurementBatch,
                        assoc_block_size: int = constants.GC_ASSOC_BLOCK_SIZE, strict_tile_state: bool = True,
                        inflate_stats: Optional[PrimitiveMapRecencyInflateStats] = None,
                        chart_id: str = constants.GC_CHART_ID) -> Tuple[MapUpdateResult, CertBundle, ExpectedEffect]:
+    return _drive(_map_update_step12b_gen(atlas_map, measurement_batch, association_result, active_tile_ids, z_t, scan_seq,
+                                          timestamp, k_insert_tile, recency_decay_lambda, eps_lift, eps_mass, h_tile,
+                                          cull_weight_threshold, forgetting_factor, assoc_block_size, strict_tile_state,
+                                          inflate_stats, chart_id))
+
+
+def _map_update_step12b_gen(atlas_map, measurement_batch, association_result, active_tile_ids, z_t, scan_seq, timestamp,
+                            k_insert_tile=constants.GC_K_INSERT_TILE, recency_decay_lambda=constants.GC_RECENCY_DECAY_LAMBDA,
+                            eps_lift=constants.GC_EPS_LIFT, eps_mass=constants.GC_EPS_MASS, h_tile=constants.GC_H_TILE,
+                            cull_weight_threshold=constants.GC_PRIMITIVE_CULL_WEIGHT_THRESHOLD,
+                            forgetting_factor=constants.GC_PRIMITIVE_FORGETTING_FACTOR,
+                            assoc_block_size=constants.GC_ASSOC_BLOCK_SIZE, strict_tile_state=True, inflate_stats=None,
+                            chart_id=constants.GC_CHART_ID):
     """
     Whole primitive-map update of one scan in one call (in place on the device pool): rigid pushforward of the
     measurement batch with z_t, PoE fuse into the associated slots, novelty-driven insertion into the lowest-retention
@@ -679,7 +720,7 @@ def map_update_step12b(atlas_map: AtlasMap, measurement_batch: MeasurementBatch,
     io.ctx.check(io.ctx.lib.gcs_map_update(io.ctx.handle, io.stream(), C.byref(ca), _i32arr(idx), _i64arr(active_tile_ids), nt,
                                            C.byref(cb), C.byref(cr), _dptr(pose), C.byref(cfg), L.ptr(new_ids), L.ptr(slots),
                                            L.ptr(stats_d)))
-    s = io.host(stats_d)
+    s = yield io, stats_d, atlas_map
     n_ins, n_cull = int(s[MU["INSERT_COUNT"]]), int(s[MU["EVICTED_COUNT"]])
     atlas_map.next_global_id = int(s[MU["NEXT_GLOBAL_ID"]])
     atlas_map.total_count = atlas_map.total_count + n_ins - n_cull
@@ -699,3 +740,49 @@ def map_update_step12b(atlas_map: AtlasMap, measurement_batch: MeasurementBatch,
     _ = n_exist_before
     cert = CertBundle.create_exact(chart_id=chart_id, anchor_id="map_update", map_update=mu, compute=io.compute())
     return result, cert, ExpectedEffect("map_update", float(n_ins), float(n_ins))
+
+
+# --------------------------------------------------------------------------------------------------
+# fused fast entry: the primitive-family LiDAR evidence path of one scan with TWO host synchronisations
+# --------------------------------------------------------------------------------------------------
+def lidar_evidence_primitives(points, timestamps, weights, scan_start_time: float, scan_end_time: float, xi_body,
+                              atlas_map: AtlasMap, active_tile_ids: List[int], pose_pred, scan_seq: int,
+                              base_batch: Optional[MeasurementBatch] = None, z_t=None,
+                              surfel_config: Optional[SurfelExtractionConfig] = None,
+                              association_config: Optional[AssociationConfig] = None,
+                              m_tile_view: int = constants.GC_M_TILE_VIEW, ess_imu: float = 1.0, update_map: bool = True,
+                              map_update_kwargs: Optional[dict] = None, chart_id: str = constants.GC_CHART_ID,
+                              anchor_id: str = "lidar_evidence_primitives") -> dict:
+    """
+    The call sequence of process_scan_single_hypothesis for the primitive family (fl/backend/pipeline.py:569-587 deskew,
+    :780-800 surfels, :835-853 recency inflate + map view, :855-877 association, :998-1010 pose evidence, :1233-1447 map
+    update) in one call.  The same C entry points run in the same order on the current stream and every stage returns
+    exactly the tuple its stand-alone operator returns -- results are bit-identical to calling the operators one by
+    one -- but the seven per-operator certificate read-backs collapse into two: one after the map view (the only point
+    where the host must decide something: empty measurement batch / empty view take the reference's early exits) and
+    one at the end.  Keys: deskew, surfels, recency_inflate, map_view, association, pose_evidence, map_update.
+    """
+    if z_t is None:
+        z_t = pose_pred
+    if association_config is None:
+        association_config = AssociationConfig(scan_seq=int(scan_seq))
+    g_dk = _Pending(_deskew_constant_twist_gen(points, timestamps, weights, scan_start_time, scan_end_time, xi_body, ess_imu,
+                                               chart_id, anchor_id))
+    dk = g_dk.provisional
+    g_sf = _Pending(_extract_lidar_surfels_gen(dk.points, dk.timestamps, dk.weights, surfel_config, base_batch, chart_id,
+                                               "surfel_extraction"))
+    g_ri = _Pending(_recency_inflate_gen(atlas_map, active_tile_ids, scan_seq, association_config.recency_decay_lambda))
+    g_mv = _Pending(_extract_atlas_map_view_gen(atlas_map, active_tile_ids, m_tile_view))
+    dk_out, sf_out, ri_out, view = drive_group([g_dk, g_sf, g_ri, g_mv])
+    batch = sf_out[0]
+    inflate_stats = ri_out[3]
+    g_as = _Pending(_associate_primitives_ot_gen(batch, view, association_config))
+    assoc = g_as.provisional
+    g_pe = _Pending(_visual_pose_evidence_gen(assoc, batch, view, pose_pred, z_lin_pose=pose_pred))
+    group = [g_as, g_pe]
+    if update_map:
+        group.append(_Pending(_map_update_step12b_gen(atlas_map, batch, assoc, active_tile_ids, z_t, scan_seq, scan_end_time,
+                                                      inflate_stats=inflate_stats, **(map_update_kwargs or {}))))
+    outs = drive_group(group)
+    return dict(deskew=dk_out, surfels=sf_out, recency_inflate=ri_out, map_view=view, association=outs[0],
+                pose_evidence=outs[1], map_update=outs[2] if update_map else None)

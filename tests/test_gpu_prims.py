@@ -207,3 +207,67 @@ def test_empty_and_error_cases(P):
         P.associate_primitives_ot(batch, view, P.AssociationConfig(b_policy=P.MapMassPolicy.PRIMITIVE_MASS))
     with pytest.raises(ValueError):
         P.extract_lidar_surfels(pts[:10], t, w)
+
+
+def test_fused_entry_is_bit_identical_to_operator_sequence(P):
+    """lidar_evidence_primitives (two host synchronisations) vs the seven stand-alone operators (seven): same C entry
+    points in the same order, so every output, certificate scalar and the updated map must be bit-identical; and the
+    empty-map early exits must be taken the same way."""
+    from gc_slam_b200 import operators as ops, synth
+    n = 30000
+    pts, t, w, _, _ = synth.vlp16_scan(n, 41, t0=synth.EPOCH_T0)
+    xi = synth.scan_twist(41)
+    cam = synth.camera_splats(150, 78)
+    atlas_np = synth.synthetic_atlas(120000, 50000, 10, scan_seq=20)
+    pose = np.array([0.1, -0.2, 0.0, 0.0, 0.0, 0.05])
+    active = P.ma_hex_stencil_tile_ids(pose[:3])
+    t0, t1 = synth.EPOCH_T0, synth.EPOCH_T0 + 0.1
+
+    def base():
+        return P.measurement_batch_from_camera_splats(cam["positions"], cam["covariances"], cam["directions"], cam["kappas"],
+                                                      cam["weights"], cam["timestamps"], cam["colors"])
+
+    # operator by operator
+    amap_a = P.AtlasMap.from_numpy(atlas_np)
+    dk, c_dk, _ = ops.deskew_constant_twist(pts, t, w, t0, t1, xi, 1.0, "GC-RIGHT-01", "a")
+    batch, c_sf, _ = P.extract_lidar_surfels(dk.points, dk.timestamps, dk.weights, None, base())
+    amap_a, _, _, inf = P.primitive_map_recency_inflate(amap_a, active, 21)
+    view = P.extract_atlas_map_view(amap_a, active, 1024)
+    assoc, c_as, e_as = P.associate_primitives_ot(batch, view, P.AssociationConfig(scan_seq=21))
+    vpe, c_pe, _ = P.visual_pose_evidence(assoc, batch, view, pose, z_lin_pose=pose)
+    res, c_mu, _ = P.map_update_step12b(amap_a, batch, assoc, active, pose, 21, t1, inflate_stats=inf)
+    # fused
+    amap_b = P.AtlasMap.from_numpy(atlas_np)
+    out = P.lidar_evidence_primitives(pts, t, w, t0, t1, xi, amap_b, active, pose, 21, base_batch=base())
+    f_dk, f_cdk, _ = out["deskew"]
+    f_batch, f_csf, _ = out["surfels"]
+    f_assoc, f_cas, f_eas = out["association"]
+    f_vpe, f_cpe, _ = out["pose_evidence"]
+    f_res, f_cmu, _ = out["map_update"]
+    assert torch.equal(f_dk.points, dk.points) and f_cdk.support.support_frac == c_dk.support.support_frac
+    assert f_batch.n_lidar_valid == batch.n_lidar_valid and torch.equal(f_batch.Lambdas, batch.Lambdas)
+    assert f_csf.support.ess_total == c_sf.support.ess_total
+    assert out["map_view"].n_valid == view.n_valid and torch.equal(out["map_view"].candidate_slots, view.candidate_slots)
+    assert torch.equal(f_assoc.responsibilities, assoc.responsibilities)
+    assert torch.equal(f_assoc.candidate_pool_indices, assoc.candidate_pool_indices)
+    assert f_cas.ot.transport_mass_total == c_as.ot.transport_mass_total and f_eas.predicted == e_as.predicted
+    assert torch.equal(f_vpe.L_pose, vpe.L_pose) and torch.equal(f_vpe.h_pose, vpe.h_pose)
+    assert f_cpe.support.ess_total == c_pe.support.ess_total
+    assert (f_res.n_fused, f_res.n_inserted, f_res.n_culled) == (res.n_fused, res.n_inserted, res.n_culled)
+    assert torch.equal(f_res.new_ids, res.new_ids) and amap_b.next_global_id == amap_a.next_global_id
+    assert f_cmu.map_update.fused_mass_total == c_mu.map_update.fused_mass_total
+    assert f_cmu.map_update.staleness_inflation_strength == c_mu.map_update.staleness_inflation_strength
+    for name in amap_a.fields:
+        assert torch.equal(amap_a.fields[name], amap_b.fields[name]), name
+    # the fused call counts two host synchronisations (first operator of each group), the operators seven
+    syncs = lambda cs: sum(c.compute.device_runtime.host_sync_count_est for c in cs)
+    assert syncs([c_dk, c_sf, c_as, c_pe, c_mu]) == 5 and syncs([f_cdk, f_csf, f_cas, f_cpe, f_cmu]) == 2
+
+    # empty map: association / pose evidence take the reference's early exits inside the fused call too
+    amap_e = P.create_empty_atlas_map(m_tile=2048, n_tiles_cap=8)
+    out_e = P.lidar_evidence_primitives(pts, t, w, t0, t1, xi, amap_e, active, pose, 1,
+                                        surfel_config=P.SurfelExtractionConfig(n_surfel=128, n_feat=16), m_tile_view=64,
+                                        map_update_kwargs=dict(k_insert_tile=16))
+    a_e, c_e, _ = out_e["association"]
+    assert c_e.exact and float(a_e.responsibilities.abs().sum().item()) == 0.0
+    assert out_e["pose_evidence"][1].exact and len(amap_e.tiles) == 7 and out_e["map_update"][0].n_inserted > 0
