@@ -69,6 +69,8 @@ class Pc2Layout(C.Structure):
 
 
 PC_N_NONFINITE, PC_TIME_RESCALED, PC_NCERT = 0, 1, 4
+HB = dict(FLOOR_ADJUSTMENT=0, SPREAD_PROXY=1, PSD_PROJECTION_DELTA=2, PSD_SYM_DELTA=3, PSD_EIG_MIN=4, PSD_EIG_MAX=5,
+          PSD_COND=6, PSD_NEAR_NULL=7, NCERT=8)
 IMU_NPARAM, IMU_NOUT = 16, 40
 IMU_OFF = dict(delta_pose=(0, 6), delta_R=(6, 15), delta_p=(15, 18), delta_v=(18, 21), ess=(21, 22), a_body_mean=(22, 25),
                a_world_nog_mean=(25, 28), a_world_mean=(28, 31), dt_eff_sum=(31, 32), xi_body=(32, 38))
@@ -88,6 +90,7 @@ PROTOTYPES = {
     "gcs_parse_pointcloud2_vlp16": (_int, [_vp, _vp, _vp, _int, _i64, C.POINTER(Pc2Layout), _vp, C.POINTER(_dbl), C.POINTER(_dbl),
                                            _vp, _vp, _vp, _vp, _vp, _vp]),
     "gcs_imu_scan_twist": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _vp, _vp, _vp]),
+    "gcs_hypothesis_barycenter": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gcs_point_budget_resample": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gcs_deskew_constant_twist": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_dbl), _dbl, _dbl, _vp, _vp, _vp]),
     "gcs_ray_directions": (_int, [_vp, _vp, _vp, _i64, C.POINTER(_dbl), _dbl, _vp]),

@@ -1,0 +1,277 @@
+// gcs_hypothesis.cu -- the step behind the per-hypothesis LiDAR evidence: combine K
+// hypotheses' posterior information (L_k, h_k, z_lin_k) into one on the device, so that 64 hypotheses evaluated on the
+// GPU(s) need no per-hypothesis host round trip.
+//   _hypothesis_barycenter_core      fl/backend/operators/hypothesis.py:51-115
+//   domain_projection_psd_core       fl/common/primitives.py:80-123   (D x D, D = 22: symmetrise, eigh, clamp, rebuild)
+//   spd_cholesky_solve_lifted_core   fl/common/primitives.py:141-165  (means of the hypotheses for the spread proxy)
+//
+// One CTA.  The symmetric eigenproblem runs as a parallel-ordered cyclic Jacobi iteration in shared memory: the D/2
+// disjoint (p, q) pairs of a round-robin step get their rotations from the current matrix, then all threads apply the
+// column rotations (A <- A J, V <- V J) and the row rotations (A <- J^T A); D - 1 steps make a sweep, a fixed number
+// of sweeps (quadratic convergence; 12 is ample for D <= 32) keeps the result bit-identical run to run.  The rebuilt
+// matrix V max(lambda, eps) V^T does not depend on the eigenvalue order.  The K lifted Cholesky solves run one warp
+// per hypothesis (lane = row).
+#include "gcs_common.cuh"
+
+namespace gcs {
+
+namespace {
+
+constexpr int kHbThreads = 256;
+constexpr int kHbMaxD = 32;
+constexpr int kHbLd = kHbMaxD + 1;   // padded leading dimension (bank conflicts)
+constexpr int kHbSweeps = 12;
+
+struct HbParams {
+  const double* L; const double* h; const double* z; const double* w;
+  int K, D;
+  double floor, eps_psd, eps_lift;
+  double* L_out; double* h_out; double* z_out; double* wn_out; double* means; double* cert;
+};
+
+// round-robin tournament on n (even) players: step s in [0, n-1), pair t in [0, n/2) -> (p, q)
+__device__ __forceinline__ void rr_pair(int n, int s, int t, int& p, int& q) {
+  const int m = n - 1;
+  int a = (t == 0) ? m : (s + t) % m;
+  int b = (s + m - t) % m;
+  p = a < b ? a : b;
+  q = a < b ? b : a;
+}
+
+__global__ void __launch_bounds__(kHbThreads) hypothesis_barycenter_kernel(const HbParams P) {
+  __shared__ double A[kHbMaxD * kHbLd], V[kHbMaxD * kHbLd], S[kHbMaxD * kHbLd];
+  __shared__ double rc[kHbMaxD / 2], rs[kHbMaxD / 2];
+  __shared__ int rp[kHbMaxD / 2], rq[kHbMaxD / 2];
+  __shared__ double sred[kHbThreads];
+  __shared__ double s_wsum, s_floor_adj;
+  const int tid = threadIdx.x, D = P.D, K = P.K;
+
+  // ---- weights: floor, renormalise (hypothesis.py:83-88)
+  if (tid == 0) {
+    double sum = 0.0, adj = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const double wf = fmax(P.w[k], P.floor);
+      adj += fabs(wf - P.w[k]);
+      sum += wf;
+    }
+    s_wsum = sum; s_floor_adj = adj;
+  }
+  __syncthreads();
+  for (int k = tid; k < K; k += kHbThreads) P.wn_out[k] = fmax(P.w[k], P.floor) / s_wsum;
+  __syncthreads();   // wn_out is re-read below by other threads of this CTA (global memory, same block: visible after the barrier)
+
+  // ---- barycenter in information form (:90-97), hypotheses summed in index order
+  for (int e = tid; e < D * D; e += kHbThreads) {
+    double acc = 0.0;
+    for (int k = 0; k < K; ++k) acc += P.wn_out[k] * P.L[(int64_t)k * D * D + e];
+    A[(e / D) * kHbLd + (e % D)] = acc;
+  }
+  for (int e = tid; e < D; e += kHbThreads) {
+    double ah = 0.0, az = 0.0;
+    for (int k = 0; k < K; ++k) {
+      ah += P.wn_out[k] * P.h[(int64_t)k * D + e];
+      if (P.z) az += P.wn_out[k] * P.z[(int64_t)k * D + e];
+    }
+    P.h_out[e] = ah;
+    if (P.z_out) P.z_out[e] = az;
+  }
+  __syncthreads();
+
+  // ---- DomainProjectionPSD: symmetrise
+  double part = 0.0;
+  for (int e = tid; e < D * D; e += kHbThreads) {
+    const int i = e / D, j = e % D;
+    const double m = 0.5 * (A[i * kHbLd + j] + A[j * kHbLd + i]);
+    const double d = m - A[i * kHbLd + j];
+    part += d * d;
+    S[i * kHbLd + j] = m;
+    V[i * kHbLd + j] = (i == j) ? 1.0 : 0.0;
+  }
+  sred[tid] = part;
+  __syncthreads();
+  double sym_delta = 0.0;
+  if (tid == 0) {
+    for (int t = 0; t < kHbThreads; ++t) sym_delta += sred[t];
+    sym_delta = sqrt(sym_delta);
+  }
+  for (int e = tid; e < D * D; e += kHbThreads) A[(e / D) * kHbLd + (e % D)] = S[(e / D) * kHbLd + (e % D)];
+  __syncthreads();
+
+  // ---- parallel-ordered cyclic Jacobi
+  const int n = (D + 1) & ~1;      // players (a dummy one when D is odd)
+  const int half = n / 2;
+  for (int sweep = 0; sweep < kHbSweeps; ++sweep) {
+    for (int s = 0; s < n - 1; ++s) {
+      if (tid < half) {
+        int p, q;
+        rr_pair(n, s, tid, p, q);
+        double c = 1.0, sn = 0.0;
+        if (q < D) {
+          const double apq = A[p * kHbLd + q];
+          if (apq != 0.0) {
+            const double app = A[p * kHbLd + p], aqq = A[q * kHbLd + q];
+            const double theta = (aqq - app) / (2.0 * apq);
+            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            c = 1.0 / sqrt(t * t + 1.0);
+            sn = t * c;
+            if (!(fabs(theta) < 1e300)) { c = 1.0; sn = 0.0; }   // apq negligible against the diagonal gap
+          }
+        } else {
+          q = p;   // pair with the dummy player: identity
+        }
+        rp[tid] = p; rq[tid] = q; rc[tid] = c; rs[tid] = sn;
+      }
+      __syncthreads();
+      // columns: A <- A J, V <- V J   (one thread per (row, pair))
+      for (int e = tid; e < D * half; e += kHbThreads) {
+        const int i = e / half, t = e - i * half;
+        const int p = rp[t], q = rq[t];
+        if (p != q) {
+          const double c = rc[t], sn = rs[t];
+          const double aip = A[i * kHbLd + p], aiq = A[i * kHbLd + q];
+          A[i * kHbLd + p] = c * aip - sn * aiq;
+          A[i * kHbLd + q] = sn * aip + c * aiq;
+          const double vip = V[i * kHbLd + p], viq = V[i * kHbLd + q];
+          V[i * kHbLd + p] = c * vip - sn * viq;
+          V[i * kHbLd + q] = sn * vip + c * viq;
+        }
+      }
+      __syncthreads();
+      // rows: A <- J^T A
+      for (int e = tid; e < D * half; e += kHbThreads) {
+        const int j = e / half, t = e - j * half;
+        const int p = rp[t], q = rq[t];
+        if (p != q) {
+          const double c = rc[t], sn = rs[t];
+          const double apj = A[p * kHbLd + j], aqj = A[q * kHbLd + j];
+          A[p * kHbLd + j] = c * apj - sn * aqj;
+          A[q * kHbLd + j] = sn * apj + c * aqj;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- clamp, rebuild, certificate (primitives.py:104-121)
+  part = 0.0;
+  for (int e = tid; e < D * D; e += kHbThreads) {
+    const int i = e / D, j = e % D;
+    double acc = 0.0;
+    for (int m = 0; m < D; ++m) acc += V[i * kHbLd + m] * fmax(A[m * kHbLd + m], P.eps_psd) * V[j * kHbLd + m];
+    P.L_out[e] = acc;
+    const double d = acc - S[i * kHbLd + j];
+    part += d * d;
+  }
+  sred[tid] = part;
+  __syncthreads();
+  if (tid == 0) {
+    double pd = 0.0;
+    for (int t = 0; t < kHbThreads; ++t) pd += sred[t];
+    double emin = 1e300, emax = -1e300, nn = 0.0;
+    for (int m = 0; m < D; ++m) {
+      const double v = fmax(A[m * kHbLd + m], P.eps_psd);
+      emin = fmin(emin, v); emax = fmax(emax, v);
+      nn += (v < 10.0 * P.eps_psd) ? 1.0 : 0.0;
+    }
+    P.cert[GCS_HB_FLOOR_ADJUSTMENT] = s_floor_adj;
+    P.cert[GCS_HB_PSD_PROJECTION_DELTA] = sqrt(pd);
+    P.cert[GCS_HB_PSD_SYM_DELTA] = sym_delta;
+    P.cert[GCS_HB_PSD_EIG_MIN] = emin;
+    P.cert[GCS_HB_PSD_EIG_MAX] = emax;
+    P.cert[GCS_HB_PSD_COND] = emax / emin;
+    P.cert[GCS_HB_PSD_NEAR_NULL] = nn;
+  }
+  __syncthreads();
+
+  // ---- means of the hypotheses: (L_k + eps_lift I) mu_k = h_k by Cholesky, one warp per hypothesis (:101-105)
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp < 3) {
+      double* Cw = warp == 0 ? A : (warp == 1 ? V : S);   // the eigen buffers are free now
+      for (int k = warp; k < K; k += 3) {
+        const double* Lk = P.L + (int64_t)k * D * D;
+        if (lane < D)
+          for (int j = 0; j <= lane; ++j)   // jnp.linalg.cholesky symmetrises its input (symmetrize_input=True)
+            Cw[lane * kHbLd + j] = 0.5 * (Lk[lane * D + j] + Lk[j * D + lane]) + (j == lane ? P.eps_lift : 0.0);
+        __syncwarp();
+        for (int j = 0; j < D; ++j) {
+          if (lane == j) {
+            double d = Cw[j * kHbLd + j];
+            for (int m = 0; m < j; ++m) d -= Cw[j * kHbLd + m] * Cw[j * kHbLd + m];
+            Cw[j * kHbLd + j] = sqrt(d);
+          }
+          __syncwarp();
+          if (lane > j && lane < D) {
+            double v = Cw[lane * kHbLd + j];
+            for (int m = 0; m < j; ++m) v -= Cw[lane * kHbLd + m] * Cw[j * kHbLd + m];
+            Cw[lane * kHbLd + j] = v / Cw[j * kHbLd + j];
+          }
+          __syncwarp();
+        }
+        if (lane == 0) {
+          double y[kHbMaxD];
+          for (int i = 0; i < D; ++i) {
+            double v = P.h[(int64_t)k * D + i];
+            for (int m = 0; m < i; ++m) v -= Cw[i * kHbLd + m] * y[m];
+            y[i] = v / Cw[i * kHbLd + i];
+          }
+          for (int i = D - 1; i >= 0; --i) {
+            double v = y[i];
+            for (int m = i + 1; m < D; ++m) v -= Cw[m * kHbLd + i] * y[m];
+            y[i] = v / Cw[i * kHbLd + i];
+          }
+          for (int i = 0; i < D; ++i) P.means[(int64_t)k * D + i] = y[i];
+        }
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- spread proxy: sum_k w_k |mu_k - sum_j w_j mu_j|^2 (:107-113)
+  if (tid < D) {
+    double m = 0.0;
+    for (int k = 0; k < K; ++k) m += P.wn_out[k] * P.means[(int64_t)k * D + tid];
+    sred[tid] = m;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double spread = 0.0;
+    for (int k = 0; k < K; ++k) {
+      double dsq = 0.0;
+      for (int i = 0; i < D; ++i) {
+        const double d = P.means[(int64_t)k * D + i] - sred[i];
+        dsq += d * d;
+      }
+      spread += P.wn_out[k] * dsq;
+    }
+    P.cert[GCS_HB_SPREAD_PROXY] = spread;
+  }
+}
+
+}  // namespace
+
+}  // namespace gcs
+
+using namespace gcs;
+
+extern "C" int gcs_hypothesis_barycenter(gcs_ctx* ctx, void* stream, const double* L_stack, const double* h_stack,
+                                         const double* z_lin_stack, const double* weights, int n_hyp, int dim,
+                                         double weight_floor, double eps_psd, double eps_lift, double* L_out, double* h_out,
+                                         double* z_lin_out, double* weights_norm_out, double* means_out, double* cert) {
+  if (!ctx) return GCS_EINVAL;
+  GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  GCS_REQUIRE(ctx, L_stack && h_stack && weights, "gcs_hypothesis_barycenter: L_stack / h_stack / weights are NULL");
+  GCS_REQUIRE(ctx, L_out && h_out && weights_norm_out && means_out && cert, "gcs_hypothesis_barycenter: an output is NULL");
+  GCS_REQUIRE(ctx, n_hyp >= 1, "gcs_hypothesis_barycenter: need at least one hypothesis (got %d)", n_hyp);
+  GCS_REQUIRE(ctx, dim >= 1 && dim <= kHbMaxD, "gcs_hypothesis_barycenter: dimension %d outside [1, %d]", dim, kHbMaxD);
+  GCS_REQUIRE(ctx, (z_lin_stack == nullptr) == (z_lin_out == nullptr),
+              "gcs_hypothesis_barycenter: z_lin_stack and z_lin_out must both be set or both NULL");
+  HbParams P;
+  P.L = L_stack; P.h = h_stack; P.z = z_lin_stack; P.w = weights; P.K = n_hyp; P.D = dim;
+  P.floor = weight_floor; P.eps_psd = eps_psd; P.eps_lift = eps_lift;
+  P.L_out = L_out; P.h_out = h_out; P.z_out = z_lin_out; P.wn_out = weights_norm_out; P.means = means_out; P.cert = cert;
+  hypothesis_barycenter_kernel<<<1, kHbThreads, 0, (cudaStream_t)stream>>>(P);
+  GCS_LAUNCH_CHECK(ctx);
+  return GCS_OK;
+}

@@ -17,6 +17,7 @@ ENTRY_POINTS = {
     "domain_projection_psd": "gcs_common.cuh:psd_project3",
     "pointcloud2_ingest": "gcs_parse_pointcloud2_vlp16",
     "imu_preintegration": "gcs_imu_scan_twist",
+    "hypothesis_combine": "gcs_hypothesis_barycenter",
     "point_budget": "gcs_point_budget_resample",
     "deskew": "gcs_deskew_constant_twist",
     "bin_soft_assign": "gcs_bin_soft_assign",

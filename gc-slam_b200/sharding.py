@@ -106,3 +106,79 @@ def hypothesis_barycenter(L_stack, h_stack, weights, weight_floor: float = 0.002
     vals, vecs = np.linalg.eigh(Ls)
     L = vecs @ np.diag(np.maximum(vals, eps_psd)) @ vecs.T
     return L, h, w, floor_adjustment
+
+
+# --------------------------------------------------------------------------------------------------
+# device-side combine: no per-hypothesis host round trip
+# --------------------------------------------------------------------------------------------------
+class HypothesisProjectionResult:
+    """Result of hypothesis_barycenter_projection: the fused information pair on the device (fields of the reference's
+    belief_out that this path produces) and the weight-floor adjustment."""
+
+    def __init__(self, L, h, z_lin, weights_normalized, means, floor_adjustment):
+        self.L, self.h, self.z_lin = L, h, z_lin
+        self.weights_normalized, self.means = weights_normalized, means
+        self.floor_adjustment = float(floor_adjustment)
+
+
+def hypothesis_barycenter_projection(L_stack, h_stack, weights, z_lin_stack=None, K_HYP: int = None,
+                                     HYP_WEIGHT_FLOOR: float = 0.0025, eps_psd: float = 1e-12, eps_lift: float = 1e-9,
+                                     anchor_id: str = "hypothesis_barycenter"):
+    """
+    HypothesisBarycenterProjection (fl/backend/operators/hypothesis.py:123-236) on stacked arrays that may already live on
+    the device -- e.g. BinEvidenceBatch.L22 / h22 of a 64-hypothesis plan, or the all-gathered stacks of gather_evidence():
+    weight floor + renormalisation, barycenter in information form, PSD projection, spread proxy; one kernel
+    (gcs_hypothesis_barycenter), one certificate read-back.  Returns (result, CertBundle, ExpectedEffect) with the
+    reference's triggers and certificate fields.  A list of belief-like objects (attributes L, h, z_lin) is accepted in
+    place of L_stack, as the reference passes it.
+    """
+    import ctypes as C
+
+    import torch
+
+    from . import _lib as L
+    from .certs import CertBundle, ConditioningCert, ExpectedEffect, InfluenceCert, SupportCert
+    from .operators import _IO
+
+    if isinstance(L_stack, (list, tuple)) and hasattr(L_stack[0], "L"):
+        hyps = L_stack
+        anchor_id = getattr(hyps[0], "anchor_id", anchor_id)
+        as_t = lambda v: v if isinstance(v, torch.Tensor) else torch.as_tensor(np.asarray(v, dtype=np.float64))
+        z_lin_stack = torch.stack([as_t(b.z_lin) for b in hyps]) if hasattr(hyps[0], "z_lin") else None
+        h_stack = torch.stack([as_t(b.h) for b in hyps])
+        L_stack = torch.stack([as_t(b.L) for b in hyps])
+    io = _IO()
+    Ls = io.dev_in(L_stack)
+    if Ls.dim() != 3 or Ls.shape[1] != Ls.shape[2]:
+        raise ValueError(f"L_stack must be (K, D, D), got {tuple(Ls.shape)}")
+    K, D = int(Ls.shape[0]), int(Ls.shape[1])
+    if K_HYP is not None and K != int(K_HYP):
+        raise ValueError(f"Expected {K_HYP} hypotheses, got {K}")
+    hs = io.dev_in(h_stack)
+    w = io.dev_in(weights).reshape(-1)
+    if tuple(hs.shape) != (K, D):
+        raise ValueError(f"h_stack must be ({K}, {D}), got {tuple(hs.shape)}")
+    if tuple(w.shape) != (K,):
+        raise ValueError(f"Expected weights shape ({K},), got {tuple(w.shape)}")
+    zs = io.dev_in(z_lin_stack) if z_lin_stack is not None else None
+    if zs is not None and tuple(zs.shape) != (K, D):
+        raise ValueError(f"z_lin_stack must be ({K}, {D}), got {tuple(zs.shape)}")
+    L_out, h_out, wn, means, cert_d = io.empty(D, D), io.empty(D), io.empty(K), io.empty(K, D), io.zeros(L.HB["NCERT"])
+    z_out = io.empty(D) if zs is not None else None
+    io.ctx.check(io.ctx.lib.gcs_hypothesis_barycenter(io.ctx.handle, io.stream(), L.ptr(Ls), L.ptr(hs), L.ptr(zs), L.ptr(w), K, D,
+                                                      float(HYP_WEIGHT_FLOOR), float(eps_psd), float(eps_lift), L.ptr(L_out),
+                                                      L.ptr(h_out), L.ptr(z_out), L.ptr(wn), L.ptr(means), L.ptr(cert_d)))
+    c = io.host(torch.cat([cert_d, wn]))
+    cs, wn_h = c[:L.HB["NCERT"]], c[L.HB["NCERT"]:]
+    cert = CertBundle.create_approx(
+        chart_id="GC-RIGHT-01", anchor_id=anchor_id, triggers=["HypothesisProjection", "I-projection-info-barycenter"],
+        conditioning=ConditioningCert(eig_min=float(cs[L.HB["PSD_EIG_MIN"]]), eig_max=float(cs[L.HB["PSD_EIG_MAX"]]),
+                                      cond=float(cs[L.HB["PSD_COND"]]), near_null_count=int(cs[L.HB["PSD_NEAR_NULL"]])),
+        support=SupportCert(ess_total=float(1.0 / np.sum(wn_h ** 2)),
+                            support_frac=float(np.sum(wn_h > HYP_WEIGHT_FLOOR) / K)),
+        influence=InfluenceCert.identity().with_overrides(psd_projection_delta=float(cs[L.HB["PSD_PROJECTION_DELTA"]]),
+                                                          mass_epsilon_ratio=float(cs[L.HB["FLOOR_ADJUSTMENT"]]) / K),
+        compute=io.compute())
+    result = HypothesisProjectionResult(L_out, h_out, z_out, wn, means, cs[L.HB["FLOOR_ADJUSTMENT"]])
+    _ = C
+    return result, cert, ExpectedEffect("predicted_projection_spread_proxy", float(cs[L.HB["SPREAD_PROXY"]]), None)

@@ -313,3 +313,32 @@ def imu_hypothesis_params(n_hyp: int, seed: int):
     rng = np.random.default_rng(seed)
     return dict(rotvec0=rng.uniform(-0.6, 0.6, (n_hyp, 3)), gyro_bias=rng.normal(0.0, 0.01, (n_hyp, 3)),
                 accel_bias=rng.normal(0.0, 0.05, (n_hyp, 3)), sigma=rng.uniform(0.01, 0.03, n_hyp))
+
+
+def hypothesis_evidence_stack(n_hyp: int, dim: int, seed: int, indefinite: bool = False):
+    """
+    K posterior information pairs (L_k, h_k), linearisation points and hypothesis weights as the combine receives them
+    (backend_node.py:2036-2097): SPD information matrices with eigenvalues over nine decades (pose blocks strong, bias /
+    extrinsic blocks weak), means scattered around a common state.  `indefinite`: nearly singular matrices (eigenvalues
+    down to 1e-15, below eps_psd, so that the projection clamps), one asymmetric input and weights under the floor.
+    """
+    rng = np.random.default_rng(seed)
+    Ls, hs, zs = [], [], []
+    mu0 = rng.normal(0.0, 1.0, dim)
+    for k in range(n_hyp):
+        Q, _ = np.linalg.qr(rng.normal(size=(dim, dim)))
+        ev = 10.0 ** rng.uniform(-3.0, 6.0, dim)
+        if indefinite:
+            ev[:3] = 10.0 ** rng.uniform(-15.0, -13.0, 3)
+            Q = np.linalg.qr(np.random.default_rng(seed + 1000).normal(size=(dim, dim)))[0]   # shared weak directions
+        L = (Q * ev) @ Q.T
+        L = 0.5 * (L + L.T)
+        if indefinite and k == 2:
+            L[0, 1] += 1e-11         # asymmetric input: sym_delta > 0, still positive definite once lifted
+        mu = mu0 + rng.normal(0.0, 0.05, dim)
+        Ls.append(L); hs.append(L @ mu); zs.append(mu0 + rng.normal(0.0, 0.01, dim))
+    w = rng.dirichlet(np.ones(n_hyp))
+    if indefinite:
+        w[0] = 1e-4
+        w[-1] = 0.0
+    return np.stack(Ls), np.stack(hs), np.stack(zs), w

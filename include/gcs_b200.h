@@ -100,6 +100,21 @@ int gcs_imu_scan_twist(gcs_ctx* ctx, void* stream, const double* stamps /*dev (M
                        int n_hyp, double* out /*dev (n_hyp, GCS_IMU_NOUT)*/, double* xi_out /*dev (n_hyp,6) or NULL*/,
                        double* weights_out /*dev (n_hyp, M) or NULL*/);
 
+/* ---- (8f-3) hypothesis combine : fl/backend/operators/hypothesis.py:51-115 (_hypothesis_barycenter_core) with
+ * domain_projection_psd_core / spd_cholesky_solve_lifted_core (fl/common/primitives.py:80-123, 141-165).
+ * K information pairs (L_k (D,D), h_k (D)) + linearisation points + weights -> floored, renormalised weights, their
+ * barycenter in information form, PSD projection of the barycenter (symmetrise, eigendecompose, clamp at eps_psd,
+ * rebuild), and the spread proxy sum_k w_k |mu_k - mean mu|^2 with mu_k = (L_k + eps_lift I)^-1 h_k.  D <= 32 (the
+ * reference state has D_Z = 22).  means_out (K, D) doubles as the scratch the spread needs.                          */
+enum { GCS_HB_FLOOR_ADJUSTMENT = 0, GCS_HB_SPREAD_PROXY, GCS_HB_PSD_PROJECTION_DELTA, GCS_HB_PSD_SYM_DELTA,
+       GCS_HB_PSD_EIG_MIN, GCS_HB_PSD_EIG_MAX, GCS_HB_PSD_COND, GCS_HB_PSD_NEAR_NULL, GCS_HB_NCERT = 8 };
+int gcs_hypothesis_barycenter(gcs_ctx* ctx, void* stream, const double* L_stack /*dev (K,D,D)*/, const double* h_stack /*dev (K,D)*/,
+                              const double* z_lin_stack /*dev (K,D) or NULL*/, const double* weights /*dev (K)*/, int n_hyp,
+                              int dim, double weight_floor, double eps_psd, double eps_lift, double* L_out /*dev (D,D)*/,
+                              double* h_out /*dev (D)*/, double* z_lin_out /*dev (D) or NULL*/,
+                              double* weights_norm_out /*dev (K)*/, double* means_out /*dev (K,D)*/,
+                              double* cert /*dev (GCS_HB_NCERT)*/);
+
 /* ---- a1 PointBudgetResample : fl/backend/operators/point_budget.py:50-109,117-221 --------------------- */
 enum { GCS_RS_MASS_IN = 0, GCS_RS_MASS_SEL, GCS_RS_SUMSQ_SEL, GCS_RS_ESS, GCS_RS_MASS_SCALE, GCS_RS_NCERT = 8 };
 int gcs_point_budget_resample(gcs_ctx* ctx, void* stream,

@@ -145,6 +145,17 @@ def _ns_wrap(mod, names=None):
 linalg = _ns_wrap(_np.linalg)
 
 
+def _cholesky(a, symmetrize_input=True, **_k):
+    """jnp.linalg.cholesky symmetrises its input by default (symmetrize_input=True); NumPy reads the lower triangle."""
+    a = _np.asarray(a)
+    if symmetrize_input:
+        a = 0.5 * (a + _np.swapaxes(a, -1, -2))
+    return _wrap(_np.linalg.cholesky(a))
+
+
+linalg.cholesky = _cholesky
+
+
 def __getattr__(name):
     obj = getattr(_np, name)
     if callable(obj) and not isinstance(obj, type):
