@@ -290,6 +290,50 @@ def primitive_path_extra(n_points, n_map=1_000_000, reps=10):
                     "the whole path through lidar_evidence_primitives (two host syncs), which scans_per_s is quoted on"}
 
 
+def prologue_combine_extra(n_hyp=64, reps=30):
+    """SURVEY 8f rows 2 and 3 beside the path: IMU scan-twist prologue and device-side hypothesis combine, K = 64."""
+    import torch
+    from gc_slam_b200 import imu, sharding, synth
+    from oracle import hypothesis as oh
+    from oracle import imu as oimu
+
+    stamps, gyro, accel = synth.imu_window(512, 40, 12, t_start=synth.EPOCH_T0)
+    hp = synth.imu_hypothesis_params(n_hyp, 13)
+    t0, t1 = synth.EPOCH_T0, synth.EPOCH_T0 + 0.1
+    g = np.array([0.0, 0.0, -9.81])
+    dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (stamps, gyro, accel)]
+    Ls, hs, zs, w = synth.hypothesis_evidence_stack(n_hyp, 22, 5)
+    Ld, hd, zd, wd = [torch.from_numpy(a).cuda() for a in (Ls, hs, zs, w)]
+
+    def wall(fn):
+        ts = []
+        for r in range(reps + 3):
+            torch.cuda.synchronize()
+            a = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            if r >= 3:
+                ts.append(time.perf_counter() - a)
+        return 1e3 * float(np.median(ts))
+
+    ms_imu = wall(lambda: imu.imu_scan_twist(dev[0], dev[1], dev[2], t0, t1, hp["sigma"], hp["rotvec0"], hp["gyro_bias"],
+                                             hp["accel_bias"], g))
+    ms_hb = wall(lambda: sharding.hypothesis_barycenter_projection(Ld, hd, wd, zd))
+    a = time.perf_counter()
+    for h in range(4):
+        oimu.imu_scan_twist(stamps, gyro, accel, t0, t1, float(hp["sigma"][h]), hp["rotvec0"][h], hp["gyro_bias"][h],
+                            hp["accel_bias"][h], g)
+    cpu_imu = (time.perf_counter() - a) / 4 * n_hyp * 1e3
+    oh.hypothesis_barycenter(Ls, hs, zs, w)          # first call pays for importing scipy
+    a = time.perf_counter()
+    oh.hypothesis_barycenter(Ls, hs, zs, w)
+    cpu_hb = (time.perf_counter() - a) * 1e3
+    return {"n_hyp": n_hyp, "imu_scan_twist_ms": ms_imu, "imu_scan_twist_cpu_oracle_ms": cpu_imu,
+            "hypothesis_combine_ms": ms_hb, "hypothesis_combine_cpu_oracle_ms": cpu_hb,
+            "note": "wall clock per call incl. the host-side parameter upload and the certificate read-back; "
+                    "512 IMU samples, 22-D evidence blocks"}
+
+
 # ----------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------
@@ -520,9 +564,10 @@ def run_ours(args):
                    "L22_rel_diff": _rel(otc.L22, o64.L22)}
         del plan64
 
-    prim = None
+    prim = aux = None
     if rank == 0 and world == 1 and not args.no_prim:
         prim = primitive_path_extra(P)
+        aux = prologue_combine_extra()
     if rank == 0:
         peak, peak_src = measured_peaks()
         bytes_per_launch = S * (BYTES_IN_PER_PT * P + BYTES_OUT_PER_PT * P)
@@ -559,7 +604,7 @@ def run_ours(args):
                          "kernel_launches_timed": k_n, "kernel_share_of_step": k_ms / ms_total},
             "latency": lat,
             "points_per_s": value * P,
-            "extra": {"primitive_path": prim, "float64_path": f64_leg,
+            "extra": {"primitive_path": prim, "prologue_and_combine": aux, "float64_path": f64_leg,
                       "e2e_decoded_arrays": {"value": e2e_arrays, "unit": "scans/s", "h2d_bytes_per_step": int(moved["arrays"]),
                                              "input": "five decoded arrays (float64 points/stamps/weights, uint8 ring/tag), 42 B/point"}},
         }

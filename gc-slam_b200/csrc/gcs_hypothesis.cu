@@ -8,9 +8,10 @@
 // One CTA.  The symmetric eigenproblem runs as a parallel-ordered cyclic Jacobi iteration in shared memory: the D/2
 // disjoint (p, q) pairs of a round-robin step get their rotations from the current matrix, then all threads apply the
 // column rotations (A <- A J, V <- V J) and the row rotations (A <- J^T A); D - 1 steps make a sweep, a fixed number
-// of sweeps (quadratic convergence; 12 is ample for D <= 32) keeps the result bit-identical run to run.  The rebuilt
+// of sweeps bounded by 12, ended as soon as the off-diagonal mass drops below 1e-30 of the squared Frobenius norm
+// (quadratic convergence: 6-8 sweeps; the count depends on the data only, so reruns stay bit-identical).  The rebuilt
 // matrix V max(lambda, eps) V^T does not depend on the eigenvalue order.  The K lifted Cholesky solves run one warp
-// per hypothesis (lane = row).
+// per hypothesis (lane = row) in a kernel of their own, eight hypotheses per CTA, before the combine.
 #include "gcs_common.cuh"
 
 namespace gcs {
@@ -20,7 +21,9 @@ namespace {
 constexpr int kHbThreads = 256;
 constexpr int kHbMaxD = 32;
 constexpr int kHbLd = kHbMaxD + 1;   // padded leading dimension (bank conflicts)
-constexpr int kHbSweeps = 12;
+constexpr int kHbSweeps = 12;        // upper bound; the iteration stops when the off-diagonal mass is below float64 resolution
+constexpr int kHbCholWarps = kHbThreads / 32;
+constexpr size_t kHbDynBytes = (size_t)kHbCholWarps * kHbMaxD * kHbLd * sizeof(double);   // per-warp Cholesky buffers
 
 struct HbParams {
   const double* L; const double* h; const double* z; const double* w;
@@ -29,6 +32,18 @@ struct HbParams {
   double* L_out; double* h_out; double* z_out; double* wn_out; double* means; double* cert;
 };
 
+// fixed-order sum of one value per thread over the CTA (shuffle tree per warp, then over the warps); result in all threads
+__device__ __forceinline__ double hb_block_sum(double v, double* sred) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < kHbThreads / 32; ++w) t += sred[w];
+  return t;
+}
+
 // round-robin tournament on n (even) players: step s in [0, n-1), pair t in [0, n/2) -> (p, q)
 __device__ __forceinline__ void rr_pair(int n, int s, int t, int& p, int& q) {
   const int m = n - 1;
@@ -36,6 +51,49 @@ __device__ __forceinline__ void rr_pair(int n, int s, int t, int& p, int& q) {
   int b = (s + m - t) % m;
   p = a < b ? a : b;
   q = a < b ? b : a;
+}
+
+// Means of the hypotheses: (L_k + eps_lift I) mu_k = h_k by Cholesky (:101-105), one warp per hypothesis (lane = row),
+// eight hypotheses per CTA -- this part is independent of the barycenter and spreads over the SMs.
+__global__ void __launch_bounds__(kHbThreads) hypothesis_means_kernel(const HbParams P) {
+  extern __shared__ double chol_buf[];
+  const int tid = threadIdx.x, D = P.D, K = P.K;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int k = blockIdx.x * kHbCholWarps + warp;
+  if (k >= K) return;
+  double* Cw = chol_buf + (size_t)warp * kHbMaxD * kHbLd;
+  const double* Lk = P.L + (int64_t)k * D * D;
+  if (lane < D)
+    for (int j = 0; j <= lane; ++j)   // jnp.linalg.cholesky symmetrises its input (symmetrize_input=True)
+      Cw[lane * kHbLd + j] = 0.5 * (Lk[lane * D + j] + Lk[j * D + lane]) + (j == lane ? P.eps_lift : 0.0);
+  __syncwarp();
+  // right-looking factorisation: column j, then the rank-one update of the trailing rows (all lanes busy)
+  for (int j = 0; j < D; ++j) {
+    const double cjj = sqrt(Cw[j * kHbLd + j]);
+    __syncwarp();
+    double cij = 0.0;
+    if (lane == j) Cw[j * kHbLd + j] = cjj;
+    if (lane > j && lane < D) { cij = Cw[lane * kHbLd + j] / cjj; Cw[lane * kHbLd + j] = cij; }
+    __syncwarp();
+    if (lane > j && lane < D)
+      for (int m = j + 1; m <= lane; ++m) Cw[lane * kHbLd + m] -= cij * Cw[m * kHbLd + j];
+    __syncwarp();
+  }
+  // C y = h (forward), C^T mu = y (backward), column-oriented: the solved component is broadcast, every lane updates
+  double r = lane < D ? P.h[(int64_t)k * D + lane] : 0.0, y = 0.0;
+  for (int j = 0; j < D; ++j) {
+    const double yj = __shfl_sync(0xffffffffu, r, j) / Cw[j * kHbLd + j];
+    if (lane == j) y = yj;
+    if (lane > j && lane < D) r -= Cw[lane * kHbLd + j] * yj;
+  }
+  r = y;
+  double x = 0.0;
+  for (int j = D - 1; j >= 0; --j) {
+    const double xj = __shfl_sync(0xffffffffu, r, j) / Cw[j * kHbLd + j];
+    if (lane == j) x = xj;
+    if (lane < j) r -= Cw[j * kHbLd + lane] * xj;
+  }
+  if (lane < D) P.means[(int64_t)k * D + lane] = x;
 }
 
 __global__ void __launch_bounds__(kHbThreads) hypothesis_barycenter_kernel(const HbParams P) {
@@ -87,13 +145,7 @@ __global__ void __launch_bounds__(kHbThreads) hypothesis_barycenter_kernel(const
     S[i * kHbLd + j] = m;
     V[i * kHbLd + j] = (i == j) ? 1.0 : 0.0;
   }
-  sred[tid] = part;
-  __syncthreads();
-  double sym_delta = 0.0;
-  if (tid == 0) {
-    for (int t = 0; t < kHbThreads; ++t) sym_delta += sred[t];
-    sym_delta = sqrt(sym_delta);
-  }
+  const double sym_delta = sqrt(hb_block_sum(part, sred));
   for (int e = tid; e < D * D; e += kHbThreads) A[(e / D) * kHbLd + (e % D)] = S[(e / D) * kHbLd + (e % D)];
   __syncthreads();
 
@@ -101,6 +153,16 @@ __global__ void __launch_bounds__(kHbThreads) hypothesis_barycenter_kernel(const
   const int n = (D + 1) & ~1;      // players (a dummy one when D is odd)
   const int half = n / 2;
   for (int sweep = 0; sweep < kHbSweeps; ++sweep) {
+    // convergence: off-diagonal sum of squares against the squared Frobenius norm (fixed-order reduction)
+    double off = 0.0, fro = 0.0;
+    for (int e = tid; e < D * D; e += kHbThreads) {
+      const int i = e / D, j = e % D;
+      const double v = A[i * kHbLd + j];
+      fro += v * v;
+      if (i != j) off += v * v;
+    }
+    const double off_sum = hb_block_sum(off, sred), fro_sum = hb_block_sum(fro, sred);
+    if (off_sum <= 1e-30 * fro_sum) break;
     for (int s = 0; s < n - 1; ++s) {
       if (tid < half) {
         int p, q;
@@ -162,11 +224,8 @@ __global__ void __launch_bounds__(kHbThreads) hypothesis_barycenter_kernel(const
     const double d = acc - S[i * kHbLd + j];
     part += d * d;
   }
-  sred[tid] = part;
-  __syncthreads();
+  const double pd = hb_block_sum(part, sred);
   if (tid == 0) {
-    double pd = 0.0;
-    for (int t = 0; t < kHbThreads; ++t) pd += sred[t];
     double emin = 1e300, emax = -1e300, nn = 0.0;
     for (int m = 0; m < D; ++m) {
       const double v = fmax(A[m * kHbLd + m], P.eps_psd);
@@ -183,70 +242,25 @@ __global__ void __launch_bounds__(kHbThreads) hypothesis_barycenter_kernel(const
   }
   __syncthreads();
 
-  // ---- means of the hypotheses: (L_k + eps_lift I) mu_k = h_k by Cholesky, one warp per hypothesis (:101-105)
-  {
-    const int warp = tid >> 5, lane = tid & 31;
-    if (warp < 3) {
-      double* Cw = warp == 0 ? A : (warp == 1 ? V : S);   // the eigen buffers are free now
-      for (int k = warp; k < K; k += 3) {
-        const double* Lk = P.L + (int64_t)k * D * D;
-        if (lane < D)
-          for (int j = 0; j <= lane; ++j)   // jnp.linalg.cholesky symmetrises its input (symmetrize_input=True)
-            Cw[lane * kHbLd + j] = 0.5 * (Lk[lane * D + j] + Lk[j * D + lane]) + (j == lane ? P.eps_lift : 0.0);
-        __syncwarp();
-        for (int j = 0; j < D; ++j) {
-          if (lane == j) {
-            double d = Cw[j * kHbLd + j];
-            for (int m = 0; m < j; ++m) d -= Cw[j * kHbLd + m] * Cw[j * kHbLd + m];
-            Cw[j * kHbLd + j] = sqrt(d);
-          }
-          __syncwarp();
-          if (lane > j && lane < D) {
-            double v = Cw[lane * kHbLd + j];
-            for (int m = 0; m < j; ++m) v -= Cw[lane * kHbLd + m] * Cw[j * kHbLd + m];
-            Cw[lane * kHbLd + j] = v / Cw[j * kHbLd + j];
-          }
-          __syncwarp();
-        }
-        if (lane == 0) {
-          double y[kHbMaxD];
-          for (int i = 0; i < D; ++i) {
-            double v = P.h[(int64_t)k * D + i];
-            for (int m = 0; m < i; ++m) v -= Cw[i * kHbLd + m] * y[m];
-            y[i] = v / Cw[i * kHbLd + i];
-          }
-          for (int i = D - 1; i >= 0; --i) {
-            double v = y[i];
-            for (int m = i + 1; m < D; ++m) v -= Cw[m * kHbLd + i] * y[m];
-            y[i] = v / Cw[i * kHbLd + i];
-          }
-          for (int i = 0; i < D; ++i) P.means[(int64_t)k * D + i] = y[i];
-        }
-        __syncwarp();
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- spread proxy: sum_k w_k |mu_k - sum_j w_j mu_j|^2 (:107-113)
+  // ---- spread proxy: sum_k w_k |mu_k - sum_j w_j mu_j|^2 (:107-113); means come from hypothesis_means_kernel
+  __shared__ double mom[kHbMaxD];
   if (tid < D) {
     double m = 0.0;
     for (int k = 0; k < K; ++k) m += P.wn_out[k] * P.means[(int64_t)k * D + tid];
-    sred[tid] = m;
+    mom[tid] = m;
   }
   __syncthreads();
-  if (tid == 0) {
-    double spread = 0.0;
-    for (int k = 0; k < K; ++k) {
-      double dsq = 0.0;
-      for (int i = 0; i < D; ++i) {
-        const double d = P.means[(int64_t)k * D + i] - sred[i];
-        dsq += d * d;
-      }
-      spread += P.wn_out[k] * dsq;
+  double sp = 0.0;
+  for (int k = tid; k < K; k += kHbThreads) {
+    double dsq = 0.0;
+    for (int i = 0; i < D; ++i) {
+      const double d = P.means[(int64_t)k * D + i] - mom[i];
+      dsq += d * d;
     }
-    P.cert[GCS_HB_SPREAD_PROXY] = spread;
+    sp += P.wn_out[k] * dsq;
   }
+  const double spread = hb_block_sum(sp, sred);
+  if (tid == 0) P.cert[GCS_HB_SPREAD_PROXY] = spread;
 }
 
 }  // namespace
@@ -271,6 +285,14 @@ extern "C" int gcs_hypothesis_barycenter(gcs_ctx* ctx, void* stream, const doubl
   P.L = L_stack; P.h = h_stack; P.z = z_lin_stack; P.w = weights; P.K = n_hyp; P.D = dim;
   P.floor = weight_floor; P.eps_psd = eps_psd; P.eps_lift = eps_lift;
   P.L_out = L_out; P.h_out = h_out; P.z_out = z_lin_out; P.wn_out = weights_norm_out; P.means = means_out; P.cert = cert;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCS_CHECK_CUDA(ctx, cudaFuncSetAttribute(hypothesis_means_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kHbDynBytes));
+    attr_set = true;
+  }
+  hypothesis_means_kernel<<<(n_hyp + kHbCholWarps - 1) / kHbCholWarps, kHbThreads, kHbDynBytes, (cudaStream_t)stream>>>(P);
+  GCS_LAUNCH_CHECK(ctx);
   hypothesis_barycenter_kernel<<<1, kHbThreads, 0, (cudaStream_t)stream>>>(P);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
