@@ -234,40 +234,138 @@ __global__ void __launch_bounds__(128) assoc_prepare_kernel(gcs_meas_batch B, in
 }
 
 // one warp per measurement row: stream the candidate pool, keep the K best (cost, pool position) per lane, merge.
+// First K of the row-wise stable sort by cost over the 7 x 1024 candidate pool (primitive_association.py:367-376), one warp
+// per measurement, eight measurements per CTA.
+//   cost = |dp|^2 + beta * d_dir with d_dir in [0, 1], so |dp|^2 is a lower bound that costs five flops.  T is an upper
+//   bound of the row's K-th best (cost, j) (the K-th smallest of the lanes' current best entries: K distinct candidates
+//   at or before it); a candidate whose (bound, j) lies beyond (T, Tj) cannot be among the first K and is skipped --
+//   its three log / sinh / exp evaluations, or, for the many rows whose stencil misses the view (every cost 1e12, the
+//   first K offsets win), everything after the first few candidates.  The view tiles are staged in shared memory one at a time (positions and
+//   validity: 25 KB), every warp scans the staged tile if it is in its stencil, survivors are queued and evaluated 32
+//   at a time (all lanes busy), which leaves a few hundred of the 7,168 exact costs per row.  Ties keep the smaller
+//   j = stencil position * m_view + offset whatever the processing order, so the selection is the reference's.
 template <int K>
 __global__ void __launch_bounds__(256) assoc_topk_kernel(gcs_meas_batch B, int N, gcs_map_view V, int m_view, int n_st,
-                                                         AssocWs W, gcs_assoc_cfg cfg, gcs_assoc_result R) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= N) return;
-  const int i = warp;
-  const double mp[3] = {W.mpos[3 * i], W.mpos[3 * i + 1], W.mpos[3 * i + 2]};
-  const double md[3] = {W.mdir[3 * i], W.mdir[3 * i + 1], W.mdir[3 * i + 2]};
-  const double mk = W.mkap[i];
+                                                         int n_view_tiles, AssocWs W, gcs_assoc_cfg cfg, gcs_assoc_result R) {
+  extern __shared__ double tile_pos[];                       // (m_view, 3), then m_view validity bytes
+  uint8_t* tile_valid = reinterpret_cast<uint8_t*>(tile_pos + 3 * (size_t)m_view);
+  __shared__ int s_queue[8][64];
+  const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + wq;
+  const bool active = i < N;
+  const int ii = active ? i : 0;
+  const double mp[3] = {W.mpos[3 * ii], W.mpos[3 * ii + 1], W.mpos[3 * ii + 2]};
+  const double md[3] = {W.mdir[3 * ii], W.mdir[3 * ii + 1], W.mdir[3 * ii + 2]};
+  const double mk = W.mkap[ii];
   const double A_k1 = A_vmf(fmax(mk, 1e-12), 1e-12);
   double bc[K];
   int bj[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) { bc[k] = 1.0e300; bj[k] = 0x7fffffff; }
-  const int P = n_st * m_view;
-  for (int j = lane; j < P; j += 32) {
-    const int s = j / m_view, off = j - s * m_view;
-    const int tix = W.stencil[i * n_st + s];
-    const int v = (tix < 0 ? 0 : tix) * m_view + off;
-    double c = 1e12;
-    if (tix >= 0 && V.valid[v])
-      c = pair_cost(mp, md, mk, A_k1, V.positions + 3 * v, V.directions + 3 * v, V.kappas[v], cfg.beta);
-    // insertion into the lane-local sorted list (j increases, so equal costs keep the earlier j first)
-    if (c < bc[K - 1]) {
-      bc[K - 1] = c; bj[K - 1] = j;
+  int* queue = s_queue[wq];
+  int qn = 0;
+  double T = 1.0e300;   // (T, Tj): K distinct candidates at or before this (cost, j) are already held
+  int Tj = 0x7fffffff;
+  const bool prune = cfg.beta >= 0.0;
+  auto flush = [&](int n_take) {
+    if (lane < n_take) {
+      const int j = queue[lane];
+      const int s = j / m_view, off = j - s * m_view;
+      const int tix = W.stencil[ii * n_st + s];
+      const int v = (tix < 0 ? 0 : tix) * m_view + off;
+      double c = 1e12;
+      if (tix >= 0 && V.valid[v])
+        c = pair_cost(mp, md, mk, A_k1, V.positions + 3 * v, V.directions + 3 * v, V.kappas[v], cfg.beta);
+      if (c < bc[K - 1] || (c == bc[K - 1] && j < bj[K - 1])) {
+        bc[K - 1] = c; bj[K - 1] = j;
 #pragma unroll
-      for (int k = K - 1; k > 0; --k) {
-        if (bc[k] < bc[k - 1]) {
-          const double tc = bc[k]; bc[k] = bc[k - 1]; bc[k - 1] = tc;
-          const int tj = bj[k]; bj[k] = bj[k - 1]; bj[k - 1] = tj;
+        for (int k = K - 1; k > 0; --k) {
+          if (bc[k] < bc[k - 1] || (bc[k] == bc[k - 1] && bj[k] < bj[k - 1])) {
+            const double tc = bc[k]; bc[k] = bc[k - 1]; bc[k - 1] = tc;
+            const int tj = bj[k]; bj[k] = bj[k - 1]; bj[k - 1] = tj;
+          }
         }
       }
     }
+    // (T, Tj) = K-th smallest of the 32 lane heads in (cost, j) order (rank by counting; j is unique)
+    const double head = bc[0];
+    const int headj = bj[0];
+    int rank = 0;
+#pragma unroll
+    for (int o = 1; o < 32; ++o) {
+      const double oh = __shfl_sync(0xffffffffu, head, (lane + o) & 31);
+      const int oj = __shfl_sync(0xffffffffu, headj, (lane + o) & 31);
+      rank += (oh < head) || (oh == head && (oj < headj || (oj == headj && ((lane + o) & 31) < lane)));
+    }
+    const unsigned kth = __ballot_sync(0xffffffffu, rank == K - 1);
+    T = __shfl_sync(0xffffffffu, head, __ffs(kth) - 1);
+    Tj = __shfl_sync(0xffffffffu, headj, __ffs(kth) - 1);
+  };
+  auto offer = [&](bool pass, int j) {
+    const unsigned pm = __ballot_sync(0xffffffffu, pass);
+    if (pm == 0u) return;
+    if (pass) queue[qn + __popc(pm & ((1u << lane) - 1u))] = j;
+    qn += __popc(pm);
+    __syncwarp();
+    if (qn >= 32) {
+      flush(32);
+      __syncwarp();
+      qn -= 32;
+      int moved = 0;
+      if (lane < qn) moved = queue[32 + lane];   // at most 31 left over
+      __syncwarp();
+      if (lane < qn) queue[lane] = moved;
+      __syncwarp();
+    }
+  };
+  // start with the tile most rows of this CTA sit in (the centre of the first row's stencil): its candidates tighten T
+  // at once and the outer tiles are then pruned almost entirely
+  __shared__ int s_first;
+  if (threadIdx.x == 0) {
+    const int c = W.stencil[(size_t)(blockIdx.x * 8) * n_st + n_st / 2];
+    s_first = (c >= 0 && c < n_view_tiles) ? c : 0;
   }
+  __syncthreads();
+  const int t_first = s_first;
+  for (int tt = 0; tt < n_view_tiles; ++tt) {
+    const int t = tt == 0 ? t_first : (tt <= t_first ? tt - 1 : tt);
+    __syncthreads();   // the previous tile has been scanned by every warp
+    for (int e = threadIdx.x; e < 3 * m_view; e += 256) tile_pos[e] = V.positions[(size_t)t * m_view * 3 + e];
+    for (int e = threadIdx.x; e < m_view; e += 256) tile_valid[e] = V.valid[(size_t)t * m_view + e];
+    __syncthreads();
+    if (!active) continue;
+    int s = -1;
+    for (int q = 0; q < n_st; ++q)
+      if (W.stencil[i * n_st + q] == t) { s = q; break; }
+    if (s < 0) continue;
+    for (int base = 0; base < m_view; base += 32) {
+      const int off = base + lane;
+      bool pass = false;
+      if (off < m_view) {
+        double lb = 1e12;
+        if (tile_valid[off]) {
+          const double d0 = mp[0] - tile_pos[3 * off], d1 = mp[1] - tile_pos[3 * off + 1], d2 = mp[2] - tile_pos[3 * off + 2];
+          lb = d0 * d0 + d1 * d1 + d2 * d2;
+        }
+        const int j = s * m_view + off;
+        pass = !prune || !(lb > T || (lb == T && j > Tj));   // lb <= cost: beyond (T, Tj) it cannot be among the first K
+      }
+      offer(pass, s * m_view + off);
+    }
+  }
+  if (!active) return;
+  // stencil positions whose tile is not in the view carry cost 1e12 for every offset: they only matter while fewer than
+  // K better candidates exist
+  for (int s = 0; s < n_st; ++s) {
+    if (W.stencil[i * n_st + s] >= 0) continue;
+    if (prune && (1e12 > T || (1e12 == T && s * m_view > Tj))) continue;
+    for (int base = 0; base < m_view; base += 32) {
+      const int off = base + lane, j = s * m_view + off;
+      if (prune && (1e12 > T || (1e12 == T && s * m_view + base > Tj))) break;
+      offer(off < m_view && (!prune || !(1e12 > T || (1e12 == T && j > Tj))), j);
+    }
+  }
+  if (qn > 0) { __syncwarp(); flush(qn); }
   // K-round tournament over the lanes' heads by (cost, j)
   const bool mvalid = B.valid[i] != 0;
   for (int r = 0; r < K; ++r) {
@@ -1073,7 +1171,11 @@ int gcs_associate_primitives_ot(gcs_ctx* ctx, void* stream, const gcs_meas_batch
   assoc_prepare_kernel<<<(N + 127) / 128, 128, 0, st>>>(*batch, N, T, *cfg, n_st, d_off, d_off + 64, d_off + 128, W);
   GCS_LAUNCH_CHECK(ctx);
   gcs_timing_begin(ctx, st);
-  assoc_topk_kernel<8><<<(unsigned)cdivm((int64_t)N * 32, 256), 256, 0, st>>>(*batch, N, *view, m_tile_view, n_st, W, *cfg, *out);
+  const size_t topk_smem = (size_t)m_tile_view * (3 * sizeof(double) + 1);
+  if (topk_smem > 40 * 1024)
+    GCS_CHECK_CUDA(ctx, cudaFuncSetAttribute(assoc_topk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
+  assoc_topk_kernel<8><<<(unsigned)cdivm((int64_t)N, 8), 256, topk_smem, st>>>(*batch, N, *view, m_tile_view, n_st, n_tiles, W,
+                                                                                *cfg, *out);
   gcs_timing_end(ctx, st);
   GCS_LAUNCH_CHECK(ctx);
   assoc_sinkhorn_kernel<8><<<1, kBig, 0, st>>>(*batch, N, *view, W, *cfg, *out, cert, (double*)(ws + o_brow));
