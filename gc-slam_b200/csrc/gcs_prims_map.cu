@@ -5,6 +5,8 @@
 //   a14  map update: PoE fuse (sorted segmented scatter, no float atomics), insert/evict, cull, forget
 // All selections reproduce jnp.argsort / lax.sort semantics (stable, first operand is the only key) through
 // cta_select_k (gcs_select.cuh).  All floating reductions are fixed-order.
+#include <cooperative_groups.h>
+
 #include "gcs_select.cuh"
 
 namespace gcs {
@@ -400,31 +402,79 @@ __global__ void __launch_bounds__(256) assoc_topk_kernel(gcs_meas_batch B, int N
 __device__ __forceinline__ double pow_pos(double x, double y) { return x > 0.0 ? exp(y * log(x)) : 0.0; }
 
 // single CTA: cost of the selected candidates, recency term, row-min shift, unbalanced Sinkhorn, certificates
+// Unbalanced Sinkhorn on the (N, K) sparse costs (primitive_association.py:105-138, :379-470) as a thread-block CLUSTER of
+// eight CTAs: every CTA owns 256 measurement rows (one per thread), the K column sums that couple all rows -- the
+// reference's v is one (K,) vector shared by every row -- are exchanged through distributed shared memory once per
+// iteration: each CTA publishes its K partial sums in its own shared memory, one cluster barrier, every CTA reads the
+// eight partial vectors in rank order (same order everywhere: identical v in every CTA, bit-identical reruns).  The
+// exchange buffers alternate with the iteration parity, so one barrier per iteration suffices.  A single CTA spent
+// 7 us per iteration on the float64 pow() of 1,536 rows (one SM's FP64 pipe); eight SMs share that work.
+constexpr int kSkCtas = 8;
+constexpr int kSkThreads = 256;
+constexpr int kSkMaxVals = 16;
+
+// Sum of NV (<= kSkMaxVals) per-thread values over the whole cluster; every thread of every CTA gets post(k, total_k).
+// Fixed order: shuffle tree per warp, warps in index order, CTAs in rank order.  Thread k of a CTA gathers column k from
+// the eight CTAs through distributed shared memory, applies `post` (e.g. the Sinkhorn scaling: one pow() per column and
+// CTA instead of one per thread) and publishes the result in local shared memory.  `phase` alternates the exchange
+// buffer, so that a CTA running ahead never overwrites values a slower one still reads.
+template <int NV, typename Post>
+__device__ __forceinline__ void cluster_sum(double (&v)[NV], double (*xch)[kSkMaxVals], double* sredw, double* tot,
+                                            unsigned& phase, Post post) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();   // sredw / tot are free (the previous call's readers are done)
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) sredw[warp * kSkMaxVals + k] = v[k];
+  }
+  __syncthreads();
+  const unsigned buf = phase & 1u;
+  if (tid < NV) {
+    double t = 0.0;
+    for (int w = 0; w < kSkThreads / 32; ++w) t += sredw[w * kSkMaxVals + tid];
+    xch[buf][tid] = t;
+  }
+  cluster.sync();
+  if (tid < NV) {
+    double t = 0.0;
+    for (int r = 0; r < kSkCtas; ++r) t += cluster.map_shared_rank(&xch[buf][0], r)[tid];
+    tot[tid] = post(tid, t);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = tot[k];
+  ++phase;
+}
+
 template <int K>
-__global__ void __launch_bounds__(kBig) assoc_sinkhorn_kernel(gcs_meas_batch B, int N, gcs_map_view V, AssocWs W,
-                                                              gcs_assoc_cfg cfg, gcs_assoc_result R,
-                                                              double* __restrict__ cert, double* __restrict__ brow_ws) {
-  __shared__ double sred[32];
-  __shared__ double sredK[(kBig / 32) * K];
-  __shared__ double sv[K];
+__global__ void __cluster_dims__(kSkCtas, 1, 1) __launch_bounds__(kSkThreads)
+    assoc_sinkhorn_kernel(gcs_meas_batch B, int N, gcs_map_view V, AssocWs W, gcs_assoc_cfg cfg, gcs_assoc_result R,
+                          double* __restrict__ cert, double* __restrict__ brow_ws) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ double xch[2][kSkMaxVals];
+  __shared__ double sredw[(kSkThreads / 32) * kSkMaxVals];
+  __shared__ double tot[kSkMaxVals];
   __shared__ SelectSmem sel;
   const int tid = threadIdx.x;
-  constexpr int RPT = 2;  // rows per thread: N <= 2048
-  double Km[RPT][K], Cm[RPT][K], u[RPT], a[RPT];
+  const int rank = (int)cluster.block_rank();
+  const int i = rank * kSkThreads + tid;   // N <= kSkCtas * kSkThreads = 2048
+  unsigned phase = 0;
+  double Km[K], Cm[K], u = 1.0, a = 0.0;
   const double eps = fmax(cfg.epsilon, 1e-12);
-  double nvalid = 0.0;
-  for (int q = 0; q < RPT; ++q) {
-    const int i = tid + q * kBig;
-    nvalid += (i < N && B.valid[i]) ? 1.0 : 0.0;
-  }
-  const double sum_valid = block_sum_1024(nvalid, sred);
+  double nv[1] = {(i < N && B.valid[i]) ? 1.0 : 0.0};
+  auto ident = [](int, double t) { return t; };
+  cluster_sum<1>(nv, xch, sredw, tot, phase, ident);
+  const double sum_valid = nv[0];
   const double sum_a = fmax(sum_valid, cfg.eps_mass);
-  for (int q = 0; q < RPT; ++q) {
-    const int i = tid + q * kBig;
-    u[q] = 1.0; a[q] = 0.0;
-    for (int k = 0; k < K; ++k) { Km[q][k] = 0.0; Cm[q][k] = 0.0; }
-    if (i >= N) continue;
-    a[q] = (B.valid[i] ? 1.0 : 0.0) / sum_a;
+#pragma unroll
+  for (int k = 0; k < K; ++k) { Km[k] = 0.0; Cm[k] = 0.0; }
+  if (i < N) {
+    a = (B.valid[i] ? 1.0 : 0.0) / sum_a;
     const double mp[3] = {W.mpos[3 * i], W.mpos[3 * i + 1], W.mpos[3 * i + 2]};
     const double md[3] = {W.mdir[3 * i], W.mdir[3 * i + 1], W.mdir[3 * i + 2]};
     const double mk = W.mkap[i];
@@ -436,80 +486,69 @@ __global__ void __launch_bounds__(kBig) assoc_sinkhorn_kernel(gcs_meas_batch B, 
       long long dt = cfg.scan_seq - V.last_supported_scan_seq[v];
       if (dt < 0) dt = 0;
       c += cfg.epsilon * cfg.recency_decay_lambda * (double)dt;
-      Cm[q][k] = c;
+      Cm[k] = c;
       rmin = fmin(rmin, c);
       double d = exp(-cfg.recency_decay_lambda * (double)dt);
       if (!(d > 0.0)) d = 0.0;
       bdec[k] = d; bsum += d;
     }
     for (int k = 0; k < K; ++k) {
-      Cm[q][k] -= rmin;
-      Km[q][k] = exp(-Cm[q][k] / eps);
+      Cm[k] -= rmin;
+      Km[k] = exp(-Cm[k] / eps);
       brow_ws[i * K + k] = bdec[k] / fmax(bsum, cfg.eps_mass);  // diagnostics only (:420-425)
     }
   }
-  if (tid < K) sv[tid] = 1.0;
-  __syncthreads();
+  double sv[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) sv[k] = 1.0;
   const double ua = 1.0 / (1.0 + cfg.tau_a / eps), vb = 1.0 / (1.0 + cfg.tau_b / eps);
   const double bk = 1.0 / (double)K;
   for (int it = 0; it < cfg.k_sinkhorn; ++it) {
     double ktu[K];
-    for (int k = 0; k < K; ++k) ktu[k] = 0.0;
-    for (int q = 0; q < RPT; ++q) {
-      const int i = tid + q * kBig;
-      if (i >= N) continue;
+    if (i < N) {
       double kv = 0.0;
-      for (int k = 0; k < K; ++k) kv += Km[q][k] * sv[k];
-      u[q] = pow_pos(a[q] / (kv + 1e-12), ua);
-      for (int k = 0; k < K; ++k) ktu[k] += Km[q][k] * u[q];
-    }
-    // all K column sums in one fixed-order block reduction (2 barriers per Sinkhorn iteration instead of 25)
 #pragma unroll
-    for (int k = 0; k < K; ++k) ktu[k] = warp_sum(ktu[k]);
-    if ((tid & 31) == 0) {
+      for (int k = 0; k < K; ++k) kv += Km[k] * sv[k];
+      u = pow_pos(a / (kv + 1e-12), ua);
 #pragma unroll
-      for (int k = 0; k < K; ++k) sredK[(tid >> 5) * K + k] = ktu[k];
-    }
-    __syncthreads();
-    if (tid < 32) {
-      // warp 0: lane l holds warp l's partials; one shuffle tree per column
-      double t = 0.0;
+      for (int k = 0; k < K; ++k) ktu[k] = Km[k] * u;
+    } else {
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const double c = warp_sum(sredK[tid * K + k]);
-        if (tid == k) t = c;
-      }
-      if (tid < K) sv[tid] = pow_pos(bk / (t + 1e-12), vb);
+      for (int k = 0; k < K; ++k) ktu[k] = 0.0;
     }
-    __syncthreads();
+    // one cluster barrier per iteration; the K column scalings v_k = (b / (K^T u + eps))^(1/(1+tau_b/eps)) are
+    // evaluated by the K gathering threads of each CTA
+    cluster_sum<K>(ktu, xch, sredw, tot, phase, [&](int, double t) { return pow_pos(bk / (t + 1e-12), vb); });
+#pragma unroll
+    for (int k = 0; k < K; ++k) sv[k] = ktu[k];
   }
   // outputs + certificate sums
-  double s_row = 0, s_row2 = 0, s_da = 0, s_nov = 0, s_cost = 0, col[K];
-  for (int k = 0; k < K; ++k) col[k] = 0.0;
-  for (int q = 0; q < RPT; ++q) {
-    const int i = tid + q * kBig;
-    if (i >= N) continue;
+  double cs[5 + K];
+#pragma unroll
+  for (int k = 0; k < 5 + K; ++k) cs[k] = 0.0;
+  if (i < N) {
     const bool mv = B.valid[i] != 0;
     double row = 0.0;
     for (int k = 0; k < K; ++k) {
-      const double pi = u[q] * Km[q][k] * sv[k];
-      row += pi; col[k] += pi; s_cost += pi * Cm[q][k];
+      const double pi = u * Km[k] * sv[k];
+      row += pi; cs[5 + k] += pi; cs[4] += pi * Cm[k];
       R.responsibilities[i * K + k] = mv ? pi : 0.0;
-      R.cost_matrix[i * K + k] = Cm[q][k];
+      R.cost_matrix[i * K + k] = Cm[k];
     }
     R.row_masses[i] = row;
-    s_row += row; s_row2 += row * row;
-    const double d = row - a[q];
-    s_da += d * d;
-    s_nov += fmax(a[q] - row, 0.0);
+    cs[0] = row; cs[1] = row * row;
+    const double d = row - a;
+    cs[2] = d * d;
+    cs[3] = fmax(a - row, 0.0);
   }
-  const double S_row = block_sum_1024(s_row, sred), S_row2 = block_sum_1024(s_row2, sred);
-  const double S_da = block_sum_1024(s_da, sred), S_nov = block_sum_1024(s_nov, sred), S_cost = block_sum_1024(s_cost, sred);
+  cluster_sum<5 + K>(cs, xch, sredw, tot, phase, ident);
+  const double S_row = cs[0], S_row2 = cs[1], S_da = cs[2], S_nov = cs[3], S_cost = cs[4];
   double db = 0.0;
-  for (int k = 0; k < K; ++k) {
-    const double ck = block_sum_1024(col[k], sred);
-    db += (ck - bk) * (ck - bk);
-  }
+  for (int k = 0; k < K; ++k) db += (cs[5 + k] - bk) * (cs[5 + k] - bk);
+  // no CTA may exit while another still reads its exchange buffer; the barrier also makes the brow_ws rows written by
+  // every CTA visible to rank 0, which finishes alone
+  cluster.sync();
+  if (rank != 0) return;
   // p95 of the diagnostic per-row recency marginal: the (total - idx)-th largest of N*K values
   const int total = N * K;
   int idx95 = (int)(0.95 * (double)total);
@@ -1178,7 +1217,7 @@ int gcs_associate_primitives_ot(gcs_ctx* ctx, void* stream, const gcs_meas_batch
                                                                                 *cfg, *out);
   gcs_timing_end(ctx, st);
   GCS_LAUNCH_CHECK(ctx);
-  assoc_sinkhorn_kernel<8><<<1, kBig, 0, st>>>(*batch, N, *view, W, *cfg, *out, cert, (double*)(ws + o_brow));
+  assoc_sinkhorn_kernel<8><<<kSkCtas, kSkThreads, 0, st>>>(*batch, N, *view, W, *cfg, *out, cert, (double*)(ws + o_brow));
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
 }
