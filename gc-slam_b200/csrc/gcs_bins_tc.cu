@@ -26,6 +26,7 @@
 // the same amount of work whatever the batch shape -- and writes one partial per unit segment it touched, in the
 // layout of bin_scan_kernel, so reduce_partials_kernel and the finalize kernel are shared with the other precisions.
 // Accumulation order is fixed (per-warp tile order, epilogue drains warps in index order): bit-identical reruns.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "gcs_bins.cuh"
@@ -86,6 +87,7 @@ struct TcGeom {
   int64_t tiles_per_unit;   // ceil(cap / 32)
   int64_t total_tiles;      // U * tiles_per_unit
   int n_cta, n_parts, flush;
+  int dbg;   // 0, or 1 + slot of the timing hook
 };
 
 __device__ __forceinline__ int64_t cta_tile0(const TcGeom& G, int c) { return (int64_t)c * G.total_tiles / G.n_cta; }
@@ -559,8 +561,12 @@ __device__ __forceinline__ void idle_role(const BinScanParams& P, const TcGeom& 
   while (next_segment(G, P.n_hyp, g0, g_end, sg)) segment_tail<Q, H>(P, G, sg, mi, stages, cta, tid, nullptr);
 }
 
+// Timing hook (GCS_TC_TIMES=1): first CTA entry and last CTA exit of the first 32 launches on %globaltimer, printed
+// after the 24th launch -- tells the launch / drain overhead apart from the time the CTAs really run (8 us of 530).
+__device__ unsigned long long g_dbg_t[64];
 template <int Q, bool H>
 __global__ void __launch_bounds__(TcCfg<Q, H>::kThreads, 1) bin_scan_tc_kernel(const BinScanParams P, const TcGeom G) {
+  if (G.dbg && threadIdx.x == 0) { unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); atomicMin(&g_dbg_t[2 * (G.dbg - 1)], g); }
   using C = TcCfg<Q, H>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1 KB alignment by pointer arithmetic on the __shared__ symbol (keeps the shared address space: STS/LDS, not generic)
@@ -623,6 +629,7 @@ __global__ void __launch_bounds__(TcCfg<Q, H>::kThreads, 1) bin_scan_tc_kernel(c
   tc::fence_before_sync();
   __syncthreads();
   if (wid == 0) tc::tmem_free(tmem, 512);
+  if (G.dbg && threadIdx.x == 0) { unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); atomicMax(&g_dbg_t[2 * (G.dbg - 1) + 1], g); }
 }
 
 int tc_flush_tiles() {
@@ -647,6 +654,7 @@ TcGeom make_geom(int sm_count, int n_units, int64_t cap, int n_parts, int n_prod
   G.n_cta = (int)n_cta;
   G.n_parts = n_parts;
   G.flush = tc_flush_tiles();
+  G.dbg = getenv("GCS_TC_TIMES") ? 1 : 0;
   return G;
 }
 
@@ -673,7 +681,25 @@ cudaError_t launch_q(cudaStream_t st, const BinScanParams& P, const TcGeom& G) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  bin_scan_tc_kernel<Q, H><<<G.n_cta, C::kThreads, smem, st>>>(P, G);
+  static int n_dbg = 0;
+  TcGeom G2 = G;
+  if (G.dbg) {
+    if (n_dbg == 0) {
+      unsigned long long z[64];
+      for (int i = 0; i < 32; ++i) { z[2 * i] = ~0ull; z[2 * i + 1] = 0ull; }
+      cudaMemcpyToSymbol(g_dbg_t, z, sizeof(z));
+    }
+    G2.dbg = n_dbg < 32 ? n_dbg + 1 : 0;
+  }
+  bin_scan_tc_kernel<Q, H><<<G.n_cta, C::kThreads, smem, st>>>(P, G2);
+  if (G.dbg && ++n_dbg == 24) {
+    cudaDeviceSynchronize();
+    unsigned long long t[64];
+    cudaMemcpyFromSymbol(t, g_dbg_t, sizeof(t));
+    for (int i = 0; i < 24; ++i)
+      fprintf(stderr, "tc launch %d: first CTA entry -> last CTA exit %.1f us; gap to next entry %.1f us\n", i,
+              (t[2 * i + 1] - t[2 * i]) * 1e-3, i < 23 ? ((double)t[2 * i + 2] - (double)t[2 * i + 1]) * 1e-3 : 0.0);
+  }
   return cudaSuccess;
 }
 
