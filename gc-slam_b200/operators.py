@@ -799,10 +799,15 @@ class BinPathPlan:
             getattr(self.map, k_dst).copy_(v)
 
     def upload(self, pts, t, w, ring=None, tag=None, t0=None, t1=None, xi=None, poses=None, non_blocking=True):
-        """Host (ideally pinned) -> device copies of one batch; returns bytes copied."""
+        """
+        Host (ideally pinned) -> device copies of one batch; returns bytes copied.  The few-hundred-byte parameter copies
+        go FIRST and the large arrays last: a small copy queued behind a large one on the same stream held back the
+        kernels of the *other* stream of a double-buffered loop until the large copy had finished (measured: 4.06 ms per
+        184.6 MB step with the small copies last, 3.42 ms with them first; tools/e2e_probe.py).
+        """
         n = 0
-        for dst, src in ((self.pts, pts), (self.t, t), (self.w, w), (self.ring, ring), (self.tag, tag), (self.t0, t0),
-                         (self.t1, t1), (self.xi, xi), (self.poses, poses)):
+        for dst, src in ((self.t0, t0), (self.t1, t1), (self.xi, xi), (self.poses, poses), (self.ring, ring), (self.tag, tag),
+                         (self.t, t), (self.w, w), (self.pts, pts)):
             if src is None:
                 continue
             src_t = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src))
@@ -849,14 +854,15 @@ class BinPathPlan:
         n = self.S * self.n_raw * self._pc2_lay.point_step
         if src.numel() < n:
             raise ValueError(f"payload has {src.numel()} bytes, the plan needs {n}")
-        self._pc2_dev[:n].copy_(src[:n], non_blocking=non_blocking)
         moved = n
+        # parameter copies first, payload last (see upload())
         for dst, s_ in ((self._pc2_stamp, header_stamps), (self.t0, t0), (self.t1, t1), (self.xi, xi), (self.poses, poses)):
             if s_ is None:
                 continue
             st = s_ if isinstance(s_, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(s_, dtype=np.float64))
             dst.copy_(st.reshape(dst.shape), non_blocking=non_blocking)
             moved += dst.numel() * dst.element_size()
+        self._pc2_dev[:n].copy_(src[:n], non_blocking=non_blocking)
         io.ctx.check(io.ctx.lib.gcs_parse_pointcloud2_vlp16(
             io.ctx.handle, io.stream(), L.ptr(self._pc2_dev), self.S, self.n_raw, C.byref(self._pc2_lay), L.ptr(self._pc2_stamp),
             self._pc2_R, self._pc2_t, L.ptr(self.pts), L.ptr(self.t), L.ptr(self.w), L.ptr(self.ring), L.ptr(self.tag),

@@ -1,4 +1,5 @@
 """Where the end-to-end step time of bench.py goes: the same two-plan / two-stream loop with stages switched off."""
+import ctypes as C
 import sys
 import time
 
@@ -36,6 +37,21 @@ def step(k, mode):
         if mode == "copy":
             pl._pc2_dev[:n].copy_(payload[:n], non_blocking=True)
             return
+        if mode in ("copy+small", "copy+small+run", "copy+run(no small)", "small+copy+run"):
+            if mode == "small+copy+run":
+                for dst, src in ((pl.t0, t0), (pl.t1, t1), (pl.xi, xi), (pl.poses, poses)):
+                    dst.copy_(src.reshape(dst.shape), non_blocking=True)
+            pl._pc2_dev[:n].copy_(payload[:n], non_blocking=True)
+            if "small" in mode and "no small" not in mode and mode != "small+copy+run":
+                for dst, src in ((pl.t0, t0), (pl.t1, t1), (pl.xi, xi), (pl.poses, poses)):
+                    dst.copy_(src.reshape(dst.shape), non_blocking=True)
+            if "run" in mode:
+                io = pl.io
+                io.ctx.check(io.ctx.lib.gcs_parse_pointcloud2_vlp16(
+                    io.ctx.handle, io.stream(), L.ptr(pl._pc2_dev), pl.S, pl.n_raw, C.byref(pl._pc2_lay), L.ptr(pl._pc2_stamp),
+                    pl._pc2_R, pl._pc2_t, L.ptr(pl.pts), L.ptr(pl.t), L.ptr(pl.w), L.ptr(pl.ring), L.ptr(pl.tag), L.ptr(pl._pc2_cert)))
+                pl.run()
+            return
         pl.upload_pointcloud2(payload, None, t0, t1, xi, poses)
         if mode == "copy+parse":
             return
@@ -46,7 +62,7 @@ def step(k, mode):
         oh[k % 2].copy_(torch.cat([o.cert.reshape(-1), o.L22.reshape(-1), o.h22.reshape(-1)]), non_blocking=True)
 
 
-for mode in ("copy", "copy+parse", "copy+parse+run", "full"):
+for mode in ("copy", "copy+small", "copy+run(no small)", "copy+small+run", "small+copy+run", "copy+parse", "copy+parse+run", "full"):
     for k in range(2):
         step(k, mode)
     torch.cuda.synchronize()
@@ -57,3 +73,4 @@ for mode in ("copy", "copy+parse", "copy+parse+run", "full"):
     torch.cuda.synchronize()
     dt = time.perf_counter() - a
     print(f"{mode:16s}: {dt * 100:.3f} ms/step  ({S * 10 / dt:.0f} scans/s, {10 * n / dt / 1e9:.1f} GB/s H2D)  cpu enqueue {cpu * 100:.3f} ms/step")
+
