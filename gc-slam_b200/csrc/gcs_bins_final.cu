@@ -265,16 +265,16 @@ __global__ void __launch_bounds__(kFinalThreads) bins_finalize_kernel(const Fina
     // hand the factors to the helper that finishes the record
     for (int k = 0; k < 9; ++k) { sMF[k] = Rmf.m[k]; sMF[9 + k] = mfV.m[k]; }
     for (int k = 0; k < 3; ++k) sMF[18 + k] = mfs[k];
-  } else if (tid == kMaxBins + 1 && P.do_mf) {
+  } else if (tid == kMaxBins && P.do_mf) {            // warp 2: the four serial tasks of this phase sit in four warps
     Mat3 St;
     for (int k = 0; k < 9; ++k) St.m[k] = tot[9 + k];
     scatter_metrics17(St, tot[27], eps, ev + GCS_EV_SCAN_METRICS);
-  } else if (tid == kMaxBins + 2 && P.do_mf) {
+  } else if (tid == kMaxBins + 32 && P.do_mf) {       // warp 3
     Mat3 Mt;
     for (int k = 0; k < 9; ++k) Mt.m[k] = tot[18 + k];
     scatter_metrics17(Mt, tot[28], eps, ev + GCS_EV_MAP_METRICS);
   }
-  if (tid == kMaxBins + 3 && P.do_pt) {
+  if (tid == 32 && P.do_pt) {                          // warp 1 (its bin threads idle until the barrier below)
     // self-adaptive z precision from the total map scatter (:579-592): needs only the column sums
     Mat3 Tm;
     const double Nd = tot[28] + eps;
