@@ -663,12 +663,10 @@ static SoftmaxShift softmax_shift(double inv_tau, double bnorm_max) {
 
 template <int Q, int PREC, int OCC>
 static cudaError_t launch_scan_q(dim3 grid, cudaStream_t st, const BinScanParams& P) {
-  static bool attr_set = false;  // opt in to > 48 KB dynamic shared memory once per instantiation
   const int smem = (int)sizeof(ScanSmem<Q>);
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(bin_scan_kernel<Q, PREC, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  {  // opt in to > 48 KB dynamic shared memory once per instantiation and device
+    cudaError_t e = gcs_smem_attr_once((const void*)bin_scan_kernel<Q, PREC, OCC>, smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   bin_scan_kernel<Q, PREC, OCC><<<grid, kScanThreads, smem, st>>>(P);
   return cudaSuccess;

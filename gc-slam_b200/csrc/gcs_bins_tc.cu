@@ -674,12 +674,10 @@ bool tc_use_f16(double inv_tau) {
 template <int Q, bool H>
 cudaError_t launch_q(cudaStream_t st, const BinScanParams& P, const TcGeom& G) {
   using C = TcCfg<Q, H>;
-  static bool attr_set = false;
   const int smem = C::kStagesBytes + (int)sizeof(TcMisc) + 1024;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(bin_scan_tc_kernel<Q, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  {
+    cudaError_t e = gcs_smem_attr_once((const void*)bin_scan_tc_kernel<Q, H>, smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   static int n_dbg = 0;
   TcGeom G2 = G;

@@ -49,6 +49,27 @@ int gcs_ws_reserve(gcs_ctx* ctx, uint64_t bytes);
     if (!(cond)) return gcs_set_error((ctx), GCS_EINVAL, __VA_ARGS__);   \
   } while (0)
 
+// Opt a kernel in to `bytes` of dynamic shared memory once per (kernel, device).  Function attributes belong to the
+// device's context, so a process that drives several GPUs (one gcs_ctx per device) must set them on each; a flag per
+// process would leave the second device with the 48 KB default and its first launch would fail.
+inline cudaError_t gcs_smem_attr_once(const void* kern, int bytes) {
+  struct Entry { const void* k; unsigned long long devs; int bytes; };
+  static Entry tab[64];
+  static int n = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (int i = 0; i < n; ++i)
+    if (tab[i].k == kern) {
+      if (dev < 64 && ((tab[i].devs >> dev) & 1ull) && tab[i].bytes >= bytes) return cudaSuccess;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (e == cudaSuccess && dev < 64) { tab[i].devs = (tab[i].bytes >= bytes ? tab[i].devs : 0ull) | (1ull << dev); if (bytes > tab[i].bytes) tab[i].bytes = bytes; }
+      return e;
+    }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && n < 64) { tab[n].k = kern; tab[n].devs = dev < 64 ? (1ull << dev) : 0ull; tab[n].bytes = bytes; ++n; }
+  return e;
+}
+
 #define GCS_LAUNCH_CHECK(ctx)                        \
   do {                                               \
     (ctx)->launches++;                               \

@@ -285,12 +285,7 @@ extern "C" int gcs_hypothesis_barycenter(gcs_ctx* ctx, void* stream, const doubl
   P.L = L_stack; P.h = h_stack; P.z = z_lin_stack; P.w = weights; P.K = n_hyp; P.D = dim;
   P.floor = weight_floor; P.eps_psd = eps_psd; P.eps_lift = eps_lift;
   P.L_out = L_out; P.h_out = h_out; P.z_out = z_lin_out; P.wn_out = weights_norm_out; P.means = means_out; P.cert = cert;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GCS_CHECK_CUDA(ctx, cudaFuncSetAttribute(hypothesis_means_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)kHbDynBytes));
-    attr_set = true;
-  }
+  GCS_CHECK_CUDA(ctx, gcs_smem_attr_once((const void*)hypothesis_means_kernel, (int)kHbDynBytes));
   hypothesis_means_kernel<<<(n_hyp + kHbCholWarps - 1) / kHbCholWarps, kHbThreads, kHbDynBytes, (cudaStream_t)stream>>>(P);
   GCS_LAUNCH_CHECK(ctx);
   hypothesis_barycenter_kernel<<<1, kHbThreads, 0, (cudaStream_t)stream>>>(P);

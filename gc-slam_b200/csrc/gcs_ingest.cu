@@ -167,12 +167,7 @@ extern "C" int gcs_parse_pointcloud2_vlp16(gcs_ctx* ctx, void* stream, const uin
     P.sentinel = 1e6; P.sigma = 0.25; P.min_r = 0.5; P.max_r = 50.0; P.wfloor = 1e-12;   // common/constants.py:256-262
     P.pts = pts; P.t = t; P.w = w; P.ring = ring; P.tag = tag; P.flags = flags;
     const int smem = gcs::kParseThreads * lay->point_step + 32;
-    static bool attr_set = false;
-    if (!attr_set) {
-      GCS_CHECK_CUDA(ctx, cudaFuncSetAttribute(gcs::pc2_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               gcs::kParseThreads * gcs::kMaxPointStep + 32));
-      attr_set = true;
-    }
+    GCS_CHECK_CUDA(ctx, gcs_smem_attr_once((const void*)gcs::pc2_parse_kernel, gcs::kParseThreads * gcs::kMaxPointStep + 32));
     dim3 grid((unsigned)((n_points + gcs::kParseThreads - 1) / gcs::kParseThreads), (unsigned)n_msgs);
     gcs::pc2_parse_kernel<<<grid, gcs::kParseThreads, smem, st>>>(P);
     GCS_LAUNCH_CHECK(ctx);

@@ -123,8 +123,7 @@ inline size_t select_cache_bytes(int m_tile) {
 }
 template <typename Kern>
 cudaError_t select_cache_attr(Kern kern, size_t bytes) {
-  return bytes > 48 * 1024 - kSelectStaticBytes
-             ? cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) : cudaSuccess;
+  return bytes > 48 * 1024 - kSelectStaticBytes ? gcs_smem_attr_once((const void*)kern, (int)bytes) : cudaSuccess;
 }
 
 __global__ void __launch_bounds__(kBig) map_view_kernel(gcs_atlas A, TileList T, int m_view, double eps_lift, double eps_mass,
@@ -1212,7 +1211,7 @@ int gcs_associate_primitives_ot(gcs_ctx* ctx, void* stream, const gcs_meas_batch
   gcs_timing_begin(ctx, st);
   const size_t topk_smem = (size_t)m_tile_view * (3 * sizeof(double) + 1);
   if (topk_smem > 40 * 1024)
-    GCS_CHECK_CUDA(ctx, cudaFuncSetAttribute(assoc_topk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
+    GCS_CHECK_CUDA(ctx, gcs_smem_attr_once((const void*)assoc_topk_kernel<8>, (int)topk_smem));
   assoc_topk_kernel<8><<<(unsigned)cdivm((int64_t)N, 8), 256, topk_smem, st>>>(*batch, N, *view, m_tile_view, n_st, n_tiles, W,
                                                                                 *cfg, *out);
   gcs_timing_end(ctx, st);
@@ -1292,11 +1291,7 @@ int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int
 
   upd_prepare_kernel<<<1, kBig, 0, st>>>(*batch, N, *assoc, pose6[0], pose6[1], pose6[2], pose6[3], pose6[4], pose6[5], *cfg, W);
   GCS_LAUNCH_CHECK(ctx);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GCS_CHECK_CUDA(ctx, cudaFuncSetAttribute(upd_sort_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-    attr_set = true;
-  }
+  GCS_CHECK_CUDA(ctx, gcs_smem_attr_once((const void*)upd_sort_pairs_kernel, 16384 * 8));
   upd_sort_pairs_kernel<<<1, kBig, (size_t)n_pow2 * 8, st>>>(*batch, N, K, *assoc, T, atlas->m_tile, n_pow2, W.pairs);
   GCS_LAUNCH_CHECK(ctx);
   gcs_timing_begin(ctx, st);

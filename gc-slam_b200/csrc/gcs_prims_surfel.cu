@@ -428,11 +428,7 @@ int gcs_extract_lidar_surfels(gcs_ctx* ctx, void* stream, const double* pts, con
   GCS_LAUNCH_CHECK(ctx);
   surfel_cell_key_kernel<<<(unsigned)cdiv(n, kSurfThreads), kSurfThreads, 0, st>>>(pts, center, n, G, key);
   GCS_LAUNCH_CHECK(ctx);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GCS_CHECK_CUDA(ctx, cudaFuncSetAttribute(surfel_rank_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
+  GCS_CHECK_CUDA(ctx, gcs_smem_attr_once((const void*)surfel_rank_chunk_kernel, 160 * 1024));
   surfel_rank_chunk_kernel<<<n_chunks, 1024, (size_t)n_keys * sizeof(int), st>>>(key, n, per_chunk, n_keys, lrank, hist);
   GCS_LAUNCH_CHECK(ctx);
   surfel_rank_scan_kernel<<<(n_keys + 255) / 256, 256, 0, st>>>(hist, n_chunks, n_keys, total);
