@@ -277,6 +277,17 @@ def primitive_path_extra(n_points, n_map=1_000_000, reps=10):
         if rep >= 2:
             fused.append(time.perf_counter() - a0)
     p50["fused_entry_total"] = 1e3 * float(np.median(fused))
+    # map export: the whole map -> renderable batch + /gc/map/points payload, on the device
+    exp_t = []
+    for rep in range(5):
+        torch.cuda.synchronize()
+        a0 = time.perf_counter()
+        groups = [sorted(amap.tile_ids)[i:i + 256] for i in range(0, len(amap.tile_ids), 256)]
+        n_exp = sum(PR.export_map_points(amap, g).count for g in groups)
+        torch.cuda.synchronize()
+        if rep >= 1:
+            exp_t.append(time.perf_counter() - a0)
+    p50["map_export_whole_map"] = 1e3 * float(np.median(exp_t))
     res = out["map_update"][0]
     batch = out["surfels"][0]
     alg_bytes = 104e6  # ~104 MB per scan at 65,536 points / 1 M-surfel map, 7 active tiles
@@ -284,7 +295,7 @@ def primitive_path_extra(n_points, n_map=1_000_000, reps=10):
                         "splats + 1024 surfels, K_ASSOC 8, 7-tile stencil, map update with K_INSERT 64",
             "p50_ms_per_stage": p50, "scans_per_s": 1e3 / p50["fused_entry_total"],
             "scans_per_s_operator_by_operator": 1e3 / p50["total"], "algorithmic_bytes_per_scan": alg_bytes,
-            "achieved_GBps_model": alg_bytes / (p50["fused_entry_total"] * 1e-3) / 1e9, "n_lidar_surfels": int(batch.n_lidar_valid),
+            "achieved_GBps_model": alg_bytes / (p50["fused_entry_total"] * 1e-3) / 1e9, "n_lidar_surfels": int(batch.n_lidar_valid), "n_exported_primitives": int(n_exp),
             "n_inserted_last": int(res.n_inserted), "map_build_s": t_build, "reps": reps,
             "note": "per-stage: wall clock per operator call incl. its one certificate read-back (host sync); fused_entry_total: "
                     "the whole path through lidar_evidence_primitives (two host syncs), which scans_per_s is quoted on"}

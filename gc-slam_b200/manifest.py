@@ -33,6 +33,7 @@ ENTRY_POINTS = {
     "pose_evidence": "gcs_visual_pose_evidence",
     "map_update": "gcs_map_update",
     "map_recency_inflate": "gcs_map_recency_inflate",
+    "map_export": "gcs_export_map_points",
 }
 
 

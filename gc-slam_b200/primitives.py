@@ -70,6 +70,11 @@ class CMapView(C.Structure):
     _fields_ = [(n, _vp) for n in _VIEW_FIELDS]
 
 
+class CMapExport(C.Structure):
+    _fields_ = [(n, _vp) for n in ("mu_world", "Sigma_world", "Lambda_world", "eta", "mass", "color", "primitive_ids",
+                                   "last_supported_scan_seq", "cloud")]
+
+
 class CAssocCfg(C.Structure):
     _fields_ = [(n, _i32) for n in ("k_assoc", "k_sinkhorn", "r_stencil_xy", "r_stencil_z")] + \
                [(n, _dbl) for n in ("beta", "epsilon", "tau_a", "tau_b", "eps_mass", "eps_lift", "h_tile",
@@ -107,6 +112,7 @@ L.register_prototypes({
                                         C.POINTER(_dbl), _dbl, _dbl, _vp, _vp, _vp]),
     "gcs_map_update": (_int, [_vp, _vp, C.POINTER(CAtlas), C.POINTER(_i32), C.POINTER(_i64), _i32, C.POINTER(CMeasBatch),
                               C.POINTER(CAssocResult), C.POINTER(_dbl), C.POINTER(CMapUpdateCfg), _vp, _vp, _vp]),
+    "gcs_export_map_points": (_int, [_vp, _vp, C.POINTER(CAtlas), C.POINTER(_i32), _i32, _dbl, C.POINTER(CMapExport), _i64, _vp]),
 })
 
 
@@ -786,3 +792,60 @@ def lidar_evidence_primitives(points, timestamps, weights, scan_start_time: floa
     outs = drive_group(group)
     return dict(deskew=dk_out, surfels=sf_out, recency_inflate=ri_out, map_view=view, association=outs[0],
                 pose_evidence=outs[1], map_update=outs[2] if update_map else None)
+
+
+# --------------------------------------------------------------------------------------------------
+# map export (export half): valid primitives of the selected tiles -> renderable batch + /gc/map/points
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class RenderablePrimitiveBatch:
+    """Canonical renderable batch (world frame), field names of primitive_map.py:452-470; device tensors, newest first."""
+    mu_world: torch.Tensor
+    Sigma_world: torch.Tensor
+    Lambda_world: torch.Tensor
+    eta: torch.Tensor
+    mass: torch.Tensor
+    color: torch.Tensor
+    primitive_ids: torch.Tensor
+    last_supported_scan_seq: torch.Tensor
+    cloud: torch.Tensor          # uint8 (N * 16): x, y, z, intensity float32 LE records of /gc/map/points
+    point_step: int = 16
+
+    @property
+    def count(self) -> int:
+        return int(self.mass.shape[0])
+
+
+def export_map_points(atlas_map: AtlasMap, tile_ids: Optional[List[int]] = None, max_primitives: Optional[int] = None,
+                      eps_lift: float = constants.GC_EPS_LIFT) -> RenderablePrimitiveBatch:
+    """
+    PrimitiveMapPublisher.publish without the ROS objects (fl/backend/map_publisher.py:131-258): every valid primitive of
+    the selected tiles (default: all, sorted tile ids) -> mu, Sigma, Lambda_world, eta, mass, colour in newest-first
+    order (ties by primitive id) and the PointCloud2 payload of /gc/map/points, all on the device; one host read (the
+    count).  `max_primitives` (per-tile down-selection) is only built for the publisher's default, None.
+    """
+    if max_primitives is not None:
+        raise ValueError("export_map_points: max_primitives is not built (the reference's publisher default is None)")
+    io = _IO(atlas_map.device)
+    if tile_ids is None:
+        tile_ids = sorted(int(t) for t in atlas_map.tile_ids)
+    tile_ids = [int(t) for t in tile_ids if int(t) in atlas_map.tiles]
+    if not tile_ids:
+        z = lambda *s, dt=F64: io.zeros(*s, dtype=dt)
+        return RenderablePrimitiveBatch(z(0, 3), z(0, 3, 3), z(0, 3, 3), z(0, constants.GC_VMF_N_LOBES, 3), z(0), z(0, 3),
+                                        z(0, dt=torch.int64), z(0, dt=torch.int64), z(0, dt=torch.uint8))
+    if len(tile_ids) > 256:
+        raise ValueError(f"export_map_points: {len(tile_ids)} tiles in one call (limit 256): export in groups")
+    idx = atlas_map.index_list(tile_ids, create=False)
+    cap = len(tile_ids) * atlas_map.m_tile
+    mu, Sig, Lam, eta = io.empty(cap, 3), io.empty(cap, 3, 3), io.empty(cap, 3, 3), io.empty(cap, constants.GC_VMF_N_LOBES, 3)
+    mass, col = io.empty(cap), io.empty(cap, 3)
+    pid, rec = io.empty(cap, dtype=torch.int64), io.empty(cap, dtype=torch.int64)
+    cloud = io.empty(cap * 16, dtype=torch.uint8)
+    n_d = io.zeros(1, dtype=torch.int32)
+    ex = CMapExport(L.ptr(mu), L.ptr(Sig), L.ptr(Lam), L.ptr(eta), L.ptr(mass), L.ptr(col), L.ptr(pid), L.ptr(rec), L.ptr(cloud))
+    ca = atlas_map._c()
+    io.ctx.check(io.ctx.lib.gcs_export_map_points(io.ctx.handle, io.stream(), C.byref(ca), _i32arr(idx), len(idx), float(eps_lift),
+                                                  C.byref(ex), int(cap), L.ptr(n_d)))
+    n = int(io.host(n_d)[0])
+    return RenderablePrimitiveBatch(mu[:n], Sig[:n], Lam[:n], eta[:n], mass[:n], col[:n], pid[:n], rec[:n], cloud[:n * 16])

@@ -397,6 +397,29 @@ int gcs_extract_atlas_map_view(gcs_ctx* ctx, void* stream, const gcs_atlas* atla
                                const int64_t* tile_ids /*host*/, int32_t n_tiles, int32_t m_tile_view,
                                double eps_lift, double eps_mass, const gcs_map_view* view, int32_t* out_n_valid);
 
+/* ---- (8f-4, export half) map export : extract_primitive_map_view (fl/backend/structures/primitive_map.py:474-576),
+ * renderable_batch_from_view (:580-616), PrimitiveMapPublisher.publish + _build_pointcloud2_from_view
+ * (fl/backend/map_publisher.py:44-90, 131-258).  Every valid slot of the listed tiles (publishing order = the order of
+ * tile_index; -1 = missing tile), moments in the world frame, sorted newest first (last_supported_scan_seq descending,
+ * ties by primitive id ascending = np.lexsort((ids, -recency))), and the /gc/map/points payload: 16-byte records
+ * x, y, z, intensity (float32 LE), intensity = clip(weight, 0, 1e6).  The per-tile down-selection max_primitives of the
+ * reference is its publisher's default (None).  capacity >= n_tiles * m_tile rows in every output array; *out_count
+ * (dev) = rows written.  cloud must be 16-byte aligned.                                                             */
+typedef struct {
+  double* mu_world;                  /* (N,3)   */
+  double* Sigma_world;               /* (N,3,3) */
+  double* Lambda_world;              /* (N,3,3) inv(Sigma + eps_lift I) */
+  double* eta;                       /* (N,3,3) */
+  double* mass;                      /* (N)     */
+  double* color;                     /* (N,3)   tile.rgb */
+  int64_t* primitive_ids;            /* (N)     */
+  int64_t* last_supported_scan_seq;  /* (N)     */
+  uint8_t* cloud;                    /* (N,16)  */
+} gcs_map_export;
+int gcs_export_map_points(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int32_t* tile_index /*host*/,
+                          int32_t n_tiles, double eps_lift, const gcs_map_export* out, int64_t capacity,
+                          int32_t* out_count /*dev int32[1]*/);
+
 /* ---- a12 associate_primitives_ot : fl/backend/operators/primitive_association.py:105-553 -------------------- */
 typedef struct {
   int32_t k_assoc, k_sinkhorn, r_stencil_xy, r_stencil_z;

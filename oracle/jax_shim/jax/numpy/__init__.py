@@ -120,6 +120,22 @@ def array(x, dtype=None, copy=True):
     return _wrap(_np.array(x, dtype=dtype, copy=True))
 
 
+def where(condition, x=None, y=None, size=None, fill_value=None):
+    """jnp.where; the one-argument form takes `size` (fixed-length nonzero: truncate, or pad with fill_value / 0)."""
+    if x is not None or y is not None:
+        return _wrap(_np.where(_np.asarray(condition), _np.asarray(x), _np.asarray(y)))
+    idx = _np.nonzero(_np.asarray(condition))
+    if size is not None:
+        out = []
+        for a in idx:
+            a = a[:size]
+            if a.shape[0] < size:
+                a = _np.concatenate([a, _np.full(size - a.shape[0], 0 if fill_value is None else fill_value, dtype=a.dtype)])
+            out.append(a)
+        idx = tuple(out)
+    return tuple(_wrap(a) for a in idx)
+
+
 def argsort(a, axis=-1, **_k):
     return _wrap(_np.argsort(_np.asarray(a), axis=axis, kind="stable"))
 
