@@ -360,6 +360,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # one rank per GPU: keep this rank's pinned staging memory on the NUMA node of its GPU
+        from gc_slam_b200.sharding import bind_to_gpu_numa_node
+        bind_to_gpu_numa_node(local_rank)
     from gc_slam_b200 import _lib as L
     from gc_slam_b200 import operators as ops
     from gc_slam_b200 import synth

@@ -109,3 +109,12 @@ def test_tiling_helpers_match_oracle():
         c = rng.uniform(-30, 30, 3)
         assert P.ma_hex_stencil_tile_ids(c, 2.0, 1, 0) == op.stencil_tile_ids(c, 2.0, 1, 0)
     assert len(P.hex_disk_axial(1)) == 7 and len(P.hex_disk_axial(2)) == 19
+
+
+def test_cpulist_parser_and_numa_binding_is_safe_without_gpu():
+    from gc_slam_b200.sharding import bind_to_gpu_numa_node, parse_cpulist
+    assert parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11] and parse_cpulist("") == [] and parse_cpulist("5") == [5]
+    import os
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), list)
+    os.sched_setaffinity(0, before)
