@@ -34,6 +34,7 @@ ENTRY_POINTS = {
     "map_update": "gcs_map_update",
     "map_recency_inflate": "gcs_map_recency_inflate",
     "map_export": "gcs_export_map_points",
+    "map_merge_reduce": "gcs_map_merge_reduce",
 }
 
 

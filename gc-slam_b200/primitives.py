@@ -112,6 +112,7 @@ L.register_prototypes({
                                         C.POINTER(_dbl), _dbl, _dbl, _vp, _vp, _vp]),
     "gcs_map_update": (_int, [_vp, _vp, C.POINTER(CAtlas), C.POINTER(_i32), C.POINTER(_i64), _i32, C.POINTER(CMeasBatch),
                               C.POINTER(CAssocResult), C.POINTER(_dbl), C.POINTER(CMapUpdateCfg), _vp, _vp, _vp]),
+    "gcs_map_merge_reduce": (_int, [_vp, _vp, C.POINTER(CAtlas), _i32, _dbl, _i32, _dbl, _dbl, _vp]),
     "gcs_export_map_points": (_int, [_vp, _vp, C.POINTER(CAtlas), C.POINTER(_i32), _i32, _dbl, C.POINTER(CMapExport), _i64, _vp]),
 })
 
@@ -849,3 +850,64 @@ def export_map_points(atlas_map: AtlasMap, tile_ids: Optional[List[int]] = None,
                                                   C.byref(ex), int(cap), L.ptr(n_d)))
     n = int(io.host(n_d)[0])
     return RenderablePrimitiveBatch(mu[:n], Sig[:n], Lam[:n], eta[:n], mass[:n], col[:n], pid[:n], rec[:n], cloud[:n * 16])
+
+
+# --------------------------------------------------------------------------------------------------
+# merge-reduce (merge half)
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class PrimitiveMapMergeReduceResult:
+    atlas_map: AtlasMap
+    tile_id: int
+    n_merged: int
+    frobenius_correction: float
+
+
+def primitive_map_merge_reduce(atlas_map: AtlasMap, tile_id: int,
+                               merge_threshold: float = constants.GC_PRIMITIVE_MERGE_THRESHOLD,
+                               max_pairs: int = constants.GC_K_MERGE_PAIRS_PER_TILE,
+                               max_tile_size: int = constants.GC_PRIMITIVE_MERGE_MAX_TILE_SIZE,
+                               eps_psd: float = constants.GC_EPS_PSD, eps_lift: float = constants.GC_EPS_LIFT,
+                               chart_id: str = constants.GC_CHART_ID, anchor_id: str = "primitive_map"
+                               ) -> Tuple[PrimitiveMapMergeReduceResult, CertBundle, ExpectedEffect]:
+    """
+    primitive_map_merge_reduce (fl/backend/structures/primitive_map.py:1809-2031), in place on the device pool: same
+    no-op ladder (missing tile / fewer than two primitives / no pair budget -> exact no-op; tile larger than
+    max_tile_size -> approximate no-op with the budget-cap trigger), same triggers and certificate fields otherwise.
+    """
+    def no_op(predicted, triggers=None, influence=None):
+        res = PrimitiveMapMergeReduceResult(atlas_map=atlas_map, tile_id=int(tile_id), n_merged=0, frobenius_correction=0.0)
+        if triggers:
+            cert = CertBundle.create_approx(chart_id=chart_id, anchor_id=anchor_id, triggers=triggers, frobenius_applied=True,
+                                            influence=influence or InfluenceCert.identity())
+        else:
+            cert = CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id)
+        return res, cert, ExpectedEffect("primitive_map_merge_reduce", float(predicted), 0.0)
+
+    tile_id = int(tile_id)
+    if tile_id not in atlas_map.tiles:
+        return no_op(0.0)
+    M = int(atlas_map.m_tile)
+    if M < 2 or int(max_pairs) <= 0:
+        return no_op(float(max_pairs))
+    if int(max_tile_size) > 0 and M > int(max_tile_size):
+        over = float(M - int(max_tile_size)) / float(max(M, 1))
+        return no_op(float(max_pairs), ["merge_reduce_budget_cap"], InfluenceCert.identity().with_overrides(mass_epsilon_ratio=over))
+    if M > 2048 or int(max_pairs) > 64:
+        raise ValueError(f"primitive_map_merge_reduce: m_tile={M}, max_pairs={max_pairs} exceed the built budgets (2048 slots, 64 pairs)")
+    io = _IO(atlas_map.device)
+    stats_d = io.zeros(4)
+    ca = atlas_map._c()
+    row = atlas_map.index_list([tile_id], create=False)[0]
+    io.ctx.check(io.ctx.lib.gcs_map_merge_reduce(io.ctx.handle, io.stream(), C.byref(ca), int(row), float(merge_threshold),
+                                                 int(max_pairs), float(eps_psd), float(eps_lift), L.ptr(stats_d)))
+    n_merged = int(io.host(stats_d)[0])
+    if n_merged <= 0:
+        return no_op(float(max_pairs))
+    atlas_map.total_count = atlas_map.total_count - n_merged
+    cert = CertBundle.create_approx(chart_id=chart_id, anchor_id=anchor_id, triggers=["primitive_map_merge_reduce"],
+                                    frobenius_applied=True,
+                                    influence=InfluenceCert.identity().with_overrides(mass_epsilon_ratio=float(n_merged) / float(max(M, 1))),
+                                    compute=io.compute())
+    res = PrimitiveMapMergeReduceResult(atlas_map=atlas_map, tile_id=tile_id, n_merged=n_merged, frobenius_correction=float(n_merged))
+    return res, cert, ExpectedEffect("primitive_map_merge_reduce", float(max_pairs), float(n_merged))

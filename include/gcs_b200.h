@@ -397,6 +397,17 @@ int gcs_extract_atlas_map_view(gcs_ctx* ctx, void* stream, const gcs_atlas* atla
                                const int64_t* tile_ids /*host*/, int32_t n_tiles, int32_t m_tile_view,
                                double eps_lift, double eps_mass, const gcs_map_view* view, int32_t* out_n_valid);
 
+/* ---- (8f-4, merge half) primitive_map_merge_reduce : fl/backend/structures/primitive_map.py:1501-2031 ----------
+ * All-pairs Bhattacharyya distance of the tile's Gaussians (mu = solve(Lambda + eps_lift I, theta), Sigma = inv(.)),
+ * greedy disjoint selection of at most max_pairs pairs in stable ascending order of distance (finite, < threshold),
+ * moment-matched merge of each pair into its first slot (second slot: weight 0, invalid), in place.  m_tile <= 2048
+ * (the reference's GC_PRIMITIVE_MERGE_MAX_TILE_SIZE: above it the operator is a declared no-op, which the host layer
+ * reports without calling this).  stats (dev): number of merged pairs, status (0 nothing to merge, 1 merged).       */
+enum { GCS_MR_N_MERGED = 0, GCS_MR_STATUS, GCS_MR_NSTATS = 4 };
+int gcs_map_merge_reduce(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, int32_t tile_index /*pool row*/,
+                         double merge_threshold, int32_t max_pairs, double eps_psd, double eps_lift,
+                         double* stats /*dev [GCS_MR_NSTATS]*/);
+
 /* ---- (8f-4, export half) map export : extract_primitive_map_view (fl/backend/structures/primitive_map.py:474-576),
  * renderable_batch_from_view (:580-616), PrimitiveMapPublisher.publish + _build_pointcloud2_from_view
  * (fl/backend/map_publisher.py:44-90, 131-258).  Every valid slot of the listed tiles (publishing order = the order of
