@@ -35,6 +35,10 @@ ENTRY_POINTS = {
     "map_recency_inflate": "gcs_map_recency_inflate",
     "map_export": "gcs_export_map_points",
     "map_merge_reduce": "gcs_map_merge_reduce",
+    "map_fuse": "gcs_map_fuse",
+    "map_insert_masked": "gcs_map_insert_masked",
+    "map_cull": "gcs_map_cull",
+    "map_forget": "gcs_map_forget",
 }
 
 

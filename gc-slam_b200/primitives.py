@@ -14,6 +14,9 @@ Primitive-family LiDAR evidence operators -- host-side mirror of the reference's
   VisualPoseEvidenceResult, visual_pose_evidence
                                      fl/backend/operators/visual_pose_evidence.py:50-436
   map_update_step12b                 fl/backend/pipeline.py:1233-1447 (fuse x blocks x tiles, insert, cull, forget)
+  primitive_map_fuse, primitive_map_insert_masked, primitive_map_cull, primitive_map_forget (one tile per call)
+                                     fl/backend/structures/primitive_map.py:807-1384
+  block_associations_for_fuse        fl/backend/operators/primitive_association.py:561-588
   ma_hex_stencil_tile_ids, tile_ids_from_xyz_batch   fl/common/tiling.py:126-209 (host integer helpers)
 
 Every operator returns ``(result, CertBundle, ExpectedEffect)``; arrays are torch CUDA tensors.  All arithmetic on
@@ -114,6 +117,11 @@ L.register_prototypes({
                               C.POINTER(CAssocResult), C.POINTER(_dbl), C.POINTER(CMapUpdateCfg), _vp, _vp, _vp]),
     "gcs_map_merge_reduce": (_int, [_vp, _vp, C.POINTER(CAtlas), _i32, _dbl, _i32, _dbl, _dbl, _vp]),
     "gcs_export_map_points": (_int, [_vp, _vp, C.POINTER(CAtlas), C.POINTER(_i32), _i32, _dbl, C.POINTER(CMapExport), _i64, _vp]),
+    "gcs_map_fuse": (_int, [_vp, _vp, C.POINTER(CAtlas), _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dbl, _i64, _dbl, _vp]),
+    "gcs_map_insert_masked": (_int, [_vp, _vp, C.POINTER(CAtlas), _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dbl, _i64, _dbl,
+                                     _i64, _vp, _vp, _vp]),
+    "gcs_map_cull": (_int, [_vp, _vp, C.POINTER(CAtlas), _i32, _dbl, _i32, _vp]),
+    "gcs_map_forget": (_int, [_vp, _vp, C.POINTER(CAtlas), _i32, _dbl]),
 })
 
 
@@ -911,3 +919,194 @@ def primitive_map_merge_reduce(atlas_map: AtlasMap, tile_id: int,
                                     compute=io.compute())
     res = PrimitiveMapMergeReduceResult(atlas_map=atlas_map, tile_id=tile_id, n_merged=n_merged, frobenius_correction=float(n_merged))
     return res, cert, ExpectedEffect("primitive_map_merge_reduce", float(max_pairs), float(n_merged))
+
+
+# --------------------------------------------------------------------------------------------------
+# the per-tile map operators, one call = one tile.  map_update_step12b runs the same arithmetic for all
+# active tiles of a scan in one pass; these keep the reference's own granularity and signatures.
+# --------------------------------------------------------------------------------------------------
+def _optr(t):
+    return L.ptr(t) if t is not None else None
+
+
+def block_associations_for_fuse(result: PrimitiveAssociationResult, valid_mask, block_size: int = constants.GC_ASSOC_BLOCK_SIZE):
+    """
+    block_associations_for_fuse (fl/backend/operators/primitive_association.py:561-588): the (N, K) association cut into
+    blocks of block_size rows (row indices clipped to N-1, rows past N or with valid_mask clear get responsibility 0).
+    Pure re-indexing of device arrays.  Returns (meas_idx, candidate_tile_ids, candidate_slots, responsibilities,
+    valid_rows) with leading shape (n_blocks, block_size).
+    """
+    resp = result.responsibilities
+    n_total, _k = resp.shape
+    block = int(max(1, block_size))
+    n_blocks = (n_total + block - 1) // block
+    meas_idx = torch.arange(n_blocks * block, dtype=torch.int32, device=resp.device).reshape(n_blocks, block)
+    clipped = torch.clamp(meas_idx, max=n_total - 1)
+    vm = _IO(resp.device).dev_in(valid_mask, torch.uint8).reshape(-1).to(torch.bool)
+    li = clipped.long()
+    valid_rows = (meas_idx < n_total) & vm[li]
+    return (clipped, result.candidate_tile_ids[li], result.candidate_slots[li],
+            resp[li] * valid_rows[:, :, None].to(resp.dtype), valid_rows)
+
+
+@dataclass
+class PrimitiveMapFuseResult:
+    atlas_map: AtlasMap
+    tile_id: int
+    n_fused: int
+
+
+def primitive_map_fuse(atlas_map: AtlasMap, tile_id: int, target_slots, Lambdas_meas, thetas_meas, etas_meas, weights_meas,
+                       responsibilities, timestamp: float, scan_seq: int = 0, valid_mask=None, colors_meas=None,
+                       sources_meas=None, eps_psd: float = constants.GC_EPS_PSD, eps_mass: float = constants.GC_EPS_MASS,
+                       fuse_chunk_size: int = constants.GC_FUSE_CHUNK_SIZE, chart_id: str = constants.GC_CHART_ID,
+                       anchor_id: str = "primitive_map") -> Tuple[PrimitiveMapFuseResult, CertBundle, ExpectedEffect]:
+    """
+    primitive_map_fuse (fl/backend/structures/primitive_map.py:992-1163), in place on the device pool.  The tile is
+    created if missing; an empty proposal list is the reference's exact no-op (the new tile is then not kept, :1031-1041).
+    fuse_chunk_size only sets the reference's chunking of one scatter-add and does not change its result: ignored.
+    """
+    del eps_psd, fuse_chunk_size
+    tile_id = int(tile_id)
+    io = _IO(atlas_map.device)
+    slots = io.dev_in(target_slots, torch.int32).reshape(-1)
+    n = int(slots.shape[0])
+    if n == 0:
+        return (PrimitiveMapFuseResult(atlas_map=atlas_map, tile_id=tile_id, n_fused=0),
+                CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id), ExpectedEffect("primitive_map_fuse", 0.0, 0.0))
+    Lm = io.dev_in(Lambdas_meas, F64, (n, 3, 3))
+    th = io.dev_in(thetas_meas, F64, (n, 3))
+    et = io.dev_in(etas_meas, F64, (n, constants.GC_VMF_N_LOBES, 3))
+    wm = io.dev_in(weights_meas, F64, (n,))
+    rs = io.dev_in(responsibilities, F64, (n,))
+    vm = io.dev_in(valid_mask, torch.uint8, (n,)) if valid_mask is not None else None
+    # the reference ignores colour / source arrays shorter than the proposal list (:1081-1095)
+    cm = io.dev_in(colors_meas, F64) if colors_meas is not None and len(colors_meas) >= n else None
+    sm = io.dev_in(sources_meas, torch.int32).reshape(-1) if sources_meas is not None and len(sources_meas) >= n else None
+    row = atlas_map.ensure_tile(tile_id)
+    stats_d = io.zeros(4)
+    ca = atlas_map._c()
+    io.ctx.check(io.ctx.lib.gcs_map_fuse(io.ctx.handle, io.stream(), C.byref(ca), int(row), L.ptr(slots), L.ptr(Lm), L.ptr(th),
+                                         L.ptr(et), L.ptr(wm), L.ptr(rs), _optr(vm), _optr(cm), _optr(sm), n, float(timestamp),
+                                         int(scan_seq), float(eps_mass), L.ptr(stats_d)))
+    n_unique = int(io.host(stats_d)[0])
+    res = PrimitiveMapFuseResult(atlas_map=atlas_map, tile_id=tile_id, n_fused=n_unique)
+    cert = CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id, compute=io.compute())
+    return res, cert, ExpectedEffect("primitive_map_fuse", float(n), float(n_unique))
+
+
+@dataclass
+class PrimitiveMapInsertResult:
+    atlas_map: AtlasMap
+    tile_id: int
+    n_inserted: int
+    new_ids: torch.Tensor
+    target_slots: Optional[torch.Tensor] = None   # not in the reference's result: the evicted / filled slots, (K,) int32
+
+
+def primitive_map_insert_masked(atlas_map: AtlasMap, tile_id: int, Lambdas_new, thetas_new, etas_new, weights_new,
+                                timestamp: float, valid_new_mask, scan_seq: int = 0,
+                                recency_decay_lambda: float = constants.GC_RECENCY_DECAY_LAMBDA, colors_new=None,
+                                sources_new=None, chart_id: str = constants.GC_CHART_ID,
+                                anchor_id: str = "primitive_map_insert_masked"
+                                ) -> Tuple[PrimitiveMapInsertResult, CertBundle, ExpectedEffect]:
+    """primitive_map_insert_masked (fl/backend/structures/primitive_map.py:807-981), in place on the device pool."""
+    tile_id = int(tile_id)
+    io = _IO(atlas_map.device)
+    Ln = io.dev_in(Lambdas_new, F64)
+    k = int(Ln.shape[0])
+    if k < 1 or k > min(1024, atlas_map.m_tile):
+        raise ValueError(f"primitive_map_insert_masked: K={k} proposals outside [1, min(1024, m_tile={atlas_map.m_tile})]")
+    Ln = Ln.reshape(k, 3, 3)
+    th = io.dev_in(thetas_new, F64, (k, 3))
+    et = io.dev_in(etas_new, F64, (k, constants.GC_VMF_N_LOBES, 3))
+    wn = io.dev_in(weights_new, F64, (k,))
+    vm = io.dev_in(valid_new_mask, torch.uint8, (k,))
+    cn = io.dev_in(colors_new, F64, (k, 3)) if colors_new is not None else None
+    sn = io.dev_in(sources_new, torch.int32, (k,)) if sources_new is not None else None
+    row = atlas_map.ensure_tile(tile_id)
+    ids_d = io.empty(k, dtype=torch.int64)
+    slots_d = io.empty(k, dtype=torch.int32)
+    stats_d = io.zeros(4)
+    ca = atlas_map._c()
+    io.ctx.check(io.ctx.lib.gcs_map_insert_masked(io.ctx.handle, io.stream(), C.byref(ca), int(row), L.ptr(Ln), L.ptr(th), L.ptr(et),
+                                                  L.ptr(wn), L.ptr(vm), _optr(cn), _optr(sn), k, float(timestamp), int(scan_seq),
+                                                  float(recency_decay_lambda), int(atlas_map.next_global_id), L.ptr(ids_d),
+                                                  L.ptr(slots_d), L.ptr(stats_d)))
+    st = io.host(stats_d)
+    n_inserted, dropped = int(st[0]), int(st[1])
+    atlas_map.next_global_id = int(atlas_map.next_global_id + n_inserted)
+    atlas_map.total_count = int(atlas_map.total_count + n_inserted)
+    cert = (CertBundle.create_approx(chart_id=chart_id, anchor_id=anchor_id, triggers=["insert_unfilled_budget"],
+                                     frobenius_applied=False, compute=io.compute())
+            if dropped > 0 else CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id, compute=io.compute()))
+    res = PrimitiveMapInsertResult(atlas_map=atlas_map, tile_id=tile_id, n_inserted=n_inserted, new_ids=ids_d, target_slots=slots_d)
+    return res, cert, ExpectedEffect("primitive_map_insert_masked", float(n_inserted), float(n_inserted))
+
+
+@dataclass
+class PrimitiveMapCullResult:
+    atlas_map: AtlasMap
+    tile_id: int
+    n_culled: int
+    mass_dropped: float
+
+
+def primitive_map_cull(atlas_map: AtlasMap, tile_id: int,
+                       weight_threshold: float = constants.GC_PRIMITIVE_CULL_WEIGHT_THRESHOLD,
+                       max_primitives: Optional[int] = None, chart_id: str = constants.GC_CHART_ID,
+                       anchor_id: str = "primitive_map") -> Tuple[PrimitiveMapCullResult, CertBundle, ExpectedEffect]:
+    """
+    primitive_map_cull (fl/backend/structures/primitive_map.py:1175-1304), in place on the device pool: an absent or
+    empty tile and "nothing below the threshold" are exact no-ops; otherwise the budgeting certificate with
+    mass_epsilon_ratio = mass_dropped / (sum of the tile's weights + eps_mass).
+    """
+    tile_id = int(tile_id)
+
+    def no_op():
+        return (PrimitiveMapCullResult(atlas_map=atlas_map, tile_id=tile_id, n_culled=0, mass_dropped=0.0),
+                CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id), ExpectedEffect("primitive_map_cull", 0.0, 0.0))
+
+    row = atlas_map.tiles.get(tile_id)
+    if row is None:
+        return no_op()
+    io = _IO(atlas_map.device)
+    stats_d = io.zeros(4)
+    ca = atlas_map._c()
+    io.ctx.check(io.ctx.lib.gcs_map_cull(io.ctx.handle, io.stream(), C.byref(ca), int(row), float(weight_threshold),
+                                         -1 if max_primitives is None else int(max_primitives), L.ptr(stats_d)))
+    st = io.host(stats_d)
+    n_culled, mass_dropped = int(st[0]), float(st[1])
+    if n_culled == 0:
+        return no_op()
+    atlas_map.total_count = atlas_map.total_count - n_culled
+    cert = CertBundle.create_approx(chart_id=chart_id, anchor_id=anchor_id, triggers=["budgeting", "mass_drop"],
+                                    influence=InfluenceCert.identity().with_overrides(
+                                        mass_epsilon_ratio=mass_dropped / (float(st[2]) + constants.GC_EPS_MASS)),
+                                    compute=io.compute())
+    res = PrimitiveMapCullResult(atlas_map=atlas_map, tile_id=tile_id, n_culled=n_culled, mass_dropped=mass_dropped)
+    return res, cert, ExpectedEffect("primitive_map_cull", float(n_culled), float(n_culled))
+
+
+@dataclass
+class PrimitiveMapForgetResult:
+    atlas_map: AtlasMap
+    tile_id: int
+
+
+def primitive_map_forget(atlas_map: AtlasMap, tile_id: int,
+                         forgetting_factor: float = constants.GC_PRIMITIVE_FORGETTING_FACTOR,
+                         chart_id: str = constants.GC_CHART_ID, anchor_id: str = "primitive_map"
+                         ) -> Tuple[PrimitiveMapForgetResult, CertBundle, ExpectedEffect]:
+    """primitive_map_forget (fl/backend/structures/primitive_map.py:1314-1384): weights *= gamma over the tile; exact."""
+    tile_id = int(tile_id)
+    res = PrimitiveMapForgetResult(atlas_map=atlas_map, tile_id=tile_id)
+    row = atlas_map.tiles.get(tile_id)
+    if row is None:
+        return res, CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id), ExpectedEffect("primitive_map_forget", 0.0, 0.0)
+    gamma = float(forgetting_factor)
+    io = _IO(atlas_map.device)
+    ca = atlas_map._c()
+    io.ctx.check(io.ctx.lib.gcs_map_forget(io.ctx.handle, io.stream(), C.byref(ca), int(row), gamma))
+    return (res, CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id, compute=io.compute()),
+            ExpectedEffect("primitive_map_forget", 1.0 - gamma, 1.0 - gamma))

@@ -485,6 +485,49 @@ int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int
                    const gcs_assoc_result* assoc, const double* pose6 /*host z_t*/, const gcs_map_update_cfg* cfg,
                    int64_t* out_new_ids, int32_t* out_insert_slots, double* stats);
 
+/* ---- a14, one operator at a time: the per-tile map operators behind gcs_map_update, with the reference's own
+ *      granularity (primitive_map_fuse / insert_masked / cull / forget keep their Python signatures).
+ *      tile_index = pool row of the tile (the host layer creates the empty tile first, as the reference does).
+ *      All array arguments are device pointers.                                                                    */
+
+/* primitive_map_fuse (fl/backend/structures/primitive_map.py:992-1163), one (block, tile) call: Product-of-Experts
+ * scatter-add of n proposals into target_slots (int32, proposals with a slot outside [0, m_tile) are dropped as a JAX
+ * scatter drops them), r = responsibilities * valid_mask (valid_mask NULL: all valid); camera / lidar masses only when
+ * sources_meas is given, camera colour accumulators only when colors_meas is given too; rgb and colors of the whole
+ * tile recomputed; timestamps stamped at every named slot, masked or not (:1112); scan-seq stamps where sum r > 0.
+ * stats (dev double[4]): [0] n_fused = number of distinct slots.  n <= 16384.                                      */
+int gcs_map_fuse(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, int32_t tile_index, const int32_t* target_slots,
+                 const double* Lambdas_meas /*(n,3,3)*/, const double* thetas_meas /*(n,3)*/,
+                 const double* etas_meas /*(n,3,3)*/, const double* weights_meas /*(n)*/,
+                 const double* responsibilities /*(n)*/, const uint8_t* valid_mask /*(n) or NULL*/,
+                 const double* colors_meas /*(n,3) or NULL*/, const int32_t* sources_meas /*(n) or NULL*/, int32_t n,
+                 double timestamp, int64_t scan_seq, double eps_mass, double* stats);
+
+/* primitive_map_insert_masked (primitive_map.py:807-981): the k lowest-retention slots of the tile (empty first,
+ * retention = weight * exp(-lambda * max(0, scan_seq - last_supported)), stable by slot: _select_lowest_mass_slots_fixed
+ * :326-353) receive the proposals whose valid_new_mask is set; ids next_global_id + (running count of set masks).
+ * colors_new NULL = zeros, sources_new NULL = all lidar (:884-893).  out_new_ids (k) int64, -1 = not inserted;
+ * out_target_slots (k) int32.  stats (dev double[4]): [0] n_inserted, [1] masked-out proposals, [2] valid slots after.
+ * k <= min(1024, m_tile).                                                                                          */
+int gcs_map_insert_masked(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, int32_t tile_index,
+                          const double* Lambdas_new, const double* thetas_new, const double* etas_new,
+                          const double* weights_new, const uint8_t* valid_new_mask, const double* colors_new,
+                          const int32_t* sources_new, int32_t k, double timestamp, int64_t scan_seq,
+                          double recency_decay_lambda, int64_t next_global_id, int64_t* out_new_ids,
+                          int32_t* out_target_slots, double* stats);
+
+/* primitive_map_cull (primitive_map.py:1175-1304): clear valid slots with weight < weight_threshold; with
+ * max_primitives >= 0 and more survivors than that, the threshold becomes the weight of rank max_primitives in the
+ * descending order of weights * valid (:1226-1232).  max_primitives < 0 = None.
+ * stats (dev double[4]): [0] n_culled, [1] mass_dropped, [2] sum of all slot weights (the certificate's denominator),
+ * [3] valid slots left.                                                                                            */
+enum { GCS_CULL_N = 0, GCS_CULL_MASS, GCS_CULL_SUM_W, GCS_CULL_N_LEFT, GCS_CULL_NSTATS = 4 };
+int gcs_map_cull(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, int32_t tile_index, double weight_threshold,
+                 int32_t max_primitives, double* stats);
+
+/* primitive_map_forget (primitive_map.py:1314-1384): weights *= forgetting_factor over every slot of the tile.      */
+int gcs_map_forget(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, int32_t tile_index, double forgetting_factor);
+
 #ifdef __cplusplus
 }
 #endif

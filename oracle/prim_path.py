@@ -533,7 +533,7 @@ def primitive_map_fuse(atlas, tile_id, target_slots, Lam, th, eta, w_meas, resp,
     if target_slots.shape[0] == 0:
         return 0
     M = t["Lambdas"].shape[0]
-    r = (resp * valid_mask.astype(np.float64)).astype(np.float64)
+    r = (resp * valid_mask.astype(np.float64)).astype(np.float64) if valid_mask is not None else np.asarray(resp, np.float64)
     dL = np.zeros((M, 3, 3)); dth = np.zeros((M, 3)); det = np.zeros((M, VMF_N_LOBES, 3)); dw = np.zeros(M)
     drs = np.zeros(M); dcam = np.zeros(M); dlid = np.zeros(M); dacc = np.zeros((M, 3)); dden = np.zeros(M)
     idx = target_slots
@@ -542,11 +542,13 @@ def primitive_map_fuse(atlas, tile_id, target_slots, Lam, th, eta, w_meas, resp,
     np.add.at(det, idx, r[:, None, None] * eta)
     np.add.at(dw, idx, r * w_meas)
     np.add.at(drs, idx, r)
-    cc = np.clip(colors, 0.0, 1.0)
-    w_cam = r * w_meas * (sources == 0).astype(np.float64)
-    w_lid = r * w_meas * (sources == 1).astype(np.float64)
-    np.add.at(dcam, idx, w_cam); np.add.at(dlid, idx, w_lid)
-    np.add.at(dacc, idx, cc * w_cam[:, None]); np.add.at(dden, idx, w_cam)
+    if sources is not None:                       # :1084-1095: masses need sources, colour accumulators need both
+        w_cam = r * w_meas * (sources == 0).astype(np.float64)
+        w_lid = r * w_meas * (sources == 1).astype(np.float64)
+        np.add.at(dcam, idx, w_cam); np.add.at(dlid, idx, w_lid)
+        if colors is not None:
+            cc = np.clip(colors, 0.0, 1.0)
+            np.add.at(dacc, idx, cc * w_cam[:, None]); np.add.at(dden, idx, w_cam)
     t["cam_mass"] = t["cam_mass"] + dcam
     t["lidar_mass"] = t["lidar_mass"] + dlid
     t["rgb_cam_accum"] = t["rgb_cam_accum"] + dacc
@@ -580,8 +582,10 @@ def primitive_map_insert_masked(atlas, tile_id, Lam, th, eta, w_new, timestamp, 
     n_ins = int(np.sum(do))
     prefix = np.cumsum(do.astype(np.int64)) - 1
     new_ids = np.where(do, np.int64(atlas["next_global_id"]) + prefix, np.int64(-1))
-    is_cam = (sources == 0).astype(np.float64)
-    is_lid = (sources == 1).astype(np.float64)
+    if colors is None:                            # :884-893 defaults: black, all lidar
+        colors = np.zeros((K, 3))
+    is_cam = (sources == 0).astype(np.float64) if sources is not None else np.zeros(K)
+    is_lid = (sources == 1).astype(np.float64) if sources is not None else np.ones(K)
     cam_new, lid_new = w_new * is_cam, w_new * is_lid
     rgb_new = np.where((cam_new > 0.0)[:, None], np.clip(colors, 0.0, 1.0), 0.5)
 
@@ -606,11 +610,18 @@ def primitive_map_insert_masked(atlas, tile_id, Lam, th, eta, w_new, timestamp, 
     return n_ins, new_ids, slots
 
 
-def primitive_map_cull(atlas, tile_id, thr=CULL_THRESHOLD):
+def primitive_map_cull(atlas, tile_id, thr=CULL_THRESHOLD, max_primitives=None):
+    """primitive_map.py:1175-1304 (max_primitives: :1226-1232, the threshold becomes the weight of descending rank
+    max_primitives of weights * valid when more than max_primitives primitives would survive)."""
     t = atlas["tiles"].get(int(tile_id))
     if t is None or t["count"] == 0:
         return 0, 0.0
     below = t["valid_mask"] & (t["weights"] < thr)
+    n_keep = t["count"] - int(np.sum(below))
+    if max_primitives is not None and n_keep > max_primitives:
+        sw = np.sort(t["weights"] * t["valid_mask"].astype(np.float64))[::-1]
+        if max_primitives < len(sw):
+            below = t["valid_mask"] & (t["weights"] < float(sw[max_primitives]))
     n = int(np.sum(below))
     if n == 0:
         return 0, 0.0
