@@ -56,3 +56,14 @@ GC_K_INSERT_TILE = GC_K_INSERT  # :477
 # point takes tau explicitly and 0.1 is only the harness default.
 GC_B_BINS = 48
 GC_TAU_SOFT_ASSIGN = 0.1
+
+# evidence fusion (pipeline steps 9-11; fl/common/constants.py and PipelineConfig, fl/backend/pipeline.py:104-125)
+GC_EXC_EPS = 1e-12  # constants.py:75
+GC_ALPHA_MIN = 1.0  # :89
+GC_ALPHA_MAX = 1.0  # :90
+GC_KAPPA_SCALE = 1.0  # :91
+GC_C0_COND = 1e6  # :92
+GC_POWER_BETA_MIN = 0.25  # pipeline.py:119
+GC_POWER_BETA_EXC_C = 50.0  # pipeline.py:120
+GC_POWER_BETA_Z_C = 1.0  # pipeline.py:121
+GC_D_Z = 22

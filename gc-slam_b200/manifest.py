@@ -35,6 +35,7 @@ ENTRY_POINTS = {
     "map_recency_inflate": "gcs_map_recency_inflate",
     "map_export": "gcs_export_map_points",
     "map_merge_reduce": "gcs_map_merge_reduce",
+    "evidence_fusion": "gcs_evidence_fusion",
     "map_fuse": "gcs_map_fuse",
     "map_insert_masked": "gcs_map_insert_masked",
     "map_cull": "gcs_map_cull",

@@ -342,3 +342,43 @@ def hypothesis_evidence_stack(n_hyp: int, dim: int, seed: int, indefinite: bool 
         w[0] = 1e-4
         w[-1] = 0.0
     return np.stack(Ls), np.stack(hs), np.stack(zs), w
+
+
+def fusion_inputs(n_hyp: int, seed: int, indefinite: bool = False):
+    """
+    Inputs of the evidence-fusion step (pipeline.py:1038-1207) for K hypotheses: LiDAR evidence living on the pose block
+    (as build_combined_lidar_evidence_22d embeds it), IMU + odometry evidence coupling pose, velocity, biases and the time
+    offset, a predicted belief (L, h) with eigenvalues over eight decades, and the certificate-level scalars of the two
+    control laws.  `indefinite`: priors with a few negative eigenvalues and an asymmetric entry, so that the PSD
+    projection of the posterior clamps and reports a projection delta.
+    """
+    rng = np.random.default_rng(seed)
+    D = 22
+    out = {k: [] for k in ("L_lidar", "h_lidar", "L_other", "h_other", "L_prior", "h_prior")}
+    for k in range(n_hyp):
+        a = rng.normal(size=(6, 6))
+        Ll = np.zeros((D, D))
+        Ll[:6, :6] = a @ a.T * 10.0 ** rng.uniform(1.0, 4.0) + np.diag(10.0 ** rng.uniform(0.0, 3.0, 6))
+        Ll[2, 2] *= 10.0 ** rng.uniform(-2.0, 1.0)          # weak / strong z: drives z_to_xy
+        hl = Ll @ rng.normal(0.0, 0.05, D)
+        b = rng.normal(size=(16, 16)) * 10.0 ** rng.uniform(-1.0, 1.5, 16)[None, :]
+        Lo = np.zeros((D, D))
+        Lo[:16, :16] = b @ b.T
+        Lo[15, 6:9] *= 10.0 ** rng.uniform(-1.0, 1.0); Lo[6:9, 15] = Lo[15, 6:9]      # dt-velocity coupling vs dt-pose: dt_asymmetry
+        Lo[16:, 16:] = np.diag(10.0 ** rng.uniform(-4.0, 0.0, 6))
+        ho = Lo @ rng.normal(0.0, 0.05, D)
+        Q, _ = np.linalg.qr(rng.normal(size=(D, D)))
+        ev = 10.0 ** rng.uniform(-2.0, 6.0, D)
+        if indefinite:
+            ev[:2] = -10.0 ** rng.uniform(3.0, 5.0, 2)
+        Lp = (Q * ev) @ Q.T
+        Lp = 0.5 * (Lp + Lp.T)
+        if indefinite:
+            Lp[3, 7] += 1e-3
+        hp = Lp @ rng.normal(0.0, 0.1, D)
+        for key, v in zip(out, (Ll, hl, Lo, ho, Lp, hp)):
+            out[key].append(v)
+    res = {k: np.stack(v) for k, v in out.items()}
+    res.update(ess_total=10.0 ** rng.uniform(0.0, 4.0, n_hyp), dt_effect=10.0 ** rng.uniform(-2.0, 1.0, n_hyp),
+               extrinsic_effect=10.0 ** rng.uniform(-2.0, 1.0, n_hyp), nll_per_ess=rng.uniform(0.0, 2.0, n_hyp))
+    return res

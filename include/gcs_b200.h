@@ -528,6 +528,35 @@ int gcs_map_cull(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, int32_t til
 /* primitive_map_forget (primitive_map.py:1314-1384): weights *= forgetting_factor over every slot of the tile.      */
 int gcs_map_forget(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, int32_t tile_index, double forgetting_factor);
 
+/* ---- (8f-3, fusion half) evidence fusion for all hypotheses of a scan in one launch: pipeline steps 9-11
+ *      fl/backend/pipeline.py:1038-1193 (raw evidence, observability sentinels, power tempering beta, pose-block
+ *      conditioning), fl/backend/operators/excitation.py:15-64 (Fisher-derived scaling of the prior),
+ *      fl/backend/operators/fusion.py:46-230 (fusion scale alpha, InfoFusionAdditive with DomainProjectionPSD,
+ *      fl/common/primitives.py:80-123).  Stacks are (K, 22, 22) / (K, 22), all (dev).
+ *      cert_scalars (K, 4): the certificate-level inputs of the two control laws, per hypothesis:
+ *      support.ess_total, excitation.dt_effect + extrinsic_effect, mismatch.nll_per_ess of the aggregated evidence
+ *      certificate (host scalars in the reference as well).  L_other / h_other = the IMU + odometry evidence (NULL: none).
+ *      Optional outputs (NULL to skip): tempered evidence, scaled prior.  rec: (K, GCS_FU_NREC).                   */
+enum { GCS_FU_SKIP_TEMPERING = 1,       /* beta = 1, evidence taken as given (info_fusion_additive on its own)      */
+       GCS_FU_SKIP_PRIOR_SCALING = 2,   /* prior taken as given                                                     */
+       GCS_FU_ALPHA_GIVEN = 4 };        /* alpha = cfg.alpha_override instead of fusion_scale_from_certificates     */
+enum { GCS_FU_IN_ESS_TOTAL = 0, GCS_FU_IN_EXC_TOTAL, GCS_FU_IN_NLL_PER_ESS, GCS_FU_IN_RESERVED };
+typedef struct {
+  double power_beta_min, power_beta_z_c, power_beta_exc_c;   /* PipelineConfig, pipeline.py:119-121 */
+  double alpha_min, alpha_max, c0_cond;                      /* fusion.py:49-52                     */
+  double eps_mass, eps_psd, exc_eps;
+  double alpha_override;
+  int32_t flags, reserved;
+} gcs_fusion_cfg;
+enum { GCS_FU_BETA = 0, GCS_FU_DT_ASYMMETRY, GCS_FU_Z_TO_XY, GCS_FU_ESS_TO_EXC, GCS_FU_S_DT, GCS_FU_S_EX,
+       GCS_FU_POSE_EIG_MIN, GCS_FU_POSE_EIG_MAX, GCS_FU_POSE_COND, GCS_FU_POSE_NEAR_NULL, GCS_FU_ALPHA, GCS_FU_QUALITY,
+       GCS_FU_PSD_PROJECTION_DELTA, GCS_FU_PSD_SYM_DELTA, GCS_FU_POST_EIG_MIN, GCS_FU_POST_EIG_MAX, GCS_FU_POST_COND,
+       GCS_FU_POST_NEAR_NULL, GCS_FU_TRACE_INCREASE, GCS_FU_NREC = 24 };
+int gcs_evidence_fusion(gcs_ctx* ctx, void* stream, const double* L_lidar, const double* h_lidar, const double* L_other,
+                        const double* h_other, const double* L_prior, const double* h_prior, const double* cert_scalars,
+                        int n_hyp, int dim, const gcs_fusion_cfg* cfg, double* L_post, double* h_post, double* L_evidence,
+                        double* h_evidence, double* L_prior_scaled, double* h_prior_scaled, double* rec);
+
 #ifdef __cplusplus
 }
 #endif
