@@ -330,6 +330,18 @@ def prologue_combine_extra(n_hyp=64, reps=30):
     ms_imu = wall(lambda: imu.imu_scan_twist(dev[0], dev[1], dev[2], t0, t1, hp["sigma"], hp["rotvec0"], hp["gyro_bias"],
                                              hp["accel_bias"], g))
     ms_hb = wall(lambda: sharding.hypothesis_barycenter_projection(Ld, hd, wd, zd))
+    from gc_slam_b200 import fusion
+    from oracle import fusion as ofu
+    fi = synth.fusion_inputs(n_hyp, 17)
+    fd = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in fi.items() if v.ndim >= 2}
+    exc = fi["dt_effect"] + fi["extrinsic_effect"]
+    ms_fu = wall(lambda: fusion.evidence_fusion_batched(fd["L_lidar"], fd["h_lidar"], fd["L_other"], fd["h_other"], fd["L_prior"],
+                                                        fd["h_prior"], fi["ess_total"], exc, fi["nll_per_ess"]))
+    a = time.perf_counter()
+    for h in range(n_hyp):
+        ofu.evidence_fusion(fi["L_lidar"][h], fi["h_lidar"][h], fi["L_other"][h], fi["h_other"][h], fi["L_prior"][h], fi["h_prior"][h],
+                            fi["ess_total"][h], exc[h], fi["nll_per_ess"][h])
+    cpu_fu = (time.perf_counter() - a) * 1e3
     a = time.perf_counter()
     for h in range(4):
         oimu.imu_scan_twist(stamps, gyro, accel, t0, t1, float(hp["sigma"][h]), hp["rotvec0"][h], hp["gyro_bias"][h],
@@ -341,6 +353,7 @@ def prologue_combine_extra(n_hyp=64, reps=30):
     cpu_hb = (time.perf_counter() - a) * 1e3
     return {"n_hyp": n_hyp, "imu_scan_twist_ms": ms_imu, "imu_scan_twist_cpu_oracle_ms": cpu_imu,
             "hypothesis_combine_ms": ms_hb, "hypothesis_combine_cpu_oracle_ms": cpu_hb,
+            "evidence_fusion_ms": ms_fu, "evidence_fusion_cpu_oracle_ms": cpu_fu,
             "note": "wall clock per call incl. the host-side parameter upload and the certificate read-back; "
                     "512 IMU samples, 22-D evidence blocks"}
 

@@ -36,6 +36,8 @@ ENTRY_POINTS = {
     "map_export": "gcs_export_map_points",
     "map_merge_reduce": "gcs_map_merge_reduce",
     "evidence_fusion": "gcs_evidence_fusion",
+    "sparse_cost_matrix": "gcs_sparse_cost_matrix",
+    "sinkhorn_unbalanced_fixed_k": "gcs_sinkhorn_unbalanced_fixed_k",
     "map_fuse": "gcs_map_fuse",
     "map_insert_masked": "gcs_map_insert_masked",
     "map_cull": "gcs_map_cull",

@@ -17,6 +17,8 @@ Primitive-family LiDAR evidence operators -- host-side mirror of the reference's
   primitive_map_fuse, primitive_map_insert_masked, primitive_map_cull, primitive_map_forget (one tile per call)
                                      fl/backend/structures/primitive_map.py:807-1384
   block_associations_for_fuse        fl/backend/operators/primitive_association.py:561-588
+  compute_sparse_cost_matrix, sinkhorn_unbalanced_fixed_k (the association's inner functions, called by the reference's
+  start-up warm-up)                  fl/backend/operators/primitive_association.py:105-197
   ma_hex_stencil_tile_ids, tile_ids_from_xyz_batch   fl/common/tiling.py:126-209 (host integer helpers)
 
 Every operator returns ``(result, CertBundle, ExpectedEffect)``; arrays are torch CUDA tensors.  All arithmetic on
@@ -122,6 +124,8 @@ L.register_prototypes({
                                      _i64, _vp, _vp, _vp]),
     "gcs_map_cull": (_int, [_vp, _vp, C.POINTER(CAtlas), _i32, _dbl, _i32, _vp]),
     "gcs_map_forget": (_int, [_vp, _vp, C.POINTER(CAtlas), _i32, _dbl]),
+    "gcs_sparse_cost_matrix": (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _dbl, _dbl, _vp]),
+    "gcs_sinkhorn_unbalanced_fixed_k": (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _i32, _vp]),
 })
 
 
@@ -1110,3 +1114,48 @@ def primitive_map_forget(atlas_map: AtlasMap, tile_id: int,
     io.ctx.check(io.ctx.lib.gcs_map_forget(io.ctx.handle, io.stream(), C.byref(ca), int(row), gamma))
     return (res, CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id, compute=io.compute()),
             ExpectedEffect("primitive_map_forget", 1.0 - gamma, 1.0 - gamma))
+
+
+# --------------------------------------------------------------------------------------------------
+# the association's inner functions on their own (fl/backend/backend_node.py:884-905 calls them directly)
+# --------------------------------------------------------------------------------------------------
+def compute_sparse_cost_matrix(meas_positions, meas_directions, meas_kappas, map_positions, map_directions, map_kappas,
+                               candidate_indices, beta: float = 0.5, eig_min: float = 1e-12) -> torch.Tensor:
+    """_compute_sparse_cost_matrix_jax (primitive_association.py:152-197): (N, K) costs of the candidate pairs, on the device."""
+    io = _IO()
+    mp = io.dev_in(meas_positions)
+    n = int(mp.shape[0])
+    vp = io.dev_in(map_positions)
+    m = int(vp.shape[0])
+    cand = io.dev_in(candidate_indices, torch.int32)
+    if cand.dim() != 2 or int(cand.shape[0]) != n:
+        raise ValueError(f"candidate_indices must be ({n}, K), got {tuple(cand.shape)}")
+    k = int(cand.shape[1])
+    md, mk = io.dev_in(meas_directions, F64, (n, 3)), io.dev_in(meas_kappas, F64, (n,))
+    vd, vk = io.dev_in(map_directions, F64, (m, 3)), io.dev_in(map_kappas, F64, (m,))
+    out = io.empty(n, k)
+    io.ctx.check(io.ctx.lib.gcs_sparse_cost_matrix(io.ctx.handle, io.stream(), L.ptr(mp.reshape(n, 3)), L.ptr(md), L.ptr(mk), n,
+                                                   L.ptr(vp.reshape(m, 3)), L.ptr(vd), L.ptr(vk), m, L.ptr(cand), k, float(beta),
+                                                   float(eig_min), L.ptr(out)))
+    return out
+
+
+def sinkhorn_unbalanced_fixed_k(C, a, b, epsilon: float, tau_a: float, tau_b: float, K: int) -> torch.Tensor:
+    """_sinkhorn_unbalanced_fixed_k_jax (primitive_association.py:105-138): transport plan after K fixed iterations."""
+    io = _IO()
+    Cm = io.dev_in(C)
+    if Cm.dim() != 2:
+        raise ValueError(f"C must be (N, M), got {tuple(Cm.shape)}")
+    n, m = int(Cm.shape[0]), int(Cm.shape[1])
+    if m > 32:
+        raise ValueError(f"sinkhorn_unbalanced_fixed_k: {m} columns exceed the built budget of 32 (K_ASSOC is 8)")
+    av, bv = io.dev_in(a, F64, (n,)), io.dev_in(b, F64, (m,))
+    pi = io.empty(n, m)
+    io.ctx.check(io.ctx.lib.gcs_sinkhorn_unbalanced_fixed_k(io.ctx.handle, io.stream(), L.ptr(Cm), L.ptr(av), L.ptr(bv), n, m,
+                                                            float(epsilon), float(tau_a), float(tau_b), int(K), L.ptr(pi)))
+    return pi
+
+
+# the reference's private names, so that its warm-up block runs unchanged after the import swap
+_compute_sparse_cost_matrix_jax = compute_sparse_cost_matrix
+_sinkhorn_unbalanced_fixed_k_jax = sinkhorn_unbalanced_fixed_k

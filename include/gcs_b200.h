@@ -557,6 +557,23 @@ int gcs_evidence_fusion(gcs_ctx* ctx, void* stream, const double* L_lidar, const
                         int n_hyp, int dim, const gcs_fusion_cfg* cfg, double* L_post, double* h_post, double* L_evidence,
                         double* h_evidence, double* L_prior_scaled, double* h_prior_scaled, double* rec);
 
+/* ---- a12, the two inner functions of the association on their own (the reference calls them directly from its
+ *      start-up warm-up, fl/backend/backend_node.py:884-905).  All pointers (dev).
+ * _compute_sparse_cost_matrix_jax (fl/backend/operators/primitive_association.py:152-197):
+ *   out_cost[i,k] = |x_i - x_j|^2 + beta * H^2_vMF(dir_i kappa_i, dir_j kappa_j), j = candidate_indices[i,k]
+ *   (negative indices wrap, out-of-range indices clamp, as the gather there).                                       */
+int gcs_sparse_cost_matrix(gcs_ctx* ctx, void* stream, const double* meas_positions /*(N,3)*/,
+                           const double* meas_directions /*(N,3)*/, const double* meas_kappas /*(N)*/, int32_t n_meas,
+                           const double* map_positions /*(M,3)*/, const double* map_directions /*(M,3)*/,
+                           const double* map_kappas /*(M)*/, int32_t n_map, const int32_t* candidate_indices /*(N,K)*/,
+                           int32_t k_cand, double beta, double eig_min, double* out_cost /*(N,K)*/);
+/* _sinkhorn_unbalanced_fixed_k_jax (primitive_association.py:105-138): K = exp(-C / max(epsilon, 1e-12)), n_iters
+ * fixed iterations u = (a / (K v + 1e-12))^(1 / (1 + tau_a / eps)), v = (b / (K^T u + 1e-12))^(1 / (1 + tau_b / eps)),
+ * out_pi = diag(u) K diag(v).  cost (n_rows, n_cols) row-major, n_cols <= 32.                                         */
+int gcs_sinkhorn_unbalanced_fixed_k(gcs_ctx* ctx, void* stream, const double* cost, const double* a, const double* b,
+                                    int32_t n_rows, int32_t n_cols, double epsilon, double tau_a, double tau_b,
+                                    int32_t n_iters, double* out_pi);
+
 #ifdef __cplusplus
 }
 #endif
