@@ -258,15 +258,20 @@ __global__ void __launch_bounds__(kOpsBig) insert_masked_kernel(gcs_atlas A, int
   // eviction targets: k lowest retention, empty slots first, ties by slot index
   auto key = [&](int s) -> unsigned long long {
     const int64_t o = base + s;
+    const uint8_t v = A.valid[o];                         // three independent loads: the sweeps are latency-bound
+    const long long lss = A.last_supported_scan_seq[o];
+    const double w = A.weights[o];
     double keyv = -INFINITY;
-    if (A.valid[o]) {
-      long long dt = I.scan_seq - A.last_supported_scan_seq[o];
+    if (v) {
+      long long dt = I.scan_seq - lss;
       if (dt < 0) dt = 0;
-      keyv = A.weights[o] * exp(-I.lambda * (double)dt);
+      keyv = w * exp(-I.lambda * (double)dt);
     }
     return f64_orderable(keyv);
   };
-  cta_select_k(A.m_tile, k, key, sm.out, sm.hist, sm.scan, use_cache ? key_cache : nullptr);
+  auto empty = [&](int s) -> bool { return A.valid[base + s] == 0; };
+  if (!cta_select_min_sentinel(A.m_tile, k, empty, f64_orderable(-INFINITY), sm.out, sm.scan))
+    cta_select_k(A.m_tile, k, key, sm.out, sm.hist, sm.scan, use_cache ? key_cache : nullptr);
   s_do[tid] = (tid < k && I.valid_new[tid]) ? 1 : 0;
   __syncthreads();
   // inclusive scan of the proposal mask (Hillis-Steele over 1024 entries, double-buffered through sm.scan)

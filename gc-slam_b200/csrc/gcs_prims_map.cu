@@ -2,10 +2,11 @@
 //   a11  recency inflation, per-tile top-k view extraction
 //   a12  OT association (pool cost -> stable top-K -> unbalanced Sinkhorn, 50 fixed iterations)
 //   a13  pose evidence from soft correspondences (WLS translation + scatter-SVD rotation)
-//   a14  map update: PoE fuse (sorted segmented scatter, no float atomics), insert/evict, cull, forget
+//   a14  map update: PoE fuse (stable radix sort by target + segmented sums, no float atomics), insert/evict, cull, forget
 // All selections reproduce jnp.argsort / lax.sort semantics (stable, first operand is the only key) through
 // cta_select_k (gcs_select.cuh).  All floating reductions are fixed-order.
 #include <cooperative_groups.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "gcs_assoc.cuh"
 #include "gcs_select.cuh"
@@ -136,8 +137,11 @@ __global__ void __launch_bounds__(kBig) map_view_kernel(gcs_atlas A, TileList T,
   const int M = A.m_tile;
   const int64_t base = (int64_t)(ti < 0 ? 0 : ti) * M;
   auto key = [&](int s) -> unsigned long long {
-    double score = -1e30;
-    if (ti >= 0 && A.valid[base + s]) score = A.weights[base + s];
+    // both loads are issued unconditionally (the weight of an empty slot is simply not used): a dependent chain
+    // valid -> weight doubles the exposed latency of every item, and the select sweeps are latency-bound
+    const uint8_t v = A.valid[base + s];
+    const double w = A.weights[base + s];
+    const double score = (ti >= 0 && v) ? w : -1e30;
     return f64_orderable(-score);  // ascending sort of -score (primitive_map.py:316-320)
   };
   cta_select_k(M, m_view, key, sm.out, sm.hist, sm.scan, use_cache ? key_cache : nullptr);
@@ -659,7 +663,8 @@ struct UpdWs {
   long long* mtile; // (N) packed tile id of the world-frame mean
   double* novelty;  // (N)
   double* score;    // (N)
-  unsigned long long* pairs;  // (n_pairs_pow2) key<<32 | pair index, sorted
+  unsigned* pkeys;  // (n_pairs) target key = active tile * m_tile + slot (n_tiles * m_tile = no target), sorted
+  unsigned* pvals;  // (n_pairs) pair index, ascending within equal keys (stable sort)
   int* ins_idx;     // (T,k)
   uint8_t* ins_new; // (T,k)
   double* ins_w;    // (T,k)
@@ -710,40 +715,26 @@ __global__ void __launch_bounds__(kBig) upd_prepare_kernel(gcs_meas_batch B, int
   }
 }
 
-// Sort all (measurement, candidate) pairs by target (active tile, slot); pair index is the tie-break, so every
-// target's contributions are added in pair order: deterministic, no floating atomics.
-__global__ void __launch_bounds__(kBig) upd_sort_pairs_kernel(gcs_meas_batch B, int N, int K, gcs_assoc_result R, TileList T,
-                                                              int m_tile, int n_pow2, unsigned long long* __restrict__ out) {
-  extern __shared__ unsigned long long sp[];
-  const int n_pairs = N * K;
-  for (int p = threadIdx.x; p < n_pow2; p += kBig) {
-    unsigned long long key = 0xffffffffull;
-    if (p < n_pairs) {
-      const int i = p / K;
-      if (B.valid[i]) {
-        const long long tid = R.candidate_tile_ids[p];
-        int a = -1;
-        for (int q = 0; q < T.n; ++q)
-          if (T.id[q] == tid) { a = q; break; }
-        const long long slot = R.candidate_slots[p];
-        if (a >= 0 && slot >= 0 && slot < m_tile) key = (unsigned long long)a * (unsigned long long)m_tile + (unsigned long long)slot;
-      }
-    }
-    sp[p] = (key << 32) | (unsigned long long)(unsigned)p;
+// Target key of every (measurement, candidate) pair: (active tile, slot), or `none` for pairs without a target.  A
+// stable radix sort by that key (cub::DeviceRadixSort, pair index as the value) then lines up every target's
+// contributions in pair order: deterministic, no floating atomics.
+__global__ void __launch_bounds__(256) upd_pair_keys_kernel(gcs_meas_batch B, int N, int K, gcs_assoc_result R, TileList T,
+                                                            int m_tile, unsigned none, unsigned* __restrict__ keys,
+                                                            unsigned* __restrict__ vals) {
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= N * K) return;
+  unsigned key = none;
+  const int i = p / K;
+  if (B.valid[i]) {
+    const long long tid = R.candidate_tile_ids[p];
+    int a = -1;
+    for (int q = 0; q < T.n; ++q)
+      if (T.id[q] == tid) { a = q; break; }
+    const long long slot = R.candidate_slots[p];
+    if (a >= 0 && slot >= 0 && slot < m_tile) key = (unsigned)a * (unsigned)m_tile + (unsigned)slot;
   }
-  for (int size = 2; size <= n_pow2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      __syncthreads();
-      for (int t = threadIdx.x; t < (n_pow2 >> 1); t += kBig) {
-        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-        const bool up = ((lo & size) == 0);
-        const unsigned long long x = sp[lo], y = sp[hi];
-        if ((y < x) == up) { sp[lo] = y; sp[hi] = x; }
-      }
-    }
-  }
-  __syncthreads();
-  for (int p = threadIdx.x; p < n_pow2; p += kBig) out[p] = sp[p];
+  keys[p] = key;
+  vals[p] = (unsigned)p;
 }
 
 // One WARP per sorted position; the warp of a segment head folds its segment into the tile slot
@@ -751,27 +742,25 @@ __global__ void __launch_bounds__(kBig) upd_sort_pairs_kernel(gcs_meas_batch B, 
 // combines the 32 lane sums -- deterministic, and popular slots (hundreds of pairs) cost L/32 iterations instead of L.
 constexpr int kFuseVals = 29;   // dLambda 9, deta 9, dtheta 3, dw, dr, dcam, dlid, dacc 3, dden
 __global__ void __launch_bounds__(256) upd_fuse_kernel(gcs_atlas A, TileList T, gcs_meas_batch B, int K, gcs_assoc_result R,
-                                                       UpdWs W, int n_pow2, gcs_map_update_cfg cfg,
+                                                       UpdWs W, int n_pairs, unsigned none, gcs_map_update_cfg cfg,
                                                        double* __restrict__ part) {
   __shared__ double sred[8];
   const int lane = threadIdx.x & 31;
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   double fused_mass = 0.0;
-  if (q < n_pow2) {
-    const unsigned long long e = W.pairs[q];
-    const unsigned key = (unsigned)(e >> 32);
-    const bool head = key != 0xffffffffu && (q == 0 || (unsigned)(W.pairs[q - 1] >> 32) != key);   // warp-uniform
+  if (q < n_pairs) {
+    const unsigned key = W.pkeys[q];
+    const bool head = key != none && (q == 0 || W.pkeys[q - 1] != key);   // warp-uniform
     if (head) {
       double v[kFuseVals];
 #pragma unroll
       for (int k = 0; k < kFuseVals; ++k) v[k] = 0.0;
       for (int base = q;; base += 32) {
         const int j = base + lane;
-        bool valid = j < n_pow2;
-        unsigned long long ej = 0;
-        if (valid) { ej = W.pairs[j]; valid = (unsigned)(ej >> 32) == key; }
+        bool valid = j < n_pairs;
+        if (valid) valid = W.pkeys[j] == key;
         if (valid) {
-          const int p = (int)(unsigned)(ej & 0xffffffffull);
+          const int p = (int)W.pvals[j];
           const int i = p / K;
           const double r = R.responsibilities[p];
           const double wm = B.weights[i];
@@ -899,15 +888,21 @@ __global__ void __launch_bounds__(kBig) upd_insert_select_kernel(gcs_atlas A, Ti
   const int64_t base = (int64_t)T.index[a] * A.m_tile;
   auto key2 = [&](int s) -> unsigned long long {
     const int64_t o = base + s;
+    const uint8_t v = A.valid[o];                         // three independent loads (see map_view_kernel)
+    const long long lss = A.last_supported_scan_seq[o];
+    const double w = A.weights[o];
     double keyv = -INFINITY;
-    if (A.valid[o]) {
-      long long dt = cfg.scan_seq - A.last_supported_scan_seq[o];
+    if (v) {
+      long long dt = cfg.scan_seq - lss;
       if (dt < 0) dt = 0;
-      keyv = A.weights[o] * exp(-cfg.recency_decay_lambda * (double)dt);
+      keyv = w * exp(-cfg.recency_decay_lambda * (double)dt);
     }
     return f64_orderable(keyv);
   };
-  cta_select_k(A.m_tile, k, key2, sm.out, sm.hist, sm.scan, use_cache ? key_cache : nullptr);
+  // a tile with at least k empty slots evicts nothing: the first k empty slots in index order
+  auto empty = [&](int s) -> bool { return A.valid[base + s] == 0; };
+  if (!cta_select_min_sentinel(A.m_tile, k, empty, f64_orderable(-INFINITY), sm.out, sm.scan))
+    cta_select_k(A.m_tile, k, key2, sm.out, sm.hist, sm.scan, use_cache ? key_cache : nullptr);
   if (tid < k) W.ins_slot[a * k + tid] = sm.out[tid].idx;
   if (tid == 0) {
     int n = 0;
@@ -1234,19 +1229,25 @@ int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int
   GCS_REQUIRE(ctx, K >= 1 && k_ins >= 1 && k_ins <= 1024 && k_ins <= N && k_ins <= atlas->m_tile, "map_update: bad k_assoc/k_insert_tile");
   GCS_REQUIRE(ctx, (int64_t)n_tiles * atlas->m_tile < 0xffffffffll, "map_update: active tiles x m_tile overflow the 32-bit target key");
   const int n_pairs = N * K;
-  int n_pow2 = 1;
-  while (n_pow2 < n_pairs) n_pow2 <<= 1;
-  GCS_REQUIRE(ctx, n_pow2 <= 16384, "map_update: N_total*K_ASSOC=%d exceeds the in-CTA sort budget 16384", n_pairs);
+  GCS_REQUIRE(ctx, n_pairs <= (1 << 20), "map_update: N_total*K_ASSOC=%d exceeds the pair budget 2^20", n_pairs);
+  const unsigned none = (unsigned)n_tiles * (unsigned)atlas->m_tile;   // key of a pair without a target: sorts last
+  int key_bits = 1;
+  while ((none >> key_bits) != 0u) ++key_bits;
+  size_t cub_bytes = 0;
+  GCS_CHECK_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
+                                                      (const unsigned*)nullptr, (unsigned*)nullptr, n_pairs, 0, key_bits,
+                                                      (cudaStream_t)stream));
   const int block_rows = cfg->assoc_block_size > 0 ? cfg->assoc_block_size : 256;
   GCS_REQUIRE(ctx, block_rows * K <= 4096, "map_update: assoc_block_size*K_ASSOC exceeds 4096");
   const int n_blocks = (N + block_rows - 1) / block_rows;
   cudaStream_t st = (cudaStream_t)stream;
   const int sweep_blocks = (int)(cdivm(atlas->m_tile, 256) < 64 ? cdivm(atlas->m_tile, 256) : 64);
-  const int fuse_blocks = (n_pow2 + 7) / 8;   // upd_fuse_kernel: one warp per sorted position, 8 warps per block
+  const int fuse_blocks = (n_pairs + 7) / 8;   // upd_fuse_kernel: one warp per sorted position, 8 warps per block
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_Lw = take((size_t)N * 72), o_thw = take((size_t)N * 24), o_etw = take((size_t)N * 72), o_mt = take((size_t)N * 8),
-               o_nov = take((size_t)N * 8), o_sc = take((size_t)N * 8), o_pairs = take((size_t)n_pow2 * 8),
+               o_nov = take((size_t)N * 8), o_sc = take((size_t)N * 8), o_pk0 = take((size_t)n_pairs * 4), o_pv0 = take((size_t)n_pairs * 4),
+               o_pk1 = take((size_t)n_pairs * 4), o_pv1 = take((size_t)n_pairs * 4), o_cub = take(cub_bytes),
                o_ii = take((size_t)n_tiles * k_ins * 4), o_in = take((size_t)n_tiles * k_ins), o_iw = take((size_t)n_tiles * k_ins * 8),
                o_is = take((size_t)n_tiles * k_ins * 4), o_ni = take(16 * 4), o_part = take(128 * 8),
                o_fpart = take((size_t)fuse_blocks * 8), o_uq = take((size_t)n_blocks * 4),
@@ -1256,7 +1257,7 @@ int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int
   char* ws = (char*)ctx->ws;
   UpdWs W;
   W.Lw = (double*)(ws + o_Lw); W.thw = (double*)(ws + o_thw); W.etw = (double*)(ws + o_etw); W.mtile = (long long*)(ws + o_mt);
-  W.novelty = (double*)(ws + o_nov); W.score = (double*)(ws + o_sc); W.pairs = (unsigned long long*)(ws + o_pairs);
+  W.novelty = (double*)(ws + o_nov); W.score = (double*)(ws + o_sc); W.pkeys = (unsigned*)(ws + o_pk1); W.pvals = (unsigned*)(ws + o_pv1);
   W.ins_idx = (int*)(ws + o_ii); W.ins_new = (uint8_t*)(ws + o_in); W.ins_w = (double*)(ws + o_iw); W.ins_slot = (int*)(ws + o_is);
   W.n_ins = (int*)(ws + o_ni); W.part = (double*)(ws + o_part);
   double* fpart = (double*)(ws + o_fpart);
@@ -1265,11 +1266,14 @@ int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int
 
   upd_prepare_kernel<<<1, kBig, 0, st>>>(*batch, N, *assoc, pose6[0], pose6[1], pose6[2], pose6[3], pose6[4], pose6[5], *cfg, W);
   GCS_LAUNCH_CHECK(ctx);
-  GCS_CHECK_CUDA(ctx, gcs_smem_attr_once((const void*)upd_sort_pairs_kernel, 16384 * 8));
-  upd_sort_pairs_kernel<<<1, kBig, (size_t)n_pow2 * 8, st>>>(*batch, N, K, *assoc, T, atlas->m_tile, n_pow2, W.pairs);
+  upd_pair_keys_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(*batch, N, K, *assoc, T, atlas->m_tile, none, (unsigned*)(ws + o_pk0),
+                                                              (unsigned*)(ws + o_pv0));
   GCS_LAUNCH_CHECK(ctx);
+  GCS_CHECK_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ws + o_cub, cub_bytes, (const unsigned*)(ws + o_pk0), W.pkeys,
+                                                      (const unsigned*)(ws + o_pv0), W.pvals, n_pairs, 0, key_bits, st));
+  ctx->launches++;
   gcs_timing_begin(ctx, st);
-  upd_fuse_kernel<<<fuse_blocks, 256, 0, st>>>(*atlas, T, *batch, K, *assoc, W, n_pow2, *cfg, fpart);
+  upd_fuse_kernel<<<fuse_blocks, 256, 0, st>>>(*atlas, T, *batch, K, *assoc, W, n_pairs, none, *cfg, fpart);
   gcs_timing_end(ctx, st);
   GCS_LAUNCH_CHECK(ctx);
   if (cfg->strict_tile_state) {

@@ -16,6 +16,8 @@ __device__ __forceinline__ unsigned long long f64_orderable(double x) {
   return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 
+constexpr int kSelBatch = 4;   // keys evaluated back to back per thread before their shared-memory atomics
+
 struct KeyIdx {
   unsigned long long key;
   int idx;
@@ -75,8 +77,8 @@ __device__ inline void cta_bitonic_sort_u64(unsigned long long* s, int n_pow2) {
 // T_idx of the last tie that is taken; a single sweep then collects {key < T} and {key == T, index <= T_idx} in any
 // order and a bitonic sort by (key, index) puts them in the order of a stable sort.  When more than 1024 items tie on
 // the k-th key (e.g. a tile with fewer than k valid slots) T_idx comes from an index-ordered count of the ties.
-template <typename KeyFn>
-__device__ inline void cta_select_k(int n, int k, KeyFn key, KeyIdx* out, int* hist, int* scan, uint32_t* kc = nullptr) {
+template <bool KC, typename KeyFn>
+__device__ inline void cta_select_k_impl(int n, int k, KeyFn key, KeyIdx* out, int* hist, int* scan, uint32_t* kc) {
   (void)hist;
   __shared__ unsigned long long s_prefix;
   __shared__ int s_need, s_count, s_slot, s_tidx;
@@ -92,13 +94,20 @@ __device__ inline void cta_select_k(int n, int k, KeyFn key, KeyIdx* out, int* h
     const unsigned long long dm = (1ull << bits) - 1ull;
     for (int b = tid; b < 1024; b += nt) h[b] = 0;
     __syncthreads();
-    if (kc && shift == 54) {
-      for (int i = tid; i < n; i += nt) {
-        const unsigned long long kk = key(i);
-        kc[i] = (uint32_t)(kk >> 32);
-        atomicAdd(&h[(int)((kk >> sh) & dm)], 1);
+    if (KC && shift == 54) {
+      // kSelBatch keys are evaluated before any of them votes: the shared-memory atomics order the memory operations
+      // around them, so without the explicit batch every item pays its global-load latency on its own
+      for (int i0 = tid; i0 < n; i0 += kSelBatch * nt) {
+        unsigned long long kk[kSelBatch];
+#pragma unroll
+        for (int u = 0; u < kSelBatch; ++u) { const int i = i0 + u * nt; kk[u] = key(i < n ? i : n - 1); }   // clamped, branch-free
+#pragma unroll
+        for (int u = 0; u < kSelBatch; ++u) {
+          const int i = i0 + u * nt;
+          if (i < n) { kc[i] = (uint32_t)(kk[u] >> 32); atomicAdd(&h[(int)((kk[u] >> sh) & dm)], 1); }
+        }
       }
-    } else if (kc && sh >= 32) {
+    } else if (KC && sh >= 32) {
       // digit and prefix live in the cached high word
       const uint32_t m32 = (uint32_t)(mask >> 32), p32 = (uint32_t)(prefix >> 32);
       for (int i = tid; i < n; i += nt) {
@@ -107,10 +116,19 @@ __device__ inline void cta_select_k(int n, int k, KeyFn key, KeyIdx* out, int* h
       }
     } else {
       const uint32_t m32 = (uint32_t)(mask >> 32), p32 = (uint32_t)(prefix >> 32);
-      for (int i = tid; i < n; i += nt) {
-        if (kc && (kc[i] & m32) != p32) continue;
-        const unsigned long long kk = key(i);
-        if ((kk & mask) == prefix) atomicAdd(&h[(int)((kk >> sh) & dm)], 1);
+      for (int i0 = tid; i0 < n; i0 += kSelBatch * nt) {
+        unsigned long long kk[kSelBatch];
+        bool act[kSelBatch];
+#pragma unroll
+        for (int u = 0; u < kSelBatch; ++u) {
+          const int i = i0 + u * nt;
+          act[u] = i < n && !(KC && (kc[i] & m32) != p32);
+          if (KC) kk[u] = act[u] ? key(i) : 0ull;     // few items survive the cached high word
+          else kk[u] = key(i < n ? i : n - 1);        // clamped index: no branch between the loads of the batch
+        }
+#pragma unroll
+        for (int u = 0; u < kSelBatch; ++u)
+          if (act[u] && (kk[u] & mask) == prefix) atomicAdd(&h[(int)((kk[u] >> sh) & dm)], 1);
       }
     }
     __syncthreads();
@@ -150,12 +168,22 @@ __device__ inline void cta_select_k(int n, int k, KeyFn key, KeyIdx* out, int* h
     __syncthreads();
     {
       const uint32_t m32 = (uint32_t)(mask >> 32), p32 = (uint32_t)(prefix >> 32);
-      for (int i = tid; i < n; i += nt) {
-        if (kc && (kc[i] & m32) != p32) continue;
-        const unsigned long long kk = key(i);
-        if ((kk & mask) == prefix) {
-          const int sl = atomicAdd(&s_slot, 1);
-          out[sl].key = kk; out[sl].idx = i;
+      for (int i0 = tid; i0 < n; i0 += kSelBatch * nt) {
+        unsigned long long kk[kSelBatch];
+        bool act[kSelBatch];
+#pragma unroll
+        for (int u = 0; u < kSelBatch; ++u) {
+          const int i = i0 + u * nt;
+          act[u] = i < n && !(KC && (kc[i] & m32) != p32);
+          if (KC) kk[u] = act[u] ? key(i) : 0ull;     // few items survive the cached high word
+          else kk[u] = key(i < n ? i : n - 1);        // clamped index: no branch between the loads of the batch
+        }
+#pragma unroll
+        for (int u = 0; u < kSelBatch; ++u) {
+          if (act[u] && (kk[u] & mask) == prefix) {
+            const int sl = atomicAdd(&s_slot, 1);
+            out[sl].key = kk[u]; out[sl].idx = i0 + u * nt;
+          }
         }
       }
     }
@@ -175,7 +203,7 @@ __device__ inline void cta_select_k(int n, int k, KeyFn key, KeyIdx* out, int* h
     const int c0 = tid * chunk, c1 = (c0 + chunk < n) ? c0 + chunk : n;
     int n_eq = 0;
     const uint32_t t32 = (uint32_t)(T >> 32);
-    for (int i = c0; i < c1; ++i) n_eq += ((!kc || kc[i] == t32) && key(i) == T);
+    for (int i = c0; i < c1; ++i) n_eq += ((!KC || kc[i] == t32) && key(i) == T);
     int inc = n_eq;
     for (int o = 1; o < 32; o <<= 1) {
       const int v = __shfl_up_sync(0xffffffffu, inc, o);
@@ -188,7 +216,7 @@ __device__ inline void cta_select_k(int n, int k, KeyFn key, KeyIdx* out, int* h
     if (before < need && need <= before + n_eq) {
       int r = before;
       for (int i = c0; i < c1; ++i)
-        if ((!kc || kc[i] == t32) && key(i) == T && ++r == need) { s_tidx = i; break; }
+        if ((!KC || kc[i] == t32) && key(i) == T && ++r == need) { s_tidx = i; break; }
     }
     __syncthreads();
     T_idx = s_tidx;
@@ -197,12 +225,23 @@ __device__ inline void cta_select_k(int n, int k, KeyFn key, KeyIdx* out, int* h
   __syncthreads();
   {
     const uint32_t t32f = (uint32_t)(T >> 32);
-    for (int i = tid; i < n; i += nt) {
-      if (kc && kc[i] > t32f) continue;             // high word above the threshold's: key > T
-      const unsigned long long kk = key(i);
-      if (kk < T || (kk == T && i <= T_idx)) {
-        const int sl = atomicAdd(&s_slot, 1);
-        out[sl].key = kk; out[sl].idx = i;
+    for (int i0 = tid; i0 < n; i0 += kSelBatch * nt) {
+      unsigned long long kk[kSelBatch];
+      bool act[kSelBatch];
+#pragma unroll
+      for (int u = 0; u < kSelBatch; ++u) {
+        const int i = i0 + u * nt;
+        act[u] = i < n && !(KC && kc[i] > t32f);    // high word above the threshold's: key > T
+        if (KC) kk[u] = act[u] ? key(i) : 0ull;
+        else kk[u] = key(i < n ? i : n - 1);
+      }
+#pragma unroll
+      for (int u = 0; u < kSelBatch; ++u) {
+        const int i = i0 + u * nt;
+        if (act[u] && (kk[u] < T || (kk[u] == T && i <= T_idx))) {
+          const int sl = atomicAdd(&s_slot, 1);
+          out[sl].key = kk[u]; out[sl].idx = i;
+        }
       }
     }
   }
@@ -212,6 +251,51 @@ __device__ inline void cta_select_k(int n, int k, KeyFn key, KeyIdx* out, int* h
   for (int i = k + tid; i < kp; i += nt) { out[i].key = ~0ull; out[i].idx = 0x7fffffff; }
   __syncthreads();
   cta_bitonic_sort(out, kp);
+}
+
+template <typename KeyFn>
+__device__ inline void cta_select_k(int n, int k, KeyFn key, KeyIdx* out, int* hist, int* scan, uint32_t* kc = nullptr) {
+  if (kc) cta_select_k_impl<true>(n, k, key, out, hist, scan, kc);
+  else cta_select_k_impl<false>(n, k, key, out, hist, scan, kc);
+}
+
+// Fast path of a select whose smallest possible key `smin` is shared by many items (the empty slots of a tile in the
+// eviction select: key -inf): if at least k items are flagged by sent(i), the result of the stable sort is the first k
+// of them in index order -- one counting sweep and a partial second one instead of the radix passes, every one of which
+// would have to walk all the tied items again.  Returns false (out untouched) if fewer than k items are flagged; all
+// threads of the CTA must call and get the same answer.  scan: shared memory, >= 64 ints.
+template <typename SentFn>
+__device__ inline bool cta_select_min_sentinel(int n, int k, SentFn sent, unsigned long long smin, KeyIdx* out, int* scan) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, nw = nt >> 5;
+  int* wsum = scan;   // per-warp totals (<= 32), then [32] = grand total
+  const int chunk = (n + nt - 1) / nt;
+  const int c0 = tid * chunk < n ? tid * chunk : n, c1 = (c0 + chunk < n) ? c0 + chunk : n;
+  int cnt = 0;
+#pragma unroll 8
+  for (int i = c0; i < c1; ++i) cnt += sent(i) ? 1 : 0;
+  int inc = cnt;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  __syncthreads();   // scan may still be in use by the caller's previous select
+  if (lane == 31) wsum[tid >> 5] = inc;
+  __syncthreads();
+  int before = inc - cnt, total = 0;
+  for (int w = 0; w < nw; ++w) {
+    const int v = wsum[w];
+    if (w < (tid >> 5)) before += v;
+    total += v;
+  }
+  __syncthreads();   // wsum is free again
+  if (total < k) return false;
+  if (cnt > 0 && before < k) {
+    int r = before;
+    for (int i = c0; i < c1 && r < k; ++i)
+      if (sent(i)) { out[r].key = smin; out[r].idx = i; ++r; }
+  }
+  __syncthreads();
+  return true;
 }
 
 }  // namespace gcs
