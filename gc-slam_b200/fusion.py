@@ -108,14 +108,15 @@ def _launch(io, L_lidar, h_lidar, L_other, h_other, L_prior, h_prior, scal, cfg_
 def evidence_fusion_batched(L_lidar, h_lidar, L_imu_odom, h_imu_odom, L_prior, h_prior, ess_total, excitation_total,
                             nll_per_ess=None, config: Optional[FusionConfig] = None, chart_id: str = constants.GC_CHART_ID,
                             anchor_id: str = "evidence_fusion"
-                            ) -> Tuple[EvidenceFusionResult, List[List[CertBundle]], List[ExpectedEffect]]:
+                            ) -> Tuple[EvidenceFusionResult, "_PerHypothesis", "_PerHypothesis"]:
     """
     Steps 9-11 of process_scan_single_hypothesis (fl/backend/pipeline.py:1038-1207) for K hypotheses at once: the stacks may
     come straight from a K-hypothesis BinPathPlan (L22, h22) and go straight into hypothesis_barycenter_projection; one
     launch, one read-back of the (K, 24) record.  ess_total / excitation_total / nll_per_ess: per-hypothesis scalars of the
     aggregated evidence certificate (support.ess_total, excitation.dt_effect + extrinsic_effect, mismatch.nll_per_ess).
     Returns the result, and per hypothesis the certificates the reference appends at these steps
-    ([PowerTempering, ExcitationPriorScaling, fusion scale (exact), InfoFusionAdditive]) and the fusion's ExpectedEffect.
+    ([PowerTempering, ExcitationPriorScaling, fusion scale (exact), InfoFusionAdditive]) and the fusion's ExpectedEffect --
+    as sequences that build entry k when it is read (len(), indexing, iteration).
     """
     cfg = config or FusionConfig()
     io = _IO()
@@ -126,28 +127,55 @@ def evidence_fusion_batched(L_lidar, h_lidar, L_imu_odom, h_imu_odom, L_prior, h
     scal = np.stack([ess, exc, nll, np.zeros(K)], axis=1)
     L_post, h_post, aux, rec_d = _launch(io, L_lidar, h_lidar, L_imu_odom, h_imu_odom, L_prior, h_prior, scal, cfg._c())
     rec = io.host(rec_d)
-    certs, effects = [], []
-    for k in range(K):
-        r = rec[k]
-        beta, alpha = float(r[FU["BETA"]]), float(r[FU["ALPHA"]])
-        temper = CertBundle.create_approx(chart_id=chart_id, anchor_id=anchor_id, triggers=["PowerTempering"],
-                                          frobenius_applied=abs(1.0 - beta) > 0.0,
-                                          influence=InfluenceCert.identity().with_overrides(power_beta=beta))
-        exc_c = CertBundle.create_approx(chart_id=chart_id, anchor_id=anchor_id, triggers=["ExcitationPriorScaling"],
-                                         influence=InfluenceCert.identity().with_overrides(dt_scale=float(1.0 - r[FU["S_DT"]]),
-                                                                                           extrinsic_scale=float(1.0 - r[FU["S_EX"]])))
-        scale_c = CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id,
-                                          overconfidence=OverconfidenceCert(excitation_total=float(exc[k]),
-                                                                            ess_to_excitation=float(r[FU["ESS_TO_EXC"]]),
-                                                                            dt_asymmetry=float(r[FU["DT_ASYMMETRY"]]),
-                                                                            z_to_xy_ratio=float(r[FU["Z_TO_XY"]])),
-                                          conditioning=ConditioningCert(eig_min=float(r[FU["POSE_EIG_MIN"]]), eig_max=float(r[FU["POSE_EIG_MAX"]]),
-                                                                        cond=float(r[FU["POSE_COND"]]), near_null_count=int(r[FU["POSE_NEAR_NULL"]])),
-                                          influence=InfluenceCert.identity().with_overrides(trust_alpha=alpha))
-        fuse_c = _fusion_cert(r, alpha, chart_id, anchor_id, io if k == 0 else None)
-        certs.append([temper, exc_c, scale_c, fuse_c])
-        effects.append(ExpectedEffect("predicted_info_trace_increase", float(r[FU["TRACE_INCREASE"]]), None))
+    certs = _PerHypothesis(K, lambda k: _step_certs(rec[k], float(exc[k]), chart_id, anchor_id, io if k == 0 else None))
+    effects = _PerHypothesis(K, lambda k: ExpectedEffect("predicted_info_trace_increase", float(rec[k][FU["TRACE_INCREASE"]]), None))
     return EvidenceFusionResult(L_post, h_post, aux[0], aux[1], aux[2], aux[3], rec), certs, effects
+
+
+class _PerHypothesis:
+    """Sequence of per-hypothesis objects assembled on access: 64 hypotheses x 4 certificates are ~2 ms of Python object
+    construction, more than the launch and the read-back together, and most callers read a few of them."""
+
+    def __init__(self, n, make):
+        self._n, self._make, self._cache = int(n), make, {}
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(self._n))]
+        k = int(k)
+        if k < 0:
+            k += self._n
+        if not 0 <= k < self._n:
+            raise IndexError(k)
+        if k not in self._cache:
+            self._cache[k] = self._make(k)
+        return self._cache[k]
+
+    def __iter__(self):
+        return (self[k] for k in range(self._n))
+
+
+def _step_certs(r, exc_total, chart_id, anchor_id, io=None):
+    """[PowerTempering, ExcitationPriorScaling, fusion scale, InfoFusionAdditive] of one hypothesis (pipeline.py:1108-1207)."""
+    beta, alpha = float(r[FU["BETA"]]), float(r[FU["ALPHA"]])
+    temper = CertBundle.create_approx(chart_id=chart_id, anchor_id=anchor_id, triggers=["PowerTempering"],
+                                      frobenius_applied=abs(1.0 - beta) > 0.0,
+                                      influence=InfluenceCert.identity().with_overrides(power_beta=beta))
+    exc_c = CertBundle.create_approx(chart_id=chart_id, anchor_id=anchor_id, triggers=["ExcitationPriorScaling"],
+                                     influence=InfluenceCert.identity().with_overrides(dt_scale=float(1.0 - r[FU["S_DT"]]),
+                                                                                       extrinsic_scale=float(1.0 - r[FU["S_EX"]])))
+    scale_c = CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id,
+                                      overconfidence=OverconfidenceCert(excitation_total=exc_total,
+                                                                        ess_to_excitation=float(r[FU["ESS_TO_EXC"]]),
+                                                                        dt_asymmetry=float(r[FU["DT_ASYMMETRY"]]),
+                                                                        z_to_xy_ratio=float(r[FU["Z_TO_XY"]])),
+                                      conditioning=ConditioningCert(eig_min=float(r[FU["POSE_EIG_MIN"]]), eig_max=float(r[FU["POSE_EIG_MAX"]]),
+                                                                    cond=float(r[FU["POSE_COND"]]), near_null_count=int(r[FU["POSE_NEAR_NULL"]])),
+                                      influence=InfluenceCert.identity().with_overrides(trust_alpha=alpha))
+    return [temper, exc_c, scale_c, _fusion_cert(r, alpha, chart_id, anchor_id, io)]
 
 
 def _fusion_cert(r, alpha, chart_id, anchor_id, io=None):
