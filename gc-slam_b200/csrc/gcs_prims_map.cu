@@ -144,7 +144,10 @@ __global__ void __launch_bounds__(kBig) map_view_kernel(gcs_atlas A, TileList T,
     const double score = (ti >= 0 && v) ? w : -1e30;
     return f64_orderable(-score);  // ascending sort of -score (primitive_map.py:316-320)
   };
-  cta_select_k(M, m_view, key, sm.out, sm.hist, sm.scan, use_cache ? key_cache : nullptr);
+  // a tile with fewer than m_view valid slots: all of them by weight, then invalid slots in index order
+  auto invalid = [&](int s) -> bool { return !(ti >= 0 && A.valid[base + s]); };
+  if (!cta_select_max_sentinel(M, m_view, key, invalid, f64_orderable(1e30), sm.out, sm.scan))
+    cta_select_k(M, m_view, key, sm.out, sm.hist, sm.scan, use_cache ? key_cache : nullptr);
   int local_valid = 0;
   for (int j = threadIdx.x; j < m_view; j += kBig) {
     const int slot = sm.out[j].idx;

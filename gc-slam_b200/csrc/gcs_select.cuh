@@ -298,4 +298,61 @@ __device__ inline bool cta_select_min_sentinel(int n, int k, SentFn sent, unsign
   return true;
 }
 
+// Fast path from the other end: the largest possible key `smax` is shared by many items (the invalid slots of a tile in
+// the view select) and fewer than k items carry a real key.  The result of the stable sort is then all real items in
+// (key, index) order followed by the first k - n_real sentinel items in index order; the radix passes could never
+// separate the tied sentinels and would run all seven digits plus the tie count.  Returns false (out untouched) if at
+// least k items are real; all threads of the CTA must call and get the same answer.  Requires k <= 1024, out capacity
+// >= 1024 entries; scan: shared memory, >= 64 ints.
+template <typename KeyFn, typename SentFn>
+__device__ inline bool cta_select_max_sentinel(int n, int k, KeyFn key, SentFn sent, unsigned long long smax, KeyIdx* out, int* scan) {
+  __shared__ int s_real_slot;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, nw = nt >> 5;
+  int* wsum = scan;
+  const int chunk = (n + nt - 1) / nt;
+  const int c0 = tid * chunk < n ? tid * chunk : n, c1 = (c0 + chunk < n) ? c0 + chunk : n;
+  int cnt = 0;   // sentinel items of this thread's chunk
+#pragma unroll 8
+  for (int i = c0; i < c1; ++i) cnt += sent(i) ? 1 : 0;
+  int inc = cnt;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  __syncthreads();
+  if (lane == 31) wsum[tid >> 5] = inc;
+  if (tid == 0) s_real_slot = 0;
+  __syncthreads();
+  int before = inc - cnt, total = 0;
+  for (int w = 0; w < nw; ++w) {
+    const int v = wsum[w];
+    if (w < (tid >> 5)) before += v;
+    total += v;
+  }
+  __syncthreads();
+  const int n_real = n - total;
+  if (n_real >= k) return false;
+  // real items, any order, then sorted by (key, index)
+  for (int i = c0; i < c1; ++i)
+    if (!sent(i)) {
+      const int sl = atomicAdd(&s_real_slot, 1);
+      out[sl].key = key(i); out[sl].idx = i;
+    }
+  int np = 1;
+  while (np < n_real) np <<= 1;
+  __syncthreads();
+  for (int i = n_real + tid; i < np; i += nt) { out[i].key = ~0ull; out[i].idx = 0x7fffffff; }
+  __syncthreads();
+  if (n_real > 1) cta_bitonic_sort(out, np);
+  // the first k - n_real sentinel items in index order go behind them
+  const int want = k - n_real;
+  if (cnt > 0 && before < want) {
+    int r = before;
+    for (int i = c0; i < c1 && r < want; ++i)
+      if (sent(i)) { out[n_real + r].key = smax; out[n_real + r].idx = i; ++r; }
+  }
+  __syncthreads();
+  return true;
+}
+
 }  // namespace gcs
