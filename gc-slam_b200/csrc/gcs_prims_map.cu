@@ -744,6 +744,7 @@ __global__ void __launch_bounds__(256) upd_pair_keys_kernel(gcs_meas_batch B, in
 // (primitive_map.py:1037-1123): lanes stride over the segment's pairs (ascending pair index), then a fixed shuffle tree
 // combines the 32 lane sums -- deterministic, and popular slots (hundreds of pairs) cost L/32 iterations instead of L.
 constexpr int kFuseVals = 29;   // dLambda 9, deta 9, dtheta 3, dw, dr, dcam, dlid, dacc 3, dden
+constexpr int kFuseU = 4;       // sub-steps of 32 sorted positions whose loads are in flight together
 __global__ void __launch_bounds__(256) upd_fuse_kernel(gcs_atlas A, TileList T, gcs_meas_batch B, int K, gcs_assoc_result R,
                                                        UpdWs W, int n_pairs, unsigned none, gcs_map_update_cfg cfg,
                                                        double* __restrict__ part) {
@@ -758,14 +759,27 @@ __global__ void __launch_bounds__(256) upd_fuse_kernel(gcs_atlas A, TileList T, 
       double v[kFuseVals];
 #pragma unroll
       for (int k = 0; k < kFuseVals; ++k) v[k] = 0.0;
-      for (int base = q;; base += 32) {
-        const int j = base + lane;
-        bool valid = j < n_pairs;
-        if (valid) valid = W.pkeys[j] == key;
-        if (valid) {
-          const int p = (int)W.pvals[j];
-          const int i = p / K;
-          const double r = R.responsibilities[p];
+      // Rounds of kFuseU x 32 sorted positions.  The loads of a round are issued for all kFuseU sub-steps before any of
+      // them is accumulated (clamped indices, responsibility 0 outside the segment: no branch between the loads), so a
+      // popular slot with a thousand pairs pays ~L / 128 load latencies instead of L / 32.  Every lane still adds its
+      // positions in ascending order.
+      for (int base = q;; base += 32 * kFuseU) {
+        int pi[kFuseU];
+        double rr[kFuseU];
+        bool ok[kFuseU];
+#pragma unroll
+        for (int u = 0; u < kFuseU; ++u) {
+          const int j = base + 32 * u + lane;
+          const int jc = j < n_pairs ? j : n_pairs - 1;
+          ok[u] = j < n_pairs && W.pkeys[jc] == key;
+          pi[u] = (int)W.pvals[jc];
+        }
+#pragma unroll
+        for (int u = 0; u < kFuseU; ++u) rr[u] = ok[u] ? R.responsibilities[pi[u]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < kFuseU; ++u) {
+          const int i = pi[u] / K;
+          const double r = rr[u];
           const double wm = B.weights[i];
 #pragma unroll
           for (int k = 0; k < 9; ++k) { v[k] += r * W.Lw[9 * i + k]; v[9 + k] += r * W.etw[9 * i + k]; }
@@ -778,7 +792,7 @@ __global__ void __launch_bounds__(256) upd_fuse_kernel(gcs_atlas A, TileList T, 
           for (int k = 0; k < 3; ++k) v[25 + k] += fmin(fmax(B.colors[3 * i + k], 0.0), 1.0) * wc;
           fused_mass += wm * r;
         }
-        if (!__all_sync(0xffffffffu, valid)) break;
+        if (!__all_sync(0xffffffffu, ok[kFuseU - 1])) break;   // keys are sorted: the segment ended inside this round
       }
 #pragma unroll
       for (int k = 0; k < kFuseVals; ++k) v[k] = warp_sum(v[k]);
