@@ -30,7 +30,9 @@ __device__ __forceinline__ double pair_cost(const double* mp, const double* md, 
   return d_pos + beta * d_dir;
 }
 
-// x^y for the Sinkhorn scalings (x >= 0, y in (0, 1)): 0^y = 0 as jnp's power gives
+// x^y for the Sinkhorn scalings (x >= 0, y in (0, 1)): 0^y = 0 as jnp's power gives.  exp(y log x): the scalings are
+// smooth in x, the ~|y log x| ulp of this form are far inside the tolerance, and it is ~3x shorter than the correctly
+// rounded pow() on the serial path of every iteration.
 __device__ __forceinline__ double pow_pos(double x, double y) { return x > 0.0 ? exp(y * log(x)) : 0.0; }
 
 }  // namespace gcs

@@ -378,9 +378,6 @@ __global__ void __launch_bounds__(256) assoc_topk_kernel(gcs_meas_batch B, int N
   }
 }
 
-// x^y for x >= 0 (0^y = 0 for y > 0) as exp(y log x): the Sinkhorn scalings are smooth in x, the ~|y log x| ulp of this
-// form are far inside the tolerance, and it is ~3x shorter than the correctly-rounded pow() on the serial path
-
 // single CTA: cost of the selected candidates, recency term, row-min shift, unbalanced Sinkhorn, certificates
 // Unbalanced Sinkhorn on the (N, K) sparse costs (primitive_association.py:105-138, :379-470) as a thread-block CLUSTER of
 // eight CTAs: every CTA owns 256 measurement rows (one per thread), the K column sums that couple all rows -- the
