@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(256) assoc_topk_kernel(gcs_meas_batch B, int N
 // Unbalanced Sinkhorn on the (N, K) sparse costs (primitive_association.py:105-138, :379-470) as a thread-block CLUSTER of
 // eight CTAs: every CTA owns 256 measurement rows (one per thread), the K column sums that couple all rows -- the
 // reference's v is one (K,) vector shared by every row -- are exchanged through distributed shared memory once per
-// iteration: each CTA publishes its K partial sums in its own shared memory, one cluster barrier, every CTA reads the
+// iteration: each CTA stores its K partial sums into every CTA's shared memory, one cluster barrier, every CTA adds the
 // eight partial vectors in rank order (same order everywhere: identical v in every CTA, bit-identical reruns).  The
 // exchange buffers alternate with the iteration parity, so one barrier per iteration suffices.  A single CTA spent
 // 7 us per iteration on the float64 pow() of 1,536 rows (one SM's FP64 pipe); eight SMs share that work.
@@ -396,7 +396,7 @@ constexpr int kSkMaxVals = 16;
 // CTA instead of one per thread) and publishes the result in local shared memory.  `phase` alternates the exchange
 // buffer, so that a CTA running ahead never overwrites values a slower one still reads.
 template <int NV, typename Post>
-__device__ __forceinline__ void cluster_sum(double (&v)[NV], double (*xch)[kSkMaxVals], double* sredw, double* tot,
+__device__ __forceinline__ void cluster_sum(double (&v)[NV], double (*xch)[kSkCtas][kSkMaxVals], double* sredw, double* tot,
                                             unsigned& phase, Post post) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
@@ -409,16 +409,21 @@ __device__ __forceinline__ void cluster_sum(double (&v)[NV], double (*xch)[kSkMa
     for (int k = 0; k < NV; ++k) sredw[warp * kSkMaxVals + k] = v[k];
   }
   __syncthreads();
+  // PUSH exchange: thread (r, k) adds up column k over this CTA's warps and stores it into row `my rank` of CTA r's
+  // exchange buffer; after the cluster barrier (release / acquire) every CTA sums its own local copy in rank order.  A
+  // pull (barrier, then remote loads) puts a distributed-shared-memory round trip behind every barrier.
   const unsigned buf = phase & 1u;
-  if (tid < NV) {
+  const unsigned my_rank = cluster.block_rank();
+  if (tid < NV * kSkCtas) {
+    const int k = tid % NV, r = tid / NV;
     double t = 0.0;
-    for (int w = 0; w < kSkThreads / 32; ++w) t += sredw[w * kSkMaxVals + tid];
-    xch[buf][tid] = t;
+    for (int w = 0; w < kSkThreads / 32; ++w) t += sredw[w * kSkMaxVals + k];
+    cluster.map_shared_rank(&xch[buf][my_rank][0], r)[k] = t;
   }
   cluster.sync();
   if (tid < NV) {
     double t = 0.0;
-    for (int r = 0; r < kSkCtas; ++r) t += cluster.map_shared_rank(&xch[buf][0], r)[tid];
+    for (int r = 0; r < kSkCtas; ++r) t += xch[buf][r][tid];
     tot[tid] = post(tid, t);
   }
   __syncthreads();
@@ -433,7 +438,7 @@ __global__ void __cluster_dims__(kSkCtas, 1, 1) __launch_bounds__(kSkThreads)
                           double* __restrict__ cert, double* __restrict__ brow_ws) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
-  __shared__ double xch[2][kSkMaxVals];
+  __shared__ double xch[2][kSkCtas][kSkMaxVals];
   __shared__ double sredw[(kSkThreads / 32) * kSkMaxVals];
   __shared__ double tot[kSkMaxVals];
   __shared__ SelectSmem sel;
@@ -560,8 +565,11 @@ __global__ void __cluster_dims__(kSkCtas, 1, 1) __launch_bounds__(kSkThreads)
 // =================================================================================================
 // a13: pose evidence
 // =================================================================================================
+// 512 threads: three rows per thread at the reference budget (1,536 rows) and 128 registers each -- the 1024-thread
+// version was capped at 64 registers and spilled the 28 accumulators
+constexpr int kPeThreads = 512;
 template <int K>
-__global__ void __launch_bounds__(kBig) pose_evidence_kernel(gcs_meas_batch B, int N, gcs_map_view V, gcs_assoc_result R,
+__global__ void __launch_bounds__(kPeThreads) pose_evidence_kernel(gcs_meas_batch B, int N, gcs_map_view V, gcs_assoc_result R,
                                                              double p0, double p1, double p2, double r0, double r1,
                                                              double r2, double eps_lift, double eps_mass,
                                                              double* __restrict__ L22, double* __restrict__ h22,
@@ -572,9 +580,10 @@ __global__ void __launch_bounds__(kBig) pose_evidence_kernel(gcs_meas_batch B, i
   const double rv[3] = {r0, r1, r2}, tp[3] = {p0, p1, p2};
   const Mat3 Rp = so3_exp(rv);
   double acc[28];
+#pragma unroll
   for (int k = 0; k < 28; ++k) acc[k] = 0.0;
   // 0..8 L_t, 9..11 h_t, 12 trans cost, 13..21 S, 22 rot cost, 23 sum row mass, 24 n valid rows
-  for (int i = tid; i < N; i += kBig) {
+  for (int i = tid; i < N; i += kPeThreads) {
     if (!B.valid[i]) continue;
     double mu[3], dir[3], kap;
     meas_row_moments(B, i, eps_lift, eps_mass, mu, dir, &kap);
@@ -609,9 +618,19 @@ __global__ void __launch_bounds__(kBig) pose_evidence_kernel(gcs_meas_batch B, i
     acc[23] += R.row_masses[i];
     acc[24] += 1.0;
   }
+  // all 25 block sums behind ONE barrier pair (same order as block_sum_1024: shuffle tree per warp, warps in index
+  // order); fully unrolled so that acc[] stays in registers
+  __shared__ double swarp[25][kPeThreads / 32];
+#pragma unroll
   for (int k = 0; k < 25; ++k) {
-    const double s = block_sum_1024(acc[k], sred);
-    if (tid == 0) tot[k] = s;
+    const double w = warp_sum(acc[k]);
+    if ((tid & 31) == 0) swarp[k][tid >> 5] = w;
+  }
+  __syncthreads();
+  if (tid < 25) {
+    double s = 0.0;
+    for (int w = 0; w < kPeThreads / 32; ++w) s += swarp[tid][w];
+    tot[tid] = s;
   }
   __syncthreads();
   if (tid == 0) {
@@ -643,7 +662,7 @@ __global__ void __launch_bounds__(kBig) pose_evidence_kernel(gcs_meas_batch B, i
     for (int k = GCS_VP_R_SCATTER + 9; k < GCS_VP_NREC; ++k) rec[k] = 0.0;
   }
   __syncthreads();
-  for (int idx = tid; idx < 22 * 22; idx += kBig) {
+  for (int idx = tid; idx < 22 * 22; idx += kPeThreads) {
     const int r = idx / 22, c = idx - r * 22;
     double v = (r == c) ? eps_lift : 0.0;
     if (r < 3 && c < 3) v = rec[GCS_VP_L_TRANS + 3 * r + c];
@@ -1218,7 +1237,7 @@ int gcs_visual_pose_evidence(gcs_ctx* ctx, void* stream, const gcs_meas_batch* b
   GCS_REQUIRE(ctx, pose6 && out_L22 && out_h22 && out_rec, "visual_pose_evidence: NULL pointer");
   GCS_REQUIRE(ctx, k_assoc == 8, "visual_pose_evidence: k_assoc=%d (this build instantiates K_ASSOC=8)", k_assoc);
   const int N = batch->n_feat + batch->n_surfel;
-  pose_evidence_kernel<8><<<1, kBig, 0, (cudaStream_t)stream>>>(*batch, N, *view, *assoc, pose6[0], pose6[1], pose6[2], pose6[3],
+  pose_evidence_kernel<8><<<1, kPeThreads, 0, (cudaStream_t)stream>>>(*batch, N, *view, *assoc, pose6[0], pose6[1], pose6[2], pose6[3],
                                                                 pose6[4], pose6[5], eps_lift, eps_mass, out_L22, out_h22, out_rec);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
