@@ -555,11 +555,13 @@ class PrimitiveAssociationResult:
         return r
 
 
-def _empty_assoc(io, N, K):
-    return PrimitiveAssociationResult(responsibilities=io.zeros(N, K), candidate_pool_indices=io.zeros(N, K, dtype=torch.int32),
-                                      candidate_tile_ids=io.zeros(N, K, dtype=torch.int64),
-                                      candidate_slots=io.zeros(N, K, dtype=torch.int64), row_masses=io.zeros(N),
-                                      cost_matrix=io.zeros(N, K))
+def _empty_assoc(io, N, K, zero=True):
+    """Result arrays; zero=False: uninitialised, for the kernels that write every entry (six fill launches per scan less)."""
+    z = io.zeros if zero else io.empty
+    return PrimitiveAssociationResult(responsibilities=z(N, K), candidate_pool_indices=z(N, K, dtype=torch.int32),
+                                      candidate_tile_ids=z(N, K, dtype=torch.int64),
+                                      candidate_slots=z(N, K, dtype=torch.int64), row_masses=z(N),
+                                      cost_matrix=z(N, K))
 
 
 def associate_primitives_ot(measurement_batch: MeasurementBatch, map_view: AtlasMapView, config: AssociationConfig = None,
@@ -586,11 +588,11 @@ def _associate_primitives_ot_gen(measurement_batch, map_view, config=None, eps_l
     if measurement_batch.n_valid == 0 or map_view.n_valid == 0:
         cert = CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id)
         return _empty_assoc(io, N, K), cert, ExpectedEffect("primitive_association_ot", 0.0, 0.0)
-    res = _empty_assoc(io, N, K)
+    res = _empty_assoc(io, N, K, zero=False)
     cfg = CAssocCfg(K, int(config.k_sinkhorn), int(config.r_stencil_tiles_xy), int(config.r_stencil_tiles_z), float(config.beta),
                     float(config.epsilon), float(config.tau_a), float(config.tau_b), float(config.eps_mass), float(eps_lift),
                     float(config.h_tile), float(config.recency_decay_lambda), int(config.scan_seq))
-    cert_d = io.zeros(OT["NCERT"])
+    cert_d = io.empty(OT["NCERT"])     # the kernel writes all NCERT entries
     cb, cv, cr = measurement_batch._c(), map_view._c(), res._c()
     io.ctx.check(io.ctx.lib.gcs_associate_primitives_ot(io.ctx.handle, io.stream(), C.byref(cb), C.byref(cv),
                                                         _i64arr(map_view.tile_ids), len(map_view.tile_ids),
@@ -661,7 +663,7 @@ def _visual_pose_evidence_gen(association_result, measurement_batch, map_view, b
         pose = _host_vec(belief_pred.mean_world_pose(eps_lift=eps_lift), 6)
     else:
         pose = _host_vec(belief_pred, 6)
-    L22, h22, rec_d = io.empty(22, 22), io.empty(22), io.zeros(VP["NREC"])
+    L22, h22, rec_d = io.empty(22, 22), io.empty(22), io.empty(VP["NREC"])   # the kernel writes all NREC entries
     cb, cv, cr = measurement_batch._c(), map_view._c(), association_result._c()
     io.ctx.check(io.ctx.lib.gcs_visual_pose_evidence(io.ctx.handle, io.stream(), C.byref(cb), C.byref(cv), C.byref(cr), int(K),
                                                      _dptr(pose), float(eps_lift), float(eps_mass), L.ptr(L22), L.ptr(h22), L.ptr(rec_d)))
