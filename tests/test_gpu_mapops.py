@@ -164,3 +164,28 @@ def test_operator_sequence_at_production_tile_size_vs_oracle(P):
     P.primitive_map_forget(amap, tid)
     op.primitive_map_forget(ref, tid)
     check_tile(amap.download_tile(tid), ref["tiles"][tid], 1e-12, prefix="")
+
+
+def test_contract_errors_are_value_errors(P):
+    """Shape / budget violations fail loudly as ValueError (GCS_EINVAL), as the reference's fail-fast checks do; the map is
+    left untouched."""
+    g = golden("mapops_forget.npz")
+    amap = P.AtlasMap.from_numpy(atlas_of(g))
+    tid = int(g["tile_id"])
+    before = amap.download_tile(tid)
+    n = 16385                                              # one more than the per-call proposal budget of gcs_map_fuse
+    with pytest.raises(ValueError):
+        P.primitive_map_fuse(amap, tid, np.zeros(n, np.int32), np.zeros((n, 3, 3)), np.zeros((n, 3)), np.zeros((n, 3, 3)), np.ones(n),
+                             np.ones(n), 1.0)
+    k = amap.m_tile + 1                                    # more proposals than the tile has slots
+    with pytest.raises(ValueError):
+        P.primitive_map_insert_masked(amap, tid, np.zeros((k, 3, 3)), np.zeros((k, 3)), np.zeros((k, 3, 3)), np.ones(k), 1.0,
+                                      np.ones(k, bool))
+    with pytest.raises(ValueError):
+        P.sinkhorn_unbalanced_fixed_k(np.zeros((4, 33)), np.ones(4) / 4, np.ones(33) / 33, 0.1, 0.5, 0.5, 5)
+    with pytest.raises(ValueError):
+        P.compute_sparse_cost_matrix(np.zeros((4, 3)), np.zeros((4, 3)), np.ones(4), np.zeros((2, 3)), np.zeros((2, 3)), np.ones(2),
+                                     np.zeros((5, 8), np.int32))
+    after = amap.download_tile(tid)
+    for k_ in EXACT + FLOAT:
+        assert np.array_equal(before[k_], after[k_]), k_
