@@ -193,12 +193,18 @@ struct AssocWs {
   double* mdir;     // (N,3)
   double* mkap;     // (N)
   int8_t* stencil;  // (N, n_st)  view tile index or -1
+  double* vAk;      // (P) A_vmf(kappa) of every view entry: one evaluation per scan instead of one per candidate pair
 };
 
 __global__ void __launch_bounds__(128) assoc_prepare_kernel(gcs_meas_batch B, int N, TileList T, gcs_assoc_cfg cfg,
                                                             int n_st, const int* __restrict__ dq,
                                                             const int* __restrict__ dr, const int* __restrict__ dz,
-                                                            AssocWs W) {
+                                                            AssocWs W, gcs_map_view V, int n_pool, int row_blocks) {
+  if ((int)blockIdx.x >= row_blocks) {   // the blocks behind the rows' blocks take the view entries
+    const int v = ((int)blockIdx.x - row_blocks) * blockDim.x + threadIdx.x;
+    if (v < n_pool) W.vAk[v] = A_vmf(fmax(V.kappas[v], 1e-12), 1e-12);
+    return;
+  }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   double mu[3], dir[3], kap;
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(256) assoc_topk_kernel(gcs_meas_batch B, int N
       const int v = (tix < 0 ? 0 : tix) * m_view + off;
       double c = 1e12;
       if (tix >= 0 && V.valid[v])
-        c = pair_cost(mp, md, mk, A_k1, V.positions + 3 * v, V.directions + 3 * v, V.kappas[v], cfg.beta);
+        c = pair_cost_pre(mp, md, mk, A_k1, V.positions + 3 * v, V.directions + 3 * v, V.kappas[v], W.vAk[v], cfg.beta);
       if (c < bc[K - 1] || (c == bc[K - 1] && j < bj[K - 1])) {
         bc[K - 1] = c; bj[K - 1] = j;
 #pragma unroll
@@ -464,7 +470,7 @@ __global__ void __cluster_dims__(kSkCtas, 1, 1) __launch_bounds__(kSkThreads)
     double rmin = 1.0e300, bsum = 0.0, bdec[K];
     for (int k = 0; k < K; ++k) {
       const int v = R.candidate_pool_indices[i * K + k];
-      double c = pair_cost(mp, md, mk, A_k1, V.positions + 3 * v, V.directions + 3 * v, V.kappas[v], cfg.beta);
+      double c = pair_cost_pre(mp, md, mk, A_k1, V.positions + 3 * v, V.directions + 3 * v, V.kappas[v], W.vAk[v], cfg.beta);
       long long dt = cfg.scan_seq - V.last_supported_scan_seq[v];
       if (dt < 0) dt = 0;
       c += cfg.epsilon * cfg.recency_decay_lambda * (double)dt;
@@ -1198,17 +1204,21 @@ int gcs_associate_primitives_ot(gcs_ctx* ctx, void* stream, const gcs_meas_batch
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_pos = take((size_t)N * 3 * 8), o_dir = take((size_t)N * 3 * 8), o_kap = take((size_t)N * 8),
-               o_st = take((size_t)N * n_st), o_off = take(3 * 64 * 4), o_brow = take((size_t)N * 8 * 8);
+               o_st = take((size_t)N * n_st), o_off = take(3 * 64 * 4), o_brow = take((size_t)N * 8 * 8),
+               o_vak = take((size_t)n_tiles * m_tile_view * 8);
   rc = gcs_ws_reserve(ctx, off);
   if (rc) return rc;
   char* ws = (char*)ctx->ws;
   AssocWs W;
   W.mpos = (double*)(ws + o_pos); W.mdir = (double*)(ws + o_dir); W.mkap = (double*)(ws + o_kap); W.stencil = (int8_t*)(ws + o_st);
+  W.vAk = (double*)(ws + o_vak);
   int* d_off = (int*)(ws + o_off);
   int h_off[3 * 64];
   for (int i = 0; i < 64; ++i) { h_off[i] = dq[i < n_st ? i : 0]; h_off[64 + i] = dr[i < n_st ? i : 0]; h_off[128 + i] = dz[i < n_st ? i : 0]; }
   GCS_CHECK_CUDA(ctx, cudaMemcpyAsync(d_off, h_off, sizeof(h_off), cudaMemcpyHostToDevice, st));
-  assoc_prepare_kernel<<<(N + 127) / 128, 128, 0, st>>>(*batch, N, T, *cfg, n_st, d_off, d_off + 64, d_off + 128, W);
+  const int n_pool = n_tiles * m_tile_view, row_blocks = (N + 127) / 128;
+  assoc_prepare_kernel<<<row_blocks + (n_pool + 127) / 128, 128, 0, st>>>(*batch, N, T, *cfg, n_st, d_off, d_off + 64, d_off + 128, W,
+                                                                           *view, n_pool, row_blocks);
   GCS_LAUNCH_CHECK(ctx);
   gcs_timing_begin(ctx, st);
   const size_t topk_smem = (size_t)m_tile_view * (3 * sizeof(double) + 1);
