@@ -580,7 +580,6 @@ __global__ void __launch_bounds__(kPeThreads) pose_evidence_kernel(gcs_meas_batc
                                                              double r2, double eps_lift, double eps_mass,
                                                              double* __restrict__ L22, double* __restrict__ h22,
                                                              double* __restrict__ rec) {
-  __shared__ double sred[32];
   __shared__ double tot[28];
   const int tid = threadIdx.x;
   const double rv[3] = {r0, r1, r2}, tp[3] = {p0, p1, p2};
