@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(128) assoc_prepare_kernel(gcs_meas_batch B, in
 
 // one warp per measurement row: stream the candidate pool, keep the K best (cost, pool position) per lane, merge.
 // First K of the row-wise stable sort by cost over the 7 x 1024 candidate pool (primitive_association.py:367-376), one warp
-// per measurement, eight measurements per CTA.
+// per measurement, kTopkRows measurements per CTA.
 //   cost = |dp|^2 + beta * d_dir with d_dir in [0, 1], so |dp|^2 is a lower bound that costs five flops.  T is an upper
 //   bound of the row's K-th best (cost, j) (the K-th smallest of the lanes' current best entries: K distinct candidates
 //   at or before it); a candidate whose (bound, j) lies beyond (T, Tj) cannot be among the first K and is skipped --
@@ -233,14 +233,15 @@ __global__ void __launch_bounds__(128) assoc_prepare_kernel(gcs_meas_batch B, in
 //   validity: 25 KB), every warp scans the staged tile if it is in its stencil, survivors are queued and evaluated 32
 //   at a time (all lanes busy), which leaves a few hundred of the 7,168 exact costs per row.  Ties keep the smaller
 //   j = stencil position * m_view + offset whatever the processing order, so the selection is the reference's.
+constexpr int kTopkRows = 4;   // measurement rows (warps) per CTA: 2 / 4 / 8 rows give 150 / 145 / 153 us -- the kernel lasts as long as its densest row
 template <int K>
-__global__ void __launch_bounds__(256) assoc_topk_kernel(gcs_meas_batch B, int N, gcs_map_view V, int m_view, int n_st,
+__global__ void __launch_bounds__(32 * kTopkRows) assoc_topk_kernel(gcs_meas_batch B, int N, gcs_map_view V, int m_view, int n_st,
                                                          int n_view_tiles, AssocWs W, gcs_assoc_cfg cfg, gcs_assoc_result R) {
   extern __shared__ double tile_pos[];                       // (m_view, 3), then m_view validity bytes
   uint8_t* tile_valid = reinterpret_cast<uint8_t*>(tile_pos + 3 * (size_t)m_view);
-  __shared__ int s_queue[8][64];
+  __shared__ int s_queue[kTopkRows][64];
   const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * 8 + wq;
+  const int i = blockIdx.x * kTopkRows + wq;
   const bool active = i < N;
   const int ii = active ? i : 0;
   const double mp[3] = {W.mpos[3 * ii], W.mpos[3 * ii + 1], W.mpos[3 * ii + 2]};
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(256) assoc_topk_kernel(gcs_meas_batch B, int N
   // at once and the outer tiles are then pruned almost entirely
   __shared__ int s_first;
   if (threadIdx.x == 0) {
-    const int c = W.stencil[(size_t)(blockIdx.x * 8) * n_st + n_st / 2];
+    const int c = W.stencil[(size_t)(blockIdx.x * kTopkRows) * n_st + n_st / 2];
     s_first = (c >= 0 && c < n_view_tiles) ? c : 0;
   }
   __syncthreads();
@@ -319,8 +320,8 @@ __global__ void __launch_bounds__(256) assoc_topk_kernel(gcs_meas_batch B, int N
   for (int tt = 0; tt < n_view_tiles; ++tt) {
     const int t = tt == 0 ? t_first : (tt <= t_first ? tt - 1 : tt);
     __syncthreads();   // the previous tile has been scanned by every warp
-    for (int e = threadIdx.x; e < 3 * m_view; e += 256) tile_pos[e] = V.positions[(size_t)t * m_view * 3 + e];
-    for (int e = threadIdx.x; e < m_view; e += 256) tile_valid[e] = V.valid[(size_t)t * m_view + e];
+    for (int e = threadIdx.x; e < 3 * m_view; e += 32 * kTopkRows) tile_pos[e] = V.positions[(size_t)t * m_view * 3 + e];
+    for (int e = threadIdx.x; e < m_view; e += 32 * kTopkRows) tile_valid[e] = V.valid[(size_t)t * m_view + e];
     __syncthreads();
     if (!active) continue;
     int s = -1;
@@ -1223,7 +1224,7 @@ int gcs_associate_primitives_ot(gcs_ctx* ctx, void* stream, const gcs_meas_batch
   const size_t topk_smem = (size_t)m_tile_view * (3 * sizeof(double) + 1);
   if (topk_smem > 40 * 1024)
     GCS_CHECK_CUDA(ctx, gcs_smem_attr_once((const void*)assoc_topk_kernel<8>, (int)topk_smem));
-  assoc_topk_kernel<8><<<(unsigned)cdivm((int64_t)N, 8), 256, topk_smem, st>>>(*batch, N, *view, m_tile_view, n_st, n_tiles, W,
+  assoc_topk_kernel<8><<<(unsigned)cdivm((int64_t)N, kTopkRows), 32 * kTopkRows, topk_smem, st>>>(*batch, N, *view, m_tile_view, n_st, n_tiles, W,
                                                                                 *cfg, *out);
   gcs_timing_end(ctx, st);
   GCS_LAUNCH_CHECK(ctx);
