@@ -35,3 +35,26 @@ def geodesic(Ra, Rb):
     c = 0.5 * (np.trace(E) - 1.0)
     s = 0.5 * np.linalg.norm([E[2, 1] - E[1, 2], E[0, 2] - E[2, 0], E[1, 0] - E[0, 1]])
     return float(np.arctan2(s, c))
+
+
+def check_compact(g, key, arr, exact=False, tol=None):
+    """
+    Compare a full per-point array with a compact golden entry written by tests/golden/make_golden.py for the
+    full-size cases: `key_rows` = every full_stride-th row, `key_sha256` = digest of the whole array (bit-exact
+    arrays), `key_sum` / `key_abssum` = column sums (floating arrays: relative tolerance `tol`).
+    """
+    import hashlib
+    a = np.ascontiguousarray(arr)
+    stride = int(g["full_stride"])
+    rows = g[key + "_rows"]
+    if exact:
+        assert a.dtype == rows.dtype, (key, a.dtype, rows.dtype)
+        assert np.array_equal(a[::stride], rows), key
+        digest = np.frombuffer(hashlib.sha256(a.tobytes()).digest(), np.uint8)
+        assert np.array_equal(digest, g[key + "_sha256"]), key + ": digest of the whole array differs"
+        return
+    scale = float(np.max(np.abs(rows))) + 1e-300
+    assert float(np.max(np.abs(a[::stride].astype(np.float64) - rows))) <= tol * scale, key
+    s_abs = g[key + "_abssum"]
+    assert np.all(np.abs(a.astype(np.float64).sum(axis=0) - g[key + "_sum"]) <= tol * s_abs + 1e-300), key + " (column sums)"
+    assert np.all(np.abs(np.abs(a.astype(np.float64)).sum(axis=0) - s_abs) <= tol * s_abs + 1e-300), key + " (abs sums)"

@@ -65,6 +65,9 @@ def cert_scalars(c):
                      c.mismatch.directional_score])
 
 
+FULL_STRIDE = 97
+
+
 def make_bin_family():
     from fl_slam_poc.common import constants
 
@@ -91,7 +94,7 @@ def make_bin_family():
         "ragged_5000_cap8192": (5000, 8192, 0.0, 1002),  # padded rows, relative stamps
         "ragged_777_cap1024_epoch": (777, 1024, synth.EPOCH_T0, 1003),  # padded rows + epoch stamps: garbage pads
     }
-    for name, (n_raw, cap, t0, seed) in cases.items():
+    def run_case(n_raw, cap, t0, seed):
         pts, t, w, ring, tag = synth.vlp16_scan(n_raw, seed, t0=t0)
         xi = synth.scan_twist(seed)
         t1 = t0 + synth.SCAN_PERIOD
@@ -119,8 +122,11 @@ def make_bin_family():
         L22, h22 = mfe.build_combined_lidar_evidence_22d(mf, pt)
         forgot = atlas.apply_forgetting(map_stats, 0.99)
         resp = A(sa.responsibilities)
-        np.savez_compressed(
-            os.path.join(HERE, f"bin_{name}.npz"),
+        # update_map_stats (archive/bin_atlas.py:137): the map statistics above plus the scan's own additive increments
+        inc_sum_p = A(st.p_bar) * A(st.N)[:, None]
+        inc_sum_ppT = (A(st.Sigma_p) + np.einsum("bi,bj->bij", A(st.p_bar), A(st.p_bar))) * A(st.N)[:, None, None]
+        upd = atlas.update_map_stats(map_stats, st.s_dir, st.S_dir_scatter, st.N, 0.5 * A(st.N), inc_sum_p, inc_sum_ppT)
+        return dict(
             n_raw=n_raw, cap=cap, t0=t0, t1=t1, seed=seed, xi=xi, tau=0.1, origin=origin, bin_dirs=bin_dirs,
             pose=pose,
             rs_points=A(rs.points), rs_t=A(rs.timestamps), rs_w=A(rs.weights), rs_ring=A(rs.ring),
@@ -149,8 +155,35 @@ def make_bin_family():
             pt_t=A(pt.t_wls), pt_L=A(pt.L_trans), pt_h=A(pt.h_trans), pt_delta=A(pt.delta_trans),
             pt_scales=np.array([pt.xy_info_scale, pt.z_info_scale]), pt_cert=cert_scalars(c_pt),
             pt_effect=e_pt.predicted, L22=A(L22), h22=A(h22),
+            upd_inc_N_pos=0.5 * A(st.N), upd_inc_sum_p=inc_sum_p, upd_inc_sum_ppT=inc_sum_ppT,
+            upd_S_dir=A(upd.S_dir), upd_S_dir_scatter=A(upd.S_dir_scatter), upd_N_dir=A(upd.N_dir),
+            upd_N_pos=A(upd.N_pos), upd_sum_p=A(upd.sum_p), upd_sum_ppT=A(upd.sum_ppT),
         )
-        print("wrote", name, "n_sel", rs.n_output, "kappa[:3]", A(st.kappa_scan)[:3])
+
+    which = set(os.environ.get("GCS_GOLDEN_BIN", "small,full").split(","))
+    if "small" in which:
+        for name, (n_raw, cap, t0, seed) in cases.items():
+            d = run_case(n_raw, cap, t0, seed)
+            np.savez_compressed(os.path.join(HERE, f"bin_{name}.npz"), **d)
+            print("wrote", name, "n_sel", d["rs_n_output"], "kappa[:3]", d["st_kappa"][:3])
+
+    # BASELINE config 3 / the bench shape: 65,536 points, stride 1, epoch stamps.  Per-point arrays are kept as every
+    # FULL_STRIDE-th row + SHA-256 digests (bit-exact arrays) + column sums, so that the fixture stays small.
+    if "full" in which:
+        import hashlib
+        for name, (n_raw, cap, t0, seed) in {"c3_65536": (65536, 65536, synth.EPOCH_T0, 1004)}.items():
+            d = run_case(n_raw, cap, t0, seed)
+            big = ("rs_points", "rs_t", "rs_w", "rs_ring", "rs_tag", "dk_points", "dk_w", "dirs")
+            out = {k: v for k, v in d.items() if k not in big}
+            out["full_stride"] = FULL_STRIDE
+            for k in big:
+                a = np.ascontiguousarray(d[k])
+                out[k + "_rows"] = a[::FULL_STRIDE]
+                out[k + "_sha256"] = np.frombuffer(hashlib.sha256(a.tobytes()).digest(), np.uint8)
+                out[k + "_sum"] = a.astype(np.float64).sum(axis=0)
+                out[k + "_abssum"] = np.abs(a.astype(np.float64)).sum(axis=0)
+            np.savez_compressed(os.path.join(HERE, f"binfull_{name}.npz"), **out)
+            print("wrote full", name, "n_sel", d["rs_n_output"], "kappa[:3]", d["st_kappa"][:3])
 
     # scalar known-answer table: kappa batch + scalar variant, so3 exp/log
     Rb = np.concatenate([np.linspace(0, 1, 41), [0.799, 0.8, 0.801, 0.999999, 1.0, 1.5, -0.2]])

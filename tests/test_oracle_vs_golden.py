@@ -74,6 +74,10 @@ def test_bin_path_matches_reference(case):
     fg = ob.apply_forgetting(ms, 0.99)
     assert rel_err(fg["N_dir"], g["map_forgot_N_dir"]) < 1e-15
     assert rel_err(fg["sum_ppT"], g["map_forgot_sum_ppT"]) < 1e-15
+    # update_map_stats (archive/bin_atlas.py:137-165) on the increments the generator recorded
+    up = ob.update_map_stats(ms, g["st_s_dir"], g["st_S"], g["st_N"], g["upd_inc_N_pos"], g["upd_inc_sum_p"], g["upd_inc_sum_ppT"])
+    for k in ("S_dir", "S_dir_scatter", "N_dir", "N_pos", "sum_p", "sum_ppT"):
+        assert np.array_equal(up[k], g["upd_" + k]), k
 
     R_pred = lie.so3_exp(g["pose"][3:6])
     mf, c_mf = ob.matrix_fisher_rotation(R_pred, st["s_dir"], st["S_dir_scatter"], st["N"], ms["S_dir"],
@@ -100,6 +104,35 @@ def test_bin_path_matches_reference(case):
     L, h = ob.combined_lidar_evidence_22d(pt["L_trans"], pt["h_trans"], mf["L_rot"], mf["h_rot"])
     assert rel_err(L, g["L22"]) < 1e-8 and rel_err(h, g["h22"]) < 1e-7
     assert L.shape == (22, 22) and np.count_nonzero(L[6:, :]) == 0
+
+
+FULL_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "binfull_*.npz")))
+
+
+@pytest.mark.parametrize("case", FULL_CASES)
+def test_bin_path_matches_reference_at_bench_size(case):
+    """BASELINE config 3 / the bench shape (65,536 points, stride 1, epoch stamps): per-point arrays through digests,
+    strided rows and column sums (conftest.check_compact), statistics and evidence in full."""
+    from conftest import check_compact
+    g = golden(case)
+    pts, t, w, ring, tag = _raw(g)
+    o = ob.lidar_evidence_bins(pts, t, w, ring, tag, int(g["cap"]), g["xi"], float(g["t0"]), float(g["t1"]), g["origin"],
+                               g["bin_dirs"], float(g["tau"]),
+                               {k[4:]: g[k] for k in g.files if k.startswith("map_") and k[4:] in
+                                ("S_dir", "S_dir_scatter", "N_dir", "N_pos", "sum_p", "sum_ppT")},
+                               lie.so3_exp(g["pose"][3:6]), g["pose"][:3])
+    rs, dk = o["resample"], o["deskew"]
+    for k_o, k_g in (("points", "rs_points"), ("timestamps", "rs_t"), ("ring", "rs_ring"), ("tag", "rs_tag")):
+        check_compact(g, k_g, rs[k_o], exact=True)
+    check_compact(g, "rs_w", rs["weights"], tol=1e-14)
+    check_compact(g, "dk_points", dk["points"], tol=1e-13)
+    check_compact(g, "dk_w", dk["weights"], tol=1e-13)
+    st = o["stats"]
+    for k_o, k_g in (("N", "st_N"), ("s_dir", "st_s_dir"), ("S_dir_scatter", "st_S"), ("p_bar", "st_p_bar"),
+                     ("Sigma_p", "st_Sigma_p"), ("kappa_scan", "st_kappa")):
+        assert rel_err(st[k_o], g[k_g]) < 1e-10, k_o
+    assert geodesic(o["mf"]["R_mf"], g["mf_R"]) < 1e-9
+    assert rel_err(o["L"], g["L22"]) < 1e-8 and rel_err(o["h"], g["h22"]) < 1e-7
 
 
 def test_scalar_tables():
