@@ -58,3 +58,32 @@ def check_compact(g, key, arr, exact=False, tol=None):
     s_abs = g[key + "_abssum"]
     assert np.all(np.abs(a.astype(np.float64).sum(axis=0) - g[key + "_sum"]) <= tol * s_abs + 1e-300), key + " (column sums)"
     assert np.all(np.abs(np.abs(a.astype(np.float64)).sum(axis=0) - s_abs) <= tol * s_abs + 1e-300), key + " (abs sums)"
+
+
+class Gold:
+    """A golden file whose large arrays may be stored in compact form (see check_compact): eq() / close() pick the form."""
+
+    def __init__(self, name):
+        self.g = golden(name)
+        self.files = set(self.g.files)
+
+    def __getitem__(self, k):
+        return self.g[k]
+
+    def has_full(self, k):
+        return k in self.files
+
+    def eq(self, key, arr):
+        arr = np.asarray(arr)
+        if key in self.files:
+            assert np.array_equal(arr, self.g[key]), key
+        else:
+            rows = self.g[key + "_rows"]
+            check_compact(self.g, key, arr.astype(rows.dtype) if arr.dtype != rows.dtype and arr.dtype.kind == rows.dtype.kind else arr,
+                          exact=True)
+
+    def close(self, key, arr, tol):
+        if key in self.files:
+            assert rel_err(arr, self.g[key]) < tol, key
+        else:
+            check_compact(self.g, key, np.asarray(arr), tol=tol)

@@ -12,13 +12,13 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, geodesic, golden, rel_err
+from conftest import GOLDEN, Gold, geodesic, golden, rel_err
 from test_oracle_prim_vs_golden import build_inputs
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
-CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "prim_*.npz")))
+CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "prim*_*.npz")))
 ESS, SUP = 1, 2
 
 
@@ -49,17 +49,18 @@ def _gpu_batch_and_view(P, g, rs, dk, atlas_np):
 
 @pytest.mark.parametrize("case", CASES)
 def test_primitive_path_vs_golden(P, case):
-    g = golden(case)
+    G = Gold(case)
+    g = G.g
     rs, dk, _, atlas_np = build_inputs(g)
     batch, c_sf, amap = _gpu_batch_and_view(P, g, rs, dk, atlas_np)
     # ---- a10
-    assert np.array_equal(_np(batch._bucket), g["bucket"]) and np.array_equal(_np(batch._bucket_count), g["bucket_count"])
+    G.eq("bucket", _np(batch._bucket)); G.eq("bucket_count", _np(batch._bucket_count))
     assert batch.n_lidar_valid == int(g["mb_n_lidar"]) and batch.n_camera_valid == int(g["mb_n_cam"])
     assert np.array_equal(_np(batch.valid_mask).astype(bool), g["mb_valid"])
     assert np.array_equal(_np(batch.sources), g["mb_sources"]) and np.array_equal(_np(batch.source_indices), g["mb_source_indices"])
     for got, key in ((batch.Lambdas, "mb_Lambdas"), (batch.thetas, "mb_thetas"), (batch.etas, "mb_etas"),
                      (batch.weights, "mb_weights"), (batch.timestamps, "mb_timestamps"), (batch.colors, "mb_colors")):
-        assert rel_err(_np(got), g[key]) < 1e-7, key
+        G.close(key, _np(got), 1e-7)
     assert c_sf.support.ess_total == g["sf_cert"][ESS] and c_sf.exact is False
     # ---- a11
     scan_seq = int(g["scan_seq"])
@@ -69,19 +70,21 @@ def test_primitive_path_vs_golden(P, case):
     got = np.array([inf.staleness_inflation_strength, inf.staleness_cov_inflation_trace, inf.stale_precision_downscale_total])
     assert rel_err(got, g["inf_stats"]) < 1e-11
     view = P.extract_atlas_map_view(amap, active, int(g["m_view"]))
-    assert np.array_equal(_np(view.candidate_slots), g["view_slots"]) and np.array_equal(_np(view.candidate_tile_ids), g["view_tids"])
-    assert np.array_equal(_np(view.valid_mask).astype(bool), g["view_valid"]) and np.array_equal(_np(view.primitive_ids), g["view_ids"])
-    vm = g["view_valid"]
-    assert rel_err(_np(view.positions)[vm], g["view_pos"][vm]) < 1e-8 and rel_err(_np(view.covariances)[vm], g["view_cov"][vm]) < 1e-8
-    assert rel_err(_np(view.directions), g["view_dir"]) < 1e-12 and rel_err(_np(view.kappas), g["view_kappa"]) < 1e-12
+    G.eq("view_slots", _np(view.candidate_slots)); G.eq("view_tids", _np(view.candidate_tile_ids))
+    vm = _np(view.valid_mask).astype(bool)
+    G.eq("view_valid", vm); G.eq("view_ids", _np(view.primitive_ids))
+    G.close("view_pos", _np(view.positions) * vm[:, None], 1e-8); G.close("view_cov", _np(view.covariances) * vm[:, None, None], 1e-8)
+    G.close("view_dir", _np(view.directions), 1e-12); G.close("view_kappa", _np(view.kappas), 1e-12)
     # ---- a12
     assoc, c_as, e_as = P.associate_primitives_ot(batch, view, P.AssociationConfig(scan_seq=scan_seq))
     pool = _np(assoc.candidate_pool_indices)
-    n_mismatch = int(np.sum(np.any(pool != g["as_pool"], axis=1)))
-    assert n_mismatch == 0, f"{n_mismatch} rows with a different candidate set"
-    assert np.array_equal(_np(assoc.candidate_tile_ids), g["as_tids"]) and np.array_equal(_np(assoc.candidate_slots), g["as_slots"])
-    assert rel_err(_np(assoc.cost_matrix), g["as_cost"]) < 1e-8
-    assert rel_err(_np(assoc.responsibilities), g["as_resp"]) < 1e-8 and rel_err(_np(assoc.row_masses), g["as_row"]) < 1e-8
+    if G.has_full("as_pool"):
+        n_mismatch = int(np.sum(np.any(pool != g["as_pool"], axis=1)))
+        assert n_mismatch == 0, f"{n_mismatch} rows with a different candidate set"
+    G.eq("as_pool", pool)
+    G.eq("as_tids", _np(assoc.candidate_tile_ids)); G.eq("as_slots", _np(assoc.candidate_slots))
+    G.close("as_cost", _np(assoc.cost_matrix), 1e-8)
+    G.close("as_resp", _np(assoc.responsibilities), 1e-8); G.close("as_row", _np(assoc.row_masses), 1e-8)
     ot = c_as.ot
     got = np.array([ot.marginal_defect_a, ot.marginal_defect_b, ot.transport_mass_total, ot.sum_a, ot.sum_m, ot.sum_novel,
                     ot.p95_a, ot.nonzero_a, ot.b_recency_p95])
@@ -106,10 +109,10 @@ def test_primitive_path_vs_golden(P, case):
     assert amap.next_global_id == int(g["next_global_id"]) and amap.total_count == int(g["total_count"])
     for a, tid in enumerate(active):
         t = amap.download_tile(tid)
-        assert np.array_equal(t["valid_mask"], g[f"tile{tid}_valid"]) and np.array_equal(t["primitive_ids"], g[f"tile{tid}_ids"])
-        assert np.array_equal(t["last_supported_scan_seq"], g[f"tile{tid}_last"])
+        G.eq(f"tile{tid}_valid", t["valid_mask"]); G.eq(f"tile{tid}_ids", t["primitive_ids"])
+        G.eq(f"tile{tid}_last", t["last_supported_scan_seq"])
         assert t["count"] == int(g[f"tile{tid}_count"]) == res.tile_counts[a]
-        assert rel_err(t["weights"], g[f"tile{tid}_weights"]) < 1e-10
+        G.close(f"tile{tid}_weights", t["weights"], 1e-10)
         for f in ("Lambdas", "thetas", "etas", "timestamps", "rgb", "cam_mass", "lidar_mass"):
             assert rel_err(t[f].astype(np.float64).sum(axis=0), g[f"tile{tid}_{f}_sum"]) < 1e-8, f
 
