@@ -16,11 +16,17 @@
 //   epilogue warps (Q per CTA, one per 32 TMEM lanes) drain every accumulator after `flush` tiles (tcgen05.ld) into
 //            float64 registers: the float32 accumulator (which truncates) never sums more than flush x 4 MMA steps.
 //
-// Operand formats.  The default keeps every operand as two fp16 terms (kind::f16, K = 16 per MMA, 64-byte rows,
-// SWIZZLE_64B): x = hi + lo / 2^11 with power-of-two pre-scales per operand class (kShift*), undone exactly on the
-// float64 partials.  Half the operand bytes of the tf32 form, so every producer warp owns TWO operand tiles and starts
-// its next tile while the tensor core still reads the previous one.  The tf32 form (kind::tf32, K = 8, 128-byte rows,
-// SWIZZLE_128B, one tile per warp) is kept for sharp kernels (tau < 0.05) where fp16's exponent range is too small.
+// Operand formats.  The default (H = true) keeps every operand as two fp16 terms (kind::f16, K = 16 per MMA) with
+// power-of-two pre-scales per operand class (kShift*), undone exactly on the float64 partials, in an MN-MAJOR,
+// unswizzled layout (tools/tc_probe_mn.cu): the 8-element chunks of one point (one K row) are 16 bytes each, so a lane
+// stores its point's 96 A values and 40 B values with 12 + 5 STS.128 instead of 134 two-byte stores, the eight lanes
+// of a quarter warp fill one 128-byte core matrix (conflict-free), and no per-row swizzle offsets are needed.  A tile is
+// 64 points: every lane owns the two consecutive points 2 lane, 2 lane + 1 (16-byte global loads / stores of the pair,
+// packed f32x2 arithmetic across the pair) and writes them to K rows lane and 32 + lane (the order inside a tile is
+// irrelevant to the contraction).  The deskew increment p0 - p is evaluated in float32 and added to the float64 point
+// (error <= 2^-24 |p0 - p|); sweep fraction, window weight and all sums stay float64.
+// The tf32 form (H = false; kind::tf32, K = 8, K-major 128-byte rows, SWIZZLE_128B, 32-point tiles, all-float64
+// geometry) is kept for sharp kernels (tau < 0.05) where fp16's exponent range is too small.
 //
 // A CTA is persistent over a contiguous range of 32-point tiles of the flattened (unit, tile) space -- every SM gets
 // the same amount of work whatever the batch shape -- and writes one partial per unit segment it touched, in the
@@ -48,6 +54,10 @@ constexpr double kLn2 = 0.6931471805599453;
 //   classes (1, d, d d^T), p, p p^T carry 2^kShiftD, 2^kShiftP, 2^kShiftPP.  With these, fp16 operands stay finite for
 //   w / Z < 2000 and |p| < 500 m; outside that range the moments come out as inf / NaN (never silently wrong).
 constexpr int kShiftE = 14, kShiftLo = 11, kShiftD = 5, kShiftP = -2, kShiftPP = -12;
+// MN-major fp16 tiles: bytes between two groups of 8 points (K groups) of the B tile (5 chunks of 8 features)
+constexpr int kKgB = 5 * 128;
+constexpr unsigned kIssuerSleepNs = 64;
+constexpr int kLoColH = 20;   // first "lo" feature column of the fp16 B operand (columns 19 and 39 are zero)
 
 template <int Q, bool H>
 struct TcCfg {
@@ -62,13 +72,20 @@ struct TcCfg {
   static constexpr int kEpi = Q;
   static constexpr int kIssuerWarp = Q <= 3 ? kProd + 3 : kProd + 4;
   static constexpr int kThreads = Q <= 3 ? 32 * (kProd + 4) : 32 * (kProd + 8);
-  static constexpr int kRowB = H ? tc::kRowBytes16 : tc::kRowBytes;   // bytes of one operand row (32 points)
-  static constexpr int kNBuf = H ? 2 : 1;                             // operand tiles per producer warp
-  static constexpr int kMmaPerTile = H ? 2 : 4;                       // K = 16 (f16) / 8 (tf32) points per MMA
-  static constexpr int kABytes = kRows * kRowB;
-  static constexpr int kBBytes = kBRows * kRowB;
-  static constexpr int kStageBytes = kABytes + kBBytes;   // tf32: 17 / 21 KB (multiples of 1 KB); f16: 8.5 / 10.5 KB (of 512 B)
-  static constexpr int kStagesBytes = kProd * kNBuf * kStageBytes + 1024;   // + tail read by the last B tile's padding rows
+  static constexpr int kTilePts = H ? 64 : 32;                        // points per operand tile
+  static constexpr int kNBuf = 1;                                     // operand tiles per producer warp
+  static constexpr int kMmaPerTile = 4;                               // K = 16 (f16, 64 points) / 8 (tf32, 32 points) per MMA
+  static constexpr int kKgA = kRows * 16;                             // fp16: bytes between K groups of the A tile
+  static constexpr int kABytes = H ? 8 * kKgA : kRows * tc::kRowBytes;
+  static constexpr int kBBytes = H ? 8 * kKgB : kBRows * tc::kRowBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;   // 17 / 21 KB in both forms (multiples of 1 KB)
+  static constexpr int kStagesBytes = kProd * kNBuf * kStageBytes + 1024;   // + tail read by the last tile's padding rows
+  static constexpr int kLoCol = H ? kLoColH : kNF;                    // first "lo" feature column of the accumulator
+};
+
+// float32 copy of the hoisted twist invariants, every scalar duplicated into a pair (one 8-byte load feeds an f32x2 operand)
+struct TwistCtxF {
+  float2 rho[3], phi[3], nphi[3], c1[3], c2[3], th1sq, nth1sq, norg[3];
 };
 
 struct TcMisc {
@@ -80,11 +97,12 @@ struct TcMisc {
   uint32_t tmem;
   double ex[kMaxProd][8];
   TwistCtx tw[kMaxProd];        // per producer warp: hoisted invariants of the current unit (reloaded every tile)
+  TwistCtxF twf[kMaxProd];
   WindowCtx win[kMaxProd];
 };
 
 struct TcGeom {
-  int64_t tiles_per_unit;   // ceil(cap / 32)
+  int64_t tiles_per_unit;   // ceil(cap / tile_pts)
   int64_t total_tiles;      // U * tiles_per_unit
   int n_cta, n_parts, flush;
   int dbg;   // 0, or 1 + slot of the timing hook
@@ -123,9 +141,9 @@ __device__ __forceinline__ void write_partial(const BinScanParams& P, const TcGe
   double* part = P.partial + ((int64_t)sg.u * G.n_parts + slot) * P.part_len;
   for (int idx = tid; idx < nb * kNF; idx += C::kThreads) {
     const int b = idx / kNF, f = idx - b * kNF;
-    if (H) {
+    if (H) {   // e_lo rows carry the unscaled residual (the 2^-kShiftLo of the feature "lo" columns is applied by the epilogue)
       const double sc_f = ldexp(1.0, -kShiftE - (f < 10 ? kShiftD : (f < 13 ? kShiftP : kShiftPP)));
-      part[b * kRowLen + f] = fma(red[(C::kBinsPad + b) * kNF + f], ldexp(1.0, -kShiftLo), red[b * kNF + f]) * sc_f;
+      part[b * kRowLen + f] = (red[b * kNF + f] + red[(C::kBinsPad + b) * kNF + f]) * sc_f;
     } else {
       part[b * kRowLen + f] = red[b * kNF + f] + red[(C::kBinsPad + b) * kNF + f];
     }
@@ -148,7 +166,7 @@ __device__ __forceinline__ void write_partial(const BinScanParams& P, const TcGe
 }
 
 // Barrier schedule of a segment (all kThreads threads, named barrier 1):
-//   [producers: tiles + MMAs | epilogue: drains]  B1  [epilogue: row sums -> red]  B2  [all: partial]  B3  [all: re-zero red]  B4
+//   [producers: tiles + MMAs | epilogue: drains]  B1  [epilogue: row sums -> red]  B2  [all: partial]  B3  ([all: re-zero red]  B4: tf32 only)
 template <int Q, bool H>
 __device__ __forceinline__ void segment_tail(const BinScanParams& P, const TcGeom& G, const TcSeg& sg, TcMisc& mi,
                                              unsigned char* stages, int cta, int tid, const double* acc_or_null) {
@@ -164,15 +182,21 @@ __device__ __forceinline__ void segment_tail(const BinScanParams& P, const TcGeo
   bar_all(C::kThreads);
   write_partial<Q, H>(P, G, sg, mi, red, cta, tid);
   bar_all(C::kThreads);
+  if (H) return;   // fp16 tiles are rewritten completely by every tile; the rows that alias this scratch feed unread accumulator rows
   // padding rows of the operand tiles alias this scratch: keep it free of NaN bit patterns
   for (int k = tid; k < (128 * kNF * 8 + 15) / 16; k += C::kThreads) reinterpret_cast<uint4*>(stages)[k] = make_uint4(0, 0, 0, 0);
   tc::fence_smem_to_async();
   bar_all(C::kThreads);
 }
 
-template <int Q, bool H>
-__device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGeom& G, TcMisc& mi, unsigned char* stages,
-                                              uint32_t tmem, int cta, int tid) {
+// ---------------------------------------------------------------------------------------------------------------------
+// Producer, tf32 operands (H = false): 32-point tiles, K-major SWIZZLE_128B, all-float64 geometry.  One lane = one point
+// in stages 1 and 3; stage 2 uses a pair layout (lane = bin half x point pair).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int Q>
+__device__ __forceinline__ void producer_role_tf32(const BinScanParams& P, const TcGeom& G, TcMisc& mi, unsigned char* stages,
+                                                   uint32_t tmem, int cta, int tid) {
+  constexpr bool H = false;
   using C = TcCfg<Q, H>;
   constexpr int kProd = C::kProd;
   const int wid = tid >> 5, lane = tid & 31;
@@ -185,13 +209,6 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
   uint32_t off2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) off2[j] = (uint32_t)(((((lane & 15) >> 1) ^ j) << 4) | ((lane & 1) << 3));
-  // 16-bit rows (64 B, SWIZZLE_64B: chunk ^= (row >> 1) & 3): element = point (2 B) / point pair (4 B)
-  uint32_t offh[4], off2h[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    offh[j] = (uint32_t)((((lane >> 3) ^ j) << 4) | ((lane & 7) << 1));
-    off2h[j] = (uint32_t)(((((lane & 15) >> 2) ^ j) << 4) | ((lane & 3) << 2));
-  }
   int64_t g0 = cta_tile0(G, cta);
   const int64_t g_end = cta_tile0(G, cta + 1);
   TcSeg sg;
@@ -265,15 +282,11 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
       const float2 g0 = make_float2(__shfl_sync(0xffffffffu, f0, 2 * pj), __shfl_sync(0xffffffffu, f0, 2 * pj + 1));
       const float2 g1 = make_float2(__shfl_sync(0xffffffffu, f1, 2 * pj), __shfl_sync(0xffffffffu, f1, 2 * pj + 1));
       const float2 g2 = make_float2(__shfl_sync(0xffffffffu, f2, 2 * pj), __shfl_sync(0xffffffffu, f2, 2 * pj + 1));
-      // the tensor core may still be reading the operand tile this one goes into
-      const uint32_t buf = H ? (n_stage_uses & 1u) : 0u;
-      unsigned char* const sA = sA0 + buf * C::kStageBytes;
+      unsigned char* const sA = sA0;
       unsigned char* const sB = sA + C::kABytes;
-      // tf32: the lane's bins are [half * NB2, half * NB2 + NB2); f16: bins 2 i + half (rows of the two halves then fall
-      // into different banks: a 64-byte row covers half of them)
-      unsigned char* const sA_lane = sA + (H ? half * tc::kRowBytes16 : half * NB2 * tc::kRowBytes);
-      if (n_stage_uses >= (uint32_t)C::kNBuf)
-        tc::mbar_wait(&mi.bar_stage[wid][buf], ((n_stage_uses / C::kNBuf) - 1) & 1);
+      unsigned char* const sA_lane = sA + half * NB2 * tc::kRowBytes;   // the lane's bins are [half * NB2, half * NB2 + NB2)
+      // the tensor core may still be reading the operand tile this one goes into
+      if (n_stage_uses >= 1u) tc::mbar_wait(&mi.bar_stage[wid][0], (n_stage_uses - 1) & 1);
       float2 sum = make_float2(0.f, 0.f), dot = sum;
       float mx0 = 0.f, mx1 = 0.f;
       // groups of kGrp bins: table loads of the next group are issued before the operand stores of this one (the
@@ -307,35 +320,14 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
           sum = tc::add2(sum, e[k]);
           dot = tc::fma2(e[k], l[k], dot);
           mx0 = fmaxf(mx0, e[k].x); mx1 = fmaxf(mx1, e[k].y);
-          if (!H) {
-            hi[k] = make_float2(tc::tf32_hi(e[k].x), tc::tf32_hi(e[k].y));
-            lo[k] = tc::sub2(e[k], hi[k]);
-          }
+          hi[k] = make_float2(tc::tf32_hi(e[k].x), tc::tf32_hi(e[k].y));
+          lo[k] = tc::sub2(e[k], hi[k]);
         }
-        if (!H) {
 #pragma unroll
-          for (int k = 0; k < kGrp; ++k) {
-            const int b = g * kGrp + k;
-            *reinterpret_cast<float2*>(sA_lane + b * tc::kRowBytes + off2[b & 7]) = hi[k];
-            *reinterpret_cast<float2*>(sA_lane + (C::kBinsPad + b) * tc::kRowBytes + off2[b & 7]) = lo[k];
-          }
-        } else {
-          // e' = hi + lo / 2^kShiftLo, both fp16: one packed conversion per point pair, residual exact in float32
-          uint32_t h2[kGrp], l2[kGrp];
-#pragma unroll
-          for (int k = 0; k < kGrp; ++k) {
-            h2[k] = tc::pack_f16x2(e[k].x, e[k].y);
-            const float2 r = tc::sub2(e[k], tc::unpack_f16x2(h2[k]));
-            const float2 rs = tc::mul2(r, make_float2((float)(1 << kShiftLo), (float)(1 << kShiftLo)));
-            l2[k] = tc::pack_f16x2(rs.x, rs.y);
-          }
-#pragma unroll
-          for (int k = 0; k < kGrp; ++k) {
-            const int i = g * kGrp + k;   // row 2 i + half; lo rows kBinsPad further down (same swizzle phase)
-            const int ro = (i >> 2) * tc::kGroupBytes16 + ((2 * i) & 7) * tc::kRowBytes16;
-            *reinterpret_cast<uint32_t*>(sA_lane + ro + off2h[i & 3]) = h2[k];
-            *reinterpret_cast<uint32_t*>(sA_lane + C::kBinsPad * tc::kRowBytes16 + ro + off2h[i & 3]) = l2[k];
-          }
+        for (int k = 0; k < kGrp; ++k) {
+          const int b = g * kGrp + k;
+          *reinterpret_cast<float2*>(sA_lane + b * tc::kRowBytes + off2[b & 7]) = hi[k];
+          *reinterpret_cast<float2*>(sA_lane + (C::kBinsPad + b) * tc::kRowBytes + off2[b & 7]) = lo[k];
         }
       }
       // both bin halves -> every lane holds the full row sums of its two points; then back to lane = point
@@ -365,39 +357,23 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
         mx_resp = fmax(mx_resp, (double)emax * inv);
       }
       {
-        const float sc0 = row ? (float)(w_dk * inv) : 0.f;
-        // 16-bit operands: inv is 1 / (2^kShiftE Z); the feature classes carry their own power-of-two scales
-        const float sc = H ? sc0 * (float)(1 << (kShiftE + kShiftD)) : sc0;
-        const float scp = H ? sc0 * (float)(1 << (kShiftE + kShiftP)) : sc0;
-        const float scpp = H ? sc0 * (float)(1 << (kShiftE + kShiftPP)) : sc0;
+        const float sc = row ? (float)(w_dk * inv) : 0.f;
         const float q0 = (float)p0[0], q1 = (float)p0[1], q2 = (float)p0[2];
         const float sd0 = sc * f0, sd1 = sc * f1, sd2 = sc * f2;
-        const float sp0 = scp * q0, sp1 = scp * q1, sp2 = scp * q2;
-        const float sq0 = scpp * q0, sq1 = scpp * q1, sq2 = scpp * q2;
+        const float sp0 = sc * q0, sp1 = sc * q1, sp2 = sc * q2;
         const float v[kNF] = {sc, sd0, sd1, sd2, sd0 * f0, sd0 * f1, sd0 * f2, sd1 * f1, sd1 * f2, sd2 * f2,
-                              sp0, sp1, sp2, sq0 * q0, sq0 * q1, sq0 * q2, sq1 * q1, sq1 * q2, sq2 * q2};
-        if (!H) {
+                              sp0, sp1, sp2, sp0 * q0, sp0 * q1, sp0 * q2, sp1 * q1, sp1 * q2, sp2 * q2};
 #pragma unroll
-          for (int f = 0; f < kNF; ++f) {
-            float hi, lo;
-            tc::split_tf32(v[f], hi, lo);
-            *reinterpret_cast<float*>(sB + f * tc::kRowBytes + off[f & 7]) = hi;
-            *reinterpret_cast<float*>(sB + (kNF + f) * tc::kRowBytes + off[(kNF + f) & 7]) = lo;
-          }
-        } else {
-#pragma unroll
-          for (int f = 0; f < kNF; ++f) {
-            const __half hi = __float2half_rn(v[f]);
-            const __half lo = __float2half_rn((v[f] - __half2float(hi)) * (float)(1 << kShiftLo));
-            constexpr int r1 = kNF;
-            *reinterpret_cast<__half*>(sB + tc::row_base16(f) + offh[(f >> 1) & 3]) = hi;
-            *reinterpret_cast<__half*>(sB + tc::row_base16(r1 + f) + offh[((r1 + f) >> 1) & 3]) = lo;
-          }
+        for (int f = 0; f < kNF; ++f) {
+          float hi, lo;
+          tc::split_tf32(v[f], hi, lo);
+          *reinterpret_cast<float*>(sB + f * tc::kRowBytes + off[f & 7]) = hi;
+          *reinterpret_cast<float*>(sB + (kNF + f) * tc::kRowBytes + off[(kNF + f) & 7]) = lo;
         }
       }
       tc::fence_smem_to_async();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&mi.bar_tile[wid][buf]);   // the issuer warp takes it from here
+      if (lane == 0) tc::mbar_arrive(&mi.bar_tile[wid][0]);   // the issuer warp takes it from here
       ++n_stage_uses;
     }
     // per-warp sums of the scalar certificates (fixed shuffle tree)
@@ -410,6 +386,322 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
     v = warp_max(mx_resp); if (lane == 0) mi.ex[wid][5] = v;
     segment_tail<Q, H>(P, G, sg, mi, stages, cta, tid, nullptr);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Producer, fp16 operands (H = true): 64-point tiles, MN-major unswizzled operand tiles, two points per lane.
+//   A tile: byte (K group kg, M block mb, row r, element) = kg * kKgA + mb * 128 + r * 16 + 2 * (m & 7)
+//   B tile: the same with kKgB; feature columns [hi 0..18, 0, lo 0..18, 0]
+// Lane l owns the points 2 l, 2 l + 1 of the tile and writes them to K rows l and 32 + l.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 16-byte accesses of a pair of consecutive doubles
+__device__ __forceinline__ double2 ldg_d2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ void stg_d2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+
+
+template <int Q>
+__device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const TcGeom& G, TcMisc& mi, unsigned char* stages,
+                                                 uint32_t tmem, int cta, int tid) {
+  constexpr bool H = true;
+  using C = TcCfg<Q, H>;
+  constexpr int kProd = C::kProd;
+  constexpr int kTile = C::kTilePts;
+  const int wid = tid >> 5, lane = tid & 31;
+  uint32_t n_stage_uses = 0;
+  unsigned char* const sA = stages + wid * C::kStageBytes;
+  unsigned char* const sB = sA + C::kABytes;
+  // K rows lane (point a) and 32 + lane (point b): K group lane >> 3 (+ 4), row lane & 7 of the core matrices
+  unsigned char* const sA_a = sA + (lane >> 3) * C::kKgA + (lane & 7) * 16;
+  unsigned char* const sA_b = sA_a + 4 * C::kKgA;
+  unsigned char* const sB_a = sB + (lane >> 3) * kKgB + (lane & 7) * 16;
+  unsigned char* const sB_b = sB_a + 4 * kKgB;
+  const TwistCtxF& tf = mi.twf[wid];
+  int64_t g0 = cta_tile0(G, cta);
+  const int64_t g_end = cta_tile0(G, cta + 1);
+  TcSeg sg;
+  while (next_segment(G, P.n_hyp, g0, g_end, sg)) {
+    const int u = sg.u, s = sg.s, h = sg.h;
+    const int64_t lt0 = sg.lt0, lt1 = sg.lt1;
+    const double t0 = P.t0s[s], t1 = P.t1s[s];
+    const double inv_denom = 1.0 / fmax(t1 - t0, 1e-12);
+    __syncwarp();
+    if (lane == 0) {
+      mi.win[wid] = make_window_ctx(t0, t1);
+      const TwistCtx c = make_twist_ctx(P.xi + (int64_t)u * 6);
+      mi.tw[wid] = c;
+      TwistCtxF& f = mi.twf[wid];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        f.rho[k] = bc2((float)c.rho[k]); f.phi[k] = bc2((float)c.phi[k]); f.nphi[k] = bc2(-(float)c.phi[k]);
+        f.c1[k] = bc2((float)c.c1[k]); f.c2[k] = bc2((float)c.c2[k]); f.norg[k] = bc2(-(float)P.origin[k]);
+      }
+      f.th1sq = bc2((float)c.th1sq); f.nth1sq = bc2(-(float)c.th1sq);
+    }
+    __syncwarp();
+    const double mass_scale = P.mass[s * kNMass + kMassAll] / (P.mass[s * kNMass + kMassSel] + P.eps_mass);
+    const double* pts = P.pts + (int64_t)s * P.n_raw * 3;
+    const double* tp = P.t + (int64_t)s * P.n_raw;
+    const double* wp = P.w + (int64_t)s * P.n_raw;
+    const uint8_t* rp = P.ring ? P.ring + (int64_t)s * P.n_raw : nullptr;
+    const uint8_t* gp = P.tag ? P.tag + (int64_t)s * P.n_raw : nullptr;
+    double* const dkp = P.dk_pts ? P.dk_pts + (int64_t)u * P.cap * 3 : nullptr;
+    double* const dkw = P.dk_w ? P.dk_w + (int64_t)u * P.cap : nullptr;
+    // 16-byte paths: consecutive raw rows (stride 1) and 16-byte aligned scan / unit bases (pair index is even)
+    const bool vec_in = P.stride == 1 && (((uintptr_t)pts | (uintptr_t)tp | (uintptr_t)wp) & 15) == 0 &&
+                        (!rp || ((uintptr_t)rp & 1) == 0) && (!gp || ((uintptr_t)gp & 1) == 0);
+    const bool vec_out = (((uintptr_t)dkp | (uintptr_t)dkw) & 15) == 0;
+    double ent_dot = 0.0, ent_log = 0.0, sum_wdk = 0.0, sum_wrs = 0.0;
+    float mx_resp = 0.f;
+    int n_rows = 0;
+
+    // software pipeline: the raw rows of the warp's next tile are requested before this tile is processed
+    double nx[10];
+    uint32_t nrt = 0;   // ring a | ring b << 8 | tag a << 16 | tag b << 24
+    auto fetch = [&](int64_t tile) {
+      const int64_t ia = tile * kTile + 2 * lane;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) nx[k] = 0.0;
+      nrt = 0;
+      if (tile >= lt1) return;
+      if (vec_in && ia + 1 < P.n_sel) {
+        const double2 a0 = ldg_d2(pts + 3 * ia), a1 = ldg_d2(pts + 3 * ia + 2), a2 = ldg_d2(pts + 3 * ia + 4);
+        const double2 tt = ldg_d2(tp + ia), ww = ldg_d2(wp + ia);
+        nx[0] = a0.x; nx[1] = a0.y; nx[2] = a1.x; nx[3] = tt.x; nx[4] = ww.x;
+        nx[5] = a1.y; nx[6] = a2.x; nx[7] = a2.y; nx[8] = tt.y; nx[9] = ww.y;
+        if (rp) nrt |= (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(rp + ia));
+        if (gp) nrt |= (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(gp + ia)) << 16;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (ia + q < P.n_sel) {
+            const int64_t j = (ia + q) * P.stride;
+            nx[5 * q] = pts[3 * j]; nx[5 * q + 1] = pts[3 * j + 1]; nx[5 * q + 2] = pts[3 * j + 2];
+            nx[5 * q + 3] = tp[j]; nx[5 * q + 4] = wp[j];
+            if (rp) nrt |= (uint32_t)rp[j] << (8 * q);
+            if (gp) nrt |= (uint32_t)gp[j] << (16 + 8 * q);
+          }
+        }
+      }
+    };
+    fetch(lt0 + wid);
+    for (int64_t lt = lt0 + wid; lt < lt1; lt += kProd) {
+      // ================= stage 1: resample gather, sweep fraction + window weight (float64), deskew increment (float32)
+      const int64_t ia = lt * kTile + 2 * lane;
+      const bool row_a = ia < P.cap, row_b = ia + 1 < P.cap;
+      const double pa[3] = {nx[0], nx[1], nx[2]}, pb[3] = {nx[5], nx[6], nx[7]};
+      const double tta = nx[3], ttb = nx[8];
+      const double w_rs_a = nx[4] * mass_scale, w_rs_b = nx[9] * mass_scale;
+      const uint32_t rt = nrt;
+      fetch(lt + kProd);
+      if (h == 0 && P.rs_pts && row_a) {
+        const int64_t o = (int64_t)s * P.cap + ia;
+        P.rs_pts[3 * o] = pa[0]; P.rs_pts[3 * o + 1] = pa[1]; P.rs_pts[3 * o + 2] = pa[2];
+        P.rs_t[o] = tta; P.rs_w[o] = w_rs_a; P.rs_ring[o] = (uint8_t)rt; P.rs_tag[o] = (uint8_t)(rt >> 16);
+        if (row_b) {
+          P.rs_pts[3 * o + 3] = pb[0]; P.rs_pts[3 * o + 4] = pb[1]; P.rs_pts[3 * o + 5] = pb[2];
+          P.rs_t[o + 1] = ttb; P.rs_w[o + 1] = w_rs_b; P.rs_ring[o + 1] = (uint8_t)(rt >> 8); P.rs_tag[o + 1] = (uint8_t)(rt >> 24);
+        }
+      }
+      const double alpha_a = (tta - t0) * inv_denom, alpha_b = (ttb - t0) * inv_denom;
+      const double w_dk_a = w_rs_a * window_weight_ctx(tta, mi.win[wid]);
+      const double w_dk_b = w_rs_b * window_weight_ctx(ttb, mi.win[wid]);
+      const float2 a = make_float2((float)alpha_a, (float)alpha_b);
+      const float2 a2 = tc::mul2(a, a);
+      const float2 th2 = tc::mul2(a2, tf.th1sq);
+      double p0a[3], p0b[3];
+      float2 q[3];   // deskewed point, float32, (point a, point b) per component
+      if (th2.x < 0.25f && th2.y < 0.25f) {
+        // Maclaurin series of sin(th)/th, (1-cos th)/th^2, (th-sin th)/th^3 in th^2 (truncation < 3e-9 for th^2 < 0.25)
+        float2 S = tc::fma2(th2, bc2(2.7557319e-06f), bc2(-1.9841270e-04f));
+        float2 Cc = tc::fma2(th2, bc2(-2.4801587e-05f), bc2(1.3888889e-03f));
+        float2 Gg = tc::fma2(th2, bc2(-2.7557319e-06f), bc2(1.9841270e-04f));
+        S = tc::fma2(S, th2, bc2(8.3333333e-03f));  Cc = tc::fma2(Cc, th2, bc2(-4.1666667e-02f)); Gg = tc::fma2(Gg, th2, bc2(-8.3333333e-03f));
+        S = tc::fma2(S, th2, bc2(-1.6666667e-01f)); Cc = tc::fma2(Cc, th2, bc2(0.5f));            Gg = tc::fma2(Gg, th2, bc2(1.6666667e-01f));
+        S = tc::fma2(S, th2, bc2(1.0f));
+        const float2 aG = tc::mul2(a, Gg);
+        const float2 na = tc::mul2(a, bc2(-1.0f));
+        const float2 pf[3] = {make_float2((float)pa[0], (float)pb[0]), make_float2((float)pa[1], (float)pb[1]),
+                              make_float2((float)pa[2], (float)pb[2])};
+        float2 d1[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float2 uu = tc::fma2(aG, tf.c2[k], tc::mul2(Cc, tf.c1[k]));
+          d1[k] = tc::mul2(na, tc::fma2(a, uu, tf.rho[k]));     // -t(a)
+          q[k] = tc::add2(pf[k], d1[k]);
+        }
+        const float2 x0 = tc::fma2(tf.phi[1], q[2], tc::mul2(tf.nphi[2], q[1]));
+        const float2 x1 = tc::fma2(tf.phi[2], q[0], tc::mul2(tf.nphi[0], q[2]));
+        const float2 x2 = tc::fma2(tf.phi[0], q[1], tc::mul2(tf.nphi[1], q[0]));
+        const float2 pq = tc::fma2(tf.phi[0], q[0], tc::fma2(tf.phi[1], q[1], tc::mul2(tf.phi[2], q[2])));
+        const float2 nsa = tc::mul2(S, na), ca = tc::mul2(Cc, a2);
+        const float2 xs[3] = {x0, x1, x2};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float2 yy = tc::fma2(tf.phi[k], pq, tc::mul2(tf.nth1sq, q[k]));
+          const float2 rot = tc::fma2(ca, yy, tc::mul2(nsa, xs[k]));
+          const float2 dl = tc::add2(d1[k], rot);               // p0 - p, float32
+          q[k] = tc::add2(q[k], rot);
+          p0a[k] = pa[k] + (double)dl.x; p0b[k] = pb[k] + (double)dl.y;
+        }
+      } else {   // large angles (garbage sweep fractions of zero-stamped padded rows): float64 closed forms
+        deskew_point_ctx(pa, alpha_a, mi.tw[wid], p0a);
+        deskew_point_ctx(pb, alpha_b, mi.tw[wid], p0b);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) q[k] = make_float2((float)p0a[k], (float)p0b[k]);
+      }
+      if (row_b && vec_out) {
+        if (dkp) {
+          stg_d2(dkp + 3 * ia, p0a[0], p0a[1]); stg_d2(dkp + 3 * ia + 2, p0a[2], p0b[0]); stg_d2(dkp + 3 * ia + 4, p0b[1], p0b[2]);
+        }
+        if (dkw) stg_d2(dkw + ia, w_dk_a, w_dk_b);
+      } else if (row_a) {
+        if (dkp) {
+          dkp[3 * ia] = p0a[0]; dkp[3 * ia + 1] = p0a[1]; dkp[3 * ia + 2] = p0a[2];
+          if (row_b) { dkp[3 * ia + 3] = p0b[0]; dkp[3 * ia + 4] = p0b[1]; dkp[3 * ia + 5] = p0b[2]; }
+        }
+        if (dkw) { dkw[ia] = w_dk_a; if (row_b) dkw[ia + 1] = w_dk_b; }
+      }
+      if (row_a) { sum_wdk += w_dk_a; sum_wrs += w_rs_a; ++n_rows; }
+      if (row_b) { sum_wdk += w_dk_b; sum_wrs += w_rs_b; ++n_rows; }
+      // ray direction d = r / (|r| + eps), r = p0 - origin
+      float2 f[3];
+      {
+        const float2 r0 = tc::add2(q[0], tf.norg[0]), r1 = tc::add2(q[1], tf.norg[1]), r2 = tc::add2(q[2], tf.norg[2]);
+        const float2 rr = tc::fma2(r0, r0, tc::fma2(r1, r1, tc::mul2(r2, r2)));
+        float2 y = make_float2(rsqrt_approx(fmaxf(rr.x, 1e-36f)), rsqrt_approx(fmaxf(rr.y, 1e-36f)));
+        const float2 nh = tc::mul2(rr, bc2(-0.5f));
+        y = tc::mul2(y, tc::fma2(nh, tc::mul2(y, y), bc2(1.5f)));                 // one Newton step
+        const float2 invn = tc::fma2(tc::mul2(y, bc2(-(float)P.eps_mass)), y, y);   // 1 / (|r| + eps) to first order
+        f[0] = tc::mul2(r0, invn); f[1] = tc::mul2(r1, invn); f[2] = tc::mul2(r2, invn);
+      }
+
+      // ================= stage 2: A = [e_hi ; e_lo] for both points; bins in pairs (b, b + 1) per f32x2 register
+      const float2 ga0 = bc2(f[0].x), ga1 = bc2(f[1].x), ga2 = bc2(f[2].x);
+      const float2 gb0 = bc2(f[0].y), gb1 = bc2(f[1].y), gb2 = bc2(f[2].y);
+      // the tensor core may still be reading this warp's operand tile
+      if (n_stage_uses >= 1u) tc::mbar_wait(&mi.bar_stage[wid][0], (n_stage_uses - 1) & 1);
+      float2 sum_a = make_float2(0.f, 0.f), dot_a = sum_a, sum_b = sum_a, dot_b = sum_a;
+      float mx_a = 0.f, mx_b = 0.f;
+      constexpr int kGroups = C::kBinsPad / 8;   // 8 bins = 4 bin pairs = one 16-byte chunk of hi and one of lo per point
+      float4 tab[2][4][2];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { tab[0][k][0] = mi.bins2[2 * k]; tab[0][k][1] = mi.bins2[2 * k + 1]; }
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) {
+        const int cur = g & 1;
+        if (g + 1 < kGroups) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            tab[cur ^ 1][k][0] = mi.bins2[2 * (4 * (g + 1) + k)];
+            tab[cur ^ 1][k][1] = mi.bins2[2 * (4 * (g + 1) + k) + 1];
+          }
+        }
+        uint32_t ha[4], la[4], hb[4], lb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 ta = tab[cur][k][0], tb = tab[cur][k][1];
+          const float2 mx = make_float2(ta.x, ta.y), my = make_float2(ta.z, ta.w), mz = make_float2(tb.x, tb.y),
+                       cc = make_float2(tb.z, tb.w);
+          const float2 l_a = tc::fma2(ga0, mx, tc::fma2(ga1, my, tc::fma2(ga2, mz, cc)));
+          const float2 l_b = tc::fma2(gb0, mx, tc::fma2(gb1, my, tc::fma2(gb2, mz, cc)));
+          const float2 e_a = make_float2(tc::ex2f(l_a.x), tc::ex2f(l_a.y));
+          const float2 e_b = make_float2(tc::ex2f(l_b.x), tc::ex2f(l_b.y));
+          sum_a = tc::add2(sum_a, e_a); dot_a = tc::fma2(e_a, l_a, dot_a); mx_a = max3f(mx_a, e_a.x, e_a.y);
+          sum_b = tc::add2(sum_b, e_b); dot_b = tc::fma2(e_b, l_b, dot_b); mx_b = max3f(mx_b, e_b.x, e_b.y);
+          // e' = hi + lo, both fp16: hi = rn(e'), lo = rn(e' - hi) (exact residual in float32)
+          ha[k] = tc::pack_f16x2(e_a.x, e_a.y);
+          hb[k] = tc::pack_f16x2(e_b.x, e_b.y);
+          const float2 r_a = tc::sub2(e_a, tc::unpack_f16x2(ha[k]));
+          const float2 r_b = tc::sub2(e_b, tc::unpack_f16x2(hb[k]));
+          la[k] = tc::pack_f16x2(r_a.x, r_a.y);
+          lb[k] = tc::pack_f16x2(r_b.x, r_b.y);
+        }
+        // M block g holds e_hi of bins 8g..8g+7, M block kBinsPad/8 + g their e_lo
+        *reinterpret_cast<uint4*>(sA_a + g * 128) = make_uint4(ha[0], ha[1], ha[2], ha[3]);
+        *reinterpret_cast<uint4*>(sA_a + (kGroups + g) * 128) = make_uint4(la[0], la[1], la[2], la[3]);
+        *reinterpret_cast<uint4*>(sA_b + g * 128) = make_uint4(hb[0], hb[1], hb[2], hb[3]);
+        *reinterpret_cast<uint4*>(sA_b + (kGroups + g) * 128) = make_uint4(lb[0], lb[1], lb[2], lb[3]);
+      }
+
+      // ================= stage 3: B = [phi_hi, 0, phi_lo, 0], phi = (w / Z) (1, d, d d^T, p, p p^T)
+      const float2 ssum = make_float2(sum_a.x + sum_a.y, sum_b.x + sum_b.y);
+      float2 inv = make_float2(rcp_approx(ssum.x), rcp_approx(ssum.y));
+      inv = tc::fma2(inv, tc::fma2(tc::mul2(ssum, bc2(-1.0f)), inv, bc2(1.0f)), inv);   // one Newton step: 1 / (2^kShiftE Z)
+      {
+        const float da_ = (dot_a.x + dot_a.y) * inv.x, db_ = (dot_b.x + dot_b.y) * inv.y;
+        const float lg_a = __log2f(ssum.x), lg_b = __log2f(ssum.y);
+        ent_dot += (double)((row_a ? da_ : 0.f) + (row_b ? db_ : 0.f));
+        ent_log += (double)((row_a ? lg_a : 0.f) + (row_b ? lg_b : 0.f));
+        mx_resp = max3f(mx_resp, row_a ? mx_a * inv.x : 0.f, row_b ? mx_b * inv.y : 0.f);
+      }
+      {
+        const float2 sc0 = tc::mul2(make_float2(row_a ? (float)w_dk_a : 0.f, row_b ? (float)w_dk_b : 0.f), inv);
+        const float2 sc = tc::mul2(sc0, bc2((float)(1 << (kShiftE + kShiftD))));
+        const float2 scp = tc::mul2(sc0, bc2((float)(1 << (kShiftE + kShiftP))));
+        const float2 scpp = tc::mul2(sc0, bc2((float)(1 << (kShiftE + kShiftPP))));
+        const float2 sd0 = tc::mul2(sc, f[0]), sd1 = tc::mul2(sc, f[1]), sd2 = tc::mul2(sc, f[2]);
+        const float2 sq0 = tc::mul2(scpp, q[0]), sq1 = tc::mul2(scpp, q[1]), sq2 = tc::mul2(scpp, q[2]);
+        // 20 columns: the 19 features and a zero
+        const float2 v[20] = {sc, sd0, sd1, sd2, tc::mul2(sd0, f[0]), tc::mul2(sd0, f[1]), tc::mul2(sd0, f[2]),
+                              tc::mul2(sd1, f[1]), tc::mul2(sd1, f[2]), tc::mul2(sd2, f[2]),
+                              tc::mul2(scp, q[0]), tc::mul2(scp, q[1]), tc::mul2(scp, q[2]),
+                              tc::mul2(sq0, q[0]), tc::mul2(sq0, q[1]), tc::mul2(sq0, q[2]),
+                              tc::mul2(sq1, q[1]), tc::mul2(sq1, q[2]), tc::mul2(sq2, q[2]), make_float2(0.f, 0.f)};
+        uint32_t ua[20], ub[20];   // 10 hi words + 10 lo words per point (two features per word)
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          ua[j] = tc::pack_f16x2(v[2 * j].x, v[2 * j + 1].x);
+          ub[j] = tc::pack_f16x2(v[2 * j].y, v[2 * j + 1].y);
+          const float2 h_a = tc::unpack_f16x2(ua[j]), h_b = tc::unpack_f16x2(ub[j]);
+          const float2 r0 = tc::mul2(tc::sub2(v[2 * j], make_float2(h_a.x, h_b.x)), bc2((float)(1 << kShiftLo)));
+          const float2 r1 = tc::mul2(tc::sub2(v[2 * j + 1], make_float2(h_a.y, h_b.y)), bc2((float)(1 << kShiftLo)));
+          ua[10 + j] = tc::pack_f16x2(r0.x, r1.x);
+          ub[10 + j] = tc::pack_f16x2(r0.y, r1.y);
+        }
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          *reinterpret_cast<uint4*>(sB_a + c * 128) = make_uint4(ua[4 * c], ua[4 * c + 1], ua[4 * c + 2], ua[4 * c + 3]);
+          *reinterpret_cast<uint4*>(sB_b + c * 128) = make_uint4(ub[4 * c], ub[4 * c + 1], ub[4 * c + 2], ub[4 * c + 3]);
+        }
+      }
+      tc::fence_smem_to_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&mi.bar_tile[wid][0]);   // the issuer warp takes it from here
+      ++n_stage_uses;
+    }
+    // per-warp sums of the scalar certificates (fixed shuffle tree)
+    double v;
+    v = warp_sum(ent_dot * kLn2); if (lane == 0) mi.ex[wid][kExEntDot] = v;
+    v = warp_sum(ent_log * kLn2); if (lane == 0) mi.ex[wid][kExEntLog] = v;
+    v = warp_sum(sum_wdk); if (lane == 0) mi.ex[wid][kExSumWdk] = v;
+    v = warp_sum(sum_wrs); if (lane == 0) mi.ex[wid][kExSumWrs] = v;
+    v = warp_sum((double)n_rows);  if (lane == 0) mi.ex[wid][kExCount] = v;
+    v = warp_max((double)mx_resp); if (lane == 0) mi.ex[wid][5] = v;
+    segment_tail<Q, H>(P, G, sg, mi, stages, cta, tid, nullptr);
+  }
+}
+
+template <int Q, bool H>
+__device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGeom& G, TcMisc& mi, unsigned char* stages,
+                                              uint32_t tmem, int cta, int tid) {
+  if (H) producer_role_mn<Q>(P, G, mi, stages, tmem, cta, tid);
+  else producer_role_tf32<Q>(P, G, mi, stages, tmem, cta, tid);
 }
 
 template <int Q, bool H>
@@ -446,27 +738,27 @@ __device__ __forceinline__ void epilogue_role(const BinScanParams& P, const TcGe
           tc::mbar_wait(&mi.bar_full[w], n_drained[w] & 1);
           ++n_drained[w];
           tc::fence_after_sync();
-          uint32_t a0[16], a1[16], a2[4], a3[2];
+          uint32_t a0[16], a1[16], a2[4], a3[4];
           const uint32_t addr = tmem + lane_base + w * kAccStride;
           tc::tmem_ld_x16(addr, a0);
           tc::tmem_ld_x16(addr + 16, a1);
           tc::tmem_ld_x4(addr + 32, a2);
-          tc::tmem_ld_x2(addr + 36, a3);
+          tc::tmem_ld_x4(addr + 36, a3);
           tc::tmem_ld_wait();
           tc::fence_before_sync();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&mi.bar_empty[w]);
-          // column f holds row x phi_hi[f], column 19 + f row x phi_lo[f] (2^-11 of the former): one float32 add, then
-          // the float64 accumulation
-          float v[2 * kNF];
+          // column f holds row x phi_hi[f], column kLoCol + f row x phi_lo[f] (fp16 operands: 2^-11 of the former): one
+          // float32 add, then the float64 accumulation
+          float v[40];
 #pragma unroll
           for (int c = 0; c < 16; ++c) { v[c] = __uint_as_float(a0[c]); v[16 + c] = __uint_as_float(a1[c]); }
 #pragma unroll
-          for (int c = 0; c < 4; ++c) v[32 + c] = __uint_as_float(a2[c]);
-          v[36] = __uint_as_float(a3[0]); v[37] = __uint_as_float(a3[1]);
+          for (int c = 0; c < 4; ++c) { v[32 + c] = __uint_as_float(a2[c]); v[36 + c] = __uint_as_float(a3[c]); }
+          constexpr int kLo = TcCfg<Q, H>::kLoCol;
 #pragma unroll
           for (int f = 0; f < kNF; ++f)
-            acc[f] += (double)(H ? fmaf(v[kNF + f], 1.0f / (float)(1 << kShiftLo), v[f]) : v[f] + v[kNF + f]);
+            acc[f] += (double)(H ? fmaf(v[kLo + f], 1.0f / (float)(1 << kShiftLo), v[f]) : v[f] + v[kLo + f]);
         }
       }
       if (!any) break;
@@ -488,7 +780,7 @@ __device__ __forceinline__ void issuer_role(const BinScanParams& P, const TcGeom
   const int lane = tid & 31;
   int64_t g0 = cta_tile0(G, cta);
   const int64_t g_end = cta_tile0(G, cta + 1);
-  const uint32_t idesc = H ? tc::idesc_f16(128, kMmaN) : tc::idesc_tf32(128, kMmaN);
+  const uint32_t idesc = H ? (tc::idesc_f16(128, kMmaN) | tc::kIdescMnMajorA | tc::kIdescMnMajorB) : tc::idesc_tf32(128, kMmaN);
   const uint32_t a0 = tc::smem_u32(stages);
   TcSeg sg;
   // lane w (< kProd) keeps the tile / round counters of producer warp w and polls its barriers; lane 0 issues
@@ -504,37 +796,38 @@ __device__ __forceinline__ void issuer_role(const BinScanParams& P, const TcGeom
         const bool pending = t < my_tiles;
         bool ready = false;
         if (pending) {
-          ready = tc::mbar_test_wait(&mi.bar_tile[lane][n_done % C::kNBuf], (n_done / C::kNBuf) & 1u);
+          ready = tc::mbar_test_wait(&mi.bar_tile[lane][0], n_done & 1u);
           if (ready && in_round == 0 && have_round) ready = tc::mbar_test_wait(&mi.bar_empty[lane], par_empty);
         }
         const unsigned rdy = __ballot_sync(0xffffffffu, ready);
         if (rdy == 0u) {
           if (__ballot_sync(0xffffffffu, pending) == 0u) break;
+          __nanosleep(kIssuerSleepNs);   // a producer needs microseconds per tile: do not spend its issue slots on polling
           continue;
         }
         const bool last = (in_round + 1 == G.flush) || (t + 1 >= my_tiles);
         const unsigned first_m = __ballot_sync(0xffffffffu, ready && in_round == 0);
         const unsigned last_m = __ballot_sync(0xffffffffu, ready && last);
-        const unsigned buf_m = H ? __ballot_sync(0xffffffffu, ready && (n_done & 1u)) : 0u;   // operand buffer of the tile
         tc::fence_after_sync();
         if (lane == 0) {
           unsigned m = rdy;
           while (m) {
             const int w = __ffs(m) - 1;
             m &= m - 1;
-            const uint32_t buf = (buf_m >> w) & 1u;
-            const uint32_t sa = a0 + (w * C::kNBuf + buf) * C::kStageBytes;
-            const uint64_t da = H ? tc::smem_desc_sw64(sa) : tc::smem_desc_sw128(sa);
-            const uint64_t db = H ? tc::smem_desc_sw64(sa + C::kABytes) : tc::smem_desc_sw128(sa + C::kABytes);
+            const uint32_t sa = a0 + w * C::kStageBytes;
+            const uint64_t da = H ? tc::smem_desc_mn(sa, C::kKgA, 128) : tc::smem_desc_sw128(sa);
+            const uint64_t db = H ? tc::smem_desc_mn(sa + C::kABytes, kKgB, 128) : tc::smem_desc_sw128(sa + C::kABytes);
             const uint32_t d_tmem = tmem + w * kAccStride;
             const uint32_t acc0 = ((first_m >> w) & 1u) ^ 1u;
-            // one MMA consumes 32 bytes of every operand row (8 tf32 / 16 fp16 points): descriptor start + 2 (x 16 B)
+            // tf32: one MMA consumes 32 bytes of every operand row (8 points): descriptor start + 2 (x 16 B);
+            // fp16: one MMA consumes two K groups (16 points): descriptor start + 2 K-group strides
 #pragma unroll
             for (int ks = 0; ks < C::kMmaPerTile; ++ks) {
-              if (H) tc::mma_f16_ss(d_tmem, da + 2 * ks, db + 2 * ks, idesc, ks ? 1u : acc0);
+              if (H) tc::mma_f16_ss(d_tmem, da + (uint64_t)(ks * ((2 * C::kKgA) >> 4)), db + (uint64_t)(ks * ((2 * kKgB) >> 4)), idesc,
+                                    ks ? 1u : acc0);
               else tc::mma_tf32_ss(d_tmem, da + 2 * ks, db + 2 * ks, idesc, ks ? 1u : acc0);
             }
-            tc::mma_commit(&mi.bar_stage[w][buf]);
+            tc::mma_commit(&mi.bar_stage[w][0]);
             if ((last_m >> w) & 1u) tc::mma_commit(&mi.bar_full[w]);
           }
         }
@@ -587,11 +880,17 @@ __global__ void __launch_bounds__(TcCfg<Q, H>::kThreads, 1) bin_scan_tc_kernel(c
         x = (float)(P.bin_dirs[3 * b] * sc); y = (float)(P.bin_dirs[3 * b + 1] * sc); z = (float)(P.bin_dirs[3 * b + 2] * sc);
         w = H ? (float)kShiftE - c2 : -c2;   // 16-bit operands: e' = 2^kShiftE e
       }
-      // interleave the two bin halves (lanes 0-15 / 16-31 read entry i of their half in the same instruction): the two
-      // 16-byte reads of a warp then fall into different banks
-      const int e = H ? b : (b % (C::kBinsPad / 2)) * 2 + b / (C::kBinsPad / 2);
-      mi.bins2[2 * e] = make_float4(x, x, y, y);
-      mi.bins2[2 * e + 1] = make_float4(z, z, w, w);
+      if (H) {
+        // per bin pair (b, b + 1): (x_b, x_b1, y_b, y_b1), (z_b, z_b1, w_b, w_b1) -- f32x2 operands over the two bins
+        float* t = reinterpret_cast<float*>(mi.bins2 + 2 * (b >> 1));
+        t[b & 1] = x; t[2 + (b & 1)] = y; t[4 + (b & 1)] = z; t[6 + (b & 1)] = w;
+      } else {
+        // interleave the two bin halves (lanes 0-15 / 16-31 read entry i of their half in the same instruction): the two
+        // 16-byte reads of a warp then fall into different banks
+        const int e = (b % (C::kBinsPad / 2)) * 2 + b / (C::kBinsPad / 2);
+        mi.bins2[2 * e] = make_float4(x, x, y, y);
+        mi.bins2[2 * e + 1] = make_float4(z, z, w, w);
+      }
     }
   }
   if (tid == 0) {
@@ -643,17 +942,18 @@ int tc_flush_tiles() {
   return v;
 }
 
-TcGeom make_geom(int sm_count, int n_units, int64_t cap, int n_parts, int n_prod) {
+TcGeom make_geom(int sm_count, int n_units, int64_t cap, int n_parts, int n_prod, int tile_pts) {
   const int kProd = n_prod;
   TcGeom G;
-  G.tiles_per_unit = (cap + tc::kTileK - 1) / tc::kTileK;
+  G.tiles_per_unit = (cap + tile_pts - 1) / tile_pts;
   G.total_tiles = G.tiles_per_unit * n_units;
   int64_t n_cta = (G.total_tiles + kProd - 1) / kProd;
   if (n_cta > sm_count) n_cta = sm_count;
   if (n_cta < 1) n_cta = 1;
   G.n_cta = (int)n_cta;
   G.n_parts = n_parts;
-  G.flush = tc_flush_tiles();
+  G.flush = tc_flush_tiles() * tc::kTileK / tile_pts;   // GCS_TC_FLUSH counts 32-point tiles
+  if (G.flush < 1) G.flush = 1;
   G.dbg = getenv("GCS_TC_TIMES") ? 1 : 0;
   return G;
 }
@@ -705,7 +1005,7 @@ cudaError_t launch_q(cudaStream_t st, const BinScanParams& P, const TcGeom& G) {
 
 // a unit is touched by at most ceil(n_cta / U) + 1 CTAs
 int bin_scan_tc_parts(int sm_count, int n_units, int64_t cap) {
-  TcGeom G = make_geom(sm_count, n_units, cap, 0, 8);   // fewest producer warps of any instantiation: most CTAs
+  TcGeom G = make_geom(sm_count, n_units, cap, 0, 8, tc::kTileK);   // fewest producer warps, smallest tiles: most CTAs
   return (G.n_cta + n_units - 1) / n_units + 1;
 }
 
@@ -716,11 +1016,11 @@ bool bin_scan_tc_supported(const BinScanParams& P) {
 cudaError_t launch_bin_scan_tc(int sm_count, cudaStream_t st, const BinScanParams& P, int n_parts) {
   const int U = P.n_scans * P.n_hyp;
   if (tc_use_f16(P.inv_tau)) {
-    if (P.n_bins <= 48) return launch_q<3, true>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<3, true>::kProd));
-    return launch_q<4, true>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<4, true>::kProd));
+    if (P.n_bins <= 48) return launch_q<3, true>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<3, true>::kProd, TcCfg<3, true>::kTilePts));
+    return launch_q<4, true>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<4, true>::kProd, TcCfg<4, true>::kTilePts));
   }
-  if (P.n_bins <= 48) return launch_q<3, false>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<3, false>::kProd));
-  return launch_q<4, false>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<4, false>::kProd));
+  if (P.n_bins <= 48) return launch_q<3, false>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<3, false>::kProd, TcCfg<3, false>::kTilePts));
+  return launch_q<4, false>(st, P, make_geom(sm_count, U, P.cap, n_parts, TcCfg<4, false>::kProd, TcCfg<4, false>::kTilePts));
 }
 
 }  // namespace gcs

@@ -53,6 +53,18 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)4 << 61;                                  // SWIZZLE_64B
   return d;
 }
+// ---- MN-major, unswizzled ("interleaved") operands: the 8 x 8 core matrix is 8 K rows of 16 bytes (8 consecutive M / N
+// elements of 16 bits) = 128 contiguous bytes; M / N blocks of 8 elements are `sbo_bytes` apart, groups of 8 K rows
+// `lbo_bytes` apart (tools/tc_probe_mn.cu: the other assignment faults).  One kind::f16 MMA (K = 16) reads two K groups.
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;                                  // descriptor version (sm_100); layout type 0: no swizzle
+  return d;
+}
+constexpr uint32_t kIdescMnMajorA = 1u << 15, kIdescMnMajorB = 1u << 16;
 // instruction descriptor, kind::f16: D f32, A/B f16 (format 0), both K-major, dense
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
