@@ -9,6 +9,7 @@ Layout
   operators.py   bin family: point_budget_resample, deskew_constant_twist, bin_soft_assign, ...
   primitives.py  primitive family: extract_lidar_surfels, associate_primitives_ot, map update, ...
   imu.py         IMU window weights + preintegration -> scan twist xi_body (the step in front of the deskew)
+  hypothesis_batch.py  the per-scan hypothesis loop, batched: H hypotheses of one scan through the primitive family at once
   fusion.py      evidence fusion for all hypotheses in one launch (tempering, prior scaling, fusion scale, additive fusion)
   sharding.py    scan / point sharding over ranks, hypothesis combine
   synth.py       seeded synthetic scans / maps
@@ -17,7 +18,7 @@ Sub-modules are imported on demand so that ``import gc_slam_b200`` itself never 
 
 __version__ = "0.1.0"
 
-_LAZY = ("constants", "certs", "synth", "_lib", "operators", "primitives", "imu", "fusion", "manifest", "sharding", "build")
+_LAZY = ("constants", "certs", "synth", "_lib", "operators", "primitives", "imu", "fusion", "manifest", "sharding", "build", "hypothesis_batch")
 
 
 def __getattr__(name):

@@ -467,13 +467,24 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
 // ------------------------------------------------------------------------------------------------
 // Stand-alone operator kernels
 // ------------------------------------------------------------------------------------------------
+// blockIdx.y = unit (hypothesis): every unit deskews the SAME raw points with its own twist.  xi_dev != NULL: twists
+// read from device memory, (n_units, 6); outputs and partial sums are stacked per unit.
 __global__ void __launch_bounds__(256) deskew_kernel(const double* __restrict__ pts, const double* __restrict__ t,
                                                      const double* __restrict__ w, int64_t n, double xi0, double xi1,
-                                                     double xi2, double xi3, double xi4, double xi5, double t0, double t1,
+                                                     double xi2, double xi3, double xi4, double xi5,
+                                                     const double* __restrict__ xi_dev, double t0, double t1,
                                                      double* __restrict__ o_pts, double* __restrict__ o_w,
                                                      double* __restrict__ partial) {
   __shared__ double sred[8];
-  const double xi[6] = {xi0, xi1, xi2, xi3, xi4, xi5};
+  const int u = blockIdx.y;
+  double xi[6] = {xi0, xi1, xi2, xi3, xi4, xi5};
+  if (xi_dev) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) xi[k] = xi_dev[6 * u + k];
+  }
+  o_pts += (int64_t)u * 3 * n;
+  o_w += (int64_t)u * n;
+  partial += (int64_t)u * gridDim.x * 2;
   const double inv_denom = 1.0 / fmax(t1 - t0, 1e-12);
   const double inv_sig = window_inv_sigma(t0, t1);
   double s_out = 0.0, s_in = 0.0;
@@ -491,14 +502,16 @@ __global__ void __launch_bounds__(256) deskew_kernel(const double* __restrict__ 
   double b = block_sum_fixed(s_in, sred);
   if (threadIdx.x == 0) { partial[2 * blockIdx.x] = a; partial[2 * blockIdx.x + 1] = b; }
 }
-__global__ void sum_pairs_kernel(const double* __restrict__ partial, int n_parts, int width, double* __restrict__ out) {
+// blockIdx.x = unit: out[u * out_stride + k] = sum over the unit's parts, in part order
+__global__ void sum_pairs_kernel(const double* __restrict__ partial, int n_parts, int width, double* __restrict__ out,
+                                 int out_stride) {
   int k = threadIdx.x;
   if (k >= width) return;
+  partial += (int64_t)blockIdx.x * n_parts * width;
   double a = 0.0;
   for (int c = 0; c < n_parts; ++c) a += partial[(int64_t)c * width + k];
-  out[k] = a;
+  out[(int64_t)blockIdx.x * out_stride + k] = a;
 }
-
 __global__ void __launch_bounds__(256) ray_dirs_kernel(const double* __restrict__ pts, int64_t n, double o0, double o1,
                                                        double o2, double eps, double* __restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -923,23 +936,41 @@ int gcs_point_budget_resample(gcs_ctx* ctx, void* stream, const double* pts, con
 }
 
 // ---- a2 ---------------------------------------------------------------------------------------------
+static int deskew_launch(gcs_ctx* ctx, cudaStream_t st, const double* pts, const double* t, const double* w, int64_t n,
+                         const double* xi_host, const double* xi_dev, int n_units, double t0, double t1, double* out_pts,
+                         double* out_w, double* cert) {
+  int blocks = (int)ceil_div64(n > 0 ? n : 1, 256);
+  int maxb = ctx->sm_count * 8;
+  if (blocks > maxb) blocks = maxb;
+  int rc = gcs_ws_reserve(ctx, (uint64_t)n_units * blocks * 2 * sizeof(double));
+  if (rc) return rc;
+  double* part = (double*)ctx->ws;
+  const double z6[6] = {0, 0, 0, 0, 0, 0};
+  const double* xi = xi_host ? xi_host : z6;
+  deskew_kernel<<<dim3(blocks, n_units), 256, 0, st>>>(pts, t, w, n, xi[0], xi[1], xi[2], xi[3], xi[4], xi[5], xi_dev, t0, t1,
+                                                       out_pts, out_w, part);
+  GCS_LAUNCH_CHECK(ctx);
+  sum_pairs_kernel<<<n_units, 32, 0, st>>>(part, blocks, 2, cert, GCS_DK_NCERT);
+  GCS_LAUNCH_CHECK(ctx);
+  return GCS_OK;
+}
+
 int gcs_deskew_constant_twist(gcs_ctx* ctx, void* stream, const double* pts, const double* t, const double* w, int64_t n,
                               const double* xi, double t0, double t1, double* out_pts, double* out_w, double* cert) {
   if (!ctx) return GCS_EINVAL;
   GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
   GCS_REQUIRE(ctx, n >= 0 && xi && cert && (n == 0 || (pts && t && w && out_pts && out_w)), "deskew_constant_twist: bad args");
-  cudaStream_t st = (cudaStream_t)stream;
-  int blocks = (int)ceil_div64(n > 0 ? n : 1, 256);
-  int maxb = ctx->sm_count * 8;
-  if (blocks > maxb) blocks = maxb;
-  int rc = gcs_ws_reserve(ctx, (uint64_t)blocks * 2 * sizeof(double));
-  if (rc) return rc;
-  double* part = (double*)ctx->ws;
-  deskew_kernel<<<blocks, 256, 0, st>>>(pts, t, w, n, xi[0], xi[1], xi[2], xi[3], xi[4], xi[5], t0, t1, out_pts, out_w, part);
-  GCS_LAUNCH_CHECK(ctx);
-  sum_pairs_kernel<<<1, 32, 0, st>>>(part, blocks, 2, cert);
-  GCS_LAUNCH_CHECK(ctx);
-  return GCS_OK;
+  return deskew_launch(ctx, (cudaStream_t)stream, pts, t, w, n, xi, nullptr, 1, t0, t1, out_pts, out_w, cert);
+}
+
+int gcs_deskew_constant_twist_batched(gcs_ctx* ctx, void* stream, const double* pts, const double* t, const double* w,
+                                      int64_t n, const double* xi_dev, int32_t n_units, double t0, double t1,
+                                      double* out_pts, double* out_w, double* cert) {
+  if (!ctx) return GCS_EINVAL;
+  GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  GCS_REQUIRE(ctx, n >= 1 && n_units >= 1 && n_units <= 65535 && xi_dev && cert && pts && t && w && out_pts && out_w,
+              "deskew_constant_twist_batched: bad args");
+  return deskew_launch(ctx, (cudaStream_t)stream, pts, t, w, n, nullptr, xi_dev, n_units, t0, t1, out_pts, out_w, cert);
 }
 
 // ---- a3 ---------------------------------------------------------------------------------------------

@@ -90,6 +90,20 @@ constexpr double kKappaR0 = 0.8;            // :95
 constexpr double kKappaTau = 0.03;          // :96
 constexpr double kF64Eps = 2.220446049250313e-16;
 
+// Unit axis of the batched primitive path: unit u (hypothesis) of a stacked (n_units, N_total, ...) structure
+__device__ __forceinline__ gcs_meas_batch meas_batch_unit(gcs_meas_batch B, int64_t u) {
+  const int64_t o = u * (B.n_feat + B.n_surfel);
+  B.Lambdas += 9 * o; B.thetas += 3 * o; B.etas += 9 * o; B.weights += o; B.sources += o; B.source_indices += o;
+  B.valid += o; B.timestamps += o; B.colors += 3 * o;
+  return B;
+}
+__device__ __forceinline__ gcs_assoc_result assoc_result_unit(gcs_assoc_result R, int64_t u, int N, int K) {
+  const int64_t o = u * N;
+  R.responsibilities += o * K; R.candidate_pool_indices += o * K; R.candidate_tile_ids += o * K; R.candidate_slots += o * K;
+  R.row_masses += o; R.cost_matrix += o * K;
+  return R;
+}
+
 struct Mat3 {
   double m[9];  // row-major
   __host__ __device__ double& operator()(int r, int c) { return m[3 * r + c]; }

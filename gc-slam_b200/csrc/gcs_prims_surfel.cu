@@ -18,6 +18,11 @@ struct SurfelGeom {
   int nc1, nc2, ncz, n_cells, max_occ, min_points;
   double h;
 };
+// Unit axis (blockIdx.y = hypothesis): element strides of the per-unit inputs (0 = shared by all units).  Work arrays
+// and outputs are stacked per unit.
+struct UnitStrides {
+  int64_t pts, w, ts;
+};
 
 __device__ __forceinline__ bool surfel_point_ok(const double* p) {
   // jnp.all(jnp.abs(points) < 0.1 * GC_NONFINITE_SENTINEL)   (lidar_surfel_extraction.py:259-262); NaN -> false
@@ -27,8 +32,10 @@ __device__ __forceinline__ bool surfel_point_ok(const double* p) {
 // ---- S1 ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSurfThreads) surfel_center_partial_kernel(const double* __restrict__ pts,
                                                                              const double* __restrict__ w, int64_t n,
-                                                                             int64_t per_block, double* __restrict__ part) {
+                                                                             int64_t per_block, double* __restrict__ part,
+                                                                             UnitStrides U) {
   __shared__ double sred[4][kSurfThreads / 32];
+  pts += blockIdx.y * U.pts; w += blockIdx.y * U.w; part += (int64_t)blockIdx.y * gridDim.x * 4;
   const int64_t i0 = (int64_t)blockIdx.x * per_block;
   const int64_t i1 = (i0 + per_block < n) ? i0 + per_block : n;
   double a[4] = {0, 0, 0, 0};
@@ -51,6 +58,7 @@ __global__ void __launch_bounds__(kSurfThreads) surfel_center_partial_kernel(con
 __global__ void surfel_center_final_kernel(const double* __restrict__ part, int n_parts, double eig_min,
                                            double* __restrict__ center) {
   if (threadIdx.x != 0) return;
+  part += (int64_t)blockIdx.x * n_parts * 4; center += blockIdx.x * 4;
   double a[4] = {0, 0, 0, 0};
   for (int c = 0; c < n_parts; ++c)
     for (int k = 0; k < 4; ++k) a[k] += part[4 * c + k];
@@ -63,9 +71,11 @@ __device__ __forceinline__ int pymod(int a, int n) { int r = a % n; return r < 0
 
 __global__ void __launch_bounds__(kSurfThreads) surfel_cell_key_kernel(const double* __restrict__ pts,
                                                                        const double* __restrict__ center, int64_t n,
-                                                                       SurfelGeom G, int32_t* __restrict__ key) {
+                                                                       SurfelGeom G, int32_t* __restrict__ key,
+                                                                       UnitStrides U) {
   const int64_t i = (int64_t)blockIdx.x * kSurfThreads + threadIdx.x;
   if (i >= n) return;
+  pts += blockIdx.y * U.pts; center += blockIdx.y * 4; key += (int64_t)blockIdx.y * n;
   const double p[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
   int k = G.n_cells;  // masked points sort last and never enter a bucket
   if (surfel_point_ok(p)) {
@@ -86,6 +96,7 @@ __global__ void __launch_bounds__(1024) surfel_rank_chunk_kernel(const int32_t* 
                                                                  int32_t* __restrict__ local_rank,
                                                                  int32_t* __restrict__ hist) {
   extern __shared__ int s_cnt[];  // n_keys ints
+  key += (int64_t)blockIdx.y * n; local_rank += (int64_t)blockIdx.y * n; hist += (int64_t)blockIdx.y * gridDim.x * n_keys;
   for (int k = threadIdx.x; k < n_keys; k += 1024) s_cnt[k] = 0;
   __syncthreads();
   const int64_t i0 = (int64_t)blockIdx.x * per_chunk;
@@ -114,6 +125,7 @@ __global__ void __launch_bounds__(1024) surfel_rank_chunk_kernel(const int32_t* 
 __global__ void surfel_rank_scan_kernel(int32_t* __restrict__ hist, int n_chunks, int n_keys, int32_t* __restrict__ total) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_keys) return;
+  hist += (int64_t)blockIdx.y * n_chunks * n_keys; total += (int64_t)blockIdx.y * n_keys;
   int acc = 0;
   for (int c = 0; c < n_chunks; ++c) {
     const int v = hist[(int64_t)c * n_keys + k];
@@ -130,9 +142,11 @@ __global__ void __launch_bounds__(kSurfThreads) surfel_bucket_fill_kernel(const 
                                                                           const int32_t* __restrict__ local_rank,
                                                                           const int32_t* __restrict__ hist, int64_t n,
                                                                           int64_t per_chunk, int n_keys, SurfelGeom G,
-                                                                          int32_t* __restrict__ bucket) {
+                                                                          int32_t* __restrict__ bucket, int n_chunks) {
   const int64_t i = (int64_t)blockIdx.x * kSurfThreads + threadIdx.x;
   if (i >= n) return;
+  key += (int64_t)blockIdx.y * n; local_rank += (int64_t)blockIdx.y * n; hist += (int64_t)blockIdx.y * n_chunks * n_keys;
+  bucket += (int64_t)blockIdx.y * G.n_cells * G.max_occ;
   const int k = key[i];
   if (k >= G.n_cells) return;
   const int chunk = (int)(i / per_chunk);
@@ -151,6 +165,12 @@ struct CellFit {  // per cell, SoA in workspace
   uint8_t* valid;    // (C)
 };
 
+__device__ __forceinline__ CellFit cellfit_unit(CellFit F, int64_t u, int n_cells) {
+  const int64_t o = u * n_cells;
+  F.centroid += 3 * o; F.Sigma += 9 * o; F.normal += 3 * o; F.kappa += o; F.w += o; F.t += o; F.valid += o;
+  return F;
+}
+
 __device__ __forceinline__ void normalize3(double* v, double eps) {
   const double inv = 1.0 / (sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) + eps);
   v[0] *= inv; v[1] *= inv; v[2] *= inv;
@@ -160,9 +180,15 @@ __global__ void __launch_bounds__(128) surfel_fit_kernel(const double* __restric
                                                          const double* __restrict__ w, const double* __restrict__ center,
                                                          const int32_t* __restrict__ bucket,
                                                          const int32_t* __restrict__ total, SurfelGeom G,
-                                                         gcs_surfel_cfg cfg, CellFit F) {
+                                                         gcs_surfel_cfg cfg, CellFit F, UnitStrides U, int n_keys) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= G.n_cells) return;
+  {
+    const int64_t u = blockIdx.y;
+    pts += u * U.pts; ts += u * U.ts; w += u * U.w; center += u * 4;
+    bucket += u * G.n_cells * G.max_occ; total += u * n_keys;
+    F = cellfit_unit(F, u, G.n_cells);
+  }
   const double eps = 1e-12, eig_min = cfg.eig_min;
   const int cnt = total[c] < G.max_occ ? total[c] : G.max_occ;
   const double cx = center[0], cy = center[1], cz = center[2];
@@ -262,10 +288,17 @@ __global__ void __launch_bounds__(128) surfel_fit_kernel(const double* __restric
 __global__ void __launch_bounds__(1024) surfel_select_kernel(CellFit F, SurfelGeom G, gcs_meas_batch B, double eps_lift,
                                                              int32_t* __restrict__ out_n_valid,
                                                              const int32_t* __restrict__ total,
-                                                             int32_t* __restrict__ out_count) {
+                                                             int32_t* __restrict__ out_count, int n_keys) {
   __shared__ int s_scan[1024];
   __shared__ int s_total;
   const int tid = threadIdx.x;
+  {
+    const int64_t u = blockIdx.x;
+    F = cellfit_unit(F, u, G.n_cells);
+    B = meas_batch_unit(B, u);
+    out_n_valid += u; total += u * n_keys;
+    if (out_count) out_count += u * G.n_cells;
+  }
   const int per = (G.n_cells + 1023) / 1024;
   const int c0 = tid * per, c1 = (c0 + per < G.n_cells) ? c0 + per : G.n_cells;
   int cnt = 0;
@@ -374,25 +407,22 @@ int gcs_batch_from_camera_splats(gcs_ctx* ctx, void* stream, const double* posit
   return GCS_OK;
 }
 
-int gcs_extract_lidar_surfels(gcs_ctx* ctx, void* stream, const double* pts, const double* timestamps,
-                              const double* weights, int64_t n, const gcs_surfel_cfg* cfg, const gcs_meas_batch* batch,
-                              int32_t* out_n_valid, int32_t* out_bucket, int32_t* out_count) {
-  if (!ctx) return GCS_EINVAL;
-  GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-  int rc = check_batch(ctx, batch, "extract_lidar_surfels");
+static int surfels_launch(gcs_ctx* ctx, cudaStream_t st, const double* pts, const double* timestamps, const double* weights,
+                          int64_t n, int n_units, UnitStrides U, const gcs_surfel_cfg* cfg, const gcs_meas_batch* batch,
+                          int32_t* out_n_valid, int32_t* out_bucket, int32_t* out_count, const char* who) {
+  int rc = check_batch(ctx, batch, who);
   if (rc) return rc;
-  GCS_REQUIRE(ctx, cfg && pts && timestamps && weights && out_n_valid && n >= 1, "extract_lidar_surfels: bad args");
+  GCS_REQUIRE(ctx, cfg && pts && timestamps && weights && out_n_valid && n >= 1, "%s: bad args", who);
   GCS_REQUIRE(ctx, cfg->n_cells_1 > 0 && cfg->n_cells_2 > 0 && cfg->n_cells_z > 0 && cfg->max_occupants > 0 &&
-                       cfg->max_occupants <= 1024, "extract_lidar_surfels: bad grid config");
-  GCS_REQUIRE(ctx, n < (1ll << 31), "extract_lidar_surfels: n too large for int32 point indices");
-  cudaStream_t st = (cudaStream_t)stream;
+                       cfg->max_occupants <= 1024, "%s: bad grid config", who);
+  GCS_REQUIRE(ctx, n < (1ll << 31), "%s: n too large for int32 point indices", who);
   SurfelGeom G;
   G.nc1 = cfg->n_cells_1; G.nc2 = cfg->n_cells_2; G.ncz = cfg->n_cells_z;
   G.n_cells = G.nc1 * G.nc2 * G.ncz;
   G.max_occ = cfg->max_occupants; G.min_points = cfg->min_points_per_voxel;
   G.h = cfg->voxel_size_m > 1e-12 ? cfg->voxel_size_m : 1e-12;
   const int n_keys = G.n_cells + 1;
-  GCS_REQUIRE(ctx, (size_t)n_keys * sizeof(int) <= 160 * 1024, "extract_lidar_surfels: %d cells exceed the shared-memory counter", G.n_cells);
+  GCS_REQUIRE(ctx, (size_t)n_keys * sizeof(int) <= 160 * 1024, "%s: %d cells exceed the shared-memory counter", who, G.n_cells);
   int n_chunks = (int)cdiv(n, 1024);
   const int max_chunks = ctx->sm_count * 2;
   if (n_chunks > max_chunks) n_chunks = max_chunks;
@@ -400,9 +430,10 @@ int gcs_extract_lidar_surfels(gcs_ctx* ctx, void* stream, const double* pts, con
   n_chunks = (int)cdiv(n, per_chunk);
   const int n_cblocks = (int)(cdiv(n, 8192) < 256 ? cdiv(n, 8192) : 256);
   const int64_t per_cblock = cdiv(n, n_cblocks);
-  // workspace carve-up
+  // workspace carve-up: every array stacked per unit
+  const size_t H = (size_t)n_units;
   size_t off = 0;
-  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes * H + 255) & ~(size_t)255; return o; };
   const size_t o_part = take((size_t)n_cblocks * 4 * 8), o_center = take(4 * 8), o_key = take((size_t)n * 4),
                o_lrank = take((size_t)n * 4), o_hist = take((size_t)n_chunks * n_keys * 4), o_total = take((size_t)n_keys * 4),
                o_bucket = take((size_t)G.n_cells * G.max_occ * 4), o_cen = take((size_t)G.n_cells * 3 * 8),
@@ -422,29 +453,52 @@ int gcs_extract_lidar_surfels(gcs_ctx* ctx, void* stream, const double* pts, con
   F.centroid = (double*)(ws + o_cen); F.Sigma = (double*)(ws + o_sig); F.normal = (double*)(ws + o_nrm);
   F.kappa = (double*)(ws + o_kap); F.w = (double*)(ws + o_w); F.t = (double*)(ws + o_t); F.valid = (uint8_t*)(ws + o_val);
 
-  surfel_center_partial_kernel<<<n_cblocks, kSurfThreads, 0, st>>>(pts, weights, n, per_cblock, part);
+  const unsigned Hu = (unsigned)n_units;
+  surfel_center_partial_kernel<<<dim3(n_cblocks, Hu), kSurfThreads, 0, st>>>(pts, weights, n, per_cblock, part, U);
   GCS_LAUNCH_CHECK(ctx);
-  surfel_center_final_kernel<<<1, 32, 0, st>>>(part, n_cblocks, cfg->eig_min, center);
+  surfel_center_final_kernel<<<Hu, 32, 0, st>>>(part, n_cblocks, cfg->eig_min, center);
   GCS_LAUNCH_CHECK(ctx);
-  surfel_cell_key_kernel<<<(unsigned)cdiv(n, kSurfThreads), kSurfThreads, 0, st>>>(pts, center, n, G, key);
+  surfel_cell_key_kernel<<<dim3((unsigned)cdiv(n, kSurfThreads), Hu), kSurfThreads, 0, st>>>(pts, center, n, G, key, U);
   GCS_LAUNCH_CHECK(ctx);
   GCS_CHECK_CUDA(ctx, gcs_smem_attr_once((const void*)surfel_rank_chunk_kernel, 160 * 1024));
-  surfel_rank_chunk_kernel<<<n_chunks, 1024, (size_t)n_keys * sizeof(int), st>>>(key, n, per_chunk, n_keys, lrank, hist);
+  surfel_rank_chunk_kernel<<<dim3(n_chunks, Hu), 1024, (size_t)n_keys * sizeof(int), st>>>(key, n, per_chunk, n_keys, lrank, hist);
   GCS_LAUNCH_CHECK(ctx);
-  surfel_rank_scan_kernel<<<(n_keys + 255) / 256, 256, 0, st>>>(hist, n_chunks, n_keys, total);
+  surfel_rank_scan_kernel<<<dim3((n_keys + 255) / 256, Hu), 256, 0, st>>>(hist, n_chunks, n_keys, total);
   GCS_LAUNCH_CHECK(ctx);
-  const int64_t nb = (int64_t)G.n_cells * G.max_occ;
+  const int64_t nb = (int64_t)G.n_cells * G.max_occ * n_units;
   surfel_bucket_init_kernel<<<(unsigned)cdiv(nb, 256), 256, 0, st>>>(bucket, nb);
   GCS_LAUNCH_CHECK(ctx);
-  surfel_bucket_fill_kernel<<<(unsigned)cdiv(n, kSurfThreads), kSurfThreads, 0, st>>>(key, lrank, hist, n, per_chunk, n_keys, G, bucket);
+  surfel_bucket_fill_kernel<<<dim3((unsigned)cdiv(n, kSurfThreads), Hu), kSurfThreads, 0, st>>>(key, lrank, hist, n, per_chunk, n_keys, G,
+                                                                                            bucket, n_chunks);
   GCS_LAUNCH_CHECK(ctx);
   gcs_timing_begin(ctx, st);
-  surfel_fit_kernel<<<(G.n_cells + 127) / 128, 128, 0, st>>>(pts, timestamps, weights, center, bucket, total, G, *cfg, F);
+  surfel_fit_kernel<<<dim3((G.n_cells + 127) / 128, Hu), 128, 0, st>>>(pts, timestamps, weights, center, bucket, total, G, *cfg, F, U, n_keys);
   gcs_timing_end(ctx, st);
   GCS_LAUNCH_CHECK(ctx);
-  surfel_select_kernel<<<1, 1024, 0, st>>>(F, G, *batch, cfg->eps_lift, out_n_valid, total, out_count);
+  surfel_select_kernel<<<Hu, 1024, 0, st>>>(F, G, *batch, cfg->eps_lift, out_n_valid, total, out_count, n_keys);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
+}
+
+int gcs_extract_lidar_surfels(gcs_ctx* ctx, void* stream, const double* pts, const double* timestamps,
+                              const double* weights, int64_t n, const gcs_surfel_cfg* cfg, const gcs_meas_batch* batch,
+                              int32_t* out_n_valid, int32_t* out_bucket, int32_t* out_count) {
+  if (!ctx) return GCS_EINVAL;
+  GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  const UnitStrides U = {0, 0, 0};
+  return surfels_launch(ctx, (cudaStream_t)stream, pts, timestamps, weights, n, 1, U, cfg, batch, out_n_valid, out_bucket,
+                        out_count, "extract_lidar_surfels");
+}
+
+int gcs_extract_lidar_surfels_batched(gcs_ctx* ctx, void* stream, const double* pts, const double* timestamps,
+                                      const double* weights, int64_t n, int32_t n_units, int32_t timestamps_shared,
+                                      const gcs_surfel_cfg* cfg, const gcs_meas_batch* batch, int32_t* out_n_valid) {
+  if (!ctx) return GCS_EINVAL;
+  GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  GCS_REQUIRE(ctx, n_units >= 1 && n_units <= 65535, "extract_lidar_surfels_batched: n_units=%d", n_units);
+  const UnitStrides U = {3 * n, n, timestamps_shared ? 0 : n};
+  return surfels_launch(ctx, (cudaStream_t)stream, pts, timestamps, weights, n, n_units, U, cfg, batch, out_n_valid, nullptr,
+                        nullptr, "extract_lidar_surfels_batched");
 }
 
 }  // extern "C"

@@ -394,11 +394,16 @@ def _deskew_constant_twist_gen(points, timestamps, weights, scan_start_time, sca
         float(scan_end_time), L.ptr(o_pts), L.ptr(o_w), L.ptr(cert_d)))
     result = DeskewConstantTwistResult(points=o_pts, timestamps=t, weights=o_w, ess_imu=float(ess_imu))
     c = yield io, cert_d, result
+    return (result,) + _deskew_cert(c, ess_imu, chart_id, anchor_id, io.compute())
+
+
+def _deskew_cert(c, ess_imu, chart_id, anchor_id, compute):
+    """Certificate + effect of deskew_constant_twist from its two mass sums (deskew_constant_twist.py:98-117)."""
     retained = float(c[L.DK_SUM_W_OUT] / (c[L.DK_SUM_W_IN] + constants.GC_EPS_MASS))
     cert = CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id,
                                    support=SupportCert(ess_total=float(ess_imu), support_frac=retained),
-                                   influence=InfluenceCert.identity(), compute=io.compute())
-    return result, cert, ExpectedEffect("deskew_variance_reduction_proxy", 0.0, None)
+                                   influence=InfluenceCert.identity(), compute=compute)
+    return cert, ExpectedEffect("deskew_variance_reduction_proxy", 0.0, None)
 
 
 def ray_directions(points, origin, eps: float = constants.GC_EPS_MASS) -> torch.Tensor:

@@ -302,15 +302,19 @@ def _extract_lidar_surfels_gen(points, timestamps, weights, config, base_batch, 
     batch.n_lidar_valid = -1                      # not known on the host yet
     n_use = int((yield io, nv_d, batch)[0])
     batch.n_lidar_valid = n_use
+    cert, effect = _surfel_cert(n_use, config, chart_id, anchor_id, io.compute())
+    if return_bucket:
+        batch._bucket, batch._bucket_count = bucket, count
+    return batch, cert, effect
+
+
+def _surfel_cert(n_use, config, chart_id, anchor_id, compute):
     support_frac = float(n_use) / float(max(config.n_surfel, 1))
     cert = CertBundle.create_approx(chart_id=chart_id, anchor_id=anchor_id,
                                     triggers=["ma_hex3d_binning", "plane_fit_batched", "wishart_regularization"],
                                     support=SupportCert(ess_total=float(n_use), support_frac=support_frac),
-                                    influence=InfluenceCert.identity(), compute=io.compute())
-    effect = ExpectedEffect("surfel_extraction", float(n_use), float(n_use))
-    if return_bucket:
-        batch._bucket, batch._bucket_count = bucket, count
-    return batch, cert, effect
+                                    influence=InfluenceCert.identity(), compute=compute)
+    return cert, ExpectedEffect("surfel_extraction", float(n_use), float(n_use))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -438,11 +442,15 @@ def _recency_inflate_gen(atlas_map, tile_ids, scan_seq, recency_decay_lambda=con
     io.ctx.check(io.ctx.lib.gcs_map_recency_inflate(io.ctx.handle, io.stream(), C.byref(ca), _i32arr(idx), len(idx),
                                                     int(scan_seq), float(recency_decay_lambda), float(min_scale), L.ptr(stats_d)))
     s = yield io, stats_d, atlas_map
+    return (atlas_map,) + _inflate_finish(s, chart_id, anchor_id, io.compute())
+
+
+def _inflate_finish(s, chart_id, anchor_id, compute):
     stats = PrimitiveMapRecencyInflateStats(staleness_inflation_strength=float(s[0] / max(s[2], 1.0)),
                                             staleness_cov_inflation_trace=float(s[1]),
                                             stale_precision_downscale_total=float(s[0]))
-    cert = CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id, compute=io.compute())
-    return atlas_map, cert, ExpectedEffect("primitive_map_recency_inflate", float(s[2]), float(s[2])), stats
+    cert = CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id, compute=compute)
+    return cert, ExpectedEffect("primitive_map_recency_inflate", float(s[2]), float(s[2])), stats
 
 
 @dataclass
@@ -476,6 +484,16 @@ class AtlasMapView:
         return v
 
 
+def _empty_view(io, tile_ids, m_tile_view) -> AtlasMapView:
+    P = len(tile_ids) * int(m_tile_view)
+    return AtlasMapView(candidate_tile_ids=io.empty(P, dtype=torch.int64), candidate_slots=io.empty(P, dtype=torch.int32),
+                        valid_mask=io.empty(P, dtype=torch.uint8), tile_ids=[int(t) for t in tile_ids], m_tile_view=int(m_tile_view),
+                        positions=io.empty(P, 3), covariances=io.empty(P, 3, 3), directions=io.empty(P, 3), kappas=io.empty(P),
+                        weights=io.empty(P), primitive_ids=io.empty(P, dtype=torch.int64),
+                        last_supported_scan_seq=io.empty(P, dtype=torch.int64), etas=io.empty(P, constants.GC_VMF_N_LOBES, 3),
+                        colors=io.empty(P, 3))
+
+
 def extract_atlas_map_view(atlas_map: AtlasMap, tile_ids: List[int], m_tile_view: int, eps_lift: float = constants.GC_EPS_LIFT,
                            eps_mass: float = constants.GC_EPS_MASS) -> AtlasMapView:
     return _drive(_extract_atlas_map_view_gen(atlas_map, tile_ids, m_tile_view, eps_lift, eps_mass))
@@ -485,13 +503,7 @@ def _extract_atlas_map_view_gen(atlas_map, tile_ids, m_tile_view, eps_lift=const
     if m_tile_view <= 0:
         raise ValueError(f"extract_atlas_map_view: m_tile_view must be > 0, got {m_tile_view}")
     io = _IO(atlas_map.device)
-    P = len(tile_ids) * int(m_tile_view)
-    view = AtlasMapView(candidate_tile_ids=io.empty(P, dtype=torch.int64), candidate_slots=io.empty(P, dtype=torch.int32),
-                        valid_mask=io.empty(P, dtype=torch.uint8), tile_ids=[int(t) for t in tile_ids], m_tile_view=int(m_tile_view),
-                        positions=io.empty(P, 3), covariances=io.empty(P, 3, 3), directions=io.empty(P, 3), kappas=io.empty(P),
-                        weights=io.empty(P), primitive_ids=io.empty(P, dtype=torch.int64),
-                        last_supported_scan_seq=io.empty(P, dtype=torch.int64), etas=io.empty(P, constants.GC_VMF_N_LOBES, 3),
-                        colors=io.empty(P, 3))
+    view = _empty_view(io, tile_ids, m_tile_view)
     nv = io.zeros(1, dtype=torch.int32)
     ca, cv = atlas_map._c(), view._c()
     idx = atlas_map.index_list(tile_ids, create=False)
@@ -575,6 +587,24 @@ def _associate_primitives_ot_gen(measurement_batch, map_view, config=None, eps_l
                                  eps_mass=constants.GC_EPS_MASS, chart_id=constants.GC_CHART_ID, anchor_id="primitive_ot"):
     if config is None:
         config = AssociationConfig()
+    _check_assoc_config(config)
+    io = _IO(measurement_batch.Lambdas.device)
+    N, K = measurement_batch.n_total, int(config.k_assoc)
+    if measurement_batch.n_valid == 0 or map_view.n_valid == 0:
+        cert = CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id)
+        return _empty_assoc(io, N, K), cert, ExpectedEffect("primitive_association_ot", 0.0, 0.0)
+    res = _empty_assoc(io, N, K, zero=False)
+    cfg = _c_assoc_cfg(config, eps_lift)
+    cert_d = io.empty(OT["NCERT"])     # the kernel writes all NCERT entries
+    cb, cv, cr = measurement_batch._c(), map_view._c(), res._c()
+    io.ctx.check(io.ctx.lib.gcs_associate_primitives_ot(io.ctx.handle, io.stream(), C.byref(cb), C.byref(cv),
+                                                        _i64arr(map_view.tile_ids), len(map_view.tile_ids),
+                                                        int(map_view.m_tile_view), C.byref(cfg), C.byref(cr), L.ptr(cert_d)))
+    c = yield io, cert_d, res
+    return (res,) + _assoc_cert(c, N, K, config, chart_id, anchor_id, io)
+
+
+def _check_assoc_config(config):
     if config.a_policy != MeasurementMassPolicy.UNIFORM:
         if config.a_policy == MeasurementMassPolicy.WEIGHT_PROPORTIONAL:
             raise ValueError("MeasurementMassPolicy.WEIGHT_PROPORTIONAL is not built in this release (pipeline uses UNIFORM)")
@@ -583,21 +613,16 @@ def _associate_primitives_ot_gen(measurement_batch, map_view, config=None, eps_l
         raise ValueError(f"Unsupported map mass policy: {config.b_policy}. Only UNIFORM is implemented.")
     if not config.cost_subtract_row_min or config.cost_scale_by_median:
         raise ValueError("associate_primitives_ot: only cost_subtract_row_min=True, cost_scale_by_median=False is built")
-    io = _IO(measurement_batch.Lambdas.device)
-    N, K = measurement_batch.n_total, int(config.k_assoc)
-    if measurement_batch.n_valid == 0 or map_view.n_valid == 0:
-        cert = CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id)
-        return _empty_assoc(io, N, K), cert, ExpectedEffect("primitive_association_ot", 0.0, 0.0)
-    res = _empty_assoc(io, N, K, zero=False)
-    cfg = CAssocCfg(K, int(config.k_sinkhorn), int(config.r_stencil_tiles_xy), int(config.r_stencil_tiles_z), float(config.beta),
-                    float(config.epsilon), float(config.tau_a), float(config.tau_b), float(config.eps_mass), float(eps_lift),
-                    float(config.h_tile), float(config.recency_decay_lambda), int(config.scan_seq))
-    cert_d = io.empty(OT["NCERT"])     # the kernel writes all NCERT entries
-    cb, cv, cr = measurement_batch._c(), map_view._c(), res._c()
-    io.ctx.check(io.ctx.lib.gcs_associate_primitives_ot(io.ctx.handle, io.stream(), C.byref(cb), C.byref(cv),
-                                                        _i64arr(map_view.tile_ids), len(map_view.tile_ids),
-                                                        int(map_view.m_tile_view), C.byref(cfg), C.byref(cr), L.ptr(cert_d)))
-    c = yield io, cert_d, res
+
+
+def _c_assoc_cfg(config, eps_lift) -> CAssocCfg:
+    return CAssocCfg(int(config.k_assoc), int(config.k_sinkhorn), int(config.r_stencil_tiles_xy), int(config.r_stencil_tiles_z),
+                     float(config.beta), float(config.epsilon), float(config.tau_a), float(config.tau_b), float(config.eps_mass),
+                     float(eps_lift), float(config.h_tile), float(config.recency_decay_lambda), int(config.scan_seq))
+
+
+def _assoc_cert(c, N, K, config, chart_id, anchor_id, io):
+    """OTCert bundle + effect from the association kernel's certificate sums (primitive_association.py:480-553)."""
     tm = float(c[OT["MASS_TOTAL"]])
     n_nonzero_a = int(c[OT["NONZERO_A"]])
     compute = io.compute(alloc_bytes_est=int(N * K * 8 * 4), largest_tensor_shape=(int(N), int(K)), segment_sum_k=int(K),
@@ -617,7 +642,7 @@ def _associate_primitives_ot_gen(measurement_batch, map_view, config=None, eps_l
                      b_policy=str(config.b_policy.value), b_recency_decay_lambda=float(config.recency_decay_lambda),
                      b_recency_p95=float(c[OT["B_RECENCY_P95"]]))
     total_cost = float(c[OT["TOTAL_COST"]])
-    return res, cert, ExpectedEffect("primitive_association_ot", total_cost, total_cost)
+    return cert, ExpectedEffect("primitive_association_ot", total_cost, total_cost)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -652,10 +677,7 @@ def _visual_pose_evidence_gen(association_result, measurement_batch, map_view, b
     N_meas = measurement_batch.n_valid
     N_assoc, K = association_result.responsibilities.shape
     if N_meas == 0 or N_assoc == 0 or map_view.n_valid == 0:
-        res = VisualPoseEvidenceResult(L_pose=eps_lift * torch.eye(22, dtype=F64, device=io.dev), h_pose=io.zeros(22),
-                                       L_trans=io.zeros(3, 3), h_trans=io.zeros(3), L_rot=io.zeros(3, 3), h_rot=io.zeros(3),
-                                       total_weighted_cost=0.0, n_associations=0, mean_transported_mass=0.0)
-        return res, CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id), ExpectedEffect("visual_pose_evidence", 0.0, 0.0)
+        return _empty_pose_evidence(io, eps_lift, chart_id, anchor_id)
     if z_lin_pose is not None:
         pose = _host_vec(z_lin_pose.detach().cpu().numpy().ravel()[:6] if isinstance(z_lin_pose, torch.Tensor)
                          else np.asarray(z_lin_pose, np.float64).ravel()[:6], 6)
@@ -668,6 +690,17 @@ def _visual_pose_evidence_gen(association_result, measurement_batch, map_view, b
     io.ctx.check(io.ctx.lib.gcs_visual_pose_evidence(io.ctx.handle, io.stream(), C.byref(cb), C.byref(cv), C.byref(cr), int(K),
                                                      _dptr(pose), float(eps_lift), float(eps_mass), L.ptr(L22), L.ptr(h22), L.ptr(rec_d)))
     r = yield io, rec_d, None
+    return _pose_evidence_finish(r, L22, h22, rec_d, N_meas, K, eps_lift, chart_id, anchor_id, io.compute())
+
+
+def _empty_pose_evidence(io, eps_lift, chart_id, anchor_id):
+    res = VisualPoseEvidenceResult(L_pose=eps_lift * torch.eye(22, dtype=F64, device=io.dev), h_pose=io.zeros(22),
+                                   L_trans=io.zeros(3, 3), h_trans=io.zeros(3), L_rot=io.zeros(3, 3), h_rot=io.zeros(3),
+                                   total_weighted_cost=0.0, n_associations=0, mean_transported_mass=0.0)
+    return res, CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id), ExpectedEffect("visual_pose_evidence", 0.0, 0.0)
+
+
+def _pose_evidence_finish(r, L22, h22, rec_d, N_meas, K, eps_lift, chart_id, anchor_id, compute):
     n_rows = int(r[VP["N_VALID_ROWS"]])
     total_cost = float(r[VP["TRANS_COST"]] + r[VP["ROT_COST"]])
     res = VisualPoseEvidenceResult(L_pose=L22, h_pose=h22, L_trans=rec_d[0:9].reshape(3, 3), h_trans=rec_d[9:12],
@@ -677,7 +710,7 @@ def _visual_pose_evidence_gen(association_result, measurement_batch, map_view, b
     cert = CertBundle.create_approx(
         chart_id=chart_id, anchor_id=anchor_id, triggers=["linearization", "ot_soft_correspondence"], frobenius_applied=True,
         support=SupportCert(ess_total=float(r[VP["SUM_ROW_MASS"]]), support_frac=float(n_rows) / float(max(N_meas, 1))),
-        influence=InfluenceCert.identity().with_overrides(lift_strength=eps_lift), compute=io.compute())
+        influence=InfluenceCert.identity().with_overrides(lift_strength=eps_lift), compute=compute)
     return res, cert, ExpectedEffect("visual_pose_evidence", total_cost, total_cost)
 
 

@@ -133,6 +133,14 @@ int gcs_deskew_constant_twist(gcs_ctx* ctx, void* stream, const double* pts /*de
                               double scan_end_time, double* out_pts /*dev (n,3)*/, double* out_w /*dev (n)*/,
                               double* cert /*dev [GCS_DK_NCERT]*/);
 
+/* Hypothesis-batched form (the per-hypothesis loop of fl/backend/backend_node.py:2036-2066 around pipeline.py:569-587):
+ * n_units twists over the SAME raw points.  xi_body: dev (n_units, 6) -- the layout gcs_imu_scan_twist writes; outputs
+ * stacked per unit: out_pts (n_units, n, 3), out_w (n_units, n), cert (n_units, GCS_DK_NCERT).                      */
+int gcs_deskew_constant_twist_batched(gcs_ctx* ctx, void* stream, const double* pts /*dev (n,3)*/, const double* t,
+                                      const double* w, int64_t n, const double* xi_body /*dev (n_units,6)*/,
+                                      int32_t n_units, double scan_start_time, double scan_end_time, double* out_pts,
+                                      double* out_w, double* cert);
+
 /* ---- a3 ray directions : fl/backend/pipeline.py:589-593 ----------------------------------------------- */
 int gcs_ray_directions(gcs_ctx* ctx, void* stream, const double* pts /*dev (n,3)*/, int64_t n,
                        const double* origin /*host [3]*/, double eps, double* out_dirs /*dev (n,3)*/);
@@ -344,6 +352,14 @@ int gcs_extract_lidar_surfels(gcs_ctx* ctx, void* stream, const double* pts /*de
                               const gcs_surfel_cfg* cfg /*host*/, const gcs_meas_batch* batch /*host struct*/,
                               int32_t* out_n_valid, int32_t* out_bucket, int32_t* out_count);
 
+/* Hypothesis-batched form: unit u reads pts + u*3n, weights + u*n (timestamps shared when timestamps_shared != 0) and
+ * writes unit u of a STACKED measurement batch -- `batch` holds the pointers of unit 0, unit u lies u * (n_feat +
+ * n_surfel) rows further in every array.  out_n_valid: dev int32[n_units].                                        */
+int gcs_extract_lidar_surfels_batched(gcs_ctx* ctx, void* stream, const double* pts /*dev (n_units,n,3)*/,
+                                      const double* timestamps, const double* weights /*dev (n_units,n)*/, int64_t n,
+                                      int32_t n_units, int32_t timestamps_shared, const gcs_surfel_cfg* cfg,
+                                      const gcs_meas_batch* batch, int32_t* out_n_valid);
+
 /* ---- a11 tiles: PrimitiveMapTile / AtlasMap (fl/backend/structures/primitive_map.py:98-211) ----------------
  * The atlas is a pool of n_tiles_cap tiles of m_tile slots each, one SoA array per field, all (dev).           */
 typedef struct {
@@ -396,6 +412,17 @@ typedef struct {
 int gcs_extract_atlas_map_view(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int32_t* tile_index /*host*/,
                                const int64_t* tile_ids /*host*/, int32_t n_tiles, int32_t m_tile_view,
                                double eps_lift, double eps_mass, const gcs_map_view* view, int32_t* out_n_valid);
+
+/* extract_atlas_map_view(primitive_map_recency_inflate(map)) without touching the map: the hypotheses after the first
+ * see an inflated COPY of the map in the reference (pipeline.py:835-853; only hypothesis 0's map is kept,
+ * backend_node.py:2079-2083).  The gathered Lambda / theta of every valid view entry are scaled by
+ * clip(exp(-lambda * max(scan_seq - last_supported_scan_seq, 0)), min_scale, 1) as primitive_map.py:1400-1484 scales
+ * them; selection and all other fields do not depend on the inflation.  out_inflate_stats (dev double[4], may be NULL):
+ * the statistics gcs_map_recency_inflate reports.                                                                  */
+int gcs_extract_atlas_map_view_inflated(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int32_t* tile_index,
+                                        const int64_t* tile_ids, int32_t n_tiles, int32_t m_tile_view, double eps_lift,
+                                        double eps_mass, int64_t scan_seq, double recency_decay_lambda, double min_scale,
+                                        const gcs_map_view* view, int32_t* out_n_valid, double* out_inflate_stats);
 
 /* ---- (8f-4, merge half) primitive_map_merge_reduce : fl/backend/structures/primitive_map.py:1501-2031 ----------
  * All-pairs Bhattacharyya distance of the tile's Gaussians (mu = solve(Lambda + eps_lift I, theta), Sigma = inv(.)),
@@ -454,6 +481,14 @@ int gcs_associate_primitives_ot(gcs_ctx* ctx, void* stream, const gcs_meas_batch
                                 const int64_t* view_tile_ids /*host*/, int32_t n_tiles, int32_t m_tile_view,
                                 const gcs_assoc_cfg* cfg, const gcs_assoc_result* out, double* cert);
 
+/* Hypothesis-batched form: n_units stacked measurement batches (see gcs_extract_lidar_surfels_batched) against ONE
+ * read-only view; `out` holds the pointers of unit 0 of stacked (n_units, Nt, K) results, cert is (n_units, GCS_OT_NCERT).
+ * One thread-block cluster runs the Sinkhorn iterations of each unit.                                              */
+int gcs_associate_primitives_ot_batched(gcs_ctx* ctx, void* stream, const gcs_meas_batch* batch, int32_t n_units,
+                                        const gcs_map_view* view, const int64_t* view_tile_ids /*host*/, int32_t n_tiles,
+                                        int32_t m_tile_view, const gcs_assoc_cfg* cfg, const gcs_assoc_result* out,
+                                        double* cert);
+
 /* ---- a13 visual_pose_evidence : fl/backend/operators/visual_pose_evidence.py:74-436 ------------------------ */
 enum { GCS_VP_L_TRANS = 0 /*9*/, GCS_VP_H_TRANS = 9 /*3*/, GCS_VP_L_ROT = 12 /*9*/, GCS_VP_H_ROT = 21 /*3*/,
        GCS_VP_TRANS_COST = 24, GCS_VP_ROT_COST, GCS_VP_SUM_ROW_MASS, GCS_VP_N_VALID_ROWS, GCS_VP_SVD_S /*3*/ = 28,
@@ -462,6 +497,12 @@ int gcs_visual_pose_evidence(gcs_ctx* ctx, void* stream, const gcs_meas_batch* b
                              const gcs_assoc_result* assoc, int32_t k_assoc, const double* pose6 /*host [t,rotvec]*/,
                              double eps_lift, double eps_mass, double* out_L22 /*dev (22,22)*/,
                              double* out_h22 /*dev (22)*/, double* out_rec /*dev [GCS_VP_NREC]*/);
+
+/* Hypothesis-batched form: poses dev (n_units, 6); outputs stacked (n_units, 22, 22), (n_units, 22), (n_units, NREC). */
+int gcs_visual_pose_evidence_batched(gcs_ctx* ctx, void* stream, const gcs_meas_batch* batch, int32_t n_units,
+                                     const gcs_map_view* view, const gcs_assoc_result* assoc, int32_t k_assoc,
+                                     const double* poses /*dev (n_units,6) [t,rotvec]*/, double eps_lift, double eps_mass,
+                                     double* out_L22, double* out_h22, double* out_rec);
 
 /* ---- a14 map update = pipeline step 12b : fl/backend/pipeline.py:1233-1447 with primitive_map_fuse /
  *      insert_masked / cull / forget (fl/backend/structures/primitive_map.py:807-1384).  This is what survives of

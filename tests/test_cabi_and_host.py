@@ -21,7 +21,7 @@ def _declared_symbols():
 def test_library_exports_every_declared_symbol():
     import __graft_entry__ as ge
     ge.build()
-    from gc_slam_b200 import _lib, fusion, primitives  # noqa: F401  (these modules register their prototypes)
+    from gc_slam_b200 import _lib, fusion, hypothesis_batch, primitives  # noqa: F401  (these modules register their prototypes)
     lib = _lib.load()
     syms = _declared_symbols()
     assert len(syms) >= 30
