@@ -10,6 +10,7 @@
 
 #include "gcs_assoc.cuh"
 #include "gcs_select.cuh"
+#include "gcs_tma.cuh"
 
 namespace gcs {
 
@@ -103,13 +104,16 @@ __global__ void __launch_bounds__(256) recency_inflate_kernel(gcs_atlas A, TileL
     part[((int64_t)a * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = s;
   }
 }
+// one warp: lane l adds parts l, l+32, ... of every column, then a fixed shuffle tree (deterministic)
 __global__ void sum_parts_kernel(const double* __restrict__ part, int n_parts, int width, double* __restrict__ out, int out_len) {
-  const int k = threadIdx.x;
-  if (k >= out_len) return;
-  double a = 0.0;
-  if (k < width)
-    for (int c = 0; c < n_parts; ++c) a += part[(int64_t)c * width + k];
-  out[k] = a;
+  const int lane = threadIdx.x & 31;
+  for (int k = 0; k < out_len; ++k) {
+    double a = 0.0;
+    if (k < width)
+      for (int c = lane; c < n_parts; c += 32) a += part[(int64_t)c * width + k];
+    a = warp_sum(a);
+    if (lane == 0) out[k] = a;
+  }
 }
 
 // =================================================================================================
@@ -254,170 +258,258 @@ __global__ void __launch_bounds__(128) assoc_prepare_kernel(gcs_meas_batch B, in
   }
 }
 
-// one warp per measurement row: stream the candidate pool, keep the K best (cost, pool position) per lane, merge.
-// First K of the row-wise stable sort by cost over the 7 x 1024 candidate pool (primitive_association.py:367-376), one warp
-// per measurement, kTopkRows measurements per CTA.
+// First K of the row-wise stable sort by cost over the 7 x 1024 candidate pool (primitive_association.py:367-376).
+//
+// PERSISTENT kernel, one CTA per SM, kTopkWarps warps.  The positions of ALL view tiles (7 x 24 KB at the reference
+// budget) are staged in shared memory ONCE per CTA by the Tensor Memory Accelerator -- one cp.async.bulk.tensor box per
+// tile, each completing on its own mbarrier, so a warp starts scanning a tile as soon as that tile has landed -- and
+// every warp then pulls (unit, row) work items from a global counter until none is left: staging traffic no longer
+// grows with the number of rows or hypotheses (it was 175 KB per 4 rows), no CTA-wide barrier sits between tiles, and a
+// dense row delays only its own warp.  Views the TMA box cannot describe (m_view not a multiple of 256, unaligned
+// base, more tiles than shared memory holds) are read through the same pointers straight from global memory / L1.
+//
+// Per row (one warp):
 //   cost = |dp|^2 + beta * d_dir with d_dir in [0, 1], so |dp|^2 is a lower bound that costs five flops.  T is an upper
 //   bound of the row's K-th best (cost, j) (the K-th smallest of the lanes' current best entries: K distinct candidates
 //   at or before it); a candidate whose (bound, j) lies beyond (T, Tj) cannot be among the first K and is skipped --
 //   its three log / sinh / exp evaluations, or, for the many rows whose stencil misses the view (every cost 1e12, the
-//   first K offsets win), everything after the first few candidates.  The view tiles are staged in shared memory one at a time (positions and
-//   validity: 25 KB), every warp scans the staged tile if it is in its stencil, survivors are queued and evaluated 32
-//   at a time (all lanes busy), which leaves a few hundred of the 7,168 exact costs per row.  Ties keep the smaller
-//   j = stencil position * m_view + offset whatever the processing order, so the selection is the reference's.
-constexpr int kTopkRows = 4;   // measurement rows (warps) per CTA: 2 / 4 / 8 rows give 150 / 145 / 153 us -- the kernel lasts as long as its densest row
+//   first K offsets win), everything after the first few candidates.  Survivors are queued and evaluated 32 at a time
+//   (all lanes busy), which leaves a few hundred of the 7,168 exact costs per row.  The row starts with the tile at the
+//   centre of its own stencil: its candidates tighten T at once and the outer tiles are then pruned almost entirely.
+//   Ties keep the smaller j = stencil position * m_view + offset whatever the processing order, so the selection is the
+//   reference's whichever warp takes the row.
+constexpr int kTopkWarps = 16;
+constexpr int kTopkMaxTiles = 16;
+
+// Lane holding the smallest (cost, j) among the `alive` lanes of the warp -- costs are non-negative float64, whose bit
+// patterns order like the numbers -- with three 32-bit REDUX.MIN steps (high word, low word, j) instead of a five-level
+// shuffle butterfly over three registers.  *key / *j receive the winning pair in every lane.
+__device__ __forceinline__ int warp_argmin_cost_j(long long cost_bits, int j, bool alive, int lane, unsigned long long* key,
+                                                  int* jmin) {
+  const unsigned hi = alive ? (unsigned)((unsigned long long)cost_bits >> 32) : 0xffffffffu;
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const bool c1 = alive && hi == mhi;
+  const unsigned lo = c1 ? (unsigned)(unsigned long long)cost_bits : 0xffffffffu;
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, lo);
+  const bool c2 = c1 && lo == mlo;
+  const unsigned jj = c2 ? (unsigned)j : 0xffffffffu;
+  const unsigned mj = __reduce_min_sync(0xffffffffu, jj);
+  const unsigned win = __ballot_sync(0xffffffffu, c2 && jj == mj);
+  *key = ((unsigned long long)mhi << 32) | mlo;
+  *jmin = (int)mj;
+  (void)lane;
+  return __ffs(win) - 1;
+}
+struct TopkShared {               // behind the staged tiles in dynamic shared memory
+  unsigned long long bar[kTopkMaxTiles];
+  int queue[kTopkWarps][64];
+};
+inline size_t topk_smem_bytes(int n_tiles, int m_view, bool staged) {
+  return (staged ? (size_t)n_tiles * m_view * 25 : 0) + 128 + sizeof(TopkShared);
+}
+
 template <int K>
-__global__ void __launch_bounds__(32 * kTopkRows) assoc_topk_kernel(gcs_meas_batch B, int N, gcs_map_view V, int m_view, int n_st,
-                                                         int n_view_tiles, AssocWs W, gcs_assoc_cfg cfg, gcs_assoc_result R) {
-  extern __shared__ double tile_pos[];                       // (m_view, 3), then m_view validity bytes
-  uint8_t* tile_valid = reinterpret_cast<uint8_t*>(tile_pos + 3 * (size_t)m_view);
-  __shared__ int s_queue[kTopkRows][64];
-  B = meas_batch_unit(B, blockIdx.y);          // blockIdx.y = unit
-  W = assoc_ws_unit(W, blockIdx.y, N, n_st);
-  R = assoc_result_unit(R, blockIdx.y, N, K);
+__global__ void __launch_bounds__(32 * kTopkWarps, 1) assoc_topk_kernel(gcs_meas_batch B0, int N, int n_units, gcs_map_view V,
+                                                                        int m_view, int n_st, int n_view_tiles, AssocWs W0,
+                                                                        gcs_assoc_cfg cfg, gcs_assoc_result R0,
+                                                                        int* __restrict__ row_counter,
+                                                                        const __grid_constant__ CUtensorMap tmap, int staged) {
+  extern __shared__ __align__(128) unsigned char topk_smem[];
+  const size_t pos_bytes = staged ? (size_t)n_view_tiles * m_view * 24 : 0;
+  const size_t val_bytes = staged ? (((size_t)n_view_tiles * m_view + 127) & ~(size_t)127) : 0;
+  double* s_pos = reinterpret_cast<double*>(topk_smem);
+  uint8_t* s_val = topk_smem + pos_bytes;
+  TopkShared& S = *reinterpret_cast<TopkShared*>(topk_smem + pos_bytes + val_bytes);
   const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * kTopkRows + wq;
-  const bool active = i < N;
-  const int ii = active ? i : 0;
-  const double mp[3] = {W.mpos[3 * ii], W.mpos[3 * ii + 1], W.mpos[3 * ii + 2]};
-  const double md[3] = {W.mdir[3 * ii], W.mdir[3 * ii + 1], W.mdir[3 * ii + 2]};
-  const double mk = W.mkap[ii];
-  const double A_k1 = A_vmf(fmax(mk, 1e-12), 1e-12);
-  double bc[K];
-  int bj[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) { bc[k] = 1.0e300; bj[k] = 0x7fffffff; }
-  int* queue = s_queue[wq];
-  int qn = 0;
-  double T = 1.0e300;   // (T, Tj): K distinct candidates at or before this (cost, j) are already held
-  int Tj = 0x7fffffff;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(S.bar);
+  if (staged) {
+    if (threadIdx.x == 0) {
+      tma::prefetch_map(&tmap);
+      for (int t = 0; t < n_view_tiles; ++t) tc::mbar_init(&bars[t], 1);
+      tc::mbar_init_fence();
+      const int rows_per_tile = (3 * m_view) >> 8;     // 256 float64 per tensor row
+      for (int t = 0; t < n_view_tiles; ++t) {
+        tma::mbar_expect_tx(&bars[t], (uint32_t)(24 * m_view));
+        tma::load_2d(s_pos + (size_t)t * 3 * m_view, &tmap, 0, t * rows_per_tile, &bars[t]);
+      }
+    }
+    for (int e = threadIdx.x; e < n_view_tiles * m_view; e += 32 * kTopkWarps) s_val[e] = V.valid[e];
+    __syncthreads();   // barriers initialised, validity bytes staged
+  }
+  int* queue = S.queue[wq];
+  const long long total_rows = (long long)n_units * N;
+  unsigned tiles_seen = 0;      // tiles whose mbarrier this warp has already seen complete
   const bool prune = cfg.beta >= 0.0;
-  auto flush = [&](int n_take) {
-    if (lane < n_take) {
-      const int j = queue[lane];
-      const int s = j / m_view, off = j - s * m_view;
-      const int tix = W.stencil[ii * n_st + s];
-      const int v = (tix < 0 ? 0 : tix) * m_view + off;
-      double c = 1e12;
-      if (tix >= 0 && V.valid[v])
-        c = pair_cost_pre(mp, md, mk, A_k1, V.positions + 3 * v, V.directions + 3 * v, V.kappas[v], W.vAk[v], cfg.beta);
-      if (c < bc[K - 1] || (c == bc[K - 1] && j < bj[K - 1])) {
-        bc[K - 1] = c; bj[K - 1] = j;
+
+  for (;;) {
+    int row = 0;
+    if (lane == 0) row = atomicAdd(row_counter, 1);
+    row = __shfl_sync(0xffffffffu, row, 0);
+    if (row >= total_rows) break;
+    const int u = row / N, i = row - u * N;
+    const gcs_meas_batch B = meas_batch_unit(B0, u);
+    const AssocWs W = assoc_ws_unit(W0, u, N, n_st);
+    const gcs_assoc_result R = assoc_result_unit(R0, u, N, K);
+    const double mp[3] = {W.mpos[3 * i], W.mpos[3 * i + 1], W.mpos[3 * i + 2]};
+    const double md[3] = {W.mdir[3 * i], W.mdir[3 * i + 1], W.mdir[3 * i + 2]};
+    const double mk = W.mkap[i];
+    const double A_k1 = A_vmf(fmax(mk, 1e-12), 1e-12);
+    const int8_t* my_st = W.stencil + (size_t)i * n_st;
+    const bool mvalid = B.valid[i] != 0;
+    // A row whose stencil has no tile in the view sees the cost 1e12 for every candidate: the first K of the stable
+    // sort are offsets 0..K-1 of stencil position 0.  Most surfels of a scan lie further from the pose than the view
+    // reaches, so this is the common case.
+    bool any_tile = false;
+    for (int q = 0; q < n_st; ++q) any_tile |= my_st[q] >= 0;
+    if (!any_tile) {
+      if (lane < K) {
+        const int v = mvalid ? lane : 0;   // invalid measurement rows point at pool entry 0 (:379)
+        R.candidate_pool_indices[i * K + lane] = v;
+        R.candidate_tile_ids[i * K + lane] = V.candidate_tile_ids[v];
+        R.candidate_slots[i * K + lane] = (long long)V.candidate_slots[v];
+      }
+      continue;
+    }
+    double bc[K];
+    int bj[K];
 #pragma unroll
-        for (int k = K - 1; k > 0; --k) {
-          if (bc[k] < bc[k - 1] || (bc[k] == bc[k - 1] && bj[k] < bj[k - 1])) {
-            const double tc = bc[k]; bc[k] = bc[k - 1]; bc[k - 1] = tc;
-            const int tj = bj[k]; bj[k] = bj[k - 1]; bj[k - 1] = tj;
+    for (int k = 0; k < K; ++k) { bc[k] = 1.0e300; bj[k] = 0x7fffffff; }
+    int qn = 0;
+    double T = 1.0e300;   // (T, Tj): K distinct candidates at or before this (cost, j) are already held
+    int Tj = 0x7fffffff;
+    // One loop over [view tiles in the row's order | stencil positions without a tile | drain]: a single copy of the
+    // exact-cost code in the instruction stream (three inlined copies thrashed the instruction cache: 16 warps, each
+    // somewhere else in 80 KB of code).
+    const int c0 = my_st[n_st / 2];
+    const int t_first = (c0 >= 0 && c0 < n_view_tiles) ? c0 : 0;
+    const int n_seg = n_view_tiles + n_st;
+    for (int g = 0; g <= n_seg; ++g) {
+      const bool drain = g == n_seg;
+      bool present = false;
+      int s = 0;
+      const double* tile_pos = nullptr;
+      const uint8_t* tile_valid = nullptr;
+      if (g < n_view_tiles) {
+        const int t = g == 0 ? t_first : (g <= t_first ? g - 1 : g);
+        s = -1;
+        for (int q = 0; q < n_st; ++q)
+          if (my_st[q] == t) { s = q; break; }
+        if (s < 0) continue;
+        present = true;
+        if (staged) {
+          if (!((tiles_seen >> t) & 1u)) { tc::mbar_wait(&bars[t], 0); tiles_seen |= 1u << t; }
+          tile_pos = s_pos + (size_t)t * 3 * m_view;
+          tile_valid = s_val + (size_t)t * m_view;
+        } else {
+          tile_pos = V.positions + (size_t)t * 3 * m_view;
+          tile_valid = V.valid + (size_t)t * m_view;
+        }
+      } else if (!drain) {
+        // stencil positions whose tile is not in the view carry cost 1e12 for every offset: they only matter while
+        // fewer than K better candidates exist
+        s = g - n_view_tiles;
+        if (my_st[s] >= 0) continue;
+        if (prune && (1e12 > T || (1e12 == T && s * m_view > Tj))) continue;
+      } else if (qn == 0) {
+        break;
+      }
+      const int jbase = s * m_view;
+      const int n_off = drain ? 1 : m_view;
+      for (int base = 0; base < n_off; base += 32) {
+        const int off = base + lane, j = jbase + off;
+        bool pass = false;
+        if (present) {
+          if (off < m_view) {
+            double lb = 1e12;
+            if (tile_valid[off]) {
+              const double d0 = mp[0] - tile_pos[3 * off], d1 = mp[1] - tile_pos[3 * off + 1], d2 = mp[2] - tile_pos[3 * off + 2];
+              lb = d0 * d0 + d1 * d1 + d2 * d2;
+            }
+            pass = !prune || !(lb > T || (lb == T && j > Tj));   // lb <= cost: beyond (T, Tj) it cannot be among the first K
           }
+        } else if (!drain) {
+          if (prune && (1e12 > T || (1e12 == T && jbase + base > Tj))) break;
+          pass = off < m_view && (!prune || !(1e12 > T || (1e12 == T && j > Tj)));
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, pass);
+        if (pm != 0u) {
+          if (pass) queue[qn + __popc(pm & ((1u << lane) - 1u))] = j;
+          qn += __popc(pm);
+          __syncwarp();
+        }
+        if (qn >= 32 || (drain && qn > 0)) {
+          const int n_take = qn < 32 ? qn : 32;
+          // ---- exact costs of n_take queued candidates, one per lane; each lane keeps its K best in (cost, j) order
+          bool head_changed = false;
+          if (lane < n_take) {
+            const int jq = queue[lane];
+            const int sq = jq / m_view, offq = jq - sq * m_view;
+            const int tix = my_st[sq];
+            const int v = (tix < 0 ? 0 : tix) * m_view + offq;
+            double c = 1e12;
+            if (tix >= 0 && V.valid[v])
+              c = pair_cost_pre(mp, md, mk, A_k1, V.positions + 3 * v, V.directions + 3 * v, V.kappas[v], W.vAk[v], cfg.beta);
+            if (c < bc[K - 1] || (c == bc[K - 1] && jq < bj[K - 1])) {
+              bc[K - 1] = c; bj[K - 1] = jq;
+#pragma unroll
+              for (int k = K - 1; k > 0; --k) {
+                if (bc[k] < bc[k - 1] || (bc[k] == bc[k - 1] && bj[k] < bj[k - 1])) {
+                  const double tc_ = bc[k]; bc[k] = bc[k - 1]; bc[k - 1] = tc_;
+                  const int tj = bj[k]; bj[k] = bj[k - 1]; bj[k - 1] = tj;
+                }
+              }
+              head_changed = bj[0] == jq;
+            }
+          }
+          // (T, Tj) = K-th smallest of the 32 lane heads in (cost, j) order; it can only move when a head moved
+          if (__any_sync(0xffffffffu, head_changed)) {
+            bool alive = true;
+            unsigned long long kkey = 0ull;
+            int kj = 0;
+#pragma unroll 1
+            for (int r = 0; r < K; ++r) {
+              const int wl = warp_argmin_cost_j(__double_as_longlong(bc[0]), bj[0], alive, lane, &kkey, &kj);
+              if (lane == wl) alive = false;
+            }
+            T = __longlong_as_double((long long)kkey);
+            Tj = kj;
+          }
+          __syncwarp();
+          qn -= n_take;
+          int moved = 0;
+          if (lane < qn) moved = queue[32 + lane];   // at most 31 left over
+          __syncwarp();
+          if (lane < qn) queue[lane] = moved;
+          __syncwarp();
         }
       }
     }
-    // (T, Tj) = K-th smallest of the 32 lane heads in (cost, j) order (rank by counting; j is unique)
-    const double head = bc[0];
-    const int headj = bj[0];
-    int rank = 0;
+    // K rounds of arg-min over the lanes' heads by (cost, j); the winner pops its list
+#pragma unroll 1
+    for (int r = 0; r < K; ++r) {
+      unsigned long long hkey;
+      int hj;
+      const int hl = warp_argmin_cost_j(__double_as_longlong(bc[0]), bj[0], true, lane, &hkey, &hj);
+      if (lane == hl) {
 #pragma unroll
-    for (int o = 1; o < 32; ++o) {
-      const double oh = __shfl_sync(0xffffffffu, head, (lane + o) & 31);
-      const int oj = __shfl_sync(0xffffffffu, headj, (lane + o) & 31);
-      rank += (oh < head) || (oh == head && (oj < headj || (oj == headj && ((lane + o) & 31) < lane)));
+        for (int k = 0; k < K - 1; ++k) { bc[k] = bc[k + 1]; bj[k] = bj[k + 1]; }
+        bc[K - 1] = 1.0e300; bj[K - 1] = 0x7fffffff;
+      }
+      if (lane == 0) {
+        const int s = hj / m_view, off = hj - s * m_view;
+        const int tix = my_st[s];
+        int v = (tix < 0 ? 0 : tix) * m_view + off;
+        if (!mvalid) v = 0;  // invalid measurement rows point at pool entry 0 (:379)
+        R.candidate_pool_indices[i * K + r] = v;
+        R.candidate_tile_ids[i * K + r] = V.candidate_tile_ids[v];
+        R.candidate_slots[i * K + r] = (long long)V.candidate_slots[v];
+      }
     }
-    const unsigned kth = __ballot_sync(0xffffffffu, rank == K - 1);
-    T = __shfl_sync(0xffffffffu, head, __ffs(kth) - 1);
-    Tj = __shfl_sync(0xffffffffu, headj, __ffs(kth) - 1);
-  };
-  auto offer = [&](bool pass, int j) {
-    const unsigned pm = __ballot_sync(0xffffffffu, pass);
-    if (pm == 0u) return;
-    if (pass) queue[qn + __popc(pm & ((1u << lane) - 1u))] = j;
-    qn += __popc(pm);
     __syncwarp();
-    if (qn >= 32) {
-      flush(32);
-      __syncwarp();
-      qn -= 32;
-      int moved = 0;
-      if (lane < qn) moved = queue[32 + lane];   // at most 31 left over
-      __syncwarp();
-      if (lane < qn) queue[lane] = moved;
-      __syncwarp();
-    }
-  };
-  // start with the tile most rows of this CTA sit in (the centre of the first row's stencil): its candidates tighten T
-  // at once and the outer tiles are then pruned almost entirely
-  __shared__ int s_first;
-  if (threadIdx.x == 0) {
-    const int c = W.stencil[(size_t)(blockIdx.x * kTopkRows) * n_st + n_st / 2];
-    s_first = (c >= 0 && c < n_view_tiles) ? c : 0;
   }
-  __syncthreads();
-  const int t_first = s_first;
-  for (int tt = 0; tt < n_view_tiles; ++tt) {
-    const int t = tt == 0 ? t_first : (tt <= t_first ? tt - 1 : tt);
-    __syncthreads();   // the previous tile has been scanned by every warp
-    for (int e = threadIdx.x; e < 3 * m_view; e += 32 * kTopkRows) tile_pos[e] = V.positions[(size_t)t * m_view * 3 + e];
-    for (int e = threadIdx.x; e < m_view; e += 32 * kTopkRows) tile_valid[e] = V.valid[(size_t)t * m_view + e];
-    __syncthreads();
-    if (!active) continue;
-    int s = -1;
-    for (int q = 0; q < n_st; ++q)
-      if (W.stencil[i * n_st + q] == t) { s = q; break; }
-    if (s < 0) continue;
-    for (int base = 0; base < m_view; base += 32) {
-      const int off = base + lane;
-      bool pass = false;
-      if (off < m_view) {
-        double lb = 1e12;
-        if (tile_valid[off]) {
-          const double d0 = mp[0] - tile_pos[3 * off], d1 = mp[1] - tile_pos[3 * off + 1], d2 = mp[2] - tile_pos[3 * off + 2];
-          lb = d0 * d0 + d1 * d1 + d2 * d2;
-        }
-        const int j = s * m_view + off;
-        pass = !prune || !(lb > T || (lb == T && j > Tj));   // lb <= cost: beyond (T, Tj) it cannot be among the first K
-      }
-      offer(pass, s * m_view + off);
-    }
-  }
-  if (!active) return;
-  // stencil positions whose tile is not in the view carry cost 1e12 for every offset: they only matter while fewer than
-  // K better candidates exist
-  for (int s = 0; s < n_st; ++s) {
-    if (W.stencil[i * n_st + s] >= 0) continue;
-    if (prune && (1e12 > T || (1e12 == T && s * m_view > Tj))) continue;
-    for (int base = 0; base < m_view; base += 32) {
-      const int off = base + lane, j = s * m_view + off;
-      if (prune && (1e12 > T || (1e12 == T && s * m_view + base > Tj))) break;
-      offer(off < m_view && (!prune || !(1e12 > T || (1e12 == T && j > Tj))), j);
-    }
-  }
-  if (qn > 0) { __syncwarp(); flush(qn); }
-  // K-round tournament over the lanes' heads by (cost, j)
-  const bool mvalid = B.valid[i] != 0;
-  for (int r = 0; r < K; ++r) {
-    double hc = bc[0];
-    int hj = bj[0], hl = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double oc = __shfl_xor_sync(0xffffffffu, hc, o);
-      const int oj = __shfl_xor_sync(0xffffffffu, hj, o);
-      const int ol = __shfl_xor_sync(0xffffffffu, hl, o);
-      if (oc < hc || (oc == hc && oj < hj)) { hc = oc; hj = oj; hl = ol; }
-    }
-    if (lane == hl) {
-#pragma unroll
-      for (int k = 0; k < K - 1; ++k) { bc[k] = bc[k + 1]; bj[k] = bj[k + 1]; }
-      bc[K - 1] = 1.0e300; bj[K - 1] = 0x7fffffff;
-    }
-    if (lane == 0) {
-      const int s = hj / m_view, off = hj - s * m_view;
-      const int tix = W.stencil[i * n_st + s];
-      int v = (tix < 0 ? 0 : tix) * m_view + off;
-      if (!mvalid) v = 0;  // invalid measurement rows point at pool entry 0 (:379)
-      R.candidate_pool_indices[i * K + r] = v;
-      R.candidate_tile_ids[i * K + r] = V.candidate_tile_ids[v];
-      R.candidate_slots[i * K + r] = (long long)V.candidate_slots[v];
-    }
-  }
+  // a CTA must not retire while the TMA may still write into its shared memory
+  if (staged && wq == 0)
+    for (int t = 0; t < n_view_tiles; ++t) tc::mbar_wait(&bars[t], 0);
 }
 
 // single CTA: cost of the selected candidates, recency term, row-min shift, unbalanced Sinkhorn, certificates
@@ -1284,7 +1376,7 @@ static int assoc_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_meas_batch* bat
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_pos = take(H * N * 3 * 8), o_dir = take(H * N * 3 * 8), o_kap = take(H * N * 8),
                o_st = take(H * N * n_st), o_brow = take(H * N * 8 * 8),
-               o_vak = take((size_t)n_tiles * m_tile_view * 8);
+               o_vak = take((size_t)n_tiles * m_tile_view * 8), o_ctr = take(256);
   rc = gcs_ws_reserve(ctx, off);
   if (rc) return rc;
   char* ws = (char*)ctx->ws;
@@ -1296,12 +1388,22 @@ static int assoc_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_meas_batch* bat
   assoc_prepare_kernel<<<dim3(row_blocks + (n_pool + 127) / 128, Hu), 128, 0, st>>>(*batch, N, T, *cfg, n_st, SO, W, *view, n_pool,
                                                                                    row_blocks);
   GCS_LAUNCH_CHECK(ctx);
+  // top-K: persistent CTAs pulling rows from a counter; view tiles staged once per CTA by TMA when the box fits
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  bool staged = (m_tile_view % 256 == 0) && topk_smem_bytes(n_tiles, m_tile_view, true) <= 200 * 1024 &&
+                tma::encode_2d_f64(&tmap, view->positions, 256, (uint64_t)n_pool * 3 / 256, 256, (uint32_t)(3 * m_tile_view / 256));
+  if (getenv("GCS_TOPK_NO_TMA")) staged = false;
+  const size_t topk_smem = topk_smem_bytes(n_tiles, m_tile_view, staged);
+  if (topk_smem > 40 * 1024) GCS_CHECK_CUDA(ctx, gcs_smem_attr_once((const void*)assoc_topk_kernel<8>, (int)topk_smem));
+  int* row_counter = (int*)(ws + o_ctr);
+  GCS_CHECK_CUDA(ctx, cudaMemsetAsync(row_counter, 0, sizeof(int), st));
+  const long long total_rows = (long long)n_units * N;
+  int topk_ctas = (int)((total_rows + kTopkWarps - 1) / kTopkWarps);
+  if (topk_ctas > ctx->sm_count) topk_ctas = ctx->sm_count;
   gcs_timing_begin(ctx, st);
-  const size_t topk_smem = (size_t)m_tile_view * (3 * sizeof(double) + 1);
-  if (topk_smem > 40 * 1024)
-    GCS_CHECK_CUDA(ctx, gcs_smem_attr_once((const void*)assoc_topk_kernel<8>, (int)topk_smem));
-  assoc_topk_kernel<8><<<dim3((unsigned)cdivm((int64_t)N, kTopkRows), Hu), 32 * kTopkRows, topk_smem, st>>>(
-      *batch, N, *view, m_tile_view, n_st, n_tiles, W, *cfg, *out);
+  assoc_topk_kernel<8><<<topk_ctas, 32 * kTopkWarps, topk_smem, st>>>(*batch, N, n_units, *view, m_tile_view, n_st, n_tiles, W, *cfg,
+                                                                      *out, row_counter, tmap, staged ? 1 : 0);
   gcs_timing_end(ctx, st);
   GCS_LAUNCH_CHECK(ctx);
   assoc_sinkhorn_kernel<8><<<dim3(kSkCtas, Hu), kSkThreads, 0, st>>>(*batch, N, *view, W, *cfg, *out, cert, (double*)(ws + o_brow));

@@ -127,10 +127,17 @@ __global__ void surfel_rank_scan_kernel(int32_t* __restrict__ hist, int n_chunks
   if (k >= n_keys) return;
   hist += (int64_t)blockIdx.y * n_chunks * n_keys; total += (int64_t)blockIdx.y * n_keys;
   int acc = 0;
-  for (int c = 0; c < n_chunks; ++c) {
-    const int v = hist[(int64_t)c * n_keys + k];
-    hist[(int64_t)c * n_keys + k] = acc;
-    acc += v;
+  // eight chunk counts are loaded before any prefix is stored (the in-place store would otherwise order every load
+  // behind it: one memory round trip per chunk)
+  for (int c0 = 0; c0 < n_chunks; c0 += 8) {
+    int v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < n_chunks) ? hist[(int64_t)(c0 + j) * n_keys + k] : 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (c0 + j < n_chunks) hist[(int64_t)(c0 + j) * n_keys + k] = acc;
+      acc += v[j];
+    }
   }
   total[k] = acc;
 }
@@ -191,6 +198,9 @@ __global__ void __launch_bounds__(128) surfel_fit_kernel(const double* __restric
   }
   const double eps = 1e-12, eig_min = cfg.eig_min;
   const int cnt = total[c] < G.max_occ ? total[c] : G.max_occ;
+  // a cell below the point budget can never be valid (:252) and nothing downstream reads the other fields of an invalid
+  // cell (surfel_select_kernel): most of the 8,192 cells of a scan are empty
+  if (cnt < G.min_points || cnt == 0) { F.valid[c] = 0; return; }
   const double cx = center[0], cy = center[1], cz = center[2];
   // pass 1: weighted centroid
   double wsum = 0.0, m0 = 0.0, m1 = 0.0, m2 = 0.0, tsum = 0.0;
@@ -423,8 +433,10 @@ static int surfels_launch(gcs_ctx* ctx, cudaStream_t st, const double* pts, cons
   G.h = cfg->voxel_size_m > 1e-12 ? cfg->voxel_size_m : 1e-12;
   const int n_keys = G.n_cells + 1;
   GCS_REQUIRE(ctx, (size_t)n_keys * sizeof(int) <= 160 * 1024, "%s: %d cells exceed the shared-memory counter", who, G.n_cells);
+  // chunks of the per-cell ranking: about two CTAs per SM over all units (the ranks do not depend on the chunking)
   int n_chunks = (int)cdiv(n, 1024);
-  const int max_chunks = ctx->sm_count * 2;
+  int max_chunks = (ctx->sm_count * 2 + n_units - 1) / n_units;
+  if (max_chunks < 4) max_chunks = 4;
   if (n_chunks > max_chunks) n_chunks = max_chunks;
   const int64_t per_chunk = cdiv(cdiv(n, n_chunks), 1024) * 1024;
   n_chunks = (int)cdiv(n, per_chunk);
