@@ -524,35 +524,42 @@ constexpr int kSkCtas = 8;
 constexpr int kSkThreads = 256;
 constexpr int kSkMaxVals = 16;
 
-// Sum of NV (<= kSkMaxVals) per-thread values over the whole cluster; every thread of every CTA gets post(k, total_k).
-// Fixed order: shuffle tree per warp, warps in index order, CTAs in rank order.  Thread k of a CTA gathers column k from
-// the eight CTAs through distributed shared memory, applies `post` (e.g. the Sinkhorn scaling: one pow() per column and
-// CTA instead of one per thread) and publishes the result in local shared memory.  `phase` alternates the exchange
-// buffer, so that a CTA running ahead never overwrites values a slower one still reads.
-template <int NV, typename Post>
-__device__ __forceinline__ void cluster_sum(double (&v)[NV], double (*xch)[kSkCtas][kSkMaxVals], double* sredw, double* tot,
-                                            unsigned& phase, Post post) {
+// Sum of NV (<= kSkMaxVals) values per row over all rows; every thread of every CTA gets post(k, total_k).
+// The rows are cut into kSkCtas = 8 VIRTUAL CTAs of 256 rows; a real CTA of a cluster of C = 8 / RPT CTAs carries RPT of
+// them (RPT rows per thread).  Fixed order whatever C is: shuffle tree per (virtual CTA, warp), warps in index order,
+// virtual CTAs in index order -- the batched launch (small clusters, many hypotheses in flight) and the single-scan
+// launch (eight SMs on one hypothesis) give bit-identical results.  Thread (r, q, k) adds up value k of this CTA's
+// virtual CTA q over the warps and PUSHES it into real CTA r's exchange buffer; after the cluster barrier (release /
+// acquire) every CTA sums its local copy.  A pull (barrier, then remote loads) puts a distributed-shared-memory round
+// trip behind every barrier.  `phase` alternates the exchange buffer, so that a CTA running ahead never overwrites
+// values a slower one still reads.
+template <int NV, int RPT, typename Post>
+__device__ __forceinline__ void cluster_sum(double (&v)[RPT][NV], double (*xch)[kSkCtas][kSkMaxVals],
+                                            double (*sredw)[kSkThreads / 32][kSkMaxVals], double* tot, unsigned& phase,
+                                            Post post) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
+  constexpr int C = kSkCtas / RPT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  for (int q = 0; q < RPT; ++q)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[q][k] = warp_sum(v[q][k]);
   __syncthreads();   // sredw / tot are free (the previous call's readers are done)
   if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) sredw[warp * kSkMaxVals + k] = v[k];
+    for (int q = 0; q < RPT; ++q)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) sredw[q][warp][k] = v[q][k];
   }
   __syncthreads();
-  // PUSH exchange: thread (r, k) adds up column k over this CTA's warps and stores it into row `my rank` of CTA r's
-  // exchange buffer; after the cluster barrier (release / acquire) every CTA sums its own local copy in rank order.  A
-  // pull (barrier, then remote loads) puts a distributed-shared-memory round trip behind every barrier.
   const unsigned buf = phase & 1u;
   const unsigned my_rank = cluster.block_rank();
-  if (tid < NV * kSkCtas) {
-    const int k = tid % NV, r = tid / NV;
+  if (tid < NV * kSkCtas) {       // NV * C * RPT threads
+    const int k = tid % NV, rest = tid / NV, r = rest % C, q = rest / C;
     double t = 0.0;
-    for (int w = 0; w < kSkThreads / 32; ++w) t += sredw[w * kSkMaxVals + k];
-    cluster.map_shared_rank(&xch[buf][my_rank][0], r)[k] = t;
+    for (int w = 0; w < kSkThreads / 32; ++w) t += sredw[q][w][k];
+    cluster.map_shared_rank(&xch[buf][my_rank * RPT + q][0], r)[k] = t;
   }
   cluster.sync();
   if (tid < NV) {
@@ -562,23 +569,25 @@ __device__ __forceinline__ void cluster_sum(double (&v)[NV], double (*xch)[kSkCt
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < NV; ++k) v[k] = tot[k];
+  for (int k = 0; k < NV; ++k) v[0][k] = tot[k];
   ++phase;
 }
 
-template <int K>
-__global__ void __cluster_dims__(kSkCtas, 1, 1) __launch_bounds__(kSkThreads)
+// RPT rows per thread, cluster of 8 / RPT CTAs (set at launch): 1 for a single hypothesis, 2 or 4 when many hypotheses
+// share the device (the iterations are bound by the float64 pipe of the SMs a hypothesis runs on and by the cluster
+// barrier: with 64 hypotheses in flight two SMs each are enough and leave room for all of them at once)
+template <int K, int RPT>
+__global__ void __launch_bounds__(kSkThreads)
     assoc_sinkhorn_kernel(gcs_meas_batch B, int N, gcs_map_view V, AssocWs W, gcs_assoc_cfg cfg, gcs_assoc_result R,
                           double* __restrict__ cert, double* __restrict__ brow_ws) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ double xch[2][kSkCtas][kSkMaxVals];
-  __shared__ double sredw[(kSkThreads / 32) * kSkMaxVals];
+  __shared__ double sredw[RPT][kSkThreads / 32][kSkMaxVals];
   __shared__ double tot[kSkMaxVals];
   __shared__ SelectSmem sel;
   const int tid = threadIdx.x;
   const int rank = (int)cluster.block_rank();
-  const int i = rank * kSkThreads + tid;   // N <= kSkCtas * kSkThreads = 2048
   {
     const int64_t un = blockIdx.y;          // unit: one cluster per hypothesis
     B = meas_batch_unit(B, un);
@@ -587,39 +596,50 @@ __global__ void __cluster_dims__(kSkCtas, 1, 1) __launch_bounds__(kSkThreads)
     cert += un * GCS_OT_NCERT;
     brow_ws += un * N * K;
   }
+  int row[RPT];                             // N <= kSkCtas * kSkThreads = 2048
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) row[q] = (rank * RPT + q) * kSkThreads + tid;
   unsigned phase = 0;
-  double Km[K], Cm[K], u = 1.0, a = 0.0;
+  double Km[RPT][K], u[RPT], a[RPT];
   const double eps = fmax(cfg.epsilon, 1e-12);
-  double nv[1] = {(i < N && B.valid[i]) ? 1.0 : 0.0};
   auto ident = [](int, double t) { return t; };
-  cluster_sum<1>(nv, xch, sredw, tot, phase, ident);
-  const double sum_valid = nv[0];
+  double nv[RPT][1];
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) nv[q][0] = (row[q] < N && B.valid[row[q]]) ? 1.0 : 0.0;
+  cluster_sum<1, RPT>(nv, xch, sredw, tot, phase, ident);
+  const double sum_valid = nv[0][0];
   const double sum_a = fmax(sum_valid, cfg.eps_mass);
 #pragma unroll
-  for (int k = 0; k < K; ++k) { Km[k] = 0.0; Cm[k] = 0.0; }
-  if (i < N) {
-    a = (B.valid[i] ? 1.0 : 0.0) / sum_a;
-    const double mp[3] = {W.mpos[3 * i], W.mpos[3 * i + 1], W.mpos[3 * i + 2]};
-    const double md[3] = {W.mdir[3 * i], W.mdir[3 * i + 1], W.mdir[3 * i + 2]};
-    const double mk = W.mkap[i];
-    const double A_k1 = A_vmf(fmax(mk, 1e-12), 1e-12);
-    double rmin = 1.0e300, bsum = 0.0, bdec[K];
-    for (int k = 0; k < K; ++k) {
-      const int v = R.candidate_pool_indices[i * K + k];
-      double c = pair_cost_pre(mp, md, mk, A_k1, V.positions + 3 * v, V.directions + 3 * v, V.kappas[v], W.vAk[v], cfg.beta);
-      long long dt = cfg.scan_seq - V.last_supported_scan_seq[v];
-      if (dt < 0) dt = 0;
-      c += cfg.epsilon * cfg.recency_decay_lambda * (double)dt;
-      Cm[k] = c;
-      rmin = fmin(rmin, c);
-      double d = exp(-cfg.recency_decay_lambda * (double)dt);
-      if (!(d > 0.0)) d = 0.0;
-      bdec[k] = d; bsum += d;
-    }
-    for (int k = 0; k < K; ++k) {
-      Cm[k] -= rmin;
-      Km[k] = exp(-Cm[k] / eps);
-      brow_ws[i * K + k] = bdec[k] / fmax(bsum, cfg.eps_mass);  // diagnostics only (:420-425)
+  for (int q = 0; q < RPT; ++q) {
+    const int i = row[q];
+    u[q] = 1.0; a[q] = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) Km[q][k] = 0.0;
+    if (i < N) {
+      a[q] = (B.valid[i] ? 1.0 : 0.0) / sum_a;
+      const double mp[3] = {W.mpos[3 * i], W.mpos[3 * i + 1], W.mpos[3 * i + 2]};
+      const double md[3] = {W.mdir[3 * i], W.mdir[3 * i + 1], W.mdir[3 * i + 2]};
+      const double mk = W.mkap[i];
+      const double A_k1 = A_vmf(fmax(mk, 1e-12), 1e-12);
+      double rmin = 1.0e300, bsum = 0.0, bdec[K], Cm[K];
+      for (int k = 0; k < K; ++k) {
+        const int v = R.candidate_pool_indices[i * K + k];
+        double c = pair_cost_pre(mp, md, mk, A_k1, V.positions + 3 * v, V.directions + 3 * v, V.kappas[v], W.vAk[v], cfg.beta);
+        long long dt = cfg.scan_seq - V.last_supported_scan_seq[v];
+        if (dt < 0) dt = 0;
+        c += cfg.epsilon * cfg.recency_decay_lambda * (double)dt;
+        Cm[k] = c;
+        rmin = fmin(rmin, c);
+        double d = exp(-cfg.recency_decay_lambda * (double)dt);
+        if (!(d > 0.0)) d = 0.0;
+        bdec[k] = d; bsum += d;
+      }
+      for (int k = 0; k < K; ++k) {
+        Cm[k] -= rmin;
+        Km[q][k] = exp(-Cm[k] / eps);
+        R.cost_matrix[i * K + k] = Cm[k];    // read back for the certificate sums after the iterations
+        brow_ws[i * K + k] = bdec[k] / fmax(bsum, cfg.eps_mass);  // diagnostics only (:420-425)
+      }
     }
   }
   double sv[K];
@@ -628,47 +648,53 @@ __global__ void __cluster_dims__(kSkCtas, 1, 1) __launch_bounds__(kSkThreads)
   const double ua = 1.0 / (1.0 + cfg.tau_a / eps), vb = 1.0 / (1.0 + cfg.tau_b / eps);
   const double bk = 1.0 / (double)K;
   for (int it = 0; it < cfg.k_sinkhorn; ++it) {
-    double ktu[K];
-    if (i < N) {
-      double kv = 0.0;
+    double ktu[RPT][K];
 #pragma unroll
-      for (int k = 0; k < K; ++k) kv += Km[k] * sv[k];
-      u = pow_pos(a / (kv + 1e-12), ua);
+    for (int q = 0; q < RPT; ++q) {
+      if (row[q] < N) {
+        double kv = 0.0;
 #pragma unroll
-      for (int k = 0; k < K; ++k) ktu[k] = Km[k] * u;
-    } else {
+        for (int k = 0; k < K; ++k) kv += Km[q][k] * sv[k];
+        u[q] = pow_pos(a[q] / (kv + 1e-12), ua);
 #pragma unroll
-      for (int k = 0; k < K; ++k) ktu[k] = 0.0;
+        for (int k = 0; k < K; ++k) ktu[q][k] = Km[q][k] * u[q];
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) ktu[q][k] = 0.0;
+      }
     }
     // one cluster barrier per iteration; the K column scalings v_k = (b / (K^T u + eps))^(1/(1+tau_b/eps)) are
     // evaluated by the K gathering threads of each CTA
-    cluster_sum<K>(ktu, xch, sredw, tot, phase, [&](int, double t) { return pow_pos(bk / (t + 1e-12), vb); });
+    cluster_sum<K, RPT>(ktu, xch, sredw, tot, phase, [&](int, double t) { return pow_pos(bk / (t + 1e-12), vb); });
 #pragma unroll
-    for (int k = 0; k < K; ++k) sv[k] = ktu[k];
+    for (int k = 0; k < K; ++k) sv[k] = ktu[0][k];
   }
   // outputs + certificate sums
-  double cs[5 + K];
+  double cs[RPT][5 + K];
 #pragma unroll
-  for (int k = 0; k < 5 + K; ++k) cs[k] = 0.0;
-  if (i < N) {
-    const bool mv = B.valid[i] != 0;
-    double row = 0.0;
-    for (int k = 0; k < K; ++k) {
-      const double pi = u * Km[k] * sv[k];
-      row += pi; cs[5 + k] += pi; cs[4] += pi * Cm[k];
-      R.responsibilities[i * K + k] = mv ? pi : 0.0;
-      R.cost_matrix[i * K + k] = Cm[k];
+  for (int q = 0; q < RPT; ++q) {
+#pragma unroll
+    for (int k = 0; k < 5 + K; ++k) cs[q][k] = 0.0;
+    const int i = row[q];
+    if (i < N) {
+      const bool mv = B.valid[i] != 0;
+      double rowm = 0.0;
+      for (int k = 0; k < K; ++k) {
+        const double pi = u[q] * Km[q][k] * sv[k];
+        rowm += pi; cs[q][5 + k] += pi; cs[q][4] += pi * R.cost_matrix[i * K + k];
+        R.responsibilities[i * K + k] = mv ? pi : 0.0;
+      }
+      R.row_masses[i] = rowm;
+      cs[q][0] = rowm; cs[q][1] = rowm * rowm;
+      const double d = rowm - a[q];
+      cs[q][2] = d * d;
+      cs[q][3] = fmax(a[q] - rowm, 0.0);
     }
-    R.row_masses[i] = row;
-    cs[0] = row; cs[1] = row * row;
-    const double d = row - a;
-    cs[2] = d * d;
-    cs[3] = fmax(a - row, 0.0);
   }
-  cluster_sum<5 + K>(cs, xch, sredw, tot, phase, ident);
-  const double S_row = cs[0], S_row2 = cs[1], S_da = cs[2], S_nov = cs[3], S_cost = cs[4];
+  cluster_sum<5 + K, RPT>(cs, xch, sredw, tot, phase, ident);
+  const double S_row = cs[0][0], S_row2 = cs[0][1], S_da = cs[0][2], S_nov = cs[0][3], S_cost = cs[0][4];
   double db = 0.0;
-  for (int k = 0; k < K; ++k) db += (cs[5 + k] - bk) * (cs[5 + k] - bk);
+  for (int k = 0; k < K; ++k) db += (cs[0][5 + k] - bk) * (cs[0][5 + k] - bk);
   // no CTA may exit while another still reads its exchange buffer; the barrier also makes the brow_ws rows written by
   // every CTA visible to rank 0, which finishes alone
   cluster.sync();
@@ -702,6 +728,35 @@ __global__ void __cluster_dims__(kSkCtas, 1, 1) __launch_bounds__(kSkThreads)
     cert[GCS_OT_SUM_M2] = S_row2;
     for (int k = GCS_OT_SUM_M2 + 1; k < GCS_OT_NCERT; ++k) cert[k] = 0.0;
   }
+}
+
+template <int RPT>
+static cudaError_t sinkhorn_launch(cudaStream_t st, unsigned n_units, gcs_meas_batch B, int N, gcs_map_view V, AssocWs W,
+                                   gcs_assoc_cfg cfg, gcs_assoc_result R, double* cert, double* brow) {
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3(kSkCtas / RPT, n_units, 1);
+  lc.blockDim = dim3(kSkThreads, 1, 1);
+  lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kSkCtas / RPT; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  return cudaLaunchKernelEx(&lc, assoc_sinkhorn_kernel<8, RPT>, B, N, V, W, cfg, R, cert, brow);
+}
+
+// every unit of a stacked batch := the base batch (camera slice, zero LiDAR rows); blockIdx.y = unit
+__global__ void __launch_bounds__(128) batch_replicate_kernel(gcs_meas_batch S, gcs_meas_batch D, int N) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= N) return;
+  D = meas_batch_unit(D, blockIdx.y);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { D.Lambdas[9 * i + k] = S.Lambdas[9 * i + k]; D.etas[9 * i + k] = S.etas[9 * i + k]; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { D.thetas[3 * i + k] = S.thetas[3 * i + k]; D.colors[3 * i + k] = S.colors[3 * i + k]; }
+  D.weights[i] = S.weights[i]; D.sources[i] = S.sources[i]; D.source_indices[i] = S.source_indices[i];
+  D.valid[i] = S.valid[i]; D.timestamps[i] = S.timestamps[i];
 }
 
 // =================================================================================================
@@ -1406,7 +1461,13 @@ static int assoc_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_meas_batch* bat
                                                                       *out, row_counter, tmap, staged ? 1 : 0);
   gcs_timing_end(ctx, st);
   GCS_LAUNCH_CHECK(ctx);
-  assoc_sinkhorn_kernel<8><<<dim3(kSkCtas, Hu), kSkThreads, 0, st>>>(*batch, N, *view, W, *cfg, *out, cert, (double*)(ws + o_brow));
+  // cluster size per hypothesis: eight SMs for one, fewer when the batch fills the device anyway
+  double* brow = (double*)(ws + o_brow);
+  // the iterations are a latency chain (log / exp / barrier), so as many CTAs as stay resident (three per SM) overlap
+  const int sk_rpt = (n_units * 8 <= 3 * ctx->sm_count) ? 1 : (n_units * 4 <= 3 * ctx->sm_count ? 2 : 4);
+  if (sk_rpt == 1) GCS_CHECK_CUDA(ctx, sinkhorn_launch<1>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow));
+  else if (sk_rpt == 2) GCS_CHECK_CUDA(ctx, sinkhorn_launch<2>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow));
+  else GCS_CHECK_CUDA(ctx, sinkhorn_launch<4>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow));
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
 }
@@ -1471,6 +1532,44 @@ int gcs_visual_pose_evidence_batched(gcs_ctx* ctx, void* stream, const gcs_meas_
                                                                                      eps_mass, out_L22, out_h22, out_rec, poses_dev);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
+}
+
+int gcs_lidar_evidence_primitives_batched(gcs_ctx* ctx, void* stream, const gcs_prim_batch_args* a) {
+  if (!ctx) return GCS_EINVAL;
+  GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  GCS_REQUIRE(ctx, a && a->atlas && a->n_units >= 1 && a->n >= 1 && a->n_tiles >= 1 && a->n_tiles <= 16,
+              "lidar_evidence_primitives_batched: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = gcs_deskew_constant_twist_batched(ctx, stream, a->pts, a->t, a->w, a->n, a->xi, a->n_units, a->scan_start_time,
+                                             a->scan_end_time, a->dk_pts, a->dk_w, a->dk_cert);
+  if (rc) return rc;
+  if (a->base.Lambdas) {
+    rc = check_mbatch(ctx, &a->base, "lidar_evidence_primitives_batched");
+    if (rc) return rc;
+    rc = check_mbatch(ctx, &a->batch, "lidar_evidence_primitives_batched");
+    if (rc) return rc;
+    GCS_REQUIRE(ctx, a->base.n_feat == a->batch.n_feat && a->base.n_surfel == a->batch.n_surfel,
+                "lidar_evidence_primitives_batched: base batch budget differs from the stacked batch");
+    const int N = a->batch.n_feat + a->batch.n_surfel;
+    batch_replicate_kernel<<<dim3((N + 127) / 128, a->n_units), 128, 0, st>>>(a->base, a->batch, N);
+    GCS_LAUNCH_CHECK(ctx);
+  }
+  rc = gcs_extract_lidar_surfels_batched(ctx, stream, a->dk_pts, a->t, a->dk_w, a->n, a->n_units, 1, &a->surfel_cfg, &a->batch,
+                                         a->n_lidar_valid);
+  if (rc) return rc;
+  if (a->inflate)
+    rc = gcs_extract_atlas_map_view_inflated(ctx, stream, a->atlas, a->tile_index, a->tile_ids, a->n_tiles, a->m_tile_view,
+                                             a->eps_lift, a->eps_mass, a->assoc_cfg.scan_seq, a->assoc_cfg.recency_decay_lambda,
+                                             a->recency_min_scale, &a->view, a->view_n_valid, a->inflate_stats);
+  else
+    rc = gcs_extract_atlas_map_view(ctx, stream, a->atlas, a->tile_index, a->tile_ids, a->n_tiles, a->m_tile_view, a->eps_lift,
+                                    a->eps_mass, &a->view, a->view_n_valid);
+  if (rc) return rc;
+  rc = gcs_associate_primitives_ot_batched(ctx, stream, &a->batch, a->n_units, &a->view, a->tile_ids, a->n_tiles, a->m_tile_view,
+                                           &a->assoc_cfg, &a->assoc, a->ot_cert);
+  if (rc) return rc;
+  return gcs_visual_pose_evidence_batched(ctx, stream, &a->batch, a->n_units, &a->view, &a->assoc, a->assoc_cfg.k_assoc, a->poses,
+                                          a->eps_lift, a->eps_mass, a->L22, a->h22, a->rec);
 }
 
 int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int32_t* tile_index, const int64_t* tile_ids,

@@ -88,44 +88,59 @@ __global__ void __launch_bounds__(kSurfThreads) surfel_cell_key_kernel(const dou
 }
 
 // ---- S3 ------------------------------------------------------------------------------------------------
-// One CTA walks a contiguous chunk of points in index order, 1024 at a time, warps strictly in order, keeping a
-// running per-cell count in shared memory.  local_rank[i] = number of earlier points of the same chunk in the
-// same cell.  hist[chunk][cell] = points of this chunk per cell.
-__global__ void __launch_bounds__(1024) surfel_rank_chunk_kernel(const int32_t* __restrict__ key, int64_t n,
-                                                                 int64_t per_chunk, int n_keys,
-                                                                 int32_t* __restrict__ local_rank,
-                                                                 int32_t* __restrict__ hist) {
+// One WARP walks a contiguous chunk of points in index order, 32 at a time, keeping a running per-cell count in its own
+// shared-memory table.  local_rank[i] = number of earlier points of the same chunk in the same cell;
+// hist[chunk][cell] = points of this chunk per cell.  No barrier anywhere: a CTA is a single warp, seven of them fit the
+// shared memory of an SM, and a batch of hypotheses brings a thousand independent chunks (the 1024-thread version let
+// one warp at a time touch the table, 32 barriers per 1024 points: 239 us for 64 hypotheses).
+__global__ void __launch_bounds__(32) surfel_rank_chunk_kernel(const int32_t* __restrict__ key, int64_t n,
+                                                               int64_t per_chunk, int n_keys,
+                                                               int32_t* __restrict__ local_rank,
+                                                               int32_t* __restrict__ hist) {
   extern __shared__ int s_cnt[];  // n_keys ints
   key += (int64_t)blockIdx.y * n; local_rank += (int64_t)blockIdx.y * n; hist += (int64_t)blockIdx.y * gridDim.x * n_keys;
-  for (int k = threadIdx.x; k < n_keys; k += 1024) s_cnt[k] = 0;
-  __syncthreads();
+  const int lane = threadIdx.x;
+  for (int k = lane; k < n_keys; k += 32) s_cnt[k] = 0;
+  __syncwarp();
   const int64_t i0 = (int64_t)blockIdx.x * per_chunk;
   const int64_t i1 = (i0 + per_chunk < n) ? i0 + per_chunk : n;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int64_t base = i0; base < i1; base += 1024) {
-    const int64_t i = base + threadIdx.x;
-    const bool on = i < i1;
-    const int k = on ? key[i] : -1 - (int)threadIdx.x;  // inactive lanes get unique negative keys
-    const unsigned peers = __match_any_sync(0xffffffffu, k);
-    const int before = __popc(peers & ((1u << lane) - 1u));
-    const bool leader = (lane == 31 - __clz(peers));  // highest lane of the group updates the counter
-    for (int wv = 0; wv < 32; ++wv) {
-      if (warp == wv && on) {
+  constexpr int kAhead = 8;   // the keys of eight 32-point steps are loaded together: one memory round trip per 256 points
+  for (int64_t base0 = i0; base0 < i1; base0 += 32 * kAhead) {
+    int kk[kAhead];
+#pragma unroll
+    for (int j = 0; j < kAhead; ++j) {
+      const int64_t i = base0 + 32 * j + lane;
+      kk[j] = i < i1 ? key[i] : -1 - lane;  // inactive lanes get unique negative keys
+    }
+#pragma unroll
+    for (int j = 0; j < kAhead; ++j) {
+      const int64_t i = base0 + 32 * j + lane;
+      const bool on = i < i1;
+      const int k = kk[j];
+      const unsigned peers = __match_any_sync(0xffffffffu, k);
+      const int before = __popc(peers & ((1u << lane) - 1u));
+      const bool leader = (lane == 31 - __clz(peers));  // highest lane of the group updates the counter
+      if (on) {
         const int basecnt = s_cnt[k];
         local_rank[i] = basecnt + before;
         __syncwarp(peers);
         if (leader) s_cnt[k] = basecnt + __popc(peers);
       }
-      __syncthreads();
+      __syncwarp();
     }
   }
-  for (int k = threadIdx.x; k < n_keys; k += 1024) hist[(int64_t)blockIdx.x * n_keys + k] = s_cnt[k];
+  for (int k = lane; k < n_keys; k += 32) hist[(int64_t)blockIdx.x * n_keys + k] = s_cnt[k];
 }
 // per key: exclusive scan over chunks (in place) + total
-__global__ void surfel_rank_scan_kernel(int32_t* __restrict__ hist, int n_chunks, int n_keys, int32_t* __restrict__ total) {
+// ... and the list of the cells that reach the point budget (the only ones the plane fit has to look at; order = arrival
+// order of the atomic: the fit of a cell does not depend on it), `valid` cleared for all others
+__global__ void surfel_rank_scan_kernel(int32_t* __restrict__ hist, int n_chunks, int n_keys, int32_t* __restrict__ total,
+                                        int min_points, int32_t* __restrict__ occ_list, int32_t* __restrict__ n_occ,
+                                        uint8_t* __restrict__ cell_valid) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_keys) return;
   hist += (int64_t)blockIdx.y * n_chunks * n_keys; total += (int64_t)blockIdx.y * n_keys;
+  occ_list += (int64_t)blockIdx.y * (n_keys - 1); cell_valid += (int64_t)blockIdx.y * (n_keys - 1);
   int acc = 0;
   // eight chunk counts are loaded before any prefix is stored (the in-place store would otherwise order every load
   // behind it: one memory round trip per chunk)
@@ -140,6 +155,10 @@ __global__ void surfel_rank_scan_kernel(int32_t* __restrict__ hist, int n_chunks
     }
   }
   total[k] = acc;
+  if (k < n_keys - 1) {           // key n_keys - 1 collects the masked points
+    if (acc >= min_points && acc > 0) occ_list[atomicAdd(n_occ + blockIdx.y, 1)] = k;
+    else cell_valid[k] = 0;
+  }
 }
 __global__ void surfel_bucket_init_kernel(int32_t* __restrict__ bucket, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -183,45 +202,93 @@ __device__ __forceinline__ void normalize3(double* v, double eps) {
   v[0] *= inv; v[1] *= inv; v[2] *= inv;
 }
 
-__global__ void __launch_bounds__(128) surfel_fit_kernel(const double* __restrict__ pts, const double* __restrict__ ts,
-                                                         const double* __restrict__ w, const double* __restrict__ center,
-                                                         const int32_t* __restrict__ bucket,
-                                                         const int32_t* __restrict__ total, SurfelGeom G,
-                                                         gcs_surfel_cfg cfg, CellFit F, UnitStrides U, int n_keys) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= G.n_cells) return;
+// Plane fit of the listed cells (surfel_rank_scan_kernel) in two kernels:
+//   surfel_moments_kernel  eight lanes per cell: weighted centroid, then the weighted scatter about it (two passes over the
+//                          cell's <= 32 points, gathers four deep instead of 32 deep, partial sums in a fixed xor tree);
+//   surfel_fit_kernel      one thread per cell: Jacobi eigh, tangent basis, Wishart-regularised precision, vMF kappa.
+// The reference's third pass -- in-plane spreads sum w (d . e)^2 -- is e^T S e with the scatter S of the second pass
+// (same number up to rounding), so the algebra kernel does not touch the points.  Groups / threads stride over the list:
+// the grids do not depend on how many cells a scan fills, and the float64-heavy algebra runs in full warps.
+constexpr int kFitLanes = 8;
+constexpr int kCellMom = 12;   // wsum, tsum, mu (3), scatter s00 s01 s02 s11 s12 s22, cnt
+__device__ __forceinline__ double group_sum8(double v, unsigned gmask) {
+  v += __shfl_xor_sync(gmask, v, 4);
+  v += __shfl_xor_sync(gmask, v, 2);
+  v += __shfl_xor_sync(gmask, v, 1);
+  return v;
+}
+__global__ void __launch_bounds__(128) surfel_moments_kernel(const double* __restrict__ pts, const double* __restrict__ ts,
+                                                             const double* __restrict__ w, const double* __restrict__ center,
+                                                             const int32_t* __restrict__ bucket,
+                                                             const int32_t* __restrict__ total, SurfelGeom G, UnitStrides U,
+                                                             int n_keys, const int32_t* __restrict__ occ_list,
+                                                             const int32_t* __restrict__ n_occ, double* __restrict__ mom) {
   {
     const int64_t u = blockIdx.y;
     pts += u * U.pts; ts += u * U.ts; w += u * U.w; center += u * 4;
     bucket += u * G.n_cells * G.max_occ; total += u * n_keys;
+    occ_list += u * G.n_cells; mom += u * G.n_cells * kCellMom;
+  }
+  const int n_list = n_occ[blockIdx.y];
+  const int lane8 = threadIdx.x & (kFitLanes - 1);
+  const unsigned gmask = 0xffu << (threadIdx.x & 24);
+  const int n_groups = (gridDim.x * blockDim.x) / kFitLanes;
+  const double eps = 1e-12;
+  const double cx = center[0], cy = center[1], cz = center[2];
+  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) / kFitLanes; e < n_list; e += n_groups) {
+    const int c = occ_list[e];
+    const int cnt = total[c] < G.max_occ ? total[c] : G.max_occ;
+    // pass 1: weighted centroid
+    double wsum = 0.0, m0 = 0.0, m1 = 0.0, m2 = 0.0, tsum = 0.0;
+    for (int o = lane8; o < cnt; o += kFitLanes) {
+      const int i = bucket[(int64_t)c * G.max_occ + o];
+      const double wi = w[i];
+      m0 += (pts[3 * i] - cx) * wi; m1 += (pts[3 * i + 1] - cy) * wi; m2 += (pts[3 * i + 2] - cz) * wi;
+      wsum += wi; tsum += ts[i];
+    }
+    wsum = group_sum8(wsum, gmask); m0 = group_sum8(m0, gmask); m1 = group_sum8(m1, gmask); m2 = group_sum8(m2, gmask);
+    tsum = group_sum8(tsum, gmask);
+    const double w_sum = wsum + eps;
+    const double mu[3] = {m0 / w_sum, m1 / w_sum, m2 / w_sum};
+    // pass 2: weighted scatter.  Absent slots gather point 0 with weight 0 in the reference
+    // (lidar_surfel_extraction.py:115-121): they add exactly 0 to every weighted sum, so they are skipped here.
+    double s00 = 0, s01 = 0, s02 = 0, s11 = 0, s12 = 0, s22 = 0;
+    for (int o = lane8; o < cnt; o += kFitLanes) {
+      const int i = bucket[(int64_t)c * G.max_occ + o];
+      const double wi = w[i];
+      const double d0 = (pts[3 * i] - cx) - mu[0], d1 = (pts[3 * i + 1] - cy) - mu[1], d2 = (pts[3 * i + 2] - cz) - mu[2];
+      s00 += wi * d0 * d0; s01 += wi * d0 * d1; s02 += wi * d0 * d2;
+      s11 += wi * d1 * d1; s12 += wi * d1 * d2; s22 += wi * d2 * d2;
+    }
+    s00 = group_sum8(s00, gmask); s01 = group_sum8(s01, gmask); s02 = group_sum8(s02, gmask);
+    s11 = group_sum8(s11, gmask); s12 = group_sum8(s12, gmask); s22 = group_sum8(s22, gmask);
+    if (lane8 == 0) {
+      double* m = mom + (int64_t)e * kCellMom;
+      m[0] = wsum; m[1] = tsum; m[2] = mu[0]; m[3] = mu[1]; m[4] = mu[2];
+      m[5] = s00; m[6] = s01; m[7] = s02; m[8] = s11; m[9] = s12; m[10] = s22; m[11] = (double)cnt;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) surfel_fit_kernel(const double* __restrict__ center, SurfelGeom G, gcs_surfel_cfg cfg,
+                                                         CellFit F, const int32_t* __restrict__ occ_list,
+                                                         const int32_t* __restrict__ n_occ, const double* __restrict__ mom) {
+  {
+    const int64_t u = blockIdx.y;
+    center += u * 4; occ_list += u * G.n_cells; mom += u * G.n_cells * kCellMom;
     F = cellfit_unit(F, u, G.n_cells);
   }
+  const int n_list = n_occ[blockIdx.y];
   const double eps = 1e-12, eig_min = cfg.eig_min;
-  const int cnt = total[c] < G.max_occ ? total[c] : G.max_occ;
-  // a cell below the point budget can never be valid (:252) and nothing downstream reads the other fields of an invalid
-  // cell (surfel_select_kernel): most of the 8,192 cells of a scan are empty
-  if (cnt < G.min_points || cnt == 0) { F.valid[c] = 0; return; }
   const double cx = center[0], cy = center[1], cz = center[2];
-  // pass 1: weighted centroid
-  double wsum = 0.0, m0 = 0.0, m1 = 0.0, m2 = 0.0, tsum = 0.0;
-  for (int o = 0; o < cnt; ++o) {
-    const int i = bucket[(int64_t)c * G.max_occ + o];
-    const double wi = w[i];
-    m0 += (pts[3 * i] - cx) * wi; m1 += (pts[3 * i + 1] - cy) * wi; m2 += (pts[3 * i + 2] - cz) * wi;
-    wsum += wi; tsum += ts[i];
-  }
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_list; e += gridDim.x * blockDim.x) {
+  const int c = occ_list[e];
+  const double* m = mom + (int64_t)e * kCellMom;
+  const double wsum = m[0], tsum = m[1];
+  const double mu[3] = {m[2], m[3], m[4]};
+  const double s00 = m[5], s01 = m[6], s02 = m[7], s11 = m[8], s12 = m[9], s22 = m[10];
+  const int cnt = (int)m[11];
   const double w_sum = wsum + eps;
-  const double mu[3] = {m0 / w_sum, m1 / w_sum, m2 / w_sum};
-  // pass 2: weighted covariance.  Absent slots gather point 0 with weight 0 in the reference (lidar_surfel_extraction.py
-  // :115-121): they add exactly 0 to every weighted sum, so they are skipped here.
-  double s00 = 0, s01 = 0, s02 = 0, s11 = 0, s12 = 0, s22 = 0;
-  for (int o = 0; o < cnt; ++o) {
-    const int i = bucket[(int64_t)c * G.max_occ + o];
-    const double wi = w[i];
-    const double d0 = (pts[3 * i] - cx) - mu[0], d1 = (pts[3 * i + 1] - cy) - mu[1], d2 = (pts[3 * i + 2] - cz) - mu[2];
-    s00 += wi * d0 * d0; s01 += wi * d0 * d1; s02 += wi * d0 * d2;
-    s11 += wi * d1 * d1; s12 += wi * d1 * d2; s22 += wi * d2 * d2;
-  }
   Mat3 cov;
   cov(0, 0) = s00 / w_sum + eig_min; cov(1, 1) = s11 / w_sum + eig_min; cov(2, 2) = s22 / w_sum + eig_min;
   cov(0, 1) = cov(1, 0) = s01 / w_sum; cov(0, 2) = cov(2, 0) = s02 / w_sum; cov(1, 2) = cov(2, 1) = s12 / w_sum;
@@ -240,16 +307,12 @@ __global__ void __launch_bounds__(128) surfel_fit_kernel(const double* __restric
   normalize3(e1, eps);
   double e2[3] = {nn[1] * e1[2] - nn[2] * e1[1], nn[2] * e1[0] - nn[0] * e1[2], nn[0] * e1[1] - nn[1] * e1[0]};
   normalize3(e2, eps);
-  // pass 3: in-plane spreads
-  double v1 = 0.0, v2 = 0.0;
-  for (int o = 0; o < cnt; ++o) {
-    const int i = bucket[(int64_t)c * G.max_occ + o];
-    const double wi = w[i];
-    const double d0 = (pts[3 * i] - cx) - mu[0], d1 = (pts[3 * i + 1] - cy) - mu[1], d2 = (pts[3 * i + 2] - cz) - mu[2];
-    const double p1 = d0 * e1[0] + d1 * e1[1] + d2 * e1[2];
-    const double p2 = d0 * e2[0] + d1 * e2[1] + d2 * e2[2];
-    v1 += wi * (p1 * p1); v2 += wi * (p2 * p2);
-  }
+  // in-plane spreads: sum w (d . e)^2 = e^T S e with the scatter S of the moments kernel
+  auto quad = [&](const double* e) {
+    return e[0] * (s00 * e[0] + s01 * e[1] + s02 * e[2]) + e[1] * (s01 * e[0] + s11 * e[1] + s12 * e[2]) +
+           e[2] * (s02 * e[0] + s12 * e[1] + s22 * e[2]);
+  };
+  const double v1 = quad(e1), v2 = quad(e2);
   // An empty cell in the reference still gathers max_occ copies of point 0 with zero weight; all sums are 0 there too.
   const double var_e1 = v1 / w_sum + cfg.sensor_noise_var_per_axis;
   const double var_e2 = v2 / w_sum + cfg.sensor_noise_var_per_axis;
@@ -292,7 +355,9 @@ __global__ void __launch_bounds__(128) surfel_fit_kernel(const double* __restric
   F.normal[3 * c] = nrm[0]; F.normal[3 * c + 1] = nrm[1]; F.normal[3 * c + 2] = nrm[2];
   F.kappa[c] = kap; F.w[c] = wsum; F.t[c] = tsum / w_sum;  // unweighted stamp sum / weight sum, as written (:160)
   F.valid[c] = valid ? 1 : 0;
+  }   // list entries of this thread
 }
+
 
 // ---- S5 ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) surfel_select_kernel(CellFit F, SurfelGeom G, gcs_meas_batch B, double eps_lift,
@@ -433,12 +498,14 @@ static int surfels_launch(gcs_ctx* ctx, cudaStream_t st, const double* pts, cons
   G.h = cfg->voxel_size_m > 1e-12 ? cfg->voxel_size_m : 1e-12;
   const int n_keys = G.n_cells + 1;
   GCS_REQUIRE(ctx, (size_t)n_keys * sizeof(int) <= 160 * 1024, "%s: %d cells exceed the shared-memory counter", who, G.n_cells);
-  // chunks of the per-cell ranking: about two CTAs per SM over all units (the ranks do not depend on the chunking)
-  int n_chunks = (int)cdiv(n, 1024);
-  int max_chunks = (ctx->sm_count * 2 + n_units - 1) / n_units;
+  // chunks of the per-cell ranking (one warp each; the ranks do not depend on the chunking): as many as the device holds
+  // at once over all units, at least 512 points each
+  const int warps_resident = ctx->sm_count * (int)(200 * 1024 / ((size_t)n_keys * sizeof(int)) > 1 ? 200 * 1024 / ((size_t)n_keys * sizeof(int)) : 1);
+  int n_chunks = (int)cdiv(n, 512);
+  int max_chunks = (warps_resident + n_units - 1) / n_units;
   if (max_chunks < 4) max_chunks = 4;
   if (n_chunks > max_chunks) n_chunks = max_chunks;
-  const int64_t per_chunk = cdiv(cdiv(n, n_chunks), 1024) * 1024;
+  const int64_t per_chunk = cdiv(cdiv(n, n_chunks), 32) * 32;
   n_chunks = (int)cdiv(n, per_chunk);
   const int n_cblocks = (int)(cdiv(n, 8192) < 256 ? cdiv(n, 8192) : 256);
   const int64_t per_cblock = cdiv(n, n_cblocks);
@@ -450,7 +517,8 @@ static int surfels_launch(gcs_ctx* ctx, cudaStream_t st, const double* pts, cons
                o_lrank = take((size_t)n * 4), o_hist = take((size_t)n_chunks * n_keys * 4), o_total = take((size_t)n_keys * 4),
                o_bucket = take((size_t)G.n_cells * G.max_occ * 4), o_cen = take((size_t)G.n_cells * 3 * 8),
                o_sig = take((size_t)G.n_cells * 9 * 8), o_nrm = take((size_t)G.n_cells * 3 * 8), o_kap = take((size_t)G.n_cells * 8),
-               o_w = take((size_t)G.n_cells * 8), o_t = take((size_t)G.n_cells * 8), o_val = take((size_t)G.n_cells);
+               o_w = take((size_t)G.n_cells * 8), o_t = take((size_t)G.n_cells * 8), o_val = take((size_t)G.n_cells),
+               o_occ = take((size_t)G.n_cells * 4), o_nocc = take(4), o_mom = take((size_t)G.n_cells * kCellMom * 8);
   rc = gcs_ws_reserve(ctx, off);
   if (rc) return rc;
   char* ws = (char*)ctx->ws;
@@ -473,9 +541,13 @@ static int surfels_launch(gcs_ctx* ctx, cudaStream_t st, const double* pts, cons
   surfel_cell_key_kernel<<<dim3((unsigned)cdiv(n, kSurfThreads), Hu), kSurfThreads, 0, st>>>(pts, center, n, G, key, U);
   GCS_LAUNCH_CHECK(ctx);
   GCS_CHECK_CUDA(ctx, gcs_smem_attr_once((const void*)surfel_rank_chunk_kernel, 160 * 1024));
-  surfel_rank_chunk_kernel<<<dim3(n_chunks, Hu), 1024, (size_t)n_keys * sizeof(int), st>>>(key, n, per_chunk, n_keys, lrank, hist);
+  surfel_rank_chunk_kernel<<<dim3(n_chunks, Hu), 32, (size_t)n_keys * sizeof(int), st>>>(key, n, per_chunk, n_keys, lrank, hist);
   GCS_LAUNCH_CHECK(ctx);
-  surfel_rank_scan_kernel<<<dim3((n_keys + 255) / 256, Hu), 256, 0, st>>>(hist, n_chunks, n_keys, total);
+  int32_t* occ_list = (int32_t*)(ws + o_occ);
+  int32_t* n_occ = (int32_t*)(ws + o_nocc);
+  GCS_CHECK_CUDA(ctx, cudaMemsetAsync(n_occ, 0, sizeof(int32_t) * H, st));
+  surfel_rank_scan_kernel<<<dim3((n_keys + 255) / 256, Hu), 256, 0, st>>>(hist, n_chunks, n_keys, total, G.min_points, occ_list, n_occ,
+                                                                           F.valid);
   GCS_LAUNCH_CHECK(ctx);
   const int64_t nb = (int64_t)G.n_cells * G.max_occ * n_units;
   surfel_bucket_init_kernel<<<(unsigned)cdiv(nb, 256), 256, 0, st>>>(bucket, nb);
@@ -484,7 +556,16 @@ static int surfels_launch(gcs_ctx* ctx, cudaStream_t st, const double* pts, cons
                                                                                             bucket, n_chunks);
   GCS_LAUNCH_CHECK(ctx);
   gcs_timing_begin(ctx, st);
-  surfel_fit_kernel<<<dim3((G.n_cells + 127) / 128, Hu), 128, 0, st>>>(pts, timestamps, weights, center, bucket, total, G, *cfg, F, U, n_keys);
+  // groups of eight lanes / single threads stride over the occupied-cell list (a typical scan fills ~2,500 of 8,192 cells)
+  double* mom = (double*)(ws + o_mom);
+  // one list entry per group / thread for a single scan (latency), a quarter of that per unit for a batch (the list of a
+  // typical scan is short and the batch fills the device anyway)
+  const int spread = n_units >= 16 ? 4 : 1;
+  const int mom_blocks = (G.n_cells * kFitLanes / spread + 127) / 128, fit_blocks = (G.n_cells / spread + 127) / 128;
+  surfel_moments_kernel<<<dim3(mom_blocks, Hu), 128, 0, st>>>(pts, timestamps, weights, center, bucket, total, G, U, n_keys, occ_list,
+                                                              n_occ, mom);
+  GCS_LAUNCH_CHECK(ctx);
+  surfel_fit_kernel<<<dim3(fit_blocks, Hu), 128, 0, st>>>(center, G, *cfg, F, occ_list, n_occ, mom);
   gcs_timing_end(ctx, st);
   GCS_LAUNCH_CHECK(ctx);
   surfel_select_kernel<<<Hu, 1024, 0, st>>>(F, G, *batch, cfg->eps_lift, out_n_valid, total, out_count, n_keys);

@@ -26,7 +26,7 @@ Results are bit-identical to calling the operators hypothesis by hypothesis (tes
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
+import threading
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -35,7 +35,7 @@ import torch
 from . import _lib as L
 from . import constants
 from .certs import CertBundle, ExpectedEffect
-from .operators import _IO, DeskewConstantTwistResult, _deskew_cert, _pinned_like
+from .operators import _IO, DeskewConstantTwistResult, _deskew_cert
 from . import primitives as PR
 from .primitives import (CAssocResult, CMeasBatch, CMapView, CSurfelCfg, CAssocCfg, CAtlas, OT, VP, AssociationConfig,
                          AtlasMap, AtlasMapView, MeasurementBatch, PrimitiveAssociationResult, SurfelExtractionConfig,
@@ -61,21 +61,51 @@ _ROW = L.DK_NCERT + 1 + OT["NCERT"] + VP["NREC"]
 _O_DK, _O_NV, _O_OT, _O_VP = 0, L.DK_NCERT, L.DK_NCERT + 1, L.DK_NCERT + 1 + OT["NCERT"]
 
 
-@dataclass
 class HypothesisGroup:
-    """Hypotheses that share one stencil (one read-only view); stacked device results, unit axis first."""
-    units: List[int]                       # hypothesis indices, in unit order
-    tile_ids: List[int]
-    deskewed_points: torch.Tensor          # (U, n, 3)
-    deskewed_weights: torch.Tensor         # (U, n)
-    batch: MeasurementBatch                # stacked: every tensor (U, N_total, ...)
-    view: AtlasMapView
-    association: PrimitiveAssociationResult  # stacked (U, N_total, K)
-    L_pose: torch.Tensor                   # (U, 22, 22)
-    h_pose: torch.Tensor                   # (U, 22)
-    rec: torch.Tensor                      # (U, GCS_VP_NREC)
-    scalars: Optional[np.ndarray] = None   # host copy of the packed certificate rows (U, _ROW) after the synchronisation
-    view_scalars: Optional[np.ndarray] = None  # [n_valid of the view, 4 inflation statistics]
+    """
+    Hypotheses that share one stencil (one read-only view).  The stacked device results (unit axis first) live in one
+    arena allocation; the tensor views below are made on first access, not per call.
+      deskewed_points (U, n, 3), deskewed_weights (U, n), batch: MeasurementBatch with every tensor (U, N_total, ...),
+      view: AtlasMapView, association: PrimitiveAssociationResult (U, N_total, K), L_pose (U, 22, 22), h_pose (U, 22),
+      rec (U, GCS_VP_NREC)
+    """
+
+    def __init__(self, units, tile_ids, arena, n_scalar_bytes, scfg, n_camera_valid, m_tile_view):
+        self.units, self.tile_ids, self._arena = list(units), [int(x) for x in tile_ids], arena
+        self._scal_d = arena.buf[:n_scalar_bytes]
+        self._scfg, self._n_cam, self._m_view = scfg, int(n_camera_valid), int(m_tile_view)
+        self.scalars: Optional[np.ndarray] = None       # host copy of the packed certificate rows (U, _ROW) after wait()
+        self.view_scalars: Optional[np.ndarray] = None  # [n_valid of the view, 4 inflation statistics]
+        self._view_n_valid = -1
+        self._cache = {}
+
+    def _lazy(self, key, make):
+        if key not in self._cache:
+            self._cache[key] = make()
+        return self._cache[key]
+
+    deskewed_points = property(lambda self: self._lazy("dk_pts", lambda: self._arena.view("dk_pts")))
+    deskewed_weights = property(lambda self: self._lazy("dk_w", lambda: self._arena.view("dk_w")))
+    L_pose = property(lambda self: self._lazy("L22", lambda: self._arena.view("L22")))
+    h_pose = property(lambda self: self._lazy("h22", lambda: self._arena.view("h22")))
+    rec = property(lambda self: self._lazy("rec", lambda: self._arena.view("rec")))
+
+    @property
+    def batch(self) -> MeasurementBatch:
+        return self._lazy("batch", lambda: MeasurementBatch(
+            **{f: self._arena.view("b_" + f) for f, _, _ in _BATCH_FIELDS}, n_feat=self._scfg.n_feat, n_surfel=self._scfg.n_surfel,
+            n_camera_valid=self._n_cam, n_lidar_valid=-1))
+
+    @property
+    def view(self) -> AtlasMapView:
+        v = self._lazy("view", lambda: AtlasMapView(**{f: self._arena.view("v_" + f) for f, _, _ in _VIEW_FIELDS},
+                                                    tile_ids=list(self.tile_ids), m_tile_view=self._m_view))
+        v.n_valid = self._view_n_valid
+        return v
+
+    @property
+    def association(self) -> PrimitiveAssociationResult:
+        return self._lazy("assoc", lambda: PrimitiveAssociationResult(**{f: self._arena.view("a_" + f) for f, _, _ in _ASSOC_FIELDS}))
 
 
 class BatchedPrimitiveEvidence:
@@ -88,11 +118,15 @@ class BatchedPrimitiveEvidence:
 
     def __init__(self, n_hyp, groups, first, cfg):
         self.n_hyp, self.groups, self.first, self._cfg = n_hyp, groups, first, cfg
+        self._pending = None
         self._where: Dict[int, tuple] = {}
         for g in groups:
             for k, h in enumerate(g.units):
                 self._where[h] = (g, k)
         dev = cfg["dev"]
+        if first is None and len(groups) == 1 and groups[0].units == list(range(n_hyp)):
+            self.L_pose, self.h_pose = groups[0].L_pose, groups[0].h_pose    # one stencil: the group's arrays are the stack
+            return
         self.L_pose = torch.empty(n_hyp, 22, 22, dtype=F64, device=dev)
         self.h_pose = torch.empty(n_hyp, 22, dtype=F64, device=dev)
         if first is not None:
@@ -107,11 +141,29 @@ class BatchedPrimitiveEvidence:
                 self.L_pose.index_copy_(0, ix, g.L_pose)
                 self.h_pose.index_copy_(0, ix, g.h_pose)
 
+    def wait(self):
+        """Block until the certificates of every hypothesis are on the host (idempotent)."""
+        if self._pending is None:
+            return self
+        self._event.synchronize()
+        dev = self._cfg["dev"]
+        for g, b1 in zip(self.groups, self._pending):
+            _unpack_scalars(g, b1.numpy().copy())
+            g._view_n_valid = int(g.view_scalars[0])
+            # the reference's early exits (empty measurement batch / empty view): evidence = eps_lift * I, h = 0
+            for k, hh in enumerate(g.units):
+                if g._view_n_valid == 0 or g._n_cam + int(round(g.scalars[k, _O_NV])) == 0:
+                    self.L_pose[hh] = self._eps_lift * torch.eye(22, dtype=F64, device=dev)
+                    self.h_pose[hh] = 0.0
+        self._pending = None
+        return self
+
     @property
     def map_update(self):
         return None if self.first is None else self.first["map_update"]
 
     def unit(self, h: int) -> dict:
+        self.wait()
         if self.first is not None and h == 0:
             return self.first
         g, k = self._where[int(h)]
@@ -144,67 +196,157 @@ class BatchedPrimitiveEvidence:
                     pose_evidence=pe_out, map_update=None)
 
 
-def _stack_batch(io, base: Optional[MeasurementBatch], U: int, cfg: SurfelExtractionConfig) -> MeasurementBatch:
-    """U copies of the camera slice (base_batch) stacked along a new unit axis; LiDAR rows zero."""
-    if base is None:
-        base = PR.create_empty_measurement_batch(cfg.n_feat, cfg.n_surfel, io.dev)
-    if base.n_surfel != cfg.n_surfel or base.n_feat != cfg.n_feat:
-        raise ValueError("lidar_evidence_primitives_batched: base_batch budget differs from the surfel config")
-    kw = {}
-    for f in base.__dataclass_fields__:
-        v = getattr(base, f)
-        kw[f] = v.unsqueeze(0).expand((U,) + tuple(v.shape)).contiguous() if isinstance(v, torch.Tensor) else v
-    return MeasurementBatch(**kw)
+class CPrimBatchArgs(C.Structure):
+    """gcs_prim_batch_args (include/gcs_b200.h)."""
+    _fields_ = [("pts", _vp), ("t", _vp), ("w", _vp), ("n", _i64), ("n_units", _i32), ("inflate", _i32), ("xi", _vp), ("poses", _vp),
+                ("scan_start_time", _dbl), ("scan_end_time", _dbl), ("dk_pts", _vp), ("dk_w", _vp), ("dk_cert", _vp),
+                ("surfel_cfg", CSurfelCfg), ("base", CMeasBatch), ("batch", CMeasBatch), ("n_lidar_valid", _vp),
+                ("atlas", C.POINTER(CAtlas)), ("tile_index", _i32 * 16), ("tile_ids", _i64 * 16), ("n_tiles", _i32),
+                ("m_tile_view", _i32), ("eps_lift", _dbl), ("eps_mass", _dbl), ("recency_min_scale", _dbl), ("view", CMapView),
+                ("view_n_valid", _vp), ("inflate_stats", _vp), ("assoc_cfg", CAssocCfg), ("assoc", CAssocResult), ("ot_cert", _vp),
+                ("L22", _vp), ("h22", _vp), ("rec", _vp)]
+
+
+L.register_prototypes({"gcs_lidar_evidence_primitives_batched": (_int, [_vp, _vp, C.POINTER(CPrimBatchArgs)])})
+
+_DT = {F64: 8, torch.int32: 4, torch.int64: 8, torch.uint8: 1}
+
+
+class _Arena:
+    """One device allocation per call, carved into the stacked result arrays; tensor views are made on access only."""
+
+    def __init__(self, dev):
+        self.dev, self.spec, self.size, self.buf = dev, {}, 0, None
+
+    def add(self, name, shape, dtype=F64):
+        nbytes = int(np.prod(shape)) * _DT[dtype]
+        self.spec[name] = (self.size, tuple(int(x) for x in shape), dtype, nbytes)
+        self.size += (nbytes + 255) & ~255
+
+    def alloc(self):
+        self.buf = torch.empty(self.size, dtype=torch.uint8, device=self.dev)
+        self.base = self.buf.data_ptr()
+
+    def ptr(self, name):
+        return _vp(self.base + self.spec[name][0])
+
+    def view(self, name):
+        off, shape, dtype, nbytes = self.spec[name]
+        return self.buf[off:off + nbytes].view(dtype).reshape(shape)
+
+
+_BATCH_FIELDS = (("Lambdas", (3, 3), F64), ("thetas", (3,), F64), ("etas", (constants.GC_VMF_N_LOBES, 3), F64), ("weights", (), F64),
+                 ("sources", (), torch.int32), ("source_indices", (), torch.int32), ("valid_mask", (), torch.uint8),
+                 ("timestamps", (), F64), ("colors", (3,), F64))
+_VIEW_FIELDS = (("candidate_tile_ids", (), torch.int64), ("candidate_slots", (), torch.int32), ("valid_mask", (), torch.uint8),
+                ("positions", (3,), F64), ("covariances", (3, 3), F64), ("directions", (3,), F64), ("kappas", (), F64),
+                ("weights", (), F64), ("primitive_ids", (), torch.int64), ("last_supported_scan_seq", (), torch.int64),
+                ("etas", (constants.GC_VMF_N_LOBES, 3), F64), ("colors", (3,), F64))
+_ASSOC_FIELDS = (("responsibilities", True, F64), ("candidate_pool_indices", True, torch.int32), ("candidate_tile_ids", True, torch.int64),
+                 ("candidate_slots", True, torch.int64), ("row_masses", False, F64), ("cost_matrix", True, F64))
+_C_BATCH_NAME = dict(valid_mask="valid")
+_C_VIEW_NAME = dict(valid_mask="valid")
 
 
 def _run_group(io, units, tile_ids, pts, t, w, n, xi_d, poses_d, t0, t1, atlas_map, scan_seq, base_batch, scfg, acfg, m_tile_view,
-               eps_lift, eps_mass, min_scale) -> HypothesisGroup:
+               eps_lift, eps_mass, min_scale, inflate=True) -> HypothesisGroup:
     U = len(units)
-    lib, h, st = io.ctx.lib, io.ctx.handle, io.stream()
     N, K = scfg.n_feat + scfg.n_surfel, int(acfg.k_assoc)
-    sel = None if units == list(range(units[0], units[0] + U)) else torch.tensor(units, device=io.dev)
-    xi_g = xi_d[units[0]:units[0] + U] if sel is None else xi_d.index_select(0, sel)
-    po_g = poses_d[units[0]:units[0] + U] if sel is None else poses_d.index_select(0, sel)
-    scal = io.empty(U, _ROW)
-    vscal = io.zeros(8)
-    dk_cert = io.empty(U, L.DK_NCERT)
-    dk_p, dk_w = io.empty(U, n, 3), io.empty(U, n)
-    io.ctx.check(lib.gcs_deskew_constant_twist_batched(h, st, L.ptr(pts), L.ptr(t), L.ptr(w), n, L.ptr(xi_g.contiguous()), U,
-                                                       float(t0), float(t1), L.ptr(dk_p), L.ptr(dk_w), L.ptr(dk_cert)))
-    batch = _stack_batch(io, base_batch, U, scfg)
-    nv_d = io.zeros(U, dtype=torch.int32)
-    cb, cc = batch._c(), scfg._c()
-    io.ctx.check(lib.gcs_extract_lidar_surfels_batched(h, st, L.ptr(dk_p), L.ptr(t), L.ptr(dk_w), n, U, 1, C.byref(cc), C.byref(cb),
-                                                       L.ptr(nv_d)))
-    view = PR._empty_view(io, tile_ids, m_tile_view)
-    nvv = vscal[5:6].view(torch.int32)        # 2 int32 words inside the packed buffer; [0] = n_valid of the view
-    ca, cv = atlas_map._c(), view._c()
+    P = len(tile_ids) * int(m_tile_view)
+    if base_batch is None:
+        base_batch = PR.create_empty_measurement_batch(scfg.n_feat, scfg.n_surfel, io.dev)
+    if base_batch.n_surfel != scfg.n_surfel or base_batch.n_feat != scfg.n_feat:
+        raise ValueError("lidar_evidence_primitives_batched: base_batch budget differs from the surfel config")
+    if units == list(range(units[0], units[0] + U)):
+        xi_g, po_g = xi_d[units[0]:units[0] + U], poses_d[units[0]:units[0] + U]
+    else:
+        sel = torch.tensor(units, device=io.dev)
+        xi_g, po_g = xi_d.index_select(0, sel), poses_d.index_select(0, sel)
+    A = _Arena(io.dev)
+    # packed certificate scalars first (one contiguous device -> host copy): _ROW float64 words per unit, then the view's
+    A.add("dk_cert", (U, L.DK_NCERT)); A.add("n_valid", (U,), torch.int32); A.add("ot_cert", (U, OT["NCERT"])); A.add("rec", (U, VP["NREC"]))
+    A.add("view_n_valid", (2,), torch.int32); A.add("inflate_stats", (4,))
+    n_scalar_bytes = A.size
+    A.add("dk_pts", (U, n, 3)); A.add("dk_w", (U, n))
+    for f, shp, dt in _BATCH_FIELDS:
+        A.add("b_" + f, (U, N) + shp, dt)
+    for f, shp, dt in _VIEW_FIELDS:
+        A.add("v_" + f, (P,) + shp, dt)
+    for f, has_k, dt in _ASSOC_FIELDS:
+        A.add("a_" + f, (U, N, K) if has_k else (U, N), dt)
+    A.add("L22", (U, 22, 22)); A.add("h22", (U, 22))
+    A.alloc()
+    A.buf[:n_scalar_bytes].zero_()
+    a = CPrimBatchArgs()
+    a.pts, a.t, a.w, a.n, a.n_units, a.inflate = L.ptr(pts), L.ptr(t), L.ptr(w), n, U, 1 if inflate else 0
+    a.xi, a.poses = L.ptr(xi_g.contiguous()), L.ptr(po_g.contiguous())
+    a.scan_start_time, a.scan_end_time = float(t0), float(t1)
+    a.dk_pts, a.dk_w, a.dk_cert = A.ptr("dk_pts"), A.ptr("dk_w"), A.ptr("dk_cert")
+    a.surfel_cfg = scfg._c()
+    a.base = base_batch._c()
+    for f, _, _ in _BATCH_FIELDS:
+        setattr(a.batch, _C_BATCH_NAME.get(f, f), A.ptr("b_" + f))
+    a.batch.n_feat, a.batch.n_surfel = scfg.n_feat, scfg.n_surfel
+    a.n_lidar_valid = A.ptr("n_valid")
+    ca = atlas_map._c()
+    a.atlas = C.pointer(ca)
     idx = atlas_map.index_list(tile_ids, create=False)
-    io.ctx.check(lib.gcs_extract_atlas_map_view_inflated(h, st, C.byref(ca), _i32arr(idx), _i64arr(tile_ids), len(tile_ids),
-                                                         int(m_tile_view), float(eps_lift), float(eps_mass), int(scan_seq),
-                                                         float(acfg.recency_decay_lambda), float(min_scale), C.byref(cv),
-                                                         L.ptr(nvv), L.ptr(vscal[0:4])))
-    z = io.empty
-    assoc = PrimitiveAssociationResult(responsibilities=z(U, N, K), candidate_pool_indices=z(U, N, K, dtype=torch.int32),
-                                       candidate_tile_ids=z(U, N, K, dtype=torch.int64), candidate_slots=z(U, N, K, dtype=torch.int64),
-                                       row_masses=z(U, N), cost_matrix=z(U, N, K))
-    ot_cert = io.empty(U, OT["NCERT"])
-    cfg_c = PR._c_assoc_cfg(acfg, eps_lift)
-    cr = assoc._c()
-    io.ctx.check(lib.gcs_associate_primitives_ot_batched(h, st, C.byref(cb), U, C.byref(cv), _i64arr(tile_ids), len(tile_ids),
-                                                         int(m_tile_view), C.byref(cfg_c), C.byref(cr), L.ptr(ot_cert)))
-    L22, h22, rec = io.empty(U, 22, 22), io.empty(U, 22), io.empty(U, VP["NREC"])
-    io.ctx.check(lib.gcs_visual_pose_evidence_batched(h, st, C.byref(cb), U, C.byref(cv), C.byref(cr), K, L.ptr(po_g.contiguous()),
-                                                      float(eps_lift), float(eps_mass), L.ptr(L22), L.ptr(h22), L.ptr(rec)))
-    # one packed row of certificate scalars per unit
-    scal[:, _O_DK:_O_DK + L.DK_NCERT] = dk_cert
-    scal[:, _O_NV] = nv_d.to(F64)
-    scal[:, _O_OT:_O_OT + OT["NCERT"]] = ot_cert
-    scal[:, _O_VP:_O_VP + VP["NREC"]] = rec
-    g = HypothesisGroup(units=list(units), tile_ids=[int(x) for x in tile_ids], deskewed_points=dk_p, deskewed_weights=dk_w,
-                        batch=batch, view=view, association=assoc, L_pose=L22, h_pose=h22, rec=rec)
-    g._scal_d, g._vscal_d = scal, vscal
-    return g
+    for k in range(len(tile_ids)):
+        a.tile_index[k], a.tile_ids[k] = int(idx[k]), int(tile_ids[k])
+    a.n_tiles, a.m_tile_view = len(tile_ids), int(m_tile_view)
+    a.eps_lift, a.eps_mass, a.recency_min_scale = float(eps_lift), float(eps_mass), float(min_scale)
+    for f, _, _ in _VIEW_FIELDS:
+        setattr(a.view, _C_VIEW_NAME.get(f, f), A.ptr("v_" + f))
+    a.view_n_valid, a.inflate_stats = A.ptr("view_n_valid"), A.ptr("inflate_stats")
+    a.assoc_cfg = PR._c_assoc_cfg(acfg, eps_lift)
+    for f, _, _ in _ASSOC_FIELDS:
+        setattr(a.assoc, f, A.ptr("a_" + f))
+    a.ot_cert, a.L22, a.h22, a.rec = A.ptr("ot_cert"), A.ptr("L22"), A.ptr("h22"), A.ptr("rec")
+    io.ctx.check(io.ctx.lib.gcs_lidar_evidence_primitives_batched(io.ctx.handle, io.stream(), C.byref(a)))
+    del xi_g, po_g
+    return HypothesisGroup(units, tile_ids, A, n_scalar_bytes, scfg, base_batch.n_camera_valid, m_tile_view)
+
+
+def _unpack_scalars(g: HypothesisGroup, host_bytes: np.ndarray):
+    """Host copy of the arena's scalar region -> per-unit rows in the _ROW layout + the view's scalars."""
+    A, U = g._arena, len(g.units)
+
+    def part(name, dtype):
+        off, shape, _, nbytes = A.spec[name]
+        return host_bytes[off:off + nbytes].view(dtype).reshape(shape)
+    rows = np.empty((U, _ROW))
+    rows[:, _O_DK:_O_DK + L.DK_NCERT] = part("dk_cert", np.float64)
+    rows[:, _O_NV] = part("n_valid", np.int32)
+    rows[:, _O_OT:_O_OT + OT["NCERT"]] = part("ot_cert", np.float64)
+    rows[:, _O_VP:_O_VP + VP["NREC"]] = part("rec", np.float64)
+    g.scalars = rows
+    g.view_scalars = np.concatenate([[float(part("view_n_valid", np.int32)[0])], part("inflate_stats", np.float64)])
+
+
+class _PinnedRing:
+    """Small pinned host buffers handed out round-robin per (thread, size): staging for asynchronous copies in both
+    directions (a pageable cudaMemcpy waits for everything enqueued before it, which would serialise back-to-back scans)."""
+    _tls = threading.local()
+
+    @classmethod
+    def get(cls, nbytes: int, depth: int = 8) -> torch.Tensor:
+        ring = getattr(cls._tls, "ring", None)
+        if ring is None:
+            ring = cls._tls.ring = {}
+        slot = ring.setdefault(int(nbytes), [[], 0])
+        if len(slot[0]) < depth:
+            slot[0].append(torch.empty(int(nbytes), dtype=torch.uint8).pin_memory())
+            return slot[0][-1]
+        slot[1] = (slot[1] + 1) % depth
+        return slot[0][slot[1]]
+
+
+def _h2d_async(io, a: np.ndarray, shape) -> torch.Tensor:
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    stage = _PinnedRing.get(a.nbytes)
+    stage.view(F64).copy_(torch.from_numpy(a).reshape(-1))
+    io.h2d += a.nbytes
+    return stage.view(F64).to(io.dev, non_blocking=True).reshape(shape)
 
 
 def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_time: float, scan_end_time: float, xi_bodies,
@@ -217,12 +359,14 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
                                       eps_mass: float = constants.GC_EPS_MASS,
                                       recency_min_scale: float = constants.GC_RECENCY_MIN_SCALE,
                                       chart_id: str = constants.GC_CHART_ID,
-                                      anchor_id: str = "lidar_evidence_primitives") -> BatchedPrimitiveEvidence:
+                                      anchor_id: str = "lidar_evidence_primitives", defer: bool = False
+                                      ) -> BatchedPrimitiveEvidence:
     """
     Primitive-family LiDAR evidence of H pose hypotheses of one scan (module docstring).  ``xi_bodies`` (H, 6): twist of
     every hypothesis (host array or device tensor, e.g. the rows gcs_imu_scan_twist wrote); ``poses_pred`` (H, 6)
     [t, rotvec] predicted world poses (map stencil centre + linearisation point).  ``update_map``: hypothesis 0 updates
-    the map first (the reference's order); False: every hypothesis sees the current map read-only.
+    the map first (the reference's order); False: every hypothesis sees the current map read-only.  ``defer``: return
+    as soon as everything is enqueued; ``out.wait()`` (or the first ``out.unit(h)``) blocks for the certificates.
     """
     io = _IO(atlas_map.device)
     pts = io.dev_in(points, shape=(-1, 3))
@@ -231,12 +375,16 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
     w = io.dev_in(weights, shape=(-1,))
     if t.shape[0] != n or w.shape[0] != n:
         raise ValueError("lidar_evidence_primitives_batched: points/timestamps/weights length mismatch")
-    xi_d = io.dev_in(xi_bodies, shape=(-1, 6))
+    xi_d = (io.dev_in(xi_bodies, shape=(-1, 6)) if isinstance(xi_bodies, torch.Tensor)
+            else _h2d_async(io, np.asarray(xi_bodies, np.float64).reshape(-1, 6), (-1, 6)))
     H = int(xi_d.shape[0])
+    # the stencil of every hypothesis is decided on the host (as the reference does, pipeline.py:808-829): poses given as a
+    # device tensor cost one blocking read here -- pass host poses to keep back-to-back scans asynchronous
     poses_h = (poses_pred.detach().cpu().numpy() if isinstance(poses_pred, torch.Tensor) else np.asarray(poses_pred, np.float64)).reshape(-1, 6)
     if poses_h.shape[0] != H or H < 1:
         raise ValueError(f"lidar_evidence_primitives_batched: {H} twists but {poses_h.shape[0]} poses")
-    poses_d = io.dev_in(poses_pred, shape=(-1, 6))
+    poses_d = (io.dev_in(poses_pred, shape=(-1, 6)) if isinstance(poses_pred, torch.Tensor) and poses_pred.is_cuda
+               else _h2d_async(io, poses_h, (-1, 6)))
     scfg = surfel_config if surfel_config is not None else SurfelExtractionConfig()
     acfg = association_config if association_config is not None else AssociationConfig(scan_seq=int(scan_seq))
     PR._check_assoc_config(acfg)
@@ -260,25 +408,16 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
     cfg = dict(dev=io.dev, chart_id=chart_id, anchor_id=anchor_id, ess_imu=ess_imu, surfel=scfg, assoc=acfg, eps_lift=eps_lift,
                atlas=atlas_map, timestamps=t)
     out = BatchedPrimitiveEvidence(H, groups, first, cfg)
-    # ONE synchronisation for the certificates of every hypothesis
-    bufs = []
-    for k, g in enumerate(groups):
-        b1, b2 = _pinned_like(g._scal_d, ("hb", k, 0)), _pinned_like(g._vscal_d, ("hb", k, 1))
-        b1.copy_(g._scal_d.reshape(-1), non_blocking=True)
-        b2.copy_(g._vscal_d, non_blocking=True)
-        bufs.append((b1, b2))
-    if groups:
-        torch.cuda.current_stream(io.dev).synchronize()
-    for g, (b1, b2) in zip(groups, bufs):
-        g.scalars = b1.numpy().reshape(len(g.units), _ROW).copy()
-        vs = b2.numpy().copy()
-        g.view_scalars = np.concatenate([[float(vs[5:6].view(np.int32)[0])], vs[0:4]])
-        g.view.n_valid = int(g.view_scalars[0])
-        g.batch.n_lidar_valid = -1             # per unit: see unit(h)
-        # the reference's early exits (empty measurement batch / empty view): evidence = eps_lift * I, h = 0
-        n_cam = g.batch.n_camera_valid
-        for k, hh in enumerate(g.units):
-            if g.view.n_valid == 0 or n_cam + int(round(g.scalars[k, _O_NV])) == 0:
-                out.L_pose[hh] = eps_lift * torch.eye(22, dtype=F64, device=io.dev)
-                out.h_pose[hh] = 0.0
+    # ONE synchronisation for the certificates of every hypothesis: the packed scalars go to pinned memory behind the
+    # kernels; `defer` leaves the wait to the caller (out.wait()), so that the next scan can be enqueued meanwhile
+    out._pending = []
+    for g in groups:
+        b1 = _PinnedRing.get(g._scal_d.numel())
+        b1.copy_(g._scal_d, non_blocking=True)
+        out._pending.append(b1)
+    out._event = torch.cuda.Event()
+    out._event.record(torch.cuda.current_stream(io.dev))
+    out._eps_lift = eps_lift
+    if not defer:
+        out.wait()
     return out

@@ -504,6 +504,50 @@ int gcs_visual_pose_evidence_batched(gcs_ctx* ctx, void* stream, const gcs_meas_
                                      const double* poses /*dev (n_units,6) [t,rotvec]*/, double eps_lift, double eps_mass,
                                      double* out_L22, double* out_h22, double* out_rec);
 
+/* ---- the hypothesis loop of one scan in ONE call (fl/backend/backend_node.py:2036-2066 around the primitive-family
+ *      steps of process_scan_single_hypothesis, fl/backend/pipeline.py:569-587, 780-877, 998-1010): n_units hypotheses
+ *      that share one stencil -- deskew with every twist, surfels of every deskewed cloud, ONE read-only view (recency
+ *      inflation applied functionally when `inflate` is set), association, pose evidence.  Runs
+ *      gcs_deskew_constant_twist_batched, gcs_extract_lidar_surfels_batched, gcs_extract_atlas_map_view[_inflated],
+ *      gcs_associate_primitives_ot_batched, gcs_visual_pose_evidence_batched in this order on `stream`; results are
+ *      bit-identical to calling them (or the single-hypothesis entries, hypothesis by hypothesis).  No host
+ *      synchronisation, no host -> device copy: the sequence can be captured in a CUDA graph.  All pointers (dev) unless
+ *      noted; stacked arrays hold unit u at offset u * (rows of one unit).                                          */
+typedef struct {
+  const double* pts;      /* (n,3) raw points, shared by all units */
+  const double* t;        /* (n)   */
+  const double* w;        /* (n)   */
+  int64_t n;
+  int32_t n_units;
+  int32_t inflate;        /* 1: view of the recency-inflated map (map itself untouched), 0: view of the map as it is */
+  const double* xi;       /* (n_units,6) twists   */
+  const double* poses;    /* (n_units,6) [t, rotvec] predicted poses (linearisation points) */
+  double scan_start_time, scan_end_time;
+  double* dk_pts;         /* out (n_units,n,3) */
+  double* dk_w;           /* out (n_units,n)   */
+  double* dk_cert;        /* out (n_units, GCS_DK_NCERT) */
+  gcs_surfel_cfg surfel_cfg;
+  gcs_meas_batch base;    /* camera slice + zero LiDAR rows, (Nt) rows: copied into every unit before the surfels are written;
+                             base.Lambdas == NULL: the stacked batch is taken as the caller prepared it                 */
+  gcs_meas_batch batch;   /* out, stacked: unit 0's pointers */
+  int32_t* n_lidar_valid; /* out (n_units) */
+  const gcs_atlas* atlas; /* host struct */
+  int32_t tile_index[16]; /* pool rows of the stencil tiles (-1: tile missing) */
+  int64_t tile_ids[16];
+  int32_t n_tiles, m_tile_view;
+  double eps_lift, eps_mass, recency_min_scale;
+  gcs_map_view view;      /* out (n_tiles * m_tile_view rows) */
+  int32_t* view_n_valid;  /* out int32[1] */
+  double* inflate_stats;  /* out double[4] (written when inflate != 0) */
+  gcs_assoc_cfg assoc_cfg;
+  gcs_assoc_result assoc; /* out, stacked */
+  double* ot_cert;        /* out (n_units, GCS_OT_NCERT) */
+  double* L22;            /* out (n_units,22,22) */
+  double* h22;            /* out (n_units,22)    */
+  double* rec;            /* out (n_units, GCS_VP_NREC) */
+} gcs_prim_batch_args;
+int gcs_lidar_evidence_primitives_batched(gcs_ctx* ctx, void* stream, const gcs_prim_batch_args* args /*host*/);
+
 /* ---- a14 map update = pipeline step 12b : fl/backend/pipeline.py:1233-1447 with primitive_map_fuse /
  *      insert_masked / cull / forget (fl/backend/structures/primitive_map.py:807-1384).  This is what survives of
  *      "PoseCovInflationPushforward" (README.md:119).  merge_reduce is not run: it is a no-op for tiles larger than
