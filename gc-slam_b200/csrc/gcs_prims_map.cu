@@ -770,7 +770,9 @@ __global__ void __launch_bounds__(kPeThreads) pose_evidence_kernel(gcs_meas_batc
                                                              double p0, double p1, double p2, double r0, double r1,
                                                              double r2, double eps_lift, double eps_mass,
                                                              double* __restrict__ L22, double* __restrict__ h22,
-                                                             double* __restrict__ rec, const double* __restrict__ poses_dev) {
+                                                             double* __restrict__ rec, const double* __restrict__ poses_dev,
+                                                             const int32_t* __restrict__ n_lidar_valid, int n_camera_valid,
+                                                             const int32_t* __restrict__ view_n_valid) {
   __shared__ double tot[28];
   const int tid = threadIdx.x;
   if (poses_dev) {                           // blockIdx.x = unit: its own pose, batch, association and outputs
@@ -780,6 +782,21 @@ __global__ void __launch_bounds__(kPeThreads) pose_evidence_kernel(gcs_meas_batc
     B = meas_batch_unit(B, u);
     R = assoc_result_unit(R, u, N, K);
     L22 += u * 22 * 22; h22 += u * 22; rec += u * GCS_VP_NREC;
+    // The reference's early exits, taken on the device (the host cannot look before a batch of hypotheses has been
+    // enqueued): an empty measurement batch or an empty view give the all-zero association of
+    // primitive_association.py:275-290 and the evidence eps_lift * I, h = 0 of visual_pose_evidence.py:300-330 -- whatever
+    // the association kernels computed from 1e12 costs is overwritten, so the map update of this unit fuses nothing.
+    if (n_lidar_valid && view_n_valid && (view_n_valid[0] == 0 || n_camera_valid + n_lidar_valid[u] == 0)) {
+      for (int e = tid; e < N * K; e += kPeThreads) {
+        R.responsibilities[e] = 0.0; R.cost_matrix[e] = 0.0; R.candidate_pool_indices[e] = 0;
+        R.candidate_tile_ids[e] = 0; R.candidate_slots[e] = 0;
+      }
+      for (int e = tid; e < N; e += kPeThreads) R.row_masses[e] = 0.0;
+      for (int e = tid; e < 22 * 22; e += kPeThreads) L22[e] = (e / 22 == e % 22) ? eps_lift : 0.0;
+      if (tid < 22) h22[tid] = 0.0;
+      for (int e = tid; e < GCS_VP_NREC; e += kPeThreads) rec[e] = 0.0;
+      return;
+    }
   }
   const double rv[3] = {r0, r1, r2}, tp[3] = {p0, p1, p2};
   const Mat3 Rp = so3_exp(rv);
@@ -1508,7 +1525,7 @@ int gcs_visual_pose_evidence(gcs_ctx* ctx, void* stream, const gcs_meas_batch* b
   const int N = batch->n_feat + batch->n_surfel;
   pose_evidence_kernel<8><<<1, kPeThreads, 0, (cudaStream_t)stream>>>(*batch, N, *view, *assoc, pose6[0], pose6[1], pose6[2], pose6[3],
                                                                 pose6[4], pose6[5], eps_lift, eps_mass, out_L22, out_h22, out_rec,
-                                                                nullptr);
+                                                                nullptr, nullptr, 0, nullptr);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
 }
@@ -1516,7 +1533,8 @@ int gcs_visual_pose_evidence(gcs_ctx* ctx, void* stream, const gcs_meas_batch* b
 int gcs_visual_pose_evidence_batched(gcs_ctx* ctx, void* stream, const gcs_meas_batch* batch, int32_t n_units,
                                      const gcs_map_view* view, const gcs_assoc_result* assoc, int32_t k_assoc,
                                      const double* poses_dev, double eps_lift, double eps_mass, double* out_L22,
-                                     double* out_h22, double* out_rec) {
+                                     double* out_h22, double* out_rec, const int32_t* n_lidar_valid,
+                                     int32_t n_camera_valid, const int32_t* view_n_valid) {
   if (!ctx) return GCS_EINVAL;
   GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
   int rc = check_mbatch(ctx, batch, "visual_pose_evidence_batched");
@@ -1529,7 +1547,8 @@ int gcs_visual_pose_evidence_batched(gcs_ctx* ctx, void* stream, const gcs_meas_
   GCS_REQUIRE(ctx, k_assoc == 8, "visual_pose_evidence_batched: k_assoc=%d (this build instantiates K_ASSOC=8)", k_assoc);
   const int N = batch->n_feat + batch->n_surfel;
   pose_evidence_kernel<8><<<(unsigned)n_units, kPeThreads, 0, (cudaStream_t)stream>>>(*batch, N, *view, *assoc, 0, 0, 0, 0, 0, 0, eps_lift,
-                                                                                     eps_mass, out_L22, out_h22, out_rec, poses_dev);
+                                                                                     eps_mass, out_L22, out_h22, out_rec, poses_dev,
+                                                                                     n_lidar_valid, n_camera_valid, view_n_valid);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
 }
@@ -1569,7 +1588,8 @@ int gcs_lidar_evidence_primitives_batched(gcs_ctx* ctx, void* stream, const gcs_
                                            &a->assoc_cfg, &a->assoc, a->ot_cert);
   if (rc) return rc;
   return gcs_visual_pose_evidence_batched(ctx, stream, &a->batch, a->n_units, &a->view, &a->assoc, a->assoc_cfg.k_assoc, a->poses,
-                                          a->eps_lift, a->eps_mass, a->L22, a->h22, a->rec);
+                                          a->eps_lift, a->eps_mass, a->L22, a->h22, a->rec, a->n_lidar_valid, a->n_camera_valid,
+                                          a->view_n_valid);
 }
 
 int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int32_t* tile_index, const int64_t* tile_ids,

@@ -53,7 +53,7 @@ L.register_prototypes({
     "gcs_associate_primitives_ot_batched": (_int, [_vp, _vp, C.POINTER(CMeasBatch), _i32, C.POINTER(CMapView), C.POINTER(_i64), _i32,
                                                    _i32, C.POINTER(CAssocCfg), C.POINTER(CAssocResult), _vp]),
     "gcs_visual_pose_evidence_batched": (_int, [_vp, _vp, C.POINTER(CMeasBatch), _i32, C.POINTER(CMapView), C.POINTER(CAssocResult),
-                                                _i32, _vp, _dbl, _dbl, _vp, _vp, _vp]),
+                                                _i32, _vp, _dbl, _dbl, _vp, _vp, _vp, _vp, _i32, _vp]),
 })
 
 # layout of one unit's row in the packed certificate buffer (float64 words)
@@ -113,25 +113,24 @@ class BatchedPrimitiveEvidence:
     Per-hypothesis results of ``lidar_evidence_primitives_batched``.  ``L_pose`` (H, 22, 22) / ``h_pose`` (H, 22) are
     the stacked evidence in hypothesis order (the input of fusion.evidence_fusion_batched); ``unit(h)`` assembles the
     same dict of operator tuples ``primitives.lidar_evidence_primitives`` returns for one hypothesis (certificate
-    objects are only built on access).
+    objects are only built on access); ``map_update`` is hypothesis 0's (result, cert, effect) when the map was updated.
     """
 
-    def __init__(self, n_hyp, groups, first, cfg):
-        self.n_hyp, self.groups, self.first, self._cfg = n_hyp, groups, first, cfg
+    def __init__(self, n_hyp, groups, cfg):
+        self.n_hyp, self.groups, self._cfg = n_hyp, groups, cfg
         self._pending = None
+        self._gens = {}          # "inflate" / "update": (generator at its yield, pinned host buffer, shape)
+        self._first_extra = None
         self._where: Dict[int, tuple] = {}
         for g in groups:
             for k, h in enumerate(g.units):
                 self._where[h] = (g, k)
         dev = cfg["dev"]
-        if first is None and len(groups) == 1 and groups[0].units == list(range(n_hyp)):
+        if len(groups) == 1 and groups[0].units == list(range(n_hyp)):
             self.L_pose, self.h_pose = groups[0].L_pose, groups[0].h_pose    # one stencil: the group's arrays are the stack
             return
         self.L_pose = torch.empty(n_hyp, 22, 22, dtype=F64, device=dev)
         self.h_pose = torch.empty(n_hyp, 22, dtype=F64, device=dev)
-        if first is not None:
-            self.L_pose[0].copy_(first["pose_evidence"][0].L_pose)
-            self.h_pose[0].copy_(first["pose_evidence"][0].h_pose)
         for g in groups:
             if g.units == list(range(g.units[0], g.units[0] + len(g.units))):
                 self.L_pose[g.units[0]:g.units[0] + len(g.units)].copy_(g.L_pose)
@@ -142,30 +141,37 @@ class BatchedPrimitiveEvidence:
                 self.h_pose.index_copy_(0, ix, g.h_pose)
 
     def wait(self):
-        """Block until the certificates of every hypothesis are on the host (idempotent)."""
+        """Block until the certificates of every hypothesis (and the map update's) are on the host (idempotent)."""
         if self._pending is None:
             return self
         self._event.synchronize()
-        dev = self._cfg["dev"]
         for g, b1 in zip(self.groups, self._pending):
             _unpack_scalars(g, b1.numpy().copy())
             g._view_n_valid = int(g.view_scalars[0])
-            # the reference's early exits (empty measurement batch / empty view): evidence = eps_lift * I, h = 0
-            for k, hh in enumerate(g.units):
-                if g._view_n_valid == 0 or g._n_cam + int(round(g.scalars[k, _O_NV])) == 0:
-                    self.L_pose[hh] = self._eps_lift * torch.eye(22, dtype=F64, device=dev)
-                    self.h_pose[hh] = 0.0
         self._pending = None
+        if self._gens:
+            fin = {}
+            for name in ("inflate", "update"):      # the update's certificate reads the inflation statistics
+                gen, buf, shape = self._gens[name]
+                try:
+                    gen.send(buf.view(F64).numpy().reshape(shape).copy())
+                    raise RuntimeError("operator body yielded twice")
+                except StopIteration as e:
+                    fin[name] = e.value
+                if name == "inflate":
+                    self._inflate_stats = fin[name][3]
+            self._first_extra = fin
+            self._gens = {}
+            self._cfg["atlas"]._pending_update = None
         return self
 
     @property
     def map_update(self):
-        return None if self.first is None else self.first["map_update"]
+        self.wait()
+        return None if self._first_extra is None else self._first_extra["update"]
 
     def unit(self, h: int) -> dict:
         self.wait()
-        if self.first is not None and h == 0:
-            return self.first
         g, k = self._where[int(h)]
         c, cfg = g.scalars[k], self._cfg
         io = _IO(cfg["dev"])
@@ -175,15 +181,17 @@ class BatchedPrimitiveEvidence:
                                        ess_imu=float(cfg["ess_imu"]))
         dk_cert, dk_eff = _deskew_cert(c[_O_DK:_O_DK + L.DK_NCERT], cfg["ess_imu"], chart, cfg["anchor_id"], io.compute())
         n_use = int(round(c[_O_NV]))
-        b = MeasurementBatch(**{f: (getattr(g.batch, f)[k] if isinstance(getattr(g.batch, f), torch.Tensor) else getattr(g.batch, f))
-                                for f in g.batch.__dataclass_fields__})
+        b = _batch_unit(g.batch, k)
         b.n_lidar_valid = n_use
         sf_cert, sf_eff = PR._surfel_cert(n_use, cfg["surfel"], chart, "surfel_extraction", io.compute())
         view = g.view
-        ri_cert, ri_eff, ri_stats = PR._inflate_finish(g.view_scalars[1:5], chart, "primitive_map_recency_inflate", io.compute())
+        updating = self._first_extra is not None and int(h) == 0
+        if updating:         # hypothesis 0 inflated the map in place: that operator's own tuple
+            ri = self._first_extra["inflate"]
+        else:
+            ri = (cfg["atlas"],) + PR._inflate_finish(g.view_scalars[1:5], chart, "primitive_map_recency_inflate", io.compute())
         assoc = PrimitiveAssociationResult(**{f: getattr(g.association, f)[k] for f in g.association.__dataclass_fields__})
         if b.n_valid == 0 or view.n_valid == 0:      # the reference's early exits (primitive_association.py:275-290)
-            assoc = PR._empty_assoc(io, N, K)
             as_out = (assoc, CertBundle.create_exact(chart_id=chart, anchor_id="primitive_ot"),
                       ExpectedEffect("primitive_association_ot", 0.0, 0.0))
             pe_out = PR._empty_pose_evidence(io, cfg["eps_lift"], chart, "visual_pose_evidence")
@@ -191,16 +199,20 @@ class BatchedPrimitiveEvidence:
             as_out = (assoc,) + PR._assoc_cert(c[_O_OT:_O_OT + OT["NCERT"]], N, K, cfg["assoc"], chart, "primitive_ot", io)
             pe_out = PR._pose_evidence_finish(c[_O_VP:_O_VP + VP["NREC"]], g.L_pose[k], g.h_pose[k], g.rec[k], b.n_valid, K,
                                               cfg["eps_lift"], chart, "visual_pose_evidence", io.compute())
-        return dict(deskew=(dk, dk_cert, dk_eff), surfels=(b, sf_cert, sf_eff),
-                    recency_inflate=(cfg["atlas"], ri_cert, ri_eff, ri_stats), map_view=view, association=as_out,
-                    pose_evidence=pe_out, map_update=None)
+        return dict(deskew=(dk, dk_cert, dk_eff), surfels=(b, sf_cert, sf_eff), recency_inflate=ri, map_view=view,
+                    association=as_out, pose_evidence=pe_out, map_update=self._first_extra["update"] if updating else None)
+
+
+def _batch_unit(stacked: MeasurementBatch, k: int) -> MeasurementBatch:
+    return MeasurementBatch(**{f: (getattr(stacked, f)[k] if isinstance(getattr(stacked, f), torch.Tensor) else getattr(stacked, f))
+                               for f in stacked.__dataclass_fields__})
 
 
 class CPrimBatchArgs(C.Structure):
     """gcs_prim_batch_args (include/gcs_b200.h)."""
     _fields_ = [("pts", _vp), ("t", _vp), ("w", _vp), ("n", _i64), ("n_units", _i32), ("inflate", _i32), ("xi", _vp), ("poses", _vp),
                 ("scan_start_time", _dbl), ("scan_end_time", _dbl), ("dk_pts", _vp), ("dk_w", _vp), ("dk_cert", _vp),
-                ("surfel_cfg", CSurfelCfg), ("base", CMeasBatch), ("batch", CMeasBatch), ("n_lidar_valid", _vp),
+                ("surfel_cfg", CSurfelCfg), ("base", CMeasBatch), ("batch", CMeasBatch), ("n_lidar_valid", _vp), ("n_camera_valid", _i32), ("reserved_", _i32),
                 ("atlas", C.POINTER(CAtlas)), ("tile_index", _i32 * 16), ("tile_ids", _i64 * 16), ("n_tiles", _i32),
                 ("m_tile_view", _i32), ("eps_lift", _dbl), ("eps_mass", _dbl), ("recency_min_scale", _dbl), ("view", CMapView),
                 ("view_n_valid", _vp), ("inflate_stats", _vp), ("assoc_cfg", CAssocCfg), ("assoc", CAssocResult), ("ot_cert", _vp),
@@ -288,6 +300,7 @@ def _run_group(io, units, tile_ids, pts, t, w, n, xi_d, poses_d, t0, t1, atlas_m
         setattr(a.batch, _C_BATCH_NAME.get(f, f), A.ptr("b_" + f))
     a.batch.n_feat, a.batch.n_surfel = scfg.n_feat, scfg.n_surfel
     a.n_lidar_valid = A.ptr("n_valid")
+    a.n_camera_valid = int(base_batch.n_camera_valid)
     ca = atlas_map._c()
     a.atlas = C.pointer(ca)
     idx = atlas_map.index_list(tile_ids, create=False)
@@ -388,26 +401,37 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
     scfg = surfel_config if surfel_config is not None else SurfelExtractionConfig()
     acfg = association_config if association_config is not None else AssociationConfig(scan_seq=int(scan_seq))
     PR._check_assoc_config(acfg)
-    first = None
+    if getattr(atlas_map, "_pending_update", None) is not None:   # a deferred earlier scan still owes the map's host state
+        atlas_map._pending_update.wait()
+    run = lambda units, tl: _run_group(io, units, list(tl), pts, t, w, n, xi_d, poses_d, scan_start_time, scan_end_time, atlas_map,
+                                       scan_seq, base_batch, scfg, acfg, m_tile_view, eps_lift, eps_mass, recency_min_scale)
+    groups, gens = [], {}
     rest = list(range(H))
     if update_map:
+        # hypothesis 0 (pipeline.py:835-877, 998-1010, 1233-1447): evidence against the view of the inflated map -- gathered
+        # functionally, bit-identical to inflating first -- then the inflation in place and the map update, all enqueued
+        # behind each other without a host synchronisation; the other hypotheses then see the updated map
         active0 = PR.ma_hex_stencil_tile_ids(poses_h[0, :3], acfg.h_tile, acfg.r_stencil_tiles_xy, acfg.r_stencil_tiles_z)
-        xi0 = xi_d[0].detach().cpu().numpy()
-        first = PR.lidar_evidence_primitives(pts, t, w, scan_start_time, scan_end_time, xi0, atlas_map, active0, poses_h[0],
-                                             scan_seq, base_batch=base_batch, surfel_config=scfg, association_config=acfg,
-                                             m_tile_view=m_tile_view, ess_imu=ess_imu, update_map=True,
-                                             map_update_kwargs=map_update_kwargs, chart_id=chart_id, anchor_id=anchor_id)
+        g0 = run([0], active0)
+        groups.append(g0)
+        gens["inflate"] = PR._recency_inflate_gen(atlas_map, active0, scan_seq, acfg.recency_decay_lambda, recency_min_scale, chart_id)
+        io_i, stats_i, _ = next(gens["inflate"])
+        out_holder = []
+        b0 = _batch_unit(g0.batch, 0)
+        a0 = PrimitiveAssociationResult(**{f: getattr(g0.association, f)[0] for f in g0.association.__dataclass_fields__})
+        gens["update"] = PR._map_update_step12b_gen(atlas_map, b0, a0, active0, poses_h[0], scan_seq, scan_end_time,
+                                                    inflate_stats=lambda: out_holder[0]._inflate_stats,
+                                                    **(map_update_kwargs or {}))
+        io_u, stats_u, _ = next(gens["update"])
         rest = rest[1:]
     by_stencil: Dict[tuple, List[int]] = {}
     for hh in rest:
         tl = tuple(PR.ma_hex_stencil_tile_ids(poses_h[hh, :3], acfg.h_tile, acfg.r_stencil_tiles_xy, acfg.r_stencil_tiles_z))
         by_stencil.setdefault(tl, []).append(hh)
-    groups = [_run_group(io, units, list(tl), pts, t, w, n, xi_d, poses_d, scan_start_time, scan_end_time, atlas_map, scan_seq,
-                         base_batch, scfg, acfg, m_tile_view, eps_lift, eps_mass, recency_min_scale)
-              for tl, units in by_stencil.items()]
+    groups += [run(units, tl) for tl, units in by_stencil.items()]
     cfg = dict(dev=io.dev, chart_id=chart_id, anchor_id=anchor_id, ess_imu=ess_imu, surfel=scfg, assoc=acfg, eps_lift=eps_lift,
                atlas=atlas_map, timestamps=t)
-    out = BatchedPrimitiveEvidence(H, groups, first, cfg)
+    out = BatchedPrimitiveEvidence(H, groups, cfg)
     # ONE synchronisation for the certificates of every hypothesis: the packed scalars go to pinned memory behind the
     # kernels; `defer` leaves the wait to the caller (out.wait()), so that the next scan can be enqueued meanwhile
     out._pending = []
@@ -415,9 +439,15 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
         b1 = _PinnedRing.get(g._scal_d.numel())
         b1.copy_(g._scal_d, non_blocking=True)
         out._pending.append(b1)
+    if update_map:
+        out_holder.append(out)
+        for name, st_d in (("inflate", stats_i), ("update", stats_u)):
+            buf = _PinnedRing.get(st_d.numel() * 8)
+            buf.view(F64).copy_(st_d.reshape(-1), non_blocking=True)
+            out._gens[name] = (gens[name], buf, tuple(st_d.shape))
+        atlas_map._pending_update = out
     out._event = torch.cuda.Event()
     out._event.record(torch.cuda.current_stream(io.dev))
-    out._eps_lift = eps_lift
     if not defer:
         out.wait()
     return out

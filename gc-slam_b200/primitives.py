@@ -775,6 +775,8 @@ def _map_update_step12b_gen(atlas_map, measurement_batch, association_result, ac
                                            C.byref(cb), C.byref(cr), _dptr(pose), C.byref(cfg), L.ptr(new_ids), L.ptr(slots),
                                            L.ptr(stats_d)))
     s = yield io, stats_d, atlas_map
+    if callable(inflate_stats):          # resolved late: the caller learns the inflation statistics in the same read-back
+        inflate_stats = inflate_stats()
     n_ins, n_cull = int(s[MU["INSERT_COUNT"]]), int(s[MU["EVICTED_COUNT"]])
     atlas_map.next_global_id = int(s[MU["NEXT_GLOBAL_ID"]])
     atlas_map.total_count = atlas_map.total_count + n_ins - n_cull

@@ -498,11 +498,16 @@ int gcs_visual_pose_evidence(gcs_ctx* ctx, void* stream, const gcs_meas_batch* b
                              double eps_lift, double eps_mass, double* out_L22 /*dev (22,22)*/,
                              double* out_h22 /*dev (22)*/, double* out_rec /*dev [GCS_VP_NREC]*/);
 
-/* Hypothesis-batched form: poses dev (n_units, 6); outputs stacked (n_units, 22, 22), (n_units, 22), (n_units, NREC). */
+/* Hypothesis-batched form: poses dev (n_units, 6); outputs stacked (n_units, 22, 22), (n_units, 22), (n_units, NREC).
+ * n_lidar_valid (dev int32[n_units]) / view_n_valid (dev int32[1]), if both given: the reference's early exits taken on
+ * the device -- a unit with n_camera_valid + n_lidar_valid[u] == 0, or every unit when the view is empty, gets the
+ * all-zero association (`assoc` is overwritten) and the evidence eps_lift * I, h = 0.                              */
 int gcs_visual_pose_evidence_batched(gcs_ctx* ctx, void* stream, const gcs_meas_batch* batch, int32_t n_units,
                                      const gcs_map_view* view, const gcs_assoc_result* assoc, int32_t k_assoc,
                                      const double* poses /*dev (n_units,6) [t,rotvec]*/, double eps_lift, double eps_mass,
-                                     double* out_L22, double* out_h22, double* out_rec);
+                                     double* out_L22, double* out_h22, double* out_rec,
+                                     const int32_t* n_lidar_valid /*dev or NULL*/, int32_t n_camera_valid,
+                                     const int32_t* view_n_valid /*dev or NULL*/);
 
 /* ---- the hypothesis loop of one scan in ONE call (fl/backend/backend_node.py:2036-2066 around the primitive-family
  *      steps of process_scan_single_hypothesis, fl/backend/pipeline.py:569-587, 780-877, 998-1010): n_units hypotheses
@@ -531,6 +536,8 @@ typedef struct {
                              base.Lambdas == NULL: the stacked batch is taken as the caller prepared it                 */
   gcs_meas_batch batch;   /* out, stacked: unit 0's pointers */
   int32_t* n_lidar_valid; /* out (n_units) */
+  int32_t n_camera_valid; /* valid rows of the camera slice (host knowledge of the base batch), for the early exits */
+  int32_t reserved_;
   const gcs_atlas* atlas; /* host struct */
   int32_t tile_index[16]; /* pool rows of the stencil tiles (-1: tile missing) */
   int64_t tile_ids[16];

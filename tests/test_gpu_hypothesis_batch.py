@@ -84,7 +84,7 @@ def test_batched_hypotheses_bit_identical_to_the_loop(mods, update_map):
                                                update_map=update_map)
     assert out.L_pose.shape == (H, 22, 22) and out.h_pose.shape == (H, 22)
     n_groups = len({tuple(P.ma_hex_stencil_tile_ids(p[:3])) for p in poses[(1 if update_map else 0):]})
-    assert len(out.groups) == n_groups >= 2
+    assert len(out.groups) == n_groups + (1 if update_map else 0) and n_groups >= 2   # hypothesis 0 runs ahead of the map update
 
     # the reference's order with the stand-alone operators
     h_first = 0
@@ -93,6 +93,16 @@ def test_batched_hypotheses_bit_identical_to_the_loop(mods, update_map):
         f = P.lidar_evidence_primitives(pts, t, w, t0, t1, xis[0], amap_ref, active0, poses[0], scan_seq, base_batch=_base(P, cam))
         assert torch.equal(out.L_pose[0], f["pose_evidence"][0].L_pose) and torch.equal(out.h_pose[0], f["pose_evidence"][0].h_pose)
         assert out.map_update[0].n_inserted == f["map_update"][0].n_inserted
+        u0 = out.unit(0)
+        assert torch.equal(u0["association"][0].responsibilities, f["association"][0].responsibilities)
+        assert torch.equal(u0["surfels"][0].Lambdas, f["surfels"][0].Lambdas) and u0["surfels"][0].n_lidar_valid == f["surfels"][0].n_lidar_valid
+        assert torch.equal(u0["map_view"].positions, f["map_view"].positions) and u0["map_view"].n_valid == f["map_view"].n_valid
+        assert u0["recency_inflate"][3].stale_precision_downscale_total == f["recency_inflate"][3].stale_precision_downscale_total
+        mu_a, mu_b = u0["map_update"][1].map_update, f["map_update"][1].map_update
+        assert (mu_a.fused_count, mu_a.insert_count_total, mu_a.evicted_count) == (mu_b.fused_count, mu_b.insert_count_total, mu_b.evicted_count)
+        assert mu_a.fused_mass_total == mu_b.fused_mass_total and mu_a.staleness_inflation_strength == mu_b.staleness_inflation_strength
+        assert torch.equal(u0["map_update"][0].new_ids, f["map_update"][0].new_ids)
+        assert amap.next_global_id == amap_ref.next_global_id and amap.total_count == amap_ref.total_count
         for name in amap.fields:                       # the batch left the updated map untouched
             assert torch.equal(amap.fields[name], amap_ref.fields[name]), name
         h_first = 1
@@ -181,6 +191,18 @@ def test_batched_empty_map_and_errors(mods):
         a, c, e = u["association"]
         assert c.exact and float(a.responsibilities.abs().sum().item()) == 0.0 and e.predicted == 0.0
         assert u["pose_evidence"][1].exact and float(u["pose_evidence"][0].h_pose.abs().sum().item()) == 0.0
+    # first scan on an empty map with the update: hypothesis 0 inserts, the others then see a map that is no longer empty
+    out = HB.lidar_evidence_primitives_batched(pts, t, w, 0.0, 0.1, xis, amap, poses, 1, surfel_config=cfg, m_tile_view=64, update_map=True,
+                                               map_update_kwargs=dict(k_insert_tile=16))
+    ref_map = P.create_empty_atlas_map(m_tile=2048, n_tiles_cap=16)
+    f = P.lidar_evidence_primitives(pts, t, w, 0.0, 0.1, xis[0], ref_map, P.ma_hex_stencil_tile_ids(poses[0, :3]), poses[0], 1,
+                                    surfel_config=cfg, m_tile_view=64, map_update_kwargs=dict(k_insert_tile=16))
+    assert out.unit(0)["association"][1].exact and out.map_update[0].n_inserted == f["map_update"][0].n_inserted > 0
+    assert torch.equal(out.L_pose[0], f["pose_evidence"][0].L_pose) and torch.equal(out.unit(0)["map_update"][0].new_ids, f["map_update"][0].new_ids)
+    for name in amap.fields:
+        assert torch.equal(amap.fields[name][:len(amap.tiles)], ref_map.fields[name][:len(ref_map.tiles)]), name
+    v1 = P.extract_atlas_map_view(amap, P.ma_hex_stencil_tile_ids(poses[1, :3]), 64)      # the map after hypothesis 0's update
+    assert out.unit(1)["map_view"].n_valid == v1.n_valid and torch.equal(out.unit(1)["map_view"].valid_mask, v1.valid_mask)
     with pytest.raises(ValueError):
         HB.lidar_evidence_primitives_batched(pts, t, w, 0.0, 0.1, xis, amap, poses[:2], 1, surfel_config=cfg, m_tile_view=64)
     with pytest.raises(ValueError):
