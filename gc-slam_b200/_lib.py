@@ -33,6 +33,8 @@ EV = dict(R_MF=0, L_ROT=9, H_ROT=18, DELTA_ROT=21, SVD_S=24, SCAN_METRICS=27, MA
           PT_MASS_EPS=98, PT_TRANS_NLL=99, PT_N_EFF=100)
 EV_NREC = 104
 
+TIME_TAGS = dict(bin_scan=0, surfel_fit=1, map_view=2, topk=3, fuse=4, inflate=5, sinkhorn=6)
+
 _vp = C.c_void_p
 _i64 = C.c_int64
 _dbl = C.c_double
@@ -109,6 +111,7 @@ PROTOTYPES = {
     "gcs_bins_mass": (_int, [_vp, _vp, C.POINTER(BinsArgs), _vp]),
     "gcs_bins_accumulate": (_int, [_vp, _vp, C.POINTER(BinsArgs), _vp, _vp, _vp]),
     "gcs_bins_finalize": (_int, [_vp, _vp, C.POINTER(BinsArgs), _vp, _vp, _vp]),
+    "gcs_bins_reduce_gathered": (_int, [_vp, _vp, _vp, C.c_int32, _i64, _i64, _vp, _vp]),
 }
 
 _lib = None
@@ -175,8 +178,10 @@ class Context:
     def sm_count(self) -> int:
         return int(self.lib.gcs_device_sm_count(self.handle))
 
-    def timing_enable(self, on: bool = True):
-        self.check(self.lib.gcs_timing_enable(self.handle, 1 if on else 0))
+    def timing_enable(self, on=True, only: str = None):
+        """Bracket the dominant kernels with CUDA events; `only`: one of TIME_TAGS (e.g. "topk") to time just that kernel."""
+        code = 0 if not on else (1 if only is None else 100 + TIME_TAGS[only])
+        self.check(self.lib.gcs_timing_enable(self.handle, code))
 
     def timing_collect(self):
         """-> (summed device ms of the dominant kernel, number of launches) since the last collect."""

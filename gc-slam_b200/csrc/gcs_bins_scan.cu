@@ -654,6 +654,25 @@ __global__ void kappa_batch_kernel(const double* __restrict__ Rbar, int64_t n, d
   if (i < n) out[i] = kappa_from_resultant(Rbar[i], eps_r, d, r0, tau);
 }
 
+
+// Rank-ordered reduction of all-gathered partial statistics (point-sharded clouds): every rank holds the packed partial
+// blocks of all ranks, (world, n_sum + n_max); sums add in rank order, maxima take the maximum -- the same arithmetic on
+// the same data on every rank, so the reduced statistics are bit-identical everywhere whatever the collective library
+// does inside.
+__global__ void __launch_bounds__(256) reduce_gathered_kernel(const double* __restrict__ g, int world, int64_t n_sum, int64_t n_max,
+                                                              double* __restrict__ out_sum, double* __restrict__ out_max) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t stride = n_sum + n_max;
+  if (i >= stride) return;
+  double a = g[i];
+  if (i < n_sum) {
+    for (int r = 1; r < world; ++r) a += g[(int64_t)r * stride + i];
+    out_sum[i] = a;
+  } else {
+    for (int r = 1; r < world; ++r) a = fmax(a, g[(int64_t)r * stride + i]);
+    out_max[i - n_sum] = a;
+  }
+}
 }  // namespace gcs
 
 // ================================================================================================
@@ -826,11 +845,11 @@ static int accumulate_impl(gcs_ctx* ctx, cudaStream_t st, const gcs_bins_args* a
     n_parts = g.tc_parts;
     GCS_CHECK_CUDA(ctx, cudaMemsetAsync(P.partial, 0, (size_t)g.U * n_parts * g.part_len * sizeof(double), st));
   }
-  gcs_timing_begin(ctx, st);
+  gcs_timing_begin(ctx, st, GCS_TIME_BIN_SCAN);
   if (use_tc) GCS_CHECK_CUDA(ctx, launch_bin_scan_tc(ctx->sm_count, st, P, n_parts));
   else if (a->precision == GCS_PREC_F64) GCS_CHECK_CUDA(ctx, launch_scan<0>(Q, grid, st, P));
   else GCS_CHECK_CUDA(ctx, launch_scan<1>(Q, grid, st, P));
-  gcs_timing_end(ctx, st);
+  gcs_timing_end(ctx, st, GCS_TIME_BIN_SCAN);
   GCS_LAUNCH_CHECK(ctx);
   reduce_partials_kernel<<<dim3((g.raw_len + kNMax + 63) / 64, g.U), 256, 0, st>>>(w.partial, n_parts, g.part_len,
                                                                                     a->n_bins, kNF, raw_sums, raw_max);
@@ -1025,6 +1044,19 @@ int gcs_kappa_from_resultant_batch(gcs_ctx* ctx, void* stream, const double* R_b
   GCS_REQUIRE(ctx, n >= 0 && (n == 0 || (R_bar && out)), "kappa_from_resultant_batch: bad args");
   if (n == 0) return GCS_OK;
   kappa_batch_kernel<<<(unsigned)ceil_div64(n, 128), 128, 0, (cudaStream_t)stream>>>(R_bar, n, eps_r, d, r0, tau, out);
+  GCS_LAUNCH_CHECK(ctx);
+  return GCS_OK;
+}
+
+
+int gcs_bins_reduce_gathered(gcs_ctx* ctx, void* stream, const double* gathered, int32_t world, int64_t n_sum, int64_t n_max,
+                             double* out_sum, double* out_max) {
+  if (!ctx) return GCS_EINVAL;
+  GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  GCS_REQUIRE(ctx, gathered && world >= 1 && n_sum >= 0 && n_max >= 0 && n_sum + n_max >= 1 && (n_sum == 0 || out_sum) &&
+                       (n_max == 0 || out_max), "bins_reduce_gathered: bad args");
+  reduce_gathered_kernel<<<(unsigned)ceil_div64(n_sum + n_max, 256), 256, 0, (cudaStream_t)stream>>>(gathered, world, n_sum, n_max,
+                                                                                                    out_sum, out_max);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
 }

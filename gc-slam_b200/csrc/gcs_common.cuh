@@ -19,18 +19,21 @@ struct gcs_ctx {
   uint64_t ws_bytes;
   uint64_t launches;
   // optional CUDA-event timing of the dominant kernel (gcs_timing_*): pairs recorded on the launching stream
-  int timing_on;
+  int timing_on;   // 0 off, 1 every bracketed kernel, 100 + tag: only the kernel with that tag (GCS_TIME_*)
   int timing_n;
   cudaEvent_t timing_ev[2 * 256];
   char err[512];
 };
 
 // Bracket the dominant kernel of a path with events when timing is enabled (no-ops otherwise).
-static inline void gcs_timing_begin(gcs_ctx* ctx, cudaStream_t st) {
-  if (ctx->timing_on && ctx->timing_n < 256) cudaEventRecord(ctx->timing_ev[2 * ctx->timing_n], st);
+static inline bool gcs_timing_wants(gcs_ctx* ctx, int tag) {
+  return ctx->timing_n < 256 && (ctx->timing_on == 1 || ctx->timing_on == 100 + tag);
 }
-static inline void gcs_timing_end(gcs_ctx* ctx, cudaStream_t st) {
-  if (ctx->timing_on && ctx->timing_n < 256) { cudaEventRecord(ctx->timing_ev[2 * ctx->timing_n + 1], st); ctx->timing_n++; }
+static inline void gcs_timing_begin(gcs_ctx* ctx, cudaStream_t st, int tag) {
+  if (gcs_timing_wants(ctx, tag)) cudaEventRecord(ctx->timing_ev[2 * ctx->timing_n], st);
+}
+static inline void gcs_timing_end(gcs_ctx* ctx, cudaStream_t st, int tag) {
+  if (gcs_timing_wants(ctx, tag)) { cudaEventRecord(ctx->timing_ev[2 * ctx->timing_n + 1], st); ctx->timing_n++; }
 }
 
 int gcs_set_error(gcs_ctx* ctx, int code, const char* fmt, ...);

@@ -66,7 +66,7 @@ int gcs_timing_enable(gcs_ctx* ctx, int on) {
   GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
   if (on && !ctx->timing_ev[0])
     for (int i = 0; i < 2 * 256; ++i) GCS_CHECK_CUDA(ctx, cudaEventCreate(&ctx->timing_ev[i]));
-  ctx->timing_on = on ? 1 : 0;
+  ctx->timing_on = on < 0 ? 0 : on;
   ctx->timing_n = 0;
   return GCS_OK;
 }

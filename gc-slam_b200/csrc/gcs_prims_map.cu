@@ -1351,9 +1351,9 @@ int gcs_map_recency_inflate(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, 
   rc = gcs_ws_reserve(ctx, (uint64_t)n_tiles * blocks * 3 * 8);
   if (rc) return rc;
   double* part = (double*)ctx->ws;
-  gcs_timing_begin(ctx, st);
+  gcs_timing_begin(ctx, st, GCS_TIME_INFLATE);
   recency_inflate_kernel<<<dim3(blocks, n_tiles), 256, 0, st>>>(*atlas, T, scan_seq, lam, min_scale, part, 1);
-  gcs_timing_end(ctx, st);
+  gcs_timing_end(ctx, st, GCS_TIME_INFLATE);
   GCS_LAUNCH_CHECK(ctx);
   sum_parts_kernel<<<1, 32, 0, st>>>(part, n_tiles * blocks, 3, stats, 4);
   GCS_LAUNCH_CHECK(ctx);
@@ -1384,11 +1384,11 @@ static int map_view_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_atlas* atlas
     GCS_LAUNCH_CHECK(ctx);
   }
   GCS_CHECK_CUDA(ctx, cudaMemsetAsync(out_n_valid, 0, sizeof(int32_t), st));
-  gcs_timing_begin(ctx, st);
+  gcs_timing_begin(ctx, st, GCS_TIME_MAP_VIEW);
   // no key cache here: the view's key is two cached loads, and the 200 KB carve-out it would take from L1 costs more
   // than the re-evaluations (measured 208 us with, 158 us without; the eviction select of the map update gains 35 %)
   map_view_kernel<<<n_tiles, kBig, 0, st>>>(*atlas, T, m_tile_view, eps_lift, eps_mass, *view, out_n_valid, 0, I);
-  gcs_timing_end(ctx, st);
+  gcs_timing_end(ctx, st, GCS_TIME_MAP_VIEW);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
 }
@@ -1473,18 +1473,20 @@ static int assoc_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_meas_batch* bat
   const long long total_rows = (long long)n_units * N;
   int topk_ctas = (int)((total_rows + kTopkWarps - 1) / kTopkWarps);
   if (topk_ctas > ctx->sm_count) topk_ctas = ctx->sm_count;
-  gcs_timing_begin(ctx, st);
+  gcs_timing_begin(ctx, st, GCS_TIME_TOPK);
   assoc_topk_kernel<8><<<topk_ctas, 32 * kTopkWarps, topk_smem, st>>>(*batch, N, n_units, *view, m_tile_view, n_st, n_tiles, W, *cfg,
                                                                       *out, row_counter, tmap, staged ? 1 : 0);
-  gcs_timing_end(ctx, st);
+  gcs_timing_end(ctx, st, GCS_TIME_TOPK);
   GCS_LAUNCH_CHECK(ctx);
   // cluster size per hypothesis: eight SMs for one, fewer when the batch fills the device anyway
   double* brow = (double*)(ws + o_brow);
   // the iterations are a latency chain (log / exp / barrier), so as many CTAs as stay resident (three per SM) overlap
   const int sk_rpt = (n_units * 8 <= 3 * ctx->sm_count) ? 1 : (n_units * 4 <= 3 * ctx->sm_count ? 2 : 4);
+  gcs_timing_begin(ctx, st, GCS_TIME_SINKHORN);
   if (sk_rpt == 1) GCS_CHECK_CUDA(ctx, sinkhorn_launch<1>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow));
   else if (sk_rpt == 2) GCS_CHECK_CUDA(ctx, sinkhorn_launch<2>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow));
   else GCS_CHECK_CUDA(ctx, sinkhorn_launch<4>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow));
+  gcs_timing_end(ctx, st, GCS_TIME_SINKHORN);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
 }
@@ -1654,9 +1656,9 @@ int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int
   GCS_CHECK_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ws + o_cub, cub_bytes, (const unsigned*)(ws + o_pk0), W.pkeys,
                                                       (const unsigned*)(ws + o_pv0), W.pvals, n_pairs, 0, key_bits, st));
   ctx->launches++;
-  gcs_timing_begin(ctx, st);
+  gcs_timing_begin(ctx, st, GCS_TIME_FUSE);
   upd_fuse_kernel<<<fuse_blocks, 256, 0, st>>>(*atlas, T, *batch, K, *assoc, W, n_pairs, none, *cfg, fpart);
-  gcs_timing_end(ctx, st);
+  gcs_timing_end(ctx, st, GCS_TIME_FUSE);
   GCS_LAUNCH_CHECK(ctx);
   if (cfg->strict_tile_state) {
     upd_stamp_strict_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(*atlas, T, *assoc, n_pairs, cfg->timestamp);

@@ -555,7 +555,7 @@ static int surfels_launch(gcs_ctx* ctx, cudaStream_t st, const double* pts, cons
   surfel_bucket_fill_kernel<<<dim3((unsigned)cdiv(n, kSurfThreads), Hu), kSurfThreads, 0, st>>>(key, lrank, hist, n, per_chunk, n_keys, G,
                                                                                             bucket, n_chunks);
   GCS_LAUNCH_CHECK(ctx);
-  gcs_timing_begin(ctx, st);
+  gcs_timing_begin(ctx, st, GCS_TIME_SURFEL_FIT);
   // groups of eight lanes / single threads stride over the occupied-cell list (a typical scan fills ~2,500 of 8,192 cells)
   double* mom = (double*)(ws + o_mom);
   // one list entry per group / thread for a single scan (latency), a quarter of that per unit for a batch (the list of a
@@ -566,7 +566,7 @@ static int surfels_launch(gcs_ctx* ctx, cudaStream_t st, const double* pts, cons
                                                               n_occ, mom);
   GCS_LAUNCH_CHECK(ctx);
   surfel_fit_kernel<<<dim3(fit_blocks, Hu), 128, 0, st>>>(center, G, *cfg, F, occ_list, n_occ, mom);
-  gcs_timing_end(ctx, st);
+  gcs_timing_end(ctx, st, GCS_TIME_SURFEL_FIT);
   GCS_LAUNCH_CHECK(ctx);
   surfel_select_kernel<<<Hu, 1024, 0, st>>>(F, G, *batch, cfg->eps_lift, out_n_valid, total, out_count, n_keys);
   GCS_LAUNCH_CHECK(ctx);

@@ -73,6 +73,9 @@ def point_shard_rows(n_raw_total: int, n_points_cap: int, world: int, rank: int)
     """
     stride = 1 if n_raw_total <= n_points_cap else -(-int(n_raw_total) // int(n_points_cap))
     n_sel_total = -(-int(n_raw_total) // stride)
+    if n_sel_total < int(world):
+        raise ValueError(f"point_shard_rows: {n_sel_total} selected rows cannot be split over {world} ranks "
+                         "(every rank needs at least one row: use fewer ranks for clouds this small)")
     lo, hi = shard_range(n_sel_total, world, rank)          # shard the SELECTED rows evenly
     row0, row1 = lo * stride, min(hi * stride, int(n_raw_total))
     # padded output rows (cap - n_sel) are dealt to the last rank so that their count is preserved globally
@@ -82,7 +85,8 @@ def point_shard_rows(n_raw_total: int, n_points_cap: int, world: int, rank: int)
 
 
 def allreduce_bin_sums(mass=None, raw_sums=None, raw_max=None, group=None):
-    """In-place all-reduce of the additive statistics of the bin path (SUM; MAX for the running maxima)."""
+    """In-place all-reduce of the additive statistics of the bin path (SUM; MAX for the running maxima): three library
+    all-reduces.  Kept for callers that hold the three arrays separately; run_point_sharded uses PointShardExchange."""
     import torch.distributed as dist
 
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
@@ -95,38 +99,115 @@ def allreduce_bin_sums(mass=None, raw_sums=None, raw_max=None, group=None):
         dist.all_reduce(raw_max, op=dist.ReduceOp.MAX, group=group)
 
 
-def run_point_sharded(plan, group=None):
+class PointShardExchange:
+    """
+    Buffers of the two exchanges of a point-sharded bin path, allocated once per plan.  Each exchange is ONE collective
+    on ONE packed buffer: this rank's partial block [additive | maxima] is all-gathered, then gcs_bins_reduce_gathered
+    adds / maximises the `world` blocks in rank order on every rank (bit-identical results everywhere, whatever
+    reduction tree the collective library would have used).  `mass`, `raw_sums`, `raw_max` are views into the packed
+    buffers, so the bin kernels write their partials straight into the exchange buffer and read the reduced values from
+    the same place: no copy on either side of the collective.
+    """
+
+    def __init__(self, plan, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.plan, self.group = plan, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        dev = plan.io.dev
+        self.n_mass = plan.S * 4
+        self.n_sum, self.n_max = plan.U * plan.raw_len, plan.U * 2
+        self.pack1 = torch.zeros(self.n_mass, dtype=torch.float64, device=dev)
+        self.pack2 = torch.zeros(self.n_sum + self.n_max, dtype=torch.float64, device=dev)
+        self.mass = self.pack1.view(plan.S, 4)
+        self.raw_sums = self.pack2[:self.n_sum].view(plan.U, plan.raw_len)
+        self.raw_max = self.pack2[self.n_sum:].view(plan.U, 2)
+        self.gath1 = torch.empty(self.world * self.n_mass, dtype=torch.float64, device=dev)
+        self.gath2 = torch.empty(self.world * (self.n_sum + self.n_max), dtype=torch.float64, device=dev)
+        self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if dev.type == "cuda" else None
+
+    def _exchange(self, pack, gath, n_sum, n_max, e0=None, e1=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib as L
+
+        if self.world == 1:
+            return
+        if e0 is not None:
+            e0.record()
+        dist.all_gather_into_tensor(gath, pack, group=self.group)
+        if pack.is_cuda:
+            io = self.plan.io
+            io.ctx.check(io.ctx.lib.gcs_bins_reduce_gathered(io.ctx.handle, io.stream(), L.ptr(gath), self.world, n_sum, n_max,
+                                                             L.ptr(pack), L.ptr(pack[n_sum:]) if n_max else None))
+        else:   # host tensors (gloo tests of the exchange logic): the same rank-ordered arithmetic
+            g = gath.view(self.world, n_sum + n_max)
+            acc = g[0, :n_sum].clone()
+            for r in range(1, self.world):
+                acc += g[r, :n_sum]
+            pack[:n_sum] = acc
+            if n_max:
+                pack[n_sum:] = torch.amax(g[:, n_sum:], dim=0)
+        if e1 is not None:
+            e1.record()
+
+    def exchange_mass(self, timed=False):
+        self._exchange(self.pack1, self.gath1, self.n_mass, 0, *(self.ev[0:2] if timed and self.ev else (None, None)))
+
+    def exchange_sums(self, timed=False):
+        self._exchange(self.pack2, self.gath2, self.n_sum, self.n_max, *(self.ev[2:4] if timed and self.ev else (None, None)))
+
+    def exchange_ms(self):
+        """Device time of the two exchanges of the last timed run (collective + rank-ordered reduction), in ms."""
+        return self.ev[0].elapsed_time(self.ev[1]), self.ev[2].elapsed_time(self.ev[3])
+
+
+def run_point_sharded(plan, group=None, exchange: "PointShardExchange" = None, timed: bool = False):
     """
     Bin path of clouds whose rows are split across ranks.  `plan` is a BinPathPlan built with this rank's
-    (shard_row0, n_raw, cap) and the global (n_raw_total, cap_total).  Three phases with two tiny collectives.
+    (shard_row0, n_raw, cap) and the global (n_raw_total, cap_total).  Three phases with two tiny exchanges, each one
+    collective on one packed buffer (PointShardExchange).  Returns (mass, raw_sums, raw_max) -- views into the exchange.
     """
-    import torch
-
-    dev = plan.io.dev
-    mass = torch.zeros((plan.S, 4), dtype=torch.float64, device=dev)
-    raw_sums = torch.zeros((plan.U, plan.raw_len), dtype=torch.float64, device=dev)
-    raw_max = torch.zeros((plan.U, 2), dtype=torch.float64, device=dev)
-    plan.run_mass(mass)
-    allreduce_bin_sums(mass=mass, group=group)
-    plan.run_accumulate(mass, raw_sums, raw_max)
-    allreduce_bin_sums(raw_sums=raw_sums, raw_max=raw_max, group=group)
-    plan.run_finalize(mass, raw_sums, raw_max)
-    return mass, raw_sums, raw_max
+    x = exchange if exchange is not None else PointShardExchange(plan, group)
+    x.pack1.zero_()
+    x.pack2.zero_()
+    plan.run_mass(x.mass)
+    x.exchange_mass(timed)
+    plan.run_accumulate(x.mass, x.raw_sums, x.raw_max)
+    x.exchange_sums(timed)
+    plan.run_finalize(x.mass, x.raw_sums, x.raw_max)
+    return x.mass, x.raw_sums, x.raw_max
 
 
 def gather_evidence(L22, h22, group=None):
-    """All-gather per-hypothesis (L, h) from every rank to every rank (4.3 KB per hypothesis)."""
+    """
+    All-gather per-hypothesis (L, h) from every rank to every rank (4.3 KB per hypothesis).  Ranks may hold different
+    numbers of hypotheses (shard_range gives 3 + 2 for five hypotheses on two GPUs): the counts are gathered first, every
+    stack is padded to the largest count for the collective and cut back afterwards.
+    """
     import torch
     import torch.distributed as dist
 
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return L22, h22
     world = dist.get_world_size(group)
-    Ls = [torch.empty_like(L22) for _ in range(world)]
-    hs = [torch.empty_like(h22) for _ in range(world)]
-    dist.all_gather(Ls, L22, group=group)
-    dist.all_gather(hs, h22, group=group)
-    return torch.cat(Ls, 0), torch.cat(hs, 0)
+    k_local = int(L22.shape[0])
+    D = int(h22.shape[1])
+    cnt = torch.tensor([k_local], dtype=torch.int64, device=L22.device)
+    cnts = torch.empty(world, dtype=torch.int64, device=L22.device)
+    dist.all_gather_into_tensor(cnts, cnt, group=group)
+    counts = [int(c) for c in cnts.tolist()]
+    k_max = max(counts)
+    pack = torch.zeros(k_max, D * D + D, dtype=L22.dtype, device=L22.device)   # (L | h) of one hypothesis per row
+    if k_local:
+        pack[:k_local, :D * D] = L22.reshape(k_local, D * D)
+        pack[:k_local, D * D:] = h22
+    gath = torch.empty(world * k_max, D * D + D, dtype=L22.dtype, device=L22.device)
+    dist.all_gather_into_tensor(gath, pack, group=group)
+    rows = torch.cat([gath[r * k_max:r * k_max + counts[r]] for r in range(world)], 0)
+    return rows[:, :D * D].reshape(-1, D, D).contiguous(), rows[:, D * D:].contiguous()
 
 
 def hypothesis_barycenter(L_stack, h_stack, weights, weight_floor: float = 0.0025, eps_psd: float = 1e-12):

@@ -47,9 +47,12 @@ const char* gcs_last_error(gcs_ctx* ctx); /* ctx may be NULL: returns the last c
 int gcs_reserve_workspace(gcs_ctx* ctx, uint64_t bytes); /* optional: pre-size so later calls never allocate */
 int gcs_device_sm_count(gcs_ctx* ctx);
 uint64_t gcs_kernel_launches(gcs_ctx* ctx); /* number of kernels this ctx has launched so far              */
-/* Measurement hook: when enabled, the dominant kernel of each path (bin_scan_kernel, ...) is bracketed by CUDA
- * events on the launching stream (up to 256 launches between collects).  collect() waits for them and returns
- * the summed device time and the number of launches, then resets.                                           */
+/* Measurement hook: when enabled, the dominant kernels of each path are bracketed by CUDA events on the launching
+ * stream (up to 256 launches between collects).  on = 1: every bracketed kernel; on = 100 + GCS_TIME_x: only that
+ * kernel; 0: off.  collect() waits for the events and returns the summed device time and the number of launches,
+ * then resets.                                                                                                */
+enum { GCS_TIME_BIN_SCAN = 0, GCS_TIME_SURFEL_FIT, GCS_TIME_MAP_VIEW, GCS_TIME_TOPK, GCS_TIME_FUSE, GCS_TIME_INFLATE,
+       GCS_TIME_SINKHORN };
 int gcs_timing_enable(gcs_ctx* ctx, int on);
 int gcs_timing_collect(gcs_ctx* ctx, double* total_ms, int* count);
 
@@ -309,6 +312,14 @@ int gcs_bins_accumulate(gcs_ctx* ctx, void* stream, const gcs_bins_args* args, c
 /* Phase 2: statistics, kappa, PSD projection, Matrix-Fisher rotation, planar translation, 22-D embed, certs. */
 int gcs_bins_finalize(gcs_ctx* ctx, void* stream, const gcs_bins_args* args, const double* mass,
                       const double* raw_sums, const double* raw_max);
+/* The exchange step of a point-sharded cloud: every rank packs its partial statistics into ONE
+ * buffer [additive block of n_sum doubles | running maxima, n_max doubles], the buffers are all-gathered (one collective,
+ * ncclAllGather through torch.distributed), and this entry reduces the gathered (world, n_sum + n_max) array in rank
+ * order -- SUM for the additive block, MAX for the maxima.  Same data, same order on every rank: bit-identical
+ * statistics everywhere.  Used for both exchanges of the path (resample masses; raw sums + maxima).                  */
+int gcs_bins_reduce_gathered(gcs_ctx* ctx, void* stream, const double* gathered /*dev (world, n_sum + n_max)*/,
+                             int32_t world, int64_t n_sum, int64_t n_max, double* out_sum /*dev (n_sum)*/,
+                             double* out_max /*dev (n_max)*/);
 
 
 /* ================================================================================================

@@ -61,20 +61,28 @@ def _worker(rank, world, port, n_raw, out_q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from gc_slam_b200 import synth
-    from gc_slam_b200.sharding import allreduce_bin_sums, gather_evidence, point_shard_rows
+    from types import SimpleNamespace
+    from gc_slam_b200.sharding import PointShardExchange, gather_evidence, point_shard_rows, shard_range
     pts, t, w, _, _ = synth.vlp16_scan(n_raw, 5, t0=0.0)
     sh = point_shard_rows(n_raw, n_raw, world, rank)
     sl = slice(sh["row0"], sh["row0"] + sh["n_raw"])
-    mass = torch.tensor([[w[sl].sum(), w[sl].sum(), (w[sl] ** 2).sum(), float(sh["n_raw"])]], dtype=torch.float64)
-    allreduce_bin_sums(mass=mass)
+    # the exchange of the point-sharded path (one packed buffer, one all-gather, rank-ordered reduction) on host tensors
+    raw_len = 48 * (1 + 3 + 9 + 3 + 9) + 2
+    x = PointShardExchange(SimpleNamespace(S=1, U=1, raw_len=raw_len, io=SimpleNamespace(dev=torch.device("cpu"))))
+    x.mass[0] = torch.tensor([w[sl].sum(), w[sl].sum(), (w[sl] ** 2).sum(), float(sh["n_raw"])], dtype=torch.float64)
+    x.exchange_mass()
+    mass = x.mass.clone()
     scale = float(mass[0, 0] / (mass[0, 1] + 1e-12))
     bins = synth.fibonacci_atlas(48)
     a = _oracle_additive(pts[sl], t[sl], w[sl], 0.0, 0.1, synth.scan_twist(5), synth.lidar_origin_base(), bins, 0.1, scale)
-    raw = torch.from_numpy(np.concatenate([a["N"], a["s_dir"].ravel(), a["S"].ravel(), a["sum_p"].ravel(), a["sum_pp"].ravel(), a["ent"]]))
-    mx = torch.from_numpy(a["mx"].copy())
-    allreduce_bin_sums(raw_sums=raw, raw_max=mx)
-    L = torch.full((2, 22, 22), float(rank + 1), dtype=torch.float64)
-    h = torch.full((2, 22), float(rank + 1), dtype=torch.float64)
+    x.raw_sums[0] = torch.from_numpy(np.concatenate([a["N"], a["s_dir"].ravel(), a["S"].ravel(), a["sum_p"].ravel(), a["sum_pp"].ravel(), a["ent"]]))
+    x.raw_max[0, 0] = float(a["mx"][0])
+    x.exchange_sums()
+    raw, mx = x.raw_sums[0].clone(), x.raw_max[0, :1].clone()
+    # five hypotheses on two ranks: 3 + 2 (uneven stacks through the gather)
+    lo, hi = shard_range(5, world, rank)
+    L = torch.stack([torch.full((22, 22), float(k + 1), dtype=torch.float64) for k in range(lo, hi)])
+    h = torch.stack([torch.full((22,), float(k + 1), dtype=torch.float64) for k in range(lo, hi)])
     Lg, hg = gather_evidence(L, h)
     if rank == 0:
         out_q.put((mass.numpy(), raw.numpy(), mx.numpy(), Lg.numpy()[:, 0, 0].copy(), hg.shape))
@@ -102,7 +110,10 @@ def test_point_sharded_allreduce_gloo_world2():
     full = _oracle_additive(pts, t, w, 0.0, 0.1, synth.scan_twist(5), synth.lidar_origin_base(), synth.fibonacci_atlas(48), 0.1, scale)
     ref = np.concatenate([full["N"], full["s_dir"].ravel(), full["S"].ravel(), full["sum_p"].ravel(), full["sum_pp"].ravel(), full["ent"]])
     assert rel_err(raw, ref) < 1e-12 and abs(mx[0] - full["mx"][0]) < 1e-15
-    assert list(Ldiag) == [1.0, 1.0, 2.0, 2.0] and tuple(hshape) == (4, 22)
+    assert list(Ldiag) == [1.0, 2.0, 3.0, 4.0, 5.0] and tuple(hshape) == (5, 22)
+    from gc_slam_b200.sharding import point_shard_rows
+    with pytest.raises(ValueError):
+        point_shard_rows(3, 8192, 4, 0)      # fewer selected rows than ranks: rejected, not an empty shard
 
 
 def test_hypothesis_barycenter_host_combine():
