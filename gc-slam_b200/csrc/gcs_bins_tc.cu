@@ -458,8 +458,9 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
     const double* pts = P.pts + (int64_t)s * P.n_raw * 3;
     const double* tp = P.t + (int64_t)s * P.n_raw;
     const double* wp = P.w + (int64_t)s * P.n_raw;
-    const uint8_t* rp = P.ring ? P.ring + (int64_t)s * P.n_raw : nullptr;
-    const uint8_t* gp = P.tag ? P.tag + (int64_t)s * P.n_raw : nullptr;
+    // ring / tag only pass through to the resampled rows: not read at all when those are not materialised
+    const uint8_t* rp = (P.ring && P.rs_pts) ? P.ring + (int64_t)s * P.n_raw : nullptr;
+    const uint8_t* gp = (P.tag && P.rs_pts) ? P.tag + (int64_t)s * P.n_raw : nullptr;
     double* const dkp = P.dk_pts ? P.dk_pts + (int64_t)u * P.cap * 3 : nullptr;
     double* const dkw = P.dk_w ? P.dk_w + (int64_t)u * P.cap : nullptr;
     // 16-byte paths: consecutive raw rows (stride 1) and 16-byte aligned scan / unit bases (pair index is even)
@@ -472,20 +473,23 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
 
     // software pipeline: the raw rows of the warp's next tile are requested before this tile is processed
     double nx[10];
-    uint32_t nrt = 0;   // ring a | ring b << 8 | tag a << 16 | tag b << 24
+    // ring / tag of the pair as loaded (ring a | ring b << 8, tag a | tag b << 8): kept in registers of their own and only
+    // combined where they are used -- any arithmetic on a prefetched value at the prefetch site waits for the load there
+    // (8 % of all stall samples sat on the shift that used to merge them)
+    unsigned short nring = 0, ntag = 0;
     auto fetch = [&](int64_t tile) {
       const int64_t ia = tile * kTile + 2 * lane;
 #pragma unroll
       for (int k = 0; k < 10; ++k) nx[k] = 0.0;
-      nrt = 0;
+      nring = 0; ntag = 0;
       if (tile >= lt1) return;
       if (vec_in && ia + 1 < P.n_sel) {
         const double2 a0 = ldg_d2(pts + 3 * ia), a1 = ldg_d2(pts + 3 * ia + 2), a2 = ldg_d2(pts + 3 * ia + 4);
         const double2 tt = ldg_d2(tp + ia), ww = ldg_d2(wp + ia);
         nx[0] = a0.x; nx[1] = a0.y; nx[2] = a1.x; nx[3] = tt.x; nx[4] = ww.x;
         nx[5] = a1.y; nx[6] = a2.x; nx[7] = a2.y; nx[8] = tt.y; nx[9] = ww.y;
-        if (rp) nrt |= (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(rp + ia));
-        if (gp) nrt |= (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(gp + ia)) << 16;
+        if (rp) nring = __ldg(reinterpret_cast<const unsigned short*>(rp + ia));
+        if (gp) ntag = __ldg(reinterpret_cast<const unsigned short*>(gp + ia));
       } else {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -493,8 +497,8 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
             const int64_t j = (ia + q) * P.stride;
             nx[5 * q] = pts[3 * j]; nx[5 * q + 1] = pts[3 * j + 1]; nx[5 * q + 2] = pts[3 * j + 2];
             nx[5 * q + 3] = tp[j]; nx[5 * q + 4] = wp[j];
-            if (rp) nrt |= (uint32_t)rp[j] << (8 * q);
-            if (gp) nrt |= (uint32_t)gp[j] << (16 + 8 * q);
+            if (rp) nring |= (unsigned short)((unsigned)rp[j] << (8 * q));
+            if (gp) ntag |= (unsigned short)((unsigned)gp[j] << (8 * q));
           }
         }
       }
@@ -507,15 +511,15 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
       const double pa[3] = {nx[0], nx[1], nx[2]}, pb[3] = {nx[5], nx[6], nx[7]};
       const double tta = nx[3], ttb = nx[8];
       const double w_rs_a = nx[4] * mass_scale, w_rs_b = nx[9] * mass_scale;
-      const uint32_t rt = nrt;
+      const unsigned short ring2 = nring, tag2 = ntag;
       fetch(lt + kProd);
       if (h == 0 && P.rs_pts && row_a) {
         const int64_t o = (int64_t)s * P.cap + ia;
         P.rs_pts[3 * o] = pa[0]; P.rs_pts[3 * o + 1] = pa[1]; P.rs_pts[3 * o + 2] = pa[2];
-        P.rs_t[o] = tta; P.rs_w[o] = w_rs_a; P.rs_ring[o] = (uint8_t)rt; P.rs_tag[o] = (uint8_t)(rt >> 16);
+        P.rs_t[o] = tta; P.rs_w[o] = w_rs_a; P.rs_ring[o] = (uint8_t)ring2; P.rs_tag[o] = (uint8_t)tag2;
         if (row_b) {
           P.rs_pts[3 * o + 3] = pb[0]; P.rs_pts[3 * o + 4] = pb[1]; P.rs_pts[3 * o + 5] = pb[2];
-          P.rs_t[o + 1] = ttb; P.rs_w[o + 1] = w_rs_b; P.rs_ring[o + 1] = (uint8_t)(rt >> 8); P.rs_tag[o + 1] = (uint8_t)(rt >> 24);
+          P.rs_t[o + 1] = ttb; P.rs_w[o + 1] = w_rs_b; P.rs_ring[o + 1] = (uint8_t)(ring2 >> 8); P.rs_tag[o + 1] = (uint8_t)(tag2 >> 8);
         }
       }
       const double alpha_a = (tta - t0) * inv_denom, alpha_b = (ttb - t0) * inv_denom;
