@@ -85,6 +85,8 @@ PROTOTYPES = {
     "gcs_destroy": (_int, [_vp]),
     "gcs_last_error": (C.c_char_p, [_vp]),
     "gcs_reserve_workspace": (_int, [_vp, C.c_uint64]),
+    "gcs_workspace_freeze": (_int, [_vp, _int]),
+    "gcs_workspace_bytes": (C.c_uint64, [_vp]),
     "gcs_device_sm_count": (_int, [_vp]),
     "gcs_kernel_launches": (C.c_uint64, [_vp]),
     "gcs_timing_enable": (_int, [_vp, _int]),
@@ -177,6 +179,17 @@ class Context:
     @property
     def sm_count(self) -> int:
         return int(self.lib.gcs_device_sm_count(self.handle))
+
+    def reserve_workspace(self, nbytes: int):
+        self.check(self.lib.gcs_reserve_workspace(self.handle, int(nbytes)))
+
+    def freeze_workspace(self, frozen: bool = True):
+        """After this, a call that would have to grow the workspace raises instead (steady state never allocates)."""
+        self.check(self.lib.gcs_workspace_freeze(self.handle, 1 if frozen else 0))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.gcs_workspace_bytes(self.handle))
 
     def timing_enable(self, on=True, only: str = None):
         """Bracket the dominant kernels with CUDA events; `only`: one of TIME_TAGS (e.g. "topk") to time just that kernel."""

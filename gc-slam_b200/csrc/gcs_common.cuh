@@ -17,6 +17,9 @@ struct gcs_ctx {
   int sm_count;
   void* ws;  // grow-only device workspace
   uint64_t ws_bytes;
+  void* ws_retired[32];  // outgrown blocks: freed in gcs_destroy / gcs_reserve_workspace, never while streams may use them
+  int n_retired;
+  int ws_frozen;         // gcs_workspace_freeze: growth inside a call is an error (steady state never allocates)
   uint64_t launches;
   // optional CUDA-event timing of the dominant kernel (gcs_timing_*): pairs recorded on the launching stream
   int timing_on;   // 0 off, 1 every bracketed kernel, 100 + tag: only the kernel with that tag (GCS_TIME_*)
@@ -52,26 +55,11 @@ int gcs_ws_reserve(gcs_ctx* ctx, uint64_t bytes);
     if (!(cond)) return gcs_set_error((ctx), GCS_EINVAL, __VA_ARGS__);   \
   } while (0)
 
-// Opt a kernel in to `bytes` of dynamic shared memory once per (kernel, device).  Function attributes belong to the
-// device's context, so a process that drives several GPUs (one gcs_ctx per device) must set them on each; a flag per
-// process would leave the second device with the 48 KB default and its first launch would fail.
-inline cudaError_t gcs_smem_attr_once(const void* kern, int bytes) {
-  struct Entry { const void* k; unsigned long long devs; int bytes; };
-  static Entry tab[64];
-  static int n = 0;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  for (int i = 0; i < n; ++i)
-    if (tab[i].k == kern) {
-      if (dev < 64 && ((tab[i].devs >> dev) & 1ull) && tab[i].bytes >= bytes) return cudaSuccess;
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-      if (e == cudaSuccess && dev < 64) { tab[i].devs = (tab[i].bytes >= bytes ? tab[i].devs : 0ull) | (1ull << dev); if (bytes > tab[i].bytes) tab[i].bytes = bytes; }
-      return e;
-    }
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess && n < 64) { tab[n].k = kern; tab[n].devs = dev < 64 ? (1ull << dev) : 0ull; tab[n].bytes = bytes; ++n; }
-  return e;
-}
+// Opt a kernel in to `bytes` of dynamic shared memory.  Function attributes belong to the device's context, so a process
+// that drives several GPUs (one gcs_ctx per device, possibly one thread each) must set them on each: the table keeps the
+// largest size set so far PER (kernel, device) and is guarded by a mutex -- contexts are per thread, this table is per
+// process.  Defined once in gcs_context.cu.
+cudaError_t gcs_smem_attr_once(const void* kern, int bytes);
 
 #define GCS_LAUNCH_CHECK(ctx)                        \
   do {                                               \

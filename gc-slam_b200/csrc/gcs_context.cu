@@ -15,19 +15,58 @@ int gcs_set_error(gcs_ctx* ctx, int code, const char* fmt, ...) {
   return code;
 }
 
+#include <mutex>
+
+cudaError_t gcs_smem_attr_once(const void* kern, int bytes) {
+  struct Entry { const void* k; int bytes[64]; };   // bytes[d]: largest size set for this kernel on device d (0: never)
+  static Entry tab[128];
+  static int n = 0;
+  static std::mutex mu;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  Entry* ent = nullptr;
+  for (int i = 0; i < n; ++i)
+    if (tab[i].k == kern) { ent = &tab[i]; break; }
+  if (ent && dev < 64 && ent->bytes[dev] >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  if (!ent && n < 128) { ent = &tab[n++]; ent->k = kern; memset(ent->bytes, 0, sizeof(ent->bytes)); }
+  if (ent && dev < 64) ent->bytes[dev] = bytes;
+  return cudaSuccess;
+}
+
+// Grow-only workspace.  Growth doubles (at least) so that it happens a handful of times per process; an outgrown block
+// is RETIRED, not freed: cudaFree synchronises the device and kernels enqueued by earlier calls may still be reading it.
+// Retired blocks are released by gcs_reserve_workspace (a call made outside the steady state) and gcs_destroy.
 int gcs_ws_reserve(gcs_ctx* ctx, uint64_t bytes) {
   if (bytes <= ctx->ws_bytes) return GCS_OK;
-  // grow-only; rounded up so that steady-state calls never allocate
+  if (ctx->ws_frozen)
+    return gcs_set_error(ctx, GCS_ENOMEM, "workspace frozen at %llu bytes, this call needs %llu: size it with "
+                         "gcs_reserve_workspace before gcs_workspace_freeze", (unsigned long long)ctx->ws_bytes,
+                         (unsigned long long)bytes);
   uint64_t want = ((bytes + (1ull << 20) - 1) >> 20) << 20;
+  if (want < 2 * ctx->ws_bytes) want = 2 * ctx->ws_bytes;
   void* p = nullptr;
   cudaError_t e = cudaMalloc(&p, want);
   if (e != cudaSuccess)
     return gcs_set_error(ctx, GCS_ENOMEM, "workspace cudaMalloc(%llu) failed: %s", (unsigned long long)want,
                          cudaGetErrorString(e));
-  if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->ws) {
+    if (ctx->n_retired < 32) ctx->ws_retired[ctx->n_retired++] = ctx->ws;
+    else { cudaDeviceSynchronize(); cudaFree(ctx->ws); }
+  }
   ctx->ws = p;
   ctx->ws_bytes = want;
   return GCS_OK;
+}
+
+static void gcs_ws_release_retired(gcs_ctx* ctx) {
+  if (ctx->n_retired == 0) return;
+  cudaDeviceSynchronize();
+  for (int i = 0; i < ctx->n_retired; ++i) cudaFree(ctx->ws_retired[i]);
+  ctx->n_retired = 0;
 }
 
 extern "C" {
@@ -57,6 +96,9 @@ int gcs_create(gcs_ctx** out, int device) {
   if (!c) return gcs_set_error(nullptr, GCS_ENOMEM, "gcs_create: calloc");
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  // default workspace: enough for a single scan of the reference budgets through either family, so that the first calls
+  // do not allocate; batches size themselves once (or up front through gcs_reserve_workspace)
+  if (gcs_ws_reserve(c, 32ull << 20) != GCS_OK) { free(c); return gcs_set_error(nullptr, GCS_ENOMEM, "gcs_create: workspace"); }
   *out = c;
   return GCS_OK;
 }
@@ -92,6 +134,7 @@ int gcs_destroy(gcs_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->timing_ev[0])
     for (int i = 0; i < 2 * 256; ++i) cudaEventDestroy(ctx->timing_ev[i]);
+  gcs_ws_release_retired(ctx);
   if (ctx->ws) cudaFree(ctx->ws);
   free(ctx);
   return GCS_OK;
@@ -102,8 +145,21 @@ const char* gcs_last_error(gcs_ctx* ctx) { return ctx ? ctx->err : g_create_err;
 int gcs_reserve_workspace(gcs_ctx* ctx, uint64_t bytes) {
   if (!ctx) return GCS_EINVAL;
   GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-  return gcs_ws_reserve(ctx, bytes);
+  const int frozen = ctx->ws_frozen;
+  ctx->ws_frozen = 0;
+  const int rc = gcs_ws_reserve(ctx, bytes);
+  ctx->ws_frozen = frozen;
+  gcs_ws_release_retired(ctx);   // an explicit sizing call is made outside the steady state: safe to synchronise
+  return rc;
 }
+
+int gcs_workspace_freeze(gcs_ctx* ctx, int frozen) {
+  if (!ctx) return GCS_EINVAL;
+  ctx->ws_frozen = frozen ? 1 : 0;
+  return GCS_OK;
+}
+
+uint64_t gcs_workspace_bytes(gcs_ctx* ctx) { return ctx ? ctx->ws_bytes : 0; }
 
 int gcs_device_sm_count(gcs_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 

@@ -135,7 +135,12 @@ extern "C" int gcs_parse_pointcloud2_vlp16(gcs_ctx* ctx, void* stream, const uin
                                            const gcs_pc2_layout* lay, const double* header_stamp,
                                            const double* R_base_lidar, const double* t_base_lidar, double* pts, double* t,
                                            double* w, uint8_t* ring, uint8_t* tag, double* cert) {
+  if (!ctx) return GCS_EINVAL;
+  GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
   GCS_REQUIRE(ctx, lay != nullptr, "gcs_parse_pointcloud2_vlp16: layout is NULL");
+  // the decoder reads the payload in aligned 16-byte words
+  GCS_REQUIRE(ctx, n_points == 0 || (data != nullptr && ((uintptr_t)data & 15) == 0),
+              "gcs_parse_pointcloud2_vlp16: payload pointer must be 16-byte aligned (clone a view with an odd storage offset)");
   GCS_REQUIRE(ctx, n_msgs >= 1 && n_points >= 0, "gcs_parse_pointcloud2_vlp16: n_msgs=%d n_points=%lld", n_msgs, (long long)n_points);
   // backend_node.py:398-403: x, y, z, ring are required
   GCS_REQUIRE(ctx, lay->off_x >= 0 && lay->off_y >= 0 && lay->off_z >= 0 && lay->off_ring >= 0,

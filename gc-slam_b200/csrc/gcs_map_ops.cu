@@ -150,25 +150,32 @@ __global__ void __launch_bounds__(kOpsBig) fuse_sort_kernel(FuseArgs F, int m_ti
                                                             double* __restrict__ stats) {
   extern __shared__ unsigned long long fs[];
   __shared__ int cnt;
+  // n_fused of the reference = len(jnp.unique(target_slots)) over ALL entries as given (:1155): a first sort by the raw
+  // value counts those
+  for (int e = threadIdx.x; e < n_pow2; e += kOpsBig)
+    fs[e] = e < F.n ? (((unsigned long long)((unsigned)F.slots[e] ^ 0x80000000u) << 32) | (unsigned)e) : ~0ull;
+  if (threadIdx.x == 0) cnt = 0;
+  cta_bitonic_sort_u64(fs, n_pow2);
+  int local = 0;
+  for (int e = threadIdx.x; e < F.n; e += kOpsBig)
+    if (e == 0 || (unsigned)(fs[e - 1] >> 32) != (unsigned)(fs[e] >> 32)) ++local;
+  if (local) atomicAdd(&cnt, local);
+  __syncthreads();
+  if (threadIdx.x == 0) stats[0] = (double)cnt;
+  __syncthreads();
+  // segments of the scatter-add: a negative index in [-m_tile, -1] wraps as .at[].add wraps it, anything else outside
+  // [0, m_tile) is dropped as a JAX scatter drops it
   for (int e = threadIdx.x; e < n_pow2; e += kOpsBig) {
     unsigned long long x = ~0ull;
     if (e < F.n) {
-      const int s = F.slots[e];
+      int s = F.slots[e];
+      if (s < 0) s += m_tile;
       if (s >= 0 && s < m_tile) x = ((unsigned long long)(unsigned)s << 32) | (unsigned)e;
     }
     fs[e] = x;
   }
-  if (threadIdx.x == 0) cnt = 0;
   cta_bitonic_sort_u64(fs, n_pow2);
-  int local = 0;
-  for (int e = threadIdx.x; e < n_pow2; e += kOpsBig) {
-    const unsigned long long x = fs[e];
-    pairs[e] = x;
-    if (x != ~0ull && (e == 0 || (unsigned)(fs[e - 1] >> 32) != (unsigned)(x >> 32))) ++local;
-  }
-  if (local) atomicAdd(&cnt, local);
-  __syncthreads();
-  if (threadIdx.x == 0) stats[0] = (double)cnt;
+  for (int e = threadIdx.x; e < n_pow2; e += kOpsBig) pairs[e] = fs[e];
 }
 
 constexpr int kFuseVals = 29;   // dLambda 9, deta 9, dtheta 3, dw, dr, dcam, dlid, dacc 3, dden

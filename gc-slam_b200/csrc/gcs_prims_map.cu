@@ -579,7 +579,7 @@ __device__ __forceinline__ void cluster_sum(double (&v)[RPT][NV], double (*xch)[
 template <int K, int RPT>
 __global__ void __launch_bounds__(kSkThreads)
     assoc_sinkhorn_kernel(gcs_meas_batch B, int N, gcs_map_view V, AssocWs W, gcs_assoc_cfg cfg, gcs_assoc_result R,
-                          double* __restrict__ cert, double* __restrict__ brow_ws) {
+                          double* __restrict__ cert, double* __restrict__ brow_ws, double* __restrict__ a_ws) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ double xch[2][kSkCtas][kSkMaxVals];
@@ -595,6 +595,7 @@ __global__ void __launch_bounds__(kSkThreads)
     R = assoc_result_unit(R, un, N, K);
     cert += un * GCS_OT_NCERT;
     brow_ws += un * N * K;
+    a_ws += un * N;
   }
   int row[RPT];                             // N <= kSkCtas * kSkThreads = 2048
 #pragma unroll
@@ -603,12 +604,20 @@ __global__ void __launch_bounds__(kSkThreads)
   double Km[RPT][K], u[RPT], a[RPT];
   const double eps = fmax(cfg.epsilon, 1e-12);
   auto ident = [](int, double t) { return t; };
-  double nv[RPT][1];
+  // measurement marginal (primitive_association.py:412-424): UNIFORM valid / sum(valid), or WEIGHT_PROPORTIONAL
+  // valid * weight / sum(valid * weight)
+  const bool wprop = cfg.a_policy == 1;
+  double nv[RPT][2], araw[RPT];
 #pragma unroll
-  for (int q = 0; q < RPT; ++q) nv[q][0] = (row[q] < N && B.valid[row[q]]) ? 1.0 : 0.0;
-  cluster_sum<1, RPT>(nv, xch, sredw, tot, phase, ident);
+  for (int q = 0; q < RPT; ++q) {
+    const bool v = row[q] < N && B.valid[row[q]];
+    nv[q][0] = v ? 1.0 : 0.0;
+    araw[q] = v ? (wprop ? B.weights[row[q]] : 1.0) : 0.0;
+    nv[q][1] = araw[q];
+  }
+  cluster_sum<2, RPT>(nv, xch, sredw, tot, phase, ident);
   const double sum_valid = nv[0][0];
-  const double sum_a = fmax(sum_valid, cfg.eps_mass);
+  const double sum_a = fmax(wprop ? nv[0][1] : sum_valid, cfg.eps_mass);
 #pragma unroll
   for (int q = 0; q < RPT; ++q) {
     const int i = row[q];
@@ -616,7 +625,8 @@ __global__ void __launch_bounds__(kSkThreads)
 #pragma unroll
     for (int k = 0; k < K; ++k) Km[q][k] = 0.0;
     if (i < N) {
-      a[q] = (B.valid[i] ? 1.0 : 0.0) / sum_a;
+      a[q] = araw[q] / sum_a;
+      if (wprop) a_ws[i] = a[q];
       const double mp[3] = {W.mpos[3 * i], W.mpos[3 * i + 1], W.mpos[3 * i + 2]};
       const double md[3] = {W.mdir[3 * i], W.mdir[3 * i + 1], W.mdir[3 * i + 2]};
       const double mk = W.mkap[i];
@@ -670,18 +680,18 @@ __global__ void __launch_bounds__(kSkThreads)
     for (int k = 0; k < K; ++k) sv[k] = ktu[0][k];
   }
   // outputs + certificate sums
-  double cs[RPT][5 + K];
+  double cs[RPT][6 + K];
 #pragma unroll
   for (int q = 0; q < RPT; ++q) {
 #pragma unroll
-    for (int k = 0; k < 5 + K; ++k) cs[q][k] = 0.0;
+    for (int k = 0; k < 6 + K; ++k) cs[q][k] = 0.0;
     const int i = row[q];
     if (i < N) {
       const bool mv = B.valid[i] != 0;
       double rowm = 0.0;
       for (int k = 0; k < K; ++k) {
         const double pi = u[q] * Km[q][k] * sv[k];
-        rowm += pi; cs[q][5 + k] += pi; cs[q][4] += pi * R.cost_matrix[i * K + k];
+        rowm += pi; cs[q][6 + k] += pi; cs[q][4] += pi * R.cost_matrix[i * K + k];
         R.responsibilities[i * K + k] = mv ? pi : 0.0;
       }
       R.row_masses[i] = rowm;
@@ -689,12 +699,13 @@ __global__ void __launch_bounds__(kSkThreads)
       const double d = rowm - a[q];
       cs[q][2] = d * d;
       cs[q][3] = fmax(a[q] - rowm, 0.0);
+      cs[q][5] = a[q] > cfg.eps_mass ? 1.0 : 0.0;
     }
   }
-  cluster_sum<5 + K, RPT>(cs, xch, sredw, tot, phase, ident);
-  const double S_row = cs[0][0], S_row2 = cs[0][1], S_da = cs[0][2], S_nov = cs[0][3], S_cost = cs[0][4];
+  cluster_sum<6 + K, RPT>(cs, xch, sredw, tot, phase, ident);
+  const double S_row = cs[0][0], S_row2 = cs[0][1], S_da = cs[0][2], S_nov = cs[0][3], S_cost = cs[0][4], n_nz_a = cs[0][5];
   double db = 0.0;
-  for (int k = 0; k < K; ++k) db += (cs[0][5 + k] - bk) * (cs[0][5 + k] - bk);
+  for (int k = 0; k < K; ++k) db += (cs[0][6 + k] - bk) * (cs[0][6 + k] - bk);
   // no CTA may exit while another still reads its exchange buffer; the barrier also makes the brow_ws rows written by
   // every CTA visible to rank 0, which finishes alone
   cluster.sync();
@@ -710,18 +721,25 @@ __global__ void __launch_bounds__(kSkThreads)
     cta_select_k(total, kk, key, sel.out, sel.hist, sel.scan);
     b95 = brow_ws[sel.out[kk - 1].idx];
   }
+  int ia = (int)(0.95 * (double)N);
+  if (ia > N - 1) ia = N - 1;
+  double a95 = 0.0;      // WEIGHT_PROPORTIONAL: sorted(a)[ia] = the (N - ia)-th largest of the stored marginal
+  if (wprop && N - ia >= 1 && N - ia <= 1024) {
+    __syncthreads();
+    auto keya = [&](int j) -> unsigned long long { return ~f64_orderable(a_ws[j]); };  // descending
+    cta_select_k(N, N - ia, keya, sel.out, sel.hist, sel.scan);
+    a95 = a_ws[sel.out[N - ia - 1].idx];
+  }
   if (tid == 0) {
     const int n0 = N - (int)sum_valid;  // zeros of a sort first
-    int ia = (int)(0.95 * (double)N);
-    if (ia > N - 1) ia = N - 1;
     cert[GCS_OT_MARGINAL_A] = sqrt(S_da);
     cert[GCS_OT_MARGINAL_B] = sqrt(db);
     cert[GCS_OT_MASS_TOTAL] = S_row;
     cert[GCS_OT_SUM_A] = sum_a;
     cert[GCS_OT_SUM_M] = S_row;
     cert[GCS_OT_SUM_NOVEL] = S_nov;
-    cert[GCS_OT_P95_A] = (ia < n0) ? 0.0 : 1.0 / sum_a;
-    cert[GCS_OT_NONZERO_A] = ((1.0 / sum_a) > cfg.eps_mass) ? sum_valid : 0.0;
+    cert[GCS_OT_P95_A] = wprop ? a95 : ((ia < n0) ? 0.0 : 1.0 / sum_a);
+    cert[GCS_OT_NONZERO_A] = wprop ? n_nz_a : (((1.0 / sum_a) > cfg.eps_mass) ? sum_valid : 0.0);
     cert[GCS_OT_B_RECENCY_P95] = b95;
     cert[GCS_OT_ESS] = S_row * S_row / (S_row2 + cfg.eps_mass);
     cert[GCS_OT_TOTAL_COST] = S_cost;
@@ -732,7 +750,7 @@ __global__ void __launch_bounds__(kSkThreads)
 
 template <int RPT>
 static cudaError_t sinkhorn_launch(cudaStream_t st, unsigned n_units, gcs_meas_batch B, int N, gcs_map_view V, AssocWs W,
-                                   gcs_assoc_cfg cfg, gcs_assoc_result R, double* cert, double* brow) {
+                                   gcs_assoc_cfg cfg, gcs_assoc_result R, double* cert, double* brow, double* a_ws) {
   cudaLaunchConfig_t lc;
   memset(&lc, 0, sizeof(lc));
   lc.gridDim = dim3(kSkCtas / RPT, n_units, 1);
@@ -743,7 +761,7 @@ static cudaError_t sinkhorn_launch(cudaStream_t st, unsigned n_units, gcs_meas_b
   at[0].val.clusterDim.x = kSkCtas / RPT; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   lc.attrs = at;
   lc.numAttrs = 1;
-  return cudaLaunchKernelEx(&lc, assoc_sinkhorn_kernel<8, RPT>, B, N, V, W, cfg, R, cert, brow);
+  return cudaLaunchKernelEx(&lc, assoc_sinkhorn_kernel<8, RPT>, B, N, V, W, cfg, R, cert, brow, a_ws);
 }
 
 // every unit of a stacked batch := the base batch (camera slice, zero LiDAR rows); blockIdx.y = unit
@@ -1425,6 +1443,7 @@ static int assoc_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_meas_batch* bat
   if (rc) return rc;
   GCS_REQUIRE(ctx, cfg && cert && view_tile_ids, "%s: NULL pointer", who);
   GCS_REQUIRE(ctx, cfg->k_assoc == 8, "%s: k_assoc=%d (this build instantiates K_ASSOC=8)", who, cfg->k_assoc);
+  GCS_REQUIRE(ctx, cfg->a_policy == 0 || cfg->a_policy == 1, "%s: a_policy=%d (0 UNIFORM, 1 WEIGHT_PROPORTIONAL)", who, cfg->a_policy);
   GCS_REQUIRE(ctx, n_tiles >= 1 && n_tiles <= 16 && m_tile_view >= cfg->k_assoc, "%s: bad view shape", who);
   const int N = batch->n_feat + batch->n_surfel;
   GCS_REQUIRE(ctx, N >= 1 && N <= 2048, "%s: N_total=%d exceeds the single-cluster Sinkhorn budget 2048", who, N);
@@ -1448,7 +1467,7 @@ static int assoc_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_meas_batch* bat
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_pos = take(H * N * 3 * 8), o_dir = take(H * N * 3 * 8), o_kap = take(H * N * 8),
                o_st = take(H * N * n_st), o_brow = take(H * N * 8 * 8),
-               o_vak = take((size_t)n_tiles * m_tile_view * 8), o_ctr = take(256);
+               o_vak = take((size_t)n_tiles * m_tile_view * 8), o_ctr = take(256), o_aws = take(H * N * 8);
   rc = gcs_ws_reserve(ctx, off);
   if (rc) return rc;
   char* ws = (char*)ctx->ws;
@@ -1480,12 +1499,13 @@ static int assoc_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_meas_batch* bat
   GCS_LAUNCH_CHECK(ctx);
   // cluster size per hypothesis: eight SMs for one, fewer when the batch fills the device anyway
   double* brow = (double*)(ws + o_brow);
+  double* a_ws = (double*)(ws + o_aws);
   // the iterations are a latency chain (log / exp / barrier), so as many CTAs as stay resident (three per SM) overlap
   const int sk_rpt = (n_units * 8 <= 3 * ctx->sm_count) ? 1 : (n_units * 4 <= 3 * ctx->sm_count ? 2 : 4);
   gcs_timing_begin(ctx, st, GCS_TIME_SINKHORN);
-  if (sk_rpt == 1) GCS_CHECK_CUDA(ctx, sinkhorn_launch<1>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow));
-  else if (sk_rpt == 2) GCS_CHECK_CUDA(ctx, sinkhorn_launch<2>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow));
-  else GCS_CHECK_CUDA(ctx, sinkhorn_launch<4>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow));
+  if (sk_rpt == 1) GCS_CHECK_CUDA(ctx, sinkhorn_launch<1>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow, a_ws));
+  else if (sk_rpt == 2) GCS_CHECK_CUDA(ctx, sinkhorn_launch<2>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow, a_ws));
+  else GCS_CHECK_CUDA(ctx, sinkhorn_launch<4>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow, a_ws));
   gcs_timing_end(ctx, st, GCS_TIME_SINKHORN);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;

@@ -107,13 +107,14 @@ def _launch(io, L_lidar, h_lidar, L_other, h_other, L_prior, h_prior, scal, cfg_
 
 def evidence_fusion_batched(L_lidar, h_lidar, L_imu_odom, h_imu_odom, L_prior, h_prior, ess_total, excitation_total,
                             nll_per_ess=None, config: Optional[FusionConfig] = None, chart_id: str = constants.GC_CHART_ID,
-                            anchor_id: str = "evidence_fusion"
+                            anchor_id: str = "evidence_fusion", support_frac=1.0
                             ) -> Tuple[EvidenceFusionResult, "_PerHypothesis", "_PerHypothesis"]:
     """
     Steps 9-11 of process_scan_single_hypothesis (fl/backend/pipeline.py:1038-1207) for K hypotheses at once: the stacks may
     come straight from a K-hypothesis BinPathPlan (L22, h22) and go straight into hypothesis_barycenter_projection; one
     launch, one read-back of the (K, 24) record.  ess_total / excitation_total / nll_per_ess: per-hypothesis scalars of the
-    aggregated evidence certificate (support.ess_total, excitation.dt_effect + extrinsic_effect, mismatch.nll_per_ess).
+    aggregated evidence certificate (support.ess_total, excitation.dt_effect + extrinsic_effect, mismatch.nll_per_ess;
+    support_frac = its support.support_frac, which only enters the fusion-scale certificate's cond_to_support).
     Returns the result, and per hypothesis the certificates the reference appends at these steps
     ([PowerTempering, ExcitationPriorScaling, fusion scale (exact), InfoFusionAdditive]) and the fusion's ExpectedEffect --
     as sequences that build entry k when it is read (len(), indexing, iteration).
@@ -124,10 +125,11 @@ def evidence_fusion_batched(L_lidar, h_lidar, L_imu_odom, h_imu_odom, L_prior, h
     K = ess.shape[0]
     exc = np.broadcast_to(np.asarray(excitation_total, dtype=np.float64).reshape(-1), (K,))
     nll = np.zeros(K) if nll_per_ess is None else np.broadcast_to(np.asarray(nll_per_ess, dtype=np.float64).reshape(-1), (K,))
+    sup = np.broadcast_to(np.asarray(support_frac, dtype=np.float64).reshape(-1), (K,))
     scal = np.stack([ess, exc, nll, np.zeros(K)], axis=1)
     L_post, h_post, aux, rec_d = _launch(io, L_lidar, h_lidar, L_imu_odom, h_imu_odom, L_prior, h_prior, scal, cfg._c())
     rec = io.host(rec_d)
-    certs = _PerHypothesis(K, lambda k: _step_certs(rec[k], float(exc[k]), chart_id, anchor_id, io if k == 0 else None))
+    certs = _PerHypothesis(K, lambda k: _step_certs(rec[k], float(exc[k]), chart_id, anchor_id, io if k == 0 else None, float(sup[k])))
     effects = _PerHypothesis(K, lambda k: ExpectedEffect("predicted_info_trace_increase", float(rec[k][FU["TRACE_INCREASE"]]), None))
     return EvidenceFusionResult(L_post, h_post, aux[0], aux[1], aux[2], aux[3], rec), certs, effects
 
@@ -158,7 +160,7 @@ class _PerHypothesis:
         return (self[k] for k in range(self._n))
 
 
-def _step_certs(r, exc_total, chart_id, anchor_id, io=None):
+def _step_certs(r, exc_total, chart_id, anchor_id, io=None, support_frac=1.0):
     """[PowerTempering, ExcitationPriorScaling, fusion scale, InfoFusionAdditive] of one hypothesis (pipeline.py:1108-1207)."""
     beta, alpha = float(r[FU["BETA"]]), float(r[FU["ALPHA"]])
     temper = CertBundle.create_approx(chart_id=chart_id, anchor_id=anchor_id, triggers=["PowerTempering"],
@@ -170,6 +172,7 @@ def _step_certs(r, exc_total, chart_id, anchor_id, io=None):
     scale_c = CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id,
                                       overconfidence=OverconfidenceCert(excitation_total=exc_total,
                                                                         ess_to_excitation=float(r[FU["ESS_TO_EXC"]]),
+                                                                        cond_to_support=float(r[FU["POSE_COND"]]) / (float(support_frac) + constants.GC_EPS_MASS),
                                                                         dt_asymmetry=float(r[FU["DT_ASYMMETRY"]]),
                                                                         z_to_xy_ratio=float(r[FU["Z_TO_XY"]])),
                                       conditioning=ConditioningCert(eig_min=float(r[FU["POSE_EIG_MIN"]]), eig_max=float(r[FU["POSE_EIG_MAX"]]),

@@ -99,14 +99,20 @@ class _IO:
 # `_drive` runs one operator the way the reference's call sites expect (one batched read-back, i.e. one host sync per
 # operator).  `drive_group` advances several operators to their yield first -- later ones may consume the provisional
 # (device-side) results of earlier ones -- and serves all their read-backs with ONE stream synchronisation.
-_PINNED = {}
+import threading
+
+_PINNED = threading.local()      # per calling thread (contexts are per thread: two threads never share a read-back buffer)
 
 
 def _pinned_like(t, slot):
-    key = (slot, t.dtype, t.numel())
-    buf = _PINNED.get(key)
+    """Pinned read-back buffer for (device, slot, dtype, size), private to the calling thread."""
+    cache = getattr(_PINNED, "bufs", None)
+    if cache is None:
+        cache = _PINNED.bufs = {}
+    key = (t.device.index, slot, t.dtype, t.numel())
+    buf = cache.get(key)
     if buf is None:
-        buf = _PINNED[key] = torch.empty(t.numel(), dtype=t.dtype).pin_memory()
+        buf = cache[key] = torch.empty(t.numel(), dtype=t.dtype).pin_memory()
     return buf
 
 
@@ -133,13 +139,18 @@ class _Pending:
 def drive_group(pending):
     """Finish a list of _Pending operators with one stream synchronisation; returns their final values in order."""
     live = [p for p in pending if not p.done]
-    bufs = []
+    bufs, events = [], {}
     for k, p in enumerate(live):
         b = _pinned_like(p.tensor, k)
-        b.copy_(p.tensor.detach().reshape(-1), non_blocking=True)
+        with torch.cuda.device(p.io.dev):
+            b.copy_(p.tensor.detach().reshape(-1), non_blocking=True)
+            # an event on the stream that performed this copy (operators of one group may live on different devices)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(p.io.dev))
+        events[p.io.dev] = ev
         bufs.append(b)
-    if live:
-        torch.cuda.current_stream(live[0].io.dev).synchronize()
+    for ev in events.values():
+        ev.synchronize()
     for k, (p, b) in enumerate(zip(live, bufs)):
         p.io.d2h += b.numel() * b.element_size()
         p.io.syncs += 1 if k == 0 else 0
@@ -313,6 +324,8 @@ def parse_pointcloud2_vlp16(data, n_points: int, point_step: int, fields, header
         return pts, t, w, ring, tag, dict(n_nonfinite=0, time_rescaled=False)
     if isinstance(data, torch.Tensor) and data.is_cuda:
         d_dev = data.reshape(-1)
+        if d_dev.data_ptr() % 16:          # a view with an odd storage offset: the decoder needs 16-byte alignment
+            d_dev = d_dev.clone()
         if d_dev.numel() % 16:
             d_dev = torch.cat([d_dev, torch.zeros((-d_dev.numel()) % 16, dtype=torch.uint8, device=d_dev.device)])
     else:

@@ -81,7 +81,7 @@ class CMapExport(C.Structure):
 
 
 class CAssocCfg(C.Structure):
-    _fields_ = [(n, _i32) for n in ("k_assoc", "k_sinkhorn", "r_stencil_xy", "r_stencil_z")] + \
+    _fields_ = [(n, _i32) for n in ("k_assoc", "k_sinkhorn", "r_stencil_xy", "r_stencil_z", "a_policy", "reserved_")] + \
                [(n, _dbl) for n in ("beta", "epsilon", "tau_a", "tau_b", "eps_mass", "eps_lift", "h_tile",
                                     "recency_decay_lambda")] + [("scan_seq", _i64)]
 
@@ -605,9 +605,7 @@ def _associate_primitives_ot_gen(measurement_batch, map_view, config=None, eps_l
 
 
 def _check_assoc_config(config):
-    if config.a_policy != MeasurementMassPolicy.UNIFORM:
-        if config.a_policy == MeasurementMassPolicy.WEIGHT_PROPORTIONAL:
-            raise ValueError("MeasurementMassPolicy.WEIGHT_PROPORTIONAL is not built in this release (pipeline uses UNIFORM)")
+    if config.a_policy not in (MeasurementMassPolicy.UNIFORM, MeasurementMassPolicy.WEIGHT_PROPORTIONAL):
         raise ValueError(f"Unsupported measurement mass policy: {config.a_policy}. Only UNIFORM and WEIGHT_PROPORTIONAL are implemented.")
     if config.b_policy != MapMassPolicy.UNIFORM:
         raise ValueError(f"Unsupported map mass policy: {config.b_policy}. Only UNIFORM is implemented.")
@@ -617,7 +615,7 @@ def _check_assoc_config(config):
 
 def _c_assoc_cfg(config, eps_lift) -> CAssocCfg:
     return CAssocCfg(int(config.k_assoc), int(config.k_sinkhorn), int(config.r_stencil_tiles_xy), int(config.r_stencil_tiles_z),
-                     float(config.beta), float(config.epsilon), float(config.tau_a), float(config.tau_b), float(config.eps_mass),
+                     1 if config.a_policy == MeasurementMassPolicy.WEIGHT_PROPORTIONAL else 0, 0, float(config.beta), float(config.epsilon), float(config.tau_a), float(config.tau_b), float(config.eps_mass),
                      float(eps_lift), float(config.h_tile), float(config.recency_decay_lambda), int(config.scan_seq))
 
 
@@ -1015,6 +1013,9 @@ def primitive_map_fuse(atlas_map: AtlasMap, tile_id: int, target_slots, Lambdas_
     if n == 0:
         return (PrimitiveMapFuseResult(atlas_map=atlas_map, tile_id=tile_id, n_fused=0),
                 CertBundle.create_exact(chart_id=chart_id, anchor_id=anchor_id), ExpectedEffect("primitive_map_fuse", 0.0, 0.0))
+    if n > 16384:      # checked before the tile is created: a rejected call leaves the map as it was
+        raise ValueError(f"primitive_map_fuse: {n} proposals in one call exceed the built budget of 16384 (the pipeline "
+                         f"fuses assoc_block_size x K_ASSOC = 2048 per call)")
     Lm = io.dev_in(Lambdas_meas, F64, (n, 3, 3))
     th = io.dev_in(thetas_meas, F64, (n, 3))
     et = io.dev_in(etas_meas, F64, (n, constants.GC_VMF_N_LOBES, 3))

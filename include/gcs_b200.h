@@ -44,7 +44,14 @@ const char* gcs_version_string(void);   /* "gcs_sm100a <semver>" : used for Runt
 int gcs_create(gcs_ctx** out, int device);
 int gcs_destroy(gcs_ctx* ctx);
 const char* gcs_last_error(gcs_ctx* ctx); /* ctx may be NULL: returns the last create() failure             */
-int gcs_reserve_workspace(gcs_ctx* ctx, uint64_t bytes); /* optional: pre-size so later calls never allocate */
+/* Workspace: gcs_create allocates 32 MB (a single scan of the reference budgets through either family); larger batches
+ * grow it on first use (doubling; the outgrown block is retired, not freed, so nothing synchronises a live stream).
+ * gcs_reserve_workspace sizes it up front (and releases retired blocks: call it outside the steady state);
+ * gcs_workspace_freeze(ctx, 1) turns any later in-call growth into GCS_ENOMEM -- the steady state then provably never
+ * allocates.  gcs_workspace_bytes reports the current size (run the workload once, read it, reserve that next time).  */
+int gcs_reserve_workspace(gcs_ctx* ctx, uint64_t bytes);
+int gcs_workspace_freeze(gcs_ctx* ctx, int frozen);
+uint64_t gcs_workspace_bytes(gcs_ctx* ctx);
 int gcs_device_sm_count(gcs_ctx* ctx);
 uint64_t gcs_kernel_launches(gcs_ctx* ctx); /* number of kernels this ctx has launched so far              */
 /* Measurement hook: when enabled, the dominant kernels of each path are bracketed by CUDA events on the launching
@@ -472,6 +479,9 @@ int gcs_export_map_points(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, co
 /* ---- a12 associate_primitives_ot : fl/backend/operators/primitive_association.py:105-553 -------------------- */
 typedef struct {
   int32_t k_assoc, k_sinkhorn, r_stencil_xy, r_stencil_z;
+  int32_t a_policy;   /* measurement marginal (primitive_association.py:412-424): 0 UNIFORM a = valid / sum(valid),
+                         1 WEIGHT_PROPORTIONAL a = valid * weight / sum(valid * weight)                              */
+  int32_t reserved_;
   double beta, epsilon, tau_a, tau_b, eps_mass, eps_lift, h_tile, recency_decay_lambda;
   int64_t scan_seq;
 } gcs_assoc_cfg;

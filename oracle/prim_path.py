@@ -389,7 +389,8 @@ def sinkhorn_unbalanced(Cm, a, b, epsilon, tau_a, tau_b, K):
 
 def associate_primitives_ot(batch, view, scan_seq=0, k_assoc=K_ASSOC, k_sinkhorn=K_SINKHORN, beta=0.5, epsilon=0.1,
                             tau_a=0.5, tau_b=0.5, eps_mass=EPS_MASS, h_tile=H_TILE, lam=RECENCY_DECAY_LAMBDA,
-                            eps_lift=EPS_LIFT, chunk=128):
+                            eps_lift=EPS_LIFT, chunk=128, a_policy="uniform"):
+    """primitive_association.py:239-553.  a_policy: "uniform" | "weight_proportional" (:412-424)."""
     N = batch["n_feat"] + batch["n_surfel"]
     n_valid = batch["n_camera_valid"] + batch["n_lidar_valid"]
     M_valid = int(np.sum(view["valid_mask"]))
@@ -428,8 +429,15 @@ def associate_primitives_ot(batch, view, scan_seq=0, k_assoc=K_ASSOC, k_sinkhorn
     cdt = np.maximum(0, np.int64(scan_seq) - view["last_supported_scan_seq"][cand]).astype(np.float64)
     Cm = Cm + float(epsilon) * float(lam) * cdt
     Cm = Cm - np.min(Cm, axis=1, keepdims=True)
-    sum_a = max(np.sum(vm), eps_mass)
-    a = vm / sum_a
+    if a_policy == "uniform":
+        sum_a = max(np.sum(vm), eps_mass)
+        a = vm / sum_a
+    elif a_policy == "weight_proportional":
+        weighted = vm * batch["weights"].astype(np.float64)
+        sum_a = max(np.sum(weighted), eps_mass)
+        a = weighted / sum_a
+    else:
+        raise ValueError(f"Unsupported measurement mass policy: {a_policy}. Only UNIFORM and WEIGHT_PROPORTIONAL are implemented.")
     b = np.ones(k_assoc) / float(k_assoc)
     pi = sinkhorn_unbalanced(Cm, a, b, epsilon, tau_a, tau_b, k_sinkhorn)
     row = np.sum(pi, axis=1)

@@ -78,11 +78,15 @@ def main():
         return lam, th, eta, w, col, src
 
     # ---------------- fuse
-    for name, m_tile, n, seed, full in (("mapops_fuse_masked_colors", 96, 700, 11, True), ("mapops_fuse_plain", 64, 150, 12, False)):
+    for name, m_tile, n, seed, full in (("mapops_fuse_masked_colors", 96, 700, 11, True), ("mapops_fuse_plain", 64, 150, 12, False),
+                                        ("mapops_fuse_negative_slots", 80, 300, 13, True)):
         td = dense_tile(3000, m_tile, seed)
         rng = np.random.default_rng(seed + 7)
         lam, th, eta, w, col, src = proposals(n, seed + 3)
         slots = rng.integers(0, m_tile // 2, size=n).astype(np.int32)     # many repeats per slot
+        if "negative" in name:     # .at[].add wraps indices in [-m_tile, -1]; jnp.unique counts -1 and m_tile - 1 separately
+            slots = rng.integers(-m_tile, m_tile, size=n).astype(np.int32)
+            slots[:4] = [-1, m_tile - 1, -m_tile, 0]
         resp = rng.random(n) * (rng.random(n) < 0.8)
         vm = rng.random(n) < 0.7
         kw = dict(valid_mask=jnp.asarray(vm), colors_meas=jnp.asarray(col), sources_meas=jnp.asarray(src)) if full else {}

@@ -207,3 +207,38 @@ def test_batched_empty_map_and_errors(mods):
         HB.lidar_evidence_primitives_batched(pts, t, w, 0.0, 0.1, xis, amap, poses[:2], 1, surfel_config=cfg, m_tile_view=64)
     with pytest.raises(ValueError):
         HB.lidar_evidence_primitives_batched(pts[:10], t, w, 0.0, 0.1, xis, amap, poses, 1, surfel_config=cfg, m_tile_view=64)
+
+
+def test_workspace_is_sized_once_and_can_be_frozen(mods):
+    """no per-call allocation in the steady state.  The context starts with 32 MB; a batch that needs more grows
+    it once (the outgrown block is retired, not freed under a live stream); frozen, a call that would have to grow raises
+    instead of allocating, and after an explicit reserve the same call runs."""
+    P, ops, HB = mods
+    from gc_slam_b200 import _lib as L
+    ctx = L.Context(torch.cuda.current_device())
+    try:
+        assert ctx.workspace_bytes == 32 << 20
+        ctx.freeze_workspace(True)
+        with pytest.raises(RuntimeError, match="workspace frozen"):
+            ctx.check(_grow_inside_a_call(ctx, L))
+        ctx.reserve_workspace(96 << 20)          # explicit sizing is allowed while frozen (it is made outside the steady state)
+        assert ctx.workspace_bytes >= 96 << 20
+        assert _grow_inside_a_call(ctx, L) == 0
+    finally:
+        ctx.close()
+
+
+def _grow_inside_a_call(ctx, L):
+    """A deskew of 2^21 points x 8 units needs 8 x blocks x 16 B of partials -- tiny; the surfel batch needs ~64 MB."""
+    import ctypes as C
+    from gc_slam_b200 import hypothesis_batch as HB, primitives as PR
+    n, U = 65536, 16
+    z = lambda *s, dt=torch.float64: torch.zeros(*s, dtype=dt, device="cuda")
+    pts, t, w = z(U, n, 3), z(n), z(U, n)
+    b = PR.create_empty_measurement_batch()
+    stacked = PR.MeasurementBatch(**{f: (getattr(b, f).unsqueeze(0).repeat((U,) + (1,) * getattr(b, f).dim()) if isinstance(getattr(b, f), torch.Tensor)
+                                         else getattr(b, f)) for f in b.__dataclass_fields__})
+    cb, cc = stacked._c(), PR.SurfelExtractionConfig()._c()
+    nv = z(U, dt=torch.int32)
+    return ctx.lib.gcs_extract_lidar_surfels_batched(ctx.handle, L.stream_ptr(torch.device("cuda")), L.ptr(pts), L.ptr(t), L.ptr(w), n, U, 1,
+                                                     C.byref(cc), C.byref(cb), L.ptr(nv))

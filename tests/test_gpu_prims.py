@@ -92,6 +92,17 @@ def test_primitive_path_vs_golden(P, case):
     assert abs(c_as.support.ess_total - g["as_cert"][ESS]) < 1e-7 * g["as_cert"][ESS]
     assert abs(e_as.predicted - float(g["as_effect"])) < 1e-7 * abs(float(g["as_effect"])) + 1e-13
     assert c_as.compute.largest_tensor_shape == (batch.n_total, 8) and c_as.compute.segment_sum_k == 8
+    if case.startswith("prim_p1"):       # MeasurementMassPolicy.WEIGHT_PROPORTIONAL (primitive_association.py:416-421)
+        wg = golden("assoc_wprop_p1.npz")
+        wa, wc, we = P.associate_primitives_ot(batch, view, P.AssociationConfig(scan_seq=scan_seq,
+                                                                              a_policy=P.MeasurementMassPolicy.WEIGHT_PROPORTIONAL))
+        assert np.array_equal(_np(wa.candidate_pool_indices), wg["pool"]) and rel_err(_np(wa.cost_matrix), wg["cost"]) < 1e-8
+        assert rel_err(_np(wa.responsibilities), wg["resp"]) < 1e-8 and rel_err(_np(wa.row_masses), wg["row"]) < 1e-8
+        wot = np.array([wc.ot.marginal_defect_a, wc.ot.marginal_defect_b, wc.ot.transport_mass_total, wc.ot.sum_a, wc.ot.sum_m,
+                        wc.ot.sum_novel, wc.ot.p95_a, wc.ot.nonzero_a, wc.ot.b_recency_p95])
+        assert np.max(np.abs(wot - wg["ot"]) / (np.abs(wg["ot"]) + 1e-12)) < 1e-7
+        assert abs(we.predicted - float(wg["effect"])) < 1e-7 * abs(float(wg["effect"])) + 1e-13
+        assert abs(wc.support.support_frac - wg["cert"][SUP]) < 1e-12
     # ---- a13
     vpe, c_vp, _ = P.visual_pose_evidence(assoc, batch, view, g["pose"], z_lin_pose=g["pose"])
     assert rel_err(_np(vpe.L_pose), g["vp_L"]) < 1e-7 and rel_err(_np(vpe.h_pose), g["vp_h"]) < 1e-6
