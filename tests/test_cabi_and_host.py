@@ -32,15 +32,27 @@ def test_library_exports_every_declared_symbol():
     assert lib.gcs_bins_raw_sums_len(48) == 48 * 25 + 8
 
 
-def test_struct_layouts_match_header_sizes():
-    from gc_slam_b200 import _lib, primitives as P
-    assert ctypes.sizeof(_lib.BinStats) == 8 * 8 and ctypes.sizeof(_lib.MapBinStats) == 6 * 8
-    # gcs_bins_args: 5 ptr + 2 i64 + 2 i32 + 4 ptr + ptr + 2 i32 + 6 dbl + ptr + 3 i64 + dbl + 8 ptr + 8 ptr + 4 ptr
-    assert ctypes.sizeof(_lib.BinsArgs) == 8 * (5 + 2 + 1 + 4 + 1 + 1 + 6 + 1 + 3 + 1 + 8 + 8 + 4)
-    assert ctypes.sizeof(P.CMeasBatch) == 9 * 8 + 8 and ctypes.sizeof(P.CAtlas) == 16 * 8 + 8
-    assert ctypes.sizeof(P.CMapView) == 12 * 8 and ctypes.sizeof(P.CAssocResult) == 6 * 8
-    assert ctypes.sizeof(P.CSurfelCfg) == 5 * 4 + 4 + 9 * 8 and ctypes.sizeof(P.CAssocCfg) == 4 * 4 + 8 * 8 + 8
-    assert ctypes.sizeof(P.CMapUpdateCfg) == 4 * 4 + 6 * 8 + 2 * 8 + 8
+def test_struct_layouts_match_header_sizes(tmp_path):
+    """Every ctypes mirror has the size the C compiler gives the header's struct (gcc on include/gcs_b200.h)."""
+    import shutil
+    import subprocess
+    from gc_slam_b200 import _lib, fusion, hypothesis_batch as HB, primitives as P
+    pairs = [("gcs_bin_stats", _lib.BinStats), ("gcs_map_bin_stats", _lib.MapBinStats), ("gcs_bins_args", _lib.BinsArgs),
+             ("gcs_pc2_layout", _lib.Pc2Layout), ("gcs_meas_batch", P.CMeasBatch), ("gcs_atlas", P.CAtlas), ("gcs_map_view", P.CMapView),
+             ("gcs_assoc_result", P.CAssocResult), ("gcs_surfel_cfg", P.CSurfelCfg), ("gcs_assoc_cfg", P.CAssocCfg),
+             ("gcs_map_update_cfg", P.CMapUpdateCfg), ("gcs_map_export", P.CMapExport), ("gcs_prim_batch_args", HB.CPrimBatchArgs)]
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "gcs_b200.h"\nint main(void){\n' +
+                   "".join(f'printf("%zu\\n", sizeof({c}));\n' for c, _ in pairs) + "return 0;}\n")
+    exe = tmp_path / "sizes"
+    subprocess.run([cc, "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    for (c, t), n in zip(pairs, sizes):
+        assert ctypes.sizeof(t) == n, f"{c}: header {n} bytes, ctypes mirror {ctypes.sizeof(t)}"
+    _ = fusion
 
 
 def test_no_gpu_means_loud_failure():
