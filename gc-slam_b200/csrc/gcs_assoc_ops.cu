@@ -9,7 +9,7 @@ namespace gcs {
 
 namespace {
 
-constexpr int kSkgThreads = 1024;
+constexpr int kSkgThreads = 512;   // 128 registers per thread: the per-thread column partials (<= 32) stay in registers
 constexpr int kSkgMaxCols = 32;
 
 struct CostArgs {

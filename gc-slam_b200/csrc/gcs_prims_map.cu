@@ -144,9 +144,8 @@ struct InflateArg {
   long long scan_seq;
   double lam, min_scale;
 };
-__global__ void __launch_bounds__(kBig) map_view_kernel(gcs_atlas A, TileList T, int m_view, double eps_lift, double eps_mass,
-                                                        gcs_map_view V, int32_t* __restrict__ n_valid_out, int use_cache,
-                                                        InflateArg I) {
+// Selection (1024 threads, one CTA per stencil tile): the first m_view slots of the stable sort by weight -> V.candidate_slots.
+__global__ void __launch_bounds__(kBig) map_view_kernel(gcs_atlas A, TileList T, int m_view, gcs_map_view V, int use_cache) {
   __shared__ SelectSmem sm;
   extern __shared__ uint32_t key_cache[];
   const int a = blockIdx.x;
@@ -165,15 +164,26 @@ __global__ void __launch_bounds__(kBig) map_view_kernel(gcs_atlas A, TileList T,
   auto invalid = [&](int s) -> bool { return !(ti >= 0 && A.valid[base + s]); };
   if (!cta_select_max_sentinel(M, m_view, key, invalid, f64_orderable(1e30), sm.out, sm.scan))
     cta_select_k(M, m_view, key, sm.out, sm.hist, sm.scan, use_cache ? key_cache : nullptr);
-  int local_valid = 0;
-  for (int j = threadIdx.x; j < m_view; j += kBig) {
-    const int slot = sm.out[j].idx;
-    const int64_t o = base + slot;
+  for (int j = threadIdx.x; j < m_view; j += kBig) V.candidate_slots[a * m_view + j] = sm.out[j].idx;
+}
+
+// Gather of the selected slots (128-thread blocks, 255 registers available: the 3x3 solve and inverse of an entry stay in
+// registers; inside the 1024-thread selection kernel they spilled 256 bytes): moments of every view entry, with the
+// recency inflation applied functionally when asked for.
+__global__ void __launch_bounds__(128) map_view_gather_kernel(gcs_atlas A, TileList T, int m_view, double eps_lift, double eps_mass,
+                                                              gcs_map_view V, int32_t* __restrict__ n_valid_out, InflateArg I) {
+  const int a = blockIdx.y;
+  const int ti = T.index[a];
+  const int64_t base = (int64_t)(ti < 0 ? 0 : ti) * A.m_tile;
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  bool v = false;
+  if (j < m_view) {
     const int r = a * m_view + j;
+    const int slot = V.candidate_slots[r];
+    const int64_t o = base + slot;
     Mat3 L;
     double th[3] = {0, 0, 0}, et[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, w = 0.0, col[3] = {0.5, 0.5, 0.5};
     long long pid = 0, last = 0;
-    bool v = false;
     for (int k = 0; k < 9; ++k) L.m[k] = 0.0;
     if (ti >= 0) {
       load_mat3(A.Lambdas + 9 * o, L);
@@ -195,7 +205,6 @@ __global__ void __launch_bounds__(kBig) map_view_kernel(gcs_atlas A, TileList T,
     const double es[3] = {et[0] + et[3] + et[6], et[1] + et[4] + et[7], et[2] + et[5] + et[8]};
     const double kap = sqrt(es[0] * es[0] + es[1] * es[1] + es[2] * es[2]);
     V.candidate_tile_ids[r] = T.id[a];
-    V.candidate_slots[r] = slot;
     V.valid[r] = v ? 1 : 0;
     for (int k = 0; k < 3; ++k) {
       V.positions[3 * r + k] = mu[k];
@@ -204,9 +213,9 @@ __global__ void __launch_bounds__(kBig) map_view_kernel(gcs_atlas A, TileList T,
     }
     for (int k = 0; k < 9; ++k) { V.covariances[9 * r + k] = S.m[k]; V.etas[9 * r + k] = et[k]; }
     V.kappas[r] = kap; V.weights[r] = w; V.primitive_ids[r] = pid; V.last_supported_scan_seq[r] = last;
-    local_valid += v ? 1 : 0;
   }
-  if (local_valid) atomicAdd(n_valid_out, local_valid);
+  const unsigned nv = __popc(__ballot_sync(0xffffffffu, v));
+  if ((threadIdx.x & 31) == 0 && nv) atomicAdd(n_valid_out, (int)nv);
 }
 
 // =================================================================================================
@@ -782,7 +791,7 @@ __global__ void __launch_bounds__(128) batch_replicate_kernel(gcs_meas_batch S, 
 // =================================================================================================
 // 512 threads: three rows per thread at the reference budget (1,536 rows) and 128 registers each -- the 1024-thread
 // version was capped at 64 registers and spilled the 28 accumulators
-constexpr int kPeThreads = 512;
+constexpr int kPeThreads = 384;   // four rows per thread at the reference budget, 170 registers: no spills
 template <int K>
 __global__ void __launch_bounds__(kPeThreads) pose_evidence_kernel(gcs_meas_batch B, int N, gcs_map_view V, gcs_assoc_result R,
                                                              double p0, double p1, double p2, double r0, double r1,
@@ -932,7 +941,8 @@ struct UpdWs {
 };
 
 // per-measurement world transform, tile id, novelty, insertion score (pipeline.py:1248-1256, :1331-1346)
-__global__ void __launch_bounds__(kBig) upd_prepare_kernel(gcs_meas_batch B, int N, gcs_assoc_result R, double p0, double p1,
+constexpr int kPrepThreads = 512;   // 128 registers per thread: the 3x3 products of a row stay in registers (1024 x 64 spilled 272 B)
+__global__ void __launch_bounds__(kPrepThreads) upd_prepare_kernel(gcs_meas_batch B, int N, gcs_assoc_result R, double p0, double p1,
                                                            double p2, double r0, double r1, double r2,
                                                            gcs_map_update_cfg cfg, UpdWs W) {
   __shared__ double sred[32];
@@ -941,9 +951,9 @@ __global__ void __launch_bounds__(kBig) upd_prepare_kernel(gcs_meas_batch B, int
   const Mat3 Rm = so3_exp(rv);
   const Mat3 Rt = mat3_T(Rm);
   double nv = 0.0;
-  for (int i = tid; i < N; i += kBig) nv += B.valid[i] ? 1.0 : 0.0;
+  for (int i = tid; i < N; i += kPrepThreads) nv += B.valid[i] ? 1.0 : 0.0;
   const double denom = fmax(block_sum_1024(nv, sred), cfg.eps_mass);
-  for (int i = tid; i < N; i += kBig) {
+  for (int i = tid; i < N; i += kPrepThreads) {
     Mat3 L;
     load_mat3(B.Lambdas + 9 * i, L);
     Mat3 Lw = mat3_mul(mat3_mul(Rm, L), Rt);
@@ -1405,8 +1415,11 @@ static int map_view_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_atlas* atlas
   gcs_timing_begin(ctx, st, GCS_TIME_MAP_VIEW);
   // no key cache here: the view's key is two cached loads, and the 200 KB carve-out it would take from L1 costs more
   // than the re-evaluations (measured 208 us with, 158 us without; the eviction select of the map update gains 35 %)
-  map_view_kernel<<<n_tiles, kBig, 0, st>>>(*atlas, T, m_tile_view, eps_lift, eps_mass, *view, out_n_valid, 0, I);
+  map_view_kernel<<<n_tiles, kBig, 0, st>>>(*atlas, T, m_tile_view, *view, 0);
   gcs_timing_end(ctx, st, GCS_TIME_MAP_VIEW);
+  GCS_LAUNCH_CHECK(ctx);
+  map_view_gather_kernel<<<dim3((m_tile_view + 127) / 128, n_tiles), 128, 0, st>>>(*atlas, T, m_tile_view, eps_lift, eps_mass, *view,
+                                                                                  out_n_valid, I);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
 }
@@ -1668,7 +1681,7 @@ int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int
   int* uq = (int*)(ws + o_uq);
   double* mpart = (double*)(ws + o_mpart);
 
-  upd_prepare_kernel<<<1, kBig, 0, st>>>(*batch, N, *assoc, pose6[0], pose6[1], pose6[2], pose6[3], pose6[4], pose6[5], *cfg, W);
+  upd_prepare_kernel<<<1, kPrepThreads, 0, st>>>(*batch, N, *assoc, pose6[0], pose6[1], pose6[2], pose6[3], pose6[4], pose6[5], *cfg, W);
   GCS_LAUNCH_CHECK(ctx);
   upd_pair_keys_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(*batch, N, K, *assoc, T, atlas->m_tile, none, (unsigned*)(ws + o_pk0),
                                                               (unsigned*)(ws + o_pv0));
