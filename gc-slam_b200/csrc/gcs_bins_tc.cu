@@ -522,9 +522,33 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
           P.rs_t[o + 1] = ttb; P.rs_w[o + 1] = w_rs_b; P.rs_ring[o + 1] = (uint8_t)(ring2 >> 8); P.rs_tag[o + 1] = (uint8_t)(tag2 >> 8);
         }
       }
-      const double alpha_a = (tta - t0) * inv_denom, alpha_b = (ttb - t0) * inv_denom;
-      const double w_dk_a = w_rs_a * window_weight_ctx(tta, mi.win[wid]);
-      const double w_dk_b = w_rs_b * window_weight_ctx(ttb, mi.win[wid]);
+      const double dta = tta - t0, dtb = ttb - t0;   // float64: epoch stamps (1.67e9 s) lose the sweep to float32
+      const double alpha_a = dta * inv_denom, alpha_b = dtb * inv_denom;
+      // Window weight sigmoid(a) sigmoid(S - a) = x / (c + x (1 + c + x)), x = e^-a = 2^(n + f): the exponent argument is
+      // reduced in float64 (n = rint, |f| <= 1/2), 2^f, the quotient and its Newton step in float32 -- relative error
+      // 3e-7 on an operator output whose stated tolerance is 1e-5 -- and the result returns to float64 for the product with
+      // the (float64) resampled weight.  The all-float64 form (exp2 polynomial + reciprocal: 30 FP64-pipe instructions per
+      // point on a pipe a quarter as wide) was a tenth of the producer's stall samples.
+      double w_dk_a, w_dk_b;
+      {
+        const WindowCtx& wc = mi.win[wid];
+        const double magic = 6755399441055744.0;   // 1.5 * 2^52: x + magic - magic = rint(x)
+        const double ea = fmin(fmax(dta * wc.inv_sig * -1.4426950408889634, -120.0), 60.0);
+        const double eb = fmin(fmax(dtb * wc.inv_sig * -1.4426950408889634, -120.0), 60.0);
+        const double na = (ea + magic) - magic, nb = (eb + magic) - magic;
+        const float2 fr = make_float2((float)(ea - na), (float)(eb - nb));
+        float2 x = make_float2(tc::ex2f(fr.x), tc::ex2f(fr.y));
+        // scale by 2^n through the exponent field (n in [-120, 60]: x stays a normal float32, x^2 stays finite)
+        x.x = __int_as_float(__float_as_int(x.x) + ((int)na << 23));
+        x.y = __int_as_float(__float_as_int(x.y) + ((int)nb << 23));
+        const float2 cf = bc2((float)wc.c), opc = bc2((float)wc.one_plus_c);
+        const float2 den = tc::fma2(x, tc::add2(opc, x), cf);
+        float2 r = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+        r = tc::fma2(r, tc::fma2(tc::mul2(den, bc2(-1.0f)), r, bc2(1.0f)), r);
+        const float2 ww = tc::mul2(x, r);
+        w_dk_a = w_rs_a * fma((double)ww.x, 1.0 - kWeightFloor, kWeightFloor);
+        w_dk_b = w_rs_b * fma((double)ww.y, 1.0 - kWeightFloor, kWeightFloor);
+      }
       const float2 a = make_float2((float)alpha_a, (float)alpha_b);
       const float2 a2 = tc::mul2(a, a);
       const float2 th2 = tc::mul2(a2, tf.th1sq);
