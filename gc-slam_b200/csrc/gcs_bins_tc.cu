@@ -99,6 +99,9 @@ struct TcMisc {
   TwistCtx tw[kMaxProd];        // per producer warp: hoisted invariants of the current unit (reloaded every tile)
   TwistCtxF twf[kMaxProd];
   WindowCtx win[kMaxProd];
+  // per producer warp: base pointers of the current segment.  Kept here instead of in ten registers across the tile loop
+  // (read back with one LDS.64 each where a tile needs them): the registers go to the soft-assign stage.
+  struct SegPtrs { const double* pts; const double* tp; const double* wp; double* dkp; double* dkw; const uint8_t* rp; const uint8_t* gp; } seg[kMaxProd];
 };
 
 struct TcGeom {
@@ -461,12 +464,20 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
     // ring / tag only pass through to the resampled rows: not read at all when those are not materialised
     const uint8_t* rp = (P.ring && P.rs_pts) ? P.ring + (int64_t)s * P.n_raw : nullptr;
     const uint8_t* gp = (P.tag && P.rs_pts) ? P.tag + (int64_t)s * P.n_raw : nullptr;
-    double* const dkp = P.dk_pts ? P.dk_pts + (int64_t)u * P.cap * 3 : nullptr;
-    double* const dkw = P.dk_w ? P.dk_w + (int64_t)u * P.cap : nullptr;
+    double* const dkp0 = P.dk_pts ? P.dk_pts + (int64_t)u * P.cap * 3 : nullptr;
+    double* const dkw0 = P.dk_w ? P.dk_w + (int64_t)u * P.cap : nullptr;
     // 16-byte paths: consecutive raw rows (stride 1) and 16-byte aligned scan / unit bases (pair index is even)
     const bool vec_in = P.stride == 1 && (((uintptr_t)pts | (uintptr_t)tp | (uintptr_t)wp) & 15) == 0 &&
                         (!rp || ((uintptr_t)rp & 1) == 0) && (!gp || ((uintptr_t)gp & 1) == 0);
-    const bool vec_out = (((uintptr_t)dkp | (uintptr_t)dkw) & 15) == 0;
+    const bool vec_out = (((uintptr_t)dkp0 | (uintptr_t)dkw0) & 15) == 0;
+    __syncwarp();
+    if (lane == 0) {
+      mi.seg[wid].pts = pts; mi.seg[wid].tp = tp; mi.seg[wid].wp = wp; mi.seg[wid].dkp = dkp0; mi.seg[wid].dkw = dkw0;
+      mi.seg[wid].rp = rp; mi.seg[wid].gp = gp;
+    }
+    __syncwarp();
+    const bool has_rt = rp != nullptr || gp != nullptr;
+    const volatile TcMisc::SegPtrs& sp = mi.seg[wid];
     double ent_dot = 0.0, ent_log = 0.0, sum_wdk = 0.0, sum_wrs = 0.0;
     float mx_resp = 0.f;
     int n_rows = 0;
@@ -484,24 +495,51 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
       nring = 0; ntag = 0;
       if (tile >= lt1) return;
       if (vec_in && ia + 1 < P.n_sel) {
-        const double2 a0 = ldg_d2(pts + 3 * ia), a1 = ldg_d2(pts + 3 * ia + 2), a2 = ldg_d2(pts + 3 * ia + 4);
-        const double2 tt = ldg_d2(tp + ia), ww = ldg_d2(wp + ia);
+        const double* pts_ = sp.pts;
+        const double* tp_ = sp.tp;
+        const double* wp_ = sp.wp;
+        const double2 a0 = ldg_d2(pts_ + 3 * ia), a1 = ldg_d2(pts_ + 3 * ia + 2), a2 = ldg_d2(pts_ + 3 * ia + 4);
+        const double2 tt = ldg_d2(tp_ + ia), ww = ldg_d2(wp_ + ia);
         nx[0] = a0.x; nx[1] = a0.y; nx[2] = a1.x; nx[3] = tt.x; nx[4] = ww.x;
         nx[5] = a1.y; nx[6] = a2.x; nx[7] = a2.y; nx[8] = tt.y; nx[9] = ww.y;
-        if (rp) nring = __ldg(reinterpret_cast<const unsigned short*>(rp + ia));
-        if (gp) ntag = __ldg(reinterpret_cast<const unsigned short*>(gp + ia));
+        if (has_rt) {
+          const uint8_t* rp_ = sp.rp;
+          const uint8_t* gp_ = sp.gp;
+          if (rp_) nring = __ldg(reinterpret_cast<const unsigned short*>(rp_ + ia));
+          if (gp_) ntag = __ldg(reinterpret_cast<const unsigned short*>(gp_ + ia));
+        }
       } else {
+        const double* pts_ = sp.pts;
+        const double* tp_ = sp.tp;
+        const double* wp_ = sp.wp;
+        const uint8_t* rp_ = sp.rp;
+        const uint8_t* gp_ = sp.gp;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           if (ia + q < P.n_sel) {
             const int64_t j = (ia + q) * P.stride;
-            nx[5 * q] = pts[3 * j]; nx[5 * q + 1] = pts[3 * j + 1]; nx[5 * q + 2] = pts[3 * j + 2];
-            nx[5 * q + 3] = tp[j]; nx[5 * q + 4] = wp[j];
-            if (rp) nring |= (unsigned short)((unsigned)rp[j] << (8 * q));
-            if (gp) ntag |= (unsigned short)((unsigned)gp[j] << (8 * q));
+            nx[5 * q] = pts_[3 * j]; nx[5 * q + 1] = pts_[3 * j + 1]; nx[5 * q + 2] = pts_[3 * j + 2];
+            nx[5 * q + 3] = tp_[j]; nx[5 * q + 4] = wp_[j];
+            if (rp_) nring |= (unsigned short)((unsigned)rp_[j] << (8 * q));
+            if (gp_) ntag |= (unsigned short)((unsigned)gp_[j] << (8 * q));
           }
         }
       }
+    };
+    // The raw rows of the warp's next tile are pulled into L2 at the top of a tile (no registers held) and loaded into
+    // registers only behind the operand stores of this tile, where the register-hungry soft-assign stage is over: with
+    // the loads at the top, 20 registers stayed live across the whole tile and loop invariants were spilled.
+    auto prefetch_l2 = [&](int64_t tile) {
+      if (tile >= lt1 || !vec_in) return;
+      const int64_t ia = tile * kTile + 2 * lane;
+      if (ia + 1 >= P.n_sel) return;
+      const double* pts_ = sp.pts;
+      const double* tp_ = sp.tp;
+      const double* wp_ = sp.wp;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pts_ + 3 * ia));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pts_ + 3 * ia + 4));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(tp_ + ia));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(wp_ + ia));
     };
     fetch(lt0 + wid);
     for (int64_t lt = lt0 + wid; lt < lt1; lt += kProd) {
@@ -512,7 +550,7 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
       const double tta = nx[3], ttb = nx[8];
       const double w_rs_a = nx[4] * mass_scale, w_rs_b = nx[9] * mass_scale;
       const unsigned short ring2 = nring, tag2 = ntag;
-      fetch(lt + kProd);
+      prefetch_l2(lt + kProd);
       if (h == 0 && P.rs_pts && row_a) {
         const int64_t o = (int64_t)s * P.cap + ia;
         P.rs_pts[3 * o] = pa[0]; P.rs_pts[3 * o + 1] = pa[1]; P.rs_pts[3 * o + 2] = pa[2];
@@ -593,6 +631,8 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
 #pragma unroll
         for (int k = 0; k < 3; ++k) q[k] = make_float2((float)p0a[k], (float)p0b[k]);
       }
+      double* const dkp = sp.dkp;
+      double* const dkw = sp.dkw;
       if (row_b && vec_out) {
         if (dkp) {
           stg_d2(dkp + 3 * ia, p0a[0], p0a[1]); stg_d2(dkp + 3 * ia + 2, p0a[2], p0b[0]); stg_d2(dkp + 3 * ia + 4, p0b[1], p0b[2]);
@@ -627,23 +667,18 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
       float2 sum_a = make_float2(0.f, 0.f), dot_a = sum_a, sum_b = sum_a, dot_b = sum_a;
       float mx_a = 0.f, mx_b = 0.f;
       constexpr int kGroups = C::kBinsPad / 8;   // 8 bins = 4 bin pairs = one 16-byte chunk of hi and one of lo per point
-      float4 tab[2][4][2];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { tab[0][k][0] = mi.bins2[2 * k]; tab[0][k][1] = mi.bins2[2 * k + 1]; }
+      // The bin table of a group (4 bin pairs, 32 registers) is loaded at the head of the group.  A second buffer that
+      // prefetched the next group cost 32 more registers: loop invariants were spilled, and their reloads -- local
+      // memory behind an L1 that streams the point data -- were a tenth of the kernel's stall samples.
 #pragma unroll
       for (int g = 0; g < kGroups; ++g) {
-        const int cur = g & 1;
-        if (g + 1 < kGroups) {
+        float4 tab[4][2];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            tab[cur ^ 1][k][0] = mi.bins2[2 * (4 * (g + 1) + k)];
-            tab[cur ^ 1][k][1] = mi.bins2[2 * (4 * (g + 1) + k) + 1];
-          }
-        }
+        for (int k = 0; k < 4; ++k) { tab[k][0] = mi.bins2[2 * (4 * g + k)]; tab[k][1] = mi.bins2[2 * (4 * g + k) + 1]; }
         uint32_t ha[4], la[4], hb[4], lb[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float4 ta = tab[cur][k][0], tb = tab[cur][k][1];
+          const float4 ta = tab[k][0], tb = tab[k][1];
           const float2 mx = make_float2(ta.x, ta.y), my = make_float2(ta.z, ta.w), mz = make_float2(tb.x, tb.y),
                        cc = make_float2(tb.z, tb.w);
           const float2 l_a = tc::fma2(ga0, mx, tc::fma2(ga1, my, tc::fma2(ga2, mz, cc)));
@@ -708,6 +743,7 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
           *reinterpret_cast<uint4*>(sB_b + c * 128) = make_uint4(ub[4 * c], ub[4 * c + 1], ub[4 * c + 2], ub[4 * c + 3]);
         }
       }
+      fetch(lt + kProd);
       tc::fence_smem_to_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&mi.bar_tile[wid][0]);   // the issuer warp takes it from here
