@@ -22,7 +22,7 @@ pass of that path over the batch.  The batch (S x 2.75 MB in, S x 2.1 MB out) is
 --impl reference times that CPU path on all host cores (one process per core) with the same metric/config.
 For N > 1 (torchrun) scans are sharded across ranks with no data-path collective ("scaling": "weak").
 
-A step is `--passes` passes over the batch (default 100: 20 steps x 100 passes keep the timed region above one second).
+A step is `--passes` passes over the batch (default 125: 20 steps x 125 passes keep the timed region above one second).
 Further top-level blocks of the line:
   dtype_matched  the same batch through the all-float64 kernels (the reference's dtype) with its own roofline fraction
   config2        BASELINE config 2: 30,000-point scans resampled to 8,192 points, 4 hypotheses per scan
@@ -321,7 +321,7 @@ def config3_block(n_points, peak, peak_src, n_map=1_000_000, with_cpu=True):
         # (a) the reference's loop order: hypothesis 0 updates the map, the others see the updated map; one host
         #     synchronisation per scan (the certificates of all hypotheses), scans back to back
         reps = 400 if H == 1 else (200 if H == 4 else 60)
-        for _ in range(3):
+        for _ in range(12):        # past the one-time allocations (arena blocks, the ring of pinned read-back buffers)
             run(H, xis, poses, True)
         torch.cuda.synchronize()
         lat = []
@@ -334,7 +334,7 @@ def config3_block(n_points, peak, peak_src, n_map=1_000_000, with_cpu=True):
         ms_upd = 1e3 * (time.perf_counter() - a0) / reps
         # (b) evidence only against a frozen map (offline replay, config 5a style): scans enqueued back to back, the wait
         #     for scan k-1 after scan k has been enqueued
-        for _ in range(3):
+        for _ in range(12):
             run(H, xis, poses, False)
         torch.cuda.synchronize()
         ctx.timing_enable(True, only="topk")
@@ -1005,7 +1005,7 @@ def main():
                     help="tc: tcgen05 moment contraction (fp16 hi/lo operands, float64 flushes), float32 soft-assign, float64 "
                          "geometry -- inside the 1e-5 parity tolerance (tests/test_gpu_bins.py); f64: everything float64")
     ap.add_argument("--no-cpu", action="store_true", help="skip the in-run CPU baseline")
-    ap.add_argument("--passes", type=int, default=100, help="passes over the batch per step (timed region = steps x passes)")
+    ap.add_argument("--passes", type=int, default=125, help="passes over the batch per step (timed region = steps x passes)")
     ap.add_argument("--no-prim", action="store_true", help="skip the config 2 / config 3 blocks")
     ap.add_argument("--no-multi", action="store_true", help="under torchrun: skip the config 4 / 5b block")
     args = ap.parse_args()

@@ -225,13 +225,18 @@ _DT = {F64: 8, torch.int32: 4, torch.int64: 8, torch.uint8: 1}
 
 
 class _Arena:
-    """One device allocation per call, carved into the stacked result arrays; tensor views are made on access only."""
+    """One device allocation per call, carved into the stacked result arrays; tensor views are made on access only.
+    The layout (name -> offset, shape, dtype) depends on the shapes alone and is computed once per shape key."""
+    _layouts: Dict[tuple, tuple] = {}
 
-    def __init__(self, dev):
-        self.dev, self.spec, self.size, self.buf = dev, {}, 0, None
+    def __init__(self, dev, spec=None, size=0):
+        self.dev, self.spec, self.size, self.buf = dev, (spec if spec is not None else {}), size, None
 
     def add(self, name, shape, dtype=F64):
-        nbytes = int(np.prod(shape)) * _DT[dtype]
+        n = 1
+        for x in shape:
+            n *= int(x)
+        nbytes = n * _DT[dtype]
         self.spec[name] = (self.size, tuple(int(x) for x in shape), dtype, nbytes)
         self.size += (nbytes + 255) & ~255
 
@@ -274,19 +279,25 @@ def _run_group(io, units, tile_ids, pts, t, w, n, xi_d, poses_d, t0, t1, atlas_m
     else:
         sel = torch.tensor(units, device=io.dev)
         xi_g, po_g = xi_d.index_select(0, sel), poses_d.index_select(0, sel)
-    A = _Arena(io.dev)
-    # packed certificate scalars first (one contiguous device -> host copy): _ROW float64 words per unit, then the view's
-    A.add("dk_cert", (U, L.DK_NCERT)); A.add("n_valid", (U,), torch.int32); A.add("ot_cert", (U, OT["NCERT"])); A.add("rec", (U, VP["NREC"]))
-    A.add("view_n_valid", (2,), torch.int32); A.add("inflate_stats", (4,))
-    n_scalar_bytes = A.size
-    A.add("dk_pts", (U, n, 3)); A.add("dk_w", (U, n))
-    for f, shp, dt in _BATCH_FIELDS:
-        A.add("b_" + f, (U, N) + shp, dt)
-    for f, shp, dt in _VIEW_FIELDS:
-        A.add("v_" + f, (P,) + shp, dt)
-    for f, has_k, dt in _ASSOC_FIELDS:
-        A.add("a_" + f, (U, N, K) if has_k else (U, N), dt)
-    A.add("L22", (U, 22, 22)); A.add("h22", (U, 22))
+    key = (U, n, N, P, K)
+    lay = _Arena._layouts.get(key)
+    if lay is None:
+        A = _Arena(io.dev)
+        # packed certificate scalars first (one contiguous device -> host copy): _ROW float64 words per unit, then the view's
+        A.add("dk_cert", (U, L.DK_NCERT)); A.add("n_valid", (U,), torch.int32); A.add("ot_cert", (U, OT["NCERT"])); A.add("rec", (U, VP["NREC"]))
+        A.add("view_n_valid", (2,), torch.int32); A.add("inflate_stats", (4,))
+        n_scalar_bytes = A.size
+        A.add("dk_pts", (U, n, 3)); A.add("dk_w", (U, n))
+        for f, shp, dt in _BATCH_FIELDS:
+            A.add("b_" + f, (U, N) + shp, dt)
+        for f, shp, dt in _VIEW_FIELDS:
+            A.add("v_" + f, (P,) + shp, dt)
+        for f, has_k, dt in _ASSOC_FIELDS:
+            A.add("a_" + f, (U, N, K) if has_k else (U, N), dt)
+        A.add("L22", (U, 22, 22)); A.add("h22", (U, 22))
+        lay = _Arena._layouts[key] = (A.spec, A.size, n_scalar_bytes)
+    spec, size, n_scalar_bytes = lay
+    A = _Arena(io.dev, spec, size)
     A.alloc()
     A.buf[:n_scalar_bytes].zero_()
     a = CPrimBatchArgs()
