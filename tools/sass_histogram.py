@@ -22,7 +22,7 @@ for line in txt.splitlines():
         m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
         if m:
             hist[cur][m.group(1)] += 1
-KEY = ("UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "REDUX", "MATCH", "UCGABAR", "MUFU", "FFMA2", "F2FP", "HADD2")
+KEY = ("UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "CREDUX", "REDUX", "MATCH", "UCGABAR", "MUFU", "FFMA2", "F2FP", "HADD2")
 for name, h in hist.items():
     print(f"== {name[:150]}\n   {sum(h.values())} instructions")
     fam = collections.Counter()
