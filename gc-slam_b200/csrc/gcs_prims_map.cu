@@ -2,11 +2,10 @@
 //   a11  recency inflation, per-tile top-k view extraction
 //   a12  OT association (pool cost -> stable top-K -> unbalanced Sinkhorn, 50 fixed iterations)
 //   a13  pose evidence from soft correspondences (WLS translation + scatter-SVD rotation)
-//   a14  map update: PoE fuse (stable radix sort by target + segmented sums, no float atomics), insert/evict, cull, forget
+//   a14  map update: PoE fuse (own stable radix sort by target + segmented sums, no float atomics), insert/evict, cull, forget
 // All selections reproduce jnp.argsort / lax.sort semantics (stable, first operand is the only key) through
 // cta_select_k (gcs_select.cuh).  All floating reductions are fixed-order.
 #include <cooperative_groups.h>
-#include <cub/device/device_radix_sort.cuh>
 
 #include "gcs_assoc.cuh"
 #include "gcs_select.cuh"
@@ -984,7 +983,7 @@ __global__ void __launch_bounds__(kPrepThreads) upd_prepare_kernel(gcs_meas_batc
 }
 
 // Target key of every (measurement, candidate) pair: (active tile, slot), or `none` for pairs without a target.  A
-// stable radix sort by that key (cub::DeviceRadixSort, pair index as the value) then lines up every target's
+// stable radix sort by that key (upd_sort_pairs_kernel, pair index as the value) then lines up every target's
 // contributions in pair order: deterministic, no floating atomics.
 __global__ void __launch_bounds__(256) upd_pair_keys_kernel(gcs_meas_batch B, int N, int K, gcs_assoc_result R, TileList T,
                                                             int m_tile, unsigned none, unsigned* __restrict__ keys,
@@ -1003,6 +1002,71 @@ __global__ void __launch_bounds__(256) upd_pair_keys_kernel(gcs_meas_batch B, in
   }
   keys[p] = key;
   vals[p] = (unsigned)p;
+}
+
+// Stable LSD radix sort of the (target key, pair index) list in ONE CTA (12,288 pairs at the reference budget): 8 bits per
+// pass, keys and values ping-pong between two global buffers (L2-resident).  Every warp owns a contiguous run of items.
+// Per pass: (1) per-warp digit counts in shared memory, (2) exclusive scan over (digit-major, warp-minor) -- the start of
+// every (digit, warp) bucket, (3) each warp walks its run in order, 32 items at a time: an item's place is the bucket start
+// plus the number of earlier items of its run with the same digit (running counter + `match_any` rank inside the step).
+// Order inside a bucket = input order: stable, deterministic.  Replaces a library sort of five launches.
+constexpr int kSortWarps = 32;
+__global__ void __launch_bounds__(32 * kSortWarps) upd_sort_pairs_kernel(unsigned* __restrict__ k0, unsigned* __restrict__ v0,
+                                                                         unsigned* __restrict__ k1, unsigned* __restrict__ v1, int n,
+                                                                         int n_passes) {
+  __shared__ int cnt[kSortWarps][256];     // counts, then running bucket positions
+  __shared__ int dig_tot[256];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int per_warp = ((n + kSortWarps - 1) / kSortWarps + 31) & ~31;
+  const int i0 = warp * per_warp, i1 = min(n, i0 + per_warp);
+  unsigned *ks = k0, *vs = v0, *kd = k1, *vd = v1;
+  for (int pass = 0; pass < n_passes; ++pass) {
+    const int shift = 8 * pass;
+    for (int e = tid; e < kSortWarps * 256; e += 32 * kSortWarps) (&cnt[0][0])[e] = 0;
+    __syncthreads();
+    for (int i = i0 + lane; i < i1; i += 32) atomicAdd(&cnt[warp][(ks[i] >> shift) & 255u], 1);
+    __syncthreads();
+    // exclusive scan: thread d < 256 walks the warps of digit d; then a scan over the 256 digit totals
+    if (tid < 256) {
+      int a = 0;
+      for (int w = 0; w < kSortWarps; ++w) { const int c = cnt[w][tid]; cnt[w][tid] = a; a += c; }
+      dig_tot[tid] = a;
+    }
+    __syncthreads();
+    if (warp == 0) {   // 256 totals: 8 per lane, shuffle scan across lanes
+      int loc[8], s_ = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { loc[j] = s_; s_ += dig_tot[8 * lane + j]; }
+      int inc = s_;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      const int base = inc - s_;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dig_tot[8 * lane + j] = base + loc[j];
+    }
+    __syncthreads();
+    for (int e = tid; e < kSortWarps * 256; e += 32 * kSortWarps) (&cnt[0][0])[e] += dig_tot[e & 255];
+    __syncthreads();
+    // stable scatter: the warp's run in order
+    for (int base = i0; base < i1; base += 32) {
+      const int i = base + lane;
+      const bool on = i < i1;
+      const unsigned key = on ? ks[i] : 0u, val = on ? vs[i] : 0u;
+      const int d = on ? (int)((key >> shift) & 255u) : 256 + lane;     // inactive lanes: unique pseudo-digits
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      const int before = __popc(peers & ((1u << lane) - 1u));
+      if (on) {
+        const int pos = cnt[warp][d] + before;
+        kd[pos] = key; vd[pos] = val;
+      }
+      __syncwarp();
+      if (on && lane == 31 - __clz(peers)) cnt[warp][d] += __popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+    unsigned* t = ks; ks = kd; kd = t;
+    t = vs; vs = vd; vd = t;
+  }
 }
 
 // One WARP per sorted position; the warp of a segment head folds its segment into the tile slot
@@ -1650,10 +1714,7 @@ int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int
   const unsigned none = (unsigned)n_tiles * (unsigned)atlas->m_tile;   // key of a pair without a target: sorts last
   int key_bits = 1;
   while ((none >> key_bits) != 0u) ++key_bits;
-  size_t cub_bytes = 0;
-  GCS_CHECK_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
-                                                      (const unsigned*)nullptr, (unsigned*)nullptr, n_pairs, 0, key_bits,
-                                                      (cudaStream_t)stream));
+  const int sort_passes = (key_bits + 7) / 8;
   const int block_rows = cfg->assoc_block_size > 0 ? cfg->assoc_block_size : 256;
   GCS_REQUIRE(ctx, block_rows * K <= 4096, "map_update: assoc_block_size*K_ASSOC exceeds 4096");
   const int n_blocks = (N + block_rows - 1) / block_rows;
@@ -1664,7 +1725,7 @@ int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_Lw = take((size_t)N * 72), o_thw = take((size_t)N * 24), o_etw = take((size_t)N * 72), o_mt = take((size_t)N * 8),
                o_nov = take((size_t)N * 8), o_sc = take((size_t)N * 8), o_pk0 = take((size_t)n_pairs * 4), o_pv0 = take((size_t)n_pairs * 4),
-               o_pk1 = take((size_t)n_pairs * 4), o_pv1 = take((size_t)n_pairs * 4), o_cub = take(cub_bytes),
+               o_pk1 = take((size_t)n_pairs * 4), o_pv1 = take((size_t)n_pairs * 4),
                o_ii = take((size_t)n_tiles * k_ins * 4), o_in = take((size_t)n_tiles * k_ins), o_iw = take((size_t)n_tiles * k_ins * 8),
                o_is = take((size_t)n_tiles * k_ins * 4), o_ni = take(16 * 4), o_part = take(128 * 8),
                o_fpart = take((size_t)fuse_blocks * 8), o_uq = take((size_t)n_blocks * 4),
@@ -1686,9 +1747,11 @@ int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int
   upd_pair_keys_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(*batch, N, K, *assoc, T, atlas->m_tile, none, (unsigned*)(ws + o_pk0),
                                                               (unsigned*)(ws + o_pv0));
   GCS_LAUNCH_CHECK(ctx);
-  GCS_CHECK_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ws + o_cub, cub_bytes, (const unsigned*)(ws + o_pk0), W.pkeys,
-                                                      (const unsigned*)(ws + o_pv0), W.pvals, n_pairs, 0, key_bits, st));
-  ctx->launches++;
+  // sorted list ends in buffer 0 after an even number of passes, in buffer 1 after an odd number
+  upd_sort_pairs_kernel<<<1, 32 * kSortWarps, 0, st>>>((unsigned*)(ws + o_pk0), (unsigned*)(ws + o_pv0), (unsigned*)(ws + o_pk1),
+                                                      (unsigned*)(ws + o_pv1), n_pairs, sort_passes);
+  GCS_LAUNCH_CHECK(ctx);
+  if ((sort_passes & 1) == 0) { W.pkeys = (unsigned*)(ws + o_pk0); W.pvals = (unsigned*)(ws + o_pv0); }
   gcs_timing_begin(ctx, st, GCS_TIME_FUSE);
   upd_fuse_kernel<<<fuse_blocks, 256, 0, st>>>(*atlas, T, *batch, K, *assoc, W, n_pairs, none, *cfg, fpart);
   gcs_timing_end(ctx, st, GCS_TIME_FUSE);
