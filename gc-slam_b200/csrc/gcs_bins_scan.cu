@@ -486,14 +486,17 @@ __global__ void __launch_bounds__(256) deskew_kernel(const double* __restrict__ 
   o_w += (int64_t)u * n;
   partial += (int64_t)u * gridDim.x * 2;
   const double inv_denom = 1.0 / fmax(t1 - t0, 1e-12);
-  const double inv_sig = window_inv_sigma(t0, t1);
+  // per-twist invariants hoisted (TwistCtx: ~60 instead of ~105 float64 operations per point, no sqrt / sincos for
+  // |theta| < 0.5) and the window weight with one exponential and no division: the forms the fused bin kernels use
+  const TwistCtx tw = make_twist_ctx(xi);
+  const WindowCtx win = make_window_ctx(t0, t1);
   double s_out = 0.0, s_in = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     double p[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
     double tt = t[i], ww = w[i];
     double p0[3];
-    deskew_point(p, (tt - t0) * inv_denom, xi, p0);
-    double wo = ww * window_weight(tt, t0, t1, inv_sig);
+    deskew_point_ctx(p, (tt - t0) * inv_denom, tw, p0);
+    double wo = ww * window_weight_ctx(tt, win);
     o_pts[3 * i] = p0[0]; o_pts[3 * i + 1] = p0[1]; o_pts[3 * i + 2] = p0[2];
     o_w[i] = wo;
     s_out += wo; s_in += ww;

@@ -423,20 +423,34 @@ __global__ void __launch_bounds__(32 * kTopkWarps, 1) assoc_topk_kernel(gcs_meas
       }
       const int jbase = s * m_view;
       const int n_off = drain ? 1 : m_view;
-      for (int base = 0; base < n_off; base += 32) {
+      for (int base2 = 0; base2 < n_off; base2 += 64) {
+      // the five-flop lower bounds of two 32-candidate steps are evaluated together (two independent load / float64
+      // chains in flight), then the steps are offered one after the other through a single copy of the queue / exact-cost code
+      double lb2[2] = {1e12, 1e12};
+      if (present) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int off = base2 + 32 * hh + lane;
+          if (off < m_view && tile_valid[off]) {
+            const double d0 = mp[0] - tile_pos[3 * off], d1 = mp[1] - tile_pos[3 * off + 1], d2 = mp[2] - tile_pos[3 * off + 2];
+            lb2[hh] = d0 * d0 + d1 * d1 + d2 * d2;
+          }
+        }
+      }
+      bool stop = false;
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        const int base = base2 + 32 * hh;
+        if (base >= n_off) break;
         const int off = base + lane, j = jbase + off;
         bool pass = false;
         if (present) {
           if (off < m_view) {
-            double lb = 1e12;
-            if (tile_valid[off]) {
-              const double d0 = mp[0] - tile_pos[3 * off], d1 = mp[1] - tile_pos[3 * off + 1], d2 = mp[2] - tile_pos[3 * off + 2];
-              lb = d0 * d0 + d1 * d1 + d2 * d2;
-            }
+            const double lb = hh ? lb2[1] : lb2[0];
             pass = !prune || !(lb > T || (lb == T && j > Tj));   // lb <= cost: beyond (T, Tj) it cannot be among the first K
           }
         } else if (!drain) {
-          if (prune && (1e12 > T || (1e12 == T && jbase + base > Tj))) break;
+          if (prune && (1e12 > T || (1e12 == T && jbase + base > Tj))) { stop = true; break; }
           pass = off < m_view && (!prune || !(1e12 > T || (1e12 == T && j > Tj)));
         }
         const unsigned pm = __ballot_sync(0xffffffffu, pass);
@@ -490,7 +504,9 @@ __global__ void __launch_bounds__(32 * kTopkWarps, 1) assoc_topk_kernel(gcs_meas
           if (lane < qn) queue[lane] = moved;
           __syncwarp();
         }
-      }
+      }   // the two steps of this pair
+      if (stop) break;
+      }   // pairs of 32-candidate steps
     }
     // K rounds of arg-min over the lanes' heads by (cost, j); the winner pops its list
 #pragma unroll 1

@@ -119,6 +119,7 @@ class BatchedPrimitiveEvidence:
     def __init__(self, n_hyp, groups, cfg):
         self.n_hyp, self.groups, self._cfg = n_hyp, groups, cfg
         self._pending = None
+        self._owned = []
         self._gens = {}          # "inflate" / "update": (generator at its yield, pinned host buffer, shape)
         self._first_extra = None
         self._where: Dict[int, tuple] = {}
@@ -163,7 +164,19 @@ class BatchedPrimitiveEvidence:
             self._first_extra = fin
             self._gens = {}
             self._cfg["atlas"]._pending_update = None
+        for buf in getattr(self, "_owned", []):
+            _PinnedRing.release(buf)
+        self._owned = []
         return self
+
+    def __del__(self):      # a deferred result dropped without wait(): its pinned buffers go back once the copies are done
+        try:
+            if self._owned:
+                self._event.synchronize()
+                for buf in self._owned:
+                    _PinnedRing.release(buf)
+        except Exception:
+            pass
 
     @property
     def map_update(self):
@@ -348,26 +361,38 @@ def _unpack_scalars(g: HypothesisGroup, host_bytes: np.ndarray):
 
 
 class _PinnedRing:
-    """Small pinned host buffers handed out round-robin per (thread, size): staging for asynchronous copies in both
-    directions (a pageable cudaMemcpy waits for everything enqueued before it, which would serialise back-to-back scans)."""
+    """Pinned host buffers per (thread, size): staging for asynchronous copies in both directions (a pageable cudaMemcpy
+    waits for everything enqueued before it, which would serialise back-to-back scans).  A buffer handed out is busy until
+    its owner releases it (a deferred result does so in wait()); a new one is only allocated when all are busy, so the
+    steady state of a double-buffered loop touches two or three buffers and never allocates."""
     _tls = threading.local()
 
     @classmethod
-    def get(cls, nbytes: int, depth: int = 8) -> torch.Tensor:
-        ring = getattr(cls._tls, "ring", None)
-        if ring is None:
-            ring = cls._tls.ring = {}
-        slot = ring.setdefault(int(nbytes), [[], 0])
-        if len(slot[0]) < depth:
-            slot[0].append(torch.empty(int(nbytes), dtype=torch.uint8).pin_memory())
-            return slot[0][-1]
-        slot[1] = (slot[1] + 1) % depth
-        return slot[0][slot[1]]
+    def get(cls, nbytes: int) -> torch.Tensor:
+        pool = getattr(cls._tls, "pool", None)
+        if pool is None:
+            pool = cls._tls.pool = {}
+        slots = pool.setdefault(int(nbytes), [])
+        for slot in slots:
+            if not slot[1]:
+                slot[1] = True
+                return slot[0]
+        slots.append([torch.empty(int(nbytes), dtype=torch.uint8).pin_memory(), True])
+        return slots[-1][0]
+
+    @classmethod
+    def release(cls, buf: torch.Tensor):
+        for slot in getattr(cls._tls, "pool", {}).get(int(buf.numel()), []):
+            if slot[0] is buf:
+                slot[1] = False
+                return
 
 
-def _h2d_async(io, a: np.ndarray, shape) -> torch.Tensor:
+def _h2d_async(io, a: np.ndarray, shape, owned: list) -> torch.Tensor:
+    """Host array -> device through a pinned staging buffer; the buffer joins `owned` and is released with the result."""
     a = np.ascontiguousarray(a, dtype=np.float64)
     stage = _PinnedRing.get(a.nbytes)
+    owned.append(stage)
     stage.view(F64).copy_(torch.from_numpy(a).reshape(-1))
     io.h2d += a.nbytes
     return stage.view(F64).to(io.dev, non_blocking=True).reshape(shape)
@@ -399,8 +424,9 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
     w = io.dev_in(weights, shape=(-1,))
     if t.shape[0] != n or w.shape[0] != n:
         raise ValueError("lidar_evidence_primitives_batched: points/timestamps/weights length mismatch")
+    owned: list = []      # pinned buffers of this call, released in wait()
     xi_d = (io.dev_in(xi_bodies, shape=(-1, 6)) if isinstance(xi_bodies, torch.Tensor)
-            else _h2d_async(io, np.asarray(xi_bodies, np.float64).reshape(-1, 6), (-1, 6)))
+            else _h2d_async(io, np.asarray(xi_bodies, np.float64).reshape(-1, 6), (-1, 6), owned))
     H = int(xi_d.shape[0])
     # the stencil of every hypothesis is decided on the host (as the reference does, pipeline.py:808-829): poses given as a
     # device tensor cost one blocking read here -- pass host poses to keep back-to-back scans asynchronous
@@ -408,7 +434,7 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
     if poses_h.shape[0] != H or H < 1:
         raise ValueError(f"lidar_evidence_primitives_batched: {H} twists but {poses_h.shape[0]} poses")
     poses_d = (io.dev_in(poses_pred, shape=(-1, 6)) if isinstance(poses_pred, torch.Tensor) and poses_pred.is_cuda
-               else _h2d_async(io, poses_h, (-1, 6)))
+               else _h2d_async(io, poses_h, (-1, 6), owned))
     scfg = surfel_config if surfel_config is not None else SurfelExtractionConfig()
     acfg = association_config if association_config is not None else AssociationConfig(scan_seq=int(scan_seq))
     PR._check_assoc_config(acfg)
@@ -446,14 +472,17 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
     # ONE synchronisation for the certificates of every hypothesis: the packed scalars go to pinned memory behind the
     # kernels; `defer` leaves the wait to the caller (out.wait()), so that the next scan can be enqueued meanwhile
     out._pending = []
+    out._owned = owned
     for g in groups:
         b1 = _PinnedRing.get(g._scal_d.numel())
+        owned.append(b1)
         b1.copy_(g._scal_d, non_blocking=True)
         out._pending.append(b1)
     if update_map:
         out_holder.append(out)
         for name, st_d in (("inflate", stats_i), ("update", stats_u)):
             buf = _PinnedRing.get(st_d.numel() * 8)
+            owned.append(buf)
             buf.view(F64).copy_(st_d.reshape(-1), non_blocking=True)
             out._gens[name] = (gens[name], buf, tuple(st_d.shape))
         atlas_map._pending_update = out
