@@ -501,25 +501,31 @@ def multi_gpu_block(world, rank, local_rank, prec):
     xi, pose = synth.scan_twist(77)[None], synth.hypothesis_poses(1, 3)
     t0a, t1a = np.array([synth.EPOCH_T0]), np.array([synth.EPOCH_T0 + 0.1])
     plan.upload(pts[sl], t[sl], w[sl], ring[sl], tag[sl], t0a, t1a, xi, pose, non_blocking=False)
-    x = sharding.PointShardExchange(plan)
-    for _ in range(5):
-        sharding.run_point_sharded(plan, exchange=x)
-    torch.cuda.synchronize()
-    dist.barrier()
-    reps, ex1, ex2 = 50, [], []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        sharding.run_point_sharded(plan, exchange=x, timed=True)
-    e1.record()
-    torch.cuda.synchronize()
-    for _ in range(10):                       # the exchanges alone, timed one by one
-        sharding.run_point_sharded(plan, exchange=x, timed=True)
+    def time_exchange(x):
+        for _ in range(5):
+            sharding.run_point_sharded(plan, exchange=x)
         torch.cuda.synchronize()
-        a, b = x.exchange_ms()
-        ex1.append(a); ex2.append(b)
-    ms_scan = tmax(e0.elapsed_time(e1) / reps)
-    ex1_us, ex2_us = tmax(1e3 * float(np.median(ex1))), tmax(1e3 * float(np.median(ex2)))
+        dist.barrier()
+        reps, ex1, ex2 = 50, [], []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            sharding.run_point_sharded(plan, exchange=x, timed=True)
+        e1.record()
+        torch.cuda.synchronize()
+        for _ in range(10):                       # the exchanges alone, timed one by one
+            sharding.run_point_sharded(plan, exchange=x, timed=True)
+            torch.cuda.synchronize()
+            a, b = x.exchange_ms()
+            ex1.append(a); ex2.append(b)
+        return tmax(e0.elapsed_time(e1) / reps), tmax(1e3 * float(np.median(ex1))), tmax(1e3 * float(np.median(ex2)))
+
+    # the library path first (one ncclAllGather of the packed buffer + rank-ordered reduction), then the peer-window kernel
+    x_lib = sharding.PointShardExchange(plan, use_peer=False)
+    ms_lib, ex1_lib, ex2_lib = time_exchange(x_lib)
+    x = sharding.PointShardExchange(plan)
+    ms_scan, ex1_us, ex2_us = time_exchange(x)
+    peer_timeout = x.peer_status()
     o = plan.outputs()
     L_sh, cert_sh = o.L22.clone(), o.cert.clone()
     parity = None
@@ -554,14 +560,17 @@ def multi_gpu_block(world, rank, local_rank, prec):
     c5b = {"workload": f"one {n_raw}-point cloud, rows sharded over {world} ranks, full bin path, precision {prec}",
            "ms_per_scan": ms_scan, "scans_per_s": 1e3 / ms_scan, "ms_single_gpu": ms_single,
            "speedup_vs_single_gpu": (ms_single / ms_scan) if ms_single else None,
-           "exchange": {"collective": "ncclAllGather (torch.distributed.all_gather_into_tensor) of ONE packed buffer + "
-                                      "gcs_bins_reduce_gathered (rank-ordered SUM / MAX), twice per scan",
+           "exchange": {"how": x.peer_note, "timed_out_exchange": peer_timeout,
                         "mass_exchange_us": ex1_us, "mass_bytes_per_rank": int(x.n_mass * 8),
-                        "sums_exchange_us": ex2_us, "sums_bytes_per_rank": int((x.n_sum + x.n_max) * 8)},
+                        "sums_exchange_us": ex2_us, "sums_bytes_per_rank": int((x.n_sum + x.n_max) * 8),
+                        "library_path": {"collective": "ncclAllGather (torch.distributed.all_gather_into_tensor) of ONE packed buffer + "
+                                                       "gcs_bins_reduce_gathered (rank-ordered SUM / MAX), twice per scan",
+                                         "ms_per_scan": ms_lib, "mass_exchange_us": ex1_lib, "sums_exchange_us": ex2_lib}},
            "algorithmic_bytes_per_scan": int(BYTES_IN_PER_PT * n_raw + BYTES_OUT_PER_PT * cap),
            "achieved_GBps_aggregate": (BYTES_IN_PER_PT * n_raw + BYTES_OUT_PER_PT * cap) / (ms_scan * 1e-3) / 1e9,
            "parity": parity, "bit_identical_across_ranks": identical}
-    del plan, x, pts, t, w
+    x.close(); x_lib.close()
+    del plan, x, x_lib, pts, t, w
 
     # ---- config 4 ---------------------------------------------------------------------------------------------
     H, P = 64, 65536

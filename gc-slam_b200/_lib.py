@@ -114,6 +114,11 @@ PROTOTYPES = {
     "gcs_bins_accumulate": (_int, [_vp, _vp, C.POINTER(BinsArgs), _vp, _vp, _vp]),
     "gcs_bins_finalize": (_int, [_vp, _vp, C.POINTER(BinsArgs), _vp, _vp, _vp]),
     "gcs_bins_reduce_gathered": (_int, [_vp, _vp, _vp, C.c_int32, _i64, _i64, _vp, _vp]),
+    "gcs_peer_xchg_create": (_int, [_vp, C.c_int32, C.c_int32, C.c_uint64, C.POINTER(_vp), _vp]),
+    "gcs_peer_xchg_connect": (_int, [_vp, _vp, _vp]),
+    "gcs_peer_xchg_reduce": (_int, [_vp, _vp, _vp, _vp, _i64, _i64]),
+    "gcs_peer_xchg_status": (_int, [_vp, _vp, C.POINTER(C.c_uint32)]),
+    "gcs_peer_xchg_destroy": (_int, [_vp, _vp]),
 }
 
 _lib = None

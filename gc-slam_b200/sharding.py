@@ -101,15 +101,19 @@ def allreduce_bin_sums(mass=None, raw_sums=None, raw_max=None, group=None):
 
 class PointShardExchange:
     """
-    Buffers of the two exchanges of a point-sharded bin path, allocated once per plan.  Each exchange is ONE collective
-    on ONE packed buffer: this rank's partial block [additive | maxima] is all-gathered, then gcs_bins_reduce_gathered
-    adds / maximises the `world` blocks in rank order on every rank (bit-identical results everywhere, whatever
-    reduction tree the collective library would have used).  `mass`, `raw_sums`, `raw_max` are views into the packed
-    buffers, so the bin kernels write their partials straight into the exchange buffer and read the reduced values from
-    the same place: no copy on either side of the collective.
+    Buffers of the two exchanges of a point-sharded bin path, allocated once per plan.  Each exchange moves ONE packed
+    buffer -- this rank's partial block [additive | maxima] -- and reduces the `world` blocks in rank order on every rank
+    (same data, same order: bit-identical results everywhere):
+      * peer windows (default on CUDA): gcs_peer_xchg_reduce, one kernel per rank that pushes the block into every rank's
+        IPC-mapped receive window over NVLink, signals, waits and reduces -- no library collective;
+      * all-gather path (host tensors, IPC not available, use_peer=False / GCS_EXCHANGE=nccl): one
+        all_gather_into_tensor (ncclAllGather) + gcs_bins_reduce_gathered.
+    `mass`, `raw_sums`, `raw_max` are views into the packed buffers, so the bin kernels write their partials straight into
+    the exchange buffer and read the reduced values from the same place: no copy on either side of the exchange.
     """
 
-    def __init__(self, plan, group=None):
+    def __init__(self, plan, group=None, use_peer=None):
+        self._use_peer = use_peer
         import torch
         import torch.distributed as dist
 
@@ -126,6 +130,63 @@ class PointShardExchange:
         self.gath1 = torch.empty(self.world * self.n_mass, dtype=torch.float64, device=dev)
         self.gath2 = torch.empty(self.world * (self.n_sum + self.n_max), dtype=torch.float64, device=dev)
         self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if dev.type == "cuda" else None
+        # Peer-memory exchange (one kernel per rank over NVLink peer windows, no library collective) when every rank can
+        # map every other rank's window; otherwise -- IPC not permitted, host tensors, GCS_EXCHANGE=nccl -- all ranks use
+        # the all-gather path.  The decision is collective: either every rank uses peer windows or none does.
+        self.peer, self.peer_note = None, "single rank"
+        if self.world > 1:
+            self._setup_peer(dev)
+
+    def _setup_peer(self, dev):
+        import ctypes as C
+        import os
+
+        import torch.distributed as dist
+
+        from . import _lib as L
+
+        want = dev.type == "cuda" and (os.environ.get("GCS_EXCHANGE", "peer") == "peer" if self._use_peer is None else bool(self._use_peer))
+        handle, buf, err = C.c_void_p(), C.create_string_buffer(64), ""
+        ok = False
+        if want:
+            io = self.plan.io
+            rank = dist.get_rank(self.group)
+            rc = io.ctx.lib.gcs_peer_xchg_create(io.ctx.handle, rank, self.world, 8 * max(self.n_mass, self.n_sum + self.n_max),
+                                                 C.byref(handle), buf)
+            ok = rc == 0
+            if not ok:
+                err = io.ctx.lib.gcs_last_error(io.ctx.handle).decode()
+        infos = [None] * self.world
+        dist.all_gather_object(infos, (ok, buf.raw if ok else b"", err), group=self.group)
+        if all(i[0] for i in infos):
+            rc = io.ctx.lib.gcs_peer_xchg_connect(io.ctx.handle, handle, b"".join(i[1] for i in infos))
+            ok2 = rc == 0
+            err = "" if ok2 else io.ctx.lib.gcs_last_error(io.ctx.handle).decode()
+            oks = [None] * self.world
+            dist.all_gather_object(oks, (ok2, err), group=self.group)
+            if all(o[0] for o in oks):
+                self.peer, self.peer_note = handle, "peer windows (CUDA IPC over NVLink), one kernel per exchange"
+                return
+            self.peer_note = "all-gather path: " + "; ".join(o[1] for o in oks if o[1])
+        else:
+            self.peer_note = "all-gather path" + ("" if not want else ": " + "; ".join(i[2] for i in infos if i[2]))
+        if ok:
+            self.plan.io.ctx.lib.gcs_peer_xchg_destroy(self.plan.io.ctx.handle, handle)
+
+    def close(self):
+        if self.peer is not None:
+            self.plan.io.ctx.lib.gcs_peer_xchg_destroy(self.plan.io.ctx.handle, self.peer)
+            self.peer = None
+
+    def peer_status(self) -> int:
+        """0, or the number of the exchange whose wait for a peer timed out (synchronises)."""
+        import ctypes as C
+        if self.peer is None:
+            return 0
+        e = C.c_uint32(0)
+        io = self.plan.io
+        io.ctx.check(io.ctx.lib.gcs_peer_xchg_status(io.ctx.handle, self.peer, C.byref(e)))
+        return int(e.value)
 
     def _exchange(self, pack, gath, n_sum, n_max, e0=None, e1=None):
         import torch
@@ -137,6 +198,12 @@ class PointShardExchange:
             return
         if e0 is not None:
             e0.record()
+        if self.peer is not None:
+            io = self.plan.io
+            io.ctx.check(io.ctx.lib.gcs_peer_xchg_reduce(io.ctx.handle, self.peer, io.stream(), L.ptr(pack), n_sum, n_max))
+            if e1 is not None:
+                e1.record()
+            return
         dist.all_gather_into_tensor(gath, pack, group=self.group)
         if pack.is_cuda:
             io = self.plan.io
@@ -178,6 +245,8 @@ def run_point_sharded(plan, group=None, exchange: "PointShardExchange" = None, t
     plan.run_accumulate(x.mass, x.raw_sums, x.raw_max)
     x.exchange_sums(timed)
     plan.run_finalize(x.mass, x.raw_sums, x.raw_max)
+    if exchange is None:
+        x.close()          # a one-off exchange: waits for the enqueued work and unmaps the peer windows
     return x.mass, x.raw_sums, x.raw_max
 
 

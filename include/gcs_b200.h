@@ -328,6 +328,23 @@ int gcs_bins_reduce_gathered(gcs_ctx* ctx, void* stream, const double* gathered 
                              int32_t world, int64_t n_sum, int64_t n_max, double* out_sum /*dev (n_sum)*/,
                              double* out_max /*dev (n_max)*/);
 
+/* The same exchange WITHOUT a library collective (SURVEY.md 8b `gcs_allreduce_bin_stats`; ranks = processes of one node,
+ * one GPU each): every rank owns a receive window in its HBM, exported through CUDA IPC and mapped by all peers
+ * (NVLink / NVSwitch peer access).  gcs_peer_xchg_reduce launches ONE kernel that pushes the rank's packed block
+ * [n_sum additive doubles | n_max maxima] into every rank's window, signals with a release store, acquire-polls for all
+ * peers (bounded: ~2 s, then the time-out is recorded and reported by gcs_peer_xchg_status), and reduces the window in rank
+ * order in place in `pack` -- bit-identical results on every rank.  Every rank must call it the same number of times.
+ *   create:  allocates the window for `bytes_per_rank` per block and writes the 64-byte IPC handle to ipc_handle_out (host)
+ *   connect: all_handles = the `world` handles in rank order (host, world * 64 bytes; exchange them with any host channel) */
+typedef struct gcs_peer_xchg gcs_peer_xchg;
+int gcs_peer_xchg_create(gcs_ctx* ctx, int32_t rank, int32_t world, uint64_t bytes_per_rank, gcs_peer_xchg** out,
+                         void* ipc_handle_out /*host, 64 bytes*/);
+int gcs_peer_xchg_connect(gcs_ctx* ctx, gcs_peer_xchg* x, const void* all_handles /*host, world * 64 bytes*/);
+int gcs_peer_xchg_reduce(gcs_ctx* ctx, gcs_peer_xchg* x, void* stream, double* pack /*dev, in place*/, int64_t n_sum,
+                         int64_t n_max);
+int gcs_peer_xchg_status(gcs_ctx* ctx, gcs_peer_xchg* x, uint32_t* out_epoch /*host: 0 = no time-out*/);
+int gcs_peer_xchg_destroy(gcs_ctx* ctx, gcs_peer_xchg* x);
+
 
 /* ================================================================================================
  * Primitive family (BASELINE config 3): LiDAR surfels -> map view -> OT association -> pose evidence -> map update

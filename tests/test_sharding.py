@@ -149,10 +149,24 @@ def _gpu_worker(rank, world, port, q):
     plan.set_map(synth.random_map_bin_stats(48, 7, bins))
     plan.upload(pts[sl], t[sl], w[sl], ring[sl], tag[sl], np.array([synth.EPOCH_T0]), np.array([synth.EPOCH_T0 + 0.1]),
                 synth.scan_twist(9)[None], synth.hypothesis_poses(1, 3), non_blocking=False)
-    run_point_sharded(plan)
+    from gc_slam_b200.sharding import PointShardExchange
+    x = PointShardExchange(plan)                      # peer windows (CUDA IPC over NVLink) when every rank can map them
+    run_point_sharded(plan, exchange=x)
     torch.cuda.synchronize()
     out = plan.outputs()
-    q.put((rank, out.L22.cpu().numpy(), out.stats["Sigma_p"].cpu().numpy(), out.cert.cpu().numpy()))
+    res = (rank, out.L22.cpu().numpy(), out.stats["Sigma_p"].cpu().numpy(), out.cert.cpu().numpy())
+    assert x.peer_status() == 0
+    how = x.peer_note
+    x.close()
+    # the library path (one all-gather of the packed buffer + the rank-ordered reduction kernel) adds the same blocks in the
+    # same order: bit-identical to the peer-window kernel
+    x2 = PointShardExchange(plan, use_peer=False)
+    run_point_sharded(plan, exchange=x2)
+    torch.cuda.synchronize()
+    out2 = plan.outputs()
+    assert np.array_equal(out2.L22.cpu().numpy(), res[1]) and np.array_equal(out2.cert.cpu().numpy(), res[3]), how
+    x2.close()
+    q.put(res + (how,))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -172,6 +186,7 @@ def test_point_sharded_nccl_matches_single_gpu():
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda x: x[0])
+    print("exchange:", res[0][4])
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
