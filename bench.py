@@ -686,8 +686,12 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         # one rank per GPU: keep this rank's pinned staging memory on the NUMA node of its GPU
-        from gc_slam_b200.sharding import bind_to_gpu_numa_node
+        from gc_slam_b200.sharding import bind_to_gpu_numa_node, numa_binding_note
         bind_to_gpu_numa_node(local_rank)
+        numa_notes = [None] * world
+        dist.all_gather_object(numa_notes, numa_binding_note())
+    else:
+        numa_notes = None
     from gc_slam_b200 import _lib as L
     from gc_slam_b200 import operators as ops
     from gc_slam_b200 import synth
@@ -967,6 +971,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "steps": e_steps,
                     "bare_copy_aggregate_GBps": bare_gbps, "achieved_copy_GBps": e2e_value / S * h2d_bytes / 1e9,
+                    "host_numa": numa_notes,
                     "note": "a step here is ONE pass over the batch (its payload copied from pinned host memory every time); the "
                             "bare copy of the same payload by all ranks at once is the ceiling of this arm",
                     "input": "PointCloud2 payloads (VLP-16 layout, 22 B/point) in pinned host memory; decode + base transform on the device",

@@ -20,13 +20,18 @@ import numpy as np
 
 def bind_to_gpu_numa_node(device_index: int):
     """
-    Pin the calling process to the CPUs of the NUMA node its GPU hangs off (sysfs `local_cpulist` of the PCI device), so
-    that pinned staging buffers are first-touched on that node.  With one rank per GPU and eight GPUs on a two-socket
-    host, ranks that stage through the other socket's memory halve the aggregate host -> device rate.  Returns the CPU
-    set it bound to, or None when the topology cannot be read (nothing is changed then).
+    Keep the calling process's host memory on the NUMA node its GPU hangs off, so that pinned staging buffers are
+    first-touched there.  With one rank per GPU and eight GPUs on a two-socket host, ranks that stage through the other
+    socket's memory lower the aggregate host -> device rate.  Two means, in this order: pin the process to the node's CPUs
+    (sysfs `local_cpulist` of the PCI device) when the process is allowed to run on any of them; otherwise (a container
+    whose CPU set lies on one socket) ask the kernel to prefer the node for this process's allocations
+    (set_mempolicy(MPOL_PREFERRED)).  Returns the CPU list it bound to (a list, as before), or a dict
+    {"node": n, "mempolicy": True} for the second means, or None when the topology cannot be read or neither is possible
+    (nothing is changed then).  `numa_binding_note()` describes the outcome for logs.
     """
     import os
 
+    global _NUMA_NOTE
     try:
         import torch
 
@@ -34,14 +39,52 @@ def bind_to_gpu_numa_node(device_index: int):
         bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
         with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
             cpus = parse_cpulist(f.read())
+        node = -1
+        try:
+            with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+                node = int(f.read().strip())
+        except Exception:
+            pass
         allowed = os.sched_getaffinity(0)
         cpus = sorted(set(cpus) & set(allowed))
-        if not cpus:
-            return None
-        os.sched_setaffinity(0, cpus)
-        return cpus
-    except Exception:
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            _NUMA_NOTE = f"gpu {device_index} ({bdf}) node {node}: bound to {len(cpus)} of its cpus"
+            return cpus
+        if node >= 0 and _prefer_numa_node(node):
+            _NUMA_NOTE = f"gpu {device_index} ({bdf}) node {node}: none of its cpus allowed here, memory policy PREFERRED node {node}"
+            return {"node": node, "mempolicy": True}
+        _NUMA_NOTE = f"gpu {device_index} ({bdf}) node {node}: none of its cpus allowed here and set_mempolicy refused; unbound"
         return None
+    except Exception as e:
+        _NUMA_NOTE = f"gpu {device_index}: topology unreadable ({type(e).__name__}); unbound"
+        return None
+
+
+_NUMA_NOTE = "not attempted"
+
+
+def numa_binding_note() -> str:
+    return _NUMA_NOTE
+
+
+def _prefer_numa_node(node: int) -> bool:
+    """set_mempolicy(MPOL_PREFERRED, {node}) for the calling thread (x86-64 / aarch64 syscall numbers); False when refused."""
+    import ctypes
+    import platform
+
+    nr = {"x86_64": 238, "aarch64": 237}.get(platform.machine())
+    if nr is None or node < 0 or node >= 1024:
+        return False
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        words = (ctypes.c_ulong * 16)()
+        words[node // 64] = 1 << (node % 64)
+        MPOL_PREFERRED = 1
+        rc = libc.syscall(ctypes.c_long(nr), ctypes.c_long(MPOL_PREFERRED), ctypes.byref(words), ctypes.c_ulong(16 * 64 + 1))
+        return rc == 0
+    except Exception:
+        return False
 
 
 def parse_cpulist(text: str):
