@@ -12,7 +12,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgcs_b200.so")
+# GCS_B200_LIB: a developer override (tools/build_variant.py builds experimental variants of the library next to the real one)
+LIB_PATH = os.environ.get("GCS_B200_LIB") or os.path.join(_HERE, "lib", "libgcs_b200.so")
 
 GCS_OK, GCS_EINVAL, GCS_ECUDA, GCS_ENOMEM, GCS_ECOMM = 0, -1, -2, -3, -4
 PREC_F64, PREC_MIXED, PREC_TC = 0, 1, 2

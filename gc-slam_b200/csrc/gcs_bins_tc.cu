@@ -56,15 +56,40 @@ constexpr double kLn2 = 0.6931471805599453;
 constexpr int kShiftE = 14, kShiftLo = 11, kShiftD = 5, kShiftP = -2, kShiftPP = -12;
 // MN-major fp16 tiles: bytes between two groups of 8 points (K groups) of the B tile (5 chunks of 8 features)
 constexpr int kKgB = 5 * 128;
-constexpr unsigned kIssuerSleepNs = 64;
+#ifndef GCS_TC_SLEEP
+#define GCS_TC_SLEEP 64
+#endif
+constexpr unsigned kIssuerSleepNs = GCS_TC_SLEEP;
+// fp16 (MN-major) producer: lane 0 of every producer warp issues the MMAs of its own tile (no hop through the issuer
+// warp's polling loop: the operand tile is released -- bar_stage -- a poll period earlier).  0: the issuer warp issues.
+#ifndef GCS_TC_SELF_ISSUE
+#define GCS_TC_SELF_ISSUE 0
+#endif
+// where the raw rows of the warp's next tile are loaded into registers: 0 behind the operand stores of stage 3, 1 ahead of
+// stage 3 (the loads then have the B-operand packing to complete in)
+// two MMA issuers per CTA (Q <= 3): see issuer_role
+#ifndef GCS_TC_DUAL_ISSUE
+#define GCS_TC_DUAL_ISSUE 0
+#endif
+// 1: wait for the operand tile's release only at the first operand store (behind the first bin group's arithmetic)
+#ifndef GCS_TC_LATE_WAIT
+#define GCS_TC_LATE_WAIT 0
+#endif
+#ifndef GCS_TC_FETCH_AT
+#define GCS_TC_FETCH_AT 1
+#endif
 constexpr int kLoColH = 20;   // first "lo" feature column of the fp16 B operand (columns 19 and 39 are zero)
 
 template <int Q, bool H>
 struct TcCfg {
   // producer warps: as many 17 KB / 21 KB operand tiles as fit in shared memory, in whole warpgroups
   static constexpr int kProd = Q <= 3 ? 12 : 8;
-  static constexpr int kRegProd = Q <= 3 ? 136 : 184;   // setmaxnreg targets (launch allocation 128 per thread)
-  static constexpr int kRegEpi = 104;
+#ifndef GCS_TC_REG_PROD
+#define GCS_TC_REG_PROD 136
+#define GCS_TC_REG_EPI 104
+#endif
+  static constexpr int kRegProd = Q <= 3 ? GCS_TC_REG_PROD : 184;   // setmaxnreg targets (launch allocation 128 per thread)
+  static constexpr int kRegEpi = Q <= 3 ? GCS_TC_REG_EPI : 104;
   static constexpr int kBinsPad = 16 * Q;   // rows of the e_hi block == first row of the e_lo block
   static constexpr int kRows = 32 * Q;      // rows of A that carry data
   // Warpgroup after the producers: epilogue warps, one per 32 TMEM lanes that carry data (Q of them).  For Q = 3 its
@@ -110,6 +135,18 @@ struct TcGeom {
   int n_cta, n_parts, flush;
   int dbg;   // 0, or 1 + slot of the timing hook
 };
+
+// Tiles of producer warp w's FIRST round in a segment; every later round has G.flush tiles.  The twelve producer warps run
+// in lock-step (same start, same work per tile): with equal rounds they all hand their accumulators to the epilogue at the
+// same moment, the drains serialise, and every warp waits for its turn at every round boundary (a tenth of the producers'
+// stall samples sat on the operand-tile barrier behind it).  Staggered first rounds spread the drains evenly over a round;
+// the first rounds grow with w, so the epilogue's fixed (round, warp) drain order is also the order of completion.
+#ifndef GCS_TC_STAGGER
+#define GCS_TC_STAGGER 0
+#endif
+__device__ __forceinline__ int first_round_tiles(const TcGeom& G, int w, int n_prod) {
+  return GCS_TC_STAGGER ? 1 + (w * G.flush) / n_prod : G.flush;
+}
 
 __device__ __forceinline__ int64_t cta_tile0(const TcGeom& G, int c) { return (int64_t)c * G.total_tiles / G.n_cta; }
 // CTA whose range contains tile g
@@ -427,6 +464,11 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
   constexpr int kTile = C::kTilePts;
   const int wid = tid >> 5, lane = tid & 31;
   uint32_t n_stage_uses = 0;
+#if GCS_TC_SELF_ISSUE
+  // round bookkeeping of this warp's accumulator (what the issuer warp keeps per lane otherwise)
+  uint32_t par_empty = 0;
+  bool have_round = false;
+#endif
   unsigned char* const sA = stages + wid * C::kStageBytes;
   unsigned char* const sB = sA + C::kABytes;
   // K rows lane (point a) and 32 + lane (point b): K group lane >> 3 (+ 4), row lane & 7 of the core matrices
@@ -542,7 +584,19 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
       asm volatile("prefetch.global.L2 [%0];" ::"l"(wp_ + ia));
     };
     fetch(lt0 + wid);
+#if GCS_TC_SELF_ISSUE
+    int in_round = 0, round_len = first_round_tiles(G, wid, kProd);
+#endif
     for (int64_t lt = lt0 + wid; lt < lt1; lt += kProd) {
+#if defined(GCS_TC_DRY) && !GCS_TC_SELF_ISSUE
+      // experiment: the hand-off protocol alone (no operand work) -- the rate the issuer warp sustains
+      if (n_stage_uses >= 1u) tc::mbar_wait(&mi.bar_stage[wid][0], (n_stage_uses - 1) & 1);
+      tc::fence_smem_to_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&mi.bar_tile[wid][0]);
+      ++n_stage_uses;
+      continue;
+#endif
       // ================= stage 1: resample gather, sweep fraction + window weight (float64), deskew increment (float32)
       const int64_t ia = lt * kTile + 2 * lane;
       const bool row_a = ia < P.cap, row_b = ia + 1 < P.cap;
@@ -663,7 +717,9 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
       const float2 ga0 = bc2(f[0].x), ga1 = bc2(f[1].x), ga2 = bc2(f[2].x);
       const float2 gb0 = bc2(f[0].y), gb1 = bc2(f[1].y), gb2 = bc2(f[2].y);
       // the tensor core may still be reading this warp's operand tile
+#if !GCS_TC_LATE_WAIT
       if (n_stage_uses >= 1u) tc::mbar_wait(&mi.bar_stage[wid][0], (n_stage_uses - 1) & 1);
+#endif
       float2 sum_a = make_float2(0.f, 0.f), dot_a = sum_a, sum_b = sum_a, dot_b = sum_a;
       float mx_a = 0.f, mx_b = 0.f;
       constexpr int kGroups = C::kBinsPad / 8;   // 8 bins = 4 bin pairs = one 16-byte chunk of hi and one of lo per point
@@ -672,6 +728,9 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
       // memory behind an L1 that streams the point data -- were a tenth of the kernel's stall samples.
 #pragma unroll
       for (int g = 0; g < kGroups; ++g) {
+#if GCS_TC_FETCH_AT >= 2
+        if (g == kGroups - (GCS_TC_FETCH_AT - 1)) fetch(lt + kProd);
+#endif
         float4 tab[4][2];
 #pragma unroll
         for (int k = 0; k < 4; ++k) { tab[k][0] = mi.bins2[2 * (4 * g + k)]; tab[k][1] = mi.bins2[2 * (4 * g + k) + 1]; }
@@ -695,6 +754,9 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
           la[k] = tc::pack_f16x2(r_a.x, r_a.y);
           lb[k] = tc::pack_f16x2(r_b.x, r_b.y);
         }
+#if GCS_TC_LATE_WAIT
+        if (g == 0 && n_stage_uses >= 1u) tc::mbar_wait(&mi.bar_stage[wid][0], (n_stage_uses - 1) & 1);
+#endif
         // M block g holds e_hi of bins 8g..8g+7, M block kBinsPad/8 + g their e_lo
         *reinterpret_cast<uint4*>(sA_a + g * 128) = make_uint4(ha[0], ha[1], ha[2], ha[3]);
         *reinterpret_cast<uint4*>(sA_a + (kGroups + g) * 128) = make_uint4(la[0], la[1], la[2], la[3]);
@@ -702,6 +764,9 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
         *reinterpret_cast<uint4*>(sA_b + (kGroups + g) * 128) = make_uint4(lb[0], lb[1], lb[2], lb[3]);
       }
 
+#if GCS_TC_FETCH_AT == 1
+      fetch(lt + kProd);
+#endif
       // ================= stage 3: B = [phi_hi, 0, phi_lo, 0], phi = (w / Z) (1, d, d d^T, p, p p^T)
       const float2 ssum = make_float2(sum_a.x + sum_a.y, sum_b.x + sum_b.y);
       float2 inv = make_float2(rcp_approx(ssum.x), rcp_approx(ssum.y));
@@ -743,10 +808,35 @@ __device__ __forceinline__ void producer_role_mn(const BinScanParams& P, const T
           *reinterpret_cast<uint4*>(sB_b + c * 128) = make_uint4(ub[4 * c], ub[4 * c + 1], ub[4 * c + 2], ub[4 * c + 3]);
         }
       }
+#if !GCS_TC_FETCH_AT
       fetch(lt + kProd);
+#endif
       tc::fence_smem_to_async();
       __syncwarp();
+#if GCS_TC_SELF_ISSUE
+      {
+        // first tile of a round overwrites the accumulator: the epilogue must have drained the previous round
+        const bool last = (in_round + 1 == round_len) || (lt + kProd >= lt1);
+        if (in_round == 0 && have_round) tc::mbar_wait(&mi.bar_empty[wid], par_empty);
+        if (lane == 0) {
+          tc::fence_after_sync();
+          const uint32_t idesc = tc::idesc_f16(128, kMmaN) | tc::kIdescMnMajorA | tc::kIdescMnMajorB;
+          const uint32_t sa = tc::smem_u32(sA);
+          const uint64_t da = tc::smem_desc_mn(sa, C::kKgA, 128);
+          const uint64_t db = tc::smem_desc_mn(sa + C::kABytes, kKgB, 128);
+          const uint32_t d_tmem = tmem + wid * kAccStride;
+#pragma unroll
+          for (int ks = 0; ks < C::kMmaPerTile; ++ks)
+            tc::mma_f16_ss(d_tmem, da + (uint64_t)(ks * ((2 * C::kKgA) >> 4)), db + (uint64_t)(ks * ((2 * kKgB) >> 4)), idesc,
+                           (ks || in_round) ? 1u : 0u);
+          tc::mma_commit(&mi.bar_stage[wid][0]);
+          if (last) tc::mma_commit(&mi.bar_full[wid]);
+        }
+        if (last) { in_round = 0; round_len = G.flush; if (have_round) par_empty ^= 1u; have_round = true; } else ++in_round;
+      }
+#else
       if (lane == 0) tc::mbar_arrive(&mi.bar_tile[wid][0]);   // the issuer warp takes it from here
+#endif
       ++n_stage_uses;
     }
     // per-warp sums of the scalar certificates (fixed shuffle tree)
@@ -766,6 +856,40 @@ __device__ __forceinline__ void producer_role(const BinScanParams& P, const TcGe
                                               uint32_t tmem, int cta, int tid) {
   if (H) producer_role_mn<Q>(P, G, mi, stages, tmem, cta, tid);
   else producer_role_tf32<Q>(P, G, mi, stages, tmem, cta, tid);
+}
+
+// Rounds (accumulator hand-overs to the epilogue) of producer warp w in a segment of n_seg tiles.
+__device__ __forceinline__ int rounds_of(const TcGeom& G, int n_seg, int w, int n_prod) {
+  const int tiles_w = n_seg > w ? (n_seg - w + n_prod - 1) / n_prod : 0;
+  const int first = first_round_tiles(G, w, n_prod);
+  return tiles_w <= first ? (tiles_w > 0 ? 1 : 0) : 1 + (tiles_w - first + G.flush - 1) / G.flush;
+}
+
+// One accumulator drain of an epilogue warp: TMEM lanes lane_base.., accumulator of producer warp w, into acc (float64).
+template <int Q, bool H>
+__device__ __forceinline__ void drain_accumulator(TcMisc& mi, uint32_t tmem, uint32_t lane_base, int w, int lane, double* acc) {
+  tc::fence_after_sync();
+  uint32_t a0[16], a1[16], a2[4], a3[4];
+  const uint32_t addr = tmem + lane_base + w * kAccStride;
+  tc::tmem_ld_x16(addr, a0);
+  tc::tmem_ld_x16(addr + 16, a1);
+  tc::tmem_ld_x4(addr + 32, a2);
+  tc::tmem_ld_x4(addr + 36, a3);
+  tc::tmem_ld_wait();
+  tc::fence_before_sync();
+  __syncwarp();
+  if (lane == 0) tc::mbar_arrive(&mi.bar_empty[w]);
+  // column f holds row x phi_hi[f], column kLoCol + f row x phi_lo[f] (fp16 operands: 2^-11 of the former): one
+  // float32 add, then the float64 accumulation
+  float v[40];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) { v[c] = __uint_as_float(a0[c]); v[16 + c] = __uint_as_float(a1[c]); }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { v[32 + c] = __uint_as_float(a2[c]); v[36 + c] = __uint_as_float(a3[c]); }
+  constexpr int kLo = TcCfg<Q, H>::kLoCol;
+#pragma unroll
+  for (int f = 0; f < kNF; ++f)
+    acc[f] += (double)(H ? fmaf(v[kLo + f], 1.0f / (float)(1 << kShiftLo), v[f]) : v[f] + v[kLo + f]);
 }
 
 template <int Q, bool H>
@@ -789,10 +913,7 @@ __device__ __forceinline__ void epilogue_role(const BinScanParams& P, const TcGe
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
     int rounds[kProd];
 #pragma unroll
-    for (int w = 0; w < kProd; ++w) {
-      const int tiles_w = n_seg > w ? (n_seg - w + kProd - 1) / kProd : 0;
-      rounds[w] = (tiles_w + G.flush - 1) / G.flush;
-    }
+    for (int w = 0; w < kProd; ++w) rounds[w] = rounds_of(G, n_seg, w, kProd);
     for (int r = 0;; ++r) {
       bool any = false;
 #pragma unroll
@@ -801,28 +922,7 @@ __device__ __forceinline__ void epilogue_role(const BinScanParams& P, const TcGe
           any = true;
           tc::mbar_wait(&mi.bar_full[w], n_drained[w] & 1);
           ++n_drained[w];
-          tc::fence_after_sync();
-          uint32_t a0[16], a1[16], a2[4], a3[4];
-          const uint32_t addr = tmem + lane_base + w * kAccStride;
-          tc::tmem_ld_x16(addr, a0);
-          tc::tmem_ld_x16(addr + 16, a1);
-          tc::tmem_ld_x4(addr + 32, a2);
-          tc::tmem_ld_x4(addr + 36, a3);
-          tc::tmem_ld_wait();
-          tc::fence_before_sync();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&mi.bar_empty[w]);
-          // column f holds row x phi_hi[f], column kLoCol + f row x phi_lo[f] (fp16 operands: 2^-11 of the former): one
-          // float32 add, then the float64 accumulation
-          float v[40];
-#pragma unroll
-          for (int c = 0; c < 16; ++c) { v[c] = __uint_as_float(a0[c]); v[16 + c] = __uint_as_float(a1[c]); }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) { v[32 + c] = __uint_as_float(a2[c]); v[36 + c] = __uint_as_float(a3[c]); }
-          constexpr int kLo = TcCfg<Q, H>::kLoCol;
-#pragma unroll
-          for (int f = 0; f < kNF; ++f)
-            acc[f] += (double)(H ? fmaf(v[kLo + f], 1.0f / (float)(1 << kShiftLo), v[f]) : v[f] + v[kLo + f]);
+          drain_accumulator<Q, H>(mi, tmem, lane_base, w, lane, acc);
         }
       }
       if (!any) break;
@@ -831,80 +931,124 @@ __device__ __forceinline__ void epilogue_role(const BinScanParams& P, const TcGe
   }
 }
 
-// MMA issuer: one thread feeds the tensor core for the whole CTA; producers never block on the tensor-core queue.  Lane w
-// of the issuer warp watches the barriers of producer warp w (one mbarrier.test_wait polls all of them at once) and
-// lane 0 issues whichever tiles are ready -- no fixed order across warps, so a late warp does not hold up the MMAs (and
-// hence the operand-tile release) of the others.  Each accumulator still sees only its own warp's tiles, in sequence,
-// and the epilogue drains in a fixed order: results do not depend on the issue order.
-template <int Q, bool H>
+// MMA issuer for producer warps [w_lo, w_hi): producers never block on the tensor-core queue.  Lane l (< w_hi - w_lo)
+// watches the barriers of producer warp w_lo + l -- one `mbarrier.test_wait` instruction polls them all -- and one elected
+// lane issues whichever tiles are ready, no fixed order across warps, so a late warp does not hold up the MMAs (and hence
+// the operand-tile release) of the others.  Each accumulator still sees only its own warp's tiles, in sequence, and the
+// epilogue drains in a fixed order: results do not depend on the issue order.
+//
+// The hand-off is a serial resource (about 0.2 us per tile: four tcgen05.mma, one or two tcgen05.commit, the poll), so the
+// producers are split between TWO issuers: the spare warp of the epilogue warpgroup and -- `kDrain` -- the first epilogue
+// warp, which drains its TMEM lanes from the same polling loop (the same (round, warp) order as the blocking epilogue warps).
+template <int Q, bool H, bool kDrain>
 __device__ __forceinline__ void issuer_role(const BinScanParams& P, const TcGeom& G, TcMisc& mi, unsigned char* stages,
-                                            uint32_t tmem, int cta, int tid) {
+                                            uint32_t tmem, int cta, int tid, int w_lo, int w_hi) {
   using C = TcCfg<Q, H>;
   constexpr int kProd = C::kProd;
   const int lane = tid & 31;
+  const int n_own = w_hi - w_lo;
+  const int my_w = w_lo + (lane < n_own ? lane : 0);
   int64_t g0 = cta_tile0(G, cta);
   const int64_t g_end = cta_tile0(G, cta + 1);
   const uint32_t idesc = H ? (tc::idesc_f16(128, kMmaN) | tc::kIdescMnMajorA | tc::kIdescMnMajorB) : tc::idesc_tf32(128, kMmaN);
   const uint32_t a0 = tc::smem_u32(stages);
+  const uint32_t tmem_u = __reduce_max_sync(0xffffffffu, tmem);   // the same value in every lane, now known to be uniform
+  const uint32_t lane_base = kDrain ? (uint32_t)(32 * ((tid >> 5) - kProd)) << 16 : 0u;
   TcSeg sg;
-  // lane w (< kProd) keeps the tile / round counters of producer warp w and polls its barriers; lane 0 issues
   uint32_t n_done = 0;      // tiles of this lane's warp issued so far: operand buffer n_done % kNBuf, phase n_done / kNBuf
   uint32_t par_empty = 0;   // phase of bar_empty to test next (the warp's previous round)
-  bool have_round = false;                // a round of this lane's warp has been handed to the epilogue
+  bool have_round = false;  // a round of this lane's warp has been handed to the epilogue
+  uint32_t par_full = 0;    // kDrain: bit w = phase of bar_full[w] to wait for next
   while (next_segment(G, P.n_hyp, g0, g_end, sg)) {
+    double acc[kNF];
+#pragma unroll
+    for (int c = 0; c < kNF; ++c) acc[c] = 0.0;
     {
       const int n_seg = (int)(sg.lt1 - sg.lt0);
-      const int my_tiles = (lane < kProd && n_seg > lane) ? (n_seg - lane + kProd - 1) / kProd : 0;
-      int t = 0, in_round = 0;
+      const int my_tiles = (lane < n_own && n_seg > my_w) ? (n_seg - my_w + kProd - 1) / kProd : 0;
+      int t = 0, in_round = 0, round_len = first_round_tiles(G, my_w, kProd);
+      // drain cursor (warp-uniform): next (round, warp) in the epilogue's fixed order
+      int dr = 0, dw = 0, max_rounds = 0;
+      bool drain_valid = false;
+      if (kDrain) {
+        for (int w = 0; w < kProd; ++w) max_rounds = max(max_rounds, rounds_of(G, n_seg, w, kProd));
+        drain_valid = max_rounds > 0;
+        while (drain_valid && dr >= rounds_of(G, n_seg, dw, kProd)) {
+          if (++dw == kProd) { dw = 0; if (++dr >= max_rounds) drain_valid = false; }
+        }
+      }
       for (;;) {
         const bool pending = t < my_tiles;
         bool ready = false;
         if (pending) {
-          ready = tc::mbar_test_wait(&mi.bar_tile[lane][0], n_done & 1u);
-          if (ready && in_round == 0 && have_round) ready = tc::mbar_test_wait(&mi.bar_empty[lane], par_empty);
+          ready = tc::mbar_test_wait(&mi.bar_tile[my_w][0], n_done & 1u);
+          if (ready && in_round == 0 && have_round) ready = tc::mbar_test_wait(&mi.bar_empty[my_w], par_empty);
         }
         const unsigned rdy = __ballot_sync(0xffffffffu, ready);
+        bool drained = false;
+        if (kDrain && drain_valid) {
+          const bool ok = tc::mbar_test_wait(&mi.bar_full[dw], (par_full >> dw) & 1u);
+          if (__ballot_sync(0xffffffffu, ok) & 1u) {   // lane 0's view, the same for every lane
+            drain_accumulator<Q, H>(mi, tmem, lane_base, dw, lane, acc);
+            par_full ^= 1u << dw;
+            drained = true;
+            do {
+              if (++dw == kProd) { dw = 0; if (++dr >= max_rounds) { drain_valid = false; break; } }
+            } while (dr >= rounds_of(G, n_seg, dw, kProd));
+          }
+        }
         if (rdy == 0u) {
-          if (__ballot_sync(0xffffffffu, pending) == 0u) break;
-          __nanosleep(kIssuerSleepNs);   // a producer needs microseconds per tile: do not spend its issue slots on polling
+          if (drained) continue;
+          if (__ballot_sync(0xffffffffu, pending) == 0u && !(kDrain && drain_valid)) break;
+          if (kIssuerSleepNs) __nanosleep(kIssuerSleepNs);   // a producer needs microseconds per tile: do not spend its issue slots on polling
           continue;
         }
-        const bool last = (in_round + 1 == G.flush) || (t + 1 >= my_tiles);
+        const bool last = (in_round + 1 == round_len) || (t + 1 >= my_tiles);
         const unsigned first_m = __ballot_sync(0xffffffffu, ready && in_round == 0);
         const unsigned last_m = __ballot_sync(0xffffffffu, ready && last);
         tc::fence_after_sync();
-        if (lane == 0) {
+        {
+          // every lane walks the (warp-uniform) ready mask; one elected lane issues.  All operands are warp-uniform.
           unsigned m = rdy;
           while (m) {
-            const int w = __ffs(m) - 1;
+            const int l = __ffs(m) - 1;
             m &= m - 1;
+            const int w = w_lo + l;
             const uint32_t sa = a0 + w * C::kStageBytes;
             const uint64_t da = H ? tc::smem_desc_mn(sa, C::kKgA, 128) : tc::smem_desc_sw128(sa);
             const uint64_t db = H ? tc::smem_desc_mn(sa + C::kABytes, kKgB, 128) : tc::smem_desc_sw128(sa + C::kABytes);
-            const uint32_t d_tmem = tmem + w * kAccStride;
-            const uint32_t acc0 = ((first_m >> w) & 1u) ^ 1u;
+            const uint32_t d_tmem = tmem_u + w * kAccStride;
+            const uint32_t acc0 = ((first_m >> l) & 1u) ^ 1u;
+            const bool fin = (last_m >> l) & 1u;
             // tf32: one MMA consumes 32 bytes of every operand row (8 points): descriptor start + 2 (x 16 B);
             // fp16: one MMA consumes two K groups (16 points): descriptor start + 2 K-group strides
+#ifdef GCS_TC_DRY_MMAS
+            constexpr int kIssue = GCS_TC_DRY_MMAS;
+#else
+            constexpr int kIssue = C::kMmaPerTile;
+#endif
+            if (tc::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < C::kMmaPerTile; ++ks) {
-              if (H) tc::mma_f16_ss(d_tmem, da + (uint64_t)(ks * ((2 * C::kKgA) >> 4)), db + (uint64_t)(ks * ((2 * kKgB) >> 4)), idesc,
-                                    ks ? 1u : acc0);
-              else tc::mma_tf32_ss(d_tmem, da + 2 * ks, db + 2 * ks, idesc, ks ? 1u : acc0);
+              for (int ks = 0; ks < kIssue; ++ks) {
+                if (H) tc::mma_f16_ss(d_tmem, da + (uint64_t)(ks * ((2 * C::kKgA) >> 4)), db + (uint64_t)(ks * ((2 * kKgB) >> 4)), idesc,
+                                      ks ? 1u : acc0);
+                else tc::mma_tf32_ss(d_tmem, da + 2 * ks, db + 2 * ks, idesc, ks ? 1u : acc0);
+              }
+              tc::mma_commit(&mi.bar_stage[w][0]);
+              if (fin) tc::mma_commit(&mi.bar_full[w]);
             }
-            tc::mma_commit(&mi.bar_stage[w][0]);
-            if ((last_m >> w) & 1u) tc::mma_commit(&mi.bar_full[w]);
           }
         }
         if (ready) {
           ++t;
           ++n_done;
-          if (last) { in_round = 0; if (have_round) par_empty ^= 1u; have_round = true; } else ++in_round;
+          if (last) { in_round = 0; round_len = G.flush; if (have_round) par_empty ^= 1u; have_round = true; } else ++in_round;
         }
         __syncwarp();
       }
     }
     __syncwarp();
-    segment_tail<Q, H>(P, G, sg, mi, stages, cta, tid, nullptr);
+    segment_tail<Q, H>(P, G, sg, mi, stages, cta, tid, kDrain ? acc : nullptr);
   }
 }
 
@@ -981,11 +1125,15 @@ __global__ void __launch_bounds__(TcCfg<Q, H>::kThreads, 1) bin_scan_tc_kernel(c
     producer_role<Q, H>(P, G, mi, stages, tmem, blockIdx.x, tid);
   } else if (wid < kProd + 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::kRegEpi));
-    if (wid < kProd + C::kEpi) epilogue_role<Q, H>(P, G, mi, stages, tmem, blockIdx.x, tid);
-    else issuer_role<Q, H>(P, G, mi, stages, tmem, blockIdx.x, tid);
+    constexpr bool kDual = GCS_TC_DUAL_ISSUE && Q <= 3;   // Q = 4: the issuer sits in a warpgroup of its own
+    constexpr int kSplit = kDual ? kProd / 2 : kProd;     // the spare warp issues for [0, kSplit), epilogue warp 0 for the rest
+    if (kDual && wid == kProd) issuer_role<Q, H, true>(P, G, mi, stages, tmem, blockIdx.x, tid, kSplit, kProd);
+    else if (wid < kProd + C::kEpi) epilogue_role<Q, H>(P, G, mi, stages, tmem, blockIdx.x, tid);
+    else if (H && GCS_TC_SELF_ISSUE) idle_role<Q, H>(P, G, mi, stages, blockIdx.x, tid);
+    else issuer_role<Q, H, false>(P, G, mi, stages, tmem, blockIdx.x, tid, 0, kSplit);
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (wid == C::kIssuerWarp) issuer_role<Q, H>(P, G, mi, stages, tmem, blockIdx.x, tid);
+    if (wid == C::kIssuerWarp && !(H && GCS_TC_SELF_ISSUE)) issuer_role<Q, H, false>(P, G, mi, stages, tmem, blockIdx.x, tid, 0, kProd);
     else idle_role<Q, H>(P, G, mi, stages, blockIdx.x, tid);
   }
 

@@ -102,6 +102,21 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// one lane of a converged warp (the same lane every time for the same mask): lets the warp run issue code with
+// warp-uniform operands -- tcgen05 instructions take uniform registers, and a thread-divergent `if (lane == 0)` around them
+// makes the compiler wrap every one in a vote / R2UR loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t"
+      "}\n"
+      : "=r"(p));
+  return p != 0;
+}
+
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core operand reads)
