@@ -408,14 +408,18 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
                                       eps_mass: float = constants.GC_EPS_MASS,
                                       recency_min_scale: float = constants.GC_RECENCY_MIN_SCALE,
                                       chart_id: str = constants.GC_CHART_ID,
-                                      anchor_id: str = "lidar_evidence_primitives", defer: bool = False
-                                      ) -> BatchedPrimitiveEvidence:
+                                      anchor_id: str = "lidar_evidence_primitives", defer: bool = False,
+                                      z_lin_poses=None, z_t=None) -> BatchedPrimitiveEvidence:
     """
     Primitive-family LiDAR evidence of H pose hypotheses of one scan (module docstring).  ``xi_bodies`` (H, 6): twist of
     every hypothesis (host array or device tensor, e.g. the rows gcs_imu_scan_twist wrote); ``poses_pred`` (H, 6)
-    [t, rotvec] predicted world poses (map stencil centre + linearisation point).  ``update_map``: hypothesis 0 updates
-    the map first (the reference's order); False: every hypothesis sees the current map read-only.  ``defer``: return
-    as soon as everything is enqueued; ``out.wait()`` (or the first ``out.unit(h)``) blocks for the certificates.
+    [t, rotvec] predicted world poses: the centre of the map stencil (pipeline.py:802-829) and, unless ``z_lin_poses``
+    (H, 6) gives the IMU + odometry informed points of pipeline.py:998-1008, the linearisation points of the pose
+    evidence.  ``update_map``: hypothesis 0 updates the map first (the reference's order) with the pose ``z_t`` (6,)
+    (pipeline.py:1244: the post-recompose pose; default: hypothesis 0's linearisation pose -- a caller that needs the
+    fused pose there runs hypothesis 0 with ``update_map=False`` and ``primitives.map_update_step12b`` itself); False:
+    every hypothesis sees the current map read-only.  ``defer``: return as soon as everything is enqueued; ``out.wait()``
+    (or the first ``out.unit(h)``) blocks for the certificates.
     """
     io = _IO(atlas_map.device)
     pts = io.dev_in(points, shape=(-1, 3))
@@ -433,8 +437,16 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
     poses_h = (poses_pred.detach().cpu().numpy() if isinstance(poses_pred, torch.Tensor) else np.asarray(poses_pred, np.float64)).reshape(-1, 6)
     if poses_h.shape[0] != H or H < 1:
         raise ValueError(f"lidar_evidence_primitives_batched: {H} twists but {poses_h.shape[0]} poses")
-    poses_d = (io.dev_in(poses_pred, shape=(-1, 6)) if isinstance(poses_pred, torch.Tensor) and poses_pred.is_cuda
-               else _h2d_async(io, poses_h, (-1, 6), owned))
+    lin = poses_pred if z_lin_poses is None else z_lin_poses
+    lin_h = None
+    if isinstance(lin, torch.Tensor) and lin.is_cuda:
+        poses_d = io.dev_in(lin, shape=(-1, 6))
+    else:
+        lin_h = poses_h if z_lin_poses is None else (lin.detach().cpu().numpy() if isinstance(lin, torch.Tensor)
+                                                     else np.asarray(lin, np.float64)).reshape(-1, 6)
+        poses_d = _h2d_async(io, lin_h, (-1, 6), owned)
+    if int(poses_d.shape[0]) != H:
+        raise ValueError(f"lidar_evidence_primitives_batched: {H} twists but {int(poses_d.shape[0])} linearisation poses")
     scfg = surfel_config if surfel_config is not None else SurfelExtractionConfig()
     acfg = association_config if association_config is not None else AssociationConfig(scan_seq=int(scan_seq))
     PR._check_assoc_config(acfg)
@@ -456,7 +468,9 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
         out_holder = []
         b0 = _batch_unit(g0.batch, 0)
         a0 = PrimitiveAssociationResult(**{f: getattr(g0.association, f)[0] for f in g0.association.__dataclass_fields__})
-        gens["update"] = PR._map_update_step12b_gen(atlas_map, b0, a0, active0, poses_h[0], scan_seq, scan_end_time,
+        if z_t is None:
+            z_t = poses_h[0] if z_lin_poses is None else (lin_h[0] if lin_h is not None else poses_d[0])
+        gens["update"] = PR._map_update_step12b_gen(atlas_map, b0, a0, active0, z_t, scan_seq, scan_end_time,
                                                     inflate_stats=lambda: out_holder[0]._inflate_stats,
                                                     **(map_update_kwargs or {}))
         io_u, stats_u, _ = next(gens["update"])

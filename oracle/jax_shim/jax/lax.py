@@ -43,3 +43,37 @@ def sort(operand, dimension=-1, is_stable=True, num_keys=1):
         for r in range(ops[0].shape[0]):
             order[r] = _np.lexsort(tuple(ops[k][r] for k in reversed(range(num_keys))))
     return tuple(_wrap(_np.take_along_axis(o, order, axis=dimension)) for o in ops)
+
+
+def _clamp_starts(shape, sizes, starts):
+    # XLA clamps start indices so that the slice stays inside the operand
+    return [int(min(max(int(s), 0), d - z)) for s, d, z in zip(starts, shape, sizes)]
+
+
+def dynamic_update_slice(operand, update, start_indices):
+    out = _np.array(_np.asarray(operand), copy=True)
+    upd = _np.asarray(update)
+    st = _clamp_starts(out.shape, upd.shape, start_indices)
+    out[tuple(slice(s, s + z) for s, z in zip(st, upd.shape))] = upd
+    return _wrap(out)
+
+
+def dynamic_slice(operand, start_indices, slice_sizes):
+    a = _np.asarray(operand)
+    st = _clamp_starts(a.shape, slice_sizes, start_indices)
+    return _wrap(a[tuple(slice(s, s + int(z)) for s, z in zip(st, slice_sizes))].copy())
+
+
+def select(pred, on_true, on_false):
+    return _wrap(_np.where(_np.asarray(pred), _np.asarray(on_true), _np.asarray(on_false)))
+
+
+def stop_gradient(x):
+    return x
+
+
+def while_loop(cond_fun, body_fun, init_val):
+    val = init_val
+    while bool(cond_fun(val)):
+        val = body_fun(val)
+    return val

@@ -14,3 +14,12 @@ def sigmoid(x):
     x = _np.asarray(x)
     with _np.errstate(over="ignore"):
         return _wrap(1.0 / (1.0 + _np.exp(-x)))
+
+
+def softplus(x):
+    """log(1 + e^x), the overflow-safe form jax.nn.softplus uses (logaddexp(x, 0))."""
+    return _wrap(_np.logaddexp(_np.asarray(x, dtype=_np.float64), 0.0))
+
+
+def relu(x):
+    return _wrap(_np.maximum(_np.asarray(x), 0))

@@ -39,11 +39,16 @@ def main():
     for rnd in range(2):
         for n in names:
             env = dict(os.environ)
+            n, *sets = n.split(":")          # name[:ENV=VALUE...]
+            for kv in sets:
+                k, v = kv.split("=")
+                env[k] = v
             if n != "main":
                 env["GCS_B200_LIB"] = os.path.join(here, "gc-slam_b200", "lib", "variants", f"libgcs_b200.{n}.so")
             else:
                 env.pop("GCS_B200_LIB", None)
             r = subprocess.run([sys.executable, "-c", CHILD], cwd=here, env=env, capture_output=True, text=True, timeout=300)
+            n = ":".join([n, *sets])
             res[n].append(r.stdout.strip().splitlines()[-1] if r.returncode == 0 and r.stdout.strip() else "ERR " + r.stderr[-300:])
     for n in names:
         print(f"{n:12s} median/min ms per launch, two rounds: {res[n]}")
