@@ -36,7 +36,8 @@ from pipeline_chain_inputs import N_RAW, SCANS, FULL_STRIDE, X_ANCHOR, scan_inpu
 SPIED = ["point_budget_resample", "deskew_constant_twist", "extract_lidar_surfels", "primitive_map_recency_inflate",
          "extract_atlas_map_view", "associate_primitives_ot", "visual_pose_evidence", "build_visual_pose_evidence_22d",
          "pose_update_frobenius_recompose", "primitive_map_fuse", "primitive_map_insert_masked", "primitive_map_cull",
-         "primitive_map_forget", "primitive_map_merge_reduce", "ma_hex_stencil_tile_ids", "block_associations_for_fuse"]
+         "primitive_map_forget", "primitive_map_merge_reduce", "ma_hex_stencil_tile_ids", "block_associations_for_fuse",
+         "smooth_window_weights", "preintegrate_imu_relative_pose_jax"]
 
 
 def A(x):
@@ -112,6 +113,12 @@ def main():
         o["xi"] = A(kw["xi_body"]); o["ess_imu"] = float(kw["ess_imu"])
         o["rs_points"] = A(kw["points"]); o["rs_weights"] = A(kw["weights"]); o["rs_timestamps"] = A(kw["timestamps"])
         o["dk_points"] = A(r[0].points); o["dk_weights"] = A(r[0].weights)
+        # step 3 (pipeline.py:436-483): the within-scan IMU window and preintegration that produced this twist
+        kw_w = calls["smooth_window_weights"][0][1]
+        kw_p = calls["preintegrate_imu_relative_pose_jax"][0][1]
+        assert float(kw_w["scan_start_time"]) == x["t0"] and float(kw_w["scan_end_time"]) == x["t1"]
+        o["imu_sigma_warp"] = float(kw_w["sigma"]); o["imu_rotvec0"] = A(kw_p["rotvec_start_WB"])
+        o["imu_gyro_bias"] = A(kw_p["gyro_bias"]); o["imu_accel_bias"] = A(kw_p["accel_bias"]); o["imu_gravity_W"] = A(kw_p["gravity_W"])
         (_, kw, r), = calls["extract_lidar_surfels"]
         batch = r[0]
         assert kw["base_batch"] is cb and A(kw["timestamps"]).shape == o["rs_timestamps"].shape

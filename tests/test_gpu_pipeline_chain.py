@@ -74,6 +74,11 @@ def _check_scan(P, S, g, x, out_deskew, batch, inf, view, assoc, c_as, vpe, mu_r
 
 
 def _scan_args(P, ops, S, g, x):
+    # step 3 (pipeline.py:436-483): the twist the loop deskews with, from the IMU window it saw
+    from gc_slam_b200 import imu
+    tw = imu.imu_scan_twist(x["imu_t"], x["gyro"], x["accel"], x["t0"], x["t1"], float(S["imu_sigma_warp"]), S["imu_rotvec0"],
+                            S["imu_gyro_bias"], S["imu_accel_bias"], S["imu_gravity_W"])
+    assert rel_err(_np(tw.xi_body)[0], S["xi"]) < 1e-9 and abs(float(tw.ess[0]) - float(S["ess_imu"])) < 1e-9 * float(S["ess_imu"])
     rs, _, _ = ops.point_budget_resample(x["points"], x["timestamps"], x["weights"], x["ring"], x["tag"], int(g["cap"]))
     S.close("rs_points", _np(rs.points), 1e-14); S.close("rs_weights", _np(rs.weights), 1e-14)
     cam = x["cam"]

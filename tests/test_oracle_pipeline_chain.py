@@ -15,6 +15,7 @@ sys.path.insert(0, GOLDEN)
 from pipeline_chain_inputs import scan_inputs  # noqa: E402
 
 from oracle import bin_path as ob  # noqa: E402
+from oracle import imu as oi  # noqa: E402
 from oracle import prim_path as op  # noqa: E402
 
 
@@ -57,6 +58,10 @@ def test_oracle_chain_matches_the_reference_loop():
     for k in range(1, int(g["n_scans"]) + 1):
         S = Scan(G, k)
         x = scan_inputs(k - 1)
+        # step 3 (pipeline.py:436-483): the twist the loop deskews with, from the IMU window it saw
+        tw = oi.imu_scan_twist(x["imu_t"], x["gyro"], x["accel"], x["t0"], x["t1"], float(S["imu_sigma_warp"]), S["imu_rotvec0"],
+                               S["imu_gyro_bias"], S["imu_accel_bias"], S["imu_gravity_W"])
+        assert rel_err(tw["xi_body"], S["xi"]) < 1e-9 and abs(tw["ess"] - float(S["ess_imu"])) < 1e-9 * float(S["ess_imu"])
         # step 1 + 5 of the loop (pipeline.py:400-418, 569-587)
         rs, _ = ob.point_budget_resample(x["points"], x["timestamps"], x["weights"], x["ring"], x["tag"], int(g["cap"]))
         S.close("rs_points", rs["points"], 1e-14); S.close("rs_weights", rs["weights"], 1e-14)
