@@ -546,7 +546,16 @@ __global__ void __launch_bounds__(32 * kTopkWarps, 1) assoc_topk_kernel(gcs_meas
 // 7 us per iteration on the float64 pow() of 1,536 rows (one SM's FP64 pipe); eight SMs share that work.
 constexpr int kSkCtas = 8;
 constexpr int kSkThreads = 256;
-constexpr int kSkMaxVals = 16;
+// K_ASSOC values this build instantiates (the reference default is 8, config k_assoc: primitive_association.py:60)
+#define GCS_K_ASSOC_DISPATCH(k_, ...)                         \
+  switch (k_) {                                               \
+    case 4: { constexpr int KK = 4; __VA_ARGS__; } break;     \
+    case 8: { constexpr int KK = 8; __VA_ARGS__; } break;     \
+    case 16: { constexpr int KK = 16; __VA_ARGS__; } break;   \
+    default: break;                                           \
+  }
+#define GCS_K_ASSOC_OK(k_) ((k_) == 4 || (k_) == 8 || (k_) == 16)
+constexpr int kSkMaxVals = 24;   // widest row of a cluster_sum: 6 + K certificate columns at K_ASSOC = 16
 
 // Sum of NV (<= kSkMaxVals) values per row over all rows; every thread of every CTA gets post(k, total_k).
 // The rows are cut into kSkCtas = 8 VIRTUAL CTAs of 256 rows; a real CTA of a cluster of C = 8 / RPT CTAs carries RPT of
@@ -772,7 +781,7 @@ __global__ void __launch_bounds__(kSkThreads)
   }
 }
 
-template <int RPT>
+template <int K, int RPT>
 static cudaError_t sinkhorn_launch(cudaStream_t st, unsigned n_units, gcs_meas_batch B, int N, gcs_map_view V, AssocWs W,
                                    gcs_assoc_cfg cfg, gcs_assoc_result R, double* cert, double* brow, double* a_ws) {
   cudaLaunchConfig_t lc;
@@ -785,7 +794,7 @@ static cudaError_t sinkhorn_launch(cudaStream_t st, unsigned n_units, gcs_meas_b
   at[0].val.clusterDim.x = kSkCtas / RPT; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   lc.attrs = at;
   lc.numAttrs = 1;
-  return cudaLaunchKernelEx(&lc, assoc_sinkhorn_kernel<8, RPT>, B, N, V, W, cfg, R, cert, brow, a_ws);
+  return cudaLaunchKernelEx(&lc, assoc_sinkhorn_kernel<K, RPT>, B, N, V, W, cfg, R, cert, brow, a_ws);
 }
 
 // every unit of a stacked batch := the base batch (camera slice, zero LiDAR rows); blockIdx.y = unit
@@ -1535,7 +1544,7 @@ static int assoc_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_meas_batch* bat
   rc = check_assoc(ctx, out, who);
   if (rc) return rc;
   GCS_REQUIRE(ctx, cfg && cert && view_tile_ids, "%s: NULL pointer", who);
-  GCS_REQUIRE(ctx, cfg->k_assoc == 8, "%s: k_assoc=%d (this build instantiates K_ASSOC=8)", who, cfg->k_assoc);
+  GCS_REQUIRE(ctx, GCS_K_ASSOC_OK(cfg->k_assoc), "%s: k_assoc=%d (this build instantiates K_ASSOC = 4, 8, 16)", who, cfg->k_assoc);
   GCS_REQUIRE(ctx, cfg->a_policy == 0 || cfg->a_policy == 1, "%s: a_policy=%d (0 UNIFORM, 1 WEIGHT_PROPORTIONAL)", who, cfg->a_policy);
   GCS_REQUIRE(ctx, n_tiles >= 1 && n_tiles <= 16 && m_tile_view >= cfg->k_assoc, "%s: bad view shape", who);
   const int N = batch->n_feat + batch->n_surfel;
@@ -1559,7 +1568,7 @@ static int assoc_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_meas_batch* bat
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_pos = take(H * N * 3 * 8), o_dir = take(H * N * 3 * 8), o_kap = take(H * N * 8),
-               o_st = take(H * N * n_st), o_brow = take(H * N * 8 * 8),
+               o_st = take(H * N * n_st), o_brow = take(H * N * (size_t)cfg->k_assoc * 8),
                o_vak = take((size_t)n_tiles * m_tile_view * 8), o_ctr = take(256), o_aws = take(H * N * 8);
   rc = gcs_ws_reserve(ctx, off);
   if (rc) return rc;
@@ -1579,15 +1588,16 @@ static int assoc_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_meas_batch* bat
                 tma::encode_2d_f64(&tmap, view->positions, 256, (uint64_t)n_pool * 3 / 256, 256, (uint32_t)(3 * m_tile_view / 256));
   if (getenv("GCS_TOPK_NO_TMA")) staged = false;
   const size_t topk_smem = topk_smem_bytes(n_tiles, m_tile_view, staged);
-  if (topk_smem > 40 * 1024) GCS_CHECK_CUDA(ctx, gcs_smem_attr_once((const void*)assoc_topk_kernel<8>, (int)topk_smem));
+  if (topk_smem > 40 * 1024)
+    GCS_K_ASSOC_DISPATCH(cfg->k_assoc, GCS_CHECK_CUDA(ctx, gcs_smem_attr_once((const void*)assoc_topk_kernel<KK>, (int)topk_smem)));
   int* row_counter = (int*)(ws + o_ctr);
   GCS_CHECK_CUDA(ctx, cudaMemsetAsync(row_counter, 0, sizeof(int), st));
   const long long total_rows = (long long)n_units * N;
   int topk_ctas = (int)((total_rows + kTopkWarps - 1) / kTopkWarps);
   if (topk_ctas > ctx->sm_count) topk_ctas = ctx->sm_count;
   gcs_timing_begin(ctx, st, GCS_TIME_TOPK);
-  assoc_topk_kernel<8><<<topk_ctas, 32 * kTopkWarps, topk_smem, st>>>(*batch, N, n_units, *view, m_tile_view, n_st, n_tiles, W, *cfg,
-                                                                      *out, row_counter, tmap, staged ? 1 : 0);
+  GCS_K_ASSOC_DISPATCH(cfg->k_assoc, (assoc_topk_kernel<KK><<<topk_ctas, 32 * kTopkWarps, topk_smem, st>>>(
+                                         *batch, N, n_units, *view, m_tile_view, n_st, n_tiles, W, *cfg, *out, row_counter, tmap, staged ? 1 : 0)));
   gcs_timing_end(ctx, st, GCS_TIME_TOPK);
   GCS_LAUNCH_CHECK(ctx);
   // cluster size per hypothesis: eight SMs for one, fewer when the batch fills the device anyway
@@ -1596,9 +1606,10 @@ static int assoc_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_meas_batch* bat
   // the iterations are a latency chain (log / exp / barrier), so as many CTAs as stay resident (three per SM) overlap
   const int sk_rpt = (n_units * 8 <= 3 * ctx->sm_count) ? 1 : (n_units * 4 <= 3 * ctx->sm_count ? 2 : 4);
   gcs_timing_begin(ctx, st, GCS_TIME_SINKHORN);
-  if (sk_rpt == 1) GCS_CHECK_CUDA(ctx, sinkhorn_launch<1>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow, a_ws));
-  else if (sk_rpt == 2) GCS_CHECK_CUDA(ctx, sinkhorn_launch<2>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow, a_ws));
-  else GCS_CHECK_CUDA(ctx, sinkhorn_launch<4>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow, a_ws));
+  GCS_K_ASSOC_DISPATCH(cfg->k_assoc,
+    if (sk_rpt == 1) GCS_CHECK_CUDA(ctx, (sinkhorn_launch<KK, 1>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow, a_ws)));
+    else if (sk_rpt == 2) GCS_CHECK_CUDA(ctx, (sinkhorn_launch<KK, 2>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow, a_ws)));
+    else GCS_CHECK_CUDA(ctx, (sinkhorn_launch<KK, 4>(st, Hu, *batch, N, *view, W, *cfg, *out, cert, brow, a_ws))));
   gcs_timing_end(ctx, st, GCS_TIME_SINKHORN);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
@@ -1636,11 +1647,11 @@ int gcs_visual_pose_evidence(gcs_ctx* ctx, void* stream, const gcs_meas_batch* b
   rc = check_assoc(ctx, assoc, "visual_pose_evidence");
   if (rc) return rc;
   GCS_REQUIRE(ctx, pose6 && out_L22 && out_h22 && out_rec, "visual_pose_evidence: NULL pointer");
-  GCS_REQUIRE(ctx, k_assoc == 8, "visual_pose_evidence: k_assoc=%d (this build instantiates K_ASSOC=8)", k_assoc);
+  GCS_REQUIRE(ctx, GCS_K_ASSOC_OK(k_assoc), "visual_pose_evidence: k_assoc=%d (this build instantiates K_ASSOC = 4, 8, 16)", k_assoc);
   const int N = batch->n_feat + batch->n_surfel;
-  pose_evidence_kernel<8><<<1, kPeThreads, 0, (cudaStream_t)stream>>>(*batch, N, *view, *assoc, pose6[0], pose6[1], pose6[2], pose6[3],
-                                                                pose6[4], pose6[5], eps_lift, eps_mass, out_L22, out_h22, out_rec,
-                                                                nullptr, nullptr, 0, nullptr);
+  GCS_K_ASSOC_DISPATCH(k_assoc, (pose_evidence_kernel<KK><<<1, kPeThreads, 0, (cudaStream_t)stream>>>(
+                                    *batch, N, *view, *assoc, pose6[0], pose6[1], pose6[2], pose6[3], pose6[4], pose6[5], eps_lift,
+                                    eps_mass, out_L22, out_h22, out_rec, nullptr, nullptr, 0, nullptr)));
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
 }
@@ -1659,11 +1670,11 @@ int gcs_visual_pose_evidence_batched(gcs_ctx* ctx, void* stream, const gcs_meas_
   rc = check_assoc(ctx, assoc, "visual_pose_evidence_batched");
   if (rc) return rc;
   GCS_REQUIRE(ctx, poses_dev && out_L22 && out_h22 && out_rec && n_units >= 1, "visual_pose_evidence_batched: bad args");
-  GCS_REQUIRE(ctx, k_assoc == 8, "visual_pose_evidence_batched: k_assoc=%d (this build instantiates K_ASSOC=8)", k_assoc);
+  GCS_REQUIRE(ctx, GCS_K_ASSOC_OK(k_assoc), "visual_pose_evidence_batched: k_assoc=%d (this build instantiates K_ASSOC = 4, 8, 16)", k_assoc);
   const int N = batch->n_feat + batch->n_surfel;
-  pose_evidence_kernel<8><<<(unsigned)n_units, kPeThreads, 0, (cudaStream_t)stream>>>(*batch, N, *view, *assoc, 0, 0, 0, 0, 0, 0, eps_lift,
-                                                                                     eps_mass, out_L22, out_h22, out_rec, poses_dev,
-                                                                                     n_lidar_valid, n_camera_valid, view_n_valid);
+  GCS_K_ASSOC_DISPATCH(k_assoc, (pose_evidence_kernel<KK><<<(unsigned)n_units, kPeThreads, 0, (cudaStream_t)stream>>>(
+                                    *batch, N, *view, *assoc, 0, 0, 0, 0, 0, 0, eps_lift, eps_mass, out_L22, out_h22, out_rec,
+                                    poses_dev, n_lidar_valid, n_camera_valid, view_n_valid)));
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
 }

@@ -495,7 +495,7 @@ int gcs_export_map_points(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, co
 
 /* ---- a12 associate_primitives_ot : fl/backend/operators/primitive_association.py:105-553 -------------------- */
 typedef struct {
-  int32_t k_assoc, k_sinkhorn, r_stencil_xy, r_stencil_z;
+  int32_t k_assoc, k_sinkhorn, r_stencil_xy, r_stencil_z;   /* k_assoc: 4, 8 (reference default) or 16 */
   int32_t a_policy;   /* measurement marginal (primitive_association.py:412-424): 0 UNIFORM a = valid / sum(valid),
                          1 WEIGHT_PROPORTIONAL a = valid * weight / sum(valid * weight)                              */
   int32_t reserved_;

@@ -103,6 +103,38 @@ def test_primitive_path_vs_golden(P, case):
         assert np.max(np.abs(wot - wg["ot"]) / (np.abs(wg["ot"]) + 1e-12)) < 1e-7
         assert abs(we.predicted - float(wg["effect"])) < 1e-7 * abs(float(wg["effect"])) + 1e-13
         assert abs(wc.support.support_frac - wg["cert"][SUP]) < 1e-12
+        for kk in (4, 16):               # other candidate counts K_ASSOC (AssociationConfig.k_assoc): association, evidence, update
+            kg = golden(f"assoc_k{kk}_p1.npz")
+            ka, kc, ke = P.associate_primitives_ot(batch, view, P.AssociationConfig(scan_seq=scan_seq, k_assoc=kk))
+            assert np.array_equal(_np(ka.candidate_pool_indices), kg["pool"]) and np.array_equal(_np(ka.candidate_slots), kg["slots"])
+            assert rel_err(_np(ka.cost_matrix), kg["cost"]) < 1e-8 and rel_err(_np(ka.responsibilities), kg["resp"]) < 1e-8
+            assert rel_err(_np(ka.row_masses), kg["row"]) < 1e-8
+            kot = np.array([kc.ot.marginal_defect_a, kc.ot.marginal_defect_b, kc.ot.transport_mass_total, kc.ot.sum_a, kc.ot.sum_m,
+                            kc.ot.sum_novel, kc.ot.p95_a, kc.ot.nonzero_a, kc.ot.b_recency_p95])
+            assert np.max(np.abs(kot - kg["ot"]) / (np.abs(kg["ot"]) + 1e-12)) < 1e-7
+            assert abs(ke.predicted - float(kg["effect"])) < 1e-7 * abs(float(kg["effect"])) + 1e-13
+            assert kc.compute.largest_tensor_shape == (batch.n_total, kk) and kc.compute.segment_sum_k == kk
+            kv, _, _ = P.visual_pose_evidence(ka, batch, view, g["pose"], z_lin_pose=g["pose"])
+            assert rel_err(_np(kv.L_pose), kg["vp_L"]) < 1e-7 and rel_err(_np(kv.h_pose), kg["vp_h"]) < 1e-6
+            assert abs(kv.total_weighted_cost - float(kg["vp_cost"])) < 1e-7 * abs(float(kg["vp_cost"]))
+            # the map update with that K against the oracle's (on copies of the map)
+            from oracle import prim_path as op
+            from test_oracle_prim_vs_golden import build_inputs as _bi
+            o_atlas, _ = op.recency_inflate(_bi(g)[3], active, scan_seq)
+            o_assoc = dict(candidate_tile_ids=_np(ka.candidate_tile_ids), candidate_slots=_np(ka.candidate_slots),
+                           responsibilities=_np(ka.responsibilities), row_masses=_np(ka.row_masses))
+            o_batch = {f: _np(getattr(batch, f)) for f in ("Lambdas", "thetas", "etas", "weights", "colors", "sources")}
+            o_batch["valid_mask"] = _np(batch.valid_mask).astype(bool)
+            o2, st = op.map_update(o_atlas, o_batch, o_assoc, active, g["z_t"], scan_seq, float(g["ts"]), k_insert=int(g["k_ins"]))
+            m2 = P.AtlasMap.from_numpy(atlas_np)
+            m2, _, _, _ = P.primitive_map_recency_inflate(m2, active, scan_seq)
+            r2, c2, _ = P.map_update_step12b(m2, batch, ka, active, g["z_t"], scan_seq, float(g["ts"]), k_insert_tile=int(g["k_ins"]))
+            assert (r2.n_fused, r2.n_inserted, r2.n_culled) == (st["fused_count"], st["insert_count_total"], st["evicted_count"])
+            assert np.array_equal(_np(r2.new_ids), np.stack(st["new_ids"]))
+            for tid in active:
+                t2 = m2.download_tile(tid)
+                assert np.array_equal(t2["valid_mask"], o2["tiles"][tid]["valid_mask"]) and rel_err(t2["weights"], o2["tiles"][tid]["weights"]) < 1e-9
+                assert rel_err(t2["Lambdas"].sum(axis=0), o2["tiles"][tid]["Lambdas"].sum(axis=0)) < 1e-8
     # ---- a13
     vpe, c_vp, _ = P.visual_pose_evidence(assoc, batch, view, g["pose"], z_lin_pose=g["pose"])
     assert rel_err(_np(vpe.L_pose), g["vp_L"]) < 1e-7 and rel_err(_np(vpe.h_pose), g["vp_h"]) < 1e-6
