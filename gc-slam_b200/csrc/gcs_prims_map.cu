@@ -226,6 +226,12 @@ struct AssocWs {
   double* mkap;     // (N)
   int8_t* stencil;  // (N, n_st)  view tile index or -1
   double* vAk;      // (P) A_vmf(kappa) of every view entry: one evaluation per scan instead of one per candidate pair
+  // the view regrouped for the top-K scan (shared by all units): per tile the valid entries in Morton order, cut into
+  // groups of 32 with their bounding boxes
+  double* gpos;     // (P,3) positions in group order
+  uint16_t* goff;   // (P)   offset within the tile of the entry at this sorted slot
+  uint8_t* gval;    // (P)   validity in group order (invalid entries last)
+  double* gbox;     // (n_tiles, ceil(m_view / 32), 6) min xyz, max xyz of the valid entries of a group (empty: min > max)
 };
 
 // unit u (hypothesis) of the stacked work arrays; the view and its vAk are shared by all units
@@ -263,6 +269,102 @@ __global__ void __launch_bounds__(128) assoc_prepare_kernel(gcs_meas_batch B, in
     for (int a = 0; a < T.n; ++a)
       if (T.id[a] == tid) { idx = a; break; }  // argmax of the equality mask = first match
     W.stencil[i * n_st + s] = (int8_t)idx;
+  }
+}
+
+// The view regrouped for the top-K scan: one CTA per view tile sorts the tile's valid entries along a Morton curve through
+// their bounding box (30-bit keys, bitonic sort in shared memory; tiles above 1024 entries keep their order), writes the
+// positions / original offsets / validity in that order and the bounding box of every group of 32 consecutive entries.
+// A measurement row then tests 32 boxes per tile with one instruction stream and scans only the groups whose box comes
+// within its current K-th best cost, nearest box first -- instead of the five-flop bound of every one of the 7 x 1024
+// candidates.  Any order is correct (ties are broken on the ORIGINAL offset); the order only decides how tight the boxes are.
+__device__ __forceinline__ unsigned morton_spread10(unsigned x) {
+  x &= 0x3ffu;
+  x = (x | (x << 16)) & 0x030000ffu;
+  x = (x | (x << 8)) & 0x0300f00fu;
+  x = (x | (x << 4)) & 0x030c30c3u;
+  x = (x | (x << 2)) & 0x09249249u;
+  return x;
+}
+
+__global__ void __launch_bounds__(1024) assoc_view_groups_kernel(gcs_map_view V, int m_view, AssocWs W) {
+  __shared__ KeyIdx srt[1024];
+  __shared__ double red[6][32];
+  __shared__ double bb[6];
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t t0 = (size_t)t * m_view;
+  const bool sortable = m_view <= 1024;
+  // bounding box of the tile's valid entries
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int r = tid; r < m_view; r += 1024) {
+    if (V.valid[t0 + r]) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { const double x = V.positions[3 * (t0 + r) + k]; lo[k] = fmin(lo[k], x); hi[k] = fmax(hi[k], x); }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+      hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+    }
+    if (lane == 0) { red[k][warp] = lo[k]; red[3 + k][warp] = hi[k]; }
+  }
+  __syncthreads();
+  if (tid < 6) {
+    double a = red[tid][0];
+    for (int w = 1; w < 32; ++w) a = tid < 3 ? fmin(a, red[tid][w]) : fmax(a, red[tid][w]);
+    bb[tid] = a;
+  }
+  __syncthreads();
+  if (sortable) {
+    int n_pow2 = 32;
+    while (n_pow2 < m_view) n_pow2 <<= 1;
+    if (tid < n_pow2) {
+      KeyIdx e;
+      e.key = ~0ull; e.idx = tid; e.pad = 0;      // invalid entries and the padding sort last, in index order
+      if (tid < m_view && V.valid[t0 + tid]) {
+        unsigned q[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double ext = bb[3 + k] - bb[k];
+          const double u = ext > 0.0 ? (V.positions[3 * (t0 + tid) + k] - bb[k]) / ext : 0.0;
+          q[k] = (unsigned)fmin(fmax(u * 1023.0, 0.0), 1023.0);
+        }
+        e.key = (unsigned long long)(morton_spread10(q[0]) | (morton_spread10(q[1]) << 1) | (morton_spread10(q[2]) << 2));
+      }
+      srt[tid] = e;
+    }
+    cta_bitonic_sort(srt, n_pow2);
+  }
+  const int G = (m_view + 31) / 32;
+  for (int g = warp; g < G; g += 32) {
+    const int r = g * 32 + lane;
+    int src = r;
+    bool v = false;
+    double p[3] = {0.0, 0.0, 0.0};
+    if (r < m_view) {
+      if (sortable) src = srt[r].idx;
+      v = src < m_view && V.valid[t0 + src] != 0;
+      if (src >= m_view) src = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) p[k] = V.positions[3 * (t0 + src) + k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) W.gpos[3 * (t0 + r) + k] = p[k];
+      W.goff[t0 + r] = (uint16_t)src;
+      W.gval[t0 + r] = v ? 1 : 0;
+    }
+    double glo[3], ghi[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      glo[k] = v ? p[k] : 1e300; ghi[k] = v ? p[k] : -1e300;
+      for (int o = 16; o > 0; o >>= 1) {
+        glo[k] = fmin(glo[k], __shfl_xor_sync(0xffffffffu, glo[k], o));
+        ghi[k] = fmax(ghi[k], __shfl_xor_sync(0xffffffffu, ghi[k], o));
+      }
+    }
+    const double out6 = lane == 0 ? glo[0] : lane == 1 ? glo[1] : lane == 2 ? glo[2] : lane == 3 ? ghi[0] : lane == 4 ? ghi[1] : ghi[2];
+    if (lane < 6) W.gbox[((size_t)t * G + g) * 6 + lane] = out6;
   }
 }
 
@@ -312,8 +414,12 @@ struct TopkShared {               // behind the staged tiles in dynamic shared m
   unsigned long long bar[kTopkMaxTiles];
   int queue[kTopkWarps][64];
 };
+// staged per view entry: position (24 B), validity (1 B), original offset (2 B); per group of 32 entries a box (48 B)
+inline size_t topk_val_bytes(int n_tiles, int m_view) { return ((size_t)n_tiles * m_view + 127) & ~(size_t)127; }
+inline size_t topk_box_bytes(int n_tiles, int m_view) { return (size_t)n_tiles * ((m_view + 31) / 32) * 48; }
 inline size_t topk_smem_bytes(int n_tiles, int m_view, bool staged) {
-  return (staged ? (size_t)n_tiles * m_view * 25 : 0) + 128 + sizeof(TopkShared);
+  return (staged ? (size_t)n_tiles * m_view * 24 + 3 * topk_val_bytes(n_tiles, m_view) + topk_box_bytes(n_tiles, m_view) : 0) + 128 +
+         sizeof(TopkShared);
 }
 
 template <int K>
@@ -323,11 +429,15 @@ __global__ void __launch_bounds__(32 * kTopkWarps, 1) assoc_topk_kernel(gcs_meas
                                                                         int* __restrict__ row_counter,
                                                                         const __grid_constant__ CUtensorMap tmap, int staged) {
   extern __shared__ __align__(128) unsigned char topk_smem[];
+  const int n_grp = (m_view + 31) / 32;          // groups of 32 sorted entries per tile
   const size_t pos_bytes = staged ? (size_t)n_view_tiles * m_view * 24 : 0;
   const size_t val_bytes = staged ? (((size_t)n_view_tiles * m_view + 127) & ~(size_t)127) : 0;
+  const size_t box_bytes = staged ? (size_t)n_view_tiles * n_grp * 48 : 0;
   double* s_pos = reinterpret_cast<double*>(topk_smem);
-  uint8_t* s_val = topk_smem + pos_bytes;
-  TopkShared& S = *reinterpret_cast<TopkShared*>(topk_smem + pos_bytes + val_bytes);
+  double* s_box = reinterpret_cast<double*>(topk_smem + pos_bytes);
+  uint16_t* s_off = reinterpret_cast<uint16_t*>(topk_smem + pos_bytes + box_bytes);
+  uint8_t* s_val = topk_smem + pos_bytes + box_bytes + 2 * val_bytes;
+  TopkShared& S = *reinterpret_cast<TopkShared*>(topk_smem + pos_bytes + box_bytes + 3 * val_bytes);
   const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(S.bar);
   if (staged) {
@@ -341,19 +451,26 @@ __global__ void __launch_bounds__(32 * kTopkWarps, 1) assoc_topk_kernel(gcs_meas
         tma::load_2d(s_pos + (size_t)t * 3 * m_view, &tmap, 0, t * rows_per_tile, &bars[t]);
       }
     }
-    for (int e = threadIdx.x; e < n_view_tiles * m_view; e += 32 * kTopkWarps) s_val[e] = V.valid[e];
-    __syncthreads();   // barriers initialised, validity bytes staged
+    for (int e = threadIdx.x; e < n_view_tiles * m_view; e += 32 * kTopkWarps) { s_val[e] = W0.gval[e]; s_off[e] = W0.goff[e]; }
+    for (int e = threadIdx.x; e < n_view_tiles * n_grp * 6; e += 32 * kTopkWarps) s_box[e] = W0.gbox[e];
+    __syncthreads();   // barriers initialised, validity bytes / offsets / group boxes staged
   }
   int* queue = S.queue[wq];
   const long long total_rows = (long long)n_units * N;
   unsigned tiles_seen = 0;      // tiles whose mbarrier this warp has already seen complete
   const bool prune = cfg.beta >= 0.0;
 
+  // the work item of the NEXT row is requested while the current row is processed: the counter's round trip to L2 was
+  // a serial 4 % of the kernel
+  // the work item of the NEXT row is requested while the current row is processed (the counter's round trip to L2 is
+  // serial otherwise).  Rows are taken one at a time: chunks of four were measured 30 % slower (heavy rows -- the camera
+  // features near the pose -- are neighbours, and a single hypothesis has too few chunks for 2,368 warps)
+  int next_row = 0;
+  if (lane == 0) next_row = atomicAdd(row_counter, 1);
   for (;;) {
-    int row = 0;
-    if (lane == 0) row = atomicAdd(row_counter, 1);
-    row = __shfl_sync(0xffffffffu, row, 0);
+    const int row = __shfl_sync(0xffffffffu, next_row, 0);
     if (row >= total_rows) break;
+    if (lane == 0) next_row = atomicAdd(row_counter, 1);
     const int u = row / N, i = row - u * N;
     const gcs_meas_batch B = meas_batch_unit(B0, u);
     const AssocWs W = assoc_ws_unit(W0, u, N, n_st);
@@ -361,14 +478,17 @@ __global__ void __launch_bounds__(32 * kTopkWarps, 1) assoc_topk_kernel(gcs_meas
     const double mp[3] = {W.mpos[3 * i], W.mpos[3 * i + 1], W.mpos[3 * i + 2]};
     const double md[3] = {W.mdir[3 * i], W.mdir[3 * i + 1], W.mdir[3 * i + 2]};
     const double mk = W.mkap[i];
-    const double A_k1 = A_vmf(fmax(mk, 1e-12), 1e-12);
-    const int8_t* my_st = W.stencil + (size_t)i * n_st;
+    const int8_t* my_st_mem = W.stencil + (size_t)i * n_st;
+    // the row's stencil (view tile index per stencil position, -1: not in the view) in a register for n_st <= 8
+    unsigned long long stw = 0ull;
+    for (int q = 0; q < n_st && q < 8; ++q) stw |= (unsigned long long)(uint8_t)my_st_mem[q] << (8 * q);
+    auto my_st = [&](int q) -> int { return q < 8 ? (int)(int8_t)(stw >> (8 * q)) : (int)my_st_mem[q]; };
     const bool mvalid = B.valid[i] != 0;
     // A row whose stencil has no tile in the view sees the cost 1e12 for every candidate: the first K of the stable
     // sort are offsets 0..K-1 of stencil position 0.  Most surfels of a scan lie further from the pose than the view
     // reaches, so this is the common case.
     bool any_tile = false;
-    for (int q = 0; q < n_st; ++q) any_tile |= my_st[q] >= 0;
+    for (int q = 0; q < n_st; ++q) any_tile |= my_st(q) >= 0;
     if (!any_tile) {
       if (lane < K) {
         const int v = mvalid ? lane : 0;   // invalid measurement rows point at pool entry 0 (:379)
@@ -378,6 +498,7 @@ __global__ void __launch_bounds__(32 * kTopkWarps, 1) assoc_topk_kernel(gcs_meas
       }
       continue;
     }
+    const double A_k1 = A_vmf(fmax(mk, 1e-12), 1e-12);
     double bc[K];
     int bj[K];
 #pragma unroll
@@ -388,7 +509,7 @@ __global__ void __launch_bounds__(32 * kTopkWarps, 1) assoc_topk_kernel(gcs_meas
     // One loop over [view tiles in the row's order | stencil positions without a tile | drain]: a single copy of the
     // exact-cost code in the instruction stream (three inlined copies thrashed the instruction cache: 16 warps, each
     // somewhere else in 80 KB of code).
-    const int c0 = my_st[n_st / 2];
+    const int c0 = my_st(n_st / 2);
     const int t_first = (c0 >= 0 && c0 < n_view_tiles) ? c0 : 0;
     const int n_seg = n_view_tiles + n_st;
     for (int g = 0; g <= n_seg; ++g) {
@@ -397,61 +518,90 @@ __global__ void __launch_bounds__(32 * kTopkWarps, 1) assoc_topk_kernel(gcs_meas
       int s = 0;
       const double* tile_pos = nullptr;
       const uint8_t* tile_valid = nullptr;
+      const uint16_t* tile_off = nullptr;
+      const double* tile_box = nullptr;
       if (g < n_view_tiles) {
         const int t = g == 0 ? t_first : (g <= t_first ? g - 1 : g);
         s = -1;
         for (int q = 0; q < n_st; ++q)
-          if (my_st[q] == t) { s = q; break; }
+          if (my_st(q) == t) { s = q; break; }
         if (s < 0) continue;
         present = true;
         if (staged) {
           if (!((tiles_seen >> t) & 1u)) { tc::mbar_wait(&bars[t], 0); tiles_seen |= 1u << t; }
           tile_pos = s_pos + (size_t)t * 3 * m_view;
           tile_valid = s_val + (size_t)t * m_view;
+          tile_off = s_off + (size_t)t * m_view;
+          tile_box = s_box + (size_t)t * n_grp * 6;
         } else {
-          tile_pos = V.positions + (size_t)t * 3 * m_view;
-          tile_valid = V.valid + (size_t)t * m_view;
+          tile_pos = W.gpos + (size_t)t * 3 * m_view;
+          tile_valid = W.gval + (size_t)t * m_view;
+          tile_off = W.goff + (size_t)t * m_view;
+          tile_box = W.gbox + (size_t)t * n_grp * 6;
         }
       } else if (!drain) {
         // stencil positions whose tile is not in the view carry cost 1e12 for every offset: they only matter while
         // fewer than K better candidates exist
         s = g - n_view_tiles;
-        if (my_st[s] >= 0) continue;
+        if (my_st(s) >= 0) continue;
         if (prune && (1e12 > T || (1e12 == T && s * m_view > Tj))) continue;
       } else if (qn == 0) {
         break;
       }
       const int jbase = s * m_view;
-      const int n_off = drain ? 1 : m_view;
-      for (int base2 = 0; base2 < n_off; base2 += 64) {
-      // the five-flop lower bounds of two 32-candidate steps are evaluated together (two independent load / float64
-      // chains in flight), then the steps are offered one after the other through a single copy of the queue / exact-cost code
-      double lb2[2] = {1e12, 1e12};
-      if (present) {
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int off = base2 + 32 * hh + lane;
-          if (off < m_view && tile_valid[off]) {
-            const double d0 = mp[0] - tile_pos[3 * off], d1 = mp[1] - tile_pos[3 * off + 1], d2 = mp[2] - tile_pos[3 * off + 2];
-            lb2[hh] = d0 * d0 + d1 * d1 + d2 * d2;
-          }
-        }
-      }
-      bool stop = false;
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        const int base = base2 + 32 * hh;
-        if (base >= n_off) break;
-        const int off = base + lane, j = jbase + off;
+      // Steps of 32 candidates (one per lane) from one of three sources, then ONE copy of the queue / exact-cost code:
+      //   tile in view: the groups of the tile, nearest bounding box first, until the nearest remaining box lies beyond T;
+      //   stencil position without a tile: offsets in order (cost 1e12 each) while they can still matter;
+      //   drain: nothing new, the queue is emptied.
+      int step = 0, g0 = 0;
+      unsigned remaining = 0u;      // groups of the current chunk of 32 (bit = lane holding the group's bound) still to scan
+      unsigned lbt_hi = 0xffffffffu;   // this lane's group bound: high word of |dp to box|^2 rounded DOWN (a valid bound, and
+                                       // 32-bit keys order the groups exactly)
+      for (;;) {
         bool pass = false;
+        int j = 0;
         if (present) {
-          if (off < m_view) {
-            const double lb = hh ? lb2[1] : lb2[0];
+          if (remaining == 0u) {
+            if (g0 >= n_grp) break;
+            const int gi = g0 + lane;
+            lbt_hi = 0xffffffffu;
+            if (gi < n_grp) {
+              const double* bx = tile_box + 6 * gi;
+              if (bx[0] <= bx[3]) {
+                const double d0 = fmax(fmax(bx[0] - mp[0], mp[0] - bx[3]), 0.0), d1 = fmax(fmax(bx[1] - mp[1], mp[1] - bx[4]), 0.0),
+                             d2 = fmax(fmax(bx[2] - mp[2], mp[2] - bx[5]), 0.0);
+                // (1 - 2^-40): the box distance is exact-arithmetic <= every |dp|^2 of the group, the rounding of either is not
+                const double lbg = (d0 * d0 + d1 * d1 + d2 * d2) * (1.0 - 9.094947017729282e-13);
+                lbt_hi = (unsigned)((unsigned long long)__double_as_longlong(lbg) >> 32);
+              }
+            }
+            remaining = __ballot_sync(0xffffffffu, lbt_hi != 0xffffffffu);
+            g0 += 32;
+            if (remaining == 0u) continue;
+          }
+          const unsigned mine = ((remaining >> lane) & 1u) ? lbt_hi : 0xffffffffu;
+          const unsigned best = __reduce_min_sync(0xffffffffu, mine);
+          const int gsel = __ffs(__ballot_sync(0xffffffffu, mine == best)) - 1;
+          // every remaining group of the chunk is at least this far: beyond T none of them holds one of the first K
+          if (prune && __longlong_as_double((long long)((unsigned long long)best << 32)) > T) { remaining = 0u; continue; }
+          remaining &= ~(1u << gsel);
+          const int r = (g0 - 32 + gsel) * 32 + lane;
+          if (r < m_view && tile_valid[r]) {
+            j = jbase + (int)tile_off[r];
+            const double d0 = mp[0] - tile_pos[3 * r], d1 = mp[1] - tile_pos[3 * r + 1], d2 = mp[2] - tile_pos[3 * r + 2];
+            const double lb = d0 * d0 + d1 * d1 + d2 * d2;
             pass = !prune || !(lb > T || (lb == T && j > Tj));   // lb <= cost: beyond (T, Tj) it cannot be among the first K
           }
         } else if (!drain) {
-          if (prune && (1e12 > T || (1e12 == T && jbase + base > Tj))) { stop = true; break; }
+          const int base = 32 * step;
+          if (base >= m_view) break;
+          if (prune && (1e12 > T || (1e12 == T && jbase + base > Tj))) break;
+          const int off = base + lane;
+          j = jbase + off;
           pass = off < m_view && (!prune || !(1e12 > T || (1e12 == T && j > Tj)));
+          ++step;
+        } else if (step++ > 0 || qn == 0) {
+          break;
         }
         const unsigned pm = __ballot_sync(0xffffffffu, pass);
         if (pm != 0u) {
@@ -459,14 +609,16 @@ __global__ void __launch_bounds__(32 * kTopkWarps, 1) assoc_topk_kernel(gcs_meas
           qn += __popc(pm);
           __syncwarp();
         }
-        if (qn >= 32 || (drain && qn > 0)) {
+        // exact costs as soon as a full warp of candidates waits -- or, while no bound exists yet, as soon as K wait: the
+        // first K exact costs are what lets the boxes prune
+        if (qn >= 32 || (drain && qn > 0) || (T >= 1.0e299 && qn >= K)) {
           const int n_take = qn < 32 ? qn : 32;
           // ---- exact costs of n_take queued candidates, one per lane; each lane keeps its K best in (cost, j) order
           bool head_changed = false;
           if (lane < n_take) {
             const int jq = queue[lane];
             const int sq = jq / m_view, offq = jq - sq * m_view;
-            const int tix = my_st[sq];
+            const int tix = my_st(sq);
             const int v = (tix < 0 ? 0 : tix) * m_view + offq;
             double c = 1e12;
             if (tix >= 0 && V.valid[v])
@@ -504,11 +656,11 @@ __global__ void __launch_bounds__(32 * kTopkWarps, 1) assoc_topk_kernel(gcs_meas
           if (lane < qn) queue[lane] = moved;
           __syncwarp();
         }
-      }   // the two steps of this pair
-      if (stop) break;
-      }   // pairs of 32-candidate steps
+      }   // steps of this segment
     }
-    // K rounds of arg-min over the lanes' heads by (cost, j); the winner pops its list
+    // K rounds of arg-min over the lanes' heads by (cost, j); the winner pops its list.  Lane r keeps the r-th winner and
+    // the K lanes write the row's outputs together (the gathers of the tile ids / slots were K serial round trips)
+    int win_j = 0;
 #pragma unroll 1
     for (int r = 0; r < K; ++r) {
       unsigned long long hkey;
@@ -519,15 +671,16 @@ __global__ void __launch_bounds__(32 * kTopkWarps, 1) assoc_topk_kernel(gcs_meas
         for (int k = 0; k < K - 1; ++k) { bc[k] = bc[k + 1]; bj[k] = bj[k + 1]; }
         bc[K - 1] = 1.0e300; bj[K - 1] = 0x7fffffff;
       }
-      if (lane == 0) {
-        const int s = hj / m_view, off = hj - s * m_view;
-        const int tix = my_st[s];
-        int v = (tix < 0 ? 0 : tix) * m_view + off;
-        if (!mvalid) v = 0;  // invalid measurement rows point at pool entry 0 (:379)
-        R.candidate_pool_indices[i * K + r] = v;
-        R.candidate_tile_ids[i * K + r] = V.candidate_tile_ids[v];
-        R.candidate_slots[i * K + r] = (long long)V.candidate_slots[v];
-      }
+      if (lane == r) win_j = hj;
+    }
+    if (lane < K) {
+      const int s = win_j / m_view, off = win_j - s * m_view;
+      const int tix = my_st(s);
+      int v = (tix < 0 ? 0 : tix) * m_view + off;
+      if (!mvalid) v = 0;  // invalid measurement rows point at pool entry 0 (:379)
+      R.candidate_pool_indices[i * K + lane] = v;
+      R.candidate_tile_ids[i * K + lane] = V.candidate_tile_ids[v];
+      R.candidate_slots[i * K + lane] = (long long)V.candidate_slots[v];
     }
     __syncwarp();
   }
@@ -1569,23 +1722,30 @@ static int assoc_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_meas_batch* bat
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_pos = take(H * N * 3 * 8), o_dir = take(H * N * 3 * 8), o_kap = take(H * N * 8),
                o_st = take(H * N * n_st), o_brow = take(H * N * (size_t)cfg->k_assoc * 8),
-               o_vak = take((size_t)n_tiles * m_tile_view * 8), o_ctr = take(256), o_aws = take(H * N * 8);
+               o_vak = take((size_t)n_tiles * m_tile_view * 8), o_ctr = take(256), o_aws = take(H * N * 8),
+               o_gpos = take((size_t)n_tiles * m_tile_view * 24), o_goff = take((size_t)n_tiles * m_tile_view * 2),
+               o_gval = take((size_t)n_tiles * m_tile_view), o_gbox = take(topk_box_bytes(n_tiles, m_tile_view));
   rc = gcs_ws_reserve(ctx, off);
   if (rc) return rc;
   char* ws = (char*)ctx->ws;
   AssocWs W;
   W.mpos = (double*)(ws + o_pos); W.mdir = (double*)(ws + o_dir); W.mkap = (double*)(ws + o_kap); W.stencil = (int8_t*)(ws + o_st);
   W.vAk = (double*)(ws + o_vak);
+  W.gpos = (double*)(ws + o_gpos); W.goff = (uint16_t*)(ws + o_goff); W.gval = (uint8_t*)(ws + o_gval); W.gbox = (double*)(ws + o_gbox);
+  GCS_REQUIRE(ctx, m_tile_view <= 65535, "%s: m_tile_view=%d exceeds the 16-bit offsets of the grouped view", who, m_tile_view);
   const int n_pool = n_tiles * m_tile_view, row_blocks = (N + 127) / 128;
   const unsigned Hu = (unsigned)n_units;
   assoc_prepare_kernel<<<dim3(row_blocks + (n_pool + 127) / 128, Hu), 128, 0, st>>>(*batch, N, T, *cfg, n_st, SO, W, *view, n_pool,
                                                                                    row_blocks);
   GCS_LAUNCH_CHECK(ctx);
+  // the view in group order (once per view: shared by every unit and every row)
+  assoc_view_groups_kernel<<<n_tiles, 1024, 0, st>>>(*view, m_tile_view, W);
+  GCS_LAUNCH_CHECK(ctx);
   // top-K: persistent CTAs pulling rows from a counter; view tiles staged once per CTA by TMA when the box fits
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  bool staged = (m_tile_view % 256 == 0) && topk_smem_bytes(n_tiles, m_tile_view, true) <= 200 * 1024 &&
-                tma::encode_2d_f64(&tmap, view->positions, 256, (uint64_t)n_pool * 3 / 256, 256, (uint32_t)(3 * m_tile_view / 256));
+  bool staged = (m_tile_view % 256 == 0) && topk_smem_bytes(n_tiles, m_tile_view, true) <= 220 * 1024 &&
+                tma::encode_2d_f64(&tmap, W.gpos, 256, (uint64_t)n_pool * 3 / 256, 256, (uint32_t)(3 * m_tile_view / 256));
   if (getenv("GCS_TOPK_NO_TMA")) staged = false;
   const size_t topk_smem = topk_smem_bytes(n_tiles, m_tile_view, staged);
   if (topk_smem > 40 * 1024)
