@@ -25,6 +25,12 @@ struct gcs_ctx {
   int timing_on;   // 0 off, 1 every bracketed kernel, 100 + tag: only the kernel with that tag (GCS_TIME_*)
   int timing_n;
   cudaEvent_t timing_ev[2 * 256];
+  // side stream of the fused primitive entry (the map view is prepared while the scan's surfels are extracted): created
+  // on first use, with a workspace of its own (the two streams' scratch must not alias)
+  cudaStream_t side_stream;
+  cudaEvent_t ev_fork, ev_join;
+  void* ws_side;
+  uint64_t ws_side_bytes;
   char err[512];
 };
 
@@ -41,6 +47,7 @@ static inline void gcs_timing_end(gcs_ctx* ctx, cudaStream_t st, int tag) {
 
 int gcs_set_error(gcs_ctx* ctx, int code, const char* fmt, ...);
 int gcs_ws_reserve(gcs_ctx* ctx, uint64_t bytes);
+int gcs_side_reserve(gcs_ctx* ctx, uint64_t bytes);   // side stream + events (first call) and its workspace (grow-only)
 
 #define GCS_CHECK_CUDA(ctx, expr)                                                                 \
   do {                                                                                            \

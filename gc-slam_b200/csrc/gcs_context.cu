@@ -62,6 +62,28 @@ int gcs_ws_reserve(gcs_ctx* ctx, uint64_t bytes) {
   return GCS_OK;
 }
 
+int gcs_side_reserve(gcs_ctx* ctx, uint64_t bytes) {
+  if (!ctx->side_stream) {
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    if (e != cudaSuccess) return gcs_set_error(ctx, GCS_ECUDA, "side stream: %s", cudaGetErrorString(e));
+  }
+  if (bytes <= ctx->ws_side_bytes) return GCS_OK;
+  if (ctx->ws_frozen)
+    return gcs_set_error(ctx, GCS_ENOMEM, "workspace frozen: the side workspace needs %llu bytes", (unsigned long long)bytes);
+  // growth (once per view shape): nothing enqueued earlier may still use the old block
+  cudaDeviceSynchronize();
+  if (ctx->ws_side) cudaFree(ctx->ws_side);
+  ctx->ws_side = nullptr; ctx->ws_side_bytes = 0;
+  const uint64_t want = ((bytes + (1ull << 20) - 1) >> 20) << 20;
+  cudaError_t e = cudaMalloc(&ctx->ws_side, want);
+  if (e != cudaSuccess)
+    return gcs_set_error(ctx, GCS_ENOMEM, "side workspace cudaMalloc(%llu) failed: %s", (unsigned long long)want, cudaGetErrorString(e));
+  ctx->ws_side_bytes = want;
+  return GCS_OK;
+}
+
 static void gcs_ws_release_retired(gcs_ctx* ctx) {
   if (ctx->n_retired == 0) return;
   cudaDeviceSynchronize();
@@ -136,6 +158,13 @@ int gcs_destroy(gcs_ctx* ctx) {
     for (int i = 0; i < 2 * 256; ++i) cudaEventDestroy(ctx->timing_ev[i]);
   gcs_ws_release_retired(ctx);
   if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->side_stream) {
+    cudaStreamSynchronize(ctx->side_stream);
+    cudaStreamDestroy(ctx->side_stream);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+  }
+  if (ctx->ws_side) cudaFree(ctx->ws_side);
   free(ctx);
   return GCS_OK;
 }

@@ -247,11 +247,7 @@ struct StencilOffsets {   // kernel parameter (no host -> device copy: the call 
 __global__ void __launch_bounds__(128) assoc_prepare_kernel(gcs_meas_batch B, int N, TileList T, gcs_assoc_cfg cfg,
                                                             int n_st, StencilOffsets SO,
                                                             AssocWs W, gcs_map_view V, int n_pool, int row_blocks) {
-  if ((int)blockIdx.x >= row_blocks) {   // the blocks behind the rows' blocks take the view entries (once: unit 0)
-    const int v = ((int)blockIdx.x - row_blocks) * blockDim.x + threadIdx.x;
-    if (blockIdx.y == 0 && v < n_pool) W.vAk[v] = A_vmf(fmax(V.kappas[v], 1e-12), 1e-12);
-    return;
-  }
+  (void)V; (void)n_pool; (void)row_blocks;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   B = meas_batch_unit(B, blockIdx.y);
@@ -337,6 +333,8 @@ __global__ void __launch_bounds__(1024) assoc_view_groups_kernel(gcs_map_view V,
     }
     cta_bitonic_sort(srt, n_pow2);
   }
+  // A_vmf(kappa) of every view entry: one evaluation per view instead of one per candidate pair
+  for (int r = tid; r < m_view; r += 1024) W.vAk[t0 + r] = A_vmf(fmax(V.kappas[t0 + r], 1e-12), 1e-12);
   const int G = (m_view + 31) / 32;
   for (int g = warp; g < G; g += 32) {
     const int r = g * 32 + lane;
@@ -1632,7 +1630,8 @@ int gcs_map_recency_inflate(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, 
 
 static int map_view_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_atlas* atlas, const int32_t* tile_index,
                            const int64_t* tile_ids, int32_t n_tiles, int32_t m_tile_view, double eps_lift, double eps_mass,
-                           const gcs_map_view* view, int32_t* out_n_valid, InflateArg I, double* inflate_stats, const char* who) {
+                           const gcs_map_view* view, int32_t* out_n_valid, InflateArg I, double* inflate_stats, const char* who,
+                           double* part_ws = nullptr /* scratch for the inflation partials; default: the context workspace */) {
   int rc = check_atlas(ctx, atlas, who);
   if (rc) return rc;
   GCS_REQUIRE(ctx, m_tile_view > 0, "%s: m_tile_view must be > 0, got %d", who, m_tile_view);
@@ -1645,9 +1644,12 @@ static int map_view_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_atlas* atlas
   if (rc) return rc;
   if (inflate_stats) {   // statistics of the inflation the view applies functionally; the map itself is not modified
     const int blocks = (int)(cdivm(atlas->m_tile, 256) < 64 ? cdivm(atlas->m_tile, 256) : 64);
-    rc = gcs_ws_reserve(ctx, (uint64_t)n_tiles * blocks * 3 * 8);
-    if (rc) return rc;
-    double* part = (double*)ctx->ws;
+    double* part = part_ws;
+    if (!part) {
+      rc = gcs_ws_reserve(ctx, (uint64_t)n_tiles * blocks * 3 * 8);
+      if (rc) return rc;
+      part = (double*)ctx->ws;
+    }
     recency_inflate_kernel<<<dim3(blocks, n_tiles), 256, 0, st>>>(*atlas, T, I.scan_seq, I.lam, I.min_scale, part, 0);
     GCS_LAUNCH_CHECK(ctx);
     sum_parts_kernel<<<1, 32, 0, st>>>(part, n_tiles * blocks, 3, inflate_stats, 4);
@@ -1687,9 +1689,39 @@ int gcs_extract_atlas_map_view_inflated(gcs_ctx* ctx, void* stream, const gcs_at
                          out_n_valid, I, out_inflate_stats, "extract_atlas_map_view_inflated");
 }
 
+// The per-view part of the association (A_vmf of the entries, the grouped view): buffers + launch.  The fused entry runs
+// it on the side stream, in the side workspace, while the scan's surfels are extracted.
+struct ViewPrep {
+  double* vAk; double* gpos; uint16_t* goff; uint8_t* gval; double* gbox;
+};
+static size_t view_prep_bytes(int n_tiles, int m_view) {
+  const size_t P = (size_t)n_tiles * m_view;
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  return up(P * 8) + up(P * 24) + up(P * 2) + up(P) + up(topk_box_bytes(n_tiles, m_view));
+}
+static ViewPrep view_prep_carve(char* base, int n_tiles, int m_view) {
+  const size_t P = (size_t)n_tiles * m_view;
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  ViewPrep p;
+  p.vAk = (double*)base; base += up(P * 8);
+  p.gpos = (double*)base; base += up(P * 24);
+  p.goff = (uint16_t*)base; base += up(P * 2);
+  p.gval = (uint8_t*)base; base += up(P);
+  p.gbox = (double*)base;
+  return p;
+}
+static int view_prep_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_map_view* view, int n_tiles, int m_view, const ViewPrep& p) {
+  AssocWs W;
+  memset(&W, 0, sizeof(W));
+  W.vAk = p.vAk; W.gpos = p.gpos; W.goff = p.goff; W.gval = p.gval; W.gbox = p.gbox;
+  assoc_view_groups_kernel<<<n_tiles, 1024, 0, st>>>(*view, m_view, W);
+  GCS_LAUNCH_CHECK(ctx);
+  return GCS_OK;
+}
+
 static int assoc_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_meas_batch* batch, int n_units, const gcs_map_view* view,
                         const int64_t* view_tile_ids, int32_t n_tiles, int32_t m_tile_view, const gcs_assoc_cfg* cfg,
-                        const gcs_assoc_result* out, double* cert, const char* who) {
+                        const gcs_assoc_result* out, double* cert, const char* who, const ViewPrep* pre = nullptr) {
   int rc = check_mbatch(ctx, batch, who);
   if (rc) return rc;
   rc = check_view(ctx, view, who);
@@ -1722,25 +1754,25 @@ static int assoc_launch(gcs_ctx* ctx, cudaStream_t st, const gcs_meas_batch* bat
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_pos = take(H * N * 3 * 8), o_dir = take(H * N * 3 * 8), o_kap = take(H * N * 8),
                o_st = take(H * N * n_st), o_brow = take(H * N * (size_t)cfg->k_assoc * 8),
-               o_vak = take((size_t)n_tiles * m_tile_view * 8), o_ctr = take(256), o_aws = take(H * N * 8),
-               o_gpos = take((size_t)n_tiles * m_tile_view * 24), o_goff = take((size_t)n_tiles * m_tile_view * 2),
-               o_gval = take((size_t)n_tiles * m_tile_view), o_gbox = take(topk_box_bytes(n_tiles, m_tile_view));
+               o_ctr = take(256), o_aws = take(H * N * 8), o_prep = take(pre ? 0 : view_prep_bytes(n_tiles, m_tile_view));
   rc = gcs_ws_reserve(ctx, off);
   if (rc) return rc;
   char* ws = (char*)ctx->ws;
   AssocWs W;
   W.mpos = (double*)(ws + o_pos); W.mdir = (double*)(ws + o_dir); W.mkap = (double*)(ws + o_kap); W.stencil = (int8_t*)(ws + o_st);
-  W.vAk = (double*)(ws + o_vak);
-  W.gpos = (double*)(ws + o_gpos); W.goff = (uint16_t*)(ws + o_goff); W.gval = (uint8_t*)(ws + o_gval); W.gbox = (double*)(ws + o_gbox);
   GCS_REQUIRE(ctx, m_tile_view <= 65535, "%s: m_tile_view=%d exceeds the 16-bit offsets of the grouped view", who, m_tile_view);
+  const ViewPrep vp = pre ? *pre : view_prep_carve(ws + o_prep, n_tiles, m_tile_view);
+  W.vAk = vp.vAk; W.gpos = vp.gpos; W.goff = vp.goff; W.gval = vp.gval; W.gbox = vp.gbox;
   const int n_pool = n_tiles * m_tile_view, row_blocks = (N + 127) / 128;
   const unsigned Hu = (unsigned)n_units;
-  assoc_prepare_kernel<<<dim3(row_blocks + (n_pool + 127) / 128, Hu), 128, 0, st>>>(*batch, N, T, *cfg, n_st, SO, W, *view, n_pool,
-                                                                                   row_blocks);
+  assoc_prepare_kernel<<<dim3(row_blocks, Hu), 128, 0, st>>>(*batch, N, T, *cfg, n_st, SO, W, *view, n_pool, row_blocks);
   GCS_LAUNCH_CHECK(ctx);
-  // the view in group order (once per view: shared by every unit and every row)
-  assoc_view_groups_kernel<<<n_tiles, 1024, 0, st>>>(*view, m_tile_view, W);
-  GCS_LAUNCH_CHECK(ctx);
+  // the view in group order + A_vmf of its entries (once per view: shared by every unit and every row), unless the
+  // caller has prepared them already
+  if (!pre) {
+    rc = view_prep_launch(ctx, st, view, n_tiles, m_tile_view, vp);
+    if (rc) return rc;
+  }
   // top-K: persistent CTAs pulling rows from a counter; view tiles staged once per CTA by TMA when the box fits
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
@@ -1845,8 +1877,30 @@ int gcs_lidar_evidence_primitives_batched(gcs_ctx* ctx, void* stream, const gcs_
   GCS_REQUIRE(ctx, a && a->atlas && a->n_units >= 1 && a->n >= 1 && a->n_tiles >= 1 && a->n_tiles <= 16,
               "lidar_evidence_primitives_batched: bad args");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = gcs_deskew_constant_twist_batched(ctx, stream, a->pts, a->t, a->w, a->n, a->xi, a->n_units, a->scan_start_time,
-                                             a->scan_end_time, a->dk_pts, a->dk_w, a->dk_cert);
+  // Fork: the map side of the path (inflation statistics, view selection + gather, grouped view) does not depend on the
+  // scan; it runs on the context's side stream, with scratch of its own, while the scan is deskewed and its surfels are
+  // extracted, and joins the caller's stream in front of the association.  The view kernels occupy one CTA per tile.
+  const int infl_blocks = (int)(cdivm(a->atlas->m_tile, 256) < 64 ? cdivm(a->atlas->m_tile, 256) : 64);
+  const size_t part_bytes = (((size_t)a->n_tiles * infl_blocks * 3 * 8) + 255) & ~(size_t)255;
+  int rc = gcs_side_reserve(ctx, part_bytes + view_prep_bytes(a->n_tiles, a->m_tile_view));
+  if (rc) return rc;
+  cudaStream_t side = ctx->side_stream;
+  GCS_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+  GCS_CHECK_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_fork, 0));
+  {
+    InflateArg I = {a->inflate ? 1 : 0, (long long)a->assoc_cfg.scan_seq, a->inflate ? a->assoc_cfg.recency_decay_lambda : 0.0,
+                    a->inflate ? a->recency_min_scale : 1.0};
+    rc = map_view_launch(ctx, side, a->atlas, a->tile_index, a->tile_ids, a->n_tiles, a->m_tile_view, a->eps_lift, a->eps_mass,
+                         &a->view, a->view_n_valid, I, a->inflate ? a->inflate_stats : nullptr, "lidar_evidence_primitives_batched",
+                         (double*)ctx->ws_side);
+    if (rc) return rc;
+  }
+  const ViewPrep vp = view_prep_carve((char*)ctx->ws_side + part_bytes, a->n_tiles, a->m_tile_view);
+  rc = view_prep_launch(ctx, side, &a->view, a->n_tiles, a->m_tile_view, vp);
+  if (rc) return rc;
+  GCS_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_join, side));
+  rc = gcs_deskew_constant_twist_batched(ctx, stream, a->pts, a->t, a->w, a->n, a->xi, a->n_units, a->scan_start_time,
+                                         a->scan_end_time, a->dk_pts, a->dk_w, a->dk_cert);
   if (rc) return rc;
   if (a->base.Lambdas) {
     rc = check_mbatch(ctx, &a->base, "lidar_evidence_primitives_batched");
@@ -1862,16 +1916,10 @@ int gcs_lidar_evidence_primitives_batched(gcs_ctx* ctx, void* stream, const gcs_
   rc = gcs_extract_lidar_surfels_batched(ctx, stream, a->dk_pts, a->t, a->dk_w, a->n, a->n_units, 1, &a->surfel_cfg, &a->batch,
                                          a->n_lidar_valid);
   if (rc) return rc;
-  if (a->inflate)
-    rc = gcs_extract_atlas_map_view_inflated(ctx, stream, a->atlas, a->tile_index, a->tile_ids, a->n_tiles, a->m_tile_view,
-                                             a->eps_lift, a->eps_mass, a->assoc_cfg.scan_seq, a->assoc_cfg.recency_decay_lambda,
-                                             a->recency_min_scale, &a->view, a->view_n_valid, a->inflate_stats);
-  else
-    rc = gcs_extract_atlas_map_view(ctx, stream, a->atlas, a->tile_index, a->tile_ids, a->n_tiles, a->m_tile_view, a->eps_lift,
-                                    a->eps_mass, &a->view, a->view_n_valid);
-  if (rc) return rc;
-  rc = gcs_associate_primitives_ot_batched(ctx, stream, &a->batch, a->n_units, &a->view, a->tile_ids, a->n_tiles, a->m_tile_view,
-                                           &a->assoc_cfg, &a->assoc, a->ot_cert);
+  // join: the view and its grouped form are complete
+  GCS_CHECK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+  rc = assoc_launch(ctx, st, &a->batch, a->n_units, &a->view, a->tile_ids, a->n_tiles, a->m_tile_view, &a->assoc_cfg, &a->assoc,
+                    a->ot_cert, "lidar_evidence_primitives_batched", &vp);
   if (rc) return rc;
   return gcs_visual_pose_evidence_batched(ctx, stream, &a->batch, a->n_units, &a->view, &a->assoc, a->assoc_cfg.k_assoc, a->poses,
                                           a->eps_lift, a->eps_mass, a->L22, a->h22, a->rec, a->n_lidar_valid, a->n_camera_valid,
