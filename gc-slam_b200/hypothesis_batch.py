@@ -278,6 +278,31 @@ _C_BATCH_NAME = dict(valid_mask="valid")
 _C_VIEW_NAME = dict(valid_mask="valid")
 
 
+_PTR_SLOTS: Dict[tuple, tuple] = {}
+
+
+def _arena_pointer_slots(key, spec):
+    """(word indices into CPrimBatchArgs, arena offsets) of every struct field that points into the arena; per layout."""
+    hit = _PTR_SLOTS.get(key)
+    if hit is not None:
+        return hit
+    T = CPrimBatchArgs
+    pairs = [(T.dk_pts.offset, "dk_pts"), (T.dk_w.offset, "dk_w"), (T.dk_cert.offset, "dk_cert"), (T.n_lidar_valid.offset, "n_valid"),
+             (T.view_n_valid.offset, "view_n_valid"), (T.inflate_stats.offset, "inflate_stats"), (T.ot_cert.offset, "ot_cert"),
+             (T.L22.offset, "L22"), (T.h22.offset, "h22"), (T.rec.offset, "rec")]
+    for f, _, _ in _BATCH_FIELDS:
+        pairs.append((T.batch.offset + getattr(CMeasBatch, _C_BATCH_NAME.get(f, f)).offset, "b_" + f))
+    for f, _, _ in _VIEW_FIELDS:
+        pairs.append((T.view.offset + getattr(CMapView, _C_VIEW_NAME.get(f, f)).offset, "v_" + f))
+    for f, _, _ in _ASSOC_FIELDS:
+        pairs.append((T.assoc.offset + getattr(CAssocResult, f).offset, "a_" + f))
+    assert all(o % 8 == 0 for o, _ in pairs)
+    words = np.array([o // 8 for o, _ in pairs], dtype=np.int64)
+    offs = np.array([spec[name][0] for _, name in pairs], dtype=np.uint64)
+    _PTR_SLOTS[key] = (words, offs)
+    return words, offs
+
+
 def _run_group(io, units, tile_ids, pts, t, w, n, xi_d, poses_d, t0, t1, atlas_map, scan_seq, base_batch, scfg, acfg, m_tile_view,
                eps_lift, eps_mass, min_scale, inflate=True) -> HypothesisGroup:
     U = len(units)
@@ -314,16 +339,15 @@ def _run_group(io, units, tile_ids, pts, t, w, n, xi_d, poses_d, t0, t1, atlas_m
     A.alloc()
     A.buf[:n_scalar_bytes].zero_()
     a = CPrimBatchArgs()
+    # every pointer into the arena in one vectorised store: (8-byte word of the struct) <- arena base + offset
+    words, offs = _arena_pointer_slots(key, spec)
+    np.frombuffer(a, dtype=np.uint64)[words] = offs + np.uint64(A.base)
     a.pts, a.t, a.w, a.n, a.n_units, a.inflate = L.ptr(pts), L.ptr(t), L.ptr(w), n, U, 1 if inflate else 0
     a.xi, a.poses = L.ptr(xi_g.contiguous()), L.ptr(po_g.contiguous())
     a.scan_start_time, a.scan_end_time = float(t0), float(t1)
-    a.dk_pts, a.dk_w, a.dk_cert = A.ptr("dk_pts"), A.ptr("dk_w"), A.ptr("dk_cert")
     a.surfel_cfg = scfg._c()
     a.base = base_batch._c()
-    for f, _, _ in _BATCH_FIELDS:
-        setattr(a.batch, _C_BATCH_NAME.get(f, f), A.ptr("b_" + f))
     a.batch.n_feat, a.batch.n_surfel = scfg.n_feat, scfg.n_surfel
-    a.n_lidar_valid = A.ptr("n_valid")
     a.n_camera_valid = int(base_batch.n_camera_valid)
     ca = atlas_map._c()
     a.atlas = C.pointer(ca)
@@ -332,13 +356,7 @@ def _run_group(io, units, tile_ids, pts, t, w, n, xi_d, poses_d, t0, t1, atlas_m
         a.tile_index[k], a.tile_ids[k] = int(idx[k]), int(tile_ids[k])
     a.n_tiles, a.m_tile_view = len(tile_ids), int(m_tile_view)
     a.eps_lift, a.eps_mass, a.recency_min_scale = float(eps_lift), float(eps_mass), float(min_scale)
-    for f, _, _ in _VIEW_FIELDS:
-        setattr(a.view, _C_VIEW_NAME.get(f, f), A.ptr("v_" + f))
-    a.view_n_valid, a.inflate_stats = A.ptr("view_n_valid"), A.ptr("inflate_stats")
     a.assoc_cfg = PR._c_assoc_cfg(acfg, eps_lift)
-    for f, _, _ in _ASSOC_FIELDS:
-        setattr(a.assoc, f, A.ptr("a_" + f))
-    a.ot_cert, a.L22, a.h22, a.rec = A.ptr("ot_cert"), A.ptr("L22"), A.ptr("h22"), A.ptr("rec")
     io.ctx.check(io.ctx.lib.gcs_lidar_evidence_primitives_batched(io.ctx.handle, io.stream(), C.byref(a)))
     del xi_g, po_g
     return HypothesisGroup(units, tile_ids, A, n_scalar_bytes, scfg, base_batch.n_camera_valid, m_tile_view)
@@ -476,9 +494,10 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
         io_u, stats_u, _ = next(gens["update"])
         rest = rest[1:]
     by_stencil: Dict[tuple, List[int]] = {}
-    for hh in rest:
-        tl = tuple(PR.ma_hex_stencil_tile_ids(poses_h[hh, :3], acfg.h_tile, acfg.r_stencil_tiles_xy, acfg.r_stencil_tiles_z))
-        by_stencil.setdefault(tl, []).append(hh)
+    if rest:
+        cells = PR.ma_hex_cells_3d_from_xyz_batch(poses_h[rest, :3], acfg.h_tile)
+        for hh, cell in zip(rest, cells):
+            by_stencil.setdefault(PR.stencil_of_cell(cell, acfg.r_stencil_tiles_xy, acfg.r_stencil_tiles_z), []).append(hh)
     groups += [run(units, tl) for tl, units in by_stencil.items()]
     cfg = dict(dev=io.dev, chart_id=chart_id, anchor_id=anchor_id, ess_imu=ess_imu, surfel=scfg, assoc=acfg, eps_lift=eps_lift,
                atlas=atlas_map, timestamps=t)

@@ -140,14 +140,32 @@ def tile_id_from_cell_3d(c1: int, c2: int, cz: int) -> int:
     return int((((int(c1) + _BIAS) & m) << (2 * _BITS)) | (((int(c2) + _BIAS) & m) << _BITS) | ((int(cz) + _BIAS) & m))
 
 
+_HEX_E1 = np.array([1.0, 0.0])
+_HEX_E2 = np.array([0.5, 0.5 * np.sqrt(3.0)])
+
+
 def ma_hex_cell_3d_from_xyz(xyz, h_tile: float):
     xyz = np.asarray(xyz, dtype=np.float64).ravel()
     if xyz.shape[0] < 3:
         raise ValueError(f"ma_hex_cell_3d_from_xyz: expected xyz (3,), got shape {xyz.shape}")
     h = max(float(h_tile), 1e-12)
-    s1 = float(np.array([1.0, 0.0]) @ xyz[:2])
-    s2 = float(np.array([0.5, 0.5 * np.sqrt(3.0)]) @ xyz[:2])
+    s1 = float(_HEX_E1 @ xyz[:2])
+    s2 = float(_HEX_E2 @ xyz[:2])
     return int(np.floor(s1 / h)), int(np.floor(s2 / h)), int(np.floor(float(xyz[2]) / h))
+
+
+def ma_hex_cells_3d_from_xyz_batch(xyz, h_tile: float):
+    """Cells of many centres at once: vectorised, except for centres within 1e-9 cells of a boundary, which take the
+    scalar function (so that the decision is the scalar one's bit for bit where rounding could matter)."""
+    xyz = np.asarray(xyz, dtype=np.float64).reshape(-1, 3)
+    h = max(float(h_tile), 1e-12)
+    f = np.stack([xyz[:, 0], xyz[:, :2] @ _HEX_E2, xyz[:, 2]], axis=1) / h
+    cells = np.floor(f).astype(np.int64)
+    near = np.any(np.abs(f - np.rint(f)) < 1e-9, axis=1) | ~np.all(np.isfinite(f), axis=1)
+    out = list(map(tuple, cells.tolist()))
+    for k in np.nonzero(near)[0]:
+        out[int(k)] = ma_hex_cell_3d_from_xyz(xyz[int(k)], h_tile)
+    return out
 
 
 def hex_disk_axial(radius: int):
@@ -159,9 +177,25 @@ def hex_disk_axial(radius: int):
 
 def ma_hex_stencil_tile_ids(center_xyz, h_tile: float = constants.GC_H_TILE, radius_xy: int = constants.GC_R_STENCIL_TILES_XY,
                             radius_z: int = constants.GC_R_STENCIL_TILES_Z) -> List[int]:
-    c1, c2, cz = ma_hex_cell_3d_from_xyz(center_xyz, h_tile)
-    return [tile_id_from_cell_3d(c1 + dq, c2 + dr, cz + dz) for dz in range(-int(radius_z), int(radius_z) + 1)
-            for dq, dr in hex_disk_axial(radius_xy)]
+    return list(stencil_of_cell(ma_hex_cell_3d_from_xyz(center_xyz, h_tile), radius_xy, radius_z))
+
+
+_STENCIL_CACHE: dict = {}
+
+
+def stencil_of_cell(cell, radius_xy: int = constants.GC_R_STENCIL_TILES_XY, radius_z: int = constants.GC_R_STENCIL_TILES_Z) -> tuple:
+    """Stencil tile ids around a cell (c1, c2, cz), in the reference's order (tiling.py:171-186); memoised (a robot stays in
+    a cell for many scans, and the hypotheses of a scan share one or two cells)."""
+    key = (int(cell[0]), int(cell[1]), int(cell[2]), int(radius_xy), int(radius_z))
+    out = _STENCIL_CACHE.get(key)
+    if out is None:
+        c1, c2, cz = key[:3]
+        out = tuple(tile_id_from_cell_3d(c1 + dq, c2 + dr, cz + dz) for dz in range(-int(radius_z), int(radius_z) + 1)
+                    for dq, dr in hex_disk_axial(radius_xy))
+        if len(_STENCIL_CACHE) > 4096:
+            _STENCIL_CACHE.clear()
+        _STENCIL_CACHE[key] = out
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -781,7 +815,8 @@ def _map_update_step12b_gen(atlas_map, measurement_batch, association_result, ac
     result = MapUpdateResult(atlas_map=atlas_map, n_fused=int(s[MU["FUSED_COUNT"]]), n_inserted=n_ins, n_culled=n_cull,
                              new_ids=new_ids, insert_slots=slots,
                              tile_counts=[int(s[MU["TILE_COUNT0"] + a]) for a in range(min(nt, 16))])
-    inactive = [int(t) for t in atlas_map.tile_ids if int(t) not in set(int(x) for x in active_tile_ids)]
+    active_set = set(int(x) for x in active_tile_ids)
+    inactive = [int(t) for t in atlas_map.tile_ids if int(t) not in active_set]
     mu = MapUpdateCert(
         n_active_tiles=nt, tile_ids_active=[int(t) for t in active_tile_ids], n_inactive_tiles=len(inactive),
         tile_ids_inactive=inactive, tile_cache_hits=nt, tile_cache_misses=0,
