@@ -410,8 +410,9 @@ def config3_block(n_points, peak, peak_src, n_map=1_000_000, with_cpu=True):
                      "kernel_ms_avg": h64["topk_kernel_ms"], "kernel_algorithmic_bytes_per_launch": int(topk_bytes),
                      "kernel_achieved_GBps": topk_bytes / (h64["topk_kernel_ms"] * 1e-3) / 1e9,
                      "kernel_share_of_step": h64["topk_share_evidence_only"],
-                     "note": "the dominant kernel is latency / float64-issue bound (exact (cost, j) pruning of 7,168 candidates per "
-                             "row), not HBM bound: its HBM fraction is reported for completeness"},
+                     "note": "the dominant kernel is latency bound (per row: 32 bounding-box tests per view tile, the nearest groups' "
+                             "exact (cost, j) pruning, float64 exact costs of the survivors), not HBM bound: its HBM fraction is "
+                             "reported for completeness"},
         "n_lidar_surfels": n_surf, "n_inserted_last": int(res.n_inserted), "map_build_s": t_build,
     }
     if with_cpu:
