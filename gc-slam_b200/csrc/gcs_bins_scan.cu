@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(256) deskew_kernel(const double* __restrict__ 
                                                      double xi2, double xi3, double xi4, double xi5,
                                                      const double* __restrict__ xi_dev, double t0, double t1,
                                                      double* __restrict__ o_pts, double* __restrict__ o_w,
-                                                     double* __restrict__ partial) {
+                                                     double* __restrict__ partial, int n_vblocks, int vb_per_block) {
   __shared__ double sred[8];
   const int u = blockIdx.y;
   double xi[6] = {xi0, xi1, xi2, xi3, xi4, xi5};
@@ -484,26 +484,32 @@ __global__ void __launch_bounds__(256) deskew_kernel(const double* __restrict__ 
   }
   o_pts += (int64_t)u * 3 * n;
   o_w += (int64_t)u * n;
-  partial += (int64_t)u * gridDim.x * 2;
+  partial += (int64_t)u * n_vblocks * 2;
   const double inv_denom = 1.0 / fmax(t1 - t0, 1e-12);
   // per-twist invariants hoisted (TwistCtx: ~60 instead of ~105 float64 operations per point, no sqrt / sincos for
   // |theta| < 0.5) and the window weight with one exponential and no division: the forms the fused bin kernels use
   const TwistCtx tw = make_twist_ctx(xi);
   const WindowCtx win = make_window_ctx(t0, t1);
-  double s_out = 0.0, s_in = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double p[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
-    double tt = t[i], ww = w[i];
-    double p0[3];
-    deskew_point_ctx(p, (tt - t0) * inv_denom, tw, p0);
-    double wo = ww * window_weight_ctx(tt, win);
-    o_pts[3 * i] = p0[0]; o_pts[3 * i + 1] = p0[1]; o_pts[3 * i + 2] = p0[2];
-    o_w[i] = wo;
-    s_out += wo; s_in += ww;
+  // The certificate sums are taken per VIRTUAL block of 256 threads striding over the points (n_vblocks of them, whatever
+  // the grid): a CTA works through vb_per_block consecutive virtual blocks, so that a batch of many units can run few CTAs
+  // per unit -- the per-thread invariants above cost five points' worth of arithmetic -- and still produce the partial
+  // sums, and hence the certificates, of the single-unit launch bit for bit.
+  for (int vb = blockIdx.x * vb_per_block; vb < n_vblocks && vb < (blockIdx.x + 1) * vb_per_block; ++vb) {
+    double s_out = 0.0, s_in = 0.0;
+    for (int64_t i = (int64_t)vb * blockDim.x + threadIdx.x; i < n; i += (int64_t)n_vblocks * blockDim.x) {
+      double p[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+      double tt = t[i], ww = w[i];
+      double p0[3];
+      deskew_point_ctx(p, (tt - t0) * inv_denom, tw, p0);
+      double wo = ww * window_weight_ctx(tt, win);
+      o_pts[3 * i] = p0[0]; o_pts[3 * i + 1] = p0[1]; o_pts[3 * i + 2] = p0[2];
+      o_w[i] = wo;
+      s_out += wo; s_in += ww;
+    }
+    double a = block_sum_fixed(s_out, sred);
+    double b = block_sum_fixed(s_in, sred);
+    if (threadIdx.x == 0) { partial[2 * vb] = a; partial[2 * vb + 1] = b; }
   }
-  double a = block_sum_fixed(s_out, sred);
-  double b = block_sum_fixed(s_in, sred);
-  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = a; partial[2 * blockIdx.x + 1] = b; }
 }
 // blockIdx.x = unit: out[u * out_stride + k] = sum over the unit's parts, in part order
 __global__ void sum_pairs_kernel(const double* __restrict__ partial, int n_parts, int width, double* __restrict__ out,
@@ -969,8 +975,17 @@ static int deskew_launch(gcs_ctx* ctx, cudaStream_t st, const double* pts, const
   double* part = (double*)ctx->ws;
   const double z6[6] = {0, 0, 0, 0, 0, 0};
   const double* xi = xi_host ? xi_host : z6;
-  deskew_kernel<<<dim3(blocks, n_units), 256, 0, st>>>(pts, t, w, n, xi[0], xi[1], xi[2], xi[3], xi[4], xi[5], xi_dev, t0, t1,
-                                                       out_pts, out_w, part);
+  // virtual blocks per CTA: one for a single unit (latency), more when the batch fills the device anyway
+  int vbp = 1;
+  if (n_units > 1) {
+    const int64_t want_ctas = (int64_t)ctx->sm_count * 8;
+    vbp = (int)(((int64_t)blocks * n_units + want_ctas - 1) / want_ctas);
+    if (vbp < 1) vbp = 1;
+    if (vbp > 16) vbp = 16;
+  }
+  const int ctas = (blocks + vbp - 1) / vbp;
+  deskew_kernel<<<dim3(ctas, n_units), 256, 0, st>>>(pts, t, w, n, xi[0], xi[1], xi[2], xi[3], xi[4], xi[5], xi_dev, t0, t1,
+                                                     out_pts, out_w, part, blocks, vbp);
   GCS_LAUNCH_CHECK(ctx);
   sum_pairs_kernel<<<n_units, 32, 0, st>>>(part, blocks, 2, cert, GCS_DK_NCERT);
   GCS_LAUNCH_CHECK(ctx);

@@ -549,9 +549,13 @@ static int surfels_launch(gcs_ctx* ctx, cudaStream_t st, const double* pts, cons
   surfel_rank_scan_kernel<<<dim3((n_keys + 255) / 256, Hu), 256, 0, st>>>(hist, n_chunks, n_keys, total, G.min_points, occ_list, n_occ,
                                                                            F.valid);
   GCS_LAUNCH_CHECK(ctx);
-  const int64_t nb = (int64_t)G.n_cells * G.max_occ * n_units;
-  surfel_bucket_init_kernel<<<(unsigned)cdiv(nb, 256), 256, 0, st>>>(bucket, nb);
-  GCS_LAUNCH_CHECK(ctx);
+  // the -1 fill of unused bucket slots only matters to a caller that receives the bucket (the reference's BucketResult);
+  // the plane fit reads the first min(count, max_occ) slots of a cell, all of which bucket_fill writes
+  if (out_bucket) {
+    const int64_t nb = (int64_t)G.n_cells * G.max_occ * n_units;
+    surfel_bucket_init_kernel<<<(unsigned)cdiv(nb, 256), 256, 0, st>>>(bucket, nb);
+    GCS_LAUNCH_CHECK(ctx);
+  }
   surfel_bucket_fill_kernel<<<dim3((unsigned)cdiv(n, kSurfThreads), Hu), kSurfThreads, 0, st>>>(key, lrank, hist, n, per_chunk, n_keys, G,
                                                                                             bucket, n_chunks);
   GCS_LAUNCH_CHECK(ctx);
