@@ -511,15 +511,18 @@ __global__ void __launch_bounds__(256) deskew_kernel(const double* __restrict__ 
     if (threadIdx.x == 0) { partial[2 * vb] = a; partial[2 * vb + 1] = b; }
   }
 }
-// blockIdx.x = unit: out[u * out_stride + k] = sum over the unit's parts, in part order
+// blockIdx.x = unit: out[u * out_stride + k] = sum over the unit's parts.  One warp per column k (blockDim = 32 * width):
+// lane l adds parts l, l + 32, ... in order, then the fixed shuffle tree -- 8 + 5 dependent additions for 256 parts instead of
+// 256 (this kernel sat between the deskew and the surfel kernels of every scan with two busy threads)
 __global__ void sum_pairs_kernel(const double* __restrict__ partial, int n_parts, int width, double* __restrict__ out,
                                  int out_stride) {
-  int k = threadIdx.x;
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (k >= width) return;
   partial += (int64_t)blockIdx.x * n_parts * width;
   double a = 0.0;
-  for (int c = 0; c < n_parts; ++c) a += partial[(int64_t)c * width + k];
-  out[(int64_t)blockIdx.x * out_stride + k] = a;
+  for (int c = lane; c < n_parts; c += 32) a += partial[(int64_t)c * width + k];
+  a = warp_sum(a);
+  if (lane == 0) out[(int64_t)blockIdx.x * out_stride + k] = a;
 }
 __global__ void __launch_bounds__(256) ray_dirs_kernel(const double* __restrict__ pts, int64_t n, double o0, double o1,
                                                        double o2, double eps, double* __restrict__ out) {
@@ -987,7 +990,7 @@ static int deskew_launch(gcs_ctx* ctx, cudaStream_t st, const double* pts, const
   deskew_kernel<<<dim3(ctas, n_units), 256, 0, st>>>(pts, t, w, n, xi[0], xi[1], xi[2], xi[3], xi[4], xi[5], xi_dev, t0, t1,
                                                      out_pts, out_w, part, blocks, vbp);
   GCS_LAUNCH_CHECK(ctx);
-  sum_pairs_kernel<<<n_units, 32, 0, st>>>(part, blocks, 2, cert, GCS_DK_NCERT);
+  sum_pairs_kernel<<<n_units, 64, 0, st>>>(part, blocks, 2, cert, GCS_DK_NCERT);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
 }
