@@ -946,6 +946,9 @@ def run_ours(args):
                                 "achieved": b64 / (k64_ms / max(k64_n, 1) * 1e-3) / 1e9, "unit": "GB/s",
                                 "frac": b64 / (k64_ms / max(k64_n, 1) * 1e-3) / 1e9 / measured_peaks()[0],
                                 "algorithmic_bytes_per_launch": int(b64)},
+                   "bound_note": "this leg is bound by the FP64 pipe, not by HBM: ncu sm__pipe_fp64_cycles_active 51 % of peak, issue "
+                                 "slots 63 % (profiles/r01_bin_scan_full.txt; ~3.4 k float64 flops per point: 48 exponentials + a "
+                                 "48 x 19 moment contraction); its HBM fraction is reported because that is the metric's roofline",
                    "ms_per_step": ms64, "scans_per_s": S / (ms64 * 1e-3),
                    "max_rel_diff_vs_headline_precision": {k: _rel(otc.stats[k], o64.stats[k]) for k in ("N", "S_scatter", "Sigma_p", "kappa")
                                                           if k in o64.stats},
