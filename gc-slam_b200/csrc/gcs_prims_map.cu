@@ -966,7 +966,13 @@ __global__ void __launch_bounds__(128) batch_replicate_kernel(gcs_meas_batch S, 
 // =================================================================================================
 // 512 threads: three rows per thread at the reference budget (1,536 rows) and 128 registers each -- the 1024-thread
 // version was capped at 64 registers and spilled the 28 accumulators
-constexpr int kPeThreads = 384;   // four rows per thread at the reference budget, 170 registers: no spills
+constexpr int kPeThreads = 384;   // 170 registers: no spills
+// kPeParts CTAs per unit (blockIdx.x = part, blockIdx.y = unit): the rows of a unit are dealt round-robin to the parts, every
+// part leaves its 25 sums in `partial`, and the part that arrives last (a counter per unit, reset for the next launch) adds
+// them in part order and finishes.  One CTA per unit spent 44 us in dependent gathers of the K candidates of four rows per
+// thread -- a tenth of a single hypothesis' path.  The part count is a constant, so a batch and a single scan add in the
+// same order.
+constexpr int kPeParts = 4;
 template <int K>
 __global__ void __launch_bounds__(kPeThreads) pose_evidence_kernel(gcs_meas_batch B, int N, gcs_map_view V, gcs_assoc_result R,
                                                              double p0, double p1, double p2, double r0, double r1,
@@ -974,11 +980,16 @@ __global__ void __launch_bounds__(kPeThreads) pose_evidence_kernel(gcs_meas_batc
                                                              double* __restrict__ L22, double* __restrict__ h22,
                                                              double* __restrict__ rec, const double* __restrict__ poses_dev,
                                                              const int32_t* __restrict__ n_lidar_valid, int n_camera_valid,
-                                                             const int32_t* __restrict__ view_n_valid) {
+                                                             const int32_t* __restrict__ view_n_valid,
+                                                             double* __restrict__ partial, int* __restrict__ arrived) {
   __shared__ double tot[28];
+  __shared__ int s_last;
   const int tid = threadIdx.x;
-  if (poses_dev) {                           // blockIdx.x = unit: its own pose, batch, association and outputs
-    const int64_t u = blockIdx.x;
+  const int part = blockIdx.x;
+  partial += (int64_t)blockIdx.y * kPeParts * 25;
+  arrived += blockIdx.y;
+  if (poses_dev) {                           // blockIdx.y = unit: its own pose, batch, association and outputs
+    const int64_t u = blockIdx.y;
     p0 = poses_dev[6 * u]; p1 = poses_dev[6 * u + 1]; p2 = poses_dev[6 * u + 2];
     r0 = poses_dev[6 * u + 3]; r1 = poses_dev[6 * u + 4]; r2 = poses_dev[6 * u + 5];
     B = meas_batch_unit(B, u);
@@ -989,6 +1000,7 @@ __global__ void __launch_bounds__(kPeThreads) pose_evidence_kernel(gcs_meas_batc
     // primitive_association.py:275-290 and the evidence eps_lift * I, h = 0 of visual_pose_evidence.py:300-330 -- whatever
     // the association kernels computed from 1e12 costs is overwritten, so the map update of this unit fuses nothing.
     if (n_lidar_valid && view_n_valid && (view_n_valid[0] == 0 || n_camera_valid + n_lidar_valid[u] == 0)) {
+      if (part != 0) return;
       for (int e = tid; e < N * K; e += kPeThreads) {
         R.responsibilities[e] = 0.0; R.cost_matrix[e] = 0.0; R.candidate_pool_indices[e] = 0;
         R.candidate_tile_ids[e] = 0; R.candidate_slots[e] = 0;
@@ -1006,7 +1018,7 @@ __global__ void __launch_bounds__(kPeThreads) pose_evidence_kernel(gcs_meas_batc
 #pragma unroll
   for (int k = 0; k < 28; ++k) acc[k] = 0.0;
   // 0..8 L_t, 9..11 h_t, 12 trans cost, 13..21 S, 22 rot cost, 23 sum row mass, 24 n valid rows
-  for (int i = tid; i < N; i += kPeThreads) {
+  for (int i = part * kPeThreads + tid; i < N; i += kPeParts * kPeThreads) {
     if (!B.valid[i]) continue;
     double mu[3], dir[3], kap;
     meas_row_moments(B, i, eps_lift, eps_mass, mu, dir, &kap);
@@ -1053,6 +1065,22 @@ __global__ void __launch_bounds__(kPeThreads) pose_evidence_kernel(gcs_meas_batc
   if (tid < 25) {
     double s = 0.0;
     for (int w = 0; w < kPeThreads / 32; ++w) s += swarp[tid][w];
+    partial[part * 25 + tid] = s;
+  }
+  // last part to arrive finishes (threadfence / atomic hand-over: its reads see every part's sums)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int prev = atomicAdd(arrived, 1);
+    s_last = prev == kPeParts - 1;
+    if (s_last) *arrived = 0;          // ready for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < 25) {
+    double s = 0.0;
+    for (int q = 0; q < kPeParts; ++q) s += __ldcg(partial + q * 25 + tid);
     tot[tid] = s;
   }
   __syncthreads();
@@ -1827,6 +1855,22 @@ int gcs_associate_primitives_ot_batched(gcs_ctx* ctx, void* stream, const gcs_me
                       "associate_primitives_ot_batched");
 }
 
+}  // extern "C"
+
+// per-unit partial sums + arrival counters of pose_evidence_kernel, at the start of the context workspace (whatever an
+// earlier call of this stream left there is dead by the time this one runs)
+static int pose_evidence_scratch(gcs_ctx* ctx, cudaStream_t st, int n_units, double** partial, int** arrived) {
+  const size_t pbytes = (((size_t)n_units * kPeParts * 25 * 8) + 255) & ~(size_t)255;
+  const int rc = gcs_ws_reserve(ctx, pbytes + (size_t)n_units * 4);
+  if (rc) return rc;
+  *partial = (double*)ctx->ws;
+  *arrived = (int*)((char*)ctx->ws + pbytes);
+  GCS_CHECK_CUDA(ctx, cudaMemsetAsync(*arrived, 0, (size_t)n_units * 4, st));
+  return GCS_OK;
+}
+
+extern "C" {
+
 int gcs_visual_pose_evidence(gcs_ctx* ctx, void* stream, const gcs_meas_batch* batch, const gcs_map_view* view,
                              const gcs_assoc_result* assoc, int32_t k_assoc, const double* pose6, double eps_lift,
                              double eps_mass, double* out_L22, double* out_h22, double* out_rec) {
@@ -1841,9 +1885,13 @@ int gcs_visual_pose_evidence(gcs_ctx* ctx, void* stream, const gcs_meas_batch* b
   GCS_REQUIRE(ctx, pose6 && out_L22 && out_h22 && out_rec, "visual_pose_evidence: NULL pointer");
   GCS_REQUIRE(ctx, GCS_K_ASSOC_OK(k_assoc), "visual_pose_evidence: k_assoc=%d (this build instantiates K_ASSOC = 4, 8, 16)", k_assoc);
   const int N = batch->n_feat + batch->n_surfel;
-  GCS_K_ASSOC_DISPATCH(k_assoc, (pose_evidence_kernel<KK><<<1, kPeThreads, 0, (cudaStream_t)stream>>>(
+  double* partial;
+  int* arrived;
+  rc = pose_evidence_scratch(ctx, (cudaStream_t)stream, 1, &partial, &arrived);
+  if (rc) return rc;
+  GCS_K_ASSOC_DISPATCH(k_assoc, (pose_evidence_kernel<KK><<<dim3(kPeParts, 1), kPeThreads, 0, (cudaStream_t)stream>>>(
                                     *batch, N, *view, *assoc, pose6[0], pose6[1], pose6[2], pose6[3], pose6[4], pose6[5], eps_lift,
-                                    eps_mass, out_L22, out_h22, out_rec, nullptr, nullptr, 0, nullptr)));
+                                    eps_mass, out_L22, out_h22, out_rec, nullptr, nullptr, 0, nullptr, partial, arrived)));
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
 }
@@ -1864,9 +1912,14 @@ int gcs_visual_pose_evidence_batched(gcs_ctx* ctx, void* stream, const gcs_meas_
   GCS_REQUIRE(ctx, poses_dev && out_L22 && out_h22 && out_rec && n_units >= 1, "visual_pose_evidence_batched: bad args");
   GCS_REQUIRE(ctx, GCS_K_ASSOC_OK(k_assoc), "visual_pose_evidence_batched: k_assoc=%d (this build instantiates K_ASSOC = 4, 8, 16)", k_assoc);
   const int N = batch->n_feat + batch->n_surfel;
-  GCS_K_ASSOC_DISPATCH(k_assoc, (pose_evidence_kernel<KK><<<(unsigned)n_units, kPeThreads, 0, (cudaStream_t)stream>>>(
+  GCS_REQUIRE(ctx, n_units <= 65535, "visual_pose_evidence_batched: n_units=%d", n_units);
+  double* partial;
+  int* arrived;
+  rc = pose_evidence_scratch(ctx, (cudaStream_t)stream, n_units, &partial, &arrived);
+  if (rc) return rc;
+  GCS_K_ASSOC_DISPATCH(k_assoc, (pose_evidence_kernel<KK><<<dim3(kPeParts, (unsigned)n_units), kPeThreads, 0, (cudaStream_t)stream>>>(
                                     *batch, N, *view, *assoc, 0, 0, 0, 0, 0, 0, eps_lift, eps_mass, out_L22, out_h22, out_rec,
-                                    poses_dev, n_lidar_valid, n_camera_valid, view_n_valid)));
+                                    poses_dev, n_lidar_valid, n_camera_valid, view_n_valid, partial, arrived)));
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
 }
