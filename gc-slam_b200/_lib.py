@@ -88,6 +88,8 @@ PROTOTYPES = {
     "gcs_reserve_workspace": (_int, [_vp, C.c_uint64]),
     "gcs_workspace_freeze": (_int, [_vp, _int]),
     "gcs_workspace_bytes": (C.c_uint64, [_vp]),
+    "gcs_side_route": (_int, [_vp, _int]),
+    "gcs_side_join": (_int, [_vp, _vp]),
     "gcs_device_sm_count": (_int, [_vp]),
     "gcs_kernel_launches": (C.c_uint64, [_vp]),
     "gcs_timing_enable": (_int, [_vp, _int]),
@@ -192,6 +194,14 @@ class Context:
     def freeze_workspace(self, frozen: bool = True):
         """After this, a call that would have to grow the workspace raises instead (steady state never allocates)."""
         self.check(self.lib.gcs_workspace_freeze(self.handle, 1 if frozen else 0))
+
+    def side_route(self, on: bool):
+        """While on, gcs_map_recency_inflate / gcs_map_update run on the context's side stream (include/gcs_b200.h)."""
+        self.check(self.lib.gcs_side_route(self.handle, 1 if on else 0))
+
+    def side_join(self, stream):
+        """`stream` waits for everything enqueued on the context's side stream."""
+        self.check(self.lib.gcs_side_join(self.handle, stream))
 
     @property
     def workspace_bytes(self) -> int:

@@ -31,6 +31,7 @@ struct gcs_ctx {
   cudaEvent_t ev_fork, ev_join;
   void* ws_side;
   uint64_t ws_side_bytes;
+  int route_side;   // gcs_side_route: map maintenance calls (recency inflate in place, map update) run on the side stream
   char err[512];
 };
 
@@ -48,6 +49,9 @@ static inline void gcs_timing_end(gcs_ctx* ctx, cudaStream_t st, int tag) {
 int gcs_set_error(gcs_ctx* ctx, int code, const char* fmt, ...);
 int gcs_ws_reserve(gcs_ctx* ctx, uint64_t bytes);
 int gcs_side_reserve(gcs_ctx* ctx, uint64_t bytes);   // side stream + events (first call) and its workspace (grow-only)
+// Stream and scratch of a map-maintenance call: the caller's stream and the context workspace, or -- while gcs_side_route is
+// on -- the side stream (made to wait for everything enqueued on the caller's stream so far) and the side workspace.
+int gcs_maint_stream(gcs_ctx* ctx, cudaStream_t caller, uint64_t ws_bytes, cudaStream_t* st, char** ws);
 
 #define GCS_CHECK_CUDA(ctx, expr)                                                                 \
   do {                                                                                            \

@@ -84,6 +84,21 @@ int gcs_side_reserve(gcs_ctx* ctx, uint64_t bytes) {
   return GCS_OK;
 }
 
+int gcs_maint_stream(gcs_ctx* ctx, cudaStream_t caller, uint64_t ws_bytes, cudaStream_t* st, char** ws) {
+  if (!ctx->route_side) {
+    const int rc = gcs_ws_reserve(ctx, ws_bytes);
+    if (rc) return rc;
+    *st = caller; *ws = (char*)ctx->ws;
+    return GCS_OK;
+  }
+  const int rc = gcs_side_reserve(ctx, ws_bytes);
+  if (rc) return rc;
+  GCS_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, caller));
+  GCS_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+  *st = ctx->side_stream; *ws = (char*)ctx->ws_side;
+  return GCS_OK;
+}
+
 static void gcs_ws_release_retired(gcs_ctx* ctx) {
   if (ctx->n_retired == 0) return;
   cudaDeviceSynchronize();
@@ -180,6 +195,21 @@ int gcs_reserve_workspace(gcs_ctx* ctx, uint64_t bytes) {
   ctx->ws_frozen = frozen;
   gcs_ws_release_retired(ctx);   // an explicit sizing call is made outside the steady state: safe to synchronise
   return rc;
+}
+
+int gcs_side_route(gcs_ctx* ctx, int on) {
+  if (!ctx) return GCS_EINVAL;
+  ctx->route_side = on ? 1 : 0;
+  return GCS_OK;
+}
+
+int gcs_side_join(gcs_ctx* ctx, void* stream) {
+  if (!ctx) return GCS_EINVAL;
+  if (!ctx->side_stream) return GCS_OK;
+  GCS_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  GCS_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+  GCS_CHECK_CUDA(ctx, cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_join, 0));
+  return GCS_OK;
 }
 
 int gcs_workspace_freeze(gcs_ctx* ctx, int frozen) {

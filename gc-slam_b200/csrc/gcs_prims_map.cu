@@ -1642,11 +1642,12 @@ int gcs_map_recency_inflate(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, 
   rc = make_tile_list(ctx, atlas, tile_index, nullptr, n_tiles, true, &T, "map_recency_inflate");
   if (rc) return rc;
   GCS_REQUIRE(ctx, stats != nullptr, "map_recency_inflate: stats is NULL");
-  cudaStream_t st = (cudaStream_t)stream;
   const int blocks = (int)(cdivm(atlas->m_tile, 256) < 64 ? cdivm(atlas->m_tile, 256) : 64);
-  rc = gcs_ws_reserve(ctx, (uint64_t)n_tiles * blocks * 3 * 8);
+  cudaStream_t st;
+  char* wsb;
+  rc = gcs_maint_stream(ctx, (cudaStream_t)stream, (uint64_t)n_tiles * blocks * 3 * 8, &st, &wsb);
   if (rc) return rc;
-  double* part = (double*)ctx->ws;
+  double* part = (double*)wsb;
   gcs_timing_begin(ctx, st, GCS_TIME_INFLATE);
   recency_inflate_kernel<<<dim3(blocks, n_tiles), 256, 0, st>>>(*atlas, T, scan_seq, lam, min_scale, part, 1);
   gcs_timing_end(ctx, st, GCS_TIME_INFLATE);
@@ -2018,9 +2019,9 @@ int gcs_map_update(gcs_ctx* ctx, void* stream, const gcs_atlas* atlas, const int
                o_is = take((size_t)n_tiles * k_ins * 4), o_ni = take(16 * 4), o_part = take(128 * 8),
                o_fpart = take((size_t)fuse_blocks * 8), o_uq = take((size_t)n_blocks * 4),
                o_mpart = take((size_t)n_tiles * sweep_blocks * 3 * 8);
-  rc = gcs_ws_reserve(ctx, off);
+  char* ws;
+  rc = gcs_maint_stream(ctx, (cudaStream_t)stream, off, &st, &ws);
   if (rc) return rc;
-  char* ws = (char*)ctx->ws;
   UpdWs W;
   W.Lw = (double*)(ws + o_Lw); W.thw = (double*)(ws + o_thw); W.etw = (double*)(ws + o_etw); W.mtile = (long long*)(ws + o_mt);
   W.novelty = (double*)(ws + o_nov); W.score = (double*)(ws + o_sc); W.pkeys = (unsigned*)(ws + o_pk1); W.pvals = (unsigned*)(ws + o_pv1);

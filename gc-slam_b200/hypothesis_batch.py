@@ -235,6 +235,8 @@ class CPrimBatchArgs(C.Structure):
 L.register_prototypes({"gcs_lidar_evidence_primitives_batched": (_int, [_vp, _vp, C.POINTER(CPrimBatchArgs)])})
 
 _DT = {F64: 8, torch.int32: 4, torch.int64: 8, torch.uint8: 1}
+import os as _os
+_NO_SIDE_ROUTE = bool(_os.environ.get("GCS_NO_SIDE_ROUTE"))   # developer switch: keep the map update on the caller's stream
 
 
 class _Arena:
@@ -481,8 +483,16 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
         active0 = PR.ma_hex_stencil_tile_ids(poses_h[0, :3], acfg.h_tile, acfg.r_stencil_tiles_xy, acfg.r_stencil_tiles_z)
         g0 = run([0], active0)
         groups.append(g0)
+        # the in-place inflation and the map update go to the context's side stream (behind hypothesis 0's evidence): they
+        # overlap the deskew + surfel extraction of the remaining hypotheses, whose view is prepared on the same side stream
+        # behind the update
+        route = H > 1 and not _NO_SIDE_ROUTE
         gens["inflate"] = PR._recency_inflate_gen(atlas_map, active0, scan_seq, acfg.recency_decay_lambda, recency_min_scale, chart_id)
-        io_i, stats_i, _ = next(gens["inflate"])
+        io.ctx.side_route(route)
+        try:
+            io_i, stats_i, _ = next(gens["inflate"])
+        finally:
+            io.ctx.side_route(False)
         out_holder = []
         b0 = _batch_unit(g0.batch, 0)
         a0 = PrimitiveAssociationResult(**{f: getattr(g0.association, f)[0] for f in g0.association.__dataclass_fields__})
@@ -491,7 +501,11 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
         gens["update"] = PR._map_update_step12b_gen(atlas_map, b0, a0, active0, z_t, scan_seq, scan_end_time,
                                                     inflate_stats=lambda: out_holder[0]._inflate_stats,
                                                     **(map_update_kwargs or {}))
-        io_u, stats_u, _ = next(gens["update"])
+        io.ctx.side_route(route)
+        try:
+            io_u, stats_u, _ = next(gens["update"])
+        finally:
+            io.ctx.side_route(False)
         rest = rest[1:]
     by_stencil: Dict[tuple, List[int]] = {}
     if rest:
@@ -506,6 +520,8 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
     # kernels; `defer` leaves the wait to the caller (out.wait()), so that the next scan can be enqueued meanwhile
     out._pending = []
     out._owned = owned
+    if update_map:
+        io.ctx.side_join(io.stream())      # the update's outputs (and the map) are read from the caller's stream from here on
     for g in groups:
         b1 = _PinnedRing.get(g._scal_d.numel())
         owned.append(b1)

@@ -52,6 +52,14 @@ const char* gcs_last_error(gcs_ctx* ctx); /* ctx may be NULL: returns the last c
 int gcs_reserve_workspace(gcs_ctx* ctx, uint64_t bytes);
 int gcs_workspace_freeze(gcs_ctx* ctx, int frozen);
 uint64_t gcs_workspace_bytes(gcs_ctx* ctx);
+
+/* Side stream of the context.  gcs_lidar_evidence_primitives_batched prepares the map view on it while the scan's surfels
+ * are extracted.  While gcs_side_route is on, gcs_map_recency_inflate and gcs_map_update run there too (after everything
+ * enqueued on the caller's stream so far), so that hypothesis 0's map update (pipeline.py:1233-1447) overlaps the
+ * scan-side work of the remaining hypotheses; gcs_side_join makes `stream` wait for everything enqueued on the side
+ * stream (call it before reading what those calls wrote).  */
+int gcs_side_route(gcs_ctx* ctx, int on);
+int gcs_side_join(gcs_ctx* ctx, void* stream);
 int gcs_device_sm_count(gcs_ctx* ctx);
 uint64_t gcs_kernel_launches(gcs_ctx* ctx); /* number of kernels this ctx has launched so far              */
 /* Measurement hook: when enabled, the dominant kernels of each path are bracketed by CUDA events on the launching
