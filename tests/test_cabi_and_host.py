@@ -7,6 +7,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -130,3 +131,48 @@ def test_cpulist_parser_and_numa_binding_is_safe_without_gpu():
     before = os.sched_getaffinity(0)
     assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), list)
     os.sched_setaffinity(0, before)
+
+
+def test_stencil_cells_batch_equals_scalar_and_oracle():
+    """Vectorised cell computation of many hypothesis poses == the scalar function (also on and next to tile boundaries)
+    == the oracle's stencil (fl/common/tiling.py:171-186)."""
+    from gc_slam_b200 import primitives as PR
+    from oracle import prim_path as op
+    rng = np.random.default_rng(3)
+    P = rng.uniform(-60.0, 60.0, (4000, 3))
+    P[:40, 0] = 2.0 * np.arange(40) - 40.0          # on x boundaries
+    P[40:80, 2] = 2.0 * np.arange(40) - 40.0        # on z boundaries
+    P[80:120, :2] = 0.0
+    P[120:160, 1] = (2.0 * np.arange(40) - 40.0 - 0.5 * P[120:160, 0]) / (0.5 * np.sqrt(3.0))   # on the second hex axis
+    P[160:200] = np.nextafter(P[:40], np.inf)       # one ulp beside a boundary
+    cells = PR.ma_hex_cells_3d_from_xyz_batch(P, 2.0)
+    assert cells == [PR.ma_hex_cell_3d_from_xyz(p, 2.0) for p in P]
+    for p, c in zip(P[:300], cells[:300]):
+        assert list(PR.stencil_of_cell(c, 1, 0)) == PR.ma_hex_stencil_tile_ids(p, 2.0, 1, 0) == op.stencil_tile_ids(p)
+
+
+def test_batch_args_pointer_slots_cover_every_arena_pointer():
+    """The vectorised pointer store of the hypothesis batch writes exactly what field-by-field assignment would."""
+    import torch
+    from gc_slam_b200 import hypothesis_batch as HB
+    A = HB._Arena("cpu")
+    names = (["dk_cert", "n_valid", "ot_cert", "rec", "view_n_valid", "inflate_stats", "dk_pts", "dk_w"] +
+             ["b_" + f for f, _, _ in HB._BATCH_FIELDS] + ["v_" + f for f, _, _ in HB._VIEW_FIELDS] +
+             ["a_" + f for f, _, _ in HB._ASSOC_FIELDS] + ["L22", "h22"])
+    for i, nm in enumerate(names):
+        A.add(nm, (3 + i,), torch.float64)
+    a = HB.CPrimBatchArgs()
+    words, offs = HB._arena_pointer_slots(("test-layout",), A.spec)
+    base = 0x7F0000001000
+    np.frombuffer(a, dtype=np.uint64)[words] = offs + np.uint64(base)
+    want = lambda name: base + A.spec[name][0]
+    assert (a.dk_pts, a.dk_w, a.dk_cert, a.n_lidar_valid) == (want("dk_pts"), want("dk_w"), want("dk_cert"), want("n_valid"))
+    assert (a.view_n_valid, a.inflate_stats, a.ot_cert) == (want("view_n_valid"), want("inflate_stats"), want("ot_cert"))
+    assert (a.L22, a.h22, a.rec) == (want("L22"), want("h22"), want("rec"))
+    for f, _, _ in HB._BATCH_FIELDS:
+        assert getattr(a.batch, HB._C_BATCH_NAME.get(f, f)) == want("b_" + f), f
+    for f, _, _ in HB._VIEW_FIELDS:
+        assert getattr(a.view, HB._C_VIEW_NAME.get(f, f)) == want("v_" + f), f
+    for f, _, _ in HB._ASSOC_FIELDS:
+        assert getattr(a.assoc, f) == want("a_" + f), f
+    assert len(words) == len(names) and a.base.Lambdas is None and a.atlas.__bool__() is False
