@@ -378,15 +378,30 @@ __global__ void __launch_bounds__(1024) surfel_select_kernel(CellFit F, SurfelGe
   const int c0 = tid * per, c1 = (c0 + per < G.n_cells) ? c0 + per : G.n_cells;
   int cnt = 0;
   for (int c = c0; c < c1; ++c) cnt += F.valid[c];
-  s_scan[tid] = cnt;
+  // exclusive prefix of the 1024 per-thread counts: shuffle scan per warp + scan of the 32 warp totals (a single thread
+  // walking the 1024 counts took 15 us of every scan's 38)
+  const int lane = tid & 31, warp = tid >> 5;
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) s_scan[warp] = inc;
   __syncthreads();
-  if (tid == 0) {
-    int a = 0;
-    for (int t = 0; t < 1024; ++t) { const int v = s_scan[t]; s_scan[t] = a; a += v; }
-    s_total = a;
+  if (warp == 0) {
+    const int w = s_scan[lane];
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += v;
+    }
+    s_scan[32 + lane] = winc - w;          // exclusive offset of warp `lane`
+    if (lane == 31) s_total = winc;
   }
   __syncthreads();
-  int slot = s_scan[tid];
+  int slot = inc - cnt + s_scan[32 + warp];
   for (int c = c0; c < c1; ++c) {
     if (out_count) out_count[c] = total[c] < G.max_occ ? total[c] : G.max_occ;
     if (!F.valid[c]) continue;
