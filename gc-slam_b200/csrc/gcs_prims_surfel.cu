@@ -402,36 +402,43 @@ __global__ void __launch_bounds__(1024) surfel_select_kernel(CellFit F, SurfelGe
   }
   __syncthreads();
   int slot = inc - cnt + s_scan[32 + warp];
+  // the cells that become surfels, in cell order (slot -> cell), then one thread per SURFEL: the valid cells are a third of
+  // the grid and unevenly spread over the threads' cell ranges
+  extern __shared__ int s_list[];          // n_surfel entries
   for (int c = c0; c < c1; ++c) {
     if (out_count) out_count[c] = total[c] < G.max_occ ? total[c] : G.max_occ;
     if (!F.valid[c]) continue;
-    if (slot < B.n_surfel) {
-      const int r = B.n_feat + slot;
-      Mat3 S;
-      for (int k = 0; k < 9; ++k) S.m[k] = F.Sigma[9 * c + k];
-      S(0, 0) += eps_lift; S(1, 1) += eps_lift; S(2, 2) += eps_lift;
-      Mat3 L = mat3_inv(S);  // measurement_batch_add_lidar_surfels (measurement_batch.py:299-301)
-      const double mu[3] = {F.centroid[3 * c], F.centroid[3 * c + 1], F.centroid[3 * c + 2]};
-      double th[3];
-      mat3_vec(L, mu, th);
-      for (int k = 0; k < 9; ++k) B.Lambdas[9 * r + k] = L.m[k];
-      const double kap = F.kappa[c];
-      const double nz = fmin(fmax(F.normal[3 * c + 2], -1.0), 1.0);
-      const double g = 0.25 + 0.5 * (nz + 1.0) / 2.0;
-      for (int k = 0; k < 3; ++k) {
-        B.thetas[3 * r + k] = th[k];
-        B.etas[9 * r + k] = kap * F.normal[3 * c + k];
-        B.etas[9 * r + 3 + k] = 0.0;
-        B.etas[9 * r + 6 + k] = 0.0;
-        B.colors[3 * r + k] = g;
-      }
-      B.weights[r] = F.w[c];
-      B.sources[r] = 1;
-      B.source_indices[r] = slot;
-      B.valid[r] = 1;
-      B.timestamps[r] = F.t[c];
-    }
+    if (slot < B.n_surfel) s_list[slot] = c;
     ++slot;
+  }
+  __syncthreads();
+  const int n_sel = s_total < B.n_surfel ? s_total : B.n_surfel;
+  for (int sl = tid; sl < n_sel; sl += 1024) {
+    const int c = s_list[sl];
+    const int r = B.n_feat + sl;
+    Mat3 S;
+    for (int k = 0; k < 9; ++k) S.m[k] = F.Sigma[9 * c + k];
+    S(0, 0) += eps_lift; S(1, 1) += eps_lift; S(2, 2) += eps_lift;
+    Mat3 L = mat3_inv(S);  // measurement_batch_add_lidar_surfels (measurement_batch.py:299-301)
+    const double mu[3] = {F.centroid[3 * c], F.centroid[3 * c + 1], F.centroid[3 * c + 2]};
+    double th[3];
+    mat3_vec(L, mu, th);
+    for (int k = 0; k < 9; ++k) B.Lambdas[9 * r + k] = L.m[k];
+    const double kap = F.kappa[c];
+    const double nz = fmin(fmax(F.normal[3 * c + 2], -1.0), 1.0);
+    const double g = 0.25 + 0.5 * (nz + 1.0) / 2.0;
+    for (int k = 0; k < 3; ++k) {
+      B.thetas[3 * r + k] = th[k];
+      B.etas[9 * r + k] = kap * F.normal[3 * c + k];
+      B.etas[9 * r + 3 + k] = 0.0;
+      B.etas[9 * r + 6 + k] = 0.0;
+      B.colors[3 * r + k] = g;
+    }
+    B.weights[r] = F.w[c];
+    B.sources[r] = 1;
+    B.source_indices[r] = sl;
+    B.valid[r] = 1;
+    B.timestamps[r] = F.t[c];
   }
   if (tid == 0) out_n_valid[0] = s_total < B.n_surfel ? s_total : B.n_surfel;
 }
@@ -474,6 +481,7 @@ static int check_batch(gcs_ctx* ctx, const gcs_meas_batch* b, const char* who) {
   GCS_REQUIRE(ctx, b && b->Lambdas && b->thetas && b->etas && b->weights && b->sources && b->source_indices && b->valid &&
                        b->timestamps && b->colors, "%s: measurement batch pointer is NULL", who);
   GCS_REQUIRE(ctx, b->n_feat >= 0 && b->n_surfel >= 0 && b->n_feat + b->n_surfel >= 1, "%s: bad batch budget", who);
+  GCS_REQUIRE(ctx, b->n_surfel <= 10240, "%s: n_surfel=%d exceeds the built budget of 10240 (the cell grid holds 8192)", who, b->n_surfel);
   return GCS_OK;
 }
 
@@ -587,7 +595,8 @@ static int surfels_launch(gcs_ctx* ctx, cudaStream_t st, const double* pts, cons
   surfel_fit_kernel<<<dim3(fit_blocks, Hu), 128, 0, st>>>(center, G, *cfg, F, occ_list, n_occ, mom);
   gcs_timing_end(ctx, st, GCS_TIME_SURFEL_FIT);
   GCS_LAUNCH_CHECK(ctx);
-  surfel_select_kernel<<<Hu, 1024, 0, st>>>(F, G, *batch, cfg->eps_lift, out_n_valid, total, out_count, n_keys);
+  surfel_select_kernel<<<Hu, 1024, (size_t)batch->n_surfel * sizeof(int), st>>>(F, G, *batch, cfg->eps_lift, out_n_valid, total, out_count,
+                                                                                 n_keys);
   GCS_LAUNCH_CHECK(ctx);
   return GCS_OK;
 }
