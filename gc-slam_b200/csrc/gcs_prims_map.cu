@@ -1478,7 +1478,7 @@ __global__ void upd_insert_apply_kernel(gcs_atlas A, TileList T, gcs_meas_batch 
                                         long long* __restrict__ out_ids, int* __restrict__ out_slots) {
   const int a = blockIdx.x, j = threadIdx.x, k = cfg.k_insert_tile;
   if (j >= k) return;
-  long long base_id = cfg.next_global_id;
+  long long base_id = cfg.next_global_id_dev ? (long long)*cfg.next_global_id_dev : (long long)cfg.next_global_id;
   for (int q = 0; q < a; ++q) base_id += W.n_ins[q];
   int prefix = 0;
   for (int m = 0; m <= j; ++m) prefix += W.ins_new[a * k + m];
@@ -1582,7 +1582,11 @@ __global__ void __launch_bounds__(256) upd_stats_kernel(UpdWs W, const double* _
   stats[GCS_MU_INSERT_MASS_P95] = p95;
   stats[GCS_MU_EVICTED_COUNT] = nc;
   stats[GCS_MU_EVICTED_MASS] = mc;
-  stats[GCS_MU_NEXT_GLOBAL_ID] = (double)(cfg.next_global_id + ni);
+  // the id counter: host scalar of this call, or the device-resident one (read above by upd_insert_apply_kernel, advanced here,
+  // behind it in stream order, by the single thread that reaches this point)
+  const long long id0 = cfg.next_global_id_dev ? (long long)*cfg.next_global_id_dev : (long long)cfg.next_global_id;
+  stats[GCS_MU_NEXT_GLOBAL_ID] = (double)(id0 + ni);
+  if (cfg.next_global_id_dev) *cfg.next_global_id_dev = (int64_t)(id0 + ni);
   (void)k_ins;
 }
 

@@ -163,7 +163,8 @@ class BatchedPrimitiveEvidence:
                     self._inflate_stats = fin[name][3]
             self._first_extra = fin
             self._gens = {}
-            self._cfg["atlas"]._pending_update = None
+            if self._cfg["atlas"]._pending_update is self:
+                self._cfg["atlas"]._pending_update = None
         for buf in getattr(self, "_owned", []):
             _PinnedRing.release(buf)
         self._owned = []
@@ -470,8 +471,15 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
     scfg = surfel_config if surfel_config is not None else SurfelExtractionConfig()
     acfg = association_config if association_config is not None else AssociationConfig(scan_seq=int(scan_seq))
     PR._check_assoc_config(acfg)
-    if getattr(atlas_map, "_pending_update", None) is not None:   # a deferred earlier scan still owes the map's host state
-        atlas_map._pending_update.wait()
+    # A deferred earlier scan still owes the map's host state (id counter, counts).  Its update keeps the id counter on the
+    # device, so ANOTHER deferred scan with an update can be enqueued behind it without that state (results are then
+    # waited for in order); anything else waits first.
+    pend = getattr(atlas_map, "_pending_update", None)
+    if pend is not None and not (update_map and defer and pend._pending is not None and getattr(pend, "_ids_on_device", False)):
+        pend.wait()
+        pend = None
+    elif pend is not None and pend._pending is None:
+        pend = None
     run = lambda units, tl: _run_group(io, units, list(tl), pts, t, w, n, xi_d, poses_d, scan_start_time, scan_end_time, atlas_map,
                                        scan_seq, base_batch, scfg, acfg, m_tile_view, eps_lift, eps_mass, recency_min_scale)
     groups, gens = [], {}
@@ -498,8 +506,16 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
         a0 = PrimitiveAssociationResult(**{f: getattr(g0.association, f)[0] for f in g0.association.__dataclass_fields__})
         if z_t is None:
             z_t = poses_h[0] if z_lin_poses is None else (lin_h[0] if lin_h is not None else poses_d[0])
+        ctr = getattr(atlas_map, "_next_id_dev", None)
+        if ctr is None:
+            ctr = atlas_map._next_id_dev = torch.zeros(1, dtype=torch.int64, device=io.dev)
+        if pend is None:          # the host attribute is current: put it on the device (stream-ordered, from pinned memory)
+            stage = _PinnedRing.get(8)
+            owned.append(stage)
+            stage.view(torch.int64)[0] = int(atlas_map.next_global_id)
+            ctr.copy_(stage.view(torch.int64), non_blocking=True)
         gens["update"] = PR._map_update_step12b_gen(atlas_map, b0, a0, active0, z_t, scan_seq, scan_end_time,
-                                                    inflate_stats=lambda: out_holder[0]._inflate_stats,
+                                                    inflate_stats=lambda: out_holder[0]._inflate_stats, next_id_dev=ctr,
                                                     **(map_update_kwargs or {}))
         io.ctx.side_route(route)
         try:
@@ -535,6 +551,7 @@ def lidar_evidence_primitives_batched(points, timestamps, weights, scan_start_ti
             buf.view(F64).copy_(st_d.reshape(-1), non_blocking=True)
             out._gens[name] = (gens[name], buf, tuple(st_d.shape))
         atlas_map._pending_update = out
+        out._ids_on_device = True
     out._event = torch.cuda.Event()
     out._event.record(torch.cuda.current_stream(io.dev))
     if not defer:

@@ -94,7 +94,8 @@ class CAssocResult(C.Structure):
 class CMapUpdateCfg(C.Structure):
     _fields_ = [(n, _i32) for n in ("k_insert_tile", "k_assoc", "assoc_block_size", "strict_tile_state")] + \
                [(n, _dbl) for n in ("recency_decay_lambda", "eps_lift", "eps_mass", "h_tile", "cull_weight_threshold",
-                                    "forgetting_factor")] + [("scan_seq", _i64), ("next_global_id", _i64), ("timestamp", _dbl)]
+                                    "forgetting_factor")] + [("scan_seq", _i64), ("next_global_id", _i64), ("timestamp", _dbl),
+                                                           ("next_global_id_dev", _vp)]
 
 
 OT = dict(MARGINAL_A=0, MARGINAL_B=1, MASS_TOTAL=2, SUM_A=3, SUM_M=4, SUM_NOVEL=5, P95_A=6, NONZERO_A=7, B_RECENCY_P95=8,
@@ -782,7 +783,7 @@ def _map_update_step12b_gen(atlas_map, measurement_batch, association_result, ac
                             cull_weight_threshold=constants.GC_PRIMITIVE_CULL_WEIGHT_THRESHOLD,
                             forgetting_factor=constants.GC_PRIMITIVE_FORGETTING_FACTOR,
                             assoc_block_size=constants.GC_ASSOC_BLOCK_SIZE, strict_tile_state=True, inflate_stats=None,
-                            chart_id=constants.GC_CHART_ID):
+                            chart_id=constants.GC_CHART_ID, next_id_dev=None):
     """
     Whole primitive-map update of one scan in one call (in place on the device pool): rigid pushforward of the
     measurement batch with z_t, PoE fuse into the associated slots, novelty-driven insertion into the lowest-retention
@@ -797,7 +798,11 @@ def _map_update_step12b_gen(atlas_map, measurement_batch, association_result, ac
     cfg = CMapUpdateCfg(int(k_insert_tile), int(K), int(assoc_block_size), 1 if strict_tile_state else 0,
                         float(recency_decay_lambda), float(eps_lift), float(eps_mass), float(h_tile),
                         float(cull_weight_threshold), float(forgetting_factor), int(scan_seq), int(atlas_map.next_global_id),
-                        float(timestamp))
+                        float(timestamp), L.ptr(next_id_dev) if next_id_dev is not None else None)
+    # (next_id_dev: a device int64[1] counter the kernels read and advance -- the caller may then enqueue the next scan's
+    # update before this one's statistics have been read; the host attribute catches up when they are)
+    active_set = set(int(x) for x in active_tile_ids)
+    inactive = [int(t) for t in atlas_map.tile_ids if int(t) not in active_set]   # as of this scan, not of the read-back
     new_ids = io.empty(nt, int(k_insert_tile), dtype=torch.int64)
     slots = io.empty(nt, int(k_insert_tile), dtype=torch.int32)
     stats_d = io.zeros(MU["NSTATS"])
@@ -810,13 +815,13 @@ def _map_update_step12b_gen(atlas_map, measurement_batch, association_result, ac
     if callable(inflate_stats):          # resolved late: the caller learns the inflation statistics in the same read-back
         inflate_stats = inflate_stats()
     n_ins, n_cull = int(s[MU["INSERT_COUNT"]]), int(s[MU["EVICTED_COUNT"]])
-    atlas_map.next_global_id = int(s[MU["NEXT_GLOBAL_ID"]])
+    # (with the device-resident counter several updates may be read back late: ids only grow)
+    atlas_map.next_global_id = max(int(atlas_map.next_global_id), int(s[MU["NEXT_GLOBAL_ID"]])) if next_id_dev is not None \
+        else int(s[MU["NEXT_GLOBAL_ID"]])
     atlas_map.total_count = atlas_map.total_count + n_ins - n_cull
     result = MapUpdateResult(atlas_map=atlas_map, n_fused=int(s[MU["FUSED_COUNT"]]), n_inserted=n_ins, n_culled=n_cull,
                              new_ids=new_ids, insert_slots=slots,
                              tile_counts=[int(s[MU["TILE_COUNT0"] + a]) for a in range(min(nt, 16))])
-    active_set = set(int(x) for x in active_tile_ids)
-    inactive = [int(t) for t in atlas_map.tile_ids if int(t) not in active_set]
     mu = MapUpdateCert(
         n_active_tiles=nt, tile_ids_active=[int(t) for t in active_tile_ids], n_inactive_tiles=len(inactive),
         tile_ids_inactive=inactive, tile_cache_hits=nt, tile_cache_misses=0,

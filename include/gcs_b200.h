@@ -611,6 +611,9 @@ typedef struct {
   double recency_decay_lambda, eps_lift, eps_mass, h_tile, cull_weight_threshold, forgetting_factor;
   int64_t scan_seq, next_global_id;
   double timestamp;
+  int64_t* next_global_id_dev; /* optional (NULL: next_global_id above is used): device int64[1] holding the next id; read by
+                                  this update and advanced by the ids it assigns, so that a caller can enqueue the next scan's
+                                  update before it has read this one's statistics back                                   */
 } gcs_map_update_cfg;
 enum { GCS_MU_FUSED_COUNT = 0, GCS_MU_FUSED_MASS, GCS_MU_INSERT_COUNT, GCS_MU_INSERT_MASS, GCS_MU_INSERT_MASS_P95,
        GCS_MU_EVICTED_COUNT, GCS_MU_EVICTED_MASS, GCS_MU_NEXT_GLOBAL_ID, GCS_MU_TILE_COUNT0 /* 16 tile counts */ = 8,

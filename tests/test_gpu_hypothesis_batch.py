@@ -242,3 +242,43 @@ def _grow_inside_a_call(ctx, L):
     nv = z(U, dt=torch.int32)
     return ctx.lib.gcs_extract_lidar_surfels_batched(ctx.handle, L.stream_ptr(torch.device("cuda")), L.ptr(pts), L.ptr(t), L.ptr(w), n, U, 1,
                                                      C.byref(cc), C.byref(cb), L.ptr(nv))
+
+
+def test_deferred_scans_with_map_update_equal_the_synchronous_loop(mods):
+    """Scans with the map update enqueued back to back (the wait for scan k-1 issued after scan k: the id counter lives on
+    the device) leave the map, the ids and the evidence of the loop that waits after every scan."""
+    P, ops, HB = mods
+    from gc_slam_b200 import synth
+    n, H = 20000, 3
+    atlas_np = synth.synthetic_atlas(120000, 50000, 12, scan_seq=20)
+    t0, t1 = synth.EPOCH_T0, synth.EPOCH_T0 + 0.1
+    scans = []
+    for k in range(5):
+        pts, t, w, xis, poses, cam = _inputs(n, H, 70 + k)
+        scans.append((pts, t, w, xis, poses, cam))
+
+    def run(deferred):
+        amap = P.AtlasMap.from_numpy(atlas_np, n_tiles_cap=len(atlas_np["tiles"]) + 24)
+        outs, prev = [], None
+        for k, (pts, t, w, xis, poses, cam) in enumerate(scans):
+            cur = HB.lidar_evidence_primitives_batched(pts, t, w, t0, t1, xis, amap, poses, 21 + k, base_batch=_base(P, cam),
+                                                       update_map=True, defer=deferred)
+            if deferred and prev is not None:
+                prev.wait()
+            prev = cur
+            outs.append(cur)
+        prev.wait()
+        return amap, outs
+
+    m_sync, o_sync = run(False)
+    m_def, o_def = run(True)
+    assert m_def.next_global_id == m_sync.next_global_id and m_def.total_count == m_sync.total_count
+    assert m_def.next_global_id > int(atlas_np["next_global_id"])
+    for name in m_sync.fields:
+        assert torch.equal(m_def.fields[name], m_sync.fields[name]), name
+    for a, b in zip(o_def, o_sync):
+        assert torch.equal(a.L_pose, b.L_pose) and torch.equal(a.h_pose, b.h_pose)
+        ra, rb = a.map_update[0], b.map_update[0]
+        assert torch.equal(ra.new_ids, rb.new_ids) and (ra.n_fused, ra.n_inserted, ra.n_culled) == (rb.n_fused, rb.n_inserted, rb.n_culled)
+        ca, cb = a.map_update[1].map_update, b.map_update[1].map_update
+        assert ca.tile_ids_inactive == cb.tile_ids_inactive and ca.insert_mass_total == cb.insert_mass_total
